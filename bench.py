@@ -1,0 +1,274 @@
+#!/usr/bin/env python
+"""Benchmark of the Law-Dieckmann hot path on B200: grid-points x Euler-steps per second (FP64).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload NAME]
+
+Prints ONE JSON line (rank 0).  A "step" is one explicit-Euler step of the whole moment grid: the integrals
+(m*C)(xi) at every node and WC, the closure, and the fused update of N and C (Solver.cpp:431-513, 577-580).
+
+Workloads:
+  g128      exp 14.4a parameters on a forced 128 x 128 moment grid = 16 384 xi-points (BASELINE config 3);
+            the N=1 headline.  With N > 1 ranks every rank advances its own replica of it (independent
+            parameter sets, one per GPU, no data-path collective) -> weak scaling.
+  exp14_4a  the reference's own default grid (G=41), latency-bound; reported for completeness.
+
+`--impl reference` times the reference's own CPU code on the same workload (oracle/_ref, compiled from the
+reference's sources; see oracle/Makefile) -- the only place besides cpu_baseline where bench.py runs oracle/.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "grid-pts*steps/sec (FP64)"
+UNIT = "grid-pts*steps/s"
+DT = 0.1
+
+WORKLOADS = {
+    # name: (sigma_w, sigma_m, b, d, d', forced_G)
+    "g128": (0.15, 0.15, 0.4, 0.2, 0.001, 128),
+    "g64": (0.1, 0.1, 0.4, 0.2, 0.001, 64),
+    "exp14_4a": (0.15, 0.15, 0.4, 0.2, 0.001, 0),
+}
+
+
+def seeded_state(grid, sigma, n0=200.0):
+    """SURVEY 8d config 3 seed: C = N^2 (1 + 0.5 exp(-|xi|^2 / 2 sigma^2)), fixed, no RNG."""
+    r2 = grid[:, None] ** 2 + grid[None, :] ** 2
+    st = np.empty(1 + grid.size ** 2)
+    st[0] = n0
+    st[1:] = (n0 * n0 * (1 + 0.5 * np.exp(-r2 / (2 * sigma * sigma)))).ravel()
+    return st
+
+
+def algorithmic_flop_per_step(props):
+    """F_step = 11 (P S_nz + nzW) + 20 P   (SURVEY.md 8d): 11 FLOP per non-zero-weight sample."""
+    def nz(table, extent):
+        idx = [abs(i + 1) for i in range(1 - extent, extent - 1, 2)]
+        return int(np.count_nonzero(table[np.ix_(idx, idx)]))
+    P = props.G * props.G
+    s_nz, nz_w = nz(props.M, props.MaxNumForM), nz(props.W, props.MaxNumForW)
+    return 11.0 * (P * s_nz + nz_w) + 20.0 * P, s_nz
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
+    QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.QUERY}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *exc):
+        if self.proc:
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except (ValueError, IndexError):
+                continue
+            for name, flag in zip(names, r[3:7]):
+                if flag.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def reference_arm(args, rank, world):
+    """The reference's own CPU implementation of the same step on the host cores (single-threaded: the
+    reference has no parallel construct on this route, Solver.cpp:885-906)."""
+    if rank != 0:
+        return
+    from refharness import Reference
+    sw, sm, b, d, dd, G = WORKLOADS[args.workload]
+    big = G == 0 or G > 48
+    ref = Reference(byref=big)
+    if not ref.available:
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built (needs /root/reference at build time)"}))
+        return
+    p = ref.from_numbers(sw, sm, b, d, dd, G)
+    grid, _ = p.grids()
+    state = seeded_state(grid, sm)
+    steps = max(1, min(args.steps, 2 if p.P >= 4096 else args.steps))
+    for _ in range(min(args.warmup, 0 if p.P >= 4096 else 1)):
+        p.rhs(state)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        deriv = p.rhs(state)                                   # Equation::operator() -- >99.9 % of a step
+        state = np.maximum(state + deriv * DT, 0.0)            # EulerSolver::Solve's update and clamp
+    sec = time.perf_counter() - t0
+    value = p.P * steps / sec
+    kind = ("reference source with its five by-value matrix parameters turned into references (oracle/Makefile; "
+            "bit-identical results, the shipped build needs ~1 h per step at this size)") if big else "unmodified reference build"
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sec / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": args.workload, "G": p.G, "xi_points": p.P, "K": p.K, "dt": DT},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
+                             "sample": f"{steps} full Euler step(s) of the workload; {kind}"},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line))
+
+
+def cpu_baseline(workload, budget_s=25.0):
+    from refharness import Reference
+    sw, sm, b, d, dd, G = WORKLOADS[workload]
+    ref = Reference(byref=True)
+    if not ref.available:
+        return {"value": None, "unit": UNIT, "cores": 1, "kind": "reference", "sample": "oracle/_ref not built"}
+    p = ref.from_numbers(sw, sm, b, d, dd, G)
+    grid, _ = p.grids()
+    state = seeded_state(grid, sm)
+    n, t0 = 0, time.perf_counter()
+    while True:
+        deriv = p.rhs(state)
+        state = np.maximum(state + deriv * DT, 0.0)
+        n += 1
+        sec = time.perf_counter() - t0
+        if sec * (n + 1) / n > budget_s or n >= 50:
+            break
+    return {"value": p.P * n / sec, "unit": UNIT, "cores": 1, "kind": "reference",
+            "sample": f"{n} Euler step(s) in {sec:.1f} s, single thread (the reference is serial on this route); "
+                      "reference source built by-reference (bit-identical to the shipped build, which is ~30x slower)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="g128", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from __graft_entry__ import load_package
+    ldm = load_package()
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    sw, sm, b, d, dd, G = WORKLOADS[args.workload]
+    props = ldm.Properties.Generate(1, sw, sm, b, d, dd, G)
+    eq = ldm.Equation(props, device=local_rank)
+    P = props.G * props.G
+    state0 = seeded_state(props.MomentsGrid, sm)
+    flop_step, s_nz = algorithmic_flop_per_step(props)
+    fp64_peak = ldm.measure_fp64_peak(local_rank)
+
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB of L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident stepping: inputs already in HBM, L2 flushed before every timed step ----
+    eq.upload(state0)
+    eq.advance(args.warmup, DT)
+    eq.synchronize()
+    launches0 = eq.launches
+    barrier()
+    step_ms = []
+    with ClockSampler(local_rank) as clocks:
+        for _ in range(args.steps):
+            flush.fill_(1)
+            torch.cuda.synchronize()
+            eq.advance(1, DT)                   # CUDA events bracket the launches on the stream they run on
+            step_ms.append(eq.last_elapsed_ms())
+    barrier()
+    launches = eq.launches - launches0
+    total_ms = float(np.sum(step_ms))
+    if world > 1:
+        t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        total_ms = float(t.item())
+    value = world * P * args.steps / (total_ms * 1e-3)
+    final = eq.download()
+    assert np.all(np.isfinite(final)) and final[0] > 0
+
+    # ---- end to end through the reference-facing call: EulerSolver::Solve with host buffers ----
+    init_pinned = torch.from_numpy(state0).pin_memory().numpy()
+    solver = ldm.EulerSolver()
+    t_max = (args.steps + 0.5) * DT             # exactly args.steps Euler steps
+    solver.Solve(eq, ldm.SquaredN, (args.warmup + 0.5) * DT, DT, init_pinned, record=ldm.RECORD_OBSERVABLES)
+    barrier()
+    t0 = time.perf_counter()
+    res = solver.Solve(eq, ldm.SquaredN, t_max, DT, init_pinned, record=ldm.RECORD_OBSERVABLES)
+    e2e_s = time.perf_counter() - t0
+    assert len(res.Times) == args.steps + 1
+    if world > 1:
+        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        e2e_s = float(t.item())
+    e2e_value = world * P * args.steps / e2e_s
+
+    if rank == 0:
+        ms_per_step = total_ms / args.steps
+        achieved = flop_step / (ms_per_step * 1e-3) / 1e12
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": args.workload, "G": props.G, "xi_points": P, "K": props.K, "mM": props.MaxNumForM,
+                       "mW": props.MaxNumForW, "S_nz": s_nz, "dt": DT, "parallelism": f"replicas x{world}" if world > 1 else "single",
+                       "l2": "flushed before every timed step (256 MiB fill)", "seed": "C = N^2 (1 + 0.5 exp(-r^2/2 sigma^2)), N = 200"},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8.0 * (1 + P) / args.steps,
+                    "d2h_bytes_per_step": 16.0, "call": "EulerSolver::Solve twin (ldm_solve, record = observables), pinned host buffers, wall clock"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+                         "traffic": None, "algorithmic_flop_per_step": flop_step,
+                         "peak_source": "measured live: DFMA chain micro-benchmark (MEASURED_PEAKS.json has no FP64 figure)",
+                         "hbm_GBps_algorithmic": 16.0 * P / (ms_per_step * 1e-3) / 1e9},
+            "clocks": clocks.summary(),
+        }
+        if not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline(args.workload)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

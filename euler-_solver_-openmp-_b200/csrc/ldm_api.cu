@@ -1,0 +1,502 @@
+// extern "C" ABI of libldm_b200.so (include/ldm.h): handles, host<->device plumbing, the stepping loop.
+// S:n = "/root/reference/Euler Solver ver.5.3/Solver.cpp" line n.
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/ldm.h"
+#include "ldm_device.h"
+#include "ldm_model.h"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const std::string& what)
+{
+    g_error = what;
+    return code;
+}
+
+struct CudaError : std::runtime_error {
+    using std::runtime_error::runtime_error;
+};
+
+#define LDM_CUDA(expr)                                                                                    \
+    do {                                                                                                  \
+        cudaError_t e_ = (expr);                                                                          \
+        if (e_ != cudaSuccess)                                                                            \
+            throw CudaError(std::string(#expr) + ": " + cudaGetErrorString(e_));                          \
+    } while (0)
+
+}  // namespace
+
+struct ldm_context {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    ldm::Tables tables;
+    ldm::DevProblem dev{};
+    std::vector<void*> allocations;
+    double* d_C[2] = {nullptr, nullptr};   // ping-pong pair density, natural layout
+    double* d_N = nullptr;                 // [2] ping-pong first moment
+    double* d_scalars = nullptr;           // [kScalars]
+    double* d_sum = nullptr;               // [P] per-node inside-sample sum
+    double* d_deriv = nullptr;             // [P] dC/dt
+    int cur = 0;
+    int algo = LDM_ALGO_DIRECT;
+    long long launches = 0;
+    float last_ms = 0.f;
+    double shard_N[2] = {0, 0};
+
+    size_t P() const { return (size_t)dev.G * dev.G; }
+
+    template <typename T>
+    T* alloc(size_t count)
+    {
+        void* p = nullptr;
+        LDM_CUDA(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
+        allocations.push_back(p);
+        return static_cast<T*>(p);
+    }
+    template <typename T>
+    T* upload(const std::vector<T>& v)
+    {
+        T* p = alloc<T>(v.size());
+        if (!v.empty()) LDM_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+        return p;
+    }
+    ~ldm_context()
+    {
+        cudaSetDevice(device);
+        for (void* p : allocations) cudaFree(p);
+        if (ev_begin) cudaEventDestroy(ev_begin);
+        if (ev_end) cudaEventDestroy(ev_end);
+        if (stream) cudaStreamDestroy(stream);
+    }
+};
+
+namespace {
+
+using ldm::DevProblem;
+
+// sum over inside samples of m * C~ for this rank's rows -> d_sum   (the m*C integral, S:277-316)
+void inside_sum(ldm_context* c, const DevProblem& P, const double* C, double* out, cudaStream_t s)
+{
+    ldm::launch_sample_sum(P, ldm::SAMPLES_INSIDE, C, out, s);
+    c->launches += 1;
+}
+
+// one right-hand side at the state (N_cur, C): scalars <- WC, dN; deriv/C_next optional
+void rhs_and_update(ldm_context* c, const DevProblem& P, const double* C, const double* N_cur, double* N_next, double dt,
+                    double* deriv_out, double* C_next, cudaStream_t s)
+{
+    inside_sum(c, P, C, c->d_sum, s);
+    ldm::launch_wc(P, C, N_cur, N_next, c->d_scalars, dt, s);
+    ldm::launch_pointwise(P, C, c->d_sum, N_cur, c->d_scalars, dt, deriv_out, C_next, s);
+    c->launches += 2;
+}
+
+void step_resident(ldm_context* c, double dt, double* deriv_out)
+{
+    const int cur = c->cur, nxt = cur ^ 1;
+    rhs_and_update(c, c->dev, c->d_C[cur], c->d_N + cur, c->d_N + nxt, dt, deriv_out, c->d_C[nxt], c->stream);
+    c->cur = nxt;
+}
+
+void upload_state(ldm_context* c, const double* state)
+{
+    c->cur = 0;
+    LDM_CUDA(cudaMemcpyAsync(c->d_N, state, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+    LDM_CUDA(cudaMemcpyAsync(c->d_C[0], state + 1, c->P() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+}
+
+template <typename F>
+int guarded(F&& body)
+{
+    try {
+        body();
+        return LDM_OK;
+    } catch (const CudaError& e) {
+        return fail(LDM_ERR_CUDA, e.what());
+    } catch (const std::invalid_argument& e) {
+        return fail(LDM_ERR_ARGUMENT, e.what());
+    } catch (const std::exception& e) {
+        return fail(LDM_ERR_ARGUMENT, e.what());
+    }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ldm_last_error(void) { return g_error.c_str(); }
+const char* ldm_version(void) { return "ldm_b200 0.1 (sm_100a)"; }
+
+int ldm_problem_generate(double sigma_w, double sigma_m, double b, double d, double d_prime, int forced_G, ldm_problem** out)
+{
+    if (!out) return fail(LDM_ERR_ARGUMENT, "out is NULL");
+    return guarded([&] {
+        auto owned = std::make_unique<ldm::OwnedProblem>();
+        ldm::generate_problem(sigma_w, sigma_m, b, d, d_prime, forced_G, *owned);
+        *out = &owned.release()->view;      // view is the first member: the pointer doubles as the owner
+    });
+}
+
+void ldm_problem_free(ldm_problem* p)
+{
+    if (p) delete reinterpret_cast<ldm::OwnedProblem*>(p);
+}
+
+int ldm_problem_check_kernels(const ldm_problem* p, double* integral_w, double* integral_m)
+{
+    if (!p || !integral_w || !integral_m) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    ldm::check_kernels(*p, *integral_w, *integral_m);
+    return LDM_OK;
+}
+
+int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
+{
+    if (!p || !out) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    if (p->species != 1) return fail(LDM_ERR_UNSUPPORTED, "only one species is supported (the reference ships multi-species inputs as UNSUPPORTED)");
+    if (p->G < 2 || p->K < 3 || !p->moments_grid || !p->kernels_grid || !p->M || !p->W)
+        return fail(LDM_ERR_ARGUMENT, "incomplete problem description");
+    return guarded([&] {
+        int count = 0;
+        cudaError_t e = cudaGetDeviceCount(&count);
+        if (e != cudaSuccess || count == 0)
+            throw CudaError("no CUDA device available -- libldm_b200 has no CPU fallback");
+        if (device < 0 || device >= count) throw std::invalid_argument("device index out of range");
+        auto c = std::make_unique<ldm_context>();
+        c->device = device;
+        LDM_CUDA(cudaSetDevice(device));
+        LDM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        LDM_CUDA(cudaEventCreate(&c->ev_begin));
+        LDM_CUDA(cudaEventCreate(&c->ev_end));
+
+        ldm::build_tables(*p, c->tables);
+        const ldm::Tables& t = c->tables;
+        DevProblem& d = c->dev;
+        d.G = t.G; d.n_off = t.offM.n_off; d.A = t.offM.A;
+        d.world = 1; d.rank = 0; d.rows_per_rank = t.G;
+        d.hh = t.hh; d.b = t.b; d.d = t.d; d.dd = t.dd; d.s_max = t.s_max; d.wc_outside = t.wc_outside;
+        d.s = c->upload(t.axisM.s);
+        d.limit = c->upload(t.axisM.limit);
+        d.weight = c->upload(t.axisM.weight);
+        d.upper = c->upload(t.axisM.upper);
+        d.alpha = c->upload(t.offM.alpha);
+        d.quadrant = c->upload(t.offM.quadrant);
+        d.m_nodes = c->upload(t.m_nodes);
+        d.w_nodes = c->upload(t.w_nodes);
+        d.wc_operator = c->upload(t.wc_operator);
+        const size_t P = c->P();
+        double* out_weight = c->alloc<double>(P);
+        d.out_weight = out_weight;
+        c->d_C[0] = c->alloc<double>(P);
+        c->d_C[1] = c->alloc<double>(P);
+        c->d_N = c->alloc<double>(2);
+        c->d_scalars = c->alloc<double>(ldm::kScalars);
+        c->d_sum = c->alloc<double>(P);
+        c->d_deriv = c->alloc<double>(P);
+        LDM_CUDA(cudaMemsetAsync(c->d_C[0], 0, P * sizeof(double), c->stream));
+        LDM_CUDA(cudaMemsetAsync(c->d_C[1], 0, P * sizeof(double), c->stream));
+        LDM_CUDA(cudaMemsetAsync(c->d_N, 0, 2 * sizeof(double), c->stream));
+        // time-invariant: the m-weight of every node's samples that fall beyond the cutoff (they see N^2, S:369-373)
+        ldm::launch_sample_sum(d, ldm::SAMPLES_OUT_WEIGHT, c->d_C[0], out_weight, c->stream);
+        c->launches += 1;
+        LDM_CUDA(cudaGetLastError());
+        LDM_CUDA(cudaStreamSynchronize(c->stream));
+        *out = c.release();
+    });
+}
+
+void ldm_destroy(ldm_handle h) { delete h; }
+
+int ldm_set_algorithm(ldm_handle h, int algo)
+{
+    if (!h) return fail(LDM_ERR_ARGUMENT, "NULL handle");
+    if (algo == LDM_ALGO_AUTO) algo = LDM_ALGO_DIRECT;
+    if (algo != LDM_ALGO_DIRECT) return fail(LDM_ERR_UNSUPPORTED, "algorithm not available in this build");
+    h->algo = algo;
+    return LDM_OK;
+}
+
+int ldm_rhs(ldm_handle h, const double* state, double* deriv)
+{
+    if (!h || !state || !deriv) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    return guarded([&] {
+        LDM_CUDA(cudaSetDevice(h->device));
+        upload_state(h, state);
+        rhs_and_update(h, h->dev, h->d_C[0], h->d_N, nullptr, 0.0, h->d_deriv, nullptr, h->stream);
+        LDM_CUDA(cudaGetLastError());
+        LDM_CUDA(cudaMemcpyAsync(deriv, h->d_scalars + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        LDM_CUDA(cudaMemcpyAsync(deriv + 1, h->d_deriv, h->P() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        LDM_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int ldm_integrals(ldm_handle h, const double* state, double* WC, double* MC)
+{
+    if (!h || !state || !WC) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    return guarded([&] {
+        LDM_CUDA(cudaSetDevice(h->device));
+        upload_state(h, state);
+        inside_sum(h, h->dev, h->d_C[0], h->d_sum, h->stream);
+        ldm::launch_wc(h->dev, h->d_C[0], h->d_N, nullptr, h->d_scalars, 0.0, h->stream);
+        h->launches += 1;
+        LDM_CUDA(cudaGetLastError());
+        LDM_CUDA(cudaMemcpyAsync(WC, h->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        std::vector<double> sum;
+        if (MC) {
+            sum.resize(h->P());
+            LDM_CUDA(cudaMemcpyAsync(sum.data(), h->d_sum, h->P() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        }
+        LDM_CUDA(cudaStreamSynchronize(h->stream));
+        if (MC) {   // the same closing expression as the pointwise kernel
+            std::vector<double> ow(h->P());
+            LDM_CUDA(cudaMemcpy(ow.data(), h->dev.out_weight, h->P() * sizeof(double), cudaMemcpyDeviceToHost));
+            const double N = state[0];
+            for (size_t q = 0; q < h->P(); q++) MC[q] = (sum[q] + (N * N) * ow[q]) * h->dev.hh;
+        }
+    });
+}
+
+int ldm_kernels_at_nodes(ldm_handle h, double* m_at_nodes, double* w_at_nodes)
+{
+    if (!h || !m_at_nodes || !w_at_nodes) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    std::memcpy(m_at_nodes, h->tables.m_nodes.data(), h->P() * sizeof(double));
+    std::memcpy(w_at_nodes, h->tables.w_nodes.data(), h->P() * sizeof(double));
+    return LDM_OK;
+}
+
+int ldm_count_points(double t_max, double dt)
+{
+    if (!(dt > 0)) return 1;
+    int n = 1;
+    double time = 0;
+    time += dt;                                   // S:574
+    while (time < t_max) { n++; time += dt; }     // S:575, S:588
+    return n;
+}
+
+int ldm_solve(ldm_handle h, const double* init, double dt, double t_max, int record, double* times, double* values,
+              double* derivs, int* n_points)
+{
+    if (!h || !init) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    if (record < LDM_RECORD_LAST || record > LDM_RECORD_ALL) return fail(LDM_ERR_ARGUMENT, "unknown record mode");
+    if (!(dt > 0)) return fail(LDM_ERR_ARGUMENT, "step must be positive");
+    if (record != LDM_RECORD_LAST && !values) return fail(LDM_ERR_ARGUMENT, "values is NULL");
+    if (record == LDM_RECORD_ALL && !derivs) return fail(LDM_ERR_ARGUMENT, "derivs is NULL");
+    return guarded([&] {
+        LDM_CUDA(cudaSetDevice(h->device));
+        const int n = ldm_count_points(t_max, dt);
+        const size_t P = h->P(), width = 1 + P;
+        if (n_points) *n_points = n;
+        if (times) {
+            double time = 0;
+            for (int k = 0; k < n; k++) { times[k] = time; time += dt; }   // the accumulated clock of S:565-588
+        }
+        double* d_hist = nullptr;        // device-side history, copied out once at the end
+        double* d_dhist = nullptr;
+        std::vector<void*> scratch;
+        auto scratch_alloc = [&](size_t count) {
+            void* p = nullptr;
+            LDM_CUDA(cudaMalloc(&p, count * sizeof(double)));
+            scratch.push_back(p);
+            return static_cast<double*>(p);
+        };
+        try {
+            if (record == LDM_RECORD_OBSERVABLES) d_hist = scratch_alloc((size_t)n * 2);
+            if (record >= LDM_RECORD_VALUES) d_hist = scratch_alloc((size_t)n * width);
+            if (record == LDM_RECORD_ALL) d_dhist = scratch_alloc((size_t)n * width);
+            upload_state(h, init);
+            LDM_CUDA(cudaEventRecord(h->ev_begin, h->stream));
+            for (int k = 0; k < n; k++) {
+                const double* Ncur = h->d_N + h->cur;
+                const double* Ccur = h->d_C[h->cur];
+                if (record == LDM_RECORD_OBSERVABLES) {
+                    ldm::launch_record_observables(h->dev, Ncur, Ccur, d_hist + (size_t)k * 2, h->stream);
+                    h->launches += 1;
+                } else if (record >= LDM_RECORD_VALUES) {
+                    LDM_CUDA(cudaMemcpyAsync(d_hist + (size_t)k * width, Ncur, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+                    LDM_CUDA(cudaMemcpyAsync(d_hist + (size_t)k * width + 1, Ccur, P * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+                }
+                const bool last = (k == n - 1);
+                const bool want_deriv = (record == LDM_RECORD_ALL) || (last && derivs);
+                if (last && !want_deriv) break;
+                if (last) {       // the reference evaluates the equation once more at the final point (S:582-583)
+                    rhs_and_update(h, h->dev, Ccur, Ncur, nullptr, dt, h->d_deriv, nullptr, h->stream);
+                } else {
+                    step_resident(h, dt, want_deriv ? h->d_deriv : nullptr);
+                }
+                if (record == LDM_RECORD_ALL) {
+                    LDM_CUDA(cudaMemcpyAsync(d_dhist + (size_t)k * width, h->d_scalars + 1, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+                    LDM_CUDA(cudaMemcpyAsync(d_dhist + (size_t)k * width + 1, h->d_deriv, P * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+                }
+            }
+            LDM_CUDA(cudaEventRecord(h->ev_end, h->stream));
+            LDM_CUDA(cudaGetLastError());
+            if (record == LDM_RECORD_LAST) {
+                if (values) {
+                    LDM_CUDA(cudaMemcpyAsync(values, h->d_N + h->cur, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+                    LDM_CUDA(cudaMemcpyAsync(values + 1, h->d_C[h->cur], P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+                }
+                if (derivs) {
+                    LDM_CUDA(cudaMemcpyAsync(derivs, h->d_scalars + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+                    LDM_CUDA(cudaMemcpyAsync(derivs + 1, h->d_deriv, P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+                }
+            } else if (record == LDM_RECORD_OBSERVABLES) {
+                LDM_CUDA(cudaMemcpyAsync(values, d_hist, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            } else {
+                LDM_CUDA(cudaMemcpyAsync(values, d_hist, (size_t)n * width * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+                if (record == LDM_RECORD_ALL)
+                    LDM_CUDA(cudaMemcpyAsync(derivs, d_dhist, (size_t)n * width * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            }
+            LDM_CUDA(cudaStreamSynchronize(h->stream));
+            LDM_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev_begin, h->ev_end));
+        } catch (...) {
+            for (void* p : scratch) cudaFree(p);
+            throw;
+        }
+        for (void* p : scratch) cudaFree(p);
+    });
+}
+
+int ldm_state_upload(ldm_handle h, const double* state)
+{
+    if (!h || !state) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    return guarded([&] {
+        LDM_CUDA(cudaSetDevice(h->device));
+        upload_state(h, state);
+        LDM_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int ldm_state_download(ldm_handle h, double* state)
+{
+    if (!h || !state) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    return guarded([&] {
+        LDM_CUDA(cudaSetDevice(h->device));
+        LDM_CUDA(cudaMemcpyAsync(state, h->d_N + h->cur, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        LDM_CUDA(cudaMemcpyAsync(state + 1, h->d_C[h->cur], h->P() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        LDM_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int ldm_advance(ldm_handle h, int n_steps, double dt)
+{
+    if (!h || n_steps < 0) return fail(LDM_ERR_ARGUMENT, "bad argument");
+    return guarded([&] {
+        LDM_CUDA(cudaSetDevice(h->device));
+        LDM_CUDA(cudaEventRecord(h->ev_begin, h->stream));
+        for (int k = 0; k < n_steps; k++) step_resident(h, dt, nullptr);
+        LDM_CUDA(cudaEventRecord(h->ev_end, h->stream));
+        LDM_CUDA(cudaGetLastError());
+    });
+}
+
+int ldm_synchronize(ldm_handle h)
+{
+    if (!h) return fail(LDM_ERR_ARGUMENT, "NULL handle");
+    return guarded([&] {
+        LDM_CUDA(cudaSetDevice(h->device));
+        LDM_CUDA(cudaStreamSynchronize(h->stream));
+    });
+}
+
+int ldm_last_elapsed_ms(ldm_handle h, float* ms)
+{
+    if (!h || !ms) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    return guarded([&] {
+        LDM_CUDA(cudaSetDevice(h->device));
+        LDM_CUDA(cudaEventSynchronize(h->ev_end));
+        LDM_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev_begin, h->ev_end));
+        *ms = h->last_ms;
+    });
+}
+
+long long ldm_launch_count(ldm_handle h) { return h ? h->launches : 0; }
+
+int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits, double dt, double t_max,
+                    double* const* last_states)
+{
+    if (n < 0 || (n > 0 && (!handles || !inits || !last_states))) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    if (!(dt > 0)) return fail(LDM_ERR_ARGUMENT, "step must be positive");
+    return guarded([&] {
+        const int points = ldm_count_points(t_max, dt);
+        for (int i = 0; i < n; i++) {
+            if (!handles[i] || !inits[i] || !last_states[i]) throw std::invalid_argument("NULL entry in batch");
+            LDM_CUDA(cudaSetDevice(handles[i]->device));
+            upload_state(handles[i], inits[i]);
+        }
+        // every parameter set advances on its own stream: independent solves overlap on the device
+        for (int k = 0; k + 1 < points; k++)
+            for (int i = 0; i < n; i++) {
+                LDM_CUDA(cudaSetDevice(handles[i]->device));
+                step_resident(handles[i], dt, nullptr);
+            }
+        for (int i = 0; i < n; i++) {
+            ldm_context* h = handles[i];
+            LDM_CUDA(cudaSetDevice(h->device));
+            LDM_CUDA(cudaGetLastError());
+            LDM_CUDA(cudaMemcpyAsync(last_states[i], h->d_N + h->cur, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            LDM_CUDA(cudaMemcpyAsync(last_states[i] + 1, h->d_C[h->cur], h->P() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        }
+        for (int i = 0; i < n; i++) {
+            LDM_CUDA(cudaSetDevice(handles[i]->device));
+            LDM_CUDA(cudaStreamSynchronize(handles[i]->stream));
+        }
+    });
+}
+
+int ldm_shard_configure(ldm_handle h, int rank, int world)
+{
+    if (!h || world < 1 || rank < 0 || rank >= world) return fail(LDM_ERR_ARGUMENT, "bad rank/world");
+    if (world > h->dev.G) return fail(LDM_ERR_ARGUMENT, "more ranks than moment-grid rows");
+    h->dev.world = world;
+    h->dev.rank = rank;
+    h->dev.rows_per_rank = (h->dev.G + world - 1) / world;
+    return LDM_OK;
+}
+
+int ldm_shard_rows_per_rank(ldm_handle h) { return h ? h->dev.rows_per_rank : 0; }
+
+int ldm_shard_set_N(ldm_handle h, double N)
+{
+    if (!h) return fail(LDM_ERR_ARGUMENT, "NULL handle");
+    return guarded([&] {
+        LDM_CUDA(cudaSetDevice(h->device));
+        h->cur = 0;
+        LDM_CUDA(cudaMemcpy(h->d_N, &N, sizeof(double), cudaMemcpyHostToDevice));
+    });
+}
+
+int ldm_shard_get_N(ldm_handle h, double* N)
+{
+    if (!h || !N) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    return guarded([&] {
+        LDM_CUDA(cudaSetDevice(h->device));
+        LDM_CUDA(cudaDeviceSynchronize());
+        LDM_CUDA(cudaMemcpy(N, h->d_N + h->cur, sizeof(double), cudaMemcpyDeviceToHost));
+    });
+}
+
+int ldm_shard_step(ldm_handle h, const double* d_C_gathered, double* d_C_shard_out, double dt, void* cuda_stream)
+{
+    if (!h || !d_C_gathered || !d_C_shard_out) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    return guarded([&] {
+        LDM_CUDA(cudaSetDevice(h->device));
+        cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+        const int cur = h->cur, nxt = cur ^ 1;
+        rhs_and_update(h, h->dev, d_C_gathered, h->d_N + cur, h->d_N + nxt, dt, nullptr, d_C_shard_out, s);
+        h->cur = nxt;
+        LDM_CUDA(cudaGetLastError());
+    });
+}
+
+}  // extern "C"

@@ -1,0 +1,58 @@
+// Device-side view of one Law-Dieckmann problem and the kernel launchers (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace ldm {
+
+// Everything a kernel needs about one parameter set; all pointers are device pointers.
+// Index conventions: moment node x, y in [0,G); signed quadrature offset o in [0,n_off);
+// alpha in [0,A) = compact index of a kernel node in the odd-node quadrant table.
+struct DevProblem {
+    int G, n_off, A;
+    // xi-sharding: this rank computes rows x = rank, rank+world, ...; the full C is held in
+    // "gathered" layout, row x at slot (x % world) * rows_per_rank + x / world.  world == 1: natural layout.
+    int world, rank, rows_per_rank;
+    double hh;                 // KernelsGridStep^2 (Solver.cpp:314)
+    double b, d, dd;
+    double s_max;              // largest sample abscissa that is still inside the moment grid
+    double wc_outside;         // sum of w over the samples of WC that lie beyond the cutoff
+    const double* s;           // [G][n_off] sample abscissa |g_x + offset_o|              (Solver.cpp:307)
+    const double* limit;       // [G][n_off] inside  <=>  partner abscissa <= limit       (Solver.cpp:329-330)
+    const double* weight;      // [G][n_off] interpolation weight along this axis          (Solver.cpp:344)
+    const int* upper;          // [G][n_off] upper node of the interval                    (Solver.cpp:335)
+    const int* alpha;          // [n_off]
+    const double* quadrant;    // [A][A] odd-node quadrant of the m table
+    const double* m_nodes;     // [G][G]  m(xi) at the moment nodes                        (Solver.cpp:469)
+    const double* w_nodes;     // [G][G]  w(xi)                                            (Solver.cpp:490)
+    const double* out_weight;  // [G][G]  sum of m over this node's samples beyond the cutoff
+    const double* wc_operator; // [G][G]  WC = hh * (<wc_operator, C> + N^2 wc_outside)   (Solver.cpp:265-274)
+};
+
+// Which samples sample_sum accumulates (all use the same (x,o_i) x (y,o_j) enumeration):
+enum SampleMode {
+    SAMPLES_INSIDE = 0,        // sum m * bilinear(C) over samples inside the cutoff circle  -> the direct algorithm
+    SAMPLES_RING = 1,          // ... over samples inside the grid square but outside the circle -> correction of the factored path
+    SAMPLES_OUT_WEIGHT = 2     // sum m over every sample outside the circle (time-invariant, run once at create)
+};
+
+// Scalars of one step, device resident: [0] WC, [1] dN/dt
+constexpr int kScalars = 4;
+
+__host__ __device__ inline int row_slot(const DevProblem& P, int x) { return (x % P.world) * P.rows_per_rank + x / P.world; }
+__host__ __device__ inline int local_rows(const DevProblem& P) { return (P.G - P.rank + P.world - 1) / P.world; }
+
+// C is always the full pair density in gathered layout; `out`, inside_sum, deriv_out, C_next are
+// shard-local [local_rows][G].
+void launch_record_observables(const DevProblem& P, const double* N_cur, const double* C, double* obs_row, cudaStream_t stream);
+
+void launch_sample_sum(const DevProblem& P, SampleMode mode, const double* C, double* out, cudaStream_t stream);
+
+void launch_wc(const DevProblem& P, const double* C, const double* N_cur, double* N_next, double* scalars,
+               double dt, cudaStream_t stream);
+
+// Pointwise assembly (Solver.cpp:459-508) + optional explicit-Euler update and clamp (Solver.cpp:577-580).
+// inside_sum: per node sum over inside samples of m*C~ (unscaled).  deriv_out / C_next may be NULL.
+void launch_pointwise(const DevProblem& P, const double* C, const double* inside_sum, const double* N_cur,
+                      const double* scalars, double dt, double* deriv_out, double* C_next, cudaStream_t stream);
+
+}  // namespace ldm

@@ -1,0 +1,205 @@
+// CUDA kernels of the Law-Dieckmann step for sm_100a (FP64 CUDA-core work: data-dependent 4-tap
+// gathers and a dense FP64 contraction -- no tensor-core shape here).
+//
+// S:n = "/root/reference/Euler Solver ver.5.3/Solver.cpp" line n.
+#include "ldm_device.h"
+
+namespace ldm {
+
+namespace {
+
+constexpr int kWarp = 32;
+constexpr int kRowsPerBlock = 8;          // y nodes per CTA in sample_sum (one warp each)
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+    // fixed butterfly: the same association order on every run
+    #pragma unroll
+    for (int off = kWarp / 2; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+    return v;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sample_sum: for output node (x, y), enumerate the quadrature samples (o_i, o_j) of
+// MakeIntegralWithPairDensity (S:297-316).  A warp owns one y; lanes stride over o_j; the loop over
+// o_i is warp-uniform.  The sample coordinates are separable -- s(x,o_i) and s(y,o_j) come from the
+// same per-axis table -- and the cutoff test hypot(sx,sy) > cutoff (S:329-330) is the exact
+// host-computed comparison  sy <= limit(x,o_i).
+// ------------------------------------------------------------------------------------------------
+template <int MODE>
+__global__ void __launch_bounds__(kWarp * kRowsPerBlock)
+sample_sum_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__ out)
+{
+    const int G = P.G, n_off = P.n_off, A = P.A;
+    const int x = P.rank + P.world * blockIdx.y;       // this rank's rows (all rows when world == 1)
+    const int y = blockIdx.x * kRowsPerBlock + threadIdx.y;
+    if (y >= G) return;
+    const int lane = threadIdx.x;
+
+    const double* sx_row = P.s + (size_t)x * n_off;
+    const double* lim_row = P.limit + (size_t)x * n_off;
+    const double* wx_row = P.weight + (size_t)x * n_off;
+    const int* ux_row = P.upper + (size_t)x * n_off;
+    const double* sy_row = P.s + (size_t)y * n_off;
+    const double* wy_row = P.weight + (size_t)y * n_off;
+    const int* uy_row = P.upper + (size_t)y * n_off;
+
+    // largest abscissa this y can produce: g_y + largest offset = the last entry of its row
+    const double sy_far = fmax(sy_row[0], sy_row[n_off - 1]);
+
+    double acc = 0.0;
+    for (int oi = 0; oi < n_off; oi++) {
+        const double lim = lim_row[oi];
+        const int ux = ux_row[oi];
+        if (MODE == SAMPLES_INSIDE && lim < 0.0) continue;              // nothing inside on this sample row
+        if (MODE == SAMPLES_RING && (ux == 0 || lim >= sy_far)) continue;   // no sample between circle and square edge
+        const double wx = wx_row[oi];
+        const double* q_row = P.quadrant + (size_t)P.alpha[oi] * A;
+        const double* c_lo = C + (size_t)row_slot(P, ux > 0 ? ux - 1 : 0) * G;
+        const double* c_hi = C + (size_t)row_slot(P, ux) * G;
+        for (int oj = lane; oj < n_off; oj += kWarp) {
+            const double sy = sy_row[oj];
+            const double m = q_row[P.alpha[oj]];
+            if (MODE == SAMPLES_OUT_WEIGHT) {
+                if (!(sy <= lim)) acc += m;
+                continue;
+            }
+            const int uy = uy_row[oj];
+            bool take;
+            if (MODE == SAMPLES_INSIDE) take = (sy <= lim);
+            else take = (uy != 0) && !(sy <= lim);                      // inside the square, outside the circle
+            if (take) {
+                const double wy = wy_row[oj];
+                const double c00 = c_lo[uy - 1], c01 = c_lo[uy];
+                const double c10 = c_hi[uy - 1], c11 = c_hi[uy];
+                const double lo = c00 + wx * (c10 - c00);
+                const double hi = c01 + wx * (c11 - c01);
+                acc += m * (lo + wy * (hi - lo));
+            }
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) out[(size_t)blockIdx.y * G + y] = acc;
+}
+
+// ------------------------------------------------------------------------------------------------
+// WC (S:265-274) as a dot product with the precomputed operator, and the first-moment equation
+// dN = N(b-d) - d' WC (S:446-451) with its Euler update and clamp (S:577-580).  One CTA,
+// fixed-shape tree reduction.
+// ------------------------------------------------------------------------------------------------
+constexpr int kWcThreads = 1024;
+
+__global__ void __launch_bounds__(kWcThreads)
+wc_kernel(DevProblem P, const double* __restrict__ C, const double* __restrict__ N_cur, double* __restrict__ N_next,
+          double* __restrict__ scalars, double dt)
+{
+    __shared__ double part[kWcThreads / kWarp];
+    const int n = P.G * P.G;
+    double acc = 0.0;
+    for (int q = threadIdx.x; q < n; q += kWcThreads) {
+        const int x = q / P.G, y = q - x * P.G;
+        acc += P.wc_operator[q] * C[(size_t)row_slot(P, x) * P.G + y];
+    }
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x < kWarp) {
+        double v = part[threadIdx.x];
+        v = warp_sum(v);
+        if (threadIdx.x == 0) {
+            const double N = N_cur[0];
+            const double WC = (v + (N * N) * P.wc_outside) * P.hh;                  // S:311, S:314
+            double dN = __dmul_rn(N, __dsub_rn(P.b, P.d));                          // S:446
+            dN = __dsub_rn(dN, __dadd_rn(0.0, __dmul_rn(P.dd, WC)));                // S:450-451
+            scalars[0] = WC;
+            scalars[1] = dN;
+            if (N_next) {
+                double v1 = __dadd_rn(N, __dmul_rn(dN, dt));                        // S:577
+                N_next[0] = v1 < 0.0 ? 0.0 : v1;                                    // S:578-580
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Pointwise assembly of dC (S:459-508), in the reference's operation order with no contraction, then
+// value + derivative*step and the clamp (S:577-580).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double second_moment_rhs(const DevProblem& P, double mc, double c, double N, double WC,
+                                                    double m_node, double w_node)
+{
+    double r = __dadd_rn(__dmul_rn(P.b, mc), __dmul_rn(P.b, mc));                   // S:464 (i == j: both terms)
+    r = __dadd_rn(r, __dmul_rn(__dmul_rn(__dmul_rn(2.0, P.b), N), m_node));         // S:469
+    const double death = __dmul_rn(P.d, c);
+    r = __dsub_rn(r, death);                                                        // S:480
+    r = __dsub_rn(r, death);                                                        // S:481
+    const double closure = __ddiv_rn(__dmul_rn(__dmul_rn(P.dd, WC), c), N);         // S:486
+    r = __dsub_rn(r, closure);
+    r = __dsub_rn(r, closure);                                                      // S:487
+    const double local = __dmul_rn(__dmul_rn(P.dd, c), w_node);                     // S:490
+    r = __dsub_rn(r, local);
+    r = __dsub_rn(r, local);                                                        // S:498
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+pointwise_kernel(DevProblem P, const double* __restrict__ C, const double* __restrict__ inside_sum,
+                 const double* __restrict__ N_cur, const double* __restrict__ scalars, double dt,
+                 double* __restrict__ deriv_out, double* __restrict__ C_next)
+{
+    const int n = local_rows(P) * P.G;
+    const int ql = blockIdx.x * blockDim.x + threadIdx.x;       // shard-local index
+    if (ql >= n) return;
+    const int lx = ql / P.G, y = ql - lx * P.G;
+    const int q = (P.rank + P.world * lx) * P.G + y;            // natural index of this node
+    const double N = N_cur[0];
+    const double WC = scalars[0];
+    const double c = C[(size_t)(P.rank * P.rows_per_rank + lx) * P.G + y];
+    const double mc = (inside_sum[ql] + (N * N) * P.out_weight[q]) * P.hh;          // S:311, S:314
+    const double dc = second_moment_rhs(P, mc, c, N, WC, P.m_nodes[q], P.w_nodes[q]);
+    if (deriv_out) deriv_out[ql] = dc;
+    if (C_next) {
+        const double v = __dadd_rn(c, __dmul_rn(dc, dt));                           // S:577
+        C_next[ql] = v < 0.0 ? 0.0 : v;                                             // S:578-580
+    }
+}
+
+__global__ void record_observables_kernel(DevProblem P, const double* __restrict__ N_cur, const double* __restrict__ C,
+                                          double* __restrict__ obs_row)
+{
+    obs_row[0] = N_cur[0];                                               // Values[k][0]   (S:1011)
+    obs_row[1] = C[(size_t)row_slot(P, 0) * P.G + (P.G - 1)];            // Values[k][G] = C[0][G-1]  (S:1014)
+}
+
+}  // namespace
+
+void launch_record_observables(const DevProblem& P, const double* N_cur, const double* C, double* obs_row, cudaStream_t stream)
+{
+    record_observables_kernel<<<1, 1, 0, stream>>>(P, N_cur, C, obs_row);
+}
+
+void launch_sample_sum(const DevProblem& P, SampleMode mode, const double* C, double* out, cudaStream_t stream)
+{
+    dim3 block(kWarp, kRowsPerBlock);
+    dim3 grid((P.G + kRowsPerBlock - 1) / kRowsPerBlock, local_rows(P));
+    switch (mode) {
+        case SAMPLES_INSIDE: sample_sum_kernel<SAMPLES_INSIDE><<<grid, block, 0, stream>>>(P, C, out); break;
+        case SAMPLES_RING: sample_sum_kernel<SAMPLES_RING><<<grid, block, 0, stream>>>(P, C, out); break;
+        case SAMPLES_OUT_WEIGHT: sample_sum_kernel<SAMPLES_OUT_WEIGHT><<<grid, block, 0, stream>>>(P, C, out); break;
+    }
+}
+
+void launch_wc(const DevProblem& P, const double* C, const double* N_cur, double* N_next, double* scalars, double dt,
+               cudaStream_t stream)
+{
+    wc_kernel<<<1, kWcThreads, 0, stream>>>(P, C, N_cur, N_next, scalars, dt);
+}
+
+void launch_pointwise(const DevProblem& P, const double* C, const double* inside_sum, const double* N_cur,
+                      const double* scalars, double dt, double* deriv_out, double* C_next, cudaStream_t stream)
+{
+    const int n = local_rows(P) * P.G;
+    pointwise_kernel<<<(n + 255) / 256, 256, 0, stream>>>(P, C, inside_sum, N_cur, scalars, dt, deriv_out, C_next);
+}
+
+}  // namespace ldm

@@ -1,0 +1,267 @@
+// Host-side model setup (see ldm_model.h).  Compiled with -ffp-contract=off: the grids and kernel
+// tables must equal the reference's bit for bit, because interval indices and the inside/outside
+// decision at the cutoff circle are derived from them by exact comparisons.
+//
+// S:n = "/root/reference/Euler Solver ver.5.3/Solver.cpp" line n, T:n = types.h line n.
+#include "ldm_model.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <stdexcept>
+
+namespace ldm {
+
+namespace {
+
+const double kPi = 3.1415927;     // S:23 -- the reference's own 8-digit constant, part of the normalisation
+const double kEpsilon = 1E-08;    // S:24
+
+// Vector::setLinSpaced (T:120-130): min + i*step for i < num-1, then max verbatim.
+std::vector<double> lin_spaced(int num, double lo, double hi)
+{
+    std::vector<double> v;
+    v.reserve((size_t)num);
+    const double step = (hi - lo) / ((double)num - 1);
+    for (int i = 0; i < num - 1; i++) v.push_back(lo + i * step);
+    v.push_back(hi);
+    return v;
+}
+
+// The reference's node formula (S:69), one Vector operator at a time:
+//   abs(-log(-setLinSpaced(n,0,n-1) / n + 1) * 0.01 * n)
+std::vector<double> stretched_nodes(int n)
+{
+    std::vector<double> v = lin_spaced(n, 0, n - 1);
+    for (double& e : v) e = -1 * e;          // unary minus is "x * -1" (T:175-183)
+    for (double& e : v) e = e / n;
+    for (double& e : v) e = e + 1;
+    for (double& e : v) e = std::log(e);
+    for (double& e : v) e = -1 * e;
+    for (double& e : v) e = e * 0.01;
+    for (double& e : v) e = e * n;
+    for (double& e : v) e = std::abs(e);
+    return v;
+}
+
+// Properties::GenerateKernel (S:98-145) for the Normal kernel type.
+int fill_kernel(const std::vector<double>& grid, double step, double sigma, double radius, std::vector<double>& table)
+{
+    const int K = (int)grid.size();
+    table.assign((size_t)K * K, 0.0);
+    int extent = 0;
+    for (int x = 0; x < K; x++)
+        for (int y = 0; y < K; y++) {
+            const double r = std::hypot(grid[x], grid[y]);
+            double value = 0;
+            if (r <= radius) {
+                const double norm = sigma * std::sqrt(2 * kPi) * (1 - std::exp((-radius * radius) / (2 * sigma * sigma)));
+                const double weight = std::exp((-r * r) / (2 * sigma * sigma));
+                value = weight / norm;
+                if (value != 0) extent = std::max({extent, x + 1, y + 1});
+            }
+            table[(size_t)x * K + y] = value;
+        }
+    if (K % 2 == 1 && extent % 2 == 0 && extent != 2) extent++;       // S:131
+    if (extent == 1) extent = 2;                                       // S:132
+
+    double integral = 0;                                               // S:135-138
+    for (int x = 1 - extent; x < extent - 1; x += 2)
+        for (int y = 1 - extent; y < extent - 1; y += 2)
+            integral += table[(size_t)std::abs(x + 1) * K + std::abs(y + 1)];
+    if (integral == 0) throw std::invalid_argument("kernel integral is zero (reference assert, Solver.cpp:140)");
+    integral *= step * step;
+    for (double& e : table) e = e / integral;                          // S:142
+    return extent;
+}
+
+double midpoint_integral(const double* table, int K, int extent, double step)
+{
+    double integral = 0;                                               // S:156-161
+    for (int x = 1 - extent; x < extent - 1; x += 2)
+        for (int y = 1 - extent; y < extent - 1; y += 2)
+            integral += table[(size_t)std::abs(x + 1) * K + std::abs(y + 1)];
+    integral *= step * step;                                           // pow(step, 2)
+    return integral;
+}
+
+// index of the first node i >= 1 with x <= grid[i]  (the scan of S:334-336)
+inline int upper_node(const double* grid, int n, double x)
+{
+    return (int)(std::lower_bound(grid + 1, grid + n, x) - grid);
+}
+
+OffsetSet make_offsets(const ldm_problem& p, const double* table, int extent)
+{
+    OffsetSet o;
+    const int K = p.K;
+    for (int i = 1 - extent; i < extent - 1; i += 2) {                 // S:300
+        o.offset.push_back(i >= 0 ? p.kernels_grid[i + 1] : -p.kernels_grid[-i - 1]);   // S:307
+        o.node.push_back(std::abs(i + 1));                             // S:311
+    }
+    o.n_off = (int)o.offset.size();
+    std::vector<int> nodes = o.node;
+    std::sort(nodes.begin(), nodes.end());
+    nodes.erase(std::unique(nodes.begin(), nodes.end()), nodes.end());
+    o.A = (int)nodes.size();
+    for (int n : o.node) o.alpha.push_back((int)(std::lower_bound(nodes.begin(), nodes.end(), n) - nodes.begin()));
+    o.quadrant.resize((size_t)o.A * o.A);
+    for (int a = 0; a < o.A; a++)
+        for (int c = 0; c < o.A; c++) o.quadrant[(size_t)a * o.A + c] = table[(size_t)nodes[a] * K + nodes[c]];
+    return o;
+}
+
+}  // namespace
+
+double bilinear(const double* grid, int n, const double* values, double x, double y, double max_distance,
+                bool squared_n, double asymptotic_value)
+{
+    const double distance = std::hypot(x, y);                          // S:329
+    if (distance > max_distance) {                                     // Extrapolation, S:355-373
+        if (std::abs(values[n - 1] - asymptotic_value) < kEpsilon) return asymptotic_value;
+        return squared_n ? asymptotic_value : 0.0;
+    }
+    const int i = upper_node(grid, n, x), j = upper_node(grid, n, y);
+    const double wx = (x - grid[i - 1]) / (grid[i] - grid[i - 1]);
+    const double wy = (y - grid[j - 1]) / (grid[j] - grid[j - 1]);
+    return values[(size_t)(i - 1) * n + (j - 1)] * (1 - wx) * (1 - wy) + values[(size_t)i * n + (j - 1)] * wx * (1 - wy) +
+           values[(size_t)(i - 1) * n + j] * (1 - wx) * wy + values[(size_t)i * n + j] * wx * wy;
+}
+
+void generate_problem(double sigma_w, double sigma_m, double b, double d, double d_prime, int forced_G, OwnedProblem& out)
+{
+    if (!(sigma_w > 0) || !(sigma_m > 0)) throw std::invalid_argument("sigma_w and sigma_m must be positive");
+    if (forced_G > 0 && forced_G < 4) throw std::invalid_argument("forced_G must be at least 4");
+
+    // GenerateGrids (S:63-95)
+    const double cutoff_distance = (sigma_w + sigma_m) * 5;
+    const double max_radius = std::max(sigma_w, sigma_m) * 5;
+    int nodes = forced_G > 0 ? forced_G : 5;
+    std::vector<double> grid = stretched_nodes(nodes);
+    if (forced_G <= 0)
+        while (grid.back() < cutoff_distance - 0.01) grid = stretched_nodes(++nodes);   // S:70-74
+    const double scale = cutoff_distance / grid.back();
+    for (double& e : grid) e = e * scale;
+    if (!(std::abs(grid.back() - cutoff_distance) < kEpsilon))
+        throw std::invalid_argument("moment grid does not end at the cutoff (reference assert, Solver.cpp:77)");
+
+    int K = (nodes - 1) * 2 - 1;
+    if (std::min(sigma_w, sigma_m) < 0.015) {                          // S:80-84
+        K = (K - 2) * 4 - 1;
+        K = (K - 1) * 2 - 1;
+    }
+    if (!((K % 2 == 1) && (K >= 5))) throw std::invalid_argument("kernel grid size must be odd and >= 5 (Solver.cpp:88)");
+
+    out.moments_grid = grid;
+    out.kernels_grid = lin_spaced(K, 0, max_radius);
+    const double h = out.kernels_grid[2] - out.kernels_grid[0];        // S:94
+
+    // Generate (S:205-239): radius 3 sigma for the Normal kernel
+    const int mW = fill_kernel(out.kernels_grid, h, sigma_w, sigma_w * 3, out.W);
+    const int mM = fill_kernel(out.kernels_grid, h, sigma_m, sigma_m * 3, out.M);
+
+    ldm_problem& v = out.view;
+    v.species = 1;
+    v.G = nodes; v.K = K; v.mM = mM; v.mW = mW;
+    v.h = h; v.cutoff = grid.back();
+    v.sigma_m = sigma_m; v.sigma_w = sigma_w; v.b = b; v.d = d; v.d_prime = d_prime;
+    v.moments_grid = out.moments_grid.data();
+    v.kernels_grid = out.kernels_grid.data();
+    v.M = out.M.data();
+    v.W = out.W.data();
+}
+
+void check_kernels(const ldm_problem& p, double& integral_w, double& integral_m)
+{
+    integral_w = midpoint_integral(p.W, p.K, p.mW, p.h);
+    integral_m = midpoint_integral(p.M, p.K, p.mM, p.h);
+}
+
+void build_tables(const ldm_problem& p, Tables& t)
+{
+    const int G = p.G, K = p.K;
+    const double* g = p.moments_grid;
+    t.G = G; t.K = K; t.h = p.h; t.hh = p.h * p.h; t.cutoff = p.cutoff;
+    t.b = p.b; t.d = p.d; t.dd = p.d_prime;
+
+    // ---- m-kernel quadrature on every moment node (the per-axis halves of S:307-308, S:334-345) ----
+    t.offM = make_offsets(p, p.M, p.mM);
+    const int n_off = t.offM.n_off;
+    AxisTable& ax = t.axisM;
+    const size_t cells = (size_t)G * n_off;
+    ax.s.resize(cells); ax.upper.assign(cells, 0); ax.weight.assign(cells, 0.0); ax.limit.assign(cells, -1.0);
+    for (int x = 0; x < G; x++)
+        for (int o = 0; o < n_off; o++) {
+            const double s = std::abs(g[x] + t.offM.offset[o]);
+            const size_t c = (size_t)x * n_off + o;
+            ax.s[c] = s;
+            if (s <= p.cutoff) {           // otherwise hypot(s, anything) > cutoff: always outside
+                const int i = upper_node(g, G, s);
+                ax.upper[c] = i;
+                ax.weight[c] = (s - g[i - 1]) / (g[i] - g[i - 1]);
+            }
+        }
+
+    // ---- the cutoff circle (S:329-330), decided once on the host with the reference's hypot ----
+    // Candidates for a sample's partner abscissa are exactly the values in ax.s, so the largest
+    // candidate that is still inside is an exact threshold for the device (no hypot on the GPU).
+    std::vector<double> sorted(ax.s);
+    std::sort(sorted.begin(), sorted.end());
+    sorted.erase(std::unique(sorted.begin(), sorted.end()), sorted.end());
+    auto inside = [&](double a, double c) { return !(std::hypot(a, c) > p.cutoff); };
+    double closest = 1e300;
+    long long non_monotone = 0;
+    for (size_t c = 0; c < cells; c++) {
+        const double s = ax.s[c];
+        if (!(s <= p.cutoff) || !inside(s, sorted.front())) { ax.limit[c] = -1.0; continue; }
+        size_t lo = 0, hi = sorted.size();           // invariant: sorted[lo] inside, sorted[hi] outside (or end)
+        while (hi - lo > 1) {
+            const size_t mid = lo + (hi - lo) / 2;
+            if (inside(s, sorted[mid])) lo = mid; else hi = mid;
+        }
+        ax.limit[c] = sorted[lo];
+        for (size_t q = (lo >= 3 ? lo - 3 : 0); q < std::min(sorted.size(), lo + 4); q++) {
+            if (inside(s, sorted[q]) != (q <= lo)) non_monotone++;
+            closest = std::min(closest, std::abs(std::hypot(s, sorted[q]) - p.cutoff) / p.cutoff);
+        }
+    }
+    if (non_monotone) throw std::runtime_error("hypot is not monotone across the sample set near the cutoff");
+    t.s_max = 0;
+    for (double v : sorted) if (v <= p.cutoff) t.s_max = v;
+    char note[160];
+    std::snprintf(note, sizeof note, "samples=%zu distinct=%zu closest |hypot-cutoff|/cutoff=%.3e", cells, sorted.size(), closest);
+    t.census = note;
+
+    // ---- kernels at the moment nodes (S:469-476, S:490-497): time-invariant ----
+    t.m_nodes.resize((size_t)G * G);
+    t.w_nodes.resize((size_t)G * G);
+    for (int x = 0; x < G; x++)
+        for (int y = 0; y < G; y++) {
+            t.m_nodes[(size_t)x * G + y] = bilinear(p.kernels_grid, K, p.M, g[x], g[y], p.sigma_m * 3, false, 0.0);
+            t.w_nodes[(size_t)x * G + y] = bilinear(p.kernels_grid, K, p.W, g[x], g[y], p.sigma_w * 3, false, 0.0);
+        }
+
+    // ---- WC = integral of w C at shift (0,0) (S:265-274, S:297-316) as a linear functional of C ----
+    // Inside samples spread w * (bilinear weights) onto four nodes; outside samples contribute w * N^2.
+    const OffsetSet offW = make_offsets(p, p.W, p.mW);
+    t.wc_operator.assign((size_t)G * G, 0.0);
+    t.wc_outside = 0;
+    for (int oi = 0; oi < offW.n_off; oi++) {
+        const double sx = std::abs(g[0] + offW.offset[oi]);
+        for (int oj = 0; oj < offW.n_off; oj++) {
+            const double sy = std::abs(g[0] + offW.offset[oj]);
+            const double w = offW.quadrant[(size_t)offW.alpha[oi] * offW.A + offW.alpha[oj]];
+            if (std::hypot(sx, sy) > p.cutoff) { t.wc_outside += w; continue; }
+            const int i = upper_node(g, G, sx), j = upper_node(g, G, sy);
+            const double wx = (sx - g[i - 1]) / (g[i] - g[i - 1]);
+            const double wy = (sy - g[j - 1]) / (g[j] - g[j - 1]);
+            t.wc_operator[(size_t)(i - 1) * G + (j - 1)] += w * ((1 - wx) * (1 - wy));
+            t.wc_operator[(size_t)i * G + (j - 1)] += w * (wx * (1 - wy));
+            t.wc_operator[(size_t)(i - 1) * G + j] += w * ((1 - wx) * wy);
+            t.wc_operator[(size_t)i * G + j] += w * (wx * wy);
+        }
+    }
+}
+
+}  // namespace ldm

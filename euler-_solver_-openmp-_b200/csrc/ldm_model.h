@@ -1,0 +1,71 @@
+// Host-side model setup for the B200 Law-Dieckmann step: everything that is time-invariant.
+//
+// Two layers:
+//   * generate_problem(): the reference's Properties::Generate / GenerateGrids / GenerateKernel
+//     (Solver.cpp:63-241) for one species, reproduced bit for bit on the host (same libm calls, same
+//     operation order; built with -ffp-contract=off).
+//   * build_tables(): what the CUDA kernels consume -- per-axis sample tables (abscissa, interval,
+//     weight, cutoff threshold), the odd-node quadrants of the kernel tables, the kernel values at the
+//     moment nodes, and the linear operator that turns C into the scalar integral WC.
+#pragma once
+#include <cstddef>
+#include <string>
+#include <vector>
+
+#include "../../include/ldm.h"
+
+namespace ldm {
+
+struct OwnedProblem {             // backing store of an ldm_problem handed out by ldm_problem_generate
+    ldm_problem view{};
+    std::vector<double> moments_grid, kernels_grid, M, W;
+};
+
+// Properties::Generate (Solver.cpp:186-241), one species.  Throws std::invalid_argument on the
+// reference's assert conditions (S:77, S:88, S:140).
+void generate_problem(double sigma_w, double sigma_m, double b, double d, double d_prime, int forced_G,
+                      OwnedProblem& out);
+
+// Properties::CheckKernels (Solver.cpp:147-183)
+void check_kernels(const ldm_problem& p, double& integral_w, double& integral_m);
+
+// Signed quadrature offsets of MakeIntegralWithPairDensity (Solver.cpp:300-308) for one kernel.
+struct OffsetSet {
+    int n_off = 0;                 // number of signed offsets per axis: m-1 (m odd) or 1 (m == 2)
+    int A = 0;                     // distinct kernel nodes used: (m-1)/2, or 1
+    std::vector<double> offset;    // n_off: +kappa[i+1] (i >= 0) or -kappa[-i-1] (i < 0), in the reference's loop order
+    std::vector<int> node;         // n_off: kernel node |i+1|
+    std::vector<int> alpha;        // n_off: compact index of that node in the quadrant table (0..A-1)
+    std::vector<double> quadrant;  // A*A: kernel[node_a][node_b], row-major
+};
+
+// Per moment node x and signed offset o (row-major [G][n_off]).
+struct AxisTable {
+    std::vector<double> s;         // sample abscissa |g_x + offset|  (S:307)
+    std::vector<int> upper;        // interval upper index i of S:335 (first i >= 1 with s <= g[i]); 0 when s > cutoff
+    std::vector<double> weight;    // (s - g[i-1]) / (g[i] - g[i-1])  (S:344)
+    std::vector<double> limit;     // largest partner abscissa t among ALL samples with hypot(s, t) <= cutoff
+                                   // (S:329-330 decided by the host's hypot); -1 when none
+};
+
+struct Tables {
+    int G = 0, K = 0;
+    double h = 0, hh = 0, cutoff = 0;
+    double b = 0, d = 0, dd = 0;
+    OffsetSet offM;                // the m-kernel quadrature
+    AxisTable axisM;               // ... on the moment nodes
+    double s_max = 0;              // largest abscissa value that is still <= cutoff (or cutoff)
+    std::vector<double> m_nodes;   // G*G: BilinearInterpolation(KernelsGrid, M, g_x, g_y, 3 sigma_M, Zero)  (S:469)
+    std::vector<double> w_nodes;   // G*G: same for W (S:490)
+    std::vector<double> wc_operator;   // G*G: WC = h^2 * (sum wc_operator .* C + N^2 * wc_outside)   (S:265-274)
+    double wc_outside = 0;
+    std::string census;            // diagnostics: how close any sample comes to the cutoff circle
+};
+
+void build_tables(const ldm_problem& p, Tables& t);
+
+// Equation::BilinearInterpolation (Solver.cpp:318-353) with Zero / SquaredN extrapolation (355-373)
+double bilinear(const double* grid, int n, const double* values, double x, double y, double max_distance,
+                bool squared_n, double asymptotic_value);
+
+}  // namespace ldm

@@ -1,0 +1,123 @@
+/* ldm.h -- C ABI of the B200-native Law-Dieckmann spatial-moment step (libldm_b200.so).
+ *
+ * The reference (Kintobor1370/Euler-_Solver_-OpenMP-, "Euler Solver ver.5.3") has no FFI: its seams
+ * are two by-value C++ calls inside one translation unit.  Each entry point below names the
+ * reference interface it replaces (S:n = Solver.cpp line n).  Plain pointers and sizes only; all
+ * state vectors use the reference's layout [N | C row-major G x G] (S:255-262), one species.
+ *
+ * Every function returns LDM_OK (0) or a negative code; ldm_last_error() gives the text.  There is no
+ * CPU fallback: without a CUDA device every compute entry point fails with LDM_ERR_CUDA.
+ */
+#ifndef LDM_H
+#define LDM_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LDM_OK              0
+#define LDM_ERR_ARGUMENT   -1   /* the reference would assert (S:260, S:327, ...) */
+#define LDM_ERR_CUDA       -2   /* no device / CUDA runtime failure */
+#define LDM_ERR_UNSUPPORTED -3  /* species != 1 (the reference ships those inputs as UNSUPPORTED) */
+
+/* What the reference keeps in `struct Properties` (S:40-60) for one species, flattened.
+ * Tables are K x K row-major, exactly the reference's M(0) and W(0,0). */
+typedef struct ldm_problem {
+    int species;                  /* SpeciesNumber (S:42); must be 1 */
+    int G;                        /* MomentsGrid.size() (S:57) */
+    int K;                        /* KernelsGrid.size() (S:59), odd */
+    int mM;                       /* MaxNumForM[0] (S:52) */
+    int mW;                       /* MaxNumForW[0][0] (S:51) */
+    double h;                     /* KernelsGridStep (S:60) */
+    double cutoff;                /* CutoffDistance (S:58) */
+    double sigma_m, sigma_w;      /* SigmaM[0], SigmaW[0][0] (S:54-55) */
+    double b, d, d_prime;         /* S:44-46 */
+    const double* moments_grid;   /* G */
+    const double* kernels_grid;   /* K */
+    const double* M;              /* K*K */
+    const double* W;              /* K*K */
+} ldm_problem;
+
+typedef struct ldm_context* ldm_handle;
+
+/* algorithm selector for ldm_set_algorithm */
+#define LDM_ALGO_AUTO      0
+#define LDM_ALGO_DIRECT    1   /* per-sample gather, the reference's sum re-ordered only */
+#define LDM_ALGO_FACTORED  2   /* interpolate - contract with the kernel table - interpolate, plus an exact cutoff correction */
+
+/* history selector of ldm_solve (SolverResults, S:525-537) */
+#define LDM_RECORD_LAST        0   /* last state only (what Experiment_14_6 reads, S:1050-1055) */
+#define LDM_RECORD_OBSERVABLES 1   /* N and C[0][G-1] at every point (what Experiment_14_4 reads, S:1011-1015) */
+#define LDM_RECORD_VALUES      2   /* SolverResults::Values: every state */
+#define LDM_RECORD_ALL         3   /* Values and Derivatives */
+
+/* ---- model setup: replaces Properties::Generate / GenerateGrids / GenerateKernel (S:63-241), host only ----
+ * forced_G > 0 pins the moment-grid node count (the synthetic grids of BASELINE.json); <= 0 = the
+ * reference's search (S:68-74).  The returned problem owns its arrays; free with ldm_problem_free. */
+int  ldm_problem_generate(double sigma_w, double sigma_m, double b, double d, double d_prime,
+                          int forced_G, ldm_problem** out);
+void ldm_problem_free(ldm_problem* p);
+/* Properties::CheckKernels (S:147-183): the two midpoint-rule integrals (each must be 1 +- 1e-8) */
+int  ldm_problem_check_kernels(const ldm_problem* p, double* integral_w, double* integral_m);
+
+/* ---- Equation(Properties) (S:413): upload tables, build the time-invariant index/weight tables ---- */
+int  ldm_create(const ldm_problem* p, int device, ldm_handle* out);
+void ldm_destroy(ldm_handle h);
+int  ldm_set_algorithm(ldm_handle h, int algo);
+
+/* ---- Equation::operator()(t, vals, SquaredN) (S:431-513): host state in, host derivative out ---- */
+int  ldm_rhs(ldm_handle h, const double* state, double* deriv);
+/* the two integrals on their own (S:265-295): WC scalar, MC G*G (MC may be NULL) */
+int  ldm_integrals(ldm_handle h, const double* state, double* WC, double* MC);
+/* the time-invariant kernel look-ups of S:469-476 / S:490-497 at the moment nodes (G*G each) */
+int  ldm_kernels_at_nodes(ldm_handle h, double* m_at_nodes, double* w_at_nodes);
+
+/* ---- EulerSolver::Solve (S:557-592) ----
+ * ldm_count_points reproduces `time += step; while (time < time_max)` (S:574-589).
+ * ldm_solve: init/1+G*G doubles.  times: n_points.  values/derivs by `record`:
+ *   LAST: values = 1+G*G (derivs, if non-NULL, = derivative at the last point);
+ *   OBSERVABLES: values = n_points*2; VALUES: values = n_points*(1+G*G); ALL: derivs likewise.
+ * Host buffers; the copies in and out are part of the call. */
+int  ldm_count_points(double t_max, double dt);
+int  ldm_solve(ldm_handle h, const double* init, double dt, double t_max, int record,
+               double* times, double* values, double* derivs, int* n_points);
+
+/* ---- device-resident stepping (state stays in HBM between calls) ---- */
+int  ldm_state_upload(ldm_handle h, const double* state);          /* 1+G*G doubles */
+int  ldm_state_download(ldm_handle h, double* state);
+int  ldm_advance(ldm_handle h, int n_steps, double dt);            /* n Euler steps, asynchronous */
+int  ldm_synchronize(ldm_handle h);
+/* device time of the last ldm_advance / ldm_solve stepping loop in ms (CUDA events on the stream) */
+int  ldm_last_elapsed_ms(ldm_handle h, float* ms);
+/* number of kernels launched by this handle since creation */
+long long ldm_launch_count(ldm_handle h);
+
+/* ---- the sigma-sweep loop Experiments::CalculateWithVaryingSigma (S:940-963): n independent solves,
+ * results slot-indexed (no shared push_back).  last_states[i] receives 1+G_i*G_i doubles. ---- */
+int  ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits, double dt, double t_max,
+                     double* const* last_states);
+
+/* ---- xi-sharded stepping for one large problem: this rank owns moment-grid rows
+ * x = rank, rank+world, ... and produces their updated C rows; the caller all-gathers.
+ * ldm_shard_layout: rows_per_rank = ceil(G/world); the gather buffer holds world*rows_per_rank*G doubles,
+ * rank-major (row x lives at slot (x%world)*rows_per_rank + x/world).
+ * ldm_shard_step: d_C_gathered (device) is the full C in gathered layout at the old time; on return
+ * (stream-ordered) d_C_shard_out (device, rows_per_rank*G) holds this rank's new rows and the handle's N is
+ * advanced (every rank recomputes N redundantly, so no all-reduce is needed). */
+int  ldm_shard_configure(ldm_handle h, int rank, int world);
+int  ldm_shard_rows_per_rank(ldm_handle h);
+int  ldm_shard_step(ldm_handle h, const double* d_C_gathered, double* d_C_shard_out, double dt, void* cuda_stream);
+int  ldm_shard_set_N(ldm_handle h, double N);
+int  ldm_shard_get_N(ldm_handle h, double* N);
+
+/* ---- measurement support: FP64 (DFMA) peak of `device` in TFLOP/s, measured live by a register-resident
+ * FMA chain; MEASURED_PEAKS.json has no FP64 figure, this is the roofline denominator bench.py reports. ---- */
+int  ldm_measure_fp64_peak(int device, double* tflops, double* reserved);
+
+const char* ldm_last_error(void);
+const char* ldm_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,73 @@
+/* TEST INFRASTRUCTURE ONLY -- the CPU oracle of the Law-Dieckmann hot path.
+ *
+ * A plain-C restatement of the reference's algorithm (one species), operation for operation, so
+ * that it rounds exactly like the reference's `g++ -O3 -fopenmp` x86-64 build.  Only tests/,
+ * __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load it; the
+ * product (euler_solver_openmp_b200/) never does.
+ *
+ * PARITY PINNING: the reference's own tests hold no vectors for this path,
+ * so the oracle is pinned against the reference itself, compiled unmodified from
+ * /root/reference into oracle/_ref/ (oracle/Makefile) -- bitwise on grids, kernel tables, RHS and
+ * whole trajectories (tests/test_oracle_vs_reference.py, tests/golden/).
+ *
+ * Citations: S:n = "/root/reference/Euler Solver ver.5.3/Solver.cpp" line n, T:n = types.h line n.
+ */
+#ifndef LDM_ORACLE_H
+#define LDM_ORACLE_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ldmo_problem {
+    int G;                /* MomentsGrid.size()            S:57  */
+    int K;                /* KernelsGrid.size()            S:59  */
+    int mM, mW;           /* MaxNumForM[0], MaxNumForW[0][0]  S:51-52 */
+    double h;             /* KernelsGridStep               S:60  */
+    double cutoff;        /* CutoffDistance                S:58  */
+    double sigmaM, sigmaW, b, d, dd;
+    double* moments_grid; /* G   */
+    double* kernels_grid; /* K   */
+    double* M;            /* K*K row-major, M(0)           S:48  */
+    double* W;            /* K*K row-major, W(0,0)         S:49  */
+} ldmo_problem;
+
+/* Properties::Generate for one species (S:186-241).  forced_G > 0 pins num_for_moments and skips
+ * the search loop S:70-74 (the synthetic-grid configurations); forced_G <= 0 is the reference. */
+ldmo_problem* ldmo_generate(double sigma_w, double sigma_m, double b, double d, double d_prime, int forced_G);
+void ldmo_free(ldmo_problem* p);
+
+/* Equation::BilinearInterpolation + Extrapolation (S:318-410); extrapolation: 0 Zero, 1 SquaredN. */
+double ldmo_bilinear(const double* grid, int n, const double* values, double x, double y,
+                     double max_distance, int extrapolation, double asymptotic_value);
+
+/* MakeIntegralWithPairDensity (S:297-316) */
+double ldmo_pair_integral(const ldmo_problem* p, int x_shift, int y_shift, int max_non_zero_num,
+                          const double* kernel, const double* C, double asymptotic_value);
+
+/* CalculateIntegralOfWAndC / CalculateIntegralOfMAndC (S:265-295); MC may be NULL */
+void ldmo_integrals(const ldmo_problem* p, const double* state, double* WC, double* MC);
+
+/* the time-invariant kernel look-ups at the moment nodes (S:469-476, S:490-497); G*G each */
+void ldmo_kernels_at_nodes(const ldmo_problem* p, double* m_at_nodes, double* w_at_nodes);
+
+/* Equation::operator() (S:431-513); state, deriv: 1 + G*G doubles */
+void ldmo_rhs(const ldmo_problem* p, const double* state, double* deriv);
+
+/* number of stored points of EulerSolver::Solve's `time += step; while (time < time_max)` (S:565-589) */
+int ldmo_count_points(double t_max, double dt);
+
+/* EulerSolver::Solve (S:557-592).  init: 1 + G*G doubles.  times: n_points.  values/derivs: either
+ * NULL, or n_points*(1+G*G) (full history) when full_history != 0, or 1+G*G (last point only).
+ * observables (may be NULL): n_points*2 = N and C[0][G-1] at every point (S:1011-1015).
+ * Returns the number of points. */
+int ldmo_solve(const ldmo_problem* p, double t_max, double dt, const double* init, int full_history,
+               double* times, double* values, double* derivs, double* observables);
+
+/* threads the integrals' outer loop may use (results are identical for any count) */
+void ldmo_set_threads(int n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,137 @@
+#!/usr/bin/env python
+"""Generate the golden fixtures in tests/golden/ from the REFERENCE ITSELF.
+
+Runs only where /root/reference is mounted and oracle/_ref has been built (`make -C oracle ref`):
+the reference's Solver.cpp is compiled unmodified (libldm_ref.so) and with five by-value parameters
+turned into references (libldm_ref_byref.so, ~30x faster).  The script first proves the two builds
+bit-identical on every cheap configuration, then uses the fast one where the shipped code would
+need hours.  The fixtures travel to the GPU box; /root/reference does not.
+
+    python tests/golden/make_golden.py            # everything (~6 min on 8 cores)
+"""
+import json
+import os
+import sys
+import time
+from concurrent.futures import ProcessPoolExecutor
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, os.path.dirname(HERE))
+from refharness import REF_DATA, Reference  # noqa: E402
+
+CASES_14_4 = {"a": (0.15, 0.15), "b": (0.05, 0.05), "c": (0.015, 0.15)}   # sigma_W, sigma_M (Data/14/4/*.csv)
+SWEEP = {"a": [0, 12, 80, 159], "b": [0, 12, 40, 159]}                    # Experiment_14_6 entries (S:1033-1043)
+
+
+def sigma_vec():
+    """Vector::setLinSpaced(160, EPSILON, 0.2) (Solver.cpp:1042, types.h:120-130)"""
+    num, lo, hi = 160.0, 1e-08, 0.2
+    step = (hi - lo) / (num - 1)
+    return np.array([lo + i * step for i in range(159)] + [hi])
+
+
+def problem_arrays(p):
+    g, k = p.grids()
+    M, W = p.tables()
+    m_nodes, w_nodes = p.kernels_at_nodes()
+    return dict(G=p.G, K=p.K, mM=p.mM, mW=p.mW, h=p.h_step, cutoff=p.cutoff, sigmaM=p.sigmaM, sigmaW=p.sigmaW,
+                b=p.b, d=p.d, dd=p.dd, moments_grid=g, kernels_grid=k, M=M, W=W, m_nodes=m_nodes, w_nodes=w_nodes)
+
+
+def job_14_4(case):
+    fast = Reference(byref=True)
+    p = fast.from_file(f"{REF_DATA}/14/4/{case}.csv")
+    out = problem_arrays(p)
+    t0 = time.time()
+    times, values, derivs = p.solve(100.0, want_derivs=True)
+    out.update(times=times, obs=np.stack([values[:, 0], values[:, p.G]], 1), final_state=values[-1],
+               final_deriv=derivs[-1], state_k100=values[100], deriv_k100=derivs[100], deriv_k0=derivs[0],
+               state_k1=values[1], state_k10=values[10], state_k500=values[500])
+    wc, mc = p.integrals(values[100])
+    out.update(wc_k100=wc, mc_k100=mc)
+    out["seconds_byref"] = time.time() - t0
+    # the shipped build, wherever it finishes in about a minute
+    slow = Reference(byref=False)
+    q = slow.from_file(f"{REF_DATA}/14/4/{case}.csv")
+    for key, val in problem_arrays(q).items():
+        assert np.array_equal(val, out[key]), (case, key)
+    assert np.array_equal(q.rhs(values[0]), derivs[0]), case
+    assert np.array_equal(q.rhs(values[100]), derivs[100]), case
+    if case == "b":
+        t0 = time.time()
+        t2, v2, d2 = q.solve(100.0, want_derivs=True)
+        assert np.array_equal(t2, times) and np.array_equal(v2, values) and np.array_equal(d2, derivs)
+        out["seconds_unmodified"] = time.time() - t0
+        out["unmodified_checked"] = "problem tables, rhs(k=0), rhs(k=100), whole trajectory"
+    else:
+        out["unmodified_checked"] = "problem tables, rhs(k=0), rhs(k=100)"
+    np.savez_compressed(os.path.join(HERE, f"exp_14_4_{case}.npz"), **out)
+    return f"14.4{case}: G={p.G} N_end={values[-1, 0]!r}"
+
+
+def job_14_6(args):
+    which, i = args
+    sig = sigma_vec()[i]
+    fast = Reference(byref=True)
+    route = 1 if which == "a" else 2          # a: GetWithoutSigmaW, b: GetWithoutSigmaM (S:1035-1041)
+    p = fast.from_file(f"{REF_DATA}/14/6/{which}.csv", route, float(sig))
+    out = problem_arrays(p)
+    t0 = time.time()
+    times, values, derivs = p.solve(200.0, want_derivs=True)
+    out.update(sigma=sig, entry=i, times=times, obs=np.stack([values[:, 0], values[:, p.G]], 1),
+               final_state=values[-1], state_k100=values[100], deriv_k100=derivs[100], deriv_k0=derivs[0],
+               state_k1=values[1], state_k2=values[2])
+    out["seconds_byref"] = time.time() - t0
+    slow = Reference(byref=False)
+    q = slow.from_file(f"{REF_DATA}/14/6/{which}.csv", route, float(sig))
+    for key, val in problem_arrays(q).items():
+        assert np.array_equal(val, out[key]), (which, i, key)
+    out["unmodified_checked"] = "problem tables"
+    if p.G * p.G * (p.mM - 1) ** 2 < 1.2e6:   # one shipped-build RHS in a few seconds
+        assert np.array_equal(q.rhs(values[100]), derivs[100]), (which, i)
+        out["unmodified_checked"] += ", rhs(k=100)"
+    np.savez_compressed(os.path.join(HERE, f"exp_14_6_{which}_{i:03d}.npz"), **out)
+    return f"14.6{which}[{i}]: sigma={sig!r} G={p.G} K={p.K} mM={p.mM} mW={p.mW} N_end={values[-1, 0]!r}"
+
+
+def job_synth(args):
+    """Forced-G grids (BASELINE.json configs 3-5): problem tables + one RHS on a non-trivial state."""
+    name, sw, sm, G, b, d = args
+    fast = Reference(byref=True)
+    p = fast.from_numbers(sw, sm, b, d, 0.001, G)
+    out = problem_arrays(p)
+    g, _ = p.grids()
+    st = np.full(1 + p.P, 200.0 ** 2)
+    st[0] = 200.0
+    r2 = g[:, None] ** 2 + g[None, :] ** 2
+    st[1:] = (200.0 ** 2 * (1 + 0.5 * np.exp(-r2 / (2 * sw * sw)))).ravel()   # SURVEY 8d config 3 seed, no RNG
+    t0 = time.time()
+    out.update(state=st, deriv=p.rhs(st))
+    wc, mc = p.integrals(st)
+    out.update(wc=wc, mc=mc, seconds_byref=time.time() - t0)
+    np.savez_compressed(os.path.join(HERE, f"synth_{name}.npz"), **out)
+    return f"synth {name}: G={p.G} K={p.K} mM={p.mM} mW={p.mW} dN={out['deriv'][0]!r}"
+
+
+def main():
+    assert Reference().available and Reference(True).available, "run `make -C oracle ref` first"
+    jobs = [(job_14_6, (w, i)) for w, idx in SWEEP.items() for i in idx]
+    jobs += [(job_14_4, c) for c in "acb"]
+    jobs += [(job_synth, ("g32", 0.15, 0.15, 32, 0.4, 0.2)), (job_synth, ("g64", 0.1, 0.1, 64, 0.45, 0.25)),
+             (job_synth, ("g48_narrow_w", 0.012, 0.1, 48, 0.4, 0.2))]
+    summary = []
+    with ProcessPoolExecutor(max_workers=os.cpu_count()) as pool:
+        futures = [pool.submit(fn, arg) for fn, arg in jobs]
+        for f in futures:
+            line = f.result()
+            print(line, flush=True)
+            summary.append(line)
+    with open(os.path.join(HERE, "SUMMARY.json"), "w") as fh:
+        json.dump({"generated_by": "tests/golden/make_golden.py", "source": "oracle/_ref (reference compiled from /root/reference)",
+                   "lines": summary}, fh, indent=1)
+
+
+if __name__ == "__main__":
+    main()

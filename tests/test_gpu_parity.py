@@ -1,0 +1,213 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the golden fixtures.
+
+Tolerances (BASELINE.json north_star: 1e-10 relative on N(t) and C(xi,t)):
+  * trajectories: |gpu - ref| <= 1e-10 * |ref| at every stored point, every component; entries the reference
+    clamps to exactly 0 (Solver.cpp:578-580) must be exactly 0 on the GPU as well;
+  * a single right-hand side: far from the origin dC is the cancellation residue of terms of size ~2bN^2, so
+    the bound is 1e-12 times the sum of the term magnitudes (SURVEY.md 8c comparison rule).
+"""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import OracleProblem
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+RTOL_TRAJECTORY = 1e-10
+RTOL_RHS_TERMS = 1e-12
+
+
+def golden(name):
+    return np.load(os.path.join(HERE, "golden", name + ".npz"))
+
+
+def problems_from(g, name, ldm):
+    forced = int(g["G"]) if "synth" in name else 0
+    args = (float(g["sigmaW"]), float(g["sigmaM"]), float(g["b"]), float(g["d"]), float(g["dd"]))
+    return ldm.Properties.Generate(1, *args, forced), OracleProblem(*args, forced)
+
+
+def rhs_term_scale(o, state):
+    """sum of |terms| of dC (Solver.cpp:464-505) and of dN (446-451), per component"""
+    N = state[0]
+    C = state[1:].reshape(o.G, o.G)
+    wc, mc = o.integrals(state)
+    m_nodes, w_nodes = o.kernels_at_nodes()
+    scale_c = (2 * o.b * np.abs(mc) + 2 * o.b * N * np.abs(m_nodes) + 2 * o.d * np.abs(C)
+               + 2 * o.dd * np.abs(wc * C / N) + 2 * o.dd * np.abs(w_nodes * C))
+    scale_n = abs(N * (o.b - o.d)) + abs(o.dd * wc)
+    return np.concatenate([[scale_n], scale_c.ravel()])
+
+
+def assert_rhs_close(o, state, got, want):
+    scale = rhs_term_scale(o, state)
+    err = np.abs(got - want)
+    worst = np.argmax(err / scale)
+    assert np.all(err <= RTOL_RHS_TERMS * scale), (worst, got[worst], want[worst], err[worst] / scale[worst])
+
+
+def assert_states_close(got, want):
+    got, want = np.asarray(got), np.asarray(want)
+    assert got.shape == want.shape
+    assert np.array_equal(got == 0, want == 0), "clamped entries differ"
+    err = np.abs(got - want)
+    bound = RTOL_TRAJECTORY * np.abs(want)
+    worst = np.unravel_index(np.argmax(err - bound), err.shape)
+    assert np.all(err <= bound), (worst, got[worst], want[worst])
+
+
+ALL = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "golden", "*.npz")))
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_kernels_at_nodes_bitwise(ldm, name):
+    g = golden(name)
+    props, _ = problems_from(g, name, ldm)
+    eq = ldm.Equation(props)
+    m, w = eq.kernels_at_nodes()
+    assert np.array_equal(m, g["m_nodes"]) and np.array_equal(w, g["w_nodes"])
+
+
+@pytest.mark.parametrize("name", ALL)
+def test_rhs_against_golden(ldm, name):
+    g = golden(name)
+    props, o = problems_from(g, name, ldm)
+    eq = ldm.Equation(props)
+    if "synth" in name:
+        cases = [(g["state"], g["deriv"])]
+    else:
+        cases = [(eq.GenerateEquilibriumValuesForNAndC(200), g["deriv_k0"]), (g["state_k100"], g["deriv_k100"])]
+    for state, want in cases:
+        got = eq(0.0, state, ldm.SquaredN)
+        assert_rhs_close(o, state, got, want)
+
+
+@pytest.mark.parametrize("name", ["exp_14_4_b", "exp_14_4_c", "exp_14_6_a_080", "synth_g32", "synth_g64"])
+def test_integrals_against_oracle(ldm, name):
+    g = golden(name)
+    props, o = problems_from(g, name, ldm)
+    eq = ldm.Equation(props)
+    state = g["state"] if "synth" in name else g["state_k100"]
+    wc, mc = eq.integrals(state)
+    wc_ref, mc_ref = o.integrals(state)
+    assert abs(wc - wc_ref) <= 1e-13 * abs(wc_ref)
+    assert np.all(np.abs(mc - mc_ref) <= 1e-13 * np.abs(mc_ref))
+
+
+@pytest.mark.parametrize("name", ["exp_14_4_a", "exp_14_4_b", "exp_14_4_c"])
+def test_experiment_14_4_trajectory(ldm, name):
+    """CalculateFirstMoment(100) (Solver.cpp:885-906): dt 0.1, 1001 points, N0 = 200."""
+    g = golden(name)
+    props, _ = problems_from(g, name, ldm)
+    eq = ldm.Equation(props)
+    res = ldm.EulerSolver().Solve(eq, ldm.SquaredN, 100, 0.1, eq.GenerateEquilibriumValuesForNAndC(200),
+                                  record=ldm.RECORD_ALL)
+    assert len(res.Times) == 1001 and np.array_equal(res.Times, g["times"])
+    assert_states_close(res.Values[:, [0, props.G]], g["obs"])
+    for k, key in ((1, "state_k1"), (10, "state_k10"), (100, "state_k100"), (500, "state_k500"), (1000, "final_state")):
+        assert_states_close(res.Values[k], g[key])
+    o = OracleProblem(float(g["sigmaW"]), float(g["sigmaM"]))
+    assert_rhs_close(o, g["final_state"], res.Derivatives[1000], g["final_deriv"])
+    # the other record modes see the same run
+    obs = ldm.EulerSolver().Solve(eq, ldm.SquaredN, 100, 0.1, eq.GenerateEquilibriumValuesForNAndC(200),
+                                  record=ldm.RECORD_OBSERVABLES)
+    assert np.array_equal(obs.Observables, res.Values[:, [0, props.G]])
+    last = ldm.EulerSolver().Solve(eq, ldm.SquaredN, 100, 0.1, eq.GenerateEquilibriumValuesForNAndC(200),
+                                   record=ldm.RECORD_LAST)
+    assert np.array_equal(last.Values[0], res.Values[-1])
+    assert np.array_equal(last.Derivatives[0], res.Derivatives[-1])
+
+
+@pytest.mark.parametrize("name", [n for n in ALL if "14_6" in n])
+def test_experiment_14_6_entries(ldm, name):
+    """One entry of CalculateWithVaryingSigma(200) (Solver.cpp:909-977): 2001 points; includes the entries where
+    the clamp is active (14.6a[0], sigma_W = 1e-8) and where the population goes extinct (14.6b[0])."""
+    g = golden(name)
+    props, _ = problems_from(g, name, ldm)
+    eq = ldm.Equation(props)
+    res = ldm.EulerSolver().Solve(eq, ldm.SquaredN, 200, 0.1, eq.GenerateEquilibriumValuesForNAndC(200),
+                                  record=ldm.RECORD_VALUES)
+    assert len(res.Times) == 2001 and np.array_equal(res.Times, g["times"])
+    assert_states_close(res.Values[:, [0, props.G]], g["obs"])
+    for k, key in ((1, "state_k1"), (2, "state_k2"), (100, "state_k100"), (2000, "final_state")):
+        assert_states_close(res.Values[k], g[key])
+
+
+def test_resident_stepping_equals_solve(ldm):
+    g = golden("exp_14_4_b")
+    props, _ = problems_from(g, "exp_14_4_b", ldm)
+    eq = ldm.Equation(props)
+    eq.upload(eq.GenerateEquilibriumValuesForNAndC(200))
+    eq.advance(100, 0.1)
+    eq.synchronize()
+    assert_states_close(eq.download(), g["state_k100"])
+    assert eq.last_elapsed_ms() > 0 and eq.launches > 0
+
+
+def test_batch_of_parameter_sets(ldm):
+    """the 14.6 loop (Solver.cpp:940-963) over a few entries at once, slot-indexed results"""
+    names = ["exp_14_6_a_012", "exp_14_6_b_040", "exp_14_6_a_080", "exp_14_6_b_012"]
+    eqs, inits, wants = [], [], []
+    for name in names:
+        g = golden(name)
+        props, _ = problems_from(g, name, ldm)
+        eq = ldm.Equation(props)
+        eqs.append(eq)
+        inits.append(eq.GenerateEquilibriumValuesForNAndC(200))
+        wants.append(g["final_state"])
+    outs = ldm.solve_batch(eqs, inits, 0.1, 200)
+    for got, want in zip(outs, wants):
+        assert_states_close(got, want)
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_sharded_step_emulated_on_one_device(ldm, world):
+    """xi-sharding with all ranks emulated on one GPU: each rank updates its rows of C from the
+    gathered replica; the 'all-gather' is a concatenation.  Must equal the unsharded run bit for bit."""
+    import torch
+    g = golden("exp_14_4_c")
+    props, _ = problems_from(g, "exp_14_4_c", ldm)
+    G = props.G
+    ranks = [ldm.ShardedEquation(props, r, world) for r in range(world)]
+    rpr = ranks[0].rows_per_rank
+    state = g["state_k100"]
+    bufs = [torch.from_numpy(ranks[0].to_gathered(state[1:])).cuda(), torch.zeros(world * rpr, G, dtype=torch.float64, device="cuda")]
+    for r in ranks:
+        r.set_N(state[0])
+    stream = torch.cuda.current_stream().cuda_stream
+    steps = 5
+    for k in range(steps):
+        src, dst = bufs[k % 2], bufs[(k + 1) % 2]
+        for r in ranks:
+            r.step(src.data_ptr(), dst[r.rank * rpr:(r.rank + 1) * rpr].data_ptr(), 0.1, stream)
+    torch.cuda.synchronize()
+    single = ldm.Equation(props)
+    single.upload(state)
+    single.advance(steps, 0.1)
+    want = single.download()
+    got_C = ranks[0].from_gathered(bufs[steps % 2].cpu().numpy())
+    assert np.array_equal(got_C.ravel(), want[1:])
+    for r in ranks:
+        assert r.get_N() == want[0]
+
+
+def test_large_grid_properties(ldm):
+    """BASELINE config 3 (G = 128): too slow for the CPU oracle in a test, so check what the domain offers:
+    the spatially uniform state C = N^2 must give dC ~ 2bN m(xi) - 2d'N^2 w(xi)... exactly the structure of the
+    reference at t=0 -- MC = N^2 and WC = N^2 because both kernels integrate to one (Solver.cpp:147-183)."""
+    props = ldm.Properties.Generate(1, 0.15, 0.15, 0.4, 0.2, 0.001, 128)
+    eq = ldm.Equation(props)
+    st = eq.GenerateEquilibriumValuesForNAndC(200)
+    wc, mc = eq.integrals(st)
+    assert abs(wc - 40000.0) <= 1e-9 * 40000 and np.all(np.abs(mc - 40000.0) <= 1e-9 * 40000)
+    # linearity of the integrals in C at fixed N
+    rng = np.random.default_rng(7)
+    a = st.copy(); a[1:] *= rng.uniform(0.5, 1.5, a.size - 1)
+    c = st.copy(); c[1:] *= rng.uniform(0.5, 1.5, c.size - 1)
+    s = a.copy(); s[1:] = 0.25 * a[1:] + 0.75 * c[1:]
+    (wa, ma), (wb, mb), (ws, ms) = eq.integrals(a), eq.integrals(c), eq.integrals(s)
+    assert abs(ws - (0.25 * wa + 0.75 * wb)) <= 1e-12 * abs(ws)
+    assert np.all(np.abs(ms - (0.25 * ma + 0.75 * mb)) <= 1e-12 * np.abs(ms))

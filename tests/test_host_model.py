@@ -1,0 +1,62 @@
+"""Host side of the product (no GPU): model setup is bit-identical to the reference's Properties::Generate,
+the C ABI exports every symbol of include/ldm.h, and compute calls fail loudly without a device."""
+import ctypes
+import glob
+import os
+import re
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = sorted(glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")))
+
+
+def generate(ldm, g, name):
+    forced = int(g["G"]) if "synth" in name else 0
+    return ldm.Properties.Generate(1, float(g["sigmaW"]), float(g["sigmaM"]), float(g["b"]), float(g["d"]),
+                                   float(g["dd"]), forced)
+
+
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_generate_matches_reference_bitwise(ldm, path):
+    g = np.load(path)
+    p = generate(ldm, g, path)
+    assert (p.G, p.K, p.MaxNumForM, p.MaxNumForW) == (int(g["G"]), int(g["K"]), int(g["mM"]), int(g["mW"]))
+    assert p.KernelsGridStep == float(g["h"]) and p.CutoffDistance == float(g["cutoff"])
+    assert np.array_equal(p.MomentsGrid, g["moments_grid"])
+    assert np.array_equal(p.KernelsGrid, g["kernels_grid"])
+    assert np.array_equal(p.M, g["M"]) and np.array_equal(p.W, g["W"])
+    p.CheckKernels()       # Solver.cpp:147-183: both integrals within 1e-8 of 1
+
+
+def test_header_symbols_are_exported(ldm):
+    header = open(os.path.join(ROOT, "include", "ldm.h")).read()
+    declared = set(re.findall(r"\b(ldm_[a-z_A-Z0-9]+)\s*\(", header))
+    assert len(declared) >= 20
+    lib = ctypes.CDLL(ldm.LIBRARY_PATH)
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} declared in include/ldm.h but not exported"
+    assert declared == set(ldm._SIGNATURES), "python binding and header disagree"
+
+
+def test_point_count(ldm):
+    assert ldm.count_points(100, 0.1) == 1001      # Experiment_14_4 (Solver.cpp:1005)
+    assert ldm.count_points(200, 0.1) == 2001      # Experiment_14_6 (Solver.cpp:1043)
+    assert ldm.count_points(0.05, 0.1) == 1
+
+
+def test_bad_arguments_are_reported(ldm):
+    with pytest.raises(ldm.LdmError):
+        ldm.Properties.Generate(2, 0.1, 0.1, 0.4, 0.2, 0.001)       # species != 1: UNSUPPORTED in the reference's Data/
+    with pytest.raises(ldm.LdmError):
+        ldm.Properties.Generate(1, -1.0, 0.1, 0.4, 0.2, 0.001)
+
+
+def test_no_cpu_fallback(ldm):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    p = ldm.Properties.Generate(1, 0.05, 0.05, 0.4, 0.2, 0.001)
+    with pytest.raises(ldm.LdmError, match="no CUDA device"):
+        ldm.Equation(p)
