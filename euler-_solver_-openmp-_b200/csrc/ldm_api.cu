@@ -48,8 +48,10 @@ struct ldm_context {
     double* d_scalars = nullptr;           // [kScalars]
     double* d_sum = nullptr;               // [P] per-node inside-sample sum
     double* d_deriv = nullptr;             // [P] dC/dt
+    double* d_partial = nullptr;           // [tiles][P] factored path: per beta-tile sums
+    double* d_ring = nullptr;              // [P] factored path: samples between the cutoff circle and the square edge
     int cur = 0;
-    int algo = LDM_ALGO_DIRECT;
+    int algo = LDM_ALGO_FACTORED;
     long long launches = 0;
     float last_ms = 0.f;
     double shard_N[2] = {0, 0};
@@ -88,8 +90,15 @@ using ldm::DevProblem;
 // sum over inside samples of m * C~ for this rank's rows -> d_sum   (the m*C integral, S:277-316)
 void inside_sum(ldm_context* c, const DevProblem& P, const double* C, double* out, cudaStream_t s)
 {
-    ldm::launch_sample_sum(P, ldm::SAMPLES_INSIDE, C, out, s);
-    c->launches += 1;
+    if (c->algo == LDM_ALGO_DIRECT) {
+        ldm::launch_sample_sum(P, ldm::SAMPLES_INSIDE, C, out, s);
+        c->launches += 1;
+        return;
+    }
+    ldm::launch_factored(P, C, c->d_partial, s);
+    ldm::launch_sample_sum(P, ldm::SAMPLES_RING, C, c->d_ring, s);
+    ldm::launch_combine(P, ldm::factored_tiles(P), c->d_partial, c->d_ring, out, s);
+    c->launches += 3;
 }
 
 // one right-hand side at the state (N_cur, C): scalars <- WC, dN; deriv/C_next optional
@@ -203,6 +212,8 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         c->d_scalars = c->alloc<double>(ldm::kScalars);
         c->d_sum = c->alloc<double>(P);
         c->d_deriv = c->alloc<double>(P);
+        c->d_partial = c->alloc<double>(P * (size_t)ldm::factored_tiles(d));
+        c->d_ring = c->alloc<double>(P);
         LDM_CUDA(cudaMemsetAsync(c->d_C[0], 0, P * sizeof(double), c->stream));
         LDM_CUDA(cudaMemsetAsync(c->d_C[1], 0, P * sizeof(double), c->stream));
         LDM_CUDA(cudaMemsetAsync(c->d_N, 0, 2 * sizeof(double), c->stream));
@@ -220,8 +231,8 @@ void ldm_destroy(ldm_handle h) { delete h; }
 int ldm_set_algorithm(ldm_handle h, int algo)
 {
     if (!h) return fail(LDM_ERR_ARGUMENT, "NULL handle");
-    if (algo == LDM_ALGO_AUTO) algo = LDM_ALGO_DIRECT;
-    if (algo != LDM_ALGO_DIRECT) return fail(LDM_ERR_UNSUPPORTED, "algorithm not available in this build");
+    if (algo == LDM_ALGO_AUTO) algo = LDM_ALGO_FACTORED;
+    if (algo != LDM_ALGO_DIRECT && algo != LDM_ALGO_FACTORED) return fail(LDM_ERR_ARGUMENT, "unknown algorithm");
     h->algo = algo;
     return LDM_OK;
 }

@@ -55,4 +55,10 @@ void launch_wc(const DevProblem& P, const double* C, const double* N_cur, double
 void launch_pointwise(const DevProblem& P, const double* C, const double* inside_sum, const double* N_cur,
                       const double* scalars, double dt, double* deriv_out, double* C_next, cudaStream_t stream);
 
+// Factored path (ldm_factored.cu): partial[tile][local_rows][G] <- per beta-tile sums over all samples inside the
+// grid square; combine: inside_sum = sum_tiles partial - ring.
+int factored_tiles(const DevProblem& P);
+void launch_factored(const DevProblem& P, const double* C, double* partial, cudaStream_t stream);
+void launch_combine(const DevProblem& P, int tiles, const double* partial, const double* ring, double* out, cudaStream_t stream);
+
 }  // namespace ldm

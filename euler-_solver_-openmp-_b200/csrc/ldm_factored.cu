@@ -1,0 +1,267 @@
+// The factored evaluation of the m*C integral (Solver.cpp:277-316) for sm_100a.
+//
+// The reference evaluates, for every node (x,y), a double sum over quadrature offsets (o_i, o_j) of
+// m[a_i][a_j] * bilinear(C)(s(x,o_i), s(y,o_j)).  Bilinear interpolation is a product of two 1-D
+// interpolations and the sample abscissae are separable, so with L[n][o] the 2-tap interpolation row of
+// node n / offset o the sum over all samples inside the grid square is
+//
+//     ext[x][y] = sum_{beta} sum_{o_j in beta} L[y][o_j] . H_x[beta][:],      H_x = Q . E_x,
+//     E_x[alpha][q] = sum_{o_i in alpha} (L[x][o_i] . C[:, q])
+//
+// with Q the odd-node quadrant of the kernel table (A x A, symmetric) and "o in alpha" the (at most two)
+// signed offsets that share kernel node alpha.  H_x = Q E_x is a dense FP64 GEMM (A x A x G per row x):
+// P*A*A fused multiply-adds per step instead of ~2 P (2A)^2 for the sample-by-sample sum.  The samples that
+// lie inside the square but outside the cutoff circle (where the reference substitutes N^2, Solver.cpp:329-331)
+// are removed afterwards by the exact ring correction (sample_sum<SAMPLES_RING>), so
+//     inside_sum = ext - ring.
+//
+// One CTA owns one row x and one tile of BM beta-rows; it walks the columns q in chunks of BN, generating
+// the E chunk on the fly from C (2-4 taps per element), accumulating the BM x BN tile of H in registers,
+// staging it in shared memory and immediately contracting it with the y-side interpolation rows.
+#include "ldm_device.h"
+
+namespace ldm {
+
+namespace {
+
+template <int BM, int BN, int TM, int TN, int BK>
+struct FactoredConfig {
+    static constexpr int TYN = BM / TM;            // thread rows
+    static constexpr int TXN = BN / TN;            // thread columns
+    static constexpr int NT = TYN * TXN;           // threads per CTA
+    static constexpr int HS_LD = BN + 2;           // H staging row: 1 halo column + BN + 1 pad
+    static constexpr int E_PER_THREAD = (BK * BN) / NT;
+    static constexpr int Q_PER_THREAD = (BK * BM + NT - 1) / NT;
+    static_assert(BM % TM == 0 && BN % TN == 0 && TN % 2 == 0, "tile shape");
+    static_assert((BK * BN) % NT == 0, "E chunk must divide evenly over the threads");
+    static size_t smem_bytes(int G, int groups)
+    {
+        return sizeof(double) * ((size_t)2 * BK * BM + (size_t)2 * BK * BN + (size_t)BM * HS_LD + (size_t)G * (1 + groups));
+    }
+};
+
+// offsets sharing kernel node alpha: (A-1-alpha, A+alpha) for an odd extent, the single offset 0 for m == 2
+__device__ __forceinline__ int folded_offset(int A, int n_fold, int alpha, int f)
+{
+    return n_fold == 1 ? 0 : (f == 0 ? A - 1 - alpha : A + alpha);
+}
+
+template <int BM, int BN, int TM, int TN, int BK>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+factored_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__ partial, int groups)
+{
+    using Cfg = FactoredConfig<BM, BN, TM, TN, BK>;
+    constexpr int TYN = Cfg::TYN, TXN = Cfg::TXN, NT = Cfg::NT, HS_LD = Cfg::HS_LD;
+    const int G = P.G, A = P.A, n_off = P.n_off;
+    const int n_fold = n_off / A;
+    const int lx = blockIdx.y;
+    const int x = P.rank + P.world * lx;
+    const int b0 = blockIdx.x * BM;                       // first beta row of this tile
+    const int tid = threadIdx.x;
+    const int tx = tid % TXN, ty = tid / TXN;
+
+    extern __shared__ __align__(16) double smem[];
+    double* Qs = smem;                                    // [2][BK][BM]
+    double* Es = Qs + 2 * BK * BM;                        // [2][BK][BN]
+    double* Hs = Es + 2 * BK * BN;                        // [BM][HS_LD]
+    double* acc_y = Hs + BM * HS_LD;                      // [G]
+    double* part = acc_y + G;                             // [groups][G]
+
+    for (int y = tid; y < G; y += NT) acc_y[y] = 0.0;
+
+    const int* ux_row = P.upper + (size_t)x * n_off;
+    const double* wx_row = P.weight + (size_t)x * n_off;
+    const int n_kc = (A + BK - 1) / BK;
+    const int n_chunks = (G + BN - 1) / BN;
+
+    double e_reg[Cfg::E_PER_THREAD];
+    double q_reg[Cfg::Q_PER_THREAD];
+
+    for (int chunk = 0; chunk < n_chunks; chunk++) {
+        const int q0 = chunk * BN;
+
+        // E chunk element e -> (k = e / BN, column = e % BN); consecutive threads take consecutive columns
+        auto load_chunk = [&](int kc) {
+            #pragma unroll
+            for (int r = 0; r < Cfg::E_PER_THREAD; r++) {
+                const int e = r * NT + tid;
+                const int k = e / BN, col = e - k * BN;
+                const int alpha = kc * BK + k, q = q0 + col;
+                double v = 0.0;
+                if (alpha < A && q < G) {
+                    for (int f = 0; f < n_fold; f++) {
+                        const int o = folded_offset(A, n_fold, alpha, f);
+                        const int u = ux_row[o];
+                        if (u != 0) {
+                            const double w = wx_row[o];
+                            v += C[(size_t)row_slot(P, u - 1) * G + q] * (1.0 - w) + C[(size_t)row_slot(P, u) * G + q] * w;
+                        }
+                    }
+                }
+                e_reg[r] = v;
+            }
+            #pragma unroll
+            for (int r = 0; r < Cfg::Q_PER_THREAD; r++) {
+                const int e = r * NT + tid;
+                const int bm = e / BK, k = e - bm * BK;          // consecutive threads walk alpha: coalesced rows of Q
+                const int beta = b0 + bm, alpha = kc * BK + k;
+                q_reg[r] = (e < BK * BM && beta < A && alpha < A) ? P.quadrant[(size_t)beta * A + alpha] : 0.0;
+            }
+        };
+        auto store_chunk = [&](int buf) {
+            #pragma unroll
+            for (int r = 0; r < Cfg::E_PER_THREAD; r++) {
+                const int e = r * NT + tid;
+                Es[buf * BK * BN + e] = e_reg[r];
+            }
+            #pragma unroll
+            for (int r = 0; r < Cfg::Q_PER_THREAD; r++) {
+                const int e = r * NT + tid;
+                if (e < BK * BM) {
+                    const int bm = e / BK, k = e - bm * BK;
+                    Qs[buf * BK * BM + k * BM + bm] = q_reg[r];
+                }
+            }
+        };
+
+        double acc[TM][TN];
+        #pragma unroll
+        for (int i = 0; i < TM; i++)
+            #pragma unroll
+            for (int j = 0; j < TN; j++) acc[i][j] = 0.0;
+
+        load_chunk(0);
+        store_chunk(0);
+        __syncthreads();
+        for (int kc = 0; kc < n_kc; kc++) {
+            const int buf = kc & 1;
+            if (kc + 1 < n_kc) load_chunk(kc + 1);               // global loads in flight under the FMAs
+            const double* qs = Qs + buf * BK * BM;
+            const double* es = Es + buf * BK * BN;
+            #pragma unroll
+            for (int k = 0; k < BK; k++) {
+                double a[TM], b[TN];
+                #pragma unroll
+                for (int i = 0; i < TM; i++) a[i] = qs[k * BM + i * TYN + ty];
+                #pragma unroll
+                for (int j = 0; j < TN; j += 2) {                // 16-byte loads, consecutive threads -> consecutive 16 B
+                    const double2 v = *reinterpret_cast<const double2*>(es + k * BN + (j / 2) * (2 * TXN) + tx * 2);
+                    b[j] = v.x; b[j + 1] = v.y;
+                }
+                #pragma unroll
+                for (int i = 0; i < TM; i++)
+                    #pragma unroll
+                    for (int j = 0; j < TN; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+            }
+            if (kc + 1 < n_kc) store_chunk(buf ^ 1);
+            __syncthreads();
+        }
+
+        // stage the H tile: Hs[row][1 + col]; column 0 keeps the last column of the previous chunk
+        #pragma unroll
+        for (int i = 0; i < TM; i++)
+            #pragma unroll
+            for (int j = 0; j < TN; j++)
+                Hs[(i * TYN + ty) * HS_LD + 1 + (j / 2) * (2 * TXN) + tx * 2 + (j & 1)] = acc[i][j];
+        __syncthreads();
+
+        // y side: every tap pair (u-1, u) whose upper node u falls in this chunk
+        const int rows_here = min(BM, A - b0);
+        for (int idx = tid; idx < G * groups; idx += NT) {
+            const int grp = idx / G, y = idx - grp * G;
+            const int* uy_row = P.upper + (size_t)y * n_off;
+            const double* wy_row = P.weight + (size_t)y * n_off;
+            double s = 0.0;
+            for (int bm = grp; bm < rows_here; bm += groups) {
+                const double* hrow = Hs + bm * HS_LD + 1 - q0;
+                for (int f = 0; f < n_fold; f++) {
+                    const int o = folded_offset(A, n_fold, b0 + bm, f);
+                    const int u = uy_row[o];
+                    if (u >= q0 && u < q0 + BN && u != 0) {
+                        const double w = wy_row[o];
+                        s += hrow[u - 1] * (1.0 - w) + hrow[u] * w;
+                    }
+                }
+            }
+            part[grp * G + y] = s;
+        }
+        __syncthreads();
+        for (int y = tid; y < G; y += NT) {
+            double s = acc_y[y];
+            for (int grp = 0; grp < groups; grp++) s += part[grp * G + y];    // fixed order
+            acc_y[y] = s;
+        }
+        if (chunk + 1 < n_chunks)
+            for (int bm = tid; bm < BM; bm += NT) Hs[bm * HS_LD] = Hs[bm * HS_LD + BN];   // carry the halo column
+        __syncthreads();
+    }
+
+    double* out = partial + ((size_t)blockIdx.x * local_rows(P) + lx) * G;
+    for (int y = tid; y < G; y += NT) out[y] = acc_y[y];
+}
+
+// inside_sum[lx][y] = sum_t partial[t][lx][y] - ring[lx][y]
+__global__ void __launch_bounds__(256)
+combine_kernel(int n, int tiles, const double* __restrict__ partial, const double* __restrict__ ring, double* __restrict__ out)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    double s = 0.0;
+    for (int t = 0; t < tiles; t++) s += partial[(size_t)t * n + q];
+    out[q] = s - ring[q];
+}
+
+template <int BM, int BN, int TM, int TN, int BK>
+void launch_variant(const DevProblem& P, const double* C, double* partial, int tiles, cudaStream_t stream)
+{
+    using Cfg = FactoredConfig<BM, BN, TM, TN, BK>;
+    const int groups = Cfg::NT >= P.G ? Cfg::NT / P.G : 1;
+    const size_t smem = Cfg::smem_bytes(P.G, groups);
+    static bool configured[64] = {};                 // the opt-in is per device
+    int device = 0;
+    cudaGetDevice(&device);
+    if (!configured[device & 63]) {
+        cudaFuncSetAttribute(factored_kernel<BM, BN, TM, TN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        configured[device & 63] = true;
+    }
+    dim3 grid(tiles, local_rows(P));
+    factored_kernel<BM, BN, TM, TN, BK><<<grid, Cfg::NT, smem, stream>>>(P, C, partial, groups);
+}
+
+}  // namespace
+
+int factored_tile_rows(const DevProblem& P)
+{
+    // pick the beta-tile height that wastes the fewest padded rows
+    const int A = P.A;
+    const int pad80 = ((A + 79) / 80) * 80, pad40 = ((A + 39) / 40) * 40;
+    return pad40 < pad80 ? 40 : 80;
+}
+
+int factored_tiles(const DevProblem& P)
+{
+    const int bm = factored_tile_rows(P);
+    return (P.A + bm - 1) / bm;
+}
+
+void launch_factored(const DevProblem& P, const double* C, double* partial, cudaStream_t stream)
+{
+    const int bm = factored_tile_rows(P);
+    const int tiles = factored_tiles(P);
+    const bool narrow = P.G <= 64;
+    if (bm == 80) {
+        if (narrow) launch_variant<80, 64, 5, 8, 16>(P, C, partial, tiles, stream);
+        else launch_variant<80, 128, 5, 8, 16>(P, C, partial, tiles, stream);
+    } else {
+        if (narrow) launch_variant<40, 64, 5, 8, 16>(P, C, partial, tiles, stream);
+        else launch_variant<40, 128, 5, 8, 16>(P, C, partial, tiles, stream);
+    }
+}
+
+void launch_combine(const DevProblem& P, int tiles, const double* partial, const double* ring, double* out, cudaStream_t stream)
+{
+    const int n = local_rows(P) * P.G;
+    combine_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, tiles, partial, ring, out);
+}
+
+}  // namespace ldm

@@ -36,7 +36,6 @@ sample_sum_kernel(DevProblem P, const double* __restrict__ C, double* __restrict
     if (y >= G) return;
     const int lane = threadIdx.x;
 
-    const double* sx_row = P.s + (size_t)x * n_off;
     const double* lim_row = P.limit + (size_t)x * n_off;
     const double* wx_row = P.weight + (size_t)x * n_off;
     const int* ux_row = P.upper + (size_t)x * n_off;
@@ -53,7 +52,7 @@ sample_sum_kernel(DevProblem P, const double* __restrict__ C, double* __restrict
         const int ux = ux_row[oi];
         if (MODE == SAMPLES_INSIDE && lim < 0.0) continue;              // nothing inside on this sample row
         if (MODE == SAMPLES_RING && (ux == 0 || lim >= sy_far)) continue;   // no sample between circle and square edge
-        const double wx = wx_row[oi];
+        const double wx = wx_row[oi], ux_w = 1.0 - wx;   // a(1-w) + b w: exact at w = 0 and w = 1, like S:348-351
         const double* q_row = P.quadrant + (size_t)P.alpha[oi] * A;
         const double* c_lo = C + (size_t)row_slot(P, ux > 0 ? ux - 1 : 0) * G;
         const double* c_hi = C + (size_t)row_slot(P, ux) * G;
@@ -72,9 +71,9 @@ sample_sum_kernel(DevProblem P, const double* __restrict__ C, double* __restrict
                 const double wy = wy_row[oj];
                 const double c00 = c_lo[uy - 1], c01 = c_lo[uy];
                 const double c10 = c_hi[uy - 1], c11 = c_hi[uy];
-                const double lo = c00 + wx * (c10 - c00);
-                const double hi = c01 + wx * (c11 - c01);
-                acc += m * (lo + wy * (hi - lo));
+                const double lo = c00 * ux_w + c10 * wx;
+                const double hi = c01 * ux_w + c11 * wx;
+                acc += m * (lo * (1.0 - wy) + hi * wy);
             }
         }
     }

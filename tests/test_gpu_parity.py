@@ -71,11 +71,12 @@ def test_kernels_at_nodes_bitwise(ldm, name):
     assert np.array_equal(m, g["m_nodes"]) and np.array_equal(w, g["w_nodes"])
 
 
+@pytest.mark.parametrize("algorithm", ["direct", "factored"])
 @pytest.mark.parametrize("name", ALL)
-def test_rhs_against_golden(ldm, name):
+def test_rhs_against_golden(ldm, name, algorithm):
     g = golden(name)
     props, o = problems_from(g, name, ldm)
-    eq = ldm.Equation(props)
+    eq = ldm.Equation(props, algorithm=ldm.ALGO_DIRECT if algorithm == "direct" else ldm.ALGO_FACTORED)
     if "synth" in name:
         cases = [(g["state"], g["deriv"])]
     else:
@@ -85,14 +86,16 @@ def test_rhs_against_golden(ldm, name):
         assert_rhs_close(o, state, got, want)
 
 
-@pytest.mark.parametrize("name", ["exp_14_4_b", "exp_14_4_c", "exp_14_6_a_080", "synth_g32", "synth_g64"])
-def test_integrals_against_oracle(ldm, name):
+@pytest.mark.parametrize("algorithm", ["direct", "factored"])
+@pytest.mark.parametrize("name", ["exp_14_4_b", "exp_14_4_c", "exp_14_6_a_080", "exp_14_6_b_000", "synth_g32", "synth_g64",
+                                  "synth_g48_narrow_w"])
+def test_integrals_against_oracle(ldm, name, algorithm):
     g = golden(name)
     props, o = problems_from(g, name, ldm)
-    eq = ldm.Equation(props)
+    eq = ldm.Equation(props, algorithm=ldm.ALGO_DIRECT if algorithm == "direct" else ldm.ALGO_FACTORED)
     state = g["state"] if "synth" in name else g["state_k100"]
     wc, mc = eq.integrals(state)
-    wc_ref, mc_ref = o.integrals(state)
+    wc_ref, mc_ref = (float(g["wc"]), g["mc"]) if "synth" in name else o.integrals(state)
     assert abs(wc - wc_ref) <= 1e-13 * abs(wc_ref)
     assert np.all(np.abs(mc - mc_ref) <= 1e-13 * np.abs(mc_ref))
 
@@ -192,6 +195,35 @@ def test_sharded_step_emulated_on_one_device(ldm, world):
     assert np.array_equal(got_C.ravel(), want[1:])
     for r in ranks:
         assert r.get_N() == want[0]
+
+
+def test_direct_path_trajectory(ldm):
+    """the sample-by-sample algorithm through a whole experiment (the default is the factored one)"""
+    g = golden("exp_14_4_b")
+    props, _ = problems_from(g, "exp_14_4_b", ldm)
+    eq = ldm.Equation(props, algorithm=ldm.ALGO_DIRECT)
+    res = ldm.EulerSolver().Solve(eq, ldm.SquaredN, 100, 0.1, eq.GenerateEquilibriumValuesForNAndC(200),
+                                  record=ldm.RECORD_VALUES)
+    assert_states_close(res.Values[:, [0, props.G]], g["obs"])
+    assert_states_close(res.Values[1000], g["final_state"])
+
+
+def test_factored_equals_direct_on_the_16k_grid(ldm):
+    """BASELINE config 3 (G = 128, 16 384 xi-points): the CPU oracle needs ~10 s per evaluation there, so the two
+    GPU algorithms -- each pinned to the oracle at the smaller sizes above -- are compared with each other."""
+    props = ldm.Properties.Generate(1, 0.15, 0.15, 0.4, 0.2, 0.001, 128)
+    direct = ldm.Equation(props, algorithm=ldm.ALGO_DIRECT)
+    factored = ldm.Equation(props, algorithm=ldm.ALGO_FACTORED)
+    g = props.MomentsGrid
+    st = direct.GenerateEquilibriumValuesForNAndC(200)
+    st[1:] *= (1 + 0.5 * np.exp(-(g[:, None] ** 2 + g[None, :] ** 2) / (2 * 0.15 ** 2))).ravel()
+    (w1, m1), (w2, m2) = direct.integrals(st), factored.integrals(st)
+    assert w1 == w2
+    assert np.all(np.abs(m1 - m2) <= 1e-13 * np.abs(m1))
+    for eq in (direct, factored):
+        eq.upload(st)
+        eq.advance(25, 0.1)
+    assert_states_close(factored.download(), direct.download())
 
 
 def test_large_grid_properties(ldm):
