@@ -204,22 +204,25 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- device-resident stepping: inputs already in HBM, L2 flushed before every timed step ----
+    # ---- device-resident stepping: inputs already in HBM.  The timed region is K consecutive Euler steps of one
+    # trajectory (each step consumes the previous step's output, as in the reference's solve loop); L2 is flushed
+    # once, immediately before the region, so the first step starts cold.  CUDA events on the launching stream. ----
     eq.upload(state0)
     eq.advance(args.warmup, DT)
     eq.synchronize()
     launches0 = eq.launches
+    flush.fill_(1)
     barrier()
-    step_ms = []
     with ClockSampler(local_rank) as clocks:
-        for _ in range(args.steps):
-            flush.fill_(1)
-            torch.cuda.synchronize()
-            eq.advance(1, DT)                   # CUDA events bracket the launches on the stream they run on
-            step_ms.append(eq.last_elapsed_ms())
+        eq.advance(args.steps, DT)
+        eq.synchronize()
+        total_ms = eq.last_elapsed_ms()
+        launches = eq.launches - launches0        # kernels of ours launched inside the timed region
+        t_end = time.time() + 1.5                 # keep the same load running until nvidia-smi has sampled it
+        while time.time() < t_end and len(clocks.rows) < 3:
+            eq.advance(args.steps, DT)
+            eq.synchronize()
     barrier()
-    launches = eq.launches - launches0
-    total_ms = float(np.sum(step_ms))
     if world > 1:
         t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -253,7 +256,7 @@ def main():
             "dtype": "f64", "data": "synthetic",
             "config": {"workload": args.workload, "G": props.G, "xi_points": P, "K": props.K, "mM": props.MaxNumForM,
                        "mW": props.MaxNumForW, "S_nz": s_nz, "dt": DT, "parallelism": f"replicas x{world}" if world > 1 else "single",
-                       "l2": "flushed before every timed step (256 MiB fill)", "seed": "C = N^2 (1 + 0.5 exp(-r^2/2 sigma^2)), N = 200"},
+                       "l2": "flushed once immediately before the timed region (256 MiB fill); the K timed steps are consecutive steps of one trajectory", "seed": "C = N^2 (1 + 0.5 exp(-r^2/2 sigma^2)), N = 200"},
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8.0 * (1 + P) / args.steps,
                     "d2h_bytes_per_step": 16.0, "call": "EulerSolver::Solve twin (ldm_solve, record = observables), pinned host buffers, wall clock"},
             "gpu_launches": int(launches),

@@ -50,6 +50,8 @@ struct ldm_context {
     double* d_deriv = nullptr;             // [P] dC/dt
     double* d_partial = nullptr;           // [tiles][P] factored path: per beta-tile sums
     double* d_ring = nullptr;              // [P] factored path: samples between the cutoff circle and the square edge
+    double* d_wc_rows = nullptr;           // [G] factored path: per-row dot products of the WC operator
+    int* d_ring_points = nullptr;          // [P] capacity
     int cur = 0;
     int algo = LDM_ALGO_FACTORED;
     long long launches = 0;
@@ -87,34 +89,53 @@ namespace {
 
 using ldm::DevProblem;
 
-// sum over inside samples of m * C~ for this rank's rows -> d_sum   (the m*C integral, S:277-316)
-void inside_sum(ldm_context* c, const DevProblem& P, const double* C, double* out, cudaStream_t s)
+// The time-invariant list of nodes that need the ring correction, for this rank's rows (see DevProblem).
+void build_ring_points(ldm_context* c)
 {
-    if (c->algo == LDM_ALGO_DIRECT) {
-        ldm::launch_sample_sum(P, ldm::SAMPLES_INSIDE, C, out, s);
-        c->launches += 1;
-        return;
+    const ldm::Tables& t = c->tables;
+    DevProblem& d = c->dev;
+    const int G = d.G, n_off = d.n_off;
+    std::vector<double> lim_min(G, 1e300);
+    for (int x = 0; x < G; x++)
+        for (int o = 0; o < n_off; o++)
+            if (t.axisM.upper[(size_t)x * n_off + o] != 0)
+                lim_min[x] = std::min(lim_min[x], t.axisM.limit[(size_t)x * n_off + o]);
+    std::vector<int> points;
+    const int rows = ldm::local_rows(d);
+    for (int lx = 0; lx < rows; lx++) {
+        const int x = d.rank + d.world * lx;
+        for (int y = 0; y < G; y++)
+            if (lim_min[x] < t.far_inside[y]) points.push_back(lx * G + y);
     }
-    ldm::launch_factored(P, C, c->d_partial, s);
-    ldm::launch_sample_sum(P, ldm::SAMPLES_RING, C, c->d_ring, s);
-    ldm::launch_combine(P, ldm::factored_tiles(P), c->d_partial, c->d_ring, out, s);
-    c->launches += 3;
+    d.n_ring = (int)points.size();
+    if (!points.empty())
+        LDM_CUDA(cudaMemcpy(c->d_ring_points, points.data(), points.size() * sizeof(int), cudaMemcpyHostToDevice));
+    LDM_CUDA(cudaMemset(c->d_ring, 0, c->P() * sizeof(double)));
 }
 
-// one right-hand side at the state (N_cur, C): scalars <- WC, dN; deriv/C_next optional
+// One right-hand side at the state (N_cur, C) for this rank's rows: scalars <- WC, dN; optional outputs:
+// sum_out (inside-sample sums), deriv_out (dC/dt), N_next / C_next (explicit-Euler update with clamp).
 void rhs_and_update(ldm_context* c, const DevProblem& P, const double* C, const double* N_cur, double* N_next, double dt,
-                    double* deriv_out, double* C_next, cudaStream_t s)
+                    double* sum_out, double* deriv_out, double* C_next, cudaStream_t s)
 {
-    inside_sum(c, P, C, c->d_sum, s);
-    ldm::launch_wc(P, C, N_cur, N_next, c->d_scalars, dt, s);
-    ldm::launch_pointwise(P, C, c->d_sum, N_cur, c->d_scalars, dt, deriv_out, C_next, s);
-    c->launches += 2;
+    if (c->algo == LDM_ALGO_DIRECT) {
+        ldm::launch_sample_sum(P, ldm::SAMPLES_INSIDE, C, c->d_sum, s);
+        ldm::launch_wc(P, C, N_cur, N_next, c->d_scalars, dt, s);
+        ldm::launch_pointwise(P, C, c->d_sum, N_cur, c->d_scalars, dt, deriv_out, C_next, s);
+        c->launches += 3;
+        return;
+    }
+    ldm::launch_factored(P, C, c->d_partial, c->d_wc_rows, s);
+    ldm::launch_ring(P, C, c->d_ring, s);
+    ldm::launch_finish_factored(P, C, ldm::factored_tiles(P), c->d_partial, c->d_ring, c->d_wc_rows, N_cur, N_next,
+                                c->d_scalars, dt, sum_out, deriv_out, C_next, s);
+    c->launches += 2 + (P.n_ring > 0 ? 1 : 0);
 }
 
 void step_resident(ldm_context* c, double dt, double* deriv_out)
 {
     const int cur = c->cur, nxt = cur ^ 1;
-    rhs_and_update(c, c->dev, c->d_C[cur], c->d_N + cur, c->d_N + nxt, dt, deriv_out, c->d_C[nxt], c->stream);
+    rhs_and_update(c, c->dev, c->d_C[cur], c->d_N + cur, c->d_N + nxt, dt, nullptr, deriv_out, c->d_C[nxt], c->stream);
     c->cur = nxt;
 }
 
@@ -214,6 +235,11 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         c->d_deriv = c->alloc<double>(P);
         c->d_partial = c->alloc<double>(P * (size_t)ldm::factored_tiles(d));
         c->d_ring = c->alloc<double>(P);
+        c->d_wc_rows = c->alloc<double>((size_t)d.G);
+        c->d_ring_points = c->alloc<int>(P);
+        d.ring_points = c->d_ring_points;
+        d.far_inside = c->upload(t.far_inside);
+        build_ring_points(c.get());
         LDM_CUDA(cudaMemsetAsync(c->d_C[0], 0, P * sizeof(double), c->stream));
         LDM_CUDA(cudaMemsetAsync(c->d_C[1], 0, P * sizeof(double), c->stream));
         LDM_CUDA(cudaMemsetAsync(c->d_N, 0, 2 * sizeof(double), c->stream));
@@ -243,7 +269,7 @@ int ldm_rhs(ldm_handle h, const double* state, double* deriv)
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
         upload_state(h, state);
-        rhs_and_update(h, h->dev, h->d_C[0], h->d_N, nullptr, 0.0, h->d_deriv, nullptr, h->stream);
+        rhs_and_update(h, h->dev, h->d_C[0], h->d_N, nullptr, 0.0, nullptr, h->d_deriv, nullptr, h->stream);
         LDM_CUDA(cudaGetLastError());
         LDM_CUDA(cudaMemcpyAsync(deriv, h->d_scalars + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         LDM_CUDA(cudaMemcpyAsync(deriv + 1, h->d_deriv, h->P() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -257,9 +283,7 @@ int ldm_integrals(ldm_handle h, const double* state, double* WC, double* MC)
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
         upload_state(h, state);
-        inside_sum(h, h->dev, h->d_C[0], h->d_sum, h->stream);
-        ldm::launch_wc(h->dev, h->d_C[0], h->d_N, nullptr, h->d_scalars, 0.0, h->stream);
-        h->launches += 1;
+        rhs_and_update(h, h->dev, h->d_C[0], h->d_N, nullptr, 0.0, h->d_sum, nullptr, nullptr, h->stream);
         LDM_CUDA(cudaGetLastError());
         LDM_CUDA(cudaMemcpyAsync(WC, h->d_scalars, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         std::vector<double> sum;
@@ -341,7 +365,7 @@ int ldm_solve(ldm_handle h, const double* init, double dt, double t_max, int rec
                 const bool want_deriv = (record == LDM_RECORD_ALL) || (last && derivs);
                 if (last && !want_deriv) break;
                 if (last) {       // the reference evaluates the equation once more at the final point (S:582-583)
-                    rhs_and_update(h, h->dev, Ccur, Ncur, nullptr, dt, h->d_deriv, nullptr, h->stream);
+                    rhs_and_update(h, h->dev, Ccur, Ncur, nullptr, dt, nullptr, h->d_deriv, nullptr, h->stream);
                 } else {
                     step_resident(h, dt, want_deriv ? h->d_deriv : nullptr);
                 }
@@ -472,7 +496,11 @@ int ldm_shard_configure(ldm_handle h, int rank, int world)
     h->dev.world = world;
     h->dev.rank = rank;
     h->dev.rows_per_rank = (h->dev.G + world - 1) / world;
-    return LDM_OK;
+    return guarded([&] {
+        LDM_CUDA(cudaSetDevice(h->device));
+        LDM_CUDA(cudaStreamSynchronize(h->stream));
+        build_ring_points(h);
+    });
 }
 
 int ldm_shard_rows_per_rank(ldm_handle h) { return h ? h->dev.rows_per_rank : 0; }
@@ -504,7 +532,7 @@ int ldm_shard_step(ldm_handle h, const double* d_C_gathered, double* d_C_shard_o
         LDM_CUDA(cudaSetDevice(h->device));
         cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
         const int cur = h->cur, nxt = cur ^ 1;
-        rhs_and_update(h, h->dev, d_C_gathered, h->d_N + cur, h->d_N + nxt, dt, nullptr, d_C_shard_out, s);
+        rhs_and_update(h, h->dev, d_C_gathered, h->d_N + cur, h->d_N + nxt, dt, nullptr, nullptr, d_C_shard_out, s);
         h->cur = nxt;
         LDM_CUDA(cudaGetLastError());
     });

@@ -26,6 +26,11 @@ struct DevProblem {
     const double* w_nodes;     // [G][G]  w(xi)                                            (Solver.cpp:490)
     const double* out_weight;  // [G][G]  sum of m over this node's samples beyond the cutoff
     const double* wc_operator; // [G][G]  WC = hh * (<wc_operator, C> + N^2 wc_outside)   (Solver.cpp:265-274)
+    // ring correction of the factored path: the nodes that own at least one sample inside the grid square but
+    // outside the cutoff circle (time-invariant list, this rank's rows only), packed as local_row * G + y
+    const int* ring_points;
+    int n_ring;
+    const double* far_inside;  // [G] largest in-square sample abscissa of each node (-1: none)
 };
 
 // Which samples sample_sum accumulates (all use the same (x,o_i) x (y,o_j) enumeration):
@@ -55,10 +60,19 @@ void launch_wc(const DevProblem& P, const double* C, const double* N_cur, double
 void launch_pointwise(const DevProblem& P, const double* C, const double* inside_sum, const double* N_cur,
                       const double* scalars, double dt, double* deriv_out, double* C_next, cudaStream_t stream);
 
+// Closing kernel of the factored path: inside_sum = sum_tiles partial - ring, WC from the per-row dot products,
+// the first-moment equation with its update (block 0), then the same pointwise assembly/update as above.
+// sum_out (may be NULL) receives inside_sum for ldm_integrals.
+void launch_finish_factored(const DevProblem& P, const double* C, int tiles, const double* partial, const double* ring,
+                            const double* wc_rows, const double* N_cur, double* N_next, double* scalars, double dt,
+                            double* sum_out, double* deriv_out, double* C_next, cudaStream_t stream);
+
+// ring[lx][y] for the nodes in P.ring_points (other entries of `ring` stay zero)
+void launch_ring(const DevProblem& P, const double* C, double* ring, cudaStream_t stream);
+
 // Factored path (ldm_factored.cu): partial[tile][local_rows][G] <- per beta-tile sums over all samples inside the
 // grid square; combine: inside_sum = sum_tiles partial - ring.
 int factored_tiles(const DevProblem& P);
-void launch_factored(const DevProblem& P, const double* C, double* partial, cudaStream_t stream);
-void launch_combine(const DevProblem& P, int tiles, const double* partial, const double* ring, double* out, cudaStream_t stream);
+void launch_factored(const DevProblem& P, const double* C, double* partial, double* wc_rows, cudaStream_t stream);
 
 }  // namespace ldm

@@ -24,6 +24,13 @@ namespace ldm {
 
 namespace {
 
+__device__ __forceinline__ double warp_sum(double v)
+{
+    #pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);   // fixed butterfly
+    return v;
+}
+
 template <int BM, int BN, int TM, int TN, int BK>
 struct FactoredConfig {
     static constexpr int TYN = BM / TM;            // thread rows
@@ -34,9 +41,9 @@ struct FactoredConfig {
     static constexpr int Q_PER_THREAD = (BK * BM + NT - 1) / NT;
     static_assert(BM % TM == 0 && BN % TN == 0 && TN % 2 == 0, "tile shape");
     static_assert((BK * BN) % NT == 0, "E chunk must divide evenly over the threads");
-    static size_t smem_bytes(int G, int groups)
+    static size_t smem_bytes(int G)
     {
-        return sizeof(double) * ((size_t)2 * BK * BM + (size_t)2 * BK * BN + (size_t)BM * HS_LD + (size_t)G * (1 + groups));
+        return sizeof(double) * ((size_t)2 * BK * BM + (size_t)2 * BK * BN + (size_t)BM * HS_LD + (size_t)G);
     }
 };
 
@@ -48,7 +55,7 @@ __device__ __forceinline__ int folded_offset(int A, int n_fold, int alpha, int f
 
 template <int BM, int BN, int TM, int TN, int BK>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
-factored_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__ partial, int groups)
+factored_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__ partial, double* __restrict__ wc_rows)
 {
     using Cfg = FactoredConfig<BM, BN, TM, TN, BK>;
     constexpr int TYN = Cfg::TYN, TXN = Cfg::TXN, NT = Cfg::NT, HS_LD = Cfg::HS_LD;
@@ -65,7 +72,6 @@ factored_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__
     double* Es = Qs + 2 * BK * BM;                        // [2][BK][BN]
     double* Hs = Es + 2 * BK * BN;                        // [BM][HS_LD]
     double* acc_y = Hs + BM * HS_LD;                      // [G]
-    double* part = acc_y + G;                             // [groups][G]
 
     for (int y = tid; y < G; y += NT) acc_y[y] = 0.0;
 
@@ -165,58 +171,58 @@ factored_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__
                 Hs[(i * TYN + ty) * HS_LD + 1 + (j / 2) * (2 * TXN) + tx * 2 + (j & 1)] = acc[i][j];
         __syncthreads();
 
-        // y side: every tap pair (u-1, u) whose upper node u falls in this chunk
+        // y side: every tap pair (u-1, u) whose upper node u falls in this chunk.  A warp owns one y; its lanes
+        // walk the (beta row, fold) pairs so that the interpolation-table reads are contiguous.
         const int rows_here = min(BM, A - b0);
-        for (int idx = tid; idx < G * groups; idx += NT) {
-            const int grp = idx / G, y = idx - grp * G;
+        const int pairs = rows_here * n_fold;
+        for (int y = tid / 32; y < G; y += NT / 32) {
             const int* uy_row = P.upper + (size_t)y * n_off;
             const double* wy_row = P.weight + (size_t)y * n_off;
             double s = 0.0;
-            for (int bm = grp; bm < rows_here; bm += groups) {
-                const double* hrow = Hs + bm * HS_LD + 1 - q0;
-                for (int f = 0; f < n_fold; f++) {
-                    const int o = folded_offset(A, n_fold, b0 + bm, f);
-                    const int u = uy_row[o];
-                    if (u >= q0 && u < q0 + BN && u != 0) {
-                        const double w = wy_row[o];
-                        s += hrow[u - 1] * (1.0 - w) + hrow[u] * w;
-                    }
+            for (int t = tid % 32; t < pairs; t += 32) {
+                const int f = t / rows_here, bm = t - f * rows_here;
+                const int o = folded_offset(A, n_fold, b0 + bm, f);
+                const int u = uy_row[o];
+                if (u >= q0 && u < q0 + BN && u != 0) {
+                    const double w = wy_row[o];
+                    const double* hrow = Hs + bm * HS_LD + 1 - q0;
+                    s += hrow[u - 1] * (1.0 - w) + hrow[u] * w;
                 }
             }
-            part[grp * G + y] = s;
+            s = warp_sum(s);
+            if (tid % 32 == 0) acc_y[y] += s;
         }
-        __syncthreads();
-        for (int y = tid; y < G; y += NT) {
-            double s = acc_y[y];
-            for (int grp = 0; grp < groups; grp++) s += part[grp * G + y];    // fixed order
-            acc_y[y] = s;
-        }
-        if (chunk + 1 < n_chunks)
+        if (chunk + 1 < n_chunks) {
+            __syncthreads();
             for (int bm = tid; bm < BM; bm += NT) Hs[bm * HS_LD] = Hs[bm * HS_LD + BN];   // carry the halo column
+        }
         __syncthreads();
     }
 
     double* out = partial + ((size_t)blockIdx.x * local_rows(P) + lx) * G;
     for (int y = tid; y < G; y += NT) out[y] = acc_y[y];
-}
 
-// inside_sum[lx][y] = sum_t partial[t][lx][y] - ring[lx][y]
-__global__ void __launch_bounds__(256)
-combine_kernel(int n, int tiles, const double* __restrict__ partial, const double* __restrict__ ring, double* __restrict__ out)
-{
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= n) return;
-    double s = 0.0;
-    for (int t = 0; t < tiles; t++) s += partial[(size_t)t * n + q];
-    out[q] = s - ring[q];
+    // WC = <wc_operator, C> (Solver.cpp:265-274) row by row, folded into this launch: the first beta-tile of local
+    // row lx covers rows lx*world .. lx*world+world-1 (every rank reduces the full operator, so no all-reduce)
+    if (blockIdx.x == 0 && wc_rows != nullptr) {
+        for (int r = tid / 32; r < P.world; r += NT / 32) {
+            const int xr = lx * P.world + r;
+            if (xr >= G) continue;
+            const double* op = P.wc_operator + (size_t)xr * G;
+            const double* crow = C + (size_t)row_slot(P, xr) * G;
+            double s = 0.0;
+            for (int y = tid % 32; y < G; y += 32) s += op[y] * crow[y];
+            s = warp_sum(s);
+            if (tid % 32 == 0) wc_rows[xr] = s;
+        }
+    }
 }
 
 template <int BM, int BN, int TM, int TN, int BK>
-void launch_variant(const DevProblem& P, const double* C, double* partial, int tiles, cudaStream_t stream)
+void launch_variant(const DevProblem& P, const double* C, double* partial, double* wc_rows, int tiles, cudaStream_t stream)
 {
     using Cfg = FactoredConfig<BM, BN, TM, TN, BK>;
-    const int groups = Cfg::NT >= P.G ? Cfg::NT / P.G : 1;
-    const size_t smem = Cfg::smem_bytes(P.G, groups);
+    const size_t smem = Cfg::smem_bytes(P.G);
     static bool configured[64] = {};                 // the opt-in is per device
     int device = 0;
     cudaGetDevice(&device);
@@ -225,7 +231,7 @@ void launch_variant(const DevProblem& P, const double* C, double* partial, int t
         configured[device & 63] = true;
     }
     dim3 grid(tiles, local_rows(P));
-    factored_kernel<BM, BN, TM, TN, BK><<<grid, Cfg::NT, smem, stream>>>(P, C, partial, groups);
+    factored_kernel<BM, BN, TM, TN, BK><<<grid, Cfg::NT, smem, stream>>>(P, C, partial, wc_rows);
 }
 
 }  // namespace
@@ -244,24 +250,18 @@ int factored_tiles(const DevProblem& P)
     return (P.A + bm - 1) / bm;
 }
 
-void launch_factored(const DevProblem& P, const double* C, double* partial, cudaStream_t stream)
+void launch_factored(const DevProblem& P, const double* C, double* partial, double* wc_rows, cudaStream_t stream)
 {
     const int bm = factored_tile_rows(P);
     const int tiles = factored_tiles(P);
     const bool narrow = P.G <= 64;
     if (bm == 80) {
-        if (narrow) launch_variant<80, 64, 5, 8, 16>(P, C, partial, tiles, stream);
-        else launch_variant<80, 128, 5, 8, 16>(P, C, partial, tiles, stream);
+        if (narrow) launch_variant<80, 64, 5, 8, 16>(P, C, partial, wc_rows, tiles, stream);
+        else launch_variant<80, 128, 5, 8, 16>(P, C, partial, wc_rows, tiles, stream);
     } else {
-        if (narrow) launch_variant<40, 64, 5, 8, 16>(P, C, partial, tiles, stream);
-        else launch_variant<40, 128, 5, 8, 16>(P, C, partial, tiles, stream);
+        if (narrow) launch_variant<40, 64, 5, 8, 16>(P, C, partial, wc_rows, tiles, stream);
+        else launch_variant<40, 128, 5, 8, 16>(P, C, partial, wc_rows, tiles, stream);
     }
-}
-
-void launch_combine(const DevProblem& P, int tiles, const double* partial, const double* ring, double* out, cudaStream_t stream)
-{
-    const int n = local_rows(P) * P.G;
-    combine_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, tiles, partial, ring, out);
 }
 
 }  // namespace ldm

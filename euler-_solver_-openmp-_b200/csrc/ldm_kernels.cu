@@ -163,6 +163,115 @@ pointwise_kernel(DevProblem P, const double* __restrict__ C, const double* __res
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Ring correction of the factored path: one CTA per listed node, warps split the o_i range, lanes the o_j
+// range; accumulates m * bilinear(C) over the samples inside the grid square but beyond the cutoff circle.
+// ------------------------------------------------------------------------------------------------
+constexpr int kRingWarps = 8;
+
+__global__ void __launch_bounds__(kWarp * kRingWarps)
+ring_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__ ring)
+{
+    __shared__ double part[kRingWarps];
+    const int G = P.G, n_off = P.n_off, A = P.A;
+    const int packed = P.ring_points[blockIdx.x];
+    const int lx = packed / G, y = packed - lx * G;
+    const int x = P.rank + P.world * lx;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double far_y = P.far_inside[y];
+    const double* lim_row = P.limit + (size_t)x * n_off;
+    const double* wx_row = P.weight + (size_t)x * n_off;
+    const int* ux_row = P.upper + (size_t)x * n_off;
+    const double* sy_row = P.s + (size_t)y * n_off;
+    const double* wy_row = P.weight + (size_t)y * n_off;
+    const int* uy_row = P.upper + (size_t)y * n_off;
+
+    double acc = 0.0;
+    for (int oi = warp; oi < n_off; oi += kRingWarps) {
+        const double lim = lim_row[oi];
+        const int ux = ux_row[oi];
+        if (ux == 0 || lim >= far_y) continue;          // this sample row has nothing between circle and square edge
+        const double wx = wx_row[oi], ux_w = 1.0 - wx;
+        const double* q_row = P.quadrant + (size_t)P.alpha[oi] * A;
+        const double* c_lo = C + (size_t)row_slot(P, ux - 1) * G;
+        const double* c_hi = C + (size_t)row_slot(P, ux) * G;
+        for (int oj = lane; oj < n_off; oj += kWarp) {
+            const int uy = uy_row[oj];
+            if (uy != 0 && !(sy_row[oj] <= lim)) {
+                const double wy = wy_row[oj];
+                const double lo = c_lo[uy - 1] * ux_w + c_hi[uy - 1] * wx;
+                const double hi = c_lo[uy] * ux_w + c_hi[uy] * wx;
+                acc += q_row[P.alpha[oj]] * (lo * (1.0 - wy) + hi * wy);
+            }
+        }
+    }
+    acc = warp_sum(acc);
+    if (lane == 0) part[warp] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double s = 0.0;
+        for (int w = 0; w < kRingWarps; w++) s += part[w];      // fixed order
+        ring[packed] = s;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Closing kernel of the factored path (see ldm_device.h).  Every CTA reduces the G per-row dot products of WC
+// in the same fixed order, so all CTAs hold the same WC; block 0 also advances the first moment.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+finish_factored_kernel(DevProblem P, const double* __restrict__ C, int tiles, const double* __restrict__ partial,
+                       const double* __restrict__ ring, const double* __restrict__ wc_rows,
+                       const double* __restrict__ N_cur, double* __restrict__ N_next, double* __restrict__ scalars, double dt,
+                       double* __restrict__ sum_out, double* __restrict__ deriv_out, double* __restrict__ C_next)
+{
+    __shared__ double red[256 / kWarp];
+    __shared__ double wc_shared;
+    const int G = P.G;
+    double acc = 0.0;
+    for (int r = threadIdx.x; r < G; r += 256) acc += wc_rows[r];
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    const double N = N_cur[0];
+    if (threadIdx.x == 0) {
+        double v = 0.0;
+        for (int w = 0; w < 256 / kWarp; w++) v += red[w];
+        const double WC = (v + (N * N) * P.wc_outside) * P.hh;                      // S:311, S:314
+        wc_shared = WC;
+        if (blockIdx.x == 0) {
+            double dN = __dmul_rn(N, __dsub_rn(P.b, P.d));                          // S:446
+            dN = __dsub_rn(dN, __dadd_rn(0.0, __dmul_rn(P.dd, WC)));                // S:450-451
+            scalars[0] = WC;
+            scalars[1] = dN;
+            if (N_next) {
+                const double v1 = __dadd_rn(N, __dmul_rn(dN, dt));                  // S:577
+                N_next[0] = v1 < 0.0 ? 0.0 : v1;                                    // S:578-580
+            }
+        }
+    }
+    __syncthreads();
+    const double WC = wc_shared;
+
+    const int n = local_rows(P) * G;
+    const int ql = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ql >= n) return;
+    const int lx = ql / G, y = ql - lx * G;
+    const int q = (P.rank + P.world * lx) * G + y;
+    double inside = 0.0;
+    for (int t = 0; t < tiles; t++) inside += partial[(size_t)t * n + ql];
+    inside -= ring[ql];
+    if (sum_out) sum_out[ql] = inside;
+    const double c = C[(size_t)(P.rank * P.rows_per_rank + lx) * G + y];
+    const double mc = (inside + (N * N) * P.out_weight[q]) * P.hh;
+    const double dc = second_moment_rhs(P, mc, c, N, WC, P.m_nodes[q], P.w_nodes[q]);
+    if (deriv_out) deriv_out[ql] = dc;
+    if (C_next) {
+        const double v = __dadd_rn(c, __dmul_rn(dc, dt));
+        C_next[ql] = v < 0.0 ? 0.0 : v;
+    }
+}
+
 __global__ void record_observables_kernel(DevProblem P, const double* __restrict__ N_cur, const double* __restrict__ C,
                                           double* __restrict__ obs_row)
 {
@@ -175,6 +284,20 @@ __global__ void record_observables_kernel(DevProblem P, const double* __restrict
 void launch_record_observables(const DevProblem& P, const double* N_cur, const double* C, double* obs_row, cudaStream_t stream)
 {
     record_observables_kernel<<<1, 1, 0, stream>>>(P, N_cur, C, obs_row);
+}
+
+void launch_ring(const DevProblem& P, const double* C, double* ring, cudaStream_t stream)
+{
+    if (P.n_ring > 0) ring_kernel<<<P.n_ring, kWarp * kRingWarps, 0, stream>>>(P, C, ring);
+}
+
+void launch_finish_factored(const DevProblem& P, const double* C, int tiles, const double* partial, const double* ring,
+                            const double* wc_rows, const double* N_cur, double* N_next, double* scalars, double dt,
+                            double* sum_out, double* deriv_out, double* C_next, cudaStream_t stream)
+{
+    const int n = local_rows(P) * P.G;
+    finish_factored_kernel<<<(n + 255) / 256, 256, 0, stream>>>(P, C, tiles, partial, ring, wc_rows, N_cur, N_next, scalars, dt,
+                                                               sum_out, deriv_out, C_next);
 }
 
 void launch_sample_sum(const DevProblem& P, SampleMode mode, const double* C, double* out, cudaStream_t stream)

@@ -229,6 +229,11 @@ void build_tables(const ldm_problem& p, Tables& t)
     if (non_monotone) throw std::runtime_error("hypot is not monotone across the sample set near the cutoff");
     t.s_max = 0;
     for (double v : sorted) if (v <= p.cutoff) t.s_max = v;
+    t.far_inside.assign((size_t)G, -1.0);
+    for (int x = 0; x < G; x++)
+        for (int o = 0; o < n_off; o++)
+            if (ax.upper[(size_t)x * n_off + o] != 0)
+                t.far_inside[x] = std::max(t.far_inside[x], ax.s[(size_t)x * n_off + o]);
     char note[160];
     std::snprintf(note, sizeof note, "samples=%zu distinct=%zu closest |hypot-cutoff|/cutoff=%.3e", cells, sorted.size(), closest);
     t.census = note;

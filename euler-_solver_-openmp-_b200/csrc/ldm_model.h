@@ -55,6 +55,7 @@ struct Tables {
     OffsetSet offM;                // the m-kernel quadrature
     AxisTable axisM;               // ... on the moment nodes
     double s_max = 0;              // largest abscissa value that is still <= cutoff (or cutoff)
+    std::vector<double> far_inside;    // G: largest sample abscissa of a node that is still inside the grid (-1: none)
     std::vector<double> m_nodes;   // G*G: BilinearInterpolation(KernelsGrid, M, g_x, g_y, 3 sigma_M, Zero)  (S:469)
     std::vector<double> w_nodes;   // G*G: same for W (S:490)
     std::vector<double> wc_operator;   // G*G: WC = h^2 * (sum wc_operator .* C + N^2 * wc_outside)   (S:265-274)
