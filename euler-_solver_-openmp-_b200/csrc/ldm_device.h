@@ -43,7 +43,10 @@ enum SampleMode {
 // Scalars of one step, device resident: [0] WC, [1] dN/dt
 constexpr int kScalars = 4;
 
-__host__ __device__ inline int row_slot(const DevProblem& P, int x) { return (x % P.world) * P.rows_per_rank + x / P.world; }
+__host__ __device__ inline int row_slot(const DevProblem& P, int x)
+{
+    return P.world == 1 ? x : (x % P.world) * P.rows_per_rank + x / P.world;
+}
 __host__ __device__ inline int local_rows(const DevProblem& P) { return (P.G - P.rank + P.world - 1) / P.world; }
 
 // C is always the full pair density in gathered layout; `out`, inside_sum, deriv_out, C_next are

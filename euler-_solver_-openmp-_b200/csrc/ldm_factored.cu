@@ -41,9 +41,12 @@ struct FactoredConfig {
     static constexpr int Q_PER_THREAD = (BK * BM + NT - 1) / NT;
     static_assert(BM % TM == 0 && BN % TN == 0 && TN % 2 == 0, "tile shape");
     static_assert((BK * BN) % NT == 0, "E chunk must divide evenly over the threads");
-    static size_t smem_bytes(int G)
+    static_assert(NT % BN == 0 && BK % (NT / BN) == 0, "a thread keeps one E column");
+    static size_t smem_bytes(int G, int A)
     {
-        return sizeof(double) * ((size_t)2 * BK * BM + (size_t)2 * BK * BN + (size_t)BM * HS_LD + (size_t)G);
+        const size_t a_pad = (size_t)((A + BK - 1) / BK) * BK;
+        return sizeof(double) * ((size_t)2 * BK * BM + (size_t)2 * BK * BN + (size_t)BM * HS_LD + (size_t)((G + 3) & ~3) + 4 * a_pad) +
+               sizeof(int) * 4 * a_pad;
     }
 };
 
@@ -59,6 +62,7 @@ factored_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__
 {
     using Cfg = FactoredConfig<BM, BN, TM, TN, BK>;
     constexpr int TYN = Cfg::TYN, TXN = Cfg::TXN, NT = Cfg::NT, HS_LD = Cfg::HS_LD;
+    constexpr int K_STRIDE = NT / BN;                     // E rows covered by one pass of the CTA's threads
     const int G = P.G, A = P.A, n_off = P.n_off;
     const int n_fold = n_off / A;
     const int lx = blockIdx.y;
@@ -66,67 +70,72 @@ factored_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__
     const int b0 = blockIdx.x * BM;                       // first beta row of this tile
     const int tid = threadIdx.x;
     const int tx = tid % TXN, ty = tid / TXN;
+    const int n_kc = (A + BK - 1) / BK;
+    const int n_chunks = (G + BN - 1) / BN;
+    const int A_pad = n_kc * BK;
 
-    extern __shared__ __align__(16) double smem[];
+    extern __shared__ __align__(32) double smem[];
     double* Qs = smem;                                    // [2][BK][BM]
     double* Es = Qs + 2 * BK * BM;                        // [2][BK][BN]
     double* Hs = Es + 2 * BK * BN;                        // [BM][HS_LD]
     double* acc_y = Hs + BM * HS_LD;                      // [G]
+    double* tap_w = acc_y + ((G + 3) & ~3);               // [A_pad][4] (32-byte aligned): weights of the (at most) four C rows feeding E[alpha]
+    int* tap_row = reinterpret_cast<int*>(tap_w + 4 * A_pad);   // [A_pad][4]: their offsets (slot * G)
 
+    // x-side interpolation taps of this row, once per CTA: E[alpha][q] = sum_t tap_w[alpha][t] * C[tap_row[alpha][t] + q]
+    for (int t = tid; t < A_pad * 2; t += NT) {
+        const int alpha = t >> 1, f = t & 1;
+        double w_lo = 0.0, w_hi = 0.0;
+        int r_lo = 0, r_hi = 0;
+        if (alpha < A && f < n_fold) {
+            const int o = folded_offset(A, n_fold, alpha, f);
+            const int u = P.upper[(size_t)x * n_off + o];
+            if (u != 0) {
+                const double w = P.weight[(size_t)x * n_off + o];
+                w_lo = 1.0 - w; w_hi = w;
+                r_lo = row_slot(P, u - 1) * G; r_hi = row_slot(P, u) * G;
+            }
+        }
+        tap_w[alpha * 4 + f * 2] = w_lo; tap_w[alpha * 4 + f * 2 + 1] = w_hi;
+        tap_row[alpha * 4 + f * 2] = r_lo; tap_row[alpha * 4 + f * 2 + 1] = r_hi;
+    }
     for (int y = tid; y < G; y += NT) acc_y[y] = 0.0;
-
-    const int* ux_row = P.upper + (size_t)x * n_off;
-    const double* wx_row = P.weight + (size_t)x * n_off;
-    const int n_kc = (A + BK - 1) / BK;
-    const int n_chunks = (G + BN - 1) / BN;
+    __syncthreads();
 
     double e_reg[Cfg::E_PER_THREAD];
     double q_reg[Cfg::Q_PER_THREAD];
+    const int e_col = tid % BN, e_k0 = tid / BN;          // this thread's E column and first row within a chunk
 
     for (int chunk = 0; chunk < n_chunks; chunk++) {
         const int q0 = chunk * BN;
+        const int q = q0 + e_col;
+        const double* c_col = C + (q < G ? q : G - 1);    // clamped: columns beyond G are multiplied by 0 below
+        const double live = q < G ? 1.0 : 0.0;
 
-        // E chunk element e -> (k = e / BN, column = e % BN); consecutive threads take consecutive columns
         auto load_chunk = [&](int kc) {
             #pragma unroll
             for (int r = 0; r < Cfg::E_PER_THREAD; r++) {
-                const int e = r * NT + tid;
-                const int k = e / BN, col = e - k * BN;
-                const int alpha = kc * BK + k, q = q0 + col;
-                double v = 0.0;
-                if (alpha < A && q < G) {
-                    for (int f = 0; f < n_fold; f++) {
-                        const int o = folded_offset(A, n_fold, alpha, f);
-                        const int u = ux_row[o];
-                        if (u != 0) {
-                            const double w = wx_row[o];
-                            v += C[(size_t)row_slot(P, u - 1) * G + q] * (1.0 - w) + C[(size_t)row_slot(P, u) * G + q] * w;
-                        }
-                    }
-                }
-                e_reg[r] = v;
+                const int alpha = kc * BK + r * K_STRIDE + e_k0;           // < A_pad; rows beyond A carry zero weights
+                const double4 wa = *reinterpret_cast<const double4*>(tap_w + alpha * 4);
+                const int4 ra = *reinterpret_cast<const int4*>(tap_row + alpha * 4);
+                e_reg[r] = (c_col[ra.x] * wa.x + c_col[ra.y] * wa.y) + (c_col[ra.z] * wa.z + c_col[ra.w] * wa.w);
             }
             #pragma unroll
             for (int r = 0; r < Cfg::Q_PER_THREAD; r++) {
                 const int e = r * NT + tid;
-                const int bm = e / BK, k = e - bm * BK;          // consecutive threads walk alpha: coalesced rows of Q
-                const int beta = b0 + bm, alpha = kc * BK + k;
-                q_reg[r] = (e < BK * BM && beta < A && alpha < A) ? P.quadrant[(size_t)beta * A + alpha] : 0.0;
+                const int k = e / BM, bm = e - k * BM;     // Q is symmetric: read it alpha-major so consecutive threads
+                const int beta = b0 + bm, alpha = kc * BK + k;   // take consecutive beta (coalesced, conflict-free store)
+                q_reg[r] = (e < BK * BM && beta < A && alpha < A) ? P.quadrant[(size_t)alpha * A + beta] : 0.0;
             }
         };
         auto store_chunk = [&](int buf) {
             #pragma unroll
-            for (int r = 0; r < Cfg::E_PER_THREAD; r++) {
-                const int e = r * NT + tid;
-                Es[buf * BK * BN + e] = e_reg[r];
-            }
+            for (int r = 0; r < Cfg::E_PER_THREAD; r++)
+                Es[buf * BK * BN + (r * K_STRIDE + e_k0) * BN + e_col] = e_reg[r] * live;
             #pragma unroll
             for (int r = 0; r < Cfg::Q_PER_THREAD; r++) {
                 const int e = r * NT + tid;
-                if (e < BK * BM) {
-                    const int bm = e / BK, k = e - bm * BK;
-                    Qs[buf * BK * BM + k * BM + bm] = q_reg[r];
-                }
+                if (e < BK * BM) Qs[buf * BK * BM + e] = q_reg[r];
             }
         };
 
@@ -171,22 +180,25 @@ factored_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__
                 Hs[(i * TYN + ty) * HS_LD + 1 + (j / 2) * (2 * TXN) + tx * 2 + (j & 1)] = acc[i][j];
         __syncthreads();
 
-        // y side: every tap pair (u-1, u) whose upper node u falls in this chunk.  A warp owns one y; its lanes
-        // walk the (beta row, fold) pairs so that the interpolation-table reads are contiguous.
+        // y side: every tap pair (u-1, u) whose upper node u falls in this chunk.  A warp owns one y at a time; its
+        // lanes walk the beta rows of one fold, so the interpolation-table reads are contiguous.
         const int rows_here = min(BM, A - b0);
-        const int pairs = rows_here * n_fold;
+        const double* hbase = Hs + 1 - q0;
         for (int y = tid / 32; y < G; y += NT / 32) {
             const int* uy_row = P.upper + (size_t)y * n_off;
             const double* wy_row = P.weight + (size_t)y * n_off;
             double s = 0.0;
-            for (int t = tid % 32; t < pairs; t += 32) {
-                const int f = t / rows_here, bm = t - f * rows_here;
-                const int o = folded_offset(A, n_fold, b0 + bm, f);
-                const int u = uy_row[o];
-                if (u >= q0 && u < q0 + BN && u != 0) {
+            for (int f = 0; f < n_fold; f++) {
+                const int o0 = folded_offset(A, n_fold, b0, f);
+                const int dir = (n_fold == 2 && f == 0) ? -1 : 1;
+                for (int bm = tid % 32; bm < rows_here; bm += 32) {
+                    const int o = o0 + dir * bm;
+                    const int u = uy_row[o];
                     const double w = wy_row[o];
-                    const double* hrow = Hs + bm * HS_LD + 1 - q0;
-                    s += hrow[u - 1] * (1.0 - w) + hrow[u] * w;
+                    if (u >= q0 && u < q0 + BN && u != 0) {
+                        const double* hrow = hbase + bm * HS_LD;
+                        s += hrow[u - 1] * (1.0 - w) + hrow[u] * w;
+                    }
                 }
             }
             s = warp_sum(s);
@@ -222,7 +234,7 @@ template <int BM, int BN, int TM, int TN, int BK>
 void launch_variant(const DevProblem& P, const double* C, double* partial, double* wc_rows, int tiles, cudaStream_t stream)
 {
     using Cfg = FactoredConfig<BM, BN, TM, TN, BK>;
-    const size_t smem = Cfg::smem_bytes(P.G);
+    const size_t smem = Cfg::smem_bytes(P.G, P.A);
     static bool configured[64] = {};                 // the opt-in is per device
     int device = 0;
     cudaGetDevice(&device);

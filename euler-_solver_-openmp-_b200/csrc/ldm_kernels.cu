@@ -172,6 +172,7 @@ constexpr int kRingWarps = 8;
 __global__ void __launch_bounds__(kWarp * kRingWarps)
 ring_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__ ring)
 {
+    extern __shared__ __align__(16) double ring_smem[];
     __shared__ double part[kRingWarps];
     const int G = P.G, n_off = P.n_off, A = P.A;
     const int packed = P.ring_points[blockIdx.x];
@@ -179,29 +180,50 @@ ring_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__ rin
     const int x = P.rank + P.world * lx;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const double far_y = P.far_inside[y];
-    const double* lim_row = P.limit + (size_t)x * n_off;
-    const double* wx_row = P.weight + (size_t)x * n_off;
-    const int* ux_row = P.upper + (size_t)x * n_off;
-    const double* sy_row = P.s + (size_t)y * n_off;
-    const double* wy_row = P.weight + (size_t)y * n_off;
-    const int* uy_row = P.upper + (size_t)y * n_off;
+
+    // this node's y-side sample row, staged once: abscissa, weight, upper node, kernel column
+    double* sy = ring_smem;                          // [n_off]
+    double* wy = sy + n_off;                         // [n_off]
+    int* uy = reinterpret_cast<int*>(wy + n_off);    // [n_off]
+    int* ay = uy + n_off;                            // [n_off]
+    for (int o = threadIdx.x; o < n_off; o += blockDim.x) {
+        sy[o] = P.s[(size_t)y * n_off + o];
+        wy[o] = P.weight[(size_t)y * n_off + o];
+        uy[o] = P.upper[(size_t)y * n_off + o];
+        ay[o] = P.alpha[o];
+    }
+    __syncthreads();
 
     double acc = 0.0;
-    for (int oi = warp; oi < n_off; oi += kRingWarps) {
-        const double lim = lim_row[oi];
-        const int ux = ux_row[oi];
-        if (ux == 0 || lim >= far_y) continue;          // this sample row has nothing between circle and square edge
-        const double wx = wx_row[oi], ux_w = 1.0 - wx;
-        const double* q_row = P.quadrant + (size_t)P.alpha[oi] * A;
-        const double* c_lo = C + (size_t)row_slot(P, ux - 1) * G;
-        const double* c_hi = C + (size_t)row_slot(P, ux) * G;
-        for (int oj = lane; oj < n_off; oj += kWarp) {
-            const int uy = uy_row[oj];
-            if (uy != 0 && !(sy_row[oj] <= lim)) {
-                const double wy = wy_row[oj];
-                const double lo = c_lo[uy - 1] * ux_w + c_hi[uy - 1] * wx;
-                const double hi = c_lo[uy] * ux_w + c_hi[uy] * wx;
-                acc += q_row[P.alpha[oj]] * (lo * (1.0 - wy) + hi * wy);
+    for (int base = warp * kWarp; base < n_off; base += kRingWarps * kWarp) {
+        // 32 sample rows o_i at once: which of them have anything between the circle and the square edge?
+        const int oi = base + lane;
+        double lim = 0.0, wx = 0.0;
+        int ux = 0;
+        if (oi < n_off) {
+            lim = P.limit[(size_t)x * n_off + oi];
+            ux = P.upper[(size_t)x * n_off + oi];
+            wx = P.weight[(size_t)x * n_off + oi];
+        }
+        unsigned todo = __ballot_sync(0xffffffffu, ux != 0 && lim < far_y);
+        while (todo) {
+            const int src = __ffs(todo) - 1;
+            todo &= todo - 1;
+            const double lim_s = __shfl_sync(0xffffffffu, lim, src);
+            const double wx_s = __shfl_sync(0xffffffffu, wx, src);
+            const int ux_s = __shfl_sync(0xffffffffu, ux, src);
+            const double ux_w = 1.0 - wx_s;
+            const double* q_row = P.quadrant + (size_t)ay[base + src] * A;
+            const double* c_lo = C + (size_t)row_slot(P, ux_s - 1) * G;
+            const double* c_hi = C + (size_t)row_slot(P, ux_s) * G;
+            for (int oj = lane; oj < n_off; oj += kWarp) {
+                const int u = uy[oj];
+                if (u != 0 && !(sy[oj] <= lim_s)) {
+                    const double w = wy[oj];
+                    const double lo = c_lo[u - 1] * ux_w + c_hi[u - 1] * wx_s;
+                    const double hi = c_lo[u] * ux_w + c_hi[u] * wx_s;
+                    acc += q_row[ay[oj]] * (lo * (1.0 - w) + hi * w);
+                }
             }
         }
     }
@@ -288,7 +310,8 @@ void launch_record_observables(const DevProblem& P, const double* N_cur, const d
 
 void launch_ring(const DevProblem& P, const double* C, double* ring, cudaStream_t stream)
 {
-    if (P.n_ring > 0) ring_kernel<<<P.n_ring, kWarp * kRingWarps, 0, stream>>>(P, C, ring);
+    const size_t smem = (size_t)P.n_off * (2 * sizeof(double) + 2 * sizeof(int));
+    if (P.n_ring > 0) ring_kernel<<<P.n_ring, kWarp * kRingWarps, smem, stream>>>(P, C, ring);
 }
 
 void launch_finish_factored(const DevProblem& P, const double* C, int tiles, const double* partial, const double* ring,
