@@ -6,6 +6,8 @@
 #include <cstring>
 #include <memory>
 #include <stdexcept>
+#include <type_traits>
+#include <algorithm>
 #include <string>
 #include <vector>
 
@@ -51,7 +53,9 @@ struct ldm_context {
     double* d_partial = nullptr;           // [tiles][P] factored path: per beta-tile sums
     double* d_ring = nullptr;              // [P] factored path: samples between the cutoff circle and the square edge
     double* d_wc_rows = nullptr;           // [G] factored path: per-row dot products of the WC operator
-    int* d_ring_points = nullptr;          // [P] capacity
+    std::vector<void*> ring_allocations;   // the ring-correction CSR of the current (rank, world)
+    int ring_rank = -1, ring_world = -1;
+    long long ring_entries = 0, ring_samples = 0;
     int cur = 0;
     int algo = LDM_ALGO_FACTORED;
     long long launches = 0;
@@ -79,6 +83,7 @@ struct ldm_context {
     {
         cudaSetDevice(device);
         for (void* p : allocations) cudaFree(p);
+        for (void* p : ring_allocations) cudaFree(p);
         if (ev_begin) cudaEventDestroy(ev_begin);
         if (ev_end) cudaEventDestroy(ev_end);
         if (stream) cudaStreamDestroy(stream);
@@ -89,28 +94,35 @@ namespace {
 
 using ldm::DevProblem;
 
-// The time-invariant list of nodes that need the ring correction, for this rank's rows (see DevProblem).
-void build_ring_points(ldm_context* c)
+// The ring-correction operator of the factored path for this rank's rows (time-invariant; rebuilt when the
+// sharding changes).  Built lazily: the direct algorithm never needs it.
+void ensure_ring_operator(ldm_context* c)
 {
-    const ldm::Tables& t = c->tables;
     DevProblem& d = c->dev;
-    const int G = d.G, n_off = d.n_off;
-    std::vector<double> lim_min(G, 1e300);
-    for (int x = 0; x < G; x++)
-        for (int o = 0; o < n_off; o++)
-            if (t.axisM.upper[(size_t)x * n_off + o] != 0)
-                lim_min[x] = std::min(lim_min[x], t.axisM.limit[(size_t)x * n_off + o]);
-    std::vector<int> points;
-    const int rows = ldm::local_rows(d);
-    for (int lx = 0; lx < rows; lx++) {
-        const int x = d.rank + d.world * lx;
-        for (int y = 0; y < G; y++)
-            if (lim_min[x] < t.far_inside[y]) points.push_back(lx * G + y);
-    }
-    d.n_ring = (int)points.size();
-    if (!points.empty())
-        LDM_CUDA(cudaMemcpy(c->d_ring_points, points.data(), points.size() * sizeof(int), cudaMemcpyHostToDevice));
+    if (c->ring_rank == d.rank && c->ring_world == d.world) return;
+    ldm::RingOperator op;
+    ldm::build_ring_operator(c->tables, d.rank, d.world, op);
+    for (void* p : c->ring_allocations) cudaFree(p);
+    c->ring_allocations.clear();
+    auto up = [&](const auto& v) {
+        using T = typename std::decay_t<decltype(v)>::value_type;
+        void* p = nullptr;
+        LDM_CUDA(cudaMalloc(&p, std::max<size_t>(v.size(), 1) * sizeof(T)));
+        c->ring_allocations.push_back(p);
+        if (!v.empty()) LDM_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+        return static_cast<const T*>(p);
+    };
+    d.n_ring = (int)op.point.size();
+    d.ring_point = up(op.point);
+    d.ring_begin = up(op.row_begin);
+    d.ring_node = up(op.node);
+    d.ring_weight = up(op.weight);
     LDM_CUDA(cudaMemset(c->d_ring, 0, c->P() * sizeof(double)));
+    c->ring_rank = d.rank;
+    c->ring_world = d.world;
+    c->ring_entries = (long long)op.node.size();
+    c->ring_samples = op.samples;
+    LDM_CUDA(cudaDeviceSynchronize());      // one-time setup: everything above is visible to every stream
 }
 
 // One right-hand side at the state (N_cur, C) for this rank's rows: scalars <- WC, dN; optional outputs:
@@ -125,11 +137,13 @@ void rhs_and_update(ldm_context* c, const DevProblem& P, const double* C, const 
         c->launches += 3;
         return;
     }
-    ldm::launch_factored(P, C, c->d_partial, c->d_wc_rows, s);
-    ldm::launch_ring(P, C, c->d_ring, s);
-    ldm::launch_finish_factored(P, C, ldm::factored_tiles(P), c->d_partial, c->d_ring, c->d_wc_rows, N_cur, N_next,
+    ensure_ring_operator(c);
+    const DevProblem& R = c->dev;       // the ring CSR pointers live in the handle's copy
+    ldm::launch_factored(R, C, c->d_partial, c->d_wc_rows, s);
+    ldm::launch_ring(R, C, c->d_ring, s);
+    ldm::launch_finish_factored(R, C, ldm::factored_tiles(R), c->d_partial, c->d_ring, c->d_wc_rows, N_cur, N_next,
                                 c->d_scalars, dt, sum_out, deriv_out, C_next, s);
-    c->launches += 2 + (P.n_ring > 0 ? 1 : 0);
+    c->launches += 2 + (R.n_ring > 0 ? 1 : 0);
 }
 
 void step_resident(ldm_context* c, double dt, double* deriv_out)
@@ -236,10 +250,7 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         c->d_partial = c->alloc<double>(P * (size_t)ldm::factored_tiles(d));
         c->d_ring = c->alloc<double>(P);
         c->d_wc_rows = c->alloc<double>((size_t)d.G);
-        c->d_ring_points = c->alloc<int>(P);
-        d.ring_points = c->d_ring_points;
-        d.far_inside = c->upload(t.far_inside);
-        build_ring_points(c.get());
+        d.n_ring = 0;
         LDM_CUDA(cudaMemsetAsync(c->d_C[0], 0, P * sizeof(double), c->stream));
         LDM_CUDA(cudaMemsetAsync(c->d_C[1], 0, P * sizeof(double), c->stream));
         LDM_CUDA(cudaMemsetAsync(c->d_N, 0, 2 * sizeof(double), c->stream));
@@ -496,11 +507,7 @@ int ldm_shard_configure(ldm_handle h, int rank, int world)
     h->dev.world = world;
     h->dev.rank = rank;
     h->dev.rows_per_rank = (h->dev.G + world - 1) / world;
-    return guarded([&] {
-        LDM_CUDA(cudaSetDevice(h->device));
-        LDM_CUDA(cudaStreamSynchronize(h->stream));
-        build_ring_points(h);
-    });
+    return LDM_OK;
 }
 
 int ldm_shard_rows_per_rank(ldm_handle h) { return h ? h->dev.rows_per_rank : 0; }

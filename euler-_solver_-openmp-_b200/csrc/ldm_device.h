@@ -26,11 +26,13 @@ struct DevProblem {
     const double* w_nodes;     // [G][G]  w(xi)                                            (Solver.cpp:490)
     const double* out_weight;  // [G][G]  sum of m over this node's samples beyond the cutoff
     const double* wc_operator; // [G][G]  WC = hh * (<wc_operator, C> + N^2 wc_outside)   (Solver.cpp:265-274)
-    // ring correction of the factored path: the nodes that own at least one sample inside the grid square but
-    // outside the cutoff circle (time-invariant list, this rank's rows only), packed as local_row * G + y
-    const int* ring_points;
-    int n_ring;
-    const double* far_inside;  // [G] largest in-square sample abscissa of each node (-1: none)
+    // ring correction of the factored path (ldm_model.h RingOperator): CSR over the nodes of this rank's rows that
+    // own samples inside the grid square but beyond the cutoff circle
+    int n_ring;                // CSR rows
+    const int* ring_point;     // [n_ring] local_row * G + y
+    const int* ring_begin;     // [n_ring + 1]
+    const int* ring_node;      // C index (gathered layout)
+    const double* ring_weight;
 };
 
 // Which samples sample_sum accumulates (all use the same (x,o_i) x (y,o_j) enumeration):

@@ -164,77 +164,22 @@ pointwise_kernel(DevProblem P, const double* __restrict__ C, const double* __res
 }
 
 // ------------------------------------------------------------------------------------------------
-// Ring correction of the factored path: one CTA per listed node, warps split the o_i range, lanes the o_j
-// range; accumulates m * bilinear(C) over the samples inside the grid square but beyond the cutoff circle.
+// Ring correction of the factored path: a sparse matrix-vector product with the time-invariant operator built on
+// the host (ldm_model.cpp build_ring_operator).  One warp per CSR row, fixed reduction order.
 // ------------------------------------------------------------------------------------------------
 constexpr int kRingWarps = 8;
 
 __global__ void __launch_bounds__(kWarp * kRingWarps)
 ring_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__ ring)
 {
-    extern __shared__ __align__(16) double ring_smem[];
-    __shared__ double part[kRingWarps];
-    const int G = P.G, n_off = P.n_off, A = P.A;
-    const int packed = P.ring_points[blockIdx.x];
-    const int lx = packed / G, y = packed - lx * G;
-    const int x = P.rank + P.world * lx;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const double far_y = P.far_inside[y];
-
-    // this node's y-side sample row, staged once: abscissa, weight, upper node, kernel column
-    double* sy = ring_smem;                          // [n_off]
-    double* wy = sy + n_off;                         // [n_off]
-    int* uy = reinterpret_cast<int*>(wy + n_off);    // [n_off]
-    int* ay = uy + n_off;                            // [n_off]
-    for (int o = threadIdx.x; o < n_off; o += blockDim.x) {
-        sy[o] = P.s[(size_t)y * n_off + o];
-        wy[o] = P.weight[(size_t)y * n_off + o];
-        uy[o] = P.upper[(size_t)y * n_off + o];
-        ay[o] = P.alpha[o];
-    }
-    __syncthreads();
-
+    const int row = blockIdx.x * kRingWarps + (threadIdx.x >> 5);
+    if (row >= P.n_ring) return;
+    const int lane = threadIdx.x & 31;
+    const int begin = P.ring_begin[row], end = P.ring_begin[row + 1];
     double acc = 0.0;
-    for (int base = warp * kWarp; base < n_off; base += kRingWarps * kWarp) {
-        // 32 sample rows o_i at once: which of them have anything between the circle and the square edge?
-        const int oi = base + lane;
-        double lim = 0.0, wx = 0.0;
-        int ux = 0;
-        if (oi < n_off) {
-            lim = P.limit[(size_t)x * n_off + oi];
-            ux = P.upper[(size_t)x * n_off + oi];
-            wx = P.weight[(size_t)x * n_off + oi];
-        }
-        unsigned todo = __ballot_sync(0xffffffffu, ux != 0 && lim < far_y);
-        while (todo) {
-            const int src = __ffs(todo) - 1;
-            todo &= todo - 1;
-            const double lim_s = __shfl_sync(0xffffffffu, lim, src);
-            const double wx_s = __shfl_sync(0xffffffffu, wx, src);
-            const int ux_s = __shfl_sync(0xffffffffu, ux, src);
-            const double ux_w = 1.0 - wx_s;
-            const double* q_row = P.quadrant + (size_t)ay[base + src] * A;
-            const double* c_lo = C + (size_t)row_slot(P, ux_s - 1) * G;
-            const double* c_hi = C + (size_t)row_slot(P, ux_s) * G;
-            for (int oj = lane; oj < n_off; oj += kWarp) {
-                const int u = uy[oj];
-                if (u != 0 && !(sy[oj] <= lim_s)) {
-                    const double w = wy[oj];
-                    const double lo = c_lo[u - 1] * ux_w + c_hi[u - 1] * wx_s;
-                    const double hi = c_lo[u] * ux_w + c_hi[u] * wx_s;
-                    acc += q_row[ay[oj]] * (lo * (1.0 - w) + hi * w);
-                }
-            }
-        }
-    }
+    for (int e = begin + lane; e < end; e += kWarp) acc += P.ring_weight[e] * C[P.ring_node[e]];
     acc = warp_sum(acc);
-    if (lane == 0) part[warp] = acc;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        double s = 0.0;
-        for (int w = 0; w < kRingWarps; w++) s += part[w];      // fixed order
-        ring[packed] = s;
-    }
+    if (lane == 0) ring[P.ring_point[row]] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -310,8 +255,7 @@ void launch_record_observables(const DevProblem& P, const double* N_cur, const d
 
 void launch_ring(const DevProblem& P, const double* C, double* ring, cudaStream_t stream)
 {
-    const size_t smem = (size_t)P.n_off * (2 * sizeof(double) + 2 * sizeof(int));
-    if (P.n_ring > 0) ring_kernel<<<P.n_ring, kWarp * kRingWarps, smem, stream>>>(P, C, ring);
+    if (P.n_ring > 0) ring_kernel<<<(P.n_ring + kRingWarps - 1) / kRingWarps, kWarp * kRingWarps, 0, stream>>>(P, C, ring);
 }
 
 void launch_finish_factored(const DevProblem& P, const double* C, int tiles, const double* partial, const double* ring,

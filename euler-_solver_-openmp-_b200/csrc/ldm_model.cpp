@@ -269,4 +269,88 @@ void build_tables(const ldm_problem& p, Tables& t)
     }
 }
 
+void build_ring_operator(const Tables& t, int rank, int world, RingOperator& out)
+{
+    const int G = t.G, n_off = t.offM.n_off, A = t.offM.A;
+    const AxisTable& ax = t.axisM;
+    const int rows_per_rank = (G + world - 1) / world;
+    auto slot = [&](int x) { return world == 1 ? x : (x % world) * rows_per_rank + x / world; };
+
+    // per node: its in-square offsets ordered by decreasing abscissa (ties by offset index: deterministic)
+    std::vector<std::vector<int>> order((size_t)G);
+    std::vector<double> lim_min((size_t)G, 1e300);
+    for (int n = 0; n < G; n++) {
+        for (int o = 0; o < n_off; o++)
+            if (ax.upper[(size_t)n * n_off + o] != 0) {
+                order[n].push_back(o);
+                lim_min[n] = std::min(lim_min[n], ax.limit[(size_t)n * n_off + o]);
+            }
+        std::sort(order[n].begin(), order[n].end(), [&](int a, int b) {
+            const double sa = ax.s[(size_t)n * n_off + a], sb = ax.s[(size_t)n * n_off + b];
+            return sa != sb ? sa > sb : a < b;
+        });
+    }
+
+    const int rows = (G - rank + world - 1) / world;
+    std::vector<RingOperator> per_row((size_t)rows);
+    #pragma omp parallel
+    {
+        std::vector<double> window((size_t)G * G, 0.0);
+        std::vector<char> seen((size_t)G * G, 0);
+        std::vector<int> touched;
+        #pragma omp for schedule(dynamic, 1)
+        for (int lx = 0; lx < rows; lx++) {
+            const int x = rank + world * lx;
+            RingOperator& mine = per_row[lx];
+            for (int y = 0; y < G; y++) {
+                if (!(lim_min[x] < t.far_inside[y])) continue;
+                touched.clear();
+                for (int oi : order[x]) {
+                    const size_t ci = (size_t)x * n_off + oi;
+                    const double lim = ax.limit[ci];
+                    if (!(lim < t.far_inside[y])) break;        // smaller abscissae only raise the limit
+                    const int ux = ax.upper[ci];
+                    const double wx = ax.weight[ci];
+                    const double* q_row = t.offM.quadrant.data() + (size_t)t.offM.alpha[oi] * A;
+                    for (int oj : order[y]) {
+                        const size_t cj = (size_t)y * n_off + oj;
+                        if (ax.s[cj] <= lim) break;             // inside the circle from here on
+                        mine.samples++;
+                        const double m = q_row[t.offM.alpha[oj]];
+                        if (m == 0.0) continue;
+                        const int uy = ax.upper[cj];
+                        const double wy = ax.weight[cj];
+                        const int idx[4] = {(ux - 1) * G + (uy - 1), ux * G + (uy - 1), (ux - 1) * G + uy, ux * G + uy};
+                        const double w4[4] = {(1 - wx) * (1 - wy), wx * (1 - wy), (1 - wx) * wy, wx * wy};   // S:348-351
+                        for (int c4 = 0; c4 < 4; c4++) {
+                            if (!seen[idx[c4]]) { seen[idx[c4]] = 1; touched.push_back(idx[c4]); }
+                            window[idx[c4]] += m * w4[c4];
+                        }
+                    }
+                }
+                if (touched.empty()) continue;
+                std::sort(touched.begin(), touched.end());
+                mine.point.push_back(lx * G + y);
+                for (int n : touched) {
+                    const int p = n / G, q = n - p * G;
+                    mine.node.push_back(slot(p) * G + q);
+                    mine.weight.push_back(window[n]);
+                    window[n] = 0.0; seen[n] = 0;
+                }
+                mine.row_begin.push_back((int)mine.node.size());
+            }
+        }
+    }
+    out = RingOperator();
+    out.row_begin.push_back(0);
+    for (const RingOperator& r : per_row) {
+        const int base = (int)out.node.size();
+        out.point.insert(out.point.end(), r.point.begin(), r.point.end());
+        for (int e : r.row_begin) out.row_begin.push_back(base + e);
+        out.node.insert(out.node.end(), r.node.begin(), r.node.end());
+        out.weight.insert(out.weight.end(), r.weight.begin(), r.weight.end());
+        out.samples += r.samples;
+    }
+}
+
 }  // namespace ldm

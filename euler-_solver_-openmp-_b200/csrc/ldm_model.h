@@ -65,6 +65,21 @@ struct Tables {
 
 void build_tables(const ldm_problem& p, Tables& t);
 
+// The exact correction of the factored path as a sparse linear operator (time-invariant).  The factored sum
+// covers every sample inside the grid square; the reference replaces the samples beyond the cutoff circle by
+// N^2 (Solver.cpp:329-331), so for each node that owns such "ring" samples
+//     ring[node] = sum_e weight[e] * C[node_index[e]]          (CSR row of that node)
+// collects m * (bilinear weights) of exactly those samples.  The far part of the moment grid is coarse, so the
+// ~10^6..10^8 ring samples collapse onto few distinct grid nodes (141 k entries for the 16 384-point grid).
+struct RingOperator {
+    std::vector<int> point;        // per CSR row: local_row * G + y
+    std::vector<int> row_begin;    // rows + 1
+    std::vector<int> node;         // C index in gathered layout: row_slot(p) * G + q
+    std::vector<double> weight;
+    long long samples = 0;         // ring samples enumerated
+};
+void build_ring_operator(const Tables& t, int rank, int world, RingOperator& out);
+
 // Equation::BilinearInterpolation (Solver.cpp:318-353) with Zero / SquaredN extrapolation (355-373)
 double bilinear(const double* grid, int n, const double* values, double x, double y, double max_distance,
                 bool squared_n, double asymptotic_value);
