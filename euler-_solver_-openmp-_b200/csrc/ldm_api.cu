@@ -233,6 +233,18 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         d.limit = c->upload(t.axisM.limit);
         d.weight = c->upload(t.axisM.weight);
         d.upper = c->upload(t.axisM.upper);
+        {
+            const int n_off = d.n_off, G = d.G;
+            std::vector<int> ut((size_t)G * n_off);
+            std::vector<double> wt((size_t)G * n_off);
+            for (int n = 0; n < G; n++)
+                for (int o = 0; o < n_off; o++) {
+                    ut[(size_t)o * G + n] = t.axisM.upper[(size_t)n * n_off + o];
+                    wt[(size_t)o * G + n] = t.axisM.weight[(size_t)n * n_off + o];
+                }
+            d.upper_t = c->upload(ut);
+            d.weight_t = c->upload(wt);
+        }
         d.alpha = c->upload(t.offM.alpha);
         d.quadrant = c->upload(t.offM.quadrant);
         d.m_nodes = c->upload(t.m_nodes);

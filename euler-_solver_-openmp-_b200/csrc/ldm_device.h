@@ -20,6 +20,8 @@ struct DevProblem {
     const double* limit;       // [G][n_off] inside  <=>  partner abscissa <= limit       (Solver.cpp:329-330)
     const double* weight;      // [G][n_off] interpolation weight along this axis          (Solver.cpp:344)
     const int* upper;          // [G][n_off] upper node of the interval                    (Solver.cpp:335)
+    const int* upper_t;        // [n_off][G] the same two tables transposed (node-contiguous)
+    const double* weight_t;
     const int* alpha;          // [n_off]
     const double* quadrant;    // [A][A] odd-node quadrant of the m table
     const double* m_nodes;     // [G][G]  m(xi) at the moment nodes                        (Solver.cpp:469)

@@ -45,7 +45,7 @@ struct FactoredConfig {
     static size_t smem_bytes(int G, int A)
     {
         const size_t a_pad = (size_t)((A + BK - 1) / BK) * BK;
-        return sizeof(double) * ((size_t)2 * BK * BM + (size_t)2 * BK * BN + (size_t)BM * HS_LD + (size_t)((G + 3) & ~3) + 4 * a_pad) +
+        return sizeof(double) * ((size_t)2 * BK * BM + (size_t)2 * BK * BN + (size_t)BM * HS_LD + (size_t)((G * (1 + (NT >= 2 * G ? NT / G : 1)) + 3) & ~3) + 4 * a_pad) +
                sizeof(int) * 4 * a_pad;
     }
 };
@@ -79,7 +79,9 @@ factored_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__
     double* Es = Qs + 2 * BK * BM;                        // [2][BK][BN]
     double* Hs = Es + 2 * BK * BN;                        // [BM][HS_LD]
     double* acc_y = Hs + BM * HS_LD;                      // [G]
-    double* tap_w = acc_y + ((G + 3) & ~3);               // [A_pad][4] (32-byte aligned): weights of the (at most) four C rows feeding E[alpha]
+    const int split = NT >= 2 * G ? NT / G : 1;           // threads sharing one y in the y-side pass
+    double* part_y = acc_y + G;                           // [split][G]
+    double* tap_w = acc_y + ((G * (1 + split) + 3) & ~3); // [A_pad][4] (32-byte aligned): weights of the four C rows feeding E[alpha]
     int* tap_row = reinterpret_cast<int*>(tap_w + 4 * A_pad);   // [A_pad][4]: their offsets (slot * G)
 
     // x-side interpolation taps of this row, once per CTA: E[alpha][q] = sum_t tap_w[alpha][t] * C[tap_row[alpha][t] + q]
@@ -180,29 +182,35 @@ factored_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__
                 Hs[(i * TYN + ty) * HS_LD + 1 + (j / 2) * (2 * TXN) + tx * 2 + (j & 1)] = acc[i][j];
         __syncthreads();
 
-        // y side: every tap pair (u-1, u) whose upper node u falls in this chunk.  A warp owns one y at a time; its
-        // lanes walk the beta rows of one fold, so the interpolation-table reads are contiguous.
+        // y side: every tap pair (u-1, u) whose upper node u falls in this chunk.  Consecutive threads own consecutive y
+        // (the transposed tables upper_t / weight_t make those reads contiguous); `split` threads share one y, each
+        // taking every split-th beta row, so every thread runs a long loop of independent loads.
         const int rows_here = min(BM, A - b0);
         const double* hbase = Hs + 1 - q0;
-        for (int y = tid / 32; y < G; y += NT / 32) {
-            const int* uy_row = P.upper + (size_t)y * n_off;
-            const double* wy_row = P.weight + (size_t)y * n_off;
+        for (int idx = tid; idx < G * split; idx += NT) {
+            const int part = idx / G, y = idx - part * G;
             double s = 0.0;
             for (int f = 0; f < n_fold; f++) {
                 const int o0 = folded_offset(A, n_fold, b0, f);
                 const int dir = (n_fold == 2 && f == 0) ? -1 : 1;
-                for (int bm = tid % 32; bm < rows_here; bm += 32) {
-                    const int o = o0 + dir * bm;
-                    const int u = uy_row[o];
-                    const double w = wy_row[o];
+                #pragma unroll 4
+                for (int bm = part; bm < rows_here; bm += split) {
+                    const size_t c = (size_t)(o0 + dir * bm) * G + y;
+                    const int u = P.upper_t[c];
+                    const double w = P.weight_t[c];
                     if (u >= q0 && u < q0 + BN && u != 0) {
                         const double* hrow = hbase + bm * HS_LD;
                         s += hrow[u - 1] * (1.0 - w) + hrow[u] * w;
                     }
                 }
             }
-            s = warp_sum(s);
-            if (tid % 32 == 0) acc_y[y] += s;
+            part_y[part * G + y] = s;
+        }
+        __syncthreads();
+        for (int y = tid; y < G; y += NT) {
+            double s = acc_y[y];
+            for (int part = 0; part < split; part++) s += part_y[part * G + y];     // fixed order
+            acc_y[y] = s;
         }
         if (chunk + 1 < n_chunks) {
             __syncthreads();
