@@ -44,6 +44,7 @@ struct ldm_context {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
     ldm::Tables tables;
     ldm::DevProblem dev{};
+    ldm::FactoredPlan plan;
     std::vector<void*> allocations;
     double* d_C[2] = {nullptr, nullptr};   // ping-pong pair density, natural layout
     double* d_N = nullptr;                 // [2] ping-pong first moment
@@ -139,9 +140,9 @@ void rhs_and_update(ldm_context* c, const DevProblem& P, const double* C, const 
     }
     ensure_ring_operator(c);
     const DevProblem& R = c->dev;       // the ring CSR pointers live in the handle's copy
-    ldm::launch_factored(R, C, c->d_partial, c->d_wc_rows, s);
+    ldm::launch_factored(R, c->plan, C, c->d_partial, c->d_wc_rows, s);
     ldm::launch_ring(R, C, c->d_ring, s);
-    ldm::launch_finish_factored(R, C, ldm::factored_tiles(R), c->d_partial, c->d_ring, c->d_wc_rows, N_cur, N_next,
+    ldm::launch_finish_factored(R, C, c->plan.slabs(), c->d_partial, c->d_ring, c->d_wc_rows, N_cur, N_next,
                                 c->d_scalars, dt, sum_out, deriv_out, C_next, s);
     c->launches += 2 + (R.n_ring > 0 ? 1 : 0);
 }
@@ -259,7 +260,8 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         c->d_scalars = c->alloc<double>(ldm::kScalars);
         c->d_sum = c->alloc<double>(P);
         c->d_deriv = c->alloc<double>(P);
-        c->d_partial = c->alloc<double>(P * (size_t)ldm::factored_tiles(d));
+        c->plan = ldm::plan_factored(d);
+        c->d_partial = c->alloc<double>(P * (size_t)c->plan.slabs());
         c->d_ring = c->alloc<double>(P);
         c->d_wc_rows = c->alloc<double>((size_t)d.G);
         d.n_ring = 0;

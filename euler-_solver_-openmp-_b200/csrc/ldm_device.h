@@ -77,9 +77,14 @@ void launch_finish_factored(const DevProblem& P, const double* C, int tiles, con
 // ring[lx][y] for the nodes in P.ring_points (other entries of `ring` stay zero)
 void launch_ring(const DevProblem& P, const double* C, double* ring, cudaStream_t stream);
 
-// Factored path (ldm_factored.cu): partial[tile][local_rows][G] <- per beta-tile sums over all samples inside the
-// grid square; combine: inside_sum = sum_tiles partial - ring.
-int factored_tiles(const DevProblem& P);
-void launch_factored(const DevProblem& P, const double* C, double* partial, double* wc_rows, cudaStream_t stream);
+// Factored path (ldm_factored.cu): partial[slab][local_rows][G] <- per-slab sums over all samples inside the grid
+// square; the closing kernel forms inside_sum = sum_slabs partial - ring.
+struct FactoredPlan {
+    int bm = 80, bn = 64;      // CTA tile: beta rows x columns
+    int tiles = 1, chunks = 1; // beta tiles x column chunks; slabs = tiles * chunks partial sums per node
+    int slabs() const { return tiles * chunks; }
+};
+FactoredPlan plan_factored(const DevProblem& P);
+void launch_factored(const DevProblem& P, const FactoredPlan& plan, const double* C, double* partial, double* wc_rows, cudaStream_t stream);
 
 }  // namespace ldm

@@ -15,9 +15,12 @@
 // are removed afterwards by the exact ring correction (sample_sum<SAMPLES_RING>), so
 //     inside_sum = ext - ring.
 //
-// One CTA owns one row x and one tile of BM beta-rows; it walks the columns q in chunks of BN, generating
-// the E chunk on the fly from C (2-4 taps per element), accumulating the BM x BN tile of H in registers,
-// staging it in shared memory and immediately contracting it with the y-side interpolation rows.
+// One CTA owns one row x, one tile of BM beta-rows and one chunk of BN columns q ("slab" = tile x chunk): it
+// generates its E chunk on the fly from C (4 taps per element), accumulates the BM x BN tile of H in registers
+// (plus the single halo column q0-1 that the first tap pairs of the chunk need), stages it in shared memory and
+// contracts it with the y-side interpolation rows.  Slabs are independent; finish_factored_kernel adds them up.
+#include <cstdlib>
+
 #include "ldm_device.h"
 
 namespace ldm {
@@ -45,7 +48,7 @@ struct FactoredConfig {
     static size_t smem_bytes(int G, int A)
     {
         const size_t a_pad = (size_t)((A + BK - 1) / BK) * BK;
-        return sizeof(double) * ((size_t)2 * BK * BM + (size_t)2 * BK * BN + (size_t)BM * HS_LD + (size_t)((G * (1 + (NT >= 2 * G ? NT / G : 1)) + 3) & ~3) + 4 * a_pad) +
+        return sizeof(double) * ((size_t)2 * BK * BM + (size_t)2 * BK * BN + (size_t)BM * HS_LD + (size_t)((G * (1 + (NT >= 2 * G ? NT / G : 1)) + 2 * BK + 3) & ~3) + 4 * a_pad) +
                sizeof(int) * 4 * a_pad;
     }
 };
@@ -68,10 +71,10 @@ factored_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__
     const int lx = blockIdx.y;
     const int x = P.rank + P.world * lx;
     const int b0 = blockIdx.x * BM;                       // first beta row of this tile
+    const int q0 = blockIdx.z * BN;                       // first column of this chunk
     const int tid = threadIdx.x;
     const int tx = tid % TXN, ty = tid / TXN;
     const int n_kc = (A + BK - 1) / BK;
-    const int n_chunks = (G + BN - 1) / BN;
     const int A_pad = n_kc * BK;
 
     extern __shared__ __align__(32) double smem[];
@@ -81,7 +84,8 @@ factored_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__
     double* acc_y = Hs + BM * HS_LD;                      // [G]
     const int split = NT >= 2 * G ? NT / G : 1;           // threads sharing one y in the y-side pass
     double* part_y = acc_y + G;                           // [split][G]
-    double* tap_w = acc_y + ((G * (1 + split) + 3) & ~3); // [A_pad][4] (32-byte aligned): weights of the four C rows feeding E[alpha]
+    double* Eh = acc_y + G * (1 + split);                 // [2][BK] E values of the halo column q0-1
+    double* tap_w = acc_y + ((G * (1 + split) + 2 * BK + 3) & ~3);   // [A_pad][4] (32-byte aligned): weights of the four C rows feeding E[alpha]
     int* tap_row = reinterpret_cast<int*>(tap_w + 4 * A_pad);   // [A_pad][4]: their offsets (slot * G)
 
     // x-side interpolation taps of this row, once per CTA: E[alpha][q] = sum_t tap_w[alpha][t] * C[tap_row[alpha][t] + q]
@@ -106,10 +110,12 @@ factored_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__
 
     double e_reg[Cfg::E_PER_THREAD];
     double q_reg[Cfg::Q_PER_THREAD];
+    double eh_reg = 0.0;                                  // threads < BK: E[alpha][q0-1]
+    double h_acc = 0.0;                                   // threads < BM: H[b0 + tid][q0-1]
+    const bool want_halo = q0 > 0;
     const int e_col = tid % BN, e_k0 = tid / BN;          // this thread's E column and first row within a chunk
 
-    for (int chunk = 0; chunk < n_chunks; chunk++) {
-        const int q0 = chunk * BN;
+    {
         const int q = q0 + e_col;
         const double* c_col = C + (q < G ? q : G - 1);    // clamped: columns beyond G are multiplied by 0 below
         const double live = q < G ? 1.0 : 0.0;
@@ -121,6 +127,13 @@ factored_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__
                 const double4 wa = *reinterpret_cast<const double4*>(tap_w + alpha * 4);
                 const int4 ra = *reinterpret_cast<const int4*>(tap_row + alpha * 4);
                 e_reg[r] = (c_col[ra.x] * wa.x + c_col[ra.y] * wa.y) + (c_col[ra.z] * wa.z + c_col[ra.w] * wa.w);
+            }
+            if (want_halo && tid < BK) {
+                const int alpha = kc * BK + tid;
+                const double* c_h = C + (q0 - 1);
+                const double4 wa = *reinterpret_cast<const double4*>(tap_w + alpha * 4);
+                const int4 ra = *reinterpret_cast<const int4*>(tap_row + alpha * 4);
+                eh_reg = (c_h[ra.x] * wa.x + c_h[ra.y] * wa.y) + (c_h[ra.z] * wa.z + c_h[ra.w] * wa.w);
             }
             #pragma unroll
             for (int r = 0; r < Cfg::Q_PER_THREAD; r++) {
@@ -134,6 +147,7 @@ factored_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__
             #pragma unroll
             for (int r = 0; r < Cfg::E_PER_THREAD; r++)
                 Es[buf * BK * BN + (r * K_STRIDE + e_k0) * BN + e_col] = e_reg[r] * live;
+            if (want_halo && tid < BK) Eh[buf * BK + tid] = eh_reg;
             #pragma unroll
             for (int r = 0; r < Cfg::Q_PER_THREAD; r++) {
                 const int e = r * NT + tid;
@@ -170,11 +184,16 @@ factored_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__
                     #pragma unroll
                     for (int j = 0; j < TN; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
             }
+            if (want_halo && tid < BM) {
+                #pragma unroll
+                for (int k = 0; k < BK; k++) h_acc = fma(qs[k * BM + tid], Eh[buf * BK + k], h_acc);
+            }
             if (kc + 1 < n_kc) store_chunk(buf ^ 1);
             __syncthreads();
         }
 
-        // stage the H tile: Hs[row][1 + col]; column 0 keeps the last column of the previous chunk
+        // stage the H tile: Hs[row][1 + col]; column 0 is the halo column q0-1
+        if (tid < BM) Hs[tid * HS_LD] = h_acc;
         #pragma unroll
         for (int i = 0; i < TM; i++)
             #pragma unroll
@@ -193,14 +212,27 @@ factored_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__
             for (int f = 0; f < n_fold; f++) {
                 const int o0 = folded_offset(A, n_fold, b0, f);
                 const int dir = (n_fold == 2 && f == 0) ? -1 : 1;
-                #pragma unroll 4
-                for (int bm = part; bm < rows_here; bm += split) {
-                    const size_t c = (size_t)(o0 + dir * bm) * G + y;
-                    const int u = P.upper_t[c];
-                    const double w = P.weight_t[c];
-                    if (u >= q0 && u < q0 + BN && u != 0) {
-                        const double* hrow = hbase + bm * HS_LD;
-                        s += hrow[u - 1] * (1.0 - w) + hrow[u] * w;
+                // batches of kBatch table reads issued together (they come from L2), then the shared-memory gathers;
+                // branch-free: a tap pair outside this chunk is redirected to column q0 with weight 0
+                constexpr int kBatch = 8;
+                for (int bm0 = part; bm0 < rows_here; bm0 += split * kBatch) {
+                    int u[kBatch];
+                    double w[kBatch];
+                    #pragma unroll
+                    for (int r = 0; r < kBatch; r++) {
+                        const int bm = min(bm0 + r * split, rows_here - 1);
+                        const size_t c = (size_t)(o0 + dir * bm) * G + y;
+                        u[r] = P.upper_t[c];
+                        w[r] = P.weight_t[c];
+                    }
+                    #pragma unroll
+                    for (int r = 0; r < kBatch; r++) {
+                        const int bm = bm0 + r * split;
+                        const bool live = bm < rows_here && u[r] >= q0 && u[r] < q0 + BN && u[r] != 0;
+                        const int uc = live ? u[r] : q0;
+                        const double* hrow = hbase + min(bm, rows_here - 1) * HS_LD;
+                        const double v = hrow[uc - 1] * (1.0 - w[r]) + hrow[uc] * w[r];
+                        s += live ? v : 0.0;
                     }
                 }
             }
@@ -212,19 +244,15 @@ factored_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__
             for (int part = 0; part < split; part++) s += part_y[part * G + y];     // fixed order
             acc_y[y] = s;
         }
-        if (chunk + 1 < n_chunks) {
-            __syncthreads();
-            for (int bm = tid; bm < BM; bm += NT) Hs[bm * HS_LD] = Hs[bm * HS_LD + BN];   // carry the halo column
-        }
         __syncthreads();
     }
 
-    double* out = partial + ((size_t)blockIdx.x * local_rows(P) + lx) * G;
+    double* out = partial + (((size_t)blockIdx.x * gridDim.z + blockIdx.z) * local_rows(P) + lx) * G;
     for (int y = tid; y < G; y += NT) out[y] = acc_y[y];
 
     // WC = <wc_operator, C> (Solver.cpp:265-274) row by row, folded into this launch: the first beta-tile of local
     // row lx covers rows lx*world .. lx*world+world-1 (every rank reduces the full operator, so no all-reduce)
-    if (blockIdx.x == 0 && wc_rows != nullptr) {
+    if (blockIdx.x == 0 && blockIdx.z == 0 && wc_rows != nullptr) {
         for (int r = tid / 32; r < P.world; r += NT / 32) {
             const int xr = lx * P.world + r;
             if (xr >= G) continue;
@@ -239,7 +267,7 @@ factored_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__
 }
 
 template <int BM, int BN, int TM, int TN, int BK>
-void launch_variant(const DevProblem& P, const double* C, double* partial, double* wc_rows, int tiles, cudaStream_t stream)
+void launch_variant(const DevProblem& P, const FactoredPlan& plan, const double* C, double* partial, double* wc_rows, cudaStream_t stream)
 {
     using Cfg = FactoredConfig<BM, BN, TM, TN, BK>;
     const size_t smem = Cfg::smem_bytes(P.G, P.A);
@@ -250,37 +278,38 @@ void launch_variant(const DevProblem& P, const double* C, double* partial, doubl
         cudaFuncSetAttribute(factored_kernel<BM, BN, TM, TN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         configured[device & 63] = true;
     }
-    dim3 grid(tiles, local_rows(P));
+    dim3 grid(plan.tiles, local_rows(P), plan.chunks);
     factored_kernel<BM, BN, TM, TN, BK><<<grid, Cfg::NT, smem, stream>>>(P, C, partial, wc_rows);
 }
 
 }  // namespace
 
-int factored_tile_rows(const DevProblem& P)
+FactoredPlan plan_factored(const DevProblem& P)
 {
-    // pick the beta-tile height that wastes the fewest padded rows
+    FactoredPlan plan;
+    // beta-tile height that wastes the fewest padded rows; 64-column chunks keep two CTAs resident per SM so that one
+    // CTA's table-gather phases overlap the other's FMA phase (LDM_FACTORED_BN overrides, for tuning)
     const int A = P.A;
     const int pad80 = ((A + 79) / 80) * 80, pad40 = ((A + 39) / 40) * 40;
-    return pad40 < pad80 ? 40 : 80;
+    plan.bm = pad40 < pad80 ? 40 : 80;
+    plan.bn = 64;
+    if (const char* env = std::getenv("LDM_FACTORED_BN")) {
+        const int v = std::atoi(env);
+        if (v == 64 || v == 128) plan.bn = v;
+    }
+    plan.tiles = (A + plan.bm - 1) / plan.bm;
+    plan.chunks = (P.G + plan.bn - 1) / plan.bn;
+    return plan;
 }
 
-int factored_tiles(const DevProblem& P)
+void launch_factored(const DevProblem& P, const FactoredPlan& plan, const double* C, double* partial, double* wc_rows, cudaStream_t stream)
 {
-    const int bm = factored_tile_rows(P);
-    return (P.A + bm - 1) / bm;
-}
-
-void launch_factored(const DevProblem& P, const double* C, double* partial, double* wc_rows, cudaStream_t stream)
-{
-    const int bm = factored_tile_rows(P);
-    const int tiles = factored_tiles(P);
-    const bool narrow = P.G <= 64;
-    if (bm == 80) {
-        if (narrow) launch_variant<80, 64, 5, 8, 16>(P, C, partial, wc_rows, tiles, stream);
-        else launch_variant<80, 128, 5, 8, 16>(P, C, partial, wc_rows, tiles, stream);
+    if (plan.bm == 80) {
+        if (plan.bn == 64) launch_variant<80, 64, 5, 8, 16>(P, plan, C, partial, wc_rows, stream);
+        else launch_variant<80, 128, 5, 8, 16>(P, plan, C, partial, wc_rows, stream);
     } else {
-        if (narrow) launch_variant<40, 64, 5, 8, 16>(P, C, partial, wc_rows, tiles, stream);
-        else launch_variant<40, 128, 5, 8, 16>(P, C, partial, wc_rows, tiles, stream);
+        if (plan.bn == 64) launch_variant<40, 64, 5, 8, 16>(P, plan, C, partial, wc_rows, stream);
+        else launch_variant<40, 128, 5, 8, 16>(P, plan, C, partial, wc_rows, stream);
     }
 }
 
