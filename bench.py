@@ -37,6 +37,8 @@ WORKLOADS = {
     # name: (sigma_w, sigma_m, b, d, d', forced_G)
     "g128": (0.15, 0.15, 0.4, 0.2, 0.001, 128),
     "g64": (0.1, 0.1, 0.4, 0.2, 0.001, 64),
+    "g256": (0.10062893578616353, 0.08, 0.4, 0.2, 0.001, 256),
+    "g512": (0.10062893578616353, 0.08, 0.4, 0.2, 0.001, 512),       # exp 14.6a entry 80 on 262 144 xi-points (config 4)
     "exp14_4a": (0.15, 0.15, 0.4, 0.2, 0.001, 0),
 }
 

@@ -41,7 +41,8 @@ struct CudaError : std::runtime_error {
 struct ldm_context {
     int device = 0;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr;
+    cudaStream_t aux_stream = nullptr;     // the ring correction runs beside the factored kernel
+    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_fork = nullptr, ev_join = nullptr;
     ldm::Tables tables;
     ldm::DevProblem dev{};
     ldm::FactoredPlan plan;
@@ -87,6 +88,9 @@ struct ldm_context {
         for (void* p : ring_allocations) cudaFree(p);
         if (ev_begin) cudaEventDestroy(ev_begin);
         if (ev_end) cudaEventDestroy(ev_end);
+        if (ev_fork) cudaEventDestroy(ev_fork);
+        if (ev_join) cudaEventDestroy(ev_join);
+        if (aux_stream) cudaStreamDestroy(aux_stream);
         if (stream) cudaStreamDestroy(stream);
     }
 };
@@ -140,8 +144,17 @@ void rhs_and_update(ldm_context* c, const DevProblem& P, const double* C, const 
     }
     ensure_ring_operator(c);
     const DevProblem& R = c->dev;       // the ring CSR pointers live in the handle's copy
+    // the sparse ring correction only reads C: it runs on a side stream beside the (register-bound, one CTA per
+    // SM) factored kernel and joins before the closing kernel
+    const bool side = R.n_ring > 0;
+    if (side) {
+        LDM_CUDA(cudaEventRecord(c->ev_fork, s));
+        LDM_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+        ldm::launch_ring(R, C, c->d_ring, c->aux_stream);
+        LDM_CUDA(cudaEventRecord(c->ev_join, c->aux_stream));
+    }
     ldm::launch_factored(R, c->plan, C, c->d_partial, c->d_wc_rows, s);
-    ldm::launch_ring(R, C, c->d_ring, s);
+    if (side) LDM_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
     ldm::launch_finish_factored(R, C, c->plan.slabs(), c->d_partial, c->d_ring, c->d_wc_rows, N_cur, N_next,
                                 c->d_scalars, dt, sum_out, deriv_out, C_next, s);
     c->launches += 2 + (R.n_ring > 0 ? 1 : 0);
@@ -221,8 +234,11 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         c->device = device;
         LDM_CUDA(cudaSetDevice(device));
         LDM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+        LDM_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
         LDM_CUDA(cudaEventCreate(&c->ev_begin));
         LDM_CUDA(cudaEventCreate(&c->ev_end));
+        LDM_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        LDM_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 
         ldm::build_tables(*p, c->tables);
         const ldm::Tables& t = c->tables;

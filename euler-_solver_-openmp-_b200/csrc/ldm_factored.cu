@@ -287,15 +287,19 @@ void launch_variant(const DevProblem& P, const FactoredPlan& plan, const double*
 FactoredPlan plan_factored(const DevProblem& P)
 {
     FactoredPlan plan;
-    // beta-tile height that wastes the fewest padded rows; 64-column chunks keep two CTAs resident per SM so that one
-    // CTA's table-gather phases overlap the other's FMA phase (LDM_FACTORED_BN overrides, for tuning)
+    // beta-tile height that wastes the fewest padded rows; one column chunk when the grid allows it, because every
+    // chunk's CTA scans the whole y-side table (LDM_FACTORED_BM / LDM_FACTORED_BN override, for tuning)
     const int A = P.A;
     const int pad80 = ((A + 79) / 80) * 80, pad40 = ((A + 39) / 40) * 40;
     plan.bm = pad40 < pad80 ? 40 : 80;
-    plan.bn = 64;
+    plan.bn = P.G <= 64 ? 64 : 128;
     if (const char* env = std::getenv("LDM_FACTORED_BN")) {
         const int v = std::atoi(env);
         if (v == 64 || v == 128) plan.bn = v;
+    }
+    if (const char* env = std::getenv("LDM_FACTORED_BM")) {
+        const int v = std::atoi(env);
+        if (v == 40 || v == 80) plan.bm = v;
     }
     plan.tiles = (A + plan.bm - 1) / plan.bm;
     plan.chunks = (P.G + plan.bn - 1) / plan.bn;

@@ -226,6 +226,23 @@ def test_factored_equals_direct_on_the_16k_grid(ldm):
     assert_states_close(factored.download(), direct.download())
 
 
+@pytest.mark.parametrize("G,bm,bn", [(128, 40, 64), (200, 80, 128), (200, 40, 64), (96, 80, 64)])
+def test_factored_tilings_equal_direct(ldm, monkeypatch, G, bm, bn):
+    """every tiling of the factored kernel (several beta tiles, several column chunks with their halo column, ragged
+    edges) against the sample-by-sample path on grids the CPU oracle cannot reach in a test"""
+    props = ldm.Properties.Generate(1, 0.12, 0.09, 0.4, 0.2, 0.001, G)
+    direct = ldm.Equation(props, algorithm=ldm.ALGO_DIRECT)
+    monkeypatch.setenv("LDM_FACTORED_BM", str(bm))
+    monkeypatch.setenv("LDM_FACTORED_BN", str(bn))
+    factored = ldm.Equation(props, algorithm=ldm.ALGO_FACTORED)
+    g = props.MomentsGrid
+    st = direct.GenerateEquilibriumValuesForNAndC(200)
+    st[1:] *= (1 + 0.5 * np.exp(-(g[:, None] ** 2 + g[None, :] ** 2) / (2 * 0.1 ** 2)) + 0.1 * np.sin(7 * g[:, None] + 3 * g[None, :])).ravel()
+    (w1, m1), (w2, m2) = direct.integrals(st), factored.integrals(st)
+    assert abs(w1 - w2) <= 1e-14 * abs(w1)
+    assert np.all(np.abs(m1 - m2) <= 1e-13 * np.abs(m1))
+
+
 def test_large_grid_properties(ldm):
     """BASELINE config 3 (G = 128): too slow for the CPU oracle in a test, so check what the domain offers:
     the spatially uniform state C = N^2 must give dC ~ 2bN m(xi) - 2d'N^2 w(xi)... exactly the structure of the
