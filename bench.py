@@ -164,6 +164,59 @@ def cpu_baseline(workload, budget_s=25.0):
                       "reference source built by-reference (bit-identical to the shipped build, which is ~30x slower)"}
 
 
+def run_sharded(ldm, torch, dist, workload, rank, world, local_rank, steps, warmup):
+    """BASELINE config 4: ONE problem, its xi output rows sharded cyclically over the ranks; per step every rank
+    updates its rows of C from the full replica and an NCCL all-gather (in place, over NVLink) rebuilds the replica.
+    N and WC are recomputed redundantly on every rank, so the all-gather is the only collective.  Strong scaling."""
+    sw, sm, b, d, dd, G = WORKLOADS[workload]
+    props = ldm.Properties.Generate(1, sw, sm, b, d, dd, G)
+    sh = ldm.ShardedEquation(props, rank, world, device=local_rank)
+    rpr = sh.rows_per_rank
+    state0 = seeded_state(props.MomentsGrid, sm)
+    bufs = [torch.from_numpy(sh.to_gathered(state0[1:])).cuda(), torch.zeros(world * rpr, G, dtype=torch.float64, device="cuda")]
+    sh.set_N(state0[0])
+    stream = torch.cuda.current_stream()
+    mine = slice(rank * rpr, (rank + 1) * rpr)
+    k = 0
+
+    def step():
+        nonlocal k
+        src, dst = bufs[k % 2], bufs[(k + 1) % 2]
+        sh.step(src.data_ptr(), dst[mine].data_ptr(), DT, stream.cuda_stream)
+        if world > 1:
+            dist.all_gather_into_tensor(dst.view(-1), dst[mine].reshape(-1))      # in place: input is this rank's slice of the output
+        k += 1
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = sh.eq.launches
+    e0.record(stream)
+    for _ in range(steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    final_C = sh.from_gathered(bufs[k % 2].cpu().numpy())
+    N_end = sh.get_N()
+    assert np.all(np.isfinite(final_C)) and N_end > 0
+    flop_step, s_nz = algorithmic_flop_per_step(props)
+    P = G * G
+    return {"workload": workload, "G": G, "xi_points": P, "S_nz": s_nz, "scaling": "strong", "steps": steps, "warmup": warmup,
+            "value": P * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+            "collective": "NCCL all_gather_into_tensor of C (in place), %d bytes per rank per step" % (rpr * G * 8) if world > 1 else "none (1 rank)",
+            "gpu_launches": int(sh.eq.launches - launches0), "algorithmic_tflops": flop_step * steps / (ms * 1e-3) / 1e12,
+            "checksum": float(final_C.sum() + N_end)}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -172,6 +225,8 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="g128", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--sharded", default="g512", help="workload of the xi-sharded strong-scaling leg ('none' to skip)")
+    ap.add_argument("--sharded-steps", type=int, default=10)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -249,6 +304,10 @@ def main():
         e2e_s = float(t.item())
     e2e_value = world * P * args.steps / e2e_s
 
+    sharded = None
+    if args.sharded != "none":
+        sharded = run_sharded(ldm, torch, dist, args.sharded, rank, world, local_rank, args.sharded_steps, 2)
+
     if rank == 0:
         ms_per_step = total_ms / args.steps
         achieved = flop_step / (ms_per_step * 1e-3) / 1e12
@@ -268,6 +327,8 @@ def main():
                          "hbm_GBps_algorithmic": 16.0 * P / (ms_per_step * 1e-3) / 1e9},
             "clocks": clocks.summary(),
         }
+        if sharded is not None:
+            line["sharded"] = sharded
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload)
         print(json.dumps(line))
