@@ -1,0 +1,98 @@
+"""The C++ experiment front-end (euler-_solver_-openmp-_b200/host): containers, input parsing, VisData output."""
+import csv
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "euler-_solver_-openmp-_b200")
+HOST = os.path.join(PKG, "host")
+REF_TEST = "/root/reference/Euler Solver ver.5.3/test_types.cpp"
+CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+
+
+def build_solver():
+    subprocess.check_call(["make", "-C", PKG, "host"], stdout=subprocess.DEVNULL)
+    return os.path.join(HOST, "solver")
+
+
+def test_own_container_test_passes(tmp_path):
+    exe = tmp_path / "containers"
+    subprocess.check_call([CXX, "-O1", "-std=c++17", "-I", HOST, "-o", str(exe), os.path.join(ROOT, "tests", "host", "test_containers.cpp")])
+    assert "containers ok" in subprocess.check_output([str(exe)], text=True)
+
+
+@pytest.mark.skipif(not os.path.exists(REF_TEST), reason="the reference is mounted only in the build container")
+def test_reference_test_types_passes_unchanged(tmp_path):
+    """the reference's own test_types.cpp, byte for byte, against host/types.h (fed on stdin so that its
+    `#include "types.h"` resolves to ours, not to the file next to it)"""
+    exe = tmp_path / "test_types"
+    with open(REF_TEST, "rb") as src:
+        subprocess.check_call([CXX, "-O1", "-std=c++17", "-x", "c++", "-o", str(exe), "-"], stdin=src, cwd=HOST)
+    assert "ALL TESTS COMPLETE" in subprocess.check_output([str(exe)], text=True)
+
+
+@pytest.mark.parametrize("choice,golden", [("14.4.a", "exp_14_4_a"), ("14.4.b", "exp_14_4_b"), ("14.4.c", "exp_14_4_c"),
+                                           ("14.6.a", "exp_14_6_a_080"), ("14.6.b", "exp_14_6_b_080")])
+def test_input_files_parse_like_the_reference(choice, golden):
+    """FileReader's three routes (Solver.cpp:745-815) on the CRLF inputs, host only: the generated model equals the
+    reference's (golden fixtures); for 14.6 the swept sigma is entry 80 of setLinSpaced(160, 1e-8, 0.2)."""
+    out = subprocess.check_output([build_solver(), "--data-dir", os.path.join(HOST, "Data"), "--describe", choice], text=True)
+    line = [l for l in out.splitlines() if l.startswith("DESCRIBE")][0]
+    got = dict(kv.split("=") for kv in line.split()[1:])
+    path = os.path.join(ROOT, "tests", "golden", golden + ".npz")
+    if not os.path.exists(path):          # 14.6b entry 80 has no fixture: check the route against the 14.6b file itself
+        assert float(got["sigmaW"]) == 0.05 and float(got["sigmaM"]) == 0.10062893578616353
+        return
+    g = np.load(path)
+    assert (int(got["G"]), int(got["K"]), int(float(got["mM"])), int(float(got["mW"]))) == (int(g["G"]), int(g["K"]), int(g["mM"]), int(g["mW"]))
+    for key, name in (("h", "h"), ("cutoff", "cutoff"), ("sigmaW", "sigmaW"), ("sigmaM", "sigmaM")):
+        assert float(got[key]) == float(g[name])
+
+
+def read_visdata(path):
+    """the parser half of the reference's Visualiser.py (V:23-45), positional"""
+    with open(path) as fh:
+        rows = list(csv.reader(fh))
+    number, title = float(rows[0][1]), rows[1][1]
+    n_plots, size = int(rows[3][1]), int(rows[6][1])
+    labels = rows[9]
+    data = np.array([[float(c) for c in r] for r in rows[10:]])
+    assert data.shape == (size, n_plots + 1)
+    return number, title, labels, data
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("choice,golden,title", [("14.4.b", "exp_14_4_b", "(b)"), ("1", "exp_14_4_b", "(b)"), ("14.4.c", "exp_14_4_c", "(c)")])
+def test_experiment_14_4_writes_visdata(tmp_path, choice, golden, title):
+    solver = build_solver()
+    os.makedirs(tmp_path / "Data")
+    subprocess.check_call(["cp", "-r", os.path.join(HOST, "Data", "14"), str(tmp_path / "Data")])
+    subprocess.check_call([solver, choice], cwd=tmp_path, stdout=subprocess.DEVNULL)
+    g = np.load(os.path.join(ROOT, "tests", "golden", golden + ".npz"))
+    for name in ("Data/VisData.csv", "Data\\VisData.csv"):       # Visualiser.py opens the literal backslash name (V:23)
+        number, got_title, labels, data = read_visdata(tmp_path / name)
+        assert number == 14.4 and got_title == title and labels == ["Time", "N", "Square root of C at cutoff distance"]
+        assert data.shape == (1001, 3)
+        want = np.stack([g["times"], g["obs"][:, 0], np.sqrt(g["obs"][:, 1])], 1)
+        assert np.allclose(data, want, rtol=1e-5, atol=0)          # the file carries 6 significant digits (S:856-858)
+    if golden == "exp_14_4_b":
+        last = open(tmp_path / "Data" / "VisData.csv").read().splitlines()[-1]
+        assert last == "100,89.4668,91.3041"                       # the row the unmodified reference writes
+
+
+@pytest.mark.gpu
+def test_experiment_14_6_b_sweep(tmp_path):
+    """the whole 160-entry sweep of Experiment_14_6('M') (Solver.cpp:1033-1071) as one batched call"""
+    solver = build_solver()
+    os.makedirs(tmp_path / "Data")
+    subprocess.check_call(["cp", "-r", os.path.join(HOST, "Data", "14"), str(tmp_path / "Data")])
+    subprocess.check_call([solver, "14.6.b"], cwd=tmp_path, stdout=subprocess.DEVNULL, timeout=900)
+    number, title, labels, data = read_visdata(tmp_path / "Data" / "VisData.csv")
+    assert number == 14.6 and title == "(b)" and labels[0] == "Dispersal radius" and data.shape == (160, 3)
+    for entry in (0, 12, 40, 159):
+        g = np.load(os.path.join(ROOT, "tests", "golden", f"exp_14_6_b_{entry:03d}.npz"))
+        want = [float(g["sigma"]), g["final_state"][0], np.sqrt(g["final_state"][int(g["G"])])]
+        assert np.allclose(data[entry], want, rtol=1e-5, atol=1e-30), (entry, data[entry], want)
