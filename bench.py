@@ -217,6 +217,52 @@ def run_sharded(ldm, torch, dist, workload, rank, world, local_rank, steps, warm
             "checksum": float(final_C.sum() + N_end)}
 
 
+def lattice_parameter_sets(count):
+    """BASELINE config 5: (b, d, sigma) sets around the exp 14.4 values on a fixed lattice -- index-derived, no RNG.
+    b in [0.3, 0.5], d in [0.1, 0.3], sigma_W = sigma_M in [0.05, 0.15]."""
+    sets = []
+    for i in range(count):
+        ib, idd, isg = i % 8, (i // 8) % 8, (i // 64) % 16
+        sets.append((0.05 + 0.1 * isg / 15.0, 0.3 + 0.2 * ib / 7.0, 0.1 + 0.2 * idd / 7.0))
+    return sets
+
+
+def run_batch(ldm, torch, dist, rank, world, local_rank, per_gpu, steps, G=64):
+    """the sigma-sweep loop (Solver.cpp:940-963) as a batch: per_gpu independent parameter sets on every GPU, all of them
+    advanced by ONE launch per kernel and step (blockIdx.z = set); no communication.  Weak scaling."""
+    sets = lattice_parameter_sets(per_gpu * world)[rank * per_gpu:(rank + 1) * per_gpu]
+    eqs, inits = [], []
+    t0 = time.perf_counter()
+    for sigma, b, d in sets:
+        props = ldm.Properties.Generate(1, sigma, sigma, b, d, 0.001, G)
+        eq = ldm.Equation(props, device=local_rank)
+        eqs.append(eq)
+        inits.append(seeded_state(props.MomentsGrid, sigma))
+    setup_s = time.perf_counter() - t0
+    t_max = (steps + 0.5) * DT
+    ldm.solve_batch(eqs, inits, DT, (2 + 0.5) * DT)                    # warm-up: builds the ring operators, loads the kernels
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    launches0 = eqs[0].launches
+    t0 = time.perf_counter()
+    outs = ldm.solve_batch(eqs, inits, DT, t_max)
+    wall_s = time.perf_counter() - t0
+    ms = eqs[0].last_elapsed_ms()                                      # CUDA events around the batched stepping loop
+    times = torch.tensor([ms, wall_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    ms, wall_ms = float(times[0]), float(times[1])
+    assert all(np.all(np.isfinite(o)) for o in outs)
+    P = G * G
+    flops = sum(algorithmic_flop_per_step(e.props)[0] for e in eqs)
+    return {"workload": f"{per_gpu} parameter sets per GPU, G={G} ({P} xi-points each), lattice of (b, d, sigma)", "sets": per_gpu * world,
+            "scaling": "weak", "steps": steps, "value": world * per_gpu * P * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+            "e2e_value": world * per_gpu * P * steps / (wall_ms * 1e-3), "gpu_launches": int(eqs[0].launches - launches0),
+            "algorithmic_tflops_per_gpu": flops * steps / (ms * 1e-3) / 1e12, "setup_s": setup_s,
+            "checksum": float(sum(o.sum() for o in outs))}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -227,6 +273,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sharded", default="g512", help="workload of the xi-sharded strong-scaling leg ('none' to skip)")
     ap.add_argument("--sharded-steps", type=int, default=10)
+    ap.add_argument("--batch-sets", type=int, default=128, help="parameter sets per GPU of the batched leg (0 to skip)")
+    ap.add_argument("--batch-steps", type=int, default=50)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -308,6 +356,10 @@ def main():
     if args.sharded != "none":
         sharded = run_sharded(ldm, torch, dist, args.sharded, rank, world, local_rank, args.sharded_steps, 2)
 
+    batch = None
+    if args.batch_sets > 0:
+        batch = run_batch(ldm, torch, dist, rank, world, local_rank, args.batch_sets, args.batch_steps)
+
     if rank == 0:
         ms_per_step = total_ms / args.steps
         achieved = flop_step / (ms_per_step * 1e-3) / 1e12
@@ -329,6 +381,8 @@ def main():
         }
         if sharded is not None:
             line["sharded"] = sharded
+        if batch is not None:
+            line["batch"] = batch
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload)
         print(json.dumps(line))

@@ -132,6 +132,19 @@ void ensure_ring_operator(ldm_context* c)
 
 // One right-hand side at the state (N_cur, C) for this rank's rows: scalars <- WC, dN; optional outputs:
 // sum_out (inside-sample sums), deriv_out (dC/dt), N_next / C_next (explicit-Euler update with clamp).
+ldm::StepArgs make_step_args(ldm_context* c, const double* C, const double* N_cur, double* N_next, double dt,
+                             double* sum_out, double* deriv_out, double* C_next)
+{
+    ldm::StepArgs a{};
+    a.P = c->dev;
+    a.C = C; a.N_cur = N_cur; a.N_next = N_next;
+    a.partial = c->d_partial; a.ring = c->d_ring; a.wc_rows = c->d_wc_rows; a.scalars = c->d_scalars;
+    a.sum_out = sum_out; a.deriv_out = deriv_out; a.C_next = C_next;
+    a.tiles = c->plan.tiles; a.chunks = c->plan.chunks;
+    a.dt = dt;
+    return a;
+}
+
 void rhs_and_update(ldm_context* c, const DevProblem& P, const double* C, const double* N_cur, double* N_next, double dt,
                     double* sum_out, double* deriv_out, double* C_next, cudaStream_t s)
 {
@@ -143,21 +156,20 @@ void rhs_and_update(ldm_context* c, const DevProblem& P, const double* C, const 
         return;
     }
     ensure_ring_operator(c);
-    const DevProblem& R = c->dev;       // the ring CSR pointers live in the handle's copy
+    const ldm::StepArgs args = make_step_args(c, C, N_cur, N_next, dt, sum_out, deriv_out, C_next);
     // the sparse ring correction only reads C: it runs on a side stream beside the (register-bound, one CTA per
     // SM) factored kernel and joins before the closing kernel
-    const bool side = R.n_ring > 0;
+    const bool side = args.P.n_ring > 0;
     if (side) {
         LDM_CUDA(cudaEventRecord(c->ev_fork, s));
         LDM_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
-        ldm::launch_ring(R, C, c->d_ring, c->aux_stream);
+        ldm::launch_ring(args, c->aux_stream);
         LDM_CUDA(cudaEventRecord(c->ev_join, c->aux_stream));
     }
-    ldm::launch_factored(R, c->plan, C, c->d_partial, c->d_wc_rows, s);
+    ldm::launch_factored(c->plan, args, s);
     if (side) LDM_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
-    ldm::launch_finish_factored(R, C, c->plan.slabs(), c->d_partial, c->d_ring, c->d_wc_rows, N_cur, N_next,
-                                c->d_scalars, dt, sum_out, deriv_out, C_next, s);
-    c->launches += 2 + (R.n_ring > 0 ? 1 : 0);
+    ldm::launch_finish_factored(args, s);
+    c->launches += 2 + (side ? 1 : 0);
 }
 
 void step_resident(ldm_context* c, double dt, double* deriv_out)
@@ -505,17 +517,97 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
     if (!(dt > 0)) return fail(LDM_ERR_ARGUMENT, "step must be positive");
     return guarded([&] {
         const int points = ldm_count_points(t_max, dt);
+        bool one_launch = n > 0;
         for (int i = 0; i < n; i++) {
             if (!handles[i] || !inits[i] || !last_states[i]) throw std::invalid_argument("NULL entry in batch");
-            LDM_CUDA(cudaSetDevice(handles[i]->device));
-            upload_state(handles[i], inits[i]);
+            ldm_context* h = handles[i];
+            LDM_CUDA(cudaSetDevice(h->device));
+            upload_state(h, inits[i]);
+            one_launch = one_launch && h->algo == LDM_ALGO_FACTORED && h->device == handles[0]->device && h->dev.world == 1;
         }
-        // every parameter set advances on its own stream: independent solves overlap on the device
-        for (int k = 0; k + 1 < points; k++)
+        for (int i = 0; i < n; i++) {
+            LDM_CUDA(cudaSetDevice(handles[i]->device));
+            LDM_CUDA(cudaStreamSynchronize(handles[i]->stream));
+        }
+        if (!one_launch) {
+            // mixed devices / algorithms: every parameter set advances on its own stream
+            for (int k = 0; k + 1 < points; k++)
+                for (int i = 0; i < n; i++) {
+                    LDM_CUDA(cudaSetDevice(handles[i]->device));
+                    step_resident(handles[i], dt, nullptr);
+                }
+        } else {
+            // All parameter sets of one tile shape advance in ONE launch per kernel: blockIdx.z is the set.
+            ldm_context* lead = handles[0];
+            LDM_CUDA(cudaSetDevice(lead->device));
+            struct Group {
+                ldm::FactoredPlan shape;
+                std::vector<int> members;
+                int max_slabs = 0, max_rows = 0, max_G = 0, max_A = 0, max_ring = 0, max_points = 0;
+                ldm::StepArgs* d_args[2] = {nullptr, nullptr};
+            };
+            std::vector<Group> groups;
             for (int i = 0; i < n; i++) {
-                LDM_CUDA(cudaSetDevice(handles[i]->device));
-                step_resident(handles[i], dt, nullptr);
+                ldm_context* h = handles[i];
+                ensure_ring_operator(h);
+                Group* g = nullptr;
+                for (Group& cand : groups)
+                    if (cand.shape.bm == h->plan.bm && cand.shape.bn == h->plan.bn) g = &cand;
+                if (!g) { groups.emplace_back(); g = &groups.back(); g->shape = h->plan; }
+                g->members.push_back(i);
+                g->max_slabs = std::max(g->max_slabs, h->plan.slabs());
+                g->max_rows = std::max(g->max_rows, h->dev.G);
+                g->max_G = std::max(g->max_G, h->dev.G);
+                g->max_A = std::max(g->max_A, h->dev.A);
+                g->max_ring = std::max(g->max_ring, h->dev.n_ring);
+                g->max_points = std::max(g->max_points, h->dev.G * h->dev.G);
             }
+            std::vector<void*> scratch;
+            try {
+                for (Group& g : groups)
+                    for (int parity = 0; parity < 2; parity++) {
+                        std::vector<ldm::StepArgs> host;
+                        for (int i : g.members) {
+                            ldm_context* h = handles[i];
+                            host.push_back(make_step_args(h, h->d_C[parity], h->d_N + parity, h->d_N + (parity ^ 1), dt, nullptr, nullptr,
+                                                          h->d_C[parity ^ 1]));
+                        }
+                        void* p = nullptr;
+                        LDM_CUDA(cudaMalloc(&p, host.size() * sizeof(ldm::StepArgs)));
+                        scratch.push_back(p);
+                        LDM_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(ldm::StepArgs), cudaMemcpyHostToDevice));
+                        g.d_args[parity] = static_cast<ldm::StepArgs*>(p);
+                    }
+                cudaStream_t s = lead->stream;
+                LDM_CUDA(cudaEventRecord(lead->ev_begin, s));
+                int parity = 0;
+                for (int k = 0; k + 1 < points; k++) {
+                    for (Group& g : groups) {
+                        const int members = (int)g.members.size();
+                        const bool side = g.max_ring > 0;
+                        if (side) {
+                            LDM_CUDA(cudaEventRecord(lead->ev_fork, s));
+                            LDM_CUDA(cudaStreamWaitEvent(lead->aux_stream, lead->ev_fork, 0));
+                            ldm::launch_ring_batch(g.d_args[parity], members, g.max_ring, lead->aux_stream);
+                            LDM_CUDA(cudaEventRecord(lead->ev_join, lead->aux_stream));
+                        }
+                        ldm::launch_factored_batch(g.shape, g.d_args[parity], members, g.max_slabs, g.max_rows, g.max_G, g.max_A, s);
+                        if (side) LDM_CUDA(cudaStreamWaitEvent(s, lead->ev_join, 0));
+                        ldm::launch_finish_factored_batch(g.d_args[parity], members, g.max_points, s);
+                        lead->launches += 2 + (side ? 1 : 0);
+                    }
+                    parity ^= 1;
+                }
+                LDM_CUDA(cudaEventRecord(lead->ev_end, s));
+                LDM_CUDA(cudaGetLastError());
+                LDM_CUDA(cudaStreamSynchronize(s));
+                for (int i = 0; i < n; i++) handles[i]->cur = parity;
+            } catch (...) {
+                for (void* p : scratch) cudaFree(p);
+                throw;
+            }
+            for (void* p : scratch) cudaFree(p);
+        }
         for (int i = 0; i < n; i++) {
             ldm_context* h = handles[i];
             LDM_CUDA(cudaSetDevice(h->device));

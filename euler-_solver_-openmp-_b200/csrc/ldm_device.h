@@ -37,6 +37,24 @@ struct DevProblem {
     const double* ring_weight;
 };
 
+// Everything one Euler step (or one right-hand side) of one problem touches.  Kernels take it by value for a single
+// problem, or index an array of them by blockIdx.z when a batch of independent parameter sets shares one launch.
+struct StepArgs {
+    DevProblem P;
+    const double* C;           // pair density at the old time, gathered layout (full replica)
+    const double* N_cur;       // first moment at the old time
+    double* N_next;            // may be NULL (right-hand side only)
+    double* partial;           // [slabs][local_rows][G] factored path
+    double* ring;              // [local_rows][G] ring correction (zero outside the listed nodes)
+    double* wc_rows;           // [G] per-row dot products of the WC operator
+    double* scalars;           // [kScalars] WC, dN/dt
+    double* sum_out;           // may be NULL: inside-sample sums
+    double* deriv_out;         // may be NULL: dC/dt of this rank's rows
+    double* C_next;            // may be NULL: updated rows
+    int tiles, chunks;         // factored plan: slab = tile * chunks + chunk
+    double dt;
+};
+
 // Which samples sample_sum accumulates (all use the same (x,o_i) x (y,o_j) enumeration):
 enum SampleMode {
     SAMPLES_INSIDE = 0,        // sum m * bilinear(C) over samples inside the cutoff circle  -> the direct algorithm
@@ -70,12 +88,12 @@ void launch_pointwise(const DevProblem& P, const double* C, const double* inside
 // Closing kernel of the factored path: inside_sum = sum_tiles partial - ring, WC from the per-row dot products,
 // the first-moment equation with its update (block 0), then the same pointwise assembly/update as above.
 // sum_out (may be NULL) receives inside_sum for ldm_integrals.
-void launch_finish_factored(const DevProblem& P, const double* C, int tiles, const double* partial, const double* ring,
-                            const double* wc_rows, const double* N_cur, double* N_next, double* scalars, double dt,
-                            double* sum_out, double* deriv_out, double* C_next, cudaStream_t stream);
+void launch_finish_factored(const StepArgs& one, cudaStream_t stream);
+void launch_finish_factored_batch(const StepArgs* d_batch, int n, int max_points, cudaStream_t stream);
 
-// ring[lx][y] for the nodes in P.ring_points (other entries of `ring` stay zero)
-void launch_ring(const DevProblem& P, const double* C, double* ring, cudaStream_t stream);
+// ring[lx][y] for the nodes of the ring CSR (other entries of `ring` stay zero)
+void launch_ring(const StepArgs& one, cudaStream_t stream);
+void launch_ring_batch(const StepArgs* d_batch, int n, int max_ring_rows, cudaStream_t stream);
 
 // Factored path (ldm_factored.cu): partial[slab][local_rows][G] <- per-slab sums over all samples inside the grid
 // square; the closing kernel forms inside_sum = sum_slabs partial - ring.
@@ -85,6 +103,9 @@ struct FactoredPlan {
     int slabs() const { return tiles * chunks; }
 };
 FactoredPlan plan_factored(const DevProblem& P);
-void launch_factored(const DevProblem& P, const FactoredPlan& plan, const double* C, double* partial, double* wc_rows, cudaStream_t stream);
+// single problem: `one` by value; batch: d_batch[n] in device memory, all entries sharing the plan's tile shape
+void launch_factored(const FactoredPlan& plan, const StepArgs& one, cudaStream_t stream);
+void launch_factored_batch(const FactoredPlan& shape, const StepArgs* d_batch, int n, int max_slabs, int max_rows, int max_G, int max_A,
+                           cudaStream_t stream);
 
 }  // namespace ldm

@@ -45,10 +45,12 @@ struct FactoredConfig {
     static_assert(BM % TM == 0 && BN % TN == 0 && TN % 2 == 0, "tile shape");
     static_assert((BK * BN) % NT == 0, "E chunk must divide evenly over the threads");
     static_assert(NT % BN == 0 && BK % (NT / BN) == 0, "a thread keeps one E column");
+    // an upper bound that is monotone in G and A (a batch launch sizes shared memory for its largest member):
+    // G * (1 + split) <= G + max(NT, G)
     static size_t smem_bytes(int G, int A)
     {
         const size_t a_pad = (size_t)((A + BK - 1) / BK) * BK;
-        return sizeof(double) * ((size_t)2 * BK * BM + (size_t)2 * BK * BN + (size_t)BM * HS_LD + (size_t)((G * (1 + (NT >= 2 * G ? NT / G : 1)) + 2 * BK + 3) & ~3) + 4 * a_pad) +
+        return sizeof(double) * ((size_t)2 * BK * BM + (size_t)2 * BK * BN + (size_t)BM * HS_LD + (size_t)((G + (NT > G ? NT : G) + 2 * BK + 3) & ~3) + 4 * a_pad) +
                sizeof(int) * 4 * a_pad;
     }
 };
@@ -59,10 +61,17 @@ __device__ __forceinline__ int folded_offset(int A, int n_fold, int alpha, int f
     return n_fold == 1 ? 0 : (f == 0 ? A - 1 - alpha : A + alpha);
 }
 
-template <int BM, int BN, int TM, int TN, int BK>
+template <int BM, int BN, int TM, int TN, int BK, bool BATCH>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
-factored_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__ partial, double* __restrict__ wc_rows)
+factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
 {
+    const StepArgs& S = BATCH ? batch[blockIdx.z] : one;
+    const DevProblem& P = S.P;
+    if (BATCH && ((int)blockIdx.x >= S.tiles * S.chunks || (int)blockIdx.y >= local_rows(P))) return;   // batch grids are padded
+    const double* __restrict__ C = S.C;
+    double* __restrict__ partial = S.partial;
+    double* __restrict__ wc_rows = S.wc_rows;
+    const int tile = blockIdx.x / S.chunks, chunk = blockIdx.x - tile * S.chunks;
     using Cfg = FactoredConfig<BM, BN, TM, TN, BK>;
     constexpr int TYN = Cfg::TYN, TXN = Cfg::TXN, NT = Cfg::NT, HS_LD = Cfg::HS_LD;
     constexpr int K_STRIDE = NT / BN;                     // E rows covered by one pass of the CTA's threads
@@ -70,8 +79,8 @@ factored_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__
     const int n_fold = n_off / A;
     const int lx = blockIdx.y;
     const int x = P.rank + P.world * lx;
-    const int b0 = blockIdx.x * BM;                       // first beta row of this tile
-    const int q0 = blockIdx.z * BN;                       // first column of this chunk
+    const int b0 = tile * BM;                             // first beta row of this tile
+    const int q0 = chunk * BN;                            // first column of this chunk
     const int tid = threadIdx.x;
     const int tx = tid % TXN, ty = tid / TXN;
     const int n_kc = (A + BK - 1) / BK;
@@ -247,12 +256,12 @@ factored_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__
         __syncthreads();
     }
 
-    double* out = partial + (((size_t)blockIdx.x * gridDim.z + blockIdx.z) * local_rows(P) + lx) * G;
+    double* out = partial + ((size_t)blockIdx.x * local_rows(P) + lx) * G;
     for (int y = tid; y < G; y += NT) out[y] = acc_y[y];
 
     // WC = <wc_operator, C> (Solver.cpp:265-274) row by row, folded into this launch: the first beta-tile of local
     // row lx covers rows lx*world .. lx*world+world-1 (every rank reduces the full operator, so no all-reduce)
-    if (blockIdx.x == 0 && blockIdx.z == 0 && wc_rows != nullptr) {
+    if (blockIdx.x == 0 && wc_rows != nullptr) {
         for (int r = tid / 32; r < P.world; r += NT / 32) {
             const int xr = lx * P.world + r;
             if (xr >= G) continue;
@@ -266,20 +275,32 @@ factored_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__
     }
 }
 
-template <int BM, int BN, int TM, int TN, int BK>
-void launch_variant(const DevProblem& P, const FactoredPlan& plan, const double* C, double* partial, double* wc_rows, cudaStream_t stream)
+template <int BM, int BN, int TM, int TN, int BK, bool BATCH>
+void launch_variant(const StepArgs* one, const StepArgs* d_batch, dim3 grid, int G, int A, cudaStream_t stream)
 {
     using Cfg = FactoredConfig<BM, BN, TM, TN, BK>;
-    const size_t smem = Cfg::smem_bytes(P.G, P.A);
+    const size_t smem = Cfg::smem_bytes(G, A);
     static bool configured[64] = {};                 // the opt-in is per device
     int device = 0;
     cudaGetDevice(&device);
     if (!configured[device & 63]) {
-        cudaFuncSetAttribute(factored_kernel<BM, BN, TM, TN, BK>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(factored_kernel<BM, BN, TM, TN, BK, BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         configured[device & 63] = true;
     }
-    dim3 grid(plan.tiles, local_rows(P), plan.chunks);
-    factored_kernel<BM, BN, TM, TN, BK><<<grid, Cfg::NT, smem, stream>>>(P, C, partial, wc_rows);
+    static const StepArgs none{};
+    factored_kernel<BM, BN, TM, TN, BK, BATCH><<<grid, Cfg::NT, smem, stream>>>(one ? *one : none, d_batch);
+}
+
+template <bool BATCH>
+void dispatch(const FactoredPlan& shape, const StepArgs* one, const StepArgs* d_batch, dim3 grid, int G, int A, cudaStream_t stream)
+{
+    if (shape.bm == 80) {
+        if (shape.bn == 64) launch_variant<80, 64, 5, 8, 16, BATCH>(one, d_batch, grid, G, A, stream);
+        else launch_variant<80, 128, 5, 8, 16, BATCH>(one, d_batch, grid, G, A, stream);
+    } else {
+        if (shape.bn == 64) launch_variant<40, 64, 5, 8, 16, BATCH>(one, d_batch, grid, G, A, stream);
+        else launch_variant<40, 128, 5, 8, 16, BATCH>(one, d_batch, grid, G, A, stream);
+    }
 }
 
 }  // namespace
@@ -306,15 +327,15 @@ FactoredPlan plan_factored(const DevProblem& P)
     return plan;
 }
 
-void launch_factored(const DevProblem& P, const FactoredPlan& plan, const double* C, double* partial, double* wc_rows, cudaStream_t stream)
+void launch_factored(const FactoredPlan& plan, const StepArgs& one, cudaStream_t stream)
 {
-    if (plan.bm == 80) {
-        if (plan.bn == 64) launch_variant<80, 64, 5, 8, 16>(P, plan, C, partial, wc_rows, stream);
-        else launch_variant<80, 128, 5, 8, 16>(P, plan, C, partial, wc_rows, stream);
-    } else {
-        if (plan.bn == 64) launch_variant<40, 64, 5, 8, 16>(P, plan, C, partial, wc_rows, stream);
-        else launch_variant<40, 128, 5, 8, 16>(P, plan, C, partial, wc_rows, stream);
-    }
+    dispatch<false>(plan, &one, nullptr, dim3(plan.slabs(), local_rows(one.P), 1), one.P.G, one.P.A, stream);
+}
+
+void launch_factored_batch(const FactoredPlan& shape, const StepArgs* d_batch, int n, int max_slabs, int max_rows, int max_G, int max_A,
+                           cudaStream_t stream)
+{
+    dispatch<true>(shape, nullptr, d_batch, dim3(max_slabs, max_rows, n), max_G, max_A, stream);
 }
 
 }  // namespace ldm

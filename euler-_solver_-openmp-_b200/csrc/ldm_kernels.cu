@@ -169,9 +169,14 @@ pointwise_kernel(DevProblem P, const double* __restrict__ C, const double* __res
 // ------------------------------------------------------------------------------------------------
 constexpr int kRingWarps = 8;
 
+template <bool BATCH>
 __global__ void __launch_bounds__(kWarp * kRingWarps)
-ring_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__ ring)
+ring_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
 {
+    const StepArgs& S = BATCH ? batch[blockIdx.z] : one;
+    const DevProblem& P = S.P;
+    const double* __restrict__ C = S.C;
+    double* __restrict__ ring = S.ring;
     const int row = blockIdx.x * kRingWarps + (threadIdx.x >> 5);
     if (row >= P.n_ring) return;
     const int lane = threadIdx.x & 31;
@@ -186,12 +191,25 @@ ring_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__ rin
 // Closing kernel of the factored path (see ldm_device.h).  Every CTA reduces the G per-row dot products of WC
 // in the same fixed order, so all CTAs hold the same WC; block 0 also advances the first moment.
 // ------------------------------------------------------------------------------------------------
+template <bool BATCH>
 __global__ void __launch_bounds__(256)
-finish_factored_kernel(DevProblem P, const double* __restrict__ C, int tiles, const double* __restrict__ partial,
-                       const double* __restrict__ ring, const double* __restrict__ wc_rows,
-                       const double* __restrict__ N_cur, double* __restrict__ N_next, double* __restrict__ scalars, double dt,
-                       double* __restrict__ sum_out, double* __restrict__ deriv_out, double* __restrict__ C_next)
+finish_factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
 {
+    const StepArgs& S = BATCH ? batch[blockIdx.z] : one;
+    const DevProblem& P = S.P;
+    if (BATCH && (int)(blockIdx.x * blockDim.x) >= local_rows(P) * P.G) return;      // batch grids are padded
+    const double* __restrict__ C = S.C;
+    const int tiles = S.tiles * S.chunks;
+    const double* __restrict__ partial = S.partial;
+    const double* __restrict__ ring = S.ring;
+    const double* __restrict__ wc_rows = S.wc_rows;
+    const double* __restrict__ N_cur = S.N_cur;
+    double* __restrict__ N_next = S.N_next;
+    double* __restrict__ scalars = S.scalars;
+    const double dt = S.dt;
+    double* __restrict__ sum_out = S.sum_out;
+    double* __restrict__ deriv_out = S.deriv_out;
+    double* __restrict__ C_next = S.C_next;
     __shared__ double red[256 / kWarp];
     __shared__ double wc_shared;
     const int G = P.G;
@@ -253,18 +271,29 @@ void launch_record_observables(const DevProblem& P, const double* N_cur, const d
     record_observables_kernel<<<1, 1, 0, stream>>>(P, N_cur, C, obs_row);
 }
 
-void launch_ring(const DevProblem& P, const double* C, double* ring, cudaStream_t stream)
+void launch_ring(const StepArgs& one, cudaStream_t stream)
 {
-    if (P.n_ring > 0) ring_kernel<<<(P.n_ring + kRingWarps - 1) / kRingWarps, kWarp * kRingWarps, 0, stream>>>(P, C, ring);
+    const int n = one.P.n_ring;
+    if (n > 0) ring_kernel<false><<<(n + kRingWarps - 1) / kRingWarps, kWarp * kRingWarps, 0, stream>>>(one, nullptr);
 }
 
-void launch_finish_factored(const DevProblem& P, const double* C, int tiles, const double* partial, const double* ring,
-                            const double* wc_rows, const double* N_cur, double* N_next, double* scalars, double dt,
-                            double* sum_out, double* deriv_out, double* C_next, cudaStream_t stream)
+void launch_ring_batch(const StepArgs* d_batch, int n, int max_ring_rows, cudaStream_t stream)
 {
-    const int n = local_rows(P) * P.G;
-    finish_factored_kernel<<<(n + 255) / 256, 256, 0, stream>>>(P, C, tiles, partial, ring, wc_rows, N_cur, N_next, scalars, dt,
-                                                               sum_out, deriv_out, C_next);
+    static const StepArgs none{};
+    if (max_ring_rows > 0)
+        ring_kernel<true><<<dim3((max_ring_rows + kRingWarps - 1) / kRingWarps, 1, n), kWarp * kRingWarps, 0, stream>>>(none, d_batch);
+}
+
+void launch_finish_factored(const StepArgs& one, cudaStream_t stream)
+{
+    const int n = local_rows(one.P) * one.P.G;
+    finish_factored_kernel<false><<<(n + 255) / 256, 256, 0, stream>>>(one, nullptr);
+}
+
+void launch_finish_factored_batch(const StepArgs* d_batch, int n, int max_points, cudaStream_t stream)
+{
+    static const StepArgs none{};
+    finish_factored_kernel<true><<<dim3((max_points + 255) / 256, 1, n), 256, 0, stream>>>(none, d_batch);
 }
 
 void launch_sample_sum(const DevProblem& P, SampleMode mode, const double* C, double* out, cudaStream_t stream)
