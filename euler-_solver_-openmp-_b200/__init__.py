@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIBRARY_PATH = os.path.join(_HERE, "libldm_b200.so")
+LIBRARY_PATH = os.environ.get("LDM_LIBRARY", os.path.join(_HERE, "libldm_b200.so"))   # LDM_LIBRARY: debug builds only
 
 ALGO_AUTO, ALGO_DIRECT, ALGO_FACTORED = 0, 1, 2
 RECORD_LAST, RECORD_OBSERVABLES, RECORD_VALUES, RECORD_ALL = 0, 1, 2, 3

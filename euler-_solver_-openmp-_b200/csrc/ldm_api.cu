@@ -552,7 +552,7 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
                 ensure_ring_operator(h);
                 Group* g = nullptr;
                 for (Group& cand : groups)
-                    if (cand.shape.bm == h->plan.bm && cand.shape.bn == h->plan.bn) g = &cand;
+                    if (cand.shape.bm == h->plan.bm && cand.shape.bn == h->plan.bn && cand.shape.tn == h->plan.tn && cand.shape.mma == h->plan.mma) g = &cand;
                 if (!g) { groups.emplace_back(); g = &groups.back(); g->shape = h->plan; }
                 g->members.push_back(i);
                 g->max_slabs = std::max(g->max_slabs, h->plan.slabs());

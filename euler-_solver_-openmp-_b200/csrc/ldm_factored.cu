@@ -25,6 +25,15 @@
 
 namespace ldm {
 
+// Optional phase timeline (build with -DLDM_PHASE_CLOCKS): thread 0 of every CTA stores clock64() at the phase
+// boundaries into the scalars array's debug tail; read back by tools/phase_clocks.py.  Off in the product build.
+#ifdef LDM_PHASE_CLOCKS
+__device__ long long g_phase_clock[148 * 4][12];
+#define PHASE_MARK(i) do { if (threadIdx.x == 0) g_phase_clock[(blockIdx.y * gridDim.x + blockIdx.x) % (148 * 4)][i] = clock64(); } while (0)
+#else
+#define PHASE_MARK(i) do { } while (0)
+#endif
+
 namespace {
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -34,12 +43,22 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
-template <int BM, int BN, int TM, int TN, int BK>
+template <int BM, int BN, int TM, int TN, int BK, bool MMA = false>
 struct FactoredConfig {
     static constexpr int TYN = BM / TM;            // thread rows
     static constexpr int TXN = BN / TN;            // thread columns
     static constexpr int NT = TYN * TXN;           // threads per CTA
     static constexpr int HS_LD = BN + 2;           // H staging row: 1 halo column + BN + 1 pad
+    // operand tiles in shared memory.  Thread-tile path: Q as [k][BM], E as [k][BN].  Tensor-core path (mma.sync
+    // m8n8k4 f64): Q as [beta][k] and E as [k][col] with row strides that spread the fragment reads over all banks.
+    static constexpr int LDQ = MMA ? BK + 4 : BM;
+    static constexpr int LDE = MMA ? BN + 4 : BN;
+    static constexpr int Q_TILE = MMA ? BM * LDQ : BK * BM;    // doubles per buffer
+    static constexpr int E_TILE = BK * LDE;
+    static constexpr int MB = BM / 8;                          // 8-row MMA blocks of the tile
+    static constexpr int WN = BN / (NT / 32);                  // columns owned by one warp
+    static constexpr int NB = WN / 8;
+    static_assert(!MMA || (BM % 8 == 0 && WN % 8 == 0 && BK % 4 == 0), "MMA tiling");
     static constexpr int E_PER_THREAD = (BK * BN) / NT;
     static constexpr int Q_PER_THREAD = (BK * BM + NT - 1) / NT;
     static_assert(BM % TM == 0 && BN % TN == 0 && TN % 2 == 0, "tile shape");
@@ -50,7 +69,7 @@ struct FactoredConfig {
     static size_t smem_bytes(int G, int A)
     {
         const size_t a_pad = (size_t)((A + BK - 1) / BK) * BK;
-        return sizeof(double) * ((size_t)2 * BK * BM + (size_t)2 * BK * BN + (size_t)BM * HS_LD + (size_t)((G + (NT > G ? NT : G) + 2 * BK + 3) & ~3) + 4 * a_pad) +
+        return sizeof(double) * ((size_t)2 * Q_TILE + (size_t)2 * E_TILE + (size_t)BM * HS_LD + (size_t)((G + (NT > G ? NT : G) + 2 * BK + 3) & ~3) + 4 * a_pad) +
                sizeof(int) * 4 * a_pad;
     }
 };
@@ -61,7 +80,13 @@ __device__ __forceinline__ int folded_offset(int A, int n_fold, int alpha, int f
     return n_fold == 1 ? 0 : (f == 0 ? A - 1 - alpha : A + alpha);
 }
 
-template <int BM, int BN, int TM, int TN, int BK, bool BATCH>
+__device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a, double b)
+{
+    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                 : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
+}
+
+template <int BM, int BN, int TM, int TN, int BK, bool BATCH, bool MMA>
 __global__ void __launch_bounds__((BM / TM) * (BN / TN))
 factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
 {
@@ -72,8 +97,10 @@ factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
     double* __restrict__ partial = S.partial;
     double* __restrict__ wc_rows = S.wc_rows;
     const int tile = blockIdx.x / S.chunks, chunk = blockIdx.x - tile * S.chunks;
-    using Cfg = FactoredConfig<BM, BN, TM, TN, BK>;
+    PHASE_MARK(0);
+    using Cfg = FactoredConfig<BM, BN, TM, TN, BK, MMA>;
     constexpr int TYN = Cfg::TYN, TXN = Cfg::TXN, NT = Cfg::NT, HS_LD = Cfg::HS_LD;
+    constexpr int LDQ = Cfg::LDQ, LDE = Cfg::LDE, Q_TILE = Cfg::Q_TILE, E_TILE = Cfg::E_TILE;
     constexpr int K_STRIDE = NT / BN;                     // E rows covered by one pass of the CTA's threads
     const int G = P.G, A = P.A, n_off = P.n_off;
     const int n_fold = n_off / A;
@@ -87,9 +114,9 @@ factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
     const int A_pad = n_kc * BK;
 
     extern __shared__ __align__(32) double smem[];
-    double* Qs = smem;                                    // [2][BK][BM]
-    double* Es = Qs + 2 * BK * BM;                        // [2][BK][BN]
-    double* Hs = Es + 2 * BK * BN;                        // [BM][HS_LD]
+    double* Qs = smem;                                    // [2][Q_TILE]
+    double* Es = Qs + 2 * Q_TILE;                         // [2][E_TILE]
+    double* Hs = Es + 2 * E_TILE;                         // [BM][HS_LD]
     double* acc_y = Hs + BM * HS_LD;                      // [G]
     const int split = NT >= 2 * G ? NT / G : 1;           // threads sharing one y in the y-side pass
     double* part_y = acc_y + G;                           // [split][G]
@@ -116,10 +143,11 @@ factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
     }
     for (int y = tid; y < G; y += NT) acc_y[y] = 0.0;
     __syncthreads();
+    PHASE_MARK(1);
 
-    double e_reg[Cfg::E_PER_THREAD];
+    double c_raw[Cfg::E_PER_THREAD][4];                   // the four C values behind each E element of the next chunk
     double q_reg[Cfg::Q_PER_THREAD];
-    double eh_reg = 0.0;                                  // threads < BK: E[alpha][q0-1]
+    double h_raw[4] = {0.0, 0.0, 0.0, 0.0};               // threads < BK: the same for the halo column q0-1
     double h_acc = 0.0;                                   // threads < BM: H[b0 + tid][q0-1]
     const bool want_halo = q0 > 0;
     const int e_col = tid % BN, e_k0 = tid / BN;          // this thread's E column and first row within a chunk
@@ -129,118 +157,172 @@ factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
         const double* c_col = C + (q < G ? q : G - 1);    // clamped: columns beyond G are multiplied by 0 below
         const double live = q < G ? 1.0 : 0.0;
 
-        auto load_chunk = [&](int kc) {
+        // Next chunk of E and Q in two halves: `issue_chunk` only issues the global loads (raw C values, Q entries) so that
+        // they fly under the contraction of the current chunk; `finish_chunk` does the interpolation arithmetic and the
+        // shared-memory stores afterwards.  (Doing the arithmetic up front would park every warp on L2 latency.)
+        auto issue_chunk = [&](int kc) {
             #pragma unroll
             for (int r = 0; r < Cfg::E_PER_THREAD; r++) {
                 const int alpha = kc * BK + r * K_STRIDE + e_k0;           // < A_pad; rows beyond A carry zero weights
-                const double4 wa = *reinterpret_cast<const double4*>(tap_w + alpha * 4);
                 const int4 ra = *reinterpret_cast<const int4*>(tap_row + alpha * 4);
-                e_reg[r] = (c_col[ra.x] * wa.x + c_col[ra.y] * wa.y) + (c_col[ra.z] * wa.z + c_col[ra.w] * wa.w);
+                c_raw[r][0] = c_col[ra.x]; c_raw[r][1] = c_col[ra.y]; c_raw[r][2] = c_col[ra.z]; c_raw[r][3] = c_col[ra.w];
             }
             if (want_halo && tid < BK) {
                 const int alpha = kc * BK + tid;
                 const double* c_h = C + (q0 - 1);
-                const double4 wa = *reinterpret_cast<const double4*>(tap_w + alpha * 4);
                 const int4 ra = *reinterpret_cast<const int4*>(tap_row + alpha * 4);
-                eh_reg = (c_h[ra.x] * wa.x + c_h[ra.y] * wa.y) + (c_h[ra.z] * wa.z + c_h[ra.w] * wa.w);
+                h_raw[0] = c_h[ra.x]; h_raw[1] = c_h[ra.y]; h_raw[2] = c_h[ra.z]; h_raw[3] = c_h[ra.w];
             }
             #pragma unroll
             for (int r = 0; r < Cfg::Q_PER_THREAD; r++) {
                 const int e = r * NT + tid;
-                const int k = e / BM, bm = e - k * BM;     // Q is symmetric: read it alpha-major so consecutive threads
-                const int beta = b0 + bm, alpha = kc * BK + k;   // take consecutive beta (coalesced, conflict-free store)
-                q_reg[r] = (e < BK * BM && beta < A && alpha < A) ? P.quadrant[(size_t)alpha * A + beta] : 0.0;
+                // Q is symmetric, so it can be read along whichever index the shared-memory layout wants contiguous:
+                // consecutive threads take consecutive beta ([k][BM] layout) or consecutive alpha ([beta][k] layout)
+                const int k = MMA ? e % BK : e / BM, bm = MMA ? e / BK : e % BM;
+                const int beta = b0 + bm, alpha = kc * BK + k;
+                q_reg[r] = (e < BK * BM && beta < A && alpha < A)
+                               ? (MMA ? P.quadrant[(size_t)beta * A + alpha] : P.quadrant[(size_t)alpha * A + beta]) : 0.0;
             }
         };
-        auto store_chunk = [&](int buf) {
+        auto finish_chunk = [&](int kc, int buf) {
             #pragma unroll
-            for (int r = 0; r < Cfg::E_PER_THREAD; r++)
-                Es[buf * BK * BN + (r * K_STRIDE + e_k0) * BN + e_col] = e_reg[r] * live;
-            if (want_halo && tid < BK) Eh[buf * BK + tid] = eh_reg;
+            for (int r = 0; r < Cfg::E_PER_THREAD; r++) {
+                const int alpha = kc * BK + r * K_STRIDE + e_k0;
+                const double4 wa = *reinterpret_cast<const double4*>(tap_w + alpha * 4);
+                const double v = (c_raw[r][0] * wa.x + c_raw[r][1] * wa.y) + (c_raw[r][2] * wa.z + c_raw[r][3] * wa.w);
+                Es[buf * E_TILE + (r * K_STRIDE + e_k0) * LDE + e_col] = v * live;
+            }
+            if (want_halo && tid < BK) {
+                const double4 wa = *reinterpret_cast<const double4*>(tap_w + (kc * BK + tid) * 4);
+                Eh[buf * BK + tid] = (h_raw[0] * wa.x + h_raw[1] * wa.y) + (h_raw[2] * wa.z + h_raw[3] * wa.w);
+            }
             #pragma unroll
             for (int r = 0; r < Cfg::Q_PER_THREAD; r++) {
                 const int e = r * NT + tid;
-                if (e < BK * BM) Qs[buf * BK * BM + e] = q_reg[r];
+                if (e < BK * BM) Qs[buf * Q_TILE + (MMA ? (e / BK) * LDQ + e % BK : e)] = q_reg[r];
             }
         };
 
-        double acc[TM][TN];
+        // accumulators: a TM x TN register tile per thread, or MB x NB tensor-core fragments (2 doubles each) per warp
+        constexpr int ACC_A = MMA ? Cfg::MB : TM, ACC_B = MMA ? Cfg::NB * 2 : TN;
+        double acc[ACC_A][ACC_B];
         #pragma unroll
-        for (int i = 0; i < TM; i++)
+        for (int i = 0; i < ACC_A; i++)
             #pragma unroll
-            for (int j = 0; j < TN; j++) acc[i][j] = 0.0;
+            for (int j = 0; j < ACC_B; j++) acc[i][j] = 0.0;
+        const int lane_g = (tid & 31) >> 2, lane_t = tid & 3;       // MMA fragment coordinates of this lane
+        const int wn0 = (tid >> 5) * Cfg::WN;                        // first column of this warp's strip
 
-        load_chunk(0);
-        store_chunk(0);
+        issue_chunk(0);
+        finish_chunk(0, 0);
         __syncthreads();
+        PHASE_MARK(2);
         for (int kc = 0; kc < n_kc; kc++) {
             const int buf = kc & 1;
-            if (kc + 1 < n_kc) load_chunk(kc + 1);               // global loads in flight under the FMAs
-            const double* qs = Qs + buf * BK * BM;
-            const double* es = Es + buf * BK * BN;
-            #pragma unroll
-            for (int k = 0; k < BK; k++) {
-                double a[TM], b[TN];
+            if (kc + 1 < n_kc) issue_chunk(kc + 1);              // global loads in flight under the contraction
+            const double* qs = Qs + buf * Q_TILE;
+            const double* es = Es + buf * E_TILE;
+            if constexpr (MMA) {
+                // FP64 tensor cores: D(8x8) += A(8x4) B(4x8); lane (g, t) holds A[g][t], B[t][g], D[g][2t..2t+1]
                 #pragma unroll
-                for (int i = 0; i < TM; i++) a[i] = qs[k * BM + i * TYN + ty];
-                #pragma unroll
-                for (int j = 0; j < TN; j += 2) {                // 16-byte loads, consecutive threads -> consecutive 16 B
-                    const double2 v = *reinterpret_cast<const double2*>(es + k * BN + (j / 2) * (2 * TXN) + tx * 2);
-                    b[j] = v.x; b[j + 1] = v.y;
-                }
-                #pragma unroll
-                for (int i = 0; i < TM; i++)
+                for (int k4 = 0; k4 < BK; k4 += 4) {
+                    double af[Cfg::MB], bf[Cfg::NB];
                     #pragma unroll
-                    for (int j = 0; j < TN; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+                    for (int mb = 0; mb < Cfg::MB; mb++) af[mb] = qs[(mb * 8 + lane_g) * LDQ + k4 + lane_t];
+                    #pragma unroll
+                    for (int nb = 0; nb < Cfg::NB; nb++) bf[nb] = es[(k4 + lane_t) * LDE + wn0 + nb * 8 + lane_g];
+                    #pragma unroll
+                    for (int mb = 0; mb < Cfg::MB; mb++)
+                        #pragma unroll
+                        for (int nb = 0; nb < Cfg::NB; nb++)
+                            dmma_8x8x4(*reinterpret_cast<double(*)[2]>(&acc[mb][nb * 2]), af[mb], bf[nb]);
+                }
+            } else {
+                #pragma unroll
+                for (int k = 0; k < BK; k++) {
+                    double a[TM], b[TN];
+                    #pragma unroll
+                    for (int i = 0; i < TM; i++) a[i] = qs[k * BM + i * TYN + ty];
+                    #pragma unroll
+                    for (int j = 0; j < TN; j += 2) {            // 16-byte loads, consecutive threads -> consecutive 16 B
+                        const double2 v = *reinterpret_cast<const double2*>(es + k * BN + (j / 2) * (2 * TXN) + tx * 2);
+                        b[j] = v.x; b[j + 1] = v.y;
+                    }
+                    #pragma unroll
+                    for (int i = 0; i < TM; i++)
+                        #pragma unroll
+                        for (int j = 0; j < TN; j++) acc[i][j] = fma(a[i], b[j], acc[i][j]);
+                }
             }
             if (want_halo && tid < BM) {
                 #pragma unroll
-                for (int k = 0; k < BK; k++) h_acc = fma(qs[k * BM + tid], Eh[buf * BK + k], h_acc);
+                for (int k = 0; k < BK; k++) h_acc = fma(qs[MMA ? tid * LDQ + k : k * BM + tid], Eh[buf * BK + k], h_acc);
             }
-            if (kc + 1 < n_kc) store_chunk(buf ^ 1);
+            if (kc + 1 < n_kc) finish_chunk(kc + 1, buf ^ 1);
             __syncthreads();
         }
 
+        PHASE_MARK(3);
         // stage the H tile: Hs[row][1 + col]; column 0 is the halo column q0-1
         if (tid < BM) Hs[tid * HS_LD] = h_acc;
-        #pragma unroll
-        for (int i = 0; i < TM; i++)
+        if constexpr (MMA) {
             #pragma unroll
-            for (int j = 0; j < TN; j++)
-                Hs[(i * TYN + ty) * HS_LD + 1 + (j / 2) * (2 * TXN) + tx * 2 + (j & 1)] = acc[i][j];
+            for (int mb = 0; mb < Cfg::MB; mb++)
+                #pragma unroll
+                for (int nb = 0; nb < Cfg::NB; nb++) {
+                    double* dst = Hs + (mb * 8 + lane_g) * HS_LD + 1 + wn0 + nb * 8 + lane_t * 2;
+                    dst[0] = acc[mb][nb * 2];
+                    dst[1] = acc[mb][nb * 2 + 1];
+                }
+        } else {
+            #pragma unroll
+            for (int i = 0; i < TM; i++)
+                #pragma unroll
+                for (int j = 0; j < TN; j++)
+                    Hs[(i * TYN + ty) * HS_LD + 1 + (j / 2) * (2 * TXN) + tx * 2 + (j & 1)] = acc[i][j];
+        }
         __syncthreads();
 
+        PHASE_MARK(4);
         // y side: every tap pair (u-1, u) whose upper node u falls in this chunk.  Consecutive threads own consecutive y
         // (the transposed tables upper_t / weight_t make those reads contiguous); `split` threads share one y, each
         // taking every split-th beta row, so every thread runs a long loop of independent loads.
+        // y side: every tap pair (u-1, u) whose upper node u falls in this chunk.  Consecutive threads own consecutive y
+        // (the transposed tables make those reads contiguous); `split` threads share one y, each taking every split-th
+        // beta row, so every thread runs a long branch-free loop of independent table reads.  With all CTAs in this
+        // phase at the same time it is L2-bandwidth bound (12 B per tap pair); recomputing the weights from node tables
+        // in shared memory instead was tried and is slower (scattered 8-byte shared-memory gathers).
+        // A sample beyond the grid is tabulated as (u = 0, w = 0): in chunk 0 it reads 1 * halo + 0 * H[0], and the halo
+        // column of chunk 0 is zero, so no validity test is needed; pairs of other chunks drop out by select.
         const int rows_here = min(BM, A - b0);
         const double* hbase = Hs + 1 - q0;
+        const bool whole_row = (S.chunks == 1);            // every tap pair lands in this chunk: no range test needed
         for (int idx = tid; idx < G * split; idx += NT) {
             const int part = idx / G, y = idx - part * G;
             double s = 0.0;
             for (int f = 0; f < n_fold; f++) {
                 const int o0 = folded_offset(A, n_fold, b0, f);
                 const int dir = (n_fold == 2 && f == 0) ? -1 : 1;
-                // batches of kBatch table reads issued together (they come from L2), then the shared-memory gathers;
-                // branch-free: a tap pair outside this chunk is redirected to column q0 with weight 0
-                constexpr int kBatch = 8;
-                for (int bm0 = part; bm0 < rows_here; bm0 += split * kBatch) {
-                    int u[kBatch];
-                    double w[kBatch];
-                    #pragma unroll
-                    for (int r = 0; r < kBatch; r++) {
-                        const int bm = min(bm0 + r * split, rows_here - 1);
-                        const size_t c = (size_t)(o0 + dir * bm) * G + y;
-                        u[r] = P.upper_t[c];
-                        w[r] = P.weight_t[c];
+                const int* up = P.upper_t + (size_t)o0 * G + y;
+                const double* wp = P.weight_t + (size_t)o0 * G + y;
+                const int stride = dir * G;
+                if (whole_row) {
+                    #pragma unroll 8
+                    for (int bm = part; bm < rows_here; bm += split) {
+                        const int u = up[bm * stride];
+                        const double w = wp[bm * stride];
+                        const double* hrow = hbase + bm * HS_LD;
+                        s += hrow[u - 1] * (1.0 - w) + hrow[u] * w;
                     }
-                    #pragma unroll
-                    for (int r = 0; r < kBatch; r++) {
-                        const int bm = bm0 + r * split;
-                        const bool live = bm < rows_here && u[r] >= q0 && u[r] < q0 + BN && u[r] != 0;
-                        const int uc = live ? u[r] : q0;
-                        const double* hrow = hbase + min(bm, rows_here - 1) * HS_LD;
-                        const double v = hrow[uc - 1] * (1.0 - w[r]) + hrow[uc] * w[r];
+                } else {
+                    #pragma unroll 8
+                    for (int bm = part; bm < rows_here; bm += split) {
+                        const int u = up[bm * stride];
+                        const double w = wp[bm * stride];
+                        const bool live = (unsigned)(u - q0) < (unsigned)BN;
+                        const int uc = live ? u : q0;
+                        const double* hrow = hbase + bm * HS_LD;
+                        const double v = hrow[uc - 1] * (1.0 - w) + hrow[uc] * w;
                         s += live ? v : 0.0;
                     }
                 }
@@ -256,6 +338,7 @@ factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
         __syncthreads();
     }
 
+    PHASE_MARK(5);
     double* out = partial + ((size_t)blockIdx.x * local_rows(P) + lx) * G;
     for (int y = tid; y < G; y += NT) out[y] = acc_y[y];
 
@@ -273,34 +356,44 @@ factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
             if (tid % 32 == 0) wc_rows[xr] = s;
         }
     }
+    PHASE_MARK(6);
 }
 
-template <int BM, int BN, int TM, int TN, int BK, bool BATCH>
+template <int BM, int BN, int TM, int TN, int BK, bool BATCH, bool MMA>
 void launch_variant(const StepArgs* one, const StepArgs* d_batch, dim3 grid, int G, int A, cudaStream_t stream)
 {
-    using Cfg = FactoredConfig<BM, BN, TM, TN, BK>;
+    using Cfg = FactoredConfig<BM, BN, TM, TN, BK, MMA>;
     const size_t smem = Cfg::smem_bytes(G, A);
     static bool configured[64] = {};                 // the opt-in is per device
     int device = 0;
     cudaGetDevice(&device);
     if (!configured[device & 63]) {
-        cudaFuncSetAttribute(factored_kernel<BM, BN, TM, TN, BK, BATCH>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
+        cudaFuncSetAttribute(factored_kernel<BM, BN, TM, TN, BK, BATCH, MMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
         configured[device & 63] = true;
     }
     static const StepArgs none{};
-    factored_kernel<BM, BN, TM, TN, BK, BATCH><<<grid, Cfg::NT, smem, stream>>>(one ? *one : none, d_batch);
+    factored_kernel<BM, BN, TM, TN, BK, BATCH, MMA><<<grid, Cfg::NT, smem, stream>>>(one ? *one : none, d_batch);
 }
 
 template <bool BATCH>
 void dispatch(const FactoredPlan& shape, const StepArgs* one, const StepArgs* d_batch, dim3 grid, int G, int A, cudaStream_t stream)
 {
-    if (shape.bm == 80) {
-        if (shape.bn == 64) launch_variant<80, 64, 5, 8, 16, BATCH>(one, d_batch, grid, G, A, stream);
-        else launch_variant<80, 128, 5, 8, 16, BATCH>(one, d_batch, grid, G, A, stream);
-    } else {
-        if (shape.bn == 64) launch_variant<40, 64, 5, 8, 16, BATCH>(one, d_batch, grid, G, A, stream);
-        else launch_variant<40, 128, 5, 8, 16, BATCH>(one, d_batch, grid, G, A, stream);
+    if (shape.mma) {              // FP64 tensor cores (DMMA) for the contraction: the default
+        if (shape.bm == 80 && shape.bn == 128) return launch_variant<80, 128, 5, 8, 16, BATCH, true>(one, d_batch, grid, G, A, stream);
+        if (shape.bm == 80 && shape.bn == 64) return launch_variant<80, 64, 5, 8, 16, BATCH, true>(one, d_batch, grid, G, A, stream);
+        if (shape.bm == 40 && shape.bn == 128) return launch_variant<40, 128, 5, 8, 16, BATCH, true>(one, d_batch, grid, G, A, stream);
+        return launch_variant<40, 64, 5, 8, 16, BATCH, true>(one, d_batch, grid, G, A, stream);
     }
+    if (shape.tn == 4) {          // twice the threads per tile: more warps to hide the gather phases
+        if (shape.bm == 80 && shape.bn == 128) return launch_variant<80, 128, 5, 4, 16, BATCH, false>(one, d_batch, grid, G, A, stream);
+        if (shape.bm == 80 && shape.bn == 64) return launch_variant<80, 64, 5, 4, 16, BATCH, false>(one, d_batch, grid, G, A, stream);
+        if (shape.bm == 40 && shape.bn == 128) return launch_variant<40, 128, 5, 4, 16, BATCH, false>(one, d_batch, grid, G, A, stream);
+        return launch_variant<40, 64, 5, 4, 16, BATCH, false>(one, d_batch, grid, G, A, stream);
+    }
+    if (shape.bm == 80 && shape.bn == 128) return launch_variant<80, 128, 5, 8, 16, BATCH, false>(one, d_batch, grid, G, A, stream);
+    if (shape.bm == 80 && shape.bn == 64) return launch_variant<80, 64, 5, 8, 16, BATCH, false>(one, d_batch, grid, G, A, stream);
+    if (shape.bm == 40 && shape.bn == 128) return launch_variant<40, 128, 5, 8, 16, BATCH, false>(one, d_batch, grid, G, A, stream);
+    return launch_variant<40, 64, 5, 8, 16, BATCH, false>(one, d_batch, grid, G, A, stream);
 }
 
 }  // namespace
@@ -318,6 +411,11 @@ FactoredPlan plan_factored(const DevProblem& P)
         const int v = std::atoi(env);
         if (v == 64 || v == 128) plan.bn = v;
     }
+    if (const char* env = std::getenv("LDM_FACTORED_MMA")) plan.mma = std::atoi(env) != 0;
+    if (const char* env = std::getenv("LDM_FACTORED_TN")) {
+        const int v = std::atoi(env);
+        if (v == 4 || v == 8) plan.tn = v;
+    }
     if (const char* env = std::getenv("LDM_FACTORED_BM")) {
         const int v = std::atoi(env);
         if (v == 40 || v == 80) plan.bm = v;
@@ -326,6 +424,14 @@ FactoredPlan plan_factored(const DevProblem& P)
     plan.chunks = (P.G + plan.bn - 1) / plan.bn;
     return plan;
 }
+
+#ifdef LDM_PHASE_CLOCKS
+extern "C" int ldm_debug_phase_clocks(long long* out, int rows)
+{
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, g_phase_clock, sizeof(long long) * 12 * (size_t)rows);
+}
+#endif
 
 void launch_factored(const FactoredPlan& plan, const StepArgs& one, cudaStream_t stream)
 {
