@@ -33,6 +33,7 @@ struct DevProblem {
     int n_ring;                // CSR rows
     const int* ring_point;     // [n_ring] local_row * G + y
     const int* ring_begin;     // [n_ring + 1]
+    const int* ring_row_begin; // [local_rows + 1] first CSR row of each local moment-grid row
     const int* ring_node;      // C index (gathered layout)
     const double* ring_weight;
 };
@@ -52,6 +53,11 @@ struct StepArgs {
     double* deriv_out;         // may be NULL: dC/dt of this rank's rows
     double* C_next;            // may be NULL: updated rows
     int tiles, chunks;         // factored plan: slab = tile * chunks + chunk
+    // fused step (one slab per row, one rank): the factored kernel also applies the ring correction and the update;
+    // WC comes from wc_in (row dots of the current C) and the row dots of the new C are left in wc_out
+    int fused;
+    const double* wc_in;
+    double* wc_out;
     double dt;
 };
 
@@ -73,6 +79,7 @@ __host__ __device__ inline int local_rows(const DevProblem& P) { return (P.G - P
 
 // C is always the full pair density in gathered layout; `out`, inside_sum, deriv_out, C_next are
 // shard-local [local_rows][G].
+void launch_wc_rows(const DevProblem& P, const double* C, double* wc_rows, cudaStream_t stream);
 void launch_record_observables(const DevProblem& P, const double* N_cur, const double* C, double* obs_row, cudaStream_t stream);
 
 void launch_sample_sum(const DevProblem& P, SampleMode mode, const double* C, double* out, cudaStream_t stream);

@@ -22,6 +22,7 @@
 #include <cstdlib>
 
 #include "ldm_device.h"
+#include "ldm_pointwise.cuh"
 
 namespace ldm {
 
@@ -339,6 +340,48 @@ factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
     }
 
     PHASE_MARK(5);
+    if (S.fused) {
+        // ---- the whole step in this launch (one slab per row, one rank): ring correction, closure, Euler update ----
+        // WC of the CURRENT C comes from per-row dots written one step earlier (or by wc_rows_kernel after an upload),
+        // so no grid-wide reduction is needed; this CTA leaves the row dot of its NEW row for the next step.
+        double& wc_sh = Eh[0];                                                     // the halo staging is dead by now
+        if (tid < 32) {
+            const double v = wc_total(S.wc_in, G, tid);
+            if (tid == 0) wc_sh = v;
+        }
+        const int ring_lo = P.ring_row_begin[lx], ring_hi = P.ring_row_begin[lx + 1];
+        for (int row = ring_lo + tid / 32; row < ring_hi; row += NT / 32) {       // this row's ring nodes: one warp each
+            double a = 0.0;
+            for (int en = P.ring_begin[row] + tid % 32; en < P.ring_begin[row + 1]; en += 32) a += P.ring_weight[en] * C[P.ring_node[en]];
+            a = warp_sum(a);
+            if (tid % 32 == 0) acc_y[P.ring_point[row] - lx * G] -= a;
+        }
+        __syncthreads();
+        const double N = S.N_cur[0];
+        const double WC = (wc_sh + (N * N) * P.wc_outside) * P.hh;                 // Solver.cpp:311, 314
+        if (lx == 0 && tid == 0) first_moment_update(P, N, WC, S.dt, S.scalars, S.N_next);
+        double* c_new = part_y;                                                    // staging of the updated row
+        for (int y = tid; y < G; y += NT) {
+            const int q = x * G + y;
+            const double inside = acc_y[y];
+            if (S.sum_out) S.sum_out[q] = inside;
+            const double c = C[q];
+            const double mc = (inside + (N * N) * P.out_weight[q]) * P.hh;
+            const double dc = second_moment_rhs(P, mc, c, N, WC, P.m_nodes[q], P.w_nodes[q]);
+            if (S.deriv_out) S.deriv_out[q] = dc;
+            double v = __dadd_rn(c, __dmul_rn(dc, S.dt));                          // Solver.cpp:577
+            v = v < 0.0 ? 0.0 : v;                                                 // Solver.cpp:578-580
+            S.C_next[q] = v;
+            c_new[y] = v;
+        }
+        __syncthreads();
+        if (tid < 32) {
+            const double s = wc_row_dot(P.wc_operator + (size_t)x * G, c_new, G, tid);
+            if (tid == 0) S.wc_out[x] = s;
+        }
+        PHASE_MARK(6);
+        return;
+    }
     double* out = partial + ((size_t)blockIdx.x * local_rows(P) + lx) * G;
     for (int y = tid; y < G; y += NT) out[y] = acc_y[y];
 
@@ -348,11 +391,7 @@ factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
         for (int r = tid / 32; r < P.world; r += NT / 32) {
             const int xr = lx * P.world + r;
             if (xr >= G) continue;
-            const double* op = P.wc_operator + (size_t)xr * G;
-            const double* crow = C + (size_t)row_slot(P, xr) * G;
-            double s = 0.0;
-            for (int y = tid % 32; y < G; y += 32) s += op[y] * crow[y];
-            s = warp_sum(s);
+            const double s = wc_row_dot(P.wc_operator + (size_t)xr * G, C + (size_t)row_slot(P, xr) * G, G, tid % 32);
             if (tid % 32 == 0) wc_rows[xr] = s;
         }
     }

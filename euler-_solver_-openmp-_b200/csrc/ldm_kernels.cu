@@ -3,6 +3,7 @@
 //
 // S:n = "/root/reference/Euler Solver ver.5.3/Solver.cpp" line n.
 #include "ldm_device.h"
+#include "ldm_pointwise.cuh"
 
 namespace ldm {
 
@@ -124,23 +125,6 @@ wc_kernel(DevProblem P, const double* __restrict__ C, const double* __restrict__
 // Pointwise assembly of dC (S:459-508), in the reference's operation order with no contraction, then
 // value + derivative*step and the clamp (S:577-580).
 // ------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double second_moment_rhs(const DevProblem& P, double mc, double c, double N, double WC,
-                                                    double m_node, double w_node)
-{
-    double r = __dadd_rn(__dmul_rn(P.b, mc), __dmul_rn(P.b, mc));                   // S:464 (i == j: both terms)
-    r = __dadd_rn(r, __dmul_rn(__dmul_rn(__dmul_rn(2.0, P.b), N), m_node));         // S:469
-    const double death = __dmul_rn(P.d, c);
-    r = __dsub_rn(r, death);                                                        // S:480
-    r = __dsub_rn(r, death);                                                        // S:481
-    const double closure = __ddiv_rn(__dmul_rn(__dmul_rn(P.dd, WC), c), N);         // S:486
-    r = __dsub_rn(r, closure);
-    r = __dsub_rn(r, closure);                                                      // S:487
-    const double local = __dmul_rn(__dmul_rn(P.dd, c), w_node);                     // S:490
-    r = __dsub_rn(r, local);
-    r = __dsub_rn(r, local);                                                        // S:498
-    return r;
-}
-
 __global__ void __launch_bounds__(256)
 pointwise_kernel(DevProblem P, const double* __restrict__ C, const double* __restrict__ inside_sum,
                  const double* __restrict__ N_cur, const double* __restrict__ scalars, double dt,
@@ -210,33 +194,16 @@ finish_factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
     double* __restrict__ sum_out = S.sum_out;
     double* __restrict__ deriv_out = S.deriv_out;
     double* __restrict__ C_next = S.C_next;
-    __shared__ double red[256 / kWarp];
     __shared__ double wc_shared;
     const int G = P.G;
-    double acc = 0.0;
-    for (int r = threadIdx.x; r < G; r += 256) acc += wc_rows[r];
-    acc = warp_sum(acc);
-    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
-    __syncthreads();
-    const double N = N_cur[0];
-    if (threadIdx.x == 0) {
-        double v = 0.0;
-        for (int w = 0; w < 256 / kWarp; w++) v += red[w];
-        const double WC = (v + (N * N) * P.wc_outside) * P.hh;                      // S:311, S:314
-        wc_shared = WC;
-        if (blockIdx.x == 0) {
-            double dN = __dmul_rn(N, __dsub_rn(P.b, P.d));                          // S:446
-            dN = __dsub_rn(dN, __dadd_rn(0.0, __dmul_rn(P.dd, WC)));                // S:450-451
-            scalars[0] = WC;
-            scalars[1] = dN;
-            if (N_next) {
-                const double v1 = __dadd_rn(N, __dmul_rn(dN, dt));                  // S:577
-                N_next[0] = v1 < 0.0 ? 0.0 : v1;                                    // S:578-580
-            }
-        }
+    if (threadIdx.x < kWarp) {
+        const double v = wc_total(wc_rows, G, threadIdx.x);
+        if (threadIdx.x == 0) wc_shared = v;
     }
     __syncthreads();
-    const double WC = wc_shared;
+    const double N = N_cur[0];
+    const double WC = (wc_shared + (N * N) * P.wc_outside) * P.hh;                  // S:311, S:314
+    if (threadIdx.x == 0 && blockIdx.x == 0) first_moment_update(P, N, WC, dt, scalars, N_next);
 
     const int n = local_rows(P) * G;
     const int ql = blockIdx.x * blockDim.x + threadIdx.x;
@@ -257,6 +224,15 @@ finish_factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
     }
 }
 
+// per-row dot products of the WC functional for a freshly uploaded C (the fused step keeps them up to date afterwards)
+__global__ void __launch_bounds__(256) wc_rows_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__ wc_rows)
+{
+    const int x = blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (x >= P.G) return;
+    const double s = wc_row_dot(P.wc_operator + (size_t)x * P.G, C + (size_t)row_slot(P, x) * P.G, P.G, threadIdx.x & 31);
+    if ((threadIdx.x & 31) == 0) wc_rows[x] = s;
+}
+
 __global__ void record_observables_kernel(DevProblem P, const double* __restrict__ N_cur, const double* __restrict__ C,
                                           double* __restrict__ obs_row)
 {
@@ -265,6 +241,11 @@ __global__ void record_observables_kernel(DevProblem P, const double* __restrict
 }
 
 }  // namespace
+
+void launch_wc_rows(const DevProblem& P, const double* C, double* wc_rows, cudaStream_t stream)
+{
+    wc_rows_kernel<<<(P.G + 7) / 8, 256, 0, stream>>>(P, C, wc_rows);
+}
 
 void launch_record_observables(const DevProblem& P, const double* N_cur, const double* C, double* obs_row, cudaStream_t stream)
 {

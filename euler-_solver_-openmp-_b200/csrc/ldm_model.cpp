@@ -343,6 +343,7 @@ void build_ring_operator(const Tables& t, int rank, int world, RingOperator& out
     }
     out = RingOperator();
     out.row_begin.push_back(0);
+    out.grid_row_begin.push_back(0);
     for (const RingOperator& r : per_row) {
         const int base = (int)out.node.size();
         out.point.insert(out.point.end(), r.point.begin(), r.point.end());
@@ -350,6 +351,7 @@ void build_ring_operator(const Tables& t, int rank, int world, RingOperator& out
         out.node.insert(out.node.end(), r.node.begin(), r.node.end());
         out.weight.insert(out.weight.end(), r.weight.begin(), r.weight.end());
         out.samples += r.samples;
+        out.grid_row_begin.push_back((int)out.point.size());
     }
 }
 

@@ -74,6 +74,7 @@ void build_tables(const ldm_problem& p, Tables& t);
 struct RingOperator {
     std::vector<int> point;        // per CSR row: local_row * G + y
     std::vector<int> row_begin;    // rows + 1
+    std::vector<int> grid_row_begin;   // local moment-grid rows + 1: first CSR row of each
     std::vector<int> node;         // C index in gathered layout: row_slot(p) * G + q
     std::vector<double> weight;
     long long samples = 0;         // ring samples enumerated

@@ -115,7 +115,32 @@ def job_synth(args):
     return f"synth {name}: G={p.G} K={p.K} mM={p.mM} mW={p.mW} dN={out['deriv'][0]!r}"
 
 
+def job_large(args):
+    """The headline grids (BASELINE configs 3 and 4) pinned to the reference itself: ONE right-hand side each with the
+    by-reference build (G=128: ~35 s; G=512: ~25 min single-threaded).  Stored without the kernel tables (those are
+    covered bitwise at the smaller sizes) to keep the fixtures small."""
+    name, sw, sm, G = args
+    fast = Reference(byref=True)
+    p = fast.from_numbers(sw, sm, 0.4, 0.2, 0.001, G)
+    g, k = p.grids()
+    st = np.full(1 + p.P, 200.0 ** 2)
+    st[0] = 200.0
+    r2 = g[:, None] ** 2 + g[None, :] ** 2
+    st[1:] = (200.0 ** 2 * (1 + 0.5 * np.exp(-r2 / (2 * sm * sm)))).ravel()
+    t0 = time.time()
+    deriv = p.rhs(st)
+    out = dict(G=p.G, K=p.K, mM=p.mM, mW=p.mW, h=p.h_step, cutoff=p.cutoff, sigmaM=p.sigmaM, sigmaW=p.sigmaW, b=p.b, d=p.d,
+               dd=p.dd, moments_grid=g, kernels_grid=k, deriv=deriv, seconds_byref=time.time() - t0)
+    np.savez_compressed(os.path.join(HERE, f"large_{name}.npz"), **out)
+    return f"large {name}: G={p.G} K={p.K} mM={p.mM} mW={p.mW} dN={deriv[0]!r} dC00={deriv[1]!r} ({out['seconds_byref']:.0f} s)"
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--large":
+        with ProcessPoolExecutor(max_workers=2) as pool:
+            for line in pool.map(job_large, [("g128", 0.15, 0.15, 128), ("g512", 0.10062893578616353, 0.08, 512)]):
+                print(line, flush=True)
+        return
     assert Reference().available and Reference(True).available, "run `make -C oracle ref` first"
     jobs = [(job_14_6, (w, i)) for w, idx in SWEEP.items() for i in idx]
     jobs += [(job_14_4, c) for c in "acb"]

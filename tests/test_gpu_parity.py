@@ -30,12 +30,12 @@ def problems_from(g, name, ldm):
     return ldm.Properties.Generate(1, *args, forced), OracleProblem(*args, forced)
 
 
-def rhs_term_scale(o, state):
+def rhs_term_scale(o, state, integrals=None, nodes=None):
     """sum of |terms| of dC (Solver.cpp:464-505) and of dN (446-451), per component"""
     N = state[0]
     C = state[1:].reshape(o.G, o.G)
-    wc, mc = o.integrals(state)
-    m_nodes, w_nodes = o.kernels_at_nodes()
+    wc, mc = integrals if integrals is not None else o.integrals(state)
+    m_nodes, w_nodes = nodes if nodes is not None else o.kernels_at_nodes()
     scale_c = (2 * o.b * np.abs(mc) + 2 * o.b * N * np.abs(m_nodes) + 2 * o.d * np.abs(C)
                + 2 * o.dd * np.abs(wc * C / N) + 2 * o.dd * np.abs(w_nodes * C))
     scale_n = abs(N * (o.b - o.d)) + abs(o.dd * wc)
@@ -241,6 +241,50 @@ def test_factored_tilings_equal_direct(ldm, monkeypatch, G, bm, bn):
     (w1, m1), (w2, m2) = direct.integrals(st), factored.integrals(st)
     assert abs(w1 - w2) <= 1e-14 * abs(w1)
     assert np.all(np.abs(m1 - m2) <= 1e-13 * np.abs(m1))
+
+
+@pytest.mark.parametrize("name", ["large_g128", "large_g512"])
+def test_headline_grids_against_the_reference(ldm, name):
+    """BASELINE configs 3 and 4 (16 384 and 262 144 xi-points): one right-hand side computed by the reference itself
+    (by-reference build, 35 s / ~25 min of CPU; tests/golden/make_golden.py --large) against the GPU."""
+    path = os.path.join(HERE, "golden", name + ".npz")
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated")
+    g = np.load(path)
+    G = int(g["G"])
+    props = ldm.Properties.Generate(1, float(g["sigmaW"]), float(g["sigmaM"]), float(g["b"]), float(g["d"]), float(g["dd"]), G)
+    assert (props.K, props.MaxNumForM, props.MaxNumForW) == (int(g["K"]), int(g["mM"]), int(g["mW"]))
+    assert np.array_equal(props.MomentsGrid, g["moments_grid"]) and np.array_equal(props.KernelsGrid, g["kernels_grid"])
+    eq = ldm.Equation(props)
+    grid = props.MomentsGrid
+    st = eq.GenerateEquilibriumValuesForNAndC(200)
+    st[1:] = (200.0 ** 2 * (1 + 0.5 * np.exp(-(grid[:, None] ** 2 + grid[None, :] ** 2) / (2 * float(g["sigmaM"]) ** 2)))).ravel()
+    got = eq(0.0, st, ldm.SquaredN)
+
+    class Rates:       # the scale only needs the rates; the integrals come from the GPU itself
+        pass
+    o = Rates()
+    o.G, o.b, o.d, o.dd = G, float(g["b"]), float(g["d"]), float(g["dd"])
+    scale = rhs_term_scale(o, st, integrals=eq.integrals(st), nodes=eq.kernels_at_nodes())
+    err = np.abs(got - g["deriv"])
+    worst = np.argmax(err / scale)
+    assert np.all(err <= RTOL_RHS_TERMS * scale), (worst, got[worst], g["deriv"][worst], err[worst] / scale[worst])
+
+
+def test_single_launch_step_equals_three_kernel_step(ldm, monkeypatch):
+    """the optional fused step (LDM_FUSED_STEP=1: ring correction and update inside the factored kernel) is the same
+    arithmetic as the default three-kernel step"""
+    g = golden("exp_14_4_a")
+    props, _ = problems_from(g, "exp_14_4_a", ldm)
+    plain = ldm.Equation(props)
+    monkeypatch.setenv("LDM_FUSED_STEP", "1")
+    fused = ldm.Equation(props)
+    for eq in (plain, fused):
+        eq.upload(g["state_k100"])
+        eq.advance(50, 0.1)
+    a, b = plain.download(), fused.download()
+    assert np.all(np.abs(a - b) <= 1e-13 * np.abs(a))
+    assert fused.launches < plain.launches
 
 
 def test_large_grid_properties(ldm):
