@@ -59,7 +59,7 @@ def assert_states_close(got, want):
     assert np.all(err <= bound), (worst, got[worst], want[worst])
 
 
-ALL = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "golden", "*.npz")))
+ALL = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(p).startswith("large_"))
 
 
 @pytest.mark.parametrize("name", ALL)
@@ -166,7 +166,7 @@ def test_batch_of_parameter_sets(ldm):
         assert_states_close(got, want)
 
 
-@pytest.mark.parametrize("world", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 5, 7])
 def test_sharded_step_emulated_on_one_device(ldm, world):
     """xi-sharding with all ranks emulated on one GPU: each rank updates its rows of C from the
     gathered replica; the 'all-gather' is a concatenation.  Must equal the unsharded run bit for bit."""
