@@ -587,7 +587,7 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
                 ensure_ring_operator(h);
                 Group* g = nullptr;
                 for (Group& cand : groups)
-                    if (cand.shape.bm == h->plan.bm && cand.shape.bn == h->plan.bn && cand.shape.tn == h->plan.tn && cand.shape.mma == h->plan.mma &&
+                    if (cand.shape.bm == h->plan.bm && cand.shape.bn == h->plan.bn && cand.shape.tn == h->plan.tn && cand.shape.mma == h->plan.mma && cand.shape.ws == h->plan.ws &&
                         cand.fused == fused_step_possible(h)) g = &cand;
                 if (!g) { groups.emplace_back(); g = &groups.back(); g->shape = h->plan; g->fused = fused_step_possible(h); }
                 g->members.push_back(i);

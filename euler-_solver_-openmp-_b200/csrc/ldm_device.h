@@ -107,6 +107,7 @@ void launch_ring_batch(const StepArgs* d_batch, int n, int max_ring_rows, cudaSt
 struct FactoredPlan {
     int bm = 80, bn = 64;      // CTA tile: beta rows x columns
     bool mma = true;           // contraction on the FP64 tensor cores (mma.sync m8n8k4) instead of DFMA register tiles
+    bool ws = true;            // warp-specialised K loop (producer warps generate E/Q, consumer warps run the MMAs)
     int tn = 8;                // columns per thread (8: 5x8 register tile, 4: 5x4 with twice the threads)
     int tiles = 1, chunks = 1; // beta tiles x column chunks; slabs = tiles * chunks partial sums per node
     int slabs() const { return tiles * chunks; }
