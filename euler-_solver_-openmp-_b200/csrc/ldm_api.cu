@@ -59,6 +59,9 @@ struct ldm_context {
     double* d_wc_step[2] = {nullptr, nullptr};   // [G] the same, kept up to date by the fused step (ping-pong with C)
     bool fused_enabled = false;            // single-launch step: measured slower (ring-heavy rows serialise), LDM_FUSED_STEP=1 enables
     std::vector<void*> ring_allocations;   // the ring-correction CSR of the current (rank, world)
+    std::vector<void*> w_allocations;      // W_x = Q . L_x of the current (rank, world)
+    int w_rank = -1, w_world = -1;
+    double w_megabytes = 0;
     int ring_rank = -1, ring_world = -1;
     long long ring_entries = 0, ring_samples = 0;
     int cur = 0;
@@ -89,6 +92,7 @@ struct ldm_context {
         cudaSetDevice(device);
         for (void* p : allocations) cudaFree(p);
         for (void* p : ring_allocations) cudaFree(p);
+        for (void* p : w_allocations) cudaFree(p);
         if (ev_begin) cudaEventDestroy(ev_begin);
         if (ev_end) cudaEventDestroy(ev_end);
         if (ev_fork) cudaEventDestroy(ev_fork);
@@ -134,6 +138,57 @@ void ensure_ring_operator(ldm_context* c)
     LDM_CUDA(cudaDeviceSynchronize());      // one-time setup: everything above is visible to every stream
 }
 
+// W_x = Q . L_x for this rank's rows (time-invariant; rebuilt when the sharding changes), see ldm_factored_w.cu.
+void ensure_w_operand(ldm_context* c)
+{
+    DevProblem& d = c->dev;
+    if (c->w_rank == d.rank && c->w_world == d.world) return;
+    const ldm::Tables& t = c->tables;
+    const int G = d.G, n_off = d.n_off;
+    const int a_pad = c->plan.tiles * c->plan.bm;
+    std::vector<long long> offset((size_t)G, -1);
+    std::vector<int> k_of((size_t)G, 16), plo((size_t)G, 0);
+    long long total = 0;
+    for (int x = d.rank; x < G; x += d.world) {
+        int lo = G, hi = -1;
+        for (int o = 0; o < n_off; o++) {
+            const int u = t.axisM.upper[(size_t)x * n_off + o];
+            if (u != 0) { lo = std::min(lo, u - 1); hi = std::max(hi, u); }
+        }
+        if (hi < 0) { lo = 0; hi = 0; }
+        plo[(size_t)x] = lo;
+        k_of[(size_t)x] = ((hi - lo + 1 + 15) / 16) * 16;
+        offset[(size_t)x] = total;
+        total += (long long)a_pad * k_of[(size_t)x];
+    }
+    for (void* p : c->w_allocations) cudaFree(p);
+    c->w_allocations.clear();
+    auto up = [&](const auto& v) {
+        using T = typename std::decay_t<decltype(v)>::value_type;
+        void* p = nullptr;
+        LDM_CUDA(cudaMalloc(&p, std::max<size_t>(v.size(), 1) * sizeof(T)));
+        c->w_allocations.push_back(p);
+        LDM_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+        return static_cast<const T*>(p);
+    };
+    d.w_offset = up(offset);
+    d.w_k = up(k_of);
+    d.w_plo = up(plo);
+    void* w = nullptr;
+    LDM_CUDA(cudaMalloc(&w, std::max<long long>(total, 1) * sizeof(double)));
+    c->w_allocations.push_back(w);
+    LDM_CUDA(cudaMemset(w, 0, std::max<long long>(total, 1) * sizeof(double)));
+    d.W = static_cast<const double*>(w);
+    // build only this rank's rows: the kernel skips rows whose offset is negative
+    ldm::launch_build_w(d, static_cast<double*>(w), a_pad, c->stream);
+    c->launches += 1;
+    LDM_CUDA(cudaGetLastError());
+    LDM_CUDA(cudaDeviceSynchronize());
+    c->w_rank = d.rank;
+    c->w_world = d.world;
+    c->w_megabytes = (double)total * sizeof(double) / 1e6;
+}
+
 // One right-hand side at the state (N_cur, C) for this rank's rows: scalars <- WC, dN; optional outputs:
 // sum_out (inside-sample sums), deriv_out (dC/dt), N_next / C_next (explicit-Euler update with clamp).
 ldm::StepArgs make_step_args(ldm_context* c, const double* C, const double* N_cur, double* N_next, double dt,
@@ -161,6 +216,7 @@ void rhs_and_update(ldm_context* c, const DevProblem& P, const double* C, const 
         return;
     }
     ensure_ring_operator(c);
+    if (c->plan.use_w) ensure_w_operand(c);
     const ldm::StepArgs args = make_step_args(c, C, N_cur, N_next, dt, sum_out, deriv_out, C_next);
     // the sparse ring correction only reads C: it runs on a side stream beside the (register-bound, one CTA per
     // SM) factored kernel and joins before the closing kernel
@@ -171,7 +227,8 @@ void rhs_and_update(ldm_context* c, const DevProblem& P, const double* C, const 
         ldm::launch_ring(args, c->aux_stream);
         LDM_CUDA(cudaEventRecord(c->ev_join, c->aux_stream));
     }
-    ldm::launch_factored(c->plan, args, s);
+    if (c->plan.use_w) ldm::launch_factored_w(c->plan, args, s);
+    else ldm::launch_factored(c->plan, args, s);
     if (side) LDM_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
     ldm::launch_finish_factored(args, s);
     c->launches += 2 + (side ? 1 : 0);
@@ -180,7 +237,7 @@ void rhs_and_update(ldm_context* c, const DevProblem& P, const double* C, const 
 // One slab per row and one rank: the factored kernel can finish the step on its own (see StepArgs::fused).
 bool fused_step_possible(const ldm_context* c)
 {
-    return c->fused_enabled && c->algo == LDM_ALGO_FACTORED && c->plan.slabs() == 1 && c->dev.world == 1;
+    return c->fused_enabled && !c->plan.use_w && c->algo == LDM_ALGO_FACTORED && c->plan.slabs() == 1 && c->dev.world == 1;
 }
 
 ldm::StepArgs make_fused_args(ldm_context* c, int parity, double dt, double* deriv_out)
@@ -585,9 +642,10 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
             for (int i = 0; i < n; i++) {
                 ldm_context* h = handles[i];
                 ensure_ring_operator(h);
+                if (h->plan.use_w) ensure_w_operand(h);
                 Group* g = nullptr;
                 for (Group& cand : groups)
-                    if (cand.shape.bm == h->plan.bm && cand.shape.bn == h->plan.bn && cand.shape.tn == h->plan.tn && cand.shape.mma == h->plan.mma && cand.shape.ws == h->plan.ws &&
+                    if (cand.shape.bm == h->plan.bm && cand.shape.bn == h->plan.bn && cand.shape.tn == h->plan.tn && cand.shape.mma == h->plan.mma && cand.shape.ws == h->plan.ws && cand.shape.use_w == h->plan.use_w &&
                         cand.fused == fused_step_possible(h)) g = &cand;
                 if (!g) { groups.emplace_back(); g = &groups.back(); g->shape = h->plan; g->fused = fused_step_possible(h); }
                 g->members.push_back(i);
@@ -633,7 +691,8 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
                             ldm::launch_ring_batch(g.d_args[parity], members, g.max_ring, lead->aux_stream);
                             LDM_CUDA(cudaEventRecord(lead->ev_join, lead->aux_stream));
                         }
-                        ldm::launch_factored_batch(g.shape, g.d_args[parity], members, g.max_slabs, g.max_rows, g.max_G, g.max_A, s);
+                        if (g.shape.use_w) ldm::launch_factored_w_batch(g.shape, g.d_args[parity], members, g.max_slabs, g.max_rows, g.max_G, s);
+                        else ldm::launch_factored_batch(g.shape, g.d_args[parity], members, g.max_slabs, g.max_rows, g.max_G, g.max_A, s);
                         if (side) LDM_CUDA(cudaStreamWaitEvent(s, lead->ev_join, 0));
                         ldm::launch_finish_factored_batch(g.d_args[parity], members, g.max_points, s);
                         lead->launches += 2 + (side ? 1 : 0);

@@ -24,6 +24,12 @@ struct DevProblem {
     const double* weight_t;
     const int* alpha;          // [n_off]
     const double* quadrant;    // [A][A] odd-node quadrant of the m table
+    // W_x = Q . L_x (ldm_factored_w.cu): for every row x of this rank a_pad rows of w_k[x] doubles at W + w_offset[x],
+    // covering the moment-grid rows w_plo[x] .. w_plo[x] + w_k[x] - 1
+    const double* W;
+    const long long* w_offset; // [G] (-1: row not held by this rank)
+    const int* w_k;            // [G] multiple of 16
+    const int* w_plo;          // [G]
     const double* m_nodes;     // [G][G]  m(xi) at the moment nodes                        (Solver.cpp:469)
     const double* w_nodes;     // [G][G]  w(xi)                                            (Solver.cpp:490)
     const double* out_weight;  // [G][G]  sum of m over this node's samples beyond the cutoff
@@ -107,7 +113,9 @@ void launch_ring_batch(const StepArgs* d_batch, int n, int max_ring_rows, cudaSt
 struct FactoredPlan {
     int bm = 80, bn = 64;      // CTA tile: beta rows x columns
     bool mma = true;           // contraction on the FP64 tensor cores (mma.sync m8n8k4) instead of DFMA register tiles
-    bool ws = true;            // warp-specialised K loop (producer warps generate E/Q, consumer warps run the MMAs)
+    bool use_w = false;        // contraction against the precomputed W_x = Q . L_x (ldm_factored_w.cu) instead of regenerating E_x:
+                               // measured slower (K_x averages 1.35-1.65 x A), LDM_FACTORED_W=1 enables
+    bool ws = false;           // E-form only: warp-specialised K loop (producer warps generate E/Q, consumer warps run the MMAs)
     int tn = 8;                // columns per thread (8: 5x8 register tile, 4: 5x4 with twice the threads)
     int tiles = 1, chunks = 1; // beta tiles x column chunks; slabs = tiles * chunks partial sums per node
     int slabs() const { return tiles * chunks; }
@@ -117,5 +125,10 @@ FactoredPlan plan_factored(const DevProblem& P);
 void launch_factored(const FactoredPlan& plan, const StepArgs& one, cudaStream_t stream);
 void launch_factored_batch(const FactoredPlan& shape, const StepArgs* d_batch, int n, int max_slabs, int max_rows, int max_G, int max_A,
                            cudaStream_t stream);
+
+void launch_factored_w(const FactoredPlan& plan, const StepArgs& one, cudaStream_t stream);
+void launch_factored_w_batch(const FactoredPlan& shape, const StepArgs* d_batch, int n, int max_slabs, int max_rows, int max_G,
+                             cudaStream_t stream);
+void launch_build_w(const DevProblem& P, double* W, int a_pad, cudaStream_t stream);
 
 }  // namespace ldm

@@ -597,6 +597,8 @@ FactoredPlan plan_factored(const DevProblem& P)
     }
     if (const char* env = std::getenv("LDM_FACTORED_MMA")) plan.mma = std::atoi(env) != 0;
     if (const char* env = std::getenv("LDM_FACTORED_WS")) plan.ws = std::atoi(env) != 0;
+    if (const char* env = std::getenv("LDM_FACTORED_W")) plan.use_w = std::atoi(env) != 0;
+    if (!plan.mma) plan.use_w = false;
     if (const char* env = std::getenv("LDM_FACTORED_TN")) {
         const int v = std::atoi(env);
         if (v == 4 || v == 8) plan.tn = v;

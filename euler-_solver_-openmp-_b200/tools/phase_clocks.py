@@ -28,7 +28,7 @@ assert lib.ldm_debug_phase_clocks(buf.ctypes.data, rows) == 0
 names = ["prologue (tap tables)", "first E/Q chunk", "K loop", "stage H tile", "y-side contraction", "write-out + WC rows"]
 buf = buf[buf[:, 0] > 0]
 d = np.diff(buf[:, :7], axis=1)
-print(f"{len(buf)} CTAs; total {np.mean(buf[:, 6] - buf[:, 0]):.0f} cycles (max {np.max(buf[:, 6] - buf[:, 0])})")
+print("K_x per row:", "n/a"); print(f"{len(buf)} CTAs; total {np.mean(buf[:, 6] - buf[:, 0]):.0f} cycles (max {np.max(buf[:, 6] - buf[:, 0])})")
 for n, col in zip(names, d.T):
     print(f"  {n:28s} mean {col.mean():9.0f}  max {col.max():9.0f} cycles")
 print(f"  K loop: consumer waited {buf[:, 7].mean():.0f} cycles for full buffers, producer waited {buf[:, 8].mean():.0f} cycles for empty buffers")

@@ -278,6 +278,7 @@ def test_single_launch_step_equals_three_kernel_step(ldm, monkeypatch):
     props, _ = problems_from(g, "exp_14_4_a", ldm)
     plain = ldm.Equation(props)
     monkeypatch.setenv("LDM_FUSED_STEP", "1")
+    monkeypatch.setenv("LDM_FACTORED_W", "0")
     fused = ldm.Equation(props)
     for eq in (plain, fused):
         eq.upload(g["state_k100"])
@@ -285,6 +286,32 @@ def test_single_launch_step_equals_three_kernel_step(ldm, monkeypatch):
     a, b = plain.download(), fused.download()
     assert np.all(np.abs(a - b) <= 1e-13 * np.abs(a))
     assert fused.launches < plain.launches
+
+
+@pytest.mark.parametrize("knob", ["LDM_FACTORED_W=1", "LDM_FACTORED_WS=1", "LDM_FACTORED_MMA=0", "LDM_FACTORED_TN=4"])
+def test_alternative_contraction_kernels(ldm, monkeypatch, knob):
+    """the optional variants of the contraction (precomputed W_x = Q.L_x with cp.async, warp-specialised producers,
+    DFMA register tiles instead of tensor cores) compute the same integrals as the default"""
+    g = golden("synth_g64")
+    props, o = problems_from(g, "synth_g64", ldm)
+    name, value = knob.split("=")
+    monkeypatch.setenv(name, value)
+    if name == "LDM_FACTORED_TN":
+        monkeypatch.setenv("LDM_FACTORED_MMA", "0")
+    eq = ldm.Equation(props)
+    wc, mc = eq.integrals(g["state"])
+    assert abs(wc - float(g["wc"])) <= 1e-13 * abs(float(g["wc"]))
+    assert np.all(np.abs(mc - g["mc"]) <= 1e-13 * np.abs(g["mc"]))
+    big = ldm.Properties.Generate(1, 0.12, 0.09, 0.4, 0.2, 0.001, 200)      # two column chunks, two beta tiles
+    a, b = ldm.Equation(big), None
+    monkeypatch.delenv(name)
+    monkeypatch.delenv("LDM_FACTORED_MMA", raising=False)
+    b = ldm.Equation(big)
+    st = b.GenerateEquilibriumValuesForNAndC(200)
+    gg = big.MomentsGrid
+    st[1:] *= (1 + 0.3 * np.exp(-(gg[:, None] ** 2 + gg[None, :] ** 2) / 0.02)).ravel()
+    (_, m1), (_, m2) = a.integrals(st), b.integrals(st)
+    assert np.all(np.abs(m1 - m2) <= 1e-13 * np.abs(m2))
 
 
 def test_large_grid_properties(ldm):
