@@ -62,6 +62,36 @@ def algorithmic_flop_per_step(props):
     return 11.0 * (P * s_nz + nz_w) + 20.0 * P, s_nz
 
 
+def executed_flop_per_step(props):
+    """FP64 operations the factored path actually issues per step (not the 11-FLOP-per-sample model): the padded dense
+    contraction on the tensor cores, the generation of E (7 per element and beta tile), the y-side contraction (6 per tap
+    pair), the closing kernel (~30 per node)."""
+    G, A = props.G, (props.MaxNumForM - 1) // 2 if props.MaxNumForM > 2 else 1
+    bm = 40 if A <= 40 else 80
+    bn = 64 if G <= 64 else 128
+    tiles, chunks = -(-A // bm), -(-G // bn)
+    k_pad = -(-A // 16) * 16
+    gemm = 2.0 * G * (tiles * bm) * (chunks * bn) * k_pad
+    e_gen = 7.0 * G * tiles * k_pad * (chunks * bn)
+    y_side = 6.0 * G * chunks * G * 2 * A
+    return gemm + e_gen + y_side + 30.0 * G * G
+
+
+def measured_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu capture"""
+    path = os.path.join(ROOT, "profiles", f"r01_ncu_factored_kernel_{workload}.csv")
+    if not os.path.exists(path):
+        return None
+    total, seen = 0.0, False
+    for line in open(path):
+        parts = line.strip().split(",")
+        if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(parts[2], 1.0)
+            total += float(parts[1]) * scale
+            seen = True
+    return total if seen else None
+
+
 class ClockSampler:
     """nvidia-smi clocks and throttle reasons DURING the timed region (B200_PROFILING.md clocks line)."""
     QUERY = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
@@ -300,6 +330,7 @@ def main():
     P = props.G * props.G
     state0 = seeded_state(props.MomentsGrid, sm)
     flop_step, s_nz = algorithmic_flop_per_step(props)
+    flop_executed = executed_flop_per_step(props)
     fp64_peak = ldm.measure_fp64_peak(local_rank)
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB of L2
@@ -374,7 +405,11 @@ def main():
                     "d2h_bytes_per_step": 16.0, "call": "EulerSolver::Solve twin (ldm_solve, record = observables), pinned host buffers, wall clock"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                         "traffic": None, "algorithmic_flop_per_step": flop_step,
+                         "traffic": measured_traffic(args.workload), "algorithmic_flop_per_step": flop_step,
+                         "executed_flop_per_step": flop_executed, "executed_tflops": flop_executed / (ms_per_step * 1e-3) / 1e12,
+                         "executed_frac": flop_executed / (ms_per_step * 1e-3) / 1e12 / fp64_peak,
+                         "note": "frac > 1 is expected: the factored algorithm issues ~14x fewer FP64 operations than the 11-FLOP-per-sample "
+                                 "model of the sample-by-sample sum (DESIGN.md 5); executed_frac is the honest pipe utilisation",
                          "peak_source": "measured live: DFMA chain micro-benchmark (MEASURED_PEAKS.json has no FP64 figure)",
                          "hbm_GBps_algorithmic": 16.0 * P / (ms_per_step * 1e-3) / 1e9},
             "clocks": clocks.summary(),

@@ -57,6 +57,8 @@ struct ldm_context {
     double* d_ring = nullptr;              // [P] factored path: samples between the cutoff circle and the square edge
     double* d_wc_rows = nullptr;           // [G] factored path: per-row dot products of the WC operator (3-kernel path)
     double* d_wc_step[2] = {nullptr, nullptr};   // [G] the same, kept up to date by the fused step (ping-pong with C)
+    int persistent_grid = 0;               // co-resident CTAs of the persistent kernel (0: not queried yet, -1: unavailable)
+    bool persistent_enabled = true;
     bool fused_enabled = false;            // single-launch step: measured slower (ring-heavy rows serialise), LDM_FUSED_STEP=1 enables
     std::vector<void*> ring_allocations;   // the ring-correction CSR of the current (rank, world)
     std::vector<void*> w_allocations;      // W_x = Q . L_x of the current (rank, world)
@@ -249,6 +251,47 @@ ldm::StepArgs make_fused_args(ldm_context* c, int parity, double dt, double* der
     return a;
 }
 
+// All Euler steps of a solve inside one cooperative launch (ldm_factored.cu persistent_kernel): possible when every row
+// is one slab, on one rank, and the grid (G row CTAs + at least one spare CTA for the ring correction) is co-resident.
+bool persistent_possible(ldm_context* c)
+{
+    if (!c->persistent_enabled || c->algo != LDM_ALGO_FACTORED || c->dev.world != 1) return false;
+    const ldm::FactoredPlan& p = c->plan;
+    if (p.slabs() != 1 || p.use_w || !p.mma || p.ws || p.tn != 8) return false;
+    if (c->persistent_grid == 0) {
+        ldm::PersistentArgs probe{};
+        probe.step = make_step_args(c, c->d_C[0], c->d_N, c->d_N + 1, 0.0, nullptr, nullptr, c->d_C[1]);
+        int max_grid = 0;
+        const cudaError_t e = ldm::launch_persistent(p, probe, 0, c->stream, &max_grid);
+        c->persistent_grid = (e == cudaSuccess && max_grid > 0) ? max_grid : -1;
+        if (e != cudaSuccess) cudaGetLastError();
+    }
+    return c->persistent_grid >= c->dev.G + 1;
+}
+
+// n_steps Euler steps from the resident state; history pointers (device) may be NULL.
+void advance_persistent(ldm_context* c, int n_steps, double dt, long long first_point, double* d_obs, double* d_values, double* d_derivs)
+{
+    if (n_steps <= 0) return;
+    ensure_ring_operator(c);
+    ldm::PersistentArgs args{};
+    args.step = make_step_args(c, c->d_C[c->cur], c->d_N + c->cur, c->d_N + (c->cur ^ 1), dt, nullptr, nullptr, c->d_C[c->cur ^ 1]);
+    args.C[0] = c->d_C[0]; args.C[1] = c->d_C[1];
+    args.N = c->d_N;
+    args.parity = c->cur;
+    args.n_steps = n_steps;
+    args.first_point = first_point;
+    args.stride = (long long)(1 + c->P());
+    args.observables = d_obs; args.values = d_values; args.derivs = d_derivs;
+    int device = 0, sms = 0;
+    cudaGetDevice(&device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    const int grid = std::min(c->persistent_grid, std::max(sms, c->dev.G + 1));
+    LDM_CUDA(ldm::launch_persistent(c->plan, args, grid, c->stream, nullptr));
+    c->launches += 1;
+    c->cur ^= (n_steps & 1);
+}
+
 void step_resident(ldm_context* c, double dt, double* deriv_out)
 {
     const int cur = c->cur, nxt = cur ^ 1;
@@ -383,6 +426,7 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         c->d_wc_step[0] = c->alloc<double>((size_t)d.G);
         c->d_wc_step[1] = c->alloc<double>((size_t)d.G);
         if (const char* env = std::getenv("LDM_FUSED_STEP")) c->fused_enabled = std::atoi(env) != 0;
+        if (const char* env = std::getenv("LDM_PERSISTENT")) c->persistent_enabled = std::atoi(env) != 0;
         d.n_ring = 0;
         LDM_CUDA(cudaMemsetAsync(c->d_C[0], 0, P * sizeof(double), c->stream));
         LDM_CUDA(cudaMemsetAsync(c->d_C[1], 0, P * sizeof(double), c->stream));
@@ -494,8 +538,29 @@ int ldm_solve(ldm_handle h, const double* init, double dt, double t_max, int rec
             if (record >= LDM_RECORD_VALUES) d_hist = scratch_alloc((size_t)n * width);
             if (record == LDM_RECORD_ALL) d_dhist = scratch_alloc((size_t)n * width);
             upload_state(h, init);
+            const bool persistent = persistent_possible(h);
             LDM_CUDA(cudaEventRecord(h->ev_begin, h->stream));
-            for (int k = 0; k < n; k++) {
+            if (persistent) {
+                // every step but the closing evaluation inside ONE launch; the kernel records the history itself
+                if (record >= LDM_RECORD_VALUES) {
+                    LDM_CUDA(cudaMemcpyAsync(d_hist, h->d_N + h->cur, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+                    LDM_CUDA(cudaMemcpyAsync(d_hist + 1, h->d_C[h->cur], P * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+                }
+                advance_persistent(h, n - 1, dt, 0, record == LDM_RECORD_OBSERVABLES ? d_hist : nullptr,
+                                   record >= LDM_RECORD_VALUES ? d_hist : nullptr, record == LDM_RECORD_ALL ? d_dhist : nullptr);
+                if (record == LDM_RECORD_OBSERVABLES) {
+                    ldm::launch_record_observables(h->dev, h->d_N + h->cur, h->d_C[h->cur], d_hist + (size_t)(n - 1) * 2, h->stream);
+                    h->launches += 1;
+                }
+                if (record == LDM_RECORD_ALL || derivs) {   // the reference evaluates the equation once more at the final point (S:582-583)
+                    rhs_and_update(h, h->dev, h->d_C[h->cur], h->d_N + h->cur, nullptr, dt, nullptr, h->d_deriv, nullptr, h->stream);
+                    if (record == LDM_RECORD_ALL) {
+                        LDM_CUDA(cudaMemcpyAsync(d_dhist + (size_t)(n - 1) * width, h->d_scalars + 1, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+                        LDM_CUDA(cudaMemcpyAsync(d_dhist + (size_t)(n - 1) * width + 1, h->d_deriv, P * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+                    }
+                }
+            }
+            for (int k = 0; k < n && !persistent; k++) {
                 const double* Ncur = h->d_N + h->cur;
                 const double* Ccur = h->d_C[h->cur];
                 if (record == LDM_RECORD_OBSERVABLES) {
@@ -572,8 +637,10 @@ int ldm_advance(ldm_handle h, int n_steps, double dt)
     if (!h || n_steps < 0) return fail(LDM_ERR_ARGUMENT, "bad argument");
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
+        const bool persistent = persistent_possible(h);
         LDM_CUDA(cudaEventRecord(h->ev_begin, h->stream));
-        for (int k = 0; k < n_steps; k++) step_resident(h, dt, nullptr);
+        if (persistent) advance_persistent(h, n_steps, dt, 0, nullptr, nullptr, nullptr);
+        else for (int k = 0; k < n_steps; k++) step_resident(h, dt, nullptr);
         LDM_CUDA(cudaEventRecord(h->ev_end, h->stream));
         LDM_CUDA(cudaGetLastError());
     });

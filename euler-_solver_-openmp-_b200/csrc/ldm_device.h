@@ -110,6 +110,21 @@ void launch_ring_batch(const StepArgs* d_batch, int n, int max_ring_rows, cudaSt
 
 // Factored path (ldm_factored.cu): partial[slab][local_rows][G] <- per-slab sums over all samples inside the grid
 // square; the closing kernel forms inside_sum = sum_slabs partial - ring.
+// Arguments of the persistent multi-step kernel (ldm_factored.cu): `step` carries the problem and the scratch
+// buffers; the state ping-pongs between C[0]/C[1] and N[0]/N[1] starting at `parity`.
+struct PersistentArgs {
+    StepArgs step;
+    double* C[2];
+    double* N;                 // [2]
+    int parity;
+    int n_steps;
+    long long first_point;     // index of the stored point the first step starts from
+    long long stride;          // doubles per stored point (1 + G*G)
+    double* observables;       // may be NULL: [points][2]
+    double* values;            // may be NULL: [points][stride]
+    double* derivs;            // may be NULL: [points][stride]
+};
+
 struct FactoredPlan {
     int bm = 80, bn = 64;      // CTA tile: beta rows x columns
     bool mma = true;           // contraction on the FP64 tensor cores (mma.sync m8n8k4) instead of DFMA register tiles
@@ -126,6 +141,8 @@ void launch_factored(const FactoredPlan& plan, const StepArgs& one, cudaStream_t
 void launch_factored_batch(const FactoredPlan& shape, const StepArgs* d_batch, int n, int max_slabs, int max_rows, int max_G, int max_A,
                            cudaStream_t stream);
 
+// grid <= 0: only report the largest co-resident grid in *max_grid
+cudaError_t launch_persistent(const FactoredPlan& plan, const PersistentArgs& args, int grid, cudaStream_t stream, int* max_grid);
 void launch_factored_w(const FactoredPlan& plan, const StepArgs& one, cudaStream_t stream);
 void launch_factored_w_batch(const FactoredPlan& shape, const StepArgs* d_batch, int n, int max_slabs, int max_rows, int max_G,
                              cudaStream_t stream);

@@ -21,6 +21,8 @@
 // contracts it with the y-side interpolation rows.  Slabs are independent; finish_factored_kernel adds them up.
 #include <cstdlib>
 
+#include <cooperative_groups.h>
+
 #include "ldm_device.h"
 #include "ldm_pointwise.cuh"
 
@@ -95,17 +97,18 @@ __device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a, double b)
 __device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
 
-template <int BM, int BN, int TM, int TN, int BK, bool BATCH, bool MMA, bool WS>
-__global__ void __launch_bounds__((BM / TM) * (BN / TN))
-factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
+// The work of one CTA: row `lx` of this rank, slab `slab` (= beta tile * chunks + column chunk).  A device function so
+// that both the one-launch-per-step kernel and the persistent multi-step kernel run exactly the same code.
+template <int BM, int BN, int TM, int TN, int BK, bool MMA, bool WS>
+__device__ __forceinline__ void factored_body(const StepArgs& S, const int slab, const int lx)
 {
-    const StepArgs& S = BATCH ? batch[blockIdx.z] : one;
     const DevProblem& P = S.P;
-    if (BATCH && ((int)blockIdx.x >= S.tiles * S.chunks || (int)blockIdx.y >= local_rows(P))) return;   // batch grids are padded
-    const double* __restrict__ C = S.C;
-    double* __restrict__ partial = S.partial;
-    double* __restrict__ wc_rows = S.wc_rows;
-    const int tile = blockIdx.x / S.chunks, chunk = blockIdx.x - tile * S.chunks;
+    // no __restrict__ on the state: inside the persistent kernel C is rewritten every step by other CTAs, so these
+    // loads must stay ordinary (coherent after grid.sync), never the read-only (.nc) path
+    const double* C = S.C;
+    double* partial = S.partial;
+    double* wc_rows = S.wc_rows;
+    const int tile = slab / S.chunks, chunk = slab - tile * S.chunks;
     PHASE_MARK(0);
 #ifdef LDM_PHASE_CLOCKS
     if (threadIdx.x == 0) { g_phase_clock[(blockIdx.y * gridDim.x + blockIdx.x) % (148 * 4)][7] = 0; g_phase_clock[(blockIdx.y * gridDim.x + blockIdx.x) % (148 * 4)][8] = 0; }
@@ -117,7 +120,6 @@ factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
     constexpr int K_STRIDE = NT / BN;                     // E rows covered by one pass of the CTA's threads
     const int G = P.G, A = P.A, n_off = P.n_off;
     const int n_fold = n_off / A;
-    const int lx = blockIdx.y;
     const int x = P.rank + P.world * lx;
     const int b0 = tile * BM;                             // first beta row of this tile
     const int q0 = chunk * BN;                            // first column of this chunk
@@ -520,12 +522,12 @@ factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
         PHASE_MARK(6);
         return;
     }
-    double* out = partial + ((size_t)blockIdx.x * local_rows(P) + lx) * G;
+    double* out = partial + ((size_t)slab * local_rows(P) + lx) * G;
     for (int y = tid; y < G; y += NT) out[y] = acc_y[y];
 
     // WC = <wc_operator, C> (Solver.cpp:265-274) row by row, folded into this launch.  Every rank reduces the FULL
     // operator (so no all-reduce is needed): the first-slab CTAs of this rank share all G rows round-robin.
-    if (blockIdx.x == 0 && wc_rows != nullptr) {
+    if (slab == 0 && wc_rows != nullptr) {
         const int n_local = local_rows(P);
         int slot = 0;
         for (int xr = lx; xr < G; xr += n_local, slot++) {
@@ -535,6 +537,83 @@ factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
         }
     }
     PHASE_MARK(6);
+}
+
+template <int BM, int BN, int TM, int TN, int BK, bool BATCH, bool MMA, bool WS>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
+{
+    const StepArgs& S = BATCH ? batch[blockIdx.z] : one;
+    if (BATCH && ((int)blockIdx.x >= S.tiles * S.chunks || (int)blockIdx.y >= local_rows(S.P))) return;   // batch grids are padded
+    factored_body<BM, BN, TM, TN, BK, MMA, WS>(S, blockIdx.x, blockIdx.y);
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// Persistent multi-step kernel (cooperative launch, one CTA per SM): ALL Euler steps of a solve inside one launch.
+// Per step: CTAs 0..G-1 run the factored contraction of their row while the spare CTAs apply the sparse ring
+// correction; grid-wide barrier; every CTA closes its share of the nodes (closure, Euler update, clamp, history);
+// grid-wide barrier.  For grids that fit one slab per row (G <= 128, A <= 80, one rank) this removes the three kernel
+// boundaries per step -- the small default grids of the reference are latency bound, not FLOP bound.
+// ------------------------------------------------------------------------------------------------------------------
+template <int BM, int BN, int TM, int TN, int BK>
+__global__ void __launch_bounds__((BM / TM) * (BN / TN))
+persistent_kernel(const PersistentArgs A)
+{
+    constexpr int NT = (BM / TM) * (BN / TN);
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    __shared__ double wc_shared;
+    StepArgs S = A.step;
+    const DevProblem& P = S.P;
+    const int G = P.G, n = G * G, tid = threadIdx.x;
+    int parity = A.parity;
+    for (int k = 0; k < A.n_steps; k++) {
+        S.C = A.C[parity]; S.C_next = A.C[parity ^ 1];
+        S.N_cur = A.N + parity; S.N_next = A.N + (parity ^ 1);
+        const long long point = A.first_point + k;                 // index of the state this step starts from
+        if (blockIdx.x == 0 && tid == 0 && A.observables) {
+            A.observables[2 * point] = S.N_cur[0];                                  // Values[k][0]       (Solver.cpp:1011)
+            A.observables[2 * point + 1] = S.C[(size_t)0 * G + (G - 1)];            // Values[k][G]       (Solver.cpp:1014)
+        }
+        if ((int)blockIdx.x < G) {
+            factored_body<BM, BN, TM, TN, BK, true, false>(S, 0, blockIdx.x);
+        } else {
+            const int warps = (gridDim.x - G) * (NT / 32);
+            for (int row = (blockIdx.x - G) * (NT / 32) + tid / 32; row < P.n_ring; row += warps) {
+                double acc = 0.0;
+                for (int en = P.ring_begin[row] + tid % 32; en < P.ring_begin[row + 1]; en += 32) acc += P.ring_weight[en] * S.C[P.ring_node[en]];
+                acc = warp_sum(acc);
+                if (tid % 32 == 0) S.ring[P.ring_point[row]] = acc;
+            }
+        }
+        grid.sync();
+        if (tid < 32) {
+            const double v = wc_total(S.wc_rows, G, tid);
+            if (tid == 0) wc_shared = v;
+        }
+        __syncthreads();
+        const double N = S.N_cur[0];
+        const double WC = (wc_shared + (N * N) * P.wc_outside) * P.hh;             // Solver.cpp:311, 314
+        double* values_next = A.values ? A.values + (point + 1) * A.stride : nullptr;
+        double* derivs_here = A.derivs ? A.derivs + point * A.stride : nullptr;
+        if (blockIdx.x == 0 && tid == 0) {
+            first_moment_update(P, N, WC, S.dt, S.scalars, S.N_next);
+            if (values_next) values_next[0] = S.N_next[0];
+            if (derivs_here) derivs_here[0] = S.scalars[1];
+        }
+        for (int q = blockIdx.x * NT + tid; q < n; q += gridDim.x * NT) {
+            const double inside = S.partial[q] - S.ring[q];
+            const double c = S.C[q];
+            const double mc = (inside + (N * N) * P.out_weight[q]) * P.hh;
+            const double dc = second_moment_rhs(P, mc, c, N, WC, P.m_nodes[q], P.w_nodes[q]);
+            double v = __dadd_rn(c, __dmul_rn(dc, S.dt));                          // Solver.cpp:577
+            v = v < 0.0 ? 0.0 : v;                                                 // Solver.cpp:578-580
+            S.C_next[q] = v;
+            if (values_next) values_next[1 + q] = v;
+            if (derivs_here) derivs_here[1 + q] = dc;
+        }
+        grid.sync();
+        parity ^= 1;
+    }
 }
 
 template <int BM, int BN, int TM, int TN, int BK, bool BATCH, bool MMA, bool WS>
@@ -581,6 +660,34 @@ void dispatch(const FactoredPlan& shape, const StepArgs* one, const StepArgs* d_
 }
 
 }  // namespace
+
+template <int BM, int BN>
+cudaError_t launch_persistent_variant(const PersistentArgs& args, int grid, cudaStream_t stream, int* max_grid)
+{
+    using Cfg = FactoredConfig<BM, BN, 5, 8, 16, true>;
+    auto kernel = persistent_kernel<BM, BN, 5, 8, 16>;
+    const size_t smem = Cfg::smem_bytes(args.step.P.G, args.step.P.A);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    if (e != cudaSuccess) return e;
+    int device = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, Cfg::NT, smem);
+    if (e != cudaSuccess) return e;
+    if (max_grid) *max_grid = sms * per_sm;
+    if (grid <= 0) return cudaSuccess;                  // query only
+    if (grid > sms * per_sm) return cudaErrorCooperativeLaunchTooLarge;
+    void* params[] = {const_cast<PersistentArgs*>(&args)};
+    return cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(Cfg::NT), params, smem, stream);
+}
+
+cudaError_t launch_persistent(const FactoredPlan& plan, const PersistentArgs& args, int grid, cudaStream_t stream, int* max_grid)
+{
+    if (plan.bm == 80 && plan.bn == 128) return launch_persistent_variant<80, 128>(args, grid, stream, max_grid);
+    if (plan.bm == 80 && plan.bn == 64) return launch_persistent_variant<80, 64>(args, grid, stream, max_grid);
+    if (plan.bm == 40 && plan.bn == 128) return launch_persistent_variant<40, 128>(args, grid, stream, max_grid);
+    return launch_persistent_variant<40, 64>(args, grid, stream, max_grid);
+}
 
 FactoredPlan plan_factored(const DevProblem& P)
 {

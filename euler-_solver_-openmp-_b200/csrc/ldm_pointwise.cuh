@@ -22,7 +22,7 @@ __device__ __forceinline__ double wc_row_dot(const double* __restrict__ op_row, 
 }
 
 // Sum of the G row dots, same order everywhere (one warp, lanes striding the rows).
-__device__ __forceinline__ double wc_total(const double* __restrict__ wc_rows, int G, int lane)
+__device__ __forceinline__ double wc_total(const double* wc_rows, int G, int lane)
 {
     double s = 0.0;
     for (int r = lane; r < G; r += 32) s += wc_rows[r];

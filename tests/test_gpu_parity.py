@@ -276,6 +276,7 @@ def test_single_launch_step_equals_three_kernel_step(ldm, monkeypatch):
     arithmetic as the default three-kernel step"""
     g = golden("exp_14_4_a")
     props, _ = problems_from(g, "exp_14_4_a", ldm)
+    monkeypatch.setenv("LDM_PERSISTENT", "0")
     plain = ldm.Equation(props)
     monkeypatch.setenv("LDM_FUSED_STEP", "1")
     monkeypatch.setenv("LDM_FACTORED_W", "0")
@@ -312,6 +313,29 @@ def test_alternative_contraction_kernels(ldm, monkeypatch, knob):
     st[1:] *= (1 + 0.3 * np.exp(-(gg[:, None] ** 2 + gg[None, :] ** 2) / 0.02)).ravel()
     (_, m1), (_, m2) = a.integrals(st), b.integrals(st)
     assert np.all(np.abs(m1 - m2) <= 1e-13 * np.abs(m2))
+
+
+def test_persistent_kernel_equals_per_step_launches(ldm, monkeypatch):
+    """the cooperative multi-step kernel (all Euler steps in one launch, the default where it fits) against the
+    three-launches-per-step path: same arithmetic, so the same bits; and every record mode of ldm_solve agrees"""
+    g = golden("exp_14_4_c")
+    props, _ = problems_from(g, "exp_14_4_c", ldm)
+    persistent = ldm.Equation(props)
+    monkeypatch.setenv("LDM_PERSISTENT", "0")
+    stepwise = ldm.Equation(props)
+    init = persistent.GenerateEquilibriumValuesForNAndC(200)
+    runs = [ldm.EulerSolver().Solve(eq, ldm.SquaredN, 30, 0.1, init, record=ldm.RECORD_ALL) for eq in (persistent, stepwise)]
+    assert persistent.launches < stepwise.launches / 50
+    assert np.array_equal(runs[0].Values, runs[1].Values)
+    assert np.array_equal(runs[0].Derivatives, runs[1].Derivatives)
+    obs = ldm.EulerSolver().Solve(persistent, ldm.SquaredN, 30, 0.1, init, record=ldm.RECORD_OBSERVABLES)
+    assert np.array_equal(obs.Observables, runs[0].Values[:, [0, props.G]])
+    for eq in (persistent, stepwise):
+        eq.upload(init)
+        eq.advance(7, 0.1)      # odd step count: the ping-pong parity must come out right
+        eq.advance(4, 0.1)
+    assert np.array_equal(persistent.download(), stepwise.download())
+    assert np.array_equal(persistent.download(), runs[0].Values[11])
 
 
 def test_large_grid_properties(ldm):
