@@ -56,10 +56,8 @@ struct ldm_context {
     double* d_partial = nullptr;           // [tiles][P] factored path: per beta-tile sums
     double* d_ring = nullptr;              // [P] factored path: samples between the cutoff circle and the square edge
     double* d_wc_rows = nullptr;           // [G] factored path: per-row dot products of the WC operator (3-kernel path)
-    double* d_wc_step[2] = {nullptr, nullptr};   // [G] the same, kept up to date by the fused step (ping-pong with C)
     int persistent_grid = 0;               // co-resident CTAs of the persistent kernel (0: not queried yet, -1: unavailable)
     bool persistent_enabled = true;
-    bool fused_enabled = false;            // single-launch step: measured slower (ring-heavy rows serialise), LDM_FUSED_STEP=1 enables
     std::vector<void*> ring_allocations;   // the ring-correction CSR of the current (rank, world)
     std::vector<void*> w_allocations;      // W_x = Q . L_x of the current (rank, world)
     int w_rank = -1, w_world = -1;
@@ -202,7 +200,6 @@ ldm::StepArgs make_step_args(ldm_context* c, const double* C, const double* N_cu
     a.partial = c->d_partial; a.ring = c->d_ring; a.wc_rows = c->d_wc_rows; a.scalars = c->d_scalars;
     a.sum_out = sum_out; a.deriv_out = deriv_out; a.C_next = C_next;
     a.tiles = c->plan.tiles; a.chunks = c->plan.chunks;
-    a.fused = 0; a.wc_in = nullptr; a.wc_out = nullptr;
     a.dt = dt;
     return a;
 }
@@ -234,21 +231,6 @@ void rhs_and_update(ldm_context* c, const DevProblem& P, const double* C, const 
     if (side) LDM_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
     ldm::launch_finish_factored(args, s);
     c->launches += 2 + (side ? 1 : 0);
-}
-
-// One slab per row and one rank: the factored kernel can finish the step on its own (see StepArgs::fused).
-bool fused_step_possible(const ldm_context* c)
-{
-    return c->fused_enabled && !c->plan.use_w && c->algo == LDM_ALGO_FACTORED && c->plan.slabs() == 1 && c->dev.world == 1;
-}
-
-ldm::StepArgs make_fused_args(ldm_context* c, int parity, double dt, double* deriv_out)
-{
-    ldm::StepArgs a = make_step_args(c, c->d_C[parity], c->d_N + parity, c->d_N + (parity ^ 1), dt, nullptr, deriv_out, c->d_C[parity ^ 1]);
-    a.fused = 1;
-    a.wc_in = c->d_wc_step[parity];
-    a.wc_out = c->d_wc_step[parity ^ 1];
-    return a;
 }
 
 // All Euler steps of a solve inside one cooperative launch (ldm_factored.cu persistent_kernel): possible when every row
@@ -295,13 +277,6 @@ void advance_persistent(ldm_context* c, int n_steps, double dt, long long first_
 void step_resident(ldm_context* c, double dt, double* deriv_out)
 {
     const int cur = c->cur, nxt = cur ^ 1;
-    if (fused_step_possible(c)) {
-        ensure_ring_operator(c);
-        ldm::launch_factored(c->plan, make_fused_args(c, cur, dt, deriv_out), c->stream);
-        c->launches += 1;
-        c->cur = nxt;
-        return;
-    }
     rhs_and_update(c, c->dev, c->d_C[cur], c->d_N + cur, c->d_N + nxt, dt, nullptr, deriv_out, c->d_C[nxt], c->stream);
     c->cur = nxt;
 }
@@ -311,10 +286,6 @@ void upload_state(ldm_context* c, const double* state)
     c->cur = 0;
     LDM_CUDA(cudaMemcpyAsync(c->d_N, state, sizeof(double), cudaMemcpyHostToDevice, c->stream));
     LDM_CUDA(cudaMemcpyAsync(c->d_C[0], state + 1, c->P() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
-    if (fused_step_possible(c)) {          // the fused step expects the WC row dots of the current C
-        ldm::launch_wc_rows(c->dev, c->d_C[0], c->d_wc_step[0], c->stream);
-        c->launches += 1;
-    }
 }
 
 template <typename F>
@@ -423,9 +394,6 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         c->d_partial = c->alloc<double>(P * (size_t)c->plan.slabs());
         c->d_ring = c->alloc<double>(P);
         c->d_wc_rows = c->alloc<double>((size_t)d.G);
-        c->d_wc_step[0] = c->alloc<double>((size_t)d.G);
-        c->d_wc_step[1] = c->alloc<double>((size_t)d.G);
-        if (const char* env = std::getenv("LDM_FUSED_STEP")) c->fused_enabled = std::atoi(env) != 0;
         if (const char* env = std::getenv("LDM_PERSISTENT")) c->persistent_enabled = std::atoi(env) != 0;
         d.n_ring = 0;
         LDM_CUDA(cudaMemsetAsync(c->d_C[0], 0, P * sizeof(double), c->stream));
@@ -703,7 +671,6 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
                 std::vector<int> members;
                 int max_slabs = 0, max_rows = 0, max_G = 0, max_A = 0, max_ring = 0, max_points = 0;
                 ldm::StepArgs* d_args[2] = {nullptr, nullptr};
-                bool fused = false;
             };
             std::vector<Group> groups;
             for (int i = 0; i < n; i++) {
@@ -712,9 +679,8 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
                 if (h->plan.use_w) ensure_w_operand(h);
                 Group* g = nullptr;
                 for (Group& cand : groups)
-                    if (cand.shape.bm == h->plan.bm && cand.shape.bn == h->plan.bn && cand.shape.tn == h->plan.tn && cand.shape.mma == h->plan.mma && cand.shape.ws == h->plan.ws && cand.shape.use_w == h->plan.use_w &&
-                        cand.fused == fused_step_possible(h)) g = &cand;
-                if (!g) { groups.emplace_back(); g = &groups.back(); g->shape = h->plan; g->fused = fused_step_possible(h); }
+                    if (cand.shape.bm == h->plan.bm && cand.shape.bn == h->plan.bn && cand.shape.tn == h->plan.tn && cand.shape.mma == h->plan.mma && cand.shape.ws == h->plan.ws && cand.shape.use_w == h->plan.use_w) g = &cand;
+                if (!g) { groups.emplace_back(); g = &groups.back(); g->shape = h->plan; }
                 g->members.push_back(i);
                 g->max_slabs = std::max(g->max_slabs, h->plan.slabs());
                 g->max_rows = std::max(g->max_rows, h->dev.G);
@@ -730,9 +696,8 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
                         std::vector<ldm::StepArgs> host;
                         for (int i : g.members) {
                             ldm_context* h = handles[i];
-                            host.push_back(g.fused ? make_fused_args(h, parity, dt, nullptr)
-                                                   : make_step_args(h, h->d_C[parity], h->d_N + parity, h->d_N + (parity ^ 1), dt, nullptr,
-                                                                    nullptr, h->d_C[parity ^ 1]));
+                            host.push_back(make_step_args(h, h->d_C[parity], h->d_N + parity, h->d_N + (parity ^ 1), dt, nullptr, nullptr,
+                                                          h->d_C[parity ^ 1]));
                         }
                         void* p = nullptr;
                         LDM_CUDA(cudaMalloc(&p, host.size() * sizeof(ldm::StepArgs)));
@@ -746,11 +711,6 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
                 for (int k = 0; k + 1 < points; k++) {
                     for (Group& g : groups) {
                         const int members = (int)g.members.size();
-                        if (g.fused) {
-                            ldm::launch_factored_batch(g.shape, g.d_args[parity], members, g.max_slabs, g.max_rows, g.max_G, g.max_A, s);
-                            lead->launches += 1;
-                            continue;
-                        }
                         const bool side = g.max_ring > 0;
                         if (side) {
                             LDM_CUDA(cudaEventRecord(lead->ev_fork, s));

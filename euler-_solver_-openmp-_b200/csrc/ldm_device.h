@@ -59,11 +59,6 @@ struct StepArgs {
     double* deriv_out;         // may be NULL: dC/dt of this rank's rows
     double* C_next;            // may be NULL: updated rows
     int tiles, chunks;         // factored plan: slab = tile * chunks + chunk
-    // fused step (one slab per row, one rank): the factored kernel also applies the ring correction and the update;
-    // WC comes from wc_in (row dots of the current C) and the row dots of the new C are left in wc_out
-    int fused;
-    const double* wc_in;
-    double* wc_out;
     double dt;
 };
 
@@ -85,7 +80,6 @@ __host__ __device__ inline int local_rows(const DevProblem& P) { return (P.G - P
 
 // C is always the full pair density in gathered layout; `out`, inside_sum, deriv_out, C_next are
 // shard-local [local_rows][G].
-void launch_wc_rows(const DevProblem& P, const double* C, double* wc_rows, cudaStream_t stream);
 void launch_record_observables(const DevProblem& P, const double* N_cur, const double* C, double* obs_row, cudaStream_t stream);
 
 void launch_sample_sum(const DevProblem& P, SampleMode mode, const double* C, double* out, cudaStream_t stream);
@@ -123,6 +117,7 @@ struct PersistentArgs {
     double* observables;       // may be NULL: [points][2]
     double* values;            // may be NULL: [points][stride]
     double* derivs;            // may be NULL: [points][stride]
+    int cached_w_rows;         // set by the launcher: offsets whose y-side weights stay in shared memory (-1: no cache)
 };
 
 struct FactoredPlan {

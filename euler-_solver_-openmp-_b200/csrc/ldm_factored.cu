@@ -100,7 +100,8 @@ __device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volati
 // The work of one CTA: row `lx` of this rank, slab `slab` (= beta tile * chunks + column chunk).  A device function so
 // that both the one-launch-per-step kernel and the persistent multi-step kernel run exactly the same code.
 template <int BM, int BN, int TM, int TN, int BK, bool MMA, bool WS>
-__device__ __forceinline__ void factored_body(const StepArgs& S, const int slab, const int lx)
+__device__ __forceinline__ void factored_body(const StepArgs& S, const int slab, const int lx, const bool build_taps = true,
+                                              const int cached_w_rows = -1)
 {
     const DevProblem& P = S.P;
     // no __restrict__ on the state: inside the persistent kernel C is rewritten every step by other CTAs, so these
@@ -138,9 +139,19 @@ __device__ __forceinline__ void factored_body(const StepArgs& S, const int slab,
     double* Eh = acc_y + G * (1 + split);                 // [2][BK] E values of the halo column q0-1
     double* tap_w = acc_y + ((G * (1 + split) + 2 * BK + 3) & ~3);   // [A_pad][4] (32-byte aligned): weights of the four C rows feeding E[alpha]
     int* tap_row = reinterpret_cast<int*>(tap_w + 4 * A_pad);   // [A_pad][4]: their offsets (slot * G)
+    // Persistent kernel only (cached_w_rows >= 0): the y-side interpolation table is the same every step, and streaming it
+    // from L2 in all CTAs at once is what bounds that phase -- so the 16-bit interval indices of the whole table and the
+    // weights of its first cached_w_rows offsets are kept in the shared memory left over, filled on the first step.
+    unsigned short* u_cache = reinterpret_cast<unsigned short*>(tap_row + 4 * A_pad);          // [n_off][G]
+    double* w_cache = reinterpret_cast<double*>(u_cache + (((size_t)n_off * G + 3) & ~(size_t)3));   // [cached_w_rows][G]
+    if (cached_w_rows >= 0 && build_taps) {
+        for (int i = tid; i < n_off * G; i += NT) u_cache[i] = (unsigned short)P.upper_t[i];
+        for (int i = tid; i < cached_w_rows * G; i += NT) w_cache[i] = P.weight_t[i];
+    }
 
     // x-side interpolation taps of this row, once per CTA: E[alpha][q] = sum_t tap_w[alpha][t] * C[tap_row[alpha][t] + q]
-    for (int t = tid; t < A_pad * 2; t += NT) {
+    // (time-invariant per row: the persistent kernel builds them once and keeps them in shared memory across steps)
+    for (int t = tid; build_taps && t < A_pad * 2; t += NT) {
         const int alpha = t >> 1, f = t & 1;
         double w_lo = 0.0, w_hi = 0.0;
         int r_lo = 0, r_hi = 0;
@@ -430,9 +441,11 @@ __device__ __forceinline__ void factored_body(const StepArgs& S, const int slab,
         // taking every split-th beta row, so every thread runs a long loop of independent loads.
         // y side: every tap pair (u-1, u) whose upper node u falls in this chunk.  Consecutive threads own consecutive y
         // (the transposed tables make those reads contiguous); `split` threads share one y, each taking every split-th
-        // beta row, so every thread runs a long branch-free loop of independent table reads.  With all CTAs in this
-        // phase at the same time it is L2-bandwidth bound (12 B per tap pair); recomputing the weights from node tables
-        // in shared memory instead was tried and is slower (scattered 8-byte shared-memory gathers).
+        // beta row, so every thread runs a long branch-free loop of independent table reads.  Measured (diagnostic builds):
+        // the table reads alone take 12.3 k cycles per CTA at G = 128 (233 KB at ~19 B/clk/SM, 8 warps of loads in
+        // flight), the shared-memory gathers alone 5.5 k, together 12.4 k -- the phase is bound by global-load
+        // throughput at this occupancy.  Tried without gain: bigger load batches, staggering the rows per CTA, rebuilding
+        // the weights from node tables in shared memory (slower: scattered 8-byte gathers).
         // A sample beyond the grid is tabulated as (u = 0, w = 0): in chunk 0 it reads 1 * halo + 0 * H[0], and the halo
         // column of chunk 0 is zero, so no validity test is needed; pairs of other chunks drop out by select.
         const int rows_here = min(BM, A - b0);
@@ -444,9 +457,22 @@ __device__ __forceinline__ void factored_body(const StepArgs& S, const int slab,
             for (int f = 0; f < n_fold; f++) {
                 const int o0 = folded_offset(A, n_fold, b0, f);
                 const int dir = (n_fold == 2 && f == 0) ? -1 : 1;
+                const int stride = dir * G;
+                if (cached_w_rows >= 0) {
+                    // whole_row is implied (the persistent kernel runs one slab per row)
+                    const unsigned short* uc = u_cache + (size_t)o0 * G + y;
+                    #pragma unroll 8
+                    for (int bm = part; bm < rows_here; bm += split) {
+                        const int o = o0 + dir * bm;
+                        const int u = uc[bm * stride];
+                        const double w = o < cached_w_rows ? w_cache[(size_t)o * G + y] : P.weight_t[(size_t)o * G + y];
+                        const double* hrow = hbase + bm * HS_LD;
+                        s += hrow[u - 1] * (1.0 - w) + hrow[u] * w;
+                    }
+                    continue;
+                }
                 const int* up = P.upper_t + (size_t)o0 * G + y;
                 const double* wp = P.weight_t + (size_t)o0 * G + y;
-                const int stride = dir * G;
                 if (whole_row) {
                     #pragma unroll 8
                     for (int bm = part; bm < rows_here; bm += split) {
@@ -480,48 +506,6 @@ __device__ __forceinline__ void factored_body(const StepArgs& S, const int slab,
     }
 
     PHASE_MARK(5);
-    if (S.fused) {
-        // ---- the whole step in this launch (one slab per row, one rank): ring correction, closure, Euler update ----
-        // WC of the CURRENT C comes from per-row dots written one step earlier (or by wc_rows_kernel after an upload),
-        // so no grid-wide reduction is needed; this CTA leaves the row dot of its NEW row for the next step.
-        double& wc_sh = Eh[0];                                                     // the halo staging is dead by now
-        if (tid < 32) {
-            const double v = wc_total(S.wc_in, G, tid);
-            if (tid == 0) wc_sh = v;
-        }
-        const int ring_lo = P.ring_row_begin[lx], ring_hi = P.ring_row_begin[lx + 1];
-        for (int row = ring_lo + tid / 32; row < ring_hi; row += NT / 32) {       // this row's ring nodes: one warp each
-            double a = 0.0;
-            for (int en = P.ring_begin[row] + tid % 32; en < P.ring_begin[row + 1]; en += 32) a += P.ring_weight[en] * C[P.ring_node[en]];
-            a = warp_sum(a);
-            if (tid % 32 == 0) acc_y[P.ring_point[row] - lx * G] -= a;
-        }
-        __syncthreads();
-        const double N = S.N_cur[0];
-        const double WC = (wc_sh + (N * N) * P.wc_outside) * P.hh;                 // Solver.cpp:311, 314
-        if (lx == 0 && tid == 0) first_moment_update(P, N, WC, S.dt, S.scalars, S.N_next);
-        double* c_new = part_y;                                                    // staging of the updated row
-        for (int y = tid; y < G; y += NT) {
-            const int q = x * G + y;
-            const double inside = acc_y[y];
-            if (S.sum_out) S.sum_out[q] = inside;
-            const double c = C[q];
-            const double mc = (inside + (N * N) * P.out_weight[q]) * P.hh;
-            const double dc = second_moment_rhs(P, mc, c, N, WC, P.m_nodes[q], P.w_nodes[q]);
-            if (S.deriv_out) S.deriv_out[q] = dc;
-            double v = __dadd_rn(c, __dmul_rn(dc, S.dt));                          // Solver.cpp:577
-            v = v < 0.0 ? 0.0 : v;                                                 // Solver.cpp:578-580
-            S.C_next[q] = v;
-            c_new[y] = v;
-        }
-        __syncthreads();
-        if (tid < 32) {
-            const double s = wc_row_dot(P.wc_operator + (size_t)x * G, c_new, G, tid);
-            if (tid == 0) S.wc_out[x] = s;
-        }
-        PHASE_MARK(6);
-        return;
-    }
     double* out = partial + ((size_t)slab * local_rows(P) + lx) * G;
     for (int y = tid; y < G; y += NT) out[y] = acc_y[y];
 
@@ -575,7 +559,7 @@ persistent_kernel(const PersistentArgs A)
             A.observables[2 * point + 1] = S.C[(size_t)0 * G + (G - 1)];            // Values[k][G]       (Solver.cpp:1014)
         }
         if ((int)blockIdx.x < G) {
-            factored_body<BM, BN, TM, TN, BK, true, false>(S, 0, blockIdx.x);
+            factored_body<BM, BN, TM, TN, BK, true, false>(S, 0, blockIdx.x, k == 0, A.cached_w_rows);
         } else {
             const int warps = (gridDim.x - G) * (NT / 32);
             for (int row = (blockIdx.x - G) * (NT / 32) + tid / 32; row < P.n_ring; row += warps) {
@@ -666,8 +650,20 @@ cudaError_t launch_persistent_variant(const PersistentArgs& args, int grid, cuda
 {
     using Cfg = FactoredConfig<BM, BN, 5, 8, 16, true>;
     auto kernel = persistent_kernel<BM, BN, 5, 8, 16>;
-    const size_t smem = Cfg::smem_bytes(args.step.P.G, args.step.P.A);
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024);
+    // shared memory: the step's working set, then the 16-bit y-side index table, then as many weight rows as still fit
+    const int G = args.step.P.G, n_off = args.step.P.n_off;
+    const size_t base = Cfg::smem_bytes(G, args.step.P.A);
+    const size_t u_bytes = (((size_t)n_off * G + 3) & ~(size_t)3) * sizeof(unsigned short);
+    const size_t budget = 226 * 1024;
+    PersistentArgs with_cache = args;
+    with_cache.cached_w_rows = -1;
+    size_t smem = base;
+    if (base + u_bytes <= budget && G <= 65535) {
+        const int rows = (int)std::min<size_t>((size_t)n_off, (budget - base - u_bytes) / ((size_t)G * sizeof(double)));
+        with_cache.cached_w_rows = rows;
+        smem = base + u_bytes + (size_t)rows * G * sizeof(double);
+    }
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget);
     if (e != cudaSuccess) return e;
     int device = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&device);
@@ -677,7 +673,7 @@ cudaError_t launch_persistent_variant(const PersistentArgs& args, int grid, cuda
     if (max_grid) *max_grid = sms * per_sm;
     if (grid <= 0) return cudaSuccess;                  // query only
     if (grid > sms * per_sm) return cudaErrorCooperativeLaunchTooLarge;
-    void* params[] = {const_cast<PersistentArgs*>(&args)};
+    void* params[] = {&with_cache};
     return cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(Cfg::NT), params, smem, stream);
 }
 

@@ -224,15 +224,6 @@ finish_factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
     }
 }
 
-// per-row dot products of the WC functional for a freshly uploaded C (the fused step keeps them up to date afterwards)
-__global__ void __launch_bounds__(256) wc_rows_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__ wc_rows)
-{
-    const int x = blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (x >= P.G) return;
-    const double s = wc_row_dot(P.wc_operator + (size_t)x * P.G, C + (size_t)row_slot(P, x) * P.G, P.G, threadIdx.x & 31);
-    if ((threadIdx.x & 31) == 0) wc_rows[x] = s;
-}
-
 __global__ void record_observables_kernel(DevProblem P, const double* __restrict__ N_cur, const double* __restrict__ C,
                                           double* __restrict__ obs_row)
 {
@@ -241,11 +232,6 @@ __global__ void record_observables_kernel(DevProblem P, const double* __restrict
 }
 
 }  // namespace
-
-void launch_wc_rows(const DevProblem& P, const double* C, double* wc_rows, cudaStream_t stream)
-{
-    wc_rows_kernel<<<(P.G + 7) / 8, 256, 0, stream>>>(P, C, wc_rows);
-}
 
 void launch_record_observables(const DevProblem& P, const double* N_cur, const double* C, double* obs_row, cudaStream_t stream)
 {

@@ -271,24 +271,6 @@ def test_headline_grids_against_the_reference(ldm, name):
     assert np.all(err <= RTOL_RHS_TERMS * scale), (worst, got[worst], g["deriv"][worst], err[worst] / scale[worst])
 
 
-def test_single_launch_step_equals_three_kernel_step(ldm, monkeypatch):
-    """the optional fused step (LDM_FUSED_STEP=1: ring correction and update inside the factored kernel) is the same
-    arithmetic as the default three-kernel step"""
-    g = golden("exp_14_4_a")
-    props, _ = problems_from(g, "exp_14_4_a", ldm)
-    monkeypatch.setenv("LDM_PERSISTENT", "0")
-    plain = ldm.Equation(props)
-    monkeypatch.setenv("LDM_FUSED_STEP", "1")
-    monkeypatch.setenv("LDM_FACTORED_W", "0")
-    fused = ldm.Equation(props)
-    for eq in (plain, fused):
-        eq.upload(g["state_k100"])
-        eq.advance(50, 0.1)
-    a, b = plain.download(), fused.download()
-    assert np.all(np.abs(a - b) <= 1e-13 * np.abs(a))
-    assert fused.launches < plain.launches
-
-
 @pytest.mark.parametrize("knob", ["LDM_FACTORED_W=1", "LDM_FACTORED_WS=1", "LDM_FACTORED_MMA=0", "LDM_FACTORED_TN=4"])
 def test_alternative_contraction_kernels(ldm, monkeypatch, knob):
     """the optional variants of the contraction (precomputed W_x = Q.L_x with cp.async, warp-specialised producers,
