@@ -78,18 +78,13 @@ def executed_flop_per_step(props):
 
 
 def measured_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel, per launch, from the committed ncu capture"""
-    path = os.path.join(ROOT, "profiles", f"r01_ncu_factored_kernel_{workload}.csv")
+    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per step, from the committed ncu capture
+    (profiles/r01_traffic.json says which launch and how many steps it held)"""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
     if not os.path.exists(path):
         return None
-    total, seen = 0.0, False
-    for line in open(path):
-        parts = line.strip().split(",")
-        if len(parts) >= 3 and parts[0] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(parts[2], 1.0)
-            total += float(parts[1]) * scale
-            seen = True
-    return total if seen else None
+    entry = json.load(open(path)).get(workload)
+    return float(entry["dram_bytes_per_step"]) if entry else None
 
 
 class ClockSampler:

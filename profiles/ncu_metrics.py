@@ -1,0 +1,19 @@
+#!/usr/bin/env python
+"""Selected raw metrics of every kernel in an .ncu-rep: `ncu -i X.ncu-rep --page raw --csv | python ncu_metrics.py`"""
+import csv
+import sys
+
+KEEP = ["gpu__time_duration.sum", "launch__grid_size", "launch__block_size", "launch__registers_per_thread",
+        "launch__shared_mem_per_block_dynamic", "launch__waves_per_multiprocessor", "sm__cycles_elapsed.max",
+        "sm__throughput.avg.pct_of_peak_sustained_elapsed", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_tensor_subpipe_dmma.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "sm__warps_active.avg.pct_of_peak_sustained_active", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "lts__t_bytes.sum", "lts__t_sector_hit_rate.pct",
+        "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"]
+rows = list(csv.reader(sys.stdin))
+H, U = rows[0], rows[1]
+for r in rows[2:]:
+    print(f"Kernel Name,{r[H.index('Kernel Name')][:120]},")
+    for k in KEEP:
+        if k in H:
+            print(f"{k},{r[H.index(k)]},{U[H.index(k)]}")
