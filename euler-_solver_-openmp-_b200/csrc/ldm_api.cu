@@ -239,7 +239,7 @@ bool persistent_possible(ldm_context* c)
 {
     if (!c->persistent_enabled || c->algo != LDM_ALGO_FACTORED || c->dev.world != 1) return false;
     const ldm::FactoredPlan& p = c->plan;
-    if (p.slabs() != 1 || p.use_w || !p.mma || p.ws || p.tn != 8) return false;
+    if (p.slabs() != 1 || p.use_w || !p.mma || p.ws) return false;
     if (c->persistent_grid == 0) {
         ldm::PersistentArgs probe{};
         probe.step = make_step_args(c, c->d_C[0], c->d_N, c->d_N + 1, 0.0, nullptr, nullptr, c->d_C[1]);
