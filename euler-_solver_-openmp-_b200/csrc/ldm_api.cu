@@ -239,7 +239,7 @@ bool persistent_possible(ldm_context* c)
 {
     if (!c->persistent_enabled || c->algo != LDM_ALGO_FACTORED || c->dev.world != 1) return false;
     const ldm::FactoredPlan& p = c->plan;
-    if (p.slabs() != 1 || p.use_w || !p.mma || p.ws) return false;
+    if (p.slabs() != 1 || p.use_w || !p.mma) return false;
     if (c->persistent_grid == 0) {
         ldm::PersistentArgs probe{};
         probe.step = make_step_args(c, c->d_C[0], c->d_N, c->d_N + 1, 0.0, nullptr, nullptr, c->d_C[1]);
@@ -679,7 +679,7 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
                 if (h->plan.use_w) ensure_w_operand(h);
                 Group* g = nullptr;
                 for (Group& cand : groups)
-                    if (cand.shape.bm == h->plan.bm && cand.shape.bn == h->plan.bn && cand.shape.tn == h->plan.tn && cand.shape.mma == h->plan.mma && cand.shape.ws == h->plan.ws && cand.shape.use_w == h->plan.use_w) g = &cand;
+                    if (cand.shape.bm == h->plan.bm && cand.shape.bn == h->plan.bn && cand.shape.tn == h->plan.tn && cand.shape.mma == h->plan.mma  && cand.shape.use_w == h->plan.use_w) g = &cand;
                 if (!g) { groups.emplace_back(); g = &groups.back(); g->shape = h->plan; }
                 g->members.push_back(i);
                 g->max_slabs = std::max(g->max_slabs, h->plan.slabs());

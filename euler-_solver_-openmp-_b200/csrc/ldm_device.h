@@ -125,7 +125,6 @@ struct FactoredPlan {
     bool mma = true;           // contraction on the FP64 tensor cores (mma.sync m8n8k4) instead of DFMA register tiles
     bool use_w = false;        // contraction against the precomputed W_x = Q . L_x (ldm_factored_w.cu) instead of regenerating E_x:
                                // measured slower (K_x averages 1.35-1.65 x A), LDM_FACTORED_W=1 enables
-    bool ws = false;           // E-form only: warp-specialised K loop (producer warps generate E/Q, consumer warps run the MMAs)
     int tn = 8;                // columns per thread (8: 5x8 register tile, 4: 5x4 with twice the threads)
     int tiles = 1, chunks = 1; // beta tiles x column chunks; slabs = tiles * chunks partial sums per node
     int slabs() const { return tiles * chunks; }

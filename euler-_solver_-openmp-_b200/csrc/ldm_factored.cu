@@ -93,10 +93,6 @@ __device__ __forceinline__ void dmma_8x8x4(double (&c)[2], double a, double b)
                  : "+d"(c[0]), "+d"(c[1]) : "d"(a), "d"(b));
 }
 
-// named barriers (ids 1..4) between the producer and consumer halves of a warp-specialised CTA
-__device__ __forceinline__ void named_bar_sync(int id, int count) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-__device__ __forceinline__ void named_bar_arrive(int id, int count) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(count) : "memory"); }
-
 // The work of one CTA: row `lx` of this rank, slab `slab` (= beta tile * chunks + column chunk).  A device function so
 // that both the one-launch-per-step kernel and the persistent multi-step kernel run exactly the same code.
 template <int BM, int BN, int TM, int TN, int BK, bool MMA, bool WS>
@@ -178,131 +174,7 @@ __device__ __forceinline__ void factored_body(const StepArgs& S, const int slab,
     const bool want_halo = q0 > 0;
     const int e_col = tid % BN, e_k0 = tid / BN;          // this thread's E column and first row within a chunk
 
-    if constexpr (WS) {
-        // ---- warp-specialised K loop: the upper half of the CTA PRODUCES the E / Q chunks (global loads, interpolation,
-        // shared-memory stores) while the lower half CONSUMES them on the FP64 tensor cores, so the L2 latency and the
-        // arithmetic of E generation never sit in front of the MMAs.  Two buffers, four named barriers. ----
-        static_assert(MMA, "the warp-specialised loop feeds the tensor-core path");
-        constexpr int NC = NT / 2, NP = NT / 2;           // consumer / producer threads
-        constexpr int CW = NC / 32;                       // consumer warps, each owning a BM x (BN / CW) strip
-        constexpr int WNW = BN / CW, NBW = WNW / 8, MBW = BM / 8;
-        constexpr int EPP = (BK * BN) / NP;               // E elements per producer thread and chunk
-        constexpr int EB = EPP < 16 ? EPP : 16;           // ... generated in batches of EB (4 loads each in flight)
-        constexpr int QPP = (BK * BM + NP - 1) / NP;
-        constexpr int HPT = (BM + NC - 1) / NC;           // halo rows per consumer thread
-        static_assert((BK * BN) % NP == 0 && EPP % EB == 0 && WNW % 8 == 0, "warp-specialised tiling");
-        constexpr int BAR_FULL = 1, BAR_EMPTY = 3;
-        if (tid >= NC) {
-            const int p = tid - NC;
-            for (int kc = 0; kc < n_kc; kc++) {
-                const int buf = kc & 1;
-                if (kc >= 2) {
-                    PHASE_WAIT_BEGIN();
-                    named_bar_sync(BAR_EMPTY + buf, NT);                      // the consumers have finished with this buffer
-                    PHASE_WAIT_END(8, NC);
-                }
-                #pragma unroll
-                for (int r0 = 0; r0 < EPP; r0 += EB) {
-                    double raw[EB][4];
-                    #pragma unroll
-                    for (int r = 0; r < EB; r++) {
-                        const int en = (r0 + r) * NP + p, k = en / BN, col = en - k * BN;
-                        const int4 ra = *reinterpret_cast<const int4*>(tap_row + (kc * BK + k) * 4);
-                        const double* cp = C + min(q0 + col, G - 1);
-                        raw[r][0] = cp[ra.x]; raw[r][1] = cp[ra.y]; raw[r][2] = cp[ra.z]; raw[r][3] = cp[ra.w];
-                    }
-                    #pragma unroll
-                    for (int r = 0; r < EB; r++) {
-                        const int en = (r0 + r) * NP + p, k = en / BN, col = en - k * BN;
-                        const double4 wa = *reinterpret_cast<const double4*>(tap_w + (kc * BK + k) * 4);
-                        const double v = (raw[r][0] * wa.x + raw[r][1] * wa.y) + (raw[r][2] * wa.z + raw[r][3] * wa.w);
-                        Es[buf * E_TILE + k * LDE + col] = (q0 + col < G) ? v : 0.0;
-                    }
-                }
-                if (want_halo && p < BK) {
-                    const int alpha = kc * BK + p;
-                    const double* cp = C + (q0 - 1);
-                    const int4 ra = *reinterpret_cast<const int4*>(tap_row + alpha * 4);
-                    const double4 wa = *reinterpret_cast<const double4*>(tap_w + alpha * 4);
-                    Eh[buf * BK + p] = (cp[ra.x] * wa.x + cp[ra.y] * wa.y) + (cp[ra.z] * wa.z + cp[ra.w] * wa.w);
-                }
-                double qv[QPP];
-                #pragma unroll
-                for (int r = 0; r < QPP; r++) {
-                    const int en = r * NP + p, k = en % BK, bm = en / BK;      // Q is symmetric: read along alpha (coalesced)
-                    const int beta = b0 + bm, alpha = kc * BK + k;
-                    qv[r] = (en < BK * BM && beta < A && alpha < A) ? P.quadrant[(size_t)beta * A + alpha] : 0.0;
-                }
-                #pragma unroll
-                for (int r = 0; r < QPP; r++) {
-                    const int en = r * NP + p;
-                    if (en < BK * BM) Qs[buf * Q_TILE + (en / BK) * LDQ + en % BK] = qv[r];
-                }
-                named_bar_arrive(BAR_FULL + buf, NT);
-            }
-        } else {
-            double acc[MBW][NBW * 2];
-            double h_acc[HPT];
-            #pragma unroll
-            for (int i = 0; i < MBW; i++)
-                #pragma unroll
-                for (int j = 0; j < NBW * 2; j++) acc[i][j] = 0.0;
-            #pragma unroll
-            for (int i = 0; i < HPT; i++) h_acc[i] = 0.0;
-            const int lane_g = (tid & 31) >> 2, lane_t = tid & 3;
-            const int wn0 = (tid >> 5) * WNW;
-            for (int kc = 0; kc < n_kc; kc++) {
-                const int buf = kc & 1;
-                {
-                    PHASE_WAIT_BEGIN();
-                    named_bar_sync(BAR_FULL + buf, NT);
-                    PHASE_WAIT_END(7, 0);
-                }
-                if (kc == 0) PHASE_MARK(2);
-                const double* qs = Qs + buf * Q_TILE;
-                const double* es = Es + buf * E_TILE;
-                #pragma unroll
-                for (int k4 = 0; k4 < BK; k4 += 4) {
-                    double af[MBW], bf[NBW];
-                    #pragma unroll
-                    for (int mb = 0; mb < MBW; mb++) af[mb] = qs[(mb * 8 + lane_g) * LDQ + k4 + lane_t];
-                    #pragma unroll
-                    for (int nb = 0; nb < NBW; nb++) bf[nb] = es[(k4 + lane_t) * LDE + wn0 + nb * 8 + lane_g];
-                    #pragma unroll
-                    for (int mb = 0; mb < MBW; mb++)
-                        #pragma unroll
-                        for (int nb = 0; nb < NBW; nb++)
-                            dmma_8x8x4(*reinterpret_cast<double(*)[2]>(&acc[mb][nb * 2]), af[mb], bf[nb]);
-                }
-                if (want_halo) {
-                    #pragma unroll
-                    for (int i = 0; i < HPT; i++) {
-                        const int row = i * NC + tid;
-                        if (row < BM) {
-                            #pragma unroll
-                            for (int k = 0; k < BK; k++) h_acc[i] = fma(qs[row * LDQ + k], Eh[buf * BK + k], h_acc[i]);
-                        }
-                    }
-                }
-                if (kc + 2 < n_kc) named_bar_arrive(BAR_EMPTY + buf, NT);
-            }
-            PHASE_MARK(3);
-            #pragma unroll
-            for (int i = 0; i < HPT; i++) {
-                const int row = i * NC + tid;
-                if (row < BM) Hs[row * HS_LD] = h_acc[i];
-            }
-            #pragma unroll
-            for (int mb = 0; mb < MBW; mb++)
-                #pragma unroll
-                for (int nb = 0; nb < NBW; nb++) {
-                    double* dst = Hs + (mb * 8 + lane_g) * HS_LD + 1 + wn0 + nb * 8 + lane_t * 2;
-                    dst[0] = acc[mb][nb * 2];
-                    dst[1] = acc[mb][nb * 2 + 1];
-                }
-        }
-        __syncthreads();
-    } else {
+    {
         const int q = q0 + e_col;
         const double* c_col = C + (q < G ? q : G - 1);    // clamped: columns beyond G are multiplied by 0 below
         const double live = q < G ? 1.0 : 0.0;
@@ -619,12 +491,6 @@ void launch_variant(const StepArgs* one, const StepArgs* d_batch, dim3 grid, int
 template <bool BATCH>
 void dispatch(const FactoredPlan& shape, const StepArgs* one, const StepArgs* d_batch, dim3 grid, int G, int A, cudaStream_t stream)
 {
-    if (shape.mma && shape.ws) {  // FP64 tensor cores fed by producer warps: the default
-        if (shape.bm == 80 && shape.bn == 128) return launch_variant<80, 128, 5, 8, 16, BATCH, true, true>(one, d_batch, grid, G, A, stream);
-        if (shape.bm == 80 && shape.bn == 64) return launch_variant<80, 64, 5, 8, 16, BATCH, true, true>(one, d_batch, grid, G, A, stream);
-        if (shape.bm == 40 && shape.bn == 128) return launch_variant<40, 128, 5, 8, 16, BATCH, true, true>(one, d_batch, grid, G, A, stream);
-        return launch_variant<40, 64, 5, 8, 16, BATCH, true, true>(one, d_batch, grid, G, A, stream);
-    }
     if (shape.mma && shape.tn == 4) {   // FP64 tensor cores with twice the threads per tile (16 warps on an 80 x 128 tile)
         if (shape.bm == 80 && shape.bn == 128) return launch_variant<80, 128, 5, 4, 16, BATCH, true, false>(one, d_batch, grid, G, A, stream);
         if (shape.bm == 80 && shape.bn == 64) return launch_variant<80, 64, 5, 4, 16, BATCH, true, false>(one, d_batch, grid, G, A, stream);
@@ -711,7 +577,6 @@ FactoredPlan plan_factored(const DevProblem& P)
         if (v == 64 || v == 128) plan.bn = v;
     }
     if (const char* env = std::getenv("LDM_FACTORED_MMA")) plan.mma = std::atoi(env) != 0;
-    if (const char* env = std::getenv("LDM_FACTORED_WS")) plan.ws = std::atoi(env) != 0;
     if (const char* env = std::getenv("LDM_FACTORED_W")) plan.use_w = std::atoi(env) != 0;
     if (!plan.mma) plan.use_w = false;
     plan.tn = 4;       // 16 warps on an 80 x 128 tile: twice the table reads in flight in the y-side phase (12.4 k -> 8.9 k cycles)

@@ -271,16 +271,14 @@ def test_headline_grids_against_the_reference(ldm, name):
     assert np.all(err <= RTOL_RHS_TERMS * scale), (worst, got[worst], g["deriv"][worst], err[worst] / scale[worst])
 
 
-@pytest.mark.parametrize("knob", ["LDM_FACTORED_W=1", "LDM_FACTORED_WS=1", "LDM_FACTORED_MMA=0", "LDM_FACTORED_TN=4"])
+@pytest.mark.parametrize("knob", ["LDM_FACTORED_W=1", "LDM_FACTORED_MMA=0", "LDM_FACTORED_TN=8"])
 def test_alternative_contraction_kernels(ldm, monkeypatch, knob):
-    """the optional variants of the contraction (precomputed W_x = Q.L_x with cp.async, warp-specialised producers,
-    DFMA register tiles instead of tensor cores) compute the same integrals as the default"""
+    """the optional variants of the contraction (precomputed W_x = Q.L_x with cp.async, DFMA register tiles instead of
+    tensor cores, 8-warp instead of 16-warp tiles) compute the same integrals as the default"""
     g = golden("synth_g64")
     props, o = problems_from(g, "synth_g64", ldm)
     name, value = knob.split("=")
     monkeypatch.setenv(name, value)
-    if name == "LDM_FACTORED_TN":
-        monkeypatch.setenv("LDM_FACTORED_MMA", "0")
     eq = ldm.Equation(props)
     wc, mc = eq.integrals(g["state"])
     assert abs(wc - float(g["wc"])) <= 1e-13 * abs(float(g["wc"]))
