@@ -492,6 +492,7 @@ template <bool BATCH>
 void dispatch(const FactoredPlan& shape, const StepArgs* one, const StepArgs* d_batch, dim3 grid, int G, int A, cudaStream_t stream)
 {
     if (shape.mma && shape.tn == 4) {   // FP64 tensor cores with twice the threads per tile (16 warps on an 80 x 128 tile)
+        if (shape.bm == 128 && shape.bn == 128) return launch_variant<128, 128, 8, 4, 16, BATCH, true, false>(one, d_batch, grid, G, A, stream);
         if (shape.bm == 80 && shape.bn == 128) return launch_variant<80, 128, 5, 4, 16, BATCH, true, false>(one, d_batch, grid, G, A, stream);
         if (shape.bm == 80 && shape.bn == 64) return launch_variant<80, 64, 5, 4, 16, BATCH, true, false>(one, d_batch, grid, G, A, stream);
         if (shape.bm == 40 && shape.bn == 128) return launch_variant<40, 128, 5, 4, 16, BATCH, true, false>(one, d_batch, grid, G, A, stream);
@@ -517,11 +518,11 @@ void dispatch(const FactoredPlan& shape, const StepArgs* one, const StepArgs* d_
 
 }  // namespace
 
-template <int BM, int BN, int TN>
+template <int BM, int BN, int TN, int TM = 5>
 cudaError_t launch_persistent_variant(const PersistentArgs& args, int grid, cudaStream_t stream, int* max_grid)
 {
-    using Cfg = FactoredConfig<BM, BN, 5, TN, 16, true>;
-    auto kernel = persistent_kernel<BM, BN, 5, TN, 16>;
+    using Cfg = FactoredConfig<BM, BN, TM, TN, 16, true>;
+    auto kernel = persistent_kernel<BM, BN, TM, TN, 16>;
     // shared memory: the step's working set, then the 16-bit y-side index table, then as many weight rows as still fit
     const int G = args.step.P.G, n_off = args.step.P.n_off;
     const size_t base = Cfg::smem_bytes(G, args.step.P.A);
@@ -551,6 +552,7 @@ cudaError_t launch_persistent_variant(const PersistentArgs& args, int grid, cuda
 
 cudaError_t launch_persistent(const FactoredPlan& plan, const PersistentArgs& args, int grid, cudaStream_t stream, int* max_grid)
 {
+    if (plan.bm == 128) return launch_persistent_variant<128, 128, 4, 8>(args, grid, stream, max_grid);
     if (plan.tn == 4) {
         if (plan.bm == 80 && plan.bn == 128) return launch_persistent_variant<80, 128, 4>(args, grid, stream, max_grid);
         if (plan.bm == 80 && plan.bn == 64) return launch_persistent_variant<80, 64, 4>(args, grid, stream, max_grid);
@@ -569,8 +571,14 @@ FactoredPlan plan_factored(const DevProblem& P)
     // one column chunk when the grid allows it, because every
     // chunk's CTA scans the whole y-side table (LDM_FACTORED_BM / LDM_FACTORED_BN override, for tuning)
     const int A = P.A;
-    plan.bm = A <= 40 ? 40 : 80;       // taller tiles amortise E generation and the y-side table scan (measured at G = 512:
-                                       // 4 tiles of 80 rows, 32 % padding, beat 7 tiles of 40 rows, 3.1 vs 4.4 ms)
+    // Tile height: every beta tile regenerates E and re-scans the y-side table, a fixed cost of roughly 40 rows' worth of
+    // contraction, so taller tiles win unless they pad too much (measured at G = 512, A = 243: 4 x 80 rows 2.9 ms,
+    // 7 x 40 rows 4.4 ms).  128-row tiles need the 16-warp tensor-core variant and 128-column chunks.
+    plan.bm = A <= 40 ? 40 : 80;
+    if (P.G > 64 && A > 80) {
+        const int cost80 = ((A + 79) / 80) * (80 + 40), cost128 = ((A + 127) / 128) * (128 + 40);
+        if (cost128 < cost80 && std::getenv("LDM_FACTORED_NO_BM128") == nullptr) plan.bm = 128;
+    }
     plan.bn = P.G <= 64 ? 64 : 128;
     if (const char* env = std::getenv("LDM_FACTORED_BN")) {
         const int v = std::atoi(env);
@@ -586,8 +594,9 @@ FactoredPlan plan_factored(const DevProblem& P)
     }
     if (const char* env = std::getenv("LDM_FACTORED_BM")) {
         const int v = std::atoi(env);
-        if (v == 40 || v == 80) plan.bm = v;
+        if (v == 40 || v == 80 || (v == 128 && P.G > 64)) plan.bm = v;
     }
+    if (plan.bm == 128) { plan.mma = true; plan.tn = 4; plan.use_w = false; plan.bn = 128; }   // the only 128-row kernel
     plan.tiles = (A + plan.bm - 1) / plan.bm;
     plan.chunks = (P.G + plan.bn - 1) / plan.bn;
     return plan;

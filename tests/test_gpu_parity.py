@@ -226,7 +226,7 @@ def test_factored_equals_direct_on_the_16k_grid(ldm):
     assert_states_close(factored.download(), direct.download())
 
 
-@pytest.mark.parametrize("G,bm,bn", [(128, 40, 64), (200, 80, 128), (200, 40, 64), (96, 80, 64)])
+@pytest.mark.parametrize("G,bm,bn", [(128, 40, 64), (200, 80, 128), (200, 40, 64), (96, 80, 64), (200, 128, 128), (100, 128, 128)])
 def test_factored_tilings_equal_direct(ldm, monkeypatch, G, bm, bn):
     """every tiling of the factored kernel (several beta tiles, several column chunks with their halo column, ragged
     edges) against the sample-by-sample path on grids the CPU oracle cannot reach in a test"""
