@@ -189,6 +189,56 @@ def cpu_baseline(workload, budget_s=25.0):
                       "reference source built by-reference (bit-identical to the shipped build, which is ~30x slower)"}
 
 
+def run_sharded_peer(ldm, torch, dist, workload, rank, world, local_rank, steps, warmup):
+    """BASELINE config 4 with the all-gather FUSED into the update: the closing kernel of every rank stores its updated
+    rows straight into all ranks' next replica over NVLink (CUDA IPC peer mappings) and publishes a per-rank epoch flag;
+    the next step starts with a device-side wait on the flags.  No NCCL call on the data path (NCCL only carried the
+    64-byte IPC handles at set-up and the timing reduction)."""
+    sw, sm, b, d, dd, G = WORKLOADS[workload]
+    props = ldm.Properties.Generate(1, sw, sm, b, d, dd, G)
+    sh = ldm.ShardedEquation(props, rank, world, device=local_rank)
+
+    def all_gather_bytes(mine):
+        t = torch.from_numpy(mine).cuda()
+        out = torch.empty(world * t.numel(), dtype=torch.uint8, device="cuda")
+        dist.all_gather_into_tensor(out, t)
+        return out.cpu().numpy().reshape(world, -1)
+
+    sh.peer_connect(all_gather_bytes)
+    state0 = seeded_state(props.MomentsGrid, sm)
+    sh.peer_upload(state0[1:], state0[0])
+    dist.barrier()
+    torch.cuda.synchronize()
+    stream = torch.cuda.current_stream()
+    for _ in range(warmup):
+        sh.peer_step(DT, stream.cuda_stream)
+    torch.cuda.synchronize()
+    dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = sh.eq.launches
+    e0.record(stream)
+    for _ in range(steps):
+        sh.peer_step(DT, stream.cuda_stream)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    final_C, N_end = sh.peer_download()
+    dist.barrier()
+    assert np.all(np.isfinite(final_C)) and N_end > 0
+    flop_step, s_nz = algorithmic_flop_per_step(props)
+    P = G * G
+    return {"workload": workload, "G": G, "xi_points": P, "S_nz": s_nz, "scaling": "strong", "steps": steps, "warmup": warmup,
+            "value": P * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+            "collective": "fused into the closing kernel: NVLink peer stores of the updated rows into every rank's replica + epoch flags "
+                          "(%d bytes to each of %d peers per rank per step); no NCCL on the data path" % (sh.rows_per_rank * G * 8, world - 1),
+            "gpu_launches": int(sh.eq.launches - launches0), "algorithmic_tflops": flop_step * steps / (ms * 1e-3) / 1e12,
+            "checksum": float(final_C.sum() + N_end)}
+
+
 def run_sharded(ldm, torch, dist, workload, rank, world, local_rank, steps, warmup):
     """BASELINE config 4: ONE problem, its xi output rows sharded cyclically over the ranks; per step every rank
     updates its rows of C from the full replica and an NCCL all-gather (in place, over NVLink) rebuilds the replica.
@@ -298,6 +348,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sharded", default="g512", help="workload of the xi-sharded strong-scaling leg ('none' to skip)")
     ap.add_argument("--sharded-steps", type=int, default=10)
+    ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
+                    help="sharded leg at N > 1: all-gather fused into the update over NVLink peer stores, or an NCCL all-gather per step")
     ap.add_argument("--batch-sets", type=int, default=128, help="parameter sets per GPU of the batched leg (0 to skip)")
     ap.add_argument("--batch-steps", type=int, default=50)
     args = ap.parse_args()
@@ -380,7 +432,11 @@ def main():
 
     sharded = None
     if args.sharded != "none":
-        sharded = run_sharded(ldm, torch, dist, args.sharded, rank, world, local_rank, args.sharded_steps, 2)
+        if world > 1 and args.exchange == "peer":
+            sharded = run_sharded_peer(ldm, torch, dist, args.sharded, rank, world, local_rank, args.sharded_steps, 2)
+            sharded["nccl_variant"] = run_sharded(ldm, torch, dist, args.sharded, rank, world, local_rank, args.sharded_steps, 2)
+        else:
+            sharded = run_sharded(ldm, torch, dist, args.sharded, rank, world, local_rank, args.sharded_steps, 2)
 
     batch = None
     if args.batch_sets > 0:

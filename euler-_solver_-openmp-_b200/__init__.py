@@ -64,6 +64,11 @@ _SIGNATURES = {
     "ldm_shard_step": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]),
     "ldm_shard_set_N": (C.c_int, [C.c_void_p, C.c_double]),
     "ldm_shard_get_N": (C.c_int, [C.c_void_p, C.POINTER(C.c_double)]),
+    "ldm_shard_peer_alloc": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ldm_shard_peer_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "ldm_shard_peer_upload": (C.c_int, [C.c_void_p, _dp, C.c_double]),
+    "ldm_shard_peer_step": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
+    "ldm_shard_peer_download": (C.c_int, [C.c_void_p, _dp, C.POINTER(C.c_double)]),
     "ldm_measure_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.c_void_p]),
     "ldm_last_error": (C.c_char_p, []),
     "ldm_version": (C.c_char_p, []),
@@ -303,6 +308,27 @@ class ShardedEquation:
         v = C.c_double()
         _check(library().ldm_shard_get_N(self.eq._h, C.byref(v)))
         return v.value
+
+    # ---- fused update + all-gather over NVLink peer stores (no NCCL on the data path) ----
+    def peer_connect(self, all_gather_bytes):
+        """all_gather_bytes(np.uint8[192]) -> np.uint8[world, 192]: the caller's collective for the IPC handles"""
+        mine = np.zeros(3 * 64, dtype=np.uint8)
+        _check(library().ldm_shard_peer_alloc(self.eq._h, mine.ctypes.data))
+        everyone = np.ascontiguousarray(all_gather_bytes(mine), dtype=np.uint8)
+        assert everyone.shape == (self.world, 3 * 64)
+        _check(library().ldm_shard_peer_connect(self.eq._h, everyone.ctypes.data))
+
+    def peer_upload(self, C_natural, N):
+        _check(library().ldm_shard_peer_upload(self.eq._h, np.ascontiguousarray(self.to_gathered(C_natural)), float(N)))
+
+    def peer_step(self, dt, stream_ptr=0):
+        _check(library().ldm_shard_peer_step(self.eq._h, float(dt), C.c_void_p(stream_ptr)))
+
+    def peer_download(self):
+        out = np.empty((self.world * self.rows_per_rank, self.G))
+        n = C.c_double()
+        _check(library().ldm_shard_peer_download(self.eq._h, out, C.byref(n)))
+        return self.from_gathered(out), n.value
 
     def step(self, d_C_gathered_ptr, d_C_shard_out_ptr, dt, stream_ptr):
         _check(library().ldm_shard_step(self.eq._h, C.c_void_p(d_C_gathered_ptr), C.c_void_p(d_C_shard_out_ptr),

@@ -56,6 +56,17 @@ struct ldm_context {
     double* d_partial = nullptr;           // [tiles][P] factored path: per beta-tile sums
     double* d_ring = nullptr;              // [P] factored path: samples between the cutoff circle and the square edge
     double* d_wc_rows = nullptr;           // [G] factored path: per-row dot products of the WC operator (3-kernel path)
+    // fused update + all-gather (ldm_shard_peer_*)
+    double* peer_own[2] = {nullptr, nullptr};                 // this rank's two replicas of C (gathered layout)
+    unsigned long long* peer_own_flags = nullptr;             // [world] last step published by every rank
+    unsigned int* peer_done = nullptr;
+    int* peer_status = nullptr;
+    double* peer_C[2][ldm::kMaxPeers] = {};                   // every rank's replicas, peer-mapped
+    unsigned long long* peer_flags[ldm::kMaxPeers] = {};
+    std::vector<void*> peer_opened;
+    unsigned long long peer_epoch = 0;
+    int peer_parity = 0;
+    bool peer_connected = false;
     int persistent_grid = 0;               // co-resident CTAs of the persistent kernel (0: not queried yet, -1: unavailable)
     bool persistent_enabled = true;
     std::vector<void*> ring_allocations;   // the ring-correction CSR of the current (rank, world)
@@ -93,6 +104,9 @@ struct ldm_context {
         for (void* p : allocations) cudaFree(p);
         for (void* p : ring_allocations) cudaFree(p);
         for (void* p : w_allocations) cudaFree(p);
+        for (void* p : peer_opened) cudaIpcCloseMemHandle(p);
+        for (void* p : {(void*)peer_own[0], (void*)peer_own[1], (void*)peer_own_flags, (void*)peer_done, (void*)peer_status})
+            if (p) cudaFree(p);
         if (ev_begin) cudaEventDestroy(ev_begin);
         if (ev_end) cudaEventDestroy(ev_end);
         if (ev_fork) cudaEventDestroy(ev_fork);
@@ -200,6 +214,7 @@ ldm::StepArgs make_step_args(ldm_context* c, const double* C, const double* N_cu
     a.partial = c->d_partial; a.ring = c->d_ring; a.wc_rows = c->d_wc_rows; a.scalars = c->d_scalars;
     a.sum_out = sum_out; a.deriv_out = deriv_out; a.C_next = C_next;
     a.tiles = c->plan.tiles; a.chunks = c->plan.chunks;
+    a.peer_count = 0; a.done_counter = nullptr; a.epoch = 0;
     a.dt = dt;
     return a;
 }
@@ -306,6 +321,140 @@ int guarded(F&& body)
 }  // namespace
 
 extern "C" {
+
+int ldm_shard_peer_alloc(ldm_handle h, unsigned char* handles)
+{
+    if (!h || !handles) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    if (h->dev.world > ldm::kMaxPeers) return fail(LDM_ERR_ARGUMENT, "at most 8 ranks");
+    return guarded([&] {
+        LDM_CUDA(cudaSetDevice(h->device));
+        const size_t words = (size_t)h->dev.world * h->dev.rows_per_rank * h->dev.G;
+        for (int b = 0; b < 2; b++) {
+            if (!h->peer_own[b]) LDM_CUDA(cudaMalloc((void**)&h->peer_own[b], words * sizeof(double)));
+            LDM_CUDA(cudaMemset(h->peer_own[b], 0, words * sizeof(double)));
+        }
+        if (!h->peer_own_flags) LDM_CUDA(cudaMalloc((void**)&h->peer_own_flags, ldm::kMaxPeers * sizeof(unsigned long long)));
+        if (!h->peer_done) LDM_CUDA(cudaMalloc((void**)&h->peer_done, sizeof(unsigned int)));
+        if (!h->peer_status) LDM_CUDA(cudaMalloc((void**)&h->peer_status, sizeof(int)));
+        LDM_CUDA(cudaMemset(h->peer_own_flags, 0, ldm::kMaxPeers * sizeof(unsigned long long)));
+        LDM_CUDA(cudaMemset(h->peer_done, 0, sizeof(unsigned int)));
+        LDM_CUDA(cudaMemset(h->peer_status, 0, sizeof(int)));
+        static_assert(sizeof(cudaIpcMemHandle_t) == LDM_IPC_HANDLE_BYTES, "IPC handle size");
+        cudaIpcMemHandle_t ipc;
+        void* exported[3] = {h->peer_own[0], h->peer_own[1], h->peer_own_flags};
+        for (int i = 0; i < 3; i++) {
+            LDM_CUDA(cudaIpcGetMemHandle(&ipc, exported[i]));
+            std::memcpy(handles + (size_t)i * LDM_IPC_HANDLE_BYTES, &ipc, LDM_IPC_HANDLE_BYTES);
+        }
+        LDM_CUDA(cudaDeviceSynchronize());
+    });
+}
+
+int ldm_shard_peer_connect(ldm_handle h, const unsigned char* all_handles)
+{
+    if (!h || !all_handles) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    if (!h->peer_own[0]) return fail(LDM_ERR_ARGUMENT, "call ldm_shard_peer_alloc first");
+    return guarded([&] {
+        LDM_CUDA(cudaSetDevice(h->device));
+        for (void* p : h->peer_opened) cudaIpcCloseMemHandle(p);
+        h->peer_opened.clear();
+        for (int r = 0; r < h->dev.world; r++) {
+            void* mapped[3] = {h->peer_own[0], h->peer_own[1], h->peer_own_flags};
+            if (r != h->dev.rank) {
+                for (int i = 0; i < 3; i++) {
+                    cudaIpcMemHandle_t ipc;
+                    std::memcpy(&ipc, all_handles + ((size_t)r * 3 + i) * LDM_IPC_HANDLE_BYTES, LDM_IPC_HANDLE_BYTES);
+                    LDM_CUDA(cudaIpcOpenMemHandle(&mapped[i], ipc, cudaIpcMemLazyEnablePeerAccess));
+                    h->peer_opened.push_back(mapped[i]);
+                }
+            }
+            h->peer_C[0][r] = static_cast<double*>(mapped[0]);
+            h->peer_C[1][r] = static_cast<double*>(mapped[1]);
+            h->peer_flags[r] = static_cast<unsigned long long*>(mapped[2]);
+        }
+        h->peer_connected = true;
+    });
+}
+
+int ldm_shard_peer_upload(ldm_handle h, const double* C_gathered, double N)
+{
+    if (!h || !C_gathered) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    if (!h->peer_connected) return fail(LDM_ERR_ARGUMENT, "peers are not connected");
+    return guarded([&] {
+        LDM_CUDA(cudaSetDevice(h->device));
+        const size_t words = (size_t)h->dev.world * h->dev.rows_per_rank * h->dev.G;
+        LDM_CUDA(cudaDeviceSynchronize());
+        LDM_CUDA(cudaMemcpy(h->peer_own[0], C_gathered, words * sizeof(double), cudaMemcpyHostToDevice));
+        LDM_CUDA(cudaMemset(h->peer_own_flags, 0, ldm::kMaxPeers * sizeof(unsigned long long)));
+        LDM_CUDA(cudaMemset(h->peer_done, 0, sizeof(unsigned int)));
+        LDM_CUDA(cudaMemset(h->peer_status, 0, sizeof(int)));
+        h->cur = 0;
+        LDM_CUDA(cudaMemcpy(h->d_N, &N, sizeof(double), cudaMemcpyHostToDevice));
+        h->peer_epoch = 0;
+        h->peer_parity = 0;
+        LDM_CUDA(cudaDeviceSynchronize());
+    });
+}
+
+int ldm_shard_peer_step(ldm_handle h, double dt, void* cuda_stream)
+{
+    if (!h) return fail(LDM_ERR_ARGUMENT, "NULL handle");
+    if (!h->peer_connected) return fail(LDM_ERR_ARGUMENT, "peers are not connected");
+    if (h->algo != LDM_ALGO_FACTORED) return fail(LDM_ERR_UNSUPPORTED, "the fused exchange rides on the factored path");
+    return guarded([&] {
+        LDM_CUDA(cudaSetDevice(h->device));
+        cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
+        ldm_context* c = h;
+        ensure_ring_operator(c);
+        if (c->plan.use_w) ensure_w_operand(c);
+        const int cur = c->cur, nxt = cur ^ 1;
+        const int pb = c->peer_parity;
+        // every rank must have delivered the previous step into this rank's current replica
+        ldm::launch_peer_wait(c->peer_own_flags, c->dev.world, c->peer_epoch, c->peer_status, s);
+        ldm::StepArgs args = make_step_args(c, c->peer_own[pb], c->d_N + cur, c->d_N + nxt, dt, nullptr, nullptr, nullptr);
+        args.peer_count = c->dev.world;
+        for (int r = 0; r < c->dev.world; r++) {
+            args.peer_C_next[r] = c->peer_C[pb ^ 1][r];
+            args.peer_flags[r] = c->peer_flags[r];
+        }
+        args.done_counter = c->peer_done;
+        args.epoch = c->peer_epoch + 1;
+        const bool side = args.P.n_ring > 0;
+        if (side) {
+            LDM_CUDA(cudaEventRecord(c->ev_fork, s));
+            LDM_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+            ldm::launch_ring(args, c->aux_stream);
+            LDM_CUDA(cudaEventRecord(c->ev_join, c->aux_stream));
+        }
+        if (c->plan.use_w) ldm::launch_factored_w(c->plan, args, s);
+        else ldm::launch_factored(c->plan, args, s);
+        if (side) LDM_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
+        ldm::launch_finish_factored(args, s);
+        c->launches += 3 + (side ? 1 : 0);
+        c->cur = nxt;
+        c->peer_parity = pb ^ 1;
+        c->peer_epoch += 1;
+        LDM_CUDA(cudaGetLastError());
+    });
+}
+
+int ldm_shard_peer_download(ldm_handle h, double* C_gathered, double* N)
+{
+    if (!h || !C_gathered) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    if (!h->peer_connected) return fail(LDM_ERR_ARGUMENT, "peers are not connected");
+    return guarded([&] {
+        LDM_CUDA(cudaSetDevice(h->device));
+        const size_t words = (size_t)h->dev.world * h->dev.rows_per_rank * h->dev.G;
+        // the current replica is complete once every rank has published the last step
+        ldm::launch_peer_wait(h->peer_own_flags, h->dev.world, h->peer_epoch, h->peer_status, h->stream);
+        LDM_CUDA(cudaDeviceSynchronize());
+        int status = 0;
+        LDM_CUDA(cudaMemcpy(&status, h->peer_status, sizeof(int), cudaMemcpyDeviceToHost));
+        if (status != 0) throw CudaError("rank " + std::to_string(status - 1) + " never published its step (peer exchange timed out)");
+        LDM_CUDA(cudaMemcpy(C_gathered, h->peer_own[h->peer_parity], words * sizeof(double), cudaMemcpyDeviceToHost));
+        if (N) LDM_CUDA(cudaMemcpy(N, h->d_N + h->cur, sizeof(double), cudaMemcpyDeviceToHost));
+    });
+}
 
 const char* ldm_last_error(void) { return g_error.c_str(); }
 const char* ldm_version(void) { return "ldm_b200 0.1 (sm_100a)"; }

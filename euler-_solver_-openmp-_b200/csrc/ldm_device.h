@@ -46,6 +46,8 @@ struct DevProblem {
 
 // Everything one Euler step (or one right-hand side) of one problem touches.  Kernels take it by value for a single
 // problem, or index an array of them by blockIdx.z when a batch of independent parameter sets shares one launch.
+constexpr int kMaxPeers = 8;
+
 struct StepArgs {
     DevProblem P;
     const double* C;           // pair density at the old time, gathered layout (full replica)
@@ -59,6 +61,14 @@ struct StepArgs {
     double* deriv_out;         // may be NULL: dC/dt of this rank's rows
     double* C_next;            // may be NULL: updated rows
     int tiles, chunks;         // factored plan: slab = tile * chunks + chunk
+    // fused update + all-gather over NVLink (xi-sharded runs, ldm_shard_peer_*): when peer_count > 0 the closing kernel
+    // stores every updated value straight into the next-step replica of EVERY rank (peer-mapped memory, own rank
+    // included), then the last CTA to finish releases this rank's epoch into every rank's flag array
+    int peer_count;
+    double* peer_C_next[kMaxPeers];
+    unsigned long long* peer_flags[kMaxPeers];
+    unsigned int* done_counter;
+    unsigned long long epoch;
     double dt;
 };
 
@@ -97,6 +107,9 @@ void launch_pointwise(const DevProblem& P, const double* C, const double* inside
 // sum_out (may be NULL) receives inside_sum for ldm_integrals.
 void launch_finish_factored(const StepArgs& one, cudaStream_t stream);
 void launch_finish_factored_batch(const StepArgs* d_batch, int n, int max_points, cudaStream_t stream);
+
+// blocks until every rank's flag has reached `epoch` (or a spin budget runs out: *status becomes non-zero)
+void launch_peer_wait(const unsigned long long* flags, int world, unsigned long long epoch, int* status, cudaStream_t stream);
 
 // ring[lx][y] for the nodes of the ring CSR (other entries of `ring` stay zero)
 void launch_ring(const StepArgs& one, cudaStream_t stream);

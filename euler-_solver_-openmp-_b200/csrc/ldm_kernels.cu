@@ -207,21 +207,52 @@ finish_factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
 
     const int n = local_rows(P) * G;
     const int ql = blockIdx.x * blockDim.x + threadIdx.x;
-    if (ql >= n) return;
-    const int lx = ql / G, y = ql - lx * G;
-    const int q = (P.rank + P.world * lx) * G + y;
-    double inside = 0.0;
-    for (int t = 0; t < tiles; t++) inside += partial[(size_t)t * n + ql];
-    inside -= ring[ql];
-    if (sum_out) sum_out[ql] = inside;
-    const double c = C[(size_t)(P.rank * P.rows_per_rank + lx) * G + y];
-    const double mc = (inside + (N * N) * P.out_weight[q]) * P.hh;
-    const double dc = second_moment_rhs(P, mc, c, N, WC, P.m_nodes[q], P.w_nodes[q]);
-    if (deriv_out) deriv_out[ql] = dc;
-    if (C_next) {
-        const double v = __dadd_rn(c, __dmul_rn(dc, dt));
-        C_next[ql] = v < 0.0 ? 0.0 : v;
+    if (ql < n) {
+        const int lx = ql / G, y = ql - lx * G;
+        const int q = (P.rank + P.world * lx) * G + y;
+        double inside = 0.0;
+        for (int t = 0; t < tiles; t++) inside += partial[(size_t)t * n + ql];
+        inside -= ring[ql];
+        if (sum_out) sum_out[ql] = inside;
+        const size_t slot = (size_t)(P.rank * P.rows_per_rank + lx) * G + y;          // this node in the gathered layout
+        const double c = C[slot];
+        const double mc = (inside + (N * N) * P.out_weight[q]) * P.hh;
+        const double dc = second_moment_rhs(P, mc, c, N, WC, P.m_nodes[q], P.w_nodes[q]);
+        if (deriv_out) deriv_out[ql] = dc;
+        double v = __dadd_rn(c, __dmul_rn(dc, dt));
+        v = v < 0.0 ? 0.0 : v;
+        if (C_next) C_next[ql] = v;
+        for (int r = 0; r < S.peer_count; r++) S.peer_C_next[r][slot] = v;           // the all-gather: NVLink peer stores
     }
+    if (S.peer_count > 0) {
+        // release: every thread's peer stores are made visible system-wide, then the last CTA of the grid publishes
+        // this rank's epoch in every rank's flag array (the classic threadfence-reduction hand-off)
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            const unsigned int arrived = atomicAdd(S.done_counter, 1u);
+            if (arrived == gridDim.x - 1) {
+                *S.done_counter = 0u;
+                __threadfence_system();
+                for (int r = 0; r < S.peer_count; r++)
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(S.peer_flags[r] + P.rank), "l"(S.epoch) : "memory");
+            }
+        }
+    }
+}
+
+// One warp: lane r spins until rank r has published `epoch` (acquire, system scope).  A spin budget turns a lost peer
+// into an error status instead of a hung GPU.
+__global__ void peer_wait_kernel(const unsigned long long* flags, int world, unsigned long long epoch, int* status)
+{
+    const int r = threadIdx.x;
+    if (r >= world) return;
+    unsigned long long seen = 0;
+    for (long long spin = 0; spin < 40000000LL; spin++) {       // ~10-20 s
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flags + r) : "memory");
+        if (seen >= epoch) return;
+    }
+    atomicExch(status, 1 + r);
 }
 
 __global__ void record_observables_kernel(DevProblem P, const double* __restrict__ N_cur, const double* __restrict__ C,
@@ -232,6 +263,11 @@ __global__ void record_observables_kernel(DevProblem P, const double* __restrict
 }
 
 }  // namespace
+
+void launch_peer_wait(const unsigned long long* flags, int world, unsigned long long epoch, int* status, cudaStream_t stream)
+{
+    peer_wait_kernel<<<1, 32, 0, stream>>>(flags, world, epoch, status);
+}
 
 void launch_record_observables(const DevProblem& P, const double* N_cur, const double* C, double* obs_row, cudaStream_t stream)
 {

@@ -110,6 +110,21 @@ int  ldm_shard_step(ldm_handle h, const double* d_C_gathered, double* d_C_shard_
 int  ldm_shard_set_N(ldm_handle h, double N);
 int  ldm_shard_get_N(ldm_handle h, double* N);
 
+/* ---- xi-sharded stepping with the all-gather fused into the update (NVLink peer stores, no NCCL on the data path).
+ * One process per GPU.  ldm_shard_peer_alloc: after ldm_shard_configure; allocates this rank's two replicas of C
+ * (gathered layout) and its flag array, returns three 64-byte CUDA IPC handles.  Exchange the handles of all ranks
+ * out of band (e.g. torch.distributed.all_gather), then ldm_shard_peer_connect maps every peer's buffers.
+ * ldm_shard_peer_upload: the full C (gathered layout, host) and N into this rank's replica 0; follow with a
+ * host-side barrier across ranks.  ldm_shard_peer_step: waits (on the device) until every rank has published the
+ * previous step, updates this rank's rows and stores them into EVERY rank's next replica, publishes the step.
+ * ldm_shard_peer_download: this rank's current replica.  Returns LDM_ERR_CUDA if a peer never showed up. ---- */
+#define LDM_IPC_HANDLE_BYTES 64
+int  ldm_shard_peer_alloc(ldm_handle h, unsigned char* handles /* 3 * LDM_IPC_HANDLE_BYTES */);
+int  ldm_shard_peer_connect(ldm_handle h, const unsigned char* all_handles /* world * 3 * LDM_IPC_HANDLE_BYTES, rank-major */);
+int  ldm_shard_peer_upload(ldm_handle h, const double* C_gathered, double N);
+int  ldm_shard_peer_step(ldm_handle h, double dt, void* cuda_stream);
+int  ldm_shard_peer_download(ldm_handle h, double* C_gathered, double* N);
+
 /* ---- measurement support: FP64 (DFMA) peak of `device` in TFLOP/s, measured live by a register-resident
  * FMA chain; MEASURED_PEAKS.json has no FP64 figure, this is the roofline denominator bench.py reports. ---- */
 int  ldm_measure_fp64_peak(int device, double* tflops, double* reserved);
