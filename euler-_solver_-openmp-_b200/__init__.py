@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIBRARY_PATH = os.environ.get("LDM_LIBRARY", os.path.join(_HERE, "libldm_b200.so"))   # LDM_LIBRARY: debug builds only
 
-ALGO_AUTO, ALGO_DIRECT, ALGO_FACTORED = 0, 1, 2
+ALGO_AUTO, ALGO_DIRECT, ALGO_FACTORED, ALGO_PREFIX = 0, 1, 2, 3
 RECORD_LAST, RECORD_OBSERVABLES, RECORD_VALUES, RECORD_ALL = 0, 1, 2, 3
 
 # enum ExtrapolationType (Solver.cpp:28); only SquaredN is reachable for C on any experiment route

@@ -46,7 +46,10 @@ struct ldm_context {
     cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_fork = nullptr, ev_join = nullptr;
     ldm::Tables tables;
     ldm::DevProblem dev{};
-    ldm::FactoredPlan plan;
+    ldm::FactoredPlan plan;                // the active plan: plan_scan or plan_dense
+    ldm::FactoredPlan plan_dense, plan_scan;
+    ldm::SeparableKernel separable;        // structure of the m table (prefix-sum path when .ok)
+    bool scan_available = false;
     std::vector<void*> allocations;
     double* d_C[2] = {nullptr, nullptr};   // ping-pong pair density, natural layout
     double* d_N = nullptr;                 // [2] ping-pong first moment
@@ -219,6 +222,14 @@ ldm::StepArgs make_step_args(ldm_context* c, const double* C, const double* N_cu
     return a;
 }
 
+// the m*C kernel of the active plan: prefix sums for a separable table, otherwise the dense contraction
+void launch_integral(ldm_context* c, const ldm::StepArgs& args, cudaStream_t s)
+{
+    if (c->plan.scan) ldm::launch_scan(args, s);
+    else if (c->plan.use_w) ldm::launch_factored_w(c->plan, args, s);
+    else ldm::launch_factored(c->plan, args, s);
+}
+
 void rhs_and_update(ldm_context* c, const DevProblem& P, const double* C, const double* N_cur, double* N_next, double dt,
                     double* sum_out, double* deriv_out, double* C_next, cudaStream_t s)
 {
@@ -241,8 +252,7 @@ void rhs_and_update(ldm_context* c, const DevProblem& P, const double* C, const 
         ldm::launch_ring(args, c->aux_stream);
         LDM_CUDA(cudaEventRecord(c->ev_join, c->aux_stream));
     }
-    if (c->plan.use_w) ldm::launch_factored_w(c->plan, args, s);
-    else ldm::launch_factored(c->plan, args, s);
+    launch_integral(c, args, s);
     if (side) LDM_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
     ldm::launch_finish_factored(args, s);
     c->launches += 2 + (side ? 1 : 0);
@@ -252,14 +262,15 @@ void rhs_and_update(ldm_context* c, const DevProblem& P, const double* C, const 
 // is one slab, on one rank, and the grid (G row CTAs + at least one spare CTA for the ring correction) is co-resident.
 bool persistent_possible(ldm_context* c)
 {
-    if (!c->persistent_enabled || c->algo != LDM_ALGO_FACTORED || c->dev.world != 1) return false;
+    if (!c->persistent_enabled || c->algo == LDM_ALGO_DIRECT || c->dev.world != 1) return false;
     const ldm::FactoredPlan& p = c->plan;
-    if (p.slabs() != 1 || p.use_w || !p.mma) return false;
+    if (p.slabs() != 1 || p.use_w || (!p.scan && !p.mma)) return false;
     if (c->persistent_grid == 0) {
         ldm::PersistentArgs probe{};
         probe.step = make_step_args(c, c->d_C[0], c->d_N, c->d_N + 1, 0.0, nullptr, nullptr, c->d_C[1]);
         int max_grid = 0;
-        const cudaError_t e = ldm::launch_persistent(p, probe, 0, c->stream, &max_grid);
+        const cudaError_t e = p.scan ? ldm::launch_persistent_scan(probe, 0, c->stream, &max_grid)
+                                     : ldm::launch_persistent(p, probe, 0, c->stream, &max_grid);
         c->persistent_grid = (e == cudaSuccess && max_grid > 0) ? max_grid : -1;
         if (e != cudaSuccess) cudaGetLastError();
     }
@@ -284,7 +295,8 @@ void advance_persistent(ldm_context* c, int n_steps, double dt, long long first_
     cudaGetDevice(&device);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     const int grid = std::min(c->persistent_grid, std::max(sms, c->dev.G + 1));
-    LDM_CUDA(ldm::launch_persistent(c->plan, args, grid, c->stream, nullptr));
+    if (c->plan.scan) LDM_CUDA(ldm::launch_persistent_scan(args, grid, c->stream, nullptr));
+    else LDM_CUDA(ldm::launch_persistent(c->plan, args, grid, c->stream, nullptr));
     c->launches += 1;
     c->cur ^= (n_steps & 1);
 }
@@ -400,7 +412,7 @@ int ldm_shard_peer_step(ldm_handle h, double dt, void* cuda_stream)
 {
     if (!h) return fail(LDM_ERR_ARGUMENT, "NULL handle");
     if (!h->peer_connected) return fail(LDM_ERR_ARGUMENT, "peers are not connected");
-    if (h->algo != LDM_ALGO_FACTORED) return fail(LDM_ERR_UNSUPPORTED, "the fused exchange rides on the factored path");
+    if (h->algo == LDM_ALGO_DIRECT) return fail(LDM_ERR_UNSUPPORTED, "the fused exchange rides on the factored path");
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
         cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
@@ -426,8 +438,7 @@ int ldm_shard_peer_step(ldm_handle h, double dt, void* cuda_stream)
             ldm::launch_ring(args, c->aux_stream);
             LDM_CUDA(cudaEventRecord(c->ev_join, c->aux_stream));
         }
-        if (c->plan.use_w) ldm::launch_factored_w(c->plan, args, s);
-        else ldm::launch_factored(c->plan, args, s);
+        launch_integral(c, args, s);
         if (side) LDM_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
         ldm::launch_finish_factored(args, s);
         c->launches += 3 + (side ? 1 : 0);
@@ -539,8 +550,36 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         c->d_scalars = c->alloc<double>(ldm::kScalars);
         c->d_sum = c->alloc<double>(P);
         c->d_deriv = c->alloc<double>(P);
-        c->plan = ldm::plan_factored(d);
-        c->d_partial = c->alloc<double>(P * (size_t)c->plan.slabs());
+        // structure of the m table: separable inside its disc (every table Properties::Generate builds) -> prefix sums
+        d.qvec = nullptr; d.a_star = nullptr; d.beta_range = nullptr; d.scan_ranges = nullptr; d.scan_bn = 0; d.scan_chunks = 0;
+        {
+            std::vector<unsigned short> u16(t.axisM.upper.size());
+            for (int n = 0; n < d.G; n++)
+                for (int o = 0; o < d.n_off; o++) u16[(size_t)o * d.G + n] = (unsigned short)t.axisM.upper[(size_t)n * d.n_off + o];
+            d.upper_t16 = c->upload(u16);
+        }
+        ldm::detect_separable(t.offM, 1e-13, c->separable);
+        const int scan_bn = (c->separable.ok && d.G <= 65535) ? ldm::scan_pick_bn(d.G, d.A) : 0;
+        c->plan_dense = ldm::plan_factored(d);
+        if (scan_bn > 0 && std::getenv("LDM_SCAN_DISABLE") == nullptr) {
+            d.qvec = c->upload(c->separable.q);
+            d.a_star = c->upload(c->separable.a_star);
+            std::vector<int> pairs((size_t)d.A * 2);
+            for (int a = 0; a < d.A; a++) { pairs[2 * (size_t)a] = c->separable.beta_lo[a]; pairs[2 * (size_t)a + 1] = c->separable.beta_hi[a]; }
+            d.beta_range = reinterpret_cast<const int2*>(c->upload(pairs));
+            std::vector<int> ranges;
+            ldm::build_scan_ranges(t, scan_bn, ranges);
+            d.scan_ranges = c->upload(ranges);
+            d.scan_bn = scan_bn;
+            d.scan_chunks = (d.G + scan_bn - 1) / scan_bn;
+            c->plan_scan = c->plan_dense;
+            c->plan_scan.scan = true; c->plan_scan.use_w = false;
+            c->plan_scan.tiles = 1; c->plan_scan.chunks = d.scan_chunks;
+            c->scan_available = true;
+        }
+        c->plan = c->scan_available ? c->plan_scan : c->plan_dense;
+        c->algo = c->scan_available ? LDM_ALGO_PREFIX : LDM_ALGO_FACTORED;
+        c->d_partial = c->alloc<double>(P * (size_t)std::max(c->plan_dense.slabs(), c->scan_available ? c->plan_scan.slabs() : 1));
         c->d_ring = c->alloc<double>(P);
         c->d_wc_rows = c->alloc<double>((size_t)d.G);
         if (const char* env = std::getenv("LDM_PERSISTENT")) c->persistent_enabled = std::atoi(env) != 0;
@@ -562,9 +601,15 @@ void ldm_destroy(ldm_handle h) { delete h; }
 int ldm_set_algorithm(ldm_handle h, int algo)
 {
     if (!h) return fail(LDM_ERR_ARGUMENT, "NULL handle");
-    if (algo == LDM_ALGO_AUTO) algo = LDM_ALGO_FACTORED;
-    if (algo != LDM_ALGO_DIRECT && algo != LDM_ALGO_FACTORED) return fail(LDM_ERR_ARGUMENT, "unknown algorithm");
+    if (algo == LDM_ALGO_AUTO) algo = h->scan_available ? LDM_ALGO_PREFIX : LDM_ALGO_FACTORED;
+    if (algo != LDM_ALGO_DIRECT && algo != LDM_ALGO_FACTORED && algo != LDM_ALGO_PREFIX) return fail(LDM_ERR_ARGUMENT, "unknown algorithm");
+    if (algo == LDM_ALGO_PREFIX && !h->scan_available)
+        return fail(LDM_ERR_UNSUPPORTED, "the m table is not separable inside its disc: prefix sums do not apply");
     h->algo = algo;
+    if (algo != LDM_ALGO_DIRECT) {
+        h->plan = algo == LDM_ALGO_PREFIX ? h->plan_scan : h->plan_dense;
+        h->persistent_grid = 0;          // co-residency differs between the two kernels: query again
+    }
     return LDM_OK;
 }
 
@@ -798,7 +843,7 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
             ldm_context* h = handles[i];
             LDM_CUDA(cudaSetDevice(h->device));
             upload_state(h, inits[i]);
-            one_launch = one_launch && h->algo == LDM_ALGO_FACTORED && h->device == handles[0]->device && h->dev.world == 1;
+            one_launch = one_launch && h->algo != LDM_ALGO_DIRECT && h->device == handles[0]->device && h->dev.world == 1;
         }
         for (int i = 0; i < n; i++) {
             LDM_CUDA(cudaSetDevice(handles[i]->device));
@@ -819,6 +864,7 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
                 ldm::FactoredPlan shape;
                 std::vector<int> members;
                 int max_slabs = 0, max_rows = 0, max_G = 0, max_A = 0, max_ring = 0, max_points = 0;
+                size_t max_smem = 0;     // prefix-sum groups: the largest member's shared memory
                 ldm::StepArgs* d_args[2] = {nullptr, nullptr};
             };
             std::vector<Group> groups;
@@ -828,7 +874,9 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
                 if (h->plan.use_w) ensure_w_operand(h);
                 Group* g = nullptr;
                 for (Group& cand : groups)
-                    if (cand.shape.bm == h->plan.bm && cand.shape.bn == h->plan.bn && cand.shape.tn == h->plan.tn && cand.shape.mma == h->plan.mma  && cand.shape.use_w == h->plan.use_w) g = &cand;
+                    if ((cand.shape.scan && h->plan.scan) ||       // the prefix-sum kernel takes its tile shape at run time
+                        (!cand.shape.scan && !h->plan.scan && cand.shape.bm == h->plan.bm && cand.shape.bn == h->plan.bn &&
+                         cand.shape.tn == h->plan.tn && cand.shape.mma == h->plan.mma && cand.shape.use_w == h->plan.use_w)) g = &cand;
                 if (!g) { groups.emplace_back(); g = &groups.back(); g->shape = h->plan; }
                 g->members.push_back(i);
                 g->max_slabs = std::max(g->max_slabs, h->plan.slabs());
@@ -837,6 +885,7 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
                 g->max_A = std::max(g->max_A, h->dev.A);
                 g->max_ring = std::max(g->max_ring, h->dev.n_ring);
                 g->max_points = std::max(g->max_points, h->dev.G * h->dev.G);
+                if (h->plan.scan) g->max_smem = std::max(g->max_smem, ldm::scan_smem_bytes(h->dev.G, h->dev.A, h->dev.scan_bn));
             }
             std::vector<void*> scratch;
             try {
@@ -867,7 +916,8 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
                             ldm::launch_ring_batch(g.d_args[parity], members, g.max_ring, lead->aux_stream);
                             LDM_CUDA(cudaEventRecord(lead->ev_join, lead->aux_stream));
                         }
-                        if (g.shape.use_w) ldm::launch_factored_w_batch(g.shape, g.d_args[parity], members, g.max_slabs, g.max_rows, g.max_G, s);
+                        if (g.shape.scan) ldm::launch_scan_batch(g.d_args[parity], members, g.max_slabs, g.max_rows, g.max_smem, s);
+                        else if (g.shape.use_w) ldm::launch_factored_w_batch(g.shape, g.d_args[parity], members, g.max_slabs, g.max_rows, g.max_G, s);
                         else ldm::launch_factored_batch(g.shape, g.d_args[parity], members, g.max_slabs, g.max_rows, g.max_G, g.max_A, s);
                         if (side) LDM_CUDA(cudaStreamWaitEvent(s, lead->ev_join, 0));
                         ldm::launch_finish_factored_batch(g.d_args[parity], members, g.max_points, s);

@@ -30,6 +30,14 @@ struct DevProblem {
     const long long* w_offset; // [G] (-1: row not held by this rank)
     const int* w_k;            // [G] multiple of 16
     const int* w_plo;          // [G]
+    // prefix-sum path (ldm_scan.cu; ldm_model.h SeparableKernel): Q[beta][alpha] = qvec[beta] qvec[alpha] for
+    // alpha <= a_star[beta], 0 beyond.  NULL qvec: the table is not separable, the dense contraction is used.
+    const double* qvec;        // [A]
+    const int* a_star;         // [A]
+    const int2* beta_range;    // [A] rows beta with a_star[beta] == alpha: [x, y)
+    const unsigned short* upper_t16;   // [n_off][G] upper_t in 16 bits
+    const int* scan_ranges;    // [scan_chunks][ceil(G/32)][3][2] offset intervals of the y-side pass per (chunk, y block)
+    int scan_bn, scan_chunks;  // column chunk width (multiple of 32) and count
     const double* m_nodes;     // [G][G]  m(xi) at the moment nodes                        (Solver.cpp:469)
     const double* w_nodes;     // [G][G]  w(xi)                                            (Solver.cpp:490)
     const double* out_weight;  // [G][G]  sum of m over this node's samples beyond the cutoff
@@ -139,10 +147,18 @@ struct FactoredPlan {
     bool use_w = false;        // contraction against the precomputed W_x = Q . L_x (ldm_factored_w.cu) instead of regenerating E_x:
                                // measured slower (K_x averages 1.35-1.65 x A), LDM_FACTORED_W=1 enables
     int tn = 8;                // columns per thread (8: 5x8 register tile, 4: 5x4 with twice the threads)
+    bool scan = false;         // prefix-sum path (separable kernel table): tiles = 1, chunks = P.scan_chunks, runtime tile shape
     int tiles = 1, chunks = 1; // beta tiles x column chunks; slabs = tiles * chunks partial sums per node
     int slabs() const { return tiles * chunks; }
 };
 FactoredPlan plan_factored(const DevProblem& P);
+
+// Prefix-sum path (ldm_scan.cu).  scan_pick_bn: widest column chunk whose working set fits one CTA's shared memory.
+int scan_pick_bn(int G, int A);
+void launch_scan(const StepArgs& one, cudaStream_t stream);
+void launch_scan_batch(const StepArgs* d_batch, int n, int max_chunks, int max_rows, size_t max_smem, cudaStream_t stream);
+size_t scan_smem_bytes(int G, int A, int bn);
+cudaError_t launch_persistent_scan(const PersistentArgs& args, int grid, cudaStream_t stream, int* max_grid);
 // single problem: `one` by value; batch: d_batch[n] in device memory, all entries sharing the plan's tile shape
 void launch_factored(const FactoredPlan& plan, const StepArgs& one, cudaStream_t stream);
 void launch_factored_batch(const FactoredPlan& shape, const StepArgs* d_batch, int n, int max_slabs, int max_rows, int max_G, int max_A,

@@ -269,6 +269,92 @@ void build_tables(const ldm_problem& p, Tables& t)
     }
 }
 
+void detect_separable(const OffsetSet& off, double tolerance, SeparableKernel& out)
+{
+    const int A = off.A;
+    const double* Q = off.quadrant.data();
+    out = SeparableKernel();
+    out.a_star.assign((size_t)A, -1);
+    for (int b = 0; b < A; b++)
+        for (int a = 0; a < A; a++)
+            if (Q[(size_t)b * A + a] != 0.0) out.a_star[b] = a;
+    // staircase: every row is non-zero exactly on [0, a_star], a_star never grows with beta, the table is symmetric
+    for (int b = 0; b < A; b++) {
+        for (int a = 0; a <= out.a_star[b]; a++)
+            if (Q[(size_t)b * A + a] == 0.0) return;
+        if (b > 0 && out.a_star[b] > out.a_star[b - 1]) return;
+        for (int a = 0; a < A; a++)
+            if (Q[(size_t)b * A + a] != Q[(size_t)a * A + b]) return;
+    }
+    if (A == 0 || !(Q[0] > 0.0)) return;
+    // q from the first column, then two sweeps of the rank-one least-squares update over the non-zero entries (averages
+    // the entries' individual rounding errors)
+    out.q.assign((size_t)A, 0.0);
+    const double root = std::sqrt(Q[0]);
+    for (int a = 0; a < A; a++) out.q[a] = Q[(size_t)a * A] / root;
+    for (int sweep = 0; sweep < 2; sweep++) {
+        std::vector<double> next((size_t)A, 0.0);
+        for (int b = 0; b < A; b++) {
+            double num = 0, den = 0;
+            for (int a = 0; a <= out.a_star[b]; a++) { num += Q[(size_t)b * A + a] * out.q[a]; den += out.q[a] * out.q[a]; }
+            next[b] = den > 0 ? num / den : 0.0;
+        }
+        out.q = next;
+    }
+    for (int b = 0; b < A; b++)
+        for (int a = 0; a <= out.a_star[b]; a++) {
+            const double model = out.q[b] * out.q[a];
+            if (!(model > 0.0)) return;
+            out.max_rel_dev = std::max(out.max_rel_dev, std::abs(Q[(size_t)b * A + a] - model) / model);
+        }
+    if (!(out.max_rel_dev <= tolerance)) return;
+    out.beta_lo.assign((size_t)A, 0);
+    out.beta_hi.assign((size_t)A, 0);
+    for (int b = A - 1; b >= 0; b--) {
+        const int a = out.a_star[b];
+        if (a < 0) continue;
+        if (out.beta_hi[a] == 0) out.beta_hi[a] = b + 1;
+        out.beta_lo[a] = b;
+    }
+    out.ok = true;
+}
+
+void build_scan_ranges(const Tables& t, int bn, std::vector<int>& ranges)
+{
+    const int G = t.G, n_off = t.offM.n_off;
+    const int chunks = (G + bn - 1) / bn, blocks = (G + 31) / 32;
+    ranges.assign((size_t)chunks * blocks * kScanRanges * 2, 0);
+    std::vector<char> hit((size_t)n_off);
+    for (int c = 0; c < chunks; c++) {
+        const int q0 = c * bn, q1 = std::min(G, q0 + bn);      // columns [q0, q1)
+        for (int yb = 0; yb < blocks; yb++) {
+            std::fill(hit.begin(), hit.end(), 0);
+            for (int y = yb * 32; y < std::min(G, yb * 32 + 32); y++)
+                for (int o = 0; o < n_off; o++) {
+                    const int u = t.axisM.upper[(size_t)y * n_off + o];
+                    if (u == 0) continue;                       // sample beyond the grid
+                    if ((u - 1 >= q0 && u - 1 < q1) || (u >= q0 && u < q1)) hit[(size_t)o] = 1;
+                }
+            // maximal runs of hit offsets; while there are too many, close the narrowest gap
+            std::vector<std::pair<int, int>> runs;
+            for (int o = 0; o < n_off; o++)
+                if (hit[(size_t)o]) {
+                    if (!runs.empty() && runs.back().second == o) runs.back().second = o + 1;
+                    else runs.emplace_back(o, o + 1);
+                }
+            while ((int)runs.size() > kScanRanges) {
+                size_t best = 1;
+                for (size_t r = 2; r < runs.size(); r++)
+                    if (runs[r].first - runs[r - 1].second < runs[best].first - runs[best - 1].second) best = r;
+                runs[best - 1].second = runs[best].second;
+                runs.erase(runs.begin() + (long)best);
+            }
+            int* dst = ranges.data() + ((size_t)c * blocks + yb) * kScanRanges * 2;
+            for (size_t r = 0; r < runs.size(); r++) { dst[2 * r] = runs[r].first; dst[2 * r + 1] = runs[r].second; }
+        }
+    }
+}
+
 void build_ring_operator(const Tables& t, int rank, int world, RingOperator& out)
 {
     const int G = t.G, n_off = t.offM.n_off, A = t.offM.A;

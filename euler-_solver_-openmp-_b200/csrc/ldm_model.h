@@ -65,6 +65,28 @@ struct Tables {
 
 void build_tables(const ldm_problem& p, Tables& t);
 
+// Structure of the m-kernel quadrant that the prefix-sum path (ldm_scan.cu) exploits.  A truncated Gaussian
+// (Solver.cpp:113-123) is separable inside its disc: Q[beta][alpha] = q[beta] q[alpha] for alpha <= a_star[beta] and 0
+// beyond, with a_star non-increasing in beta (the quarter circle r <= 3 sigma as a staircase).  Then
+//     H_x[beta][:] = sum_alpha Q[beta][alpha] E_x[alpha][:] = q[beta] * (prefix sum over alpha <= a_star[beta] of q[alpha] E_x[alpha][:])
+// and the dense contraction collapses to one running sum along alpha.  detect_separable() verifies the structure on the
+// table it is given (any K x K table may arrive through ldm_create); `ok` is false when it does not hold to `tolerance`
+// relative, and the dense contraction is used instead.
+struct SeparableKernel {
+    bool ok = false;
+    double max_rel_dev = 0;        // max |Q - q q^T| / (q q^T) over the non-zero entries
+    std::vector<double> q;         // A
+    std::vector<int> a_star;       // A: last non-zero column of row beta (-1: empty row)
+    std::vector<int> beta_lo, beta_hi;   // A: rows beta in [beta_lo[a], beta_hi[a]) have a_star[beta] == a
+};
+void detect_separable(const OffsetSet& off, double tolerance, SeparableKernel& out);
+
+// y-side work list of the prefix-sum path for column chunks of width bn: for every (chunk, block of 32 consecutive nodes
+// y) up to kScanRanges intervals [lo, hi) of signed offsets o that cover every (y, o) whose interpolation pair
+// (upper-1, upper) touches a column of the chunk.  Layout [chunks][ceil(G/32)][kScanRanges][2].
+constexpr int kScanRanges = 3;
+void build_scan_ranges(const Tables& t, int bn, std::vector<int>& ranges);
+
 // The exact correction of the factored path as a sparse linear operator (time-invariant).  The factored sum
 // covers every sample inside the grid square; the reference replaces the samples beyond the cutoff circle by
 // N^2 (Solver.cpp:329-331), so for each node that owns such "ring" samples

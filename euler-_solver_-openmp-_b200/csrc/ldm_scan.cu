@@ -1,0 +1,417 @@
+// The prefix-sum evaluation of the m*C integral (Solver.cpp:277-316) for sm_100a.
+//
+// Same factorisation as ldm_factored.cu --
+//
+//     ext[x][y] = sum_{beta} sum_{o_j in beta} L[y][o_j] . H_x[beta][:],      H_x = Q . E_x,
+//     E_x[alpha][q] = sum_{o_i in alpha} (L[x][o_i] . C[:, q])
+//
+// -- but for the kernel tables the reference actually builds (Solver.cpp:98-145: a Gaussian truncated to the disc
+// r <= 3 sigma) Q is separable inside the disc: Q[beta][alpha] = q[beta] q[alpha] for alpha <= a_star[beta], 0 beyond,
+// a_star the quarter circle as a staircase (ldm_model.h SeparableKernel, verified per table at ldm_create).  So
+//
+//     H_x[beta][:] = q[beta] * R_x[a_star[beta]][:],      R_x[a][:] = sum_{alpha <= a} q[alpha] E_x[alpha][:]
+//
+// and the dense A x A x G contraction per row becomes ONE running sum along alpha: P*A additions per step instead of
+// P*A*A fused multiply-adds.  What remains is gather work: 4 loads per element of E, 2 shared-memory gathers per
+// (node y, signed offset) on the y side.
+//
+// One CTA owns one row x and one chunk of bn columns q (runtime shape: the H tile is A x bn doubles in shared memory):
+//   1. tap tables of the row (time-invariant; resident across steps in the persistent kernel), q folded into the weights;
+//   2. threads = (column, alpha segment): E on the fly from C (coalesced along q), running sum, and whenever alpha is
+//      the last in-disc column of some rows beta, H[beta][col] = q[beta] * sum;  the segments' totals are added afterwards;
+//   3. y side: a warp owns 32 consecutive nodes y and walks the offset intervals that touch this chunk (scan_ranges),
+//      lanes read the transposed tables coalesced, gather the two H columns of their interpolation pair and accumulate;
+//   4. per-chunk partial sums to global memory; finish_factored_kernel adds the chunks, subtracts the ring correction
+//      and closes the step.
+#include <algorithm>
+#include <cstdlib>
+
+#include <cooperative_groups.h>
+
+#include "ldm_device.h"
+#include "ldm_pointwise.cuh"
+
+namespace ldm {
+
+namespace {
+
+constexpr int kScanThreads = 512;
+constexpr int kScanUnroll = 4;            // E rows whose loads are in flight together (16 global loads per thread)
+constexpr int kTapPad = 8;                // zero-weight tap rows behind the last alpha (the unrolled loop reads ahead)
+
+struct ScanLayout {                       // byte offsets into dynamic shared memory, identical on host and device
+    int ld, a_pad, n_yblk, split, part_stride, ng, seg;
+    size_t hs, part, tot, offs, tap_w, qv, tap_row, sel, a_star, end;
+};
+
+__host__ __device__ inline size_t align32(size_t v) { return (v + 31) & ~(size_t)31; }
+
+__host__ __device__ inline ScanLayout scan_layout(int G, int A, int bn, int NT)
+{
+    ScanLayout L;
+    L.ld = bn + 2;                                        // one leading zero column (the "beyond the grid" pair reads it)
+    L.a_pad = (A + kTapPad + 3) & ~3;
+    L.n_yblk = (G + 31) / 32;
+    const int warps = NT / 32;
+    L.split = warps / L.n_yblk > 1 ? warps / L.n_yblk : 1;    // warps sharing one block of 32 nodes y
+    L.part_stride = L.n_yblk * 32;
+    L.ng = NT / bn > 1 ? NT / bn : 1;                     // alpha segments (thread groups of bn columns)
+    L.seg = (A + L.ng - 1) / L.ng;
+    size_t at = 0;
+    L.hs = at;      at = align32(at + sizeof(double) * (size_t)A * L.ld);
+    L.part = at;    at = align32(at + sizeof(double) * (size_t)L.split * L.part_stride);
+    L.tot = at;     at = align32(at + sizeof(double) * (size_t)L.ng * bn);
+    L.offs = at;    at = align32(at + sizeof(double) * (size_t)L.ng * bn);
+    L.tap_w = at;   at = align32(at + sizeof(double) * 4 * (size_t)L.a_pad);
+    L.qv = at;      at = align32(at + sizeof(double) * (size_t)L.a_pad);
+    L.tap_row = at; at = align32(at + sizeof(int) * 4 * (size_t)L.a_pad);
+    L.sel = at;     at = align32(at + sizeof(int2) * (size_t)L.a_pad);
+    L.a_star = at;  at = align32(at + sizeof(int) * (size_t)L.a_pad);
+    L.end = at;
+    return L;
+}
+
+// offsets sharing kernel node alpha: (A-1-alpha, A+alpha) for an odd extent, the single offset 0 for m == 2
+__device__ __forceinline__ int folded_offset(int A, int n_fold, int alpha, int f)
+{
+    return n_fold == 1 ? 0 : (f == 0 ? A - 1 - alpha : A + alpha);
+}
+
+// y side over one interval of offsets for one lane's node y.  MASKED: the chunk holds only columns [q0, q0 + bn), the
+// two taps of a pair are taken separately.  CACHED (persistent kernel): 16-bit interval indices and the first
+// cached_w_rows weight rows live in shared memory.
+template <bool MASKED, bool CACHED>
+__device__ __forceinline__ double y_side_interval(const DevProblem& P, const double* Hs, int ld, int q0, int bn, int lo, int hi, int step,
+                                                  int y, const unsigned short* u_cache, const double* w_cache, int cached_w_rows)
+{
+    const int G = P.G, A = P.A;
+    const bool single = P.n_off == 1;
+    double s = 0.0;
+    #pragma unroll 4
+    for (int o = lo; o < hi; o += step) {
+        const int beta = single ? 0 : (o < A ? A - 1 - o : o - A);
+        const size_t at = (size_t)o * G + y;
+        const int u = CACHED ? (int)u_cache[at] : (int)P.upper_t16[at];
+        const double w = (CACHED && o < cached_w_rows) ? w_cache[at] : P.weight_t[at];
+        const double* hrow = Hs + beta * ld + 1 - q0;
+        if (MASKED) {
+            const bool ok_a = (unsigned)(u - 1 - q0) < (unsigned)bn, ok_b = (unsigned)(u - q0) < (unsigned)bn;
+            const double a = hrow[ok_a ? u - 1 : q0], b = hrow[ok_b ? u : q0];
+            s += (ok_a ? a * (1.0 - w) : 0.0) + (ok_b ? b * w : 0.0);
+        } else {
+            s += hrow[u - 1] * (1.0 - w) + hrow[u] * w;
+        }
+    }
+    return s;
+}
+
+// The work of one CTA: row `lx` of this rank, column chunk `chunk`.
+template <int NT>
+__device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, const int lx, const bool build_tables,
+                                          const int cached_w_rows)
+{
+    const DevProblem& P = S.P;
+    // no __restrict__ / read-only path on the state: inside the persistent kernel other CTAs rewrite C every step
+    const double* C = S.C;
+    const int G = P.G, A = P.A, n_off = P.n_off, bn = P.scan_bn;
+    const int n_fold = n_off / A;
+    const int x = P.rank + P.world * lx;
+    const int q0 = chunk * bn;
+    const int tid = threadIdx.x;
+    const ScanLayout L = scan_layout(G, A, bn, NT);
+    const int ld = L.ld;
+
+    extern __shared__ __align__(32) unsigned char scan_smem[];
+    double* Hs = reinterpret_cast<double*>(scan_smem + L.hs);            // [A][ld]
+    double* part_y = reinterpret_cast<double*>(scan_smem + L.part);      // [split][n_yblk * 32]
+    double* tot = reinterpret_cast<double*>(scan_smem + L.tot);          // [ng][bn] running sum at the end of each segment
+    double* offs = reinterpret_cast<double*>(scan_smem + L.offs);        // [ng][bn] sum of the segments before
+    double* tap_w = reinterpret_cast<double*>(scan_smem + L.tap_w);      // [a_pad][4] q[alpha] * weights of the four C rows feeding E[alpha]
+    double* qv = reinterpret_cast<double*>(scan_smem + L.qv);            // [a_pad]
+    int* tap_row = reinterpret_cast<int*>(scan_smem + L.tap_row);        // [a_pad][4] their offsets (slot * G)
+    int2* sel = reinterpret_cast<int2*>(scan_smem + L.sel);              // [a_pad] rows beta closed by alpha
+    int* a_star = reinterpret_cast<int*>(scan_smem + L.a_star);          // [a_pad]
+    unsigned short* u_cache = reinterpret_cast<unsigned short*>(scan_smem + L.end);                    // [n_off][G]
+    double* w_cache = reinterpret_cast<double*>(scan_smem + align32(L.end + sizeof(unsigned short) * (size_t)n_off * G));
+
+    if (build_tables) {
+        if (cached_w_rows >= 0) {
+            for (int i = tid; i < n_off * G; i += NT) u_cache[i] = P.upper_t16[i];
+            for (int i = tid; i < cached_w_rows * G; i += NT) w_cache[i] = P.weight_t[i];
+        }
+        for (int t = tid; t < L.a_pad * 2; t += NT) {
+            const int alpha = t >> 1, f = t & 1;
+            double w_lo = 0.0, w_hi = 0.0;
+            int r_lo = 0, r_hi = 0;
+            if (alpha < A && f < n_fold) {
+                const int o = folded_offset(A, n_fold, alpha, f);
+                const int u = P.upper[(size_t)x * n_off + o];
+                if (u != 0) {
+                    const double w = P.weight[(size_t)x * n_off + o], qa = P.qvec[alpha];
+                    w_lo = qa * (1.0 - w); w_hi = qa * w;
+                    r_lo = row_slot(P, u - 1) * G; r_hi = row_slot(P, u) * G;
+                }
+            }
+            tap_w[alpha * 4 + f * 2] = w_lo; tap_w[alpha * 4 + f * 2 + 1] = w_hi;
+            tap_row[alpha * 4 + f * 2] = r_lo; tap_row[alpha * 4 + f * 2 + 1] = r_hi;
+        }
+        for (int a = tid; a < L.a_pad; a += NT) {
+            qv[a] = a < A ? P.qvec[a] : 0.0;
+            a_star[a] = a < A ? P.a_star[a] : -1;
+            sel[a] = a < A ? P.beta_range[a] : make_int2(0, 0);
+        }
+        for (int b = tid; b < A; b += NT) Hs[b * ld] = 0.0;              // the leading zero column (never written again)
+        __syncthreads();
+    }
+
+    // ---- E on the fly, running sum along alpha, H rows closed as their last in-disc column passes ----
+    const int col = tid % bn, grp = tid / bn;
+    const bool active = grp < L.ng;
+    if (active) {
+        const int a0 = grp * L.seg, a1 = min(A, a0 + L.seg);
+        const int q = q0 + col;
+        const bool live = q < G;
+        const double* c = C + (live ? q : G - 1);
+        double* hcol = Hs + 1 + col;
+        double run = 0.0;
+        for (int a = a0; a < a1; a += kScanUnroll) {
+            double e[kScanUnroll];
+            #pragma unroll
+            for (int k = 0; k < kScanUnroll; k++) {
+                const int4 ra = *reinterpret_cast<const int4*>(tap_row + (a + k) * 4);
+                const double4 wa = *reinterpret_cast<const double4*>(tap_w + (a + k) * 4);
+                e[k] = (c[ra.x] * wa.x + c[ra.y] * wa.y) + (c[ra.z] * wa.z + c[ra.w] * wa.w);
+            }
+            #pragma unroll
+            for (int k = 0; k < kScanUnroll; k++) {
+                if (a + k < a1) {
+                    run += e[k];
+                    const int2 rows = sel[a + k];
+                    for (int b = rows.x; b < rows.y; b++) hcol[b * ld] = live ? run * qv[b] : 0.0;
+                }
+            }
+        }
+        tot[grp * bn + col] = live ? run : 0.0;
+    }
+    __syncthreads();
+    if (active) {
+        double before = 0.0;
+        for (int g = 0; g < grp; g++) before += tot[g * bn + col];        // fixed order
+        offs[grp * bn + col] = before;
+    }
+    __syncthreads();
+    if (active) {
+        double* hcol = Hs + 1 + col;
+        for (int b = grp; b < A; b += L.ng) {
+            const int as = a_star[b];
+            if (as < 0) hcol[b * ld] = 0.0;                               // an empty row of the table
+            else {
+                const int g = as / L.seg;
+                if (g > 0) hcol[b * ld] += qv[b] * offs[g * bn + col];
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- y side ----
+    {
+        const int warp = tid >> 5, lane = tid & 31, warps = NT / 32;
+        const bool masked = P.scan_chunks > 1;
+        for (int item = warp; item < L.n_yblk * L.split; item += warps) {
+            const int yb = item % L.n_yblk, part = item / L.n_yblk;
+            const int y = min(yb * 32 + lane, G - 1);
+            const int* rng = P.scan_ranges + ((size_t)chunk * L.n_yblk + yb) * 6;
+            double s = 0.0;
+            #pragma unroll
+            for (int r = 0; r < 3; r++) {
+                const int lo = rng[2 * r] + part, hi = rng[2 * r + 1];
+                if (cached_w_rows >= 0) s += y_side_interval<false, true>(P, Hs, ld, q0, bn, lo, hi, L.split, y, u_cache, w_cache, cached_w_rows);
+                else if (masked) s += y_side_interval<true, false>(P, Hs, ld, q0, bn, lo, hi, L.split, y, nullptr, nullptr, 0);
+                else s += y_side_interval<false, false>(P, Hs, ld, q0, bn, lo, hi, L.split, y, nullptr, nullptr, 0);
+            }
+            part_y[part * L.part_stride + yb * 32 + lane] = s;
+        }
+        __syncthreads();
+        double* out = S.partial + ((size_t)chunk * local_rows(P) + lx) * G;
+        for (int y = tid; y < G; y += NT) {
+            double s = 0.0;
+            for (int part = 0; part < L.split; part++) s += part_y[part * L.part_stride + y];     // fixed order
+            out[y] = s;
+        }
+    }
+
+    // WC = <wc_operator, C> (Solver.cpp:265-274) row by row, folded into this launch.  Every rank reduces the FULL
+    // operator (no all-reduce needed): the first-chunk CTAs of this rank share all G rows round-robin.
+    if (chunk == 0 && S.wc_rows != nullptr) {
+        const int n_local = local_rows(P);
+        int slot = 0;
+        for (int xr = lx; xr < G; xr += n_local, slot++) {
+            if (slot % (NT / 32) != tid / 32) continue;          // one warp per row
+            const double s = wc_row_dot(P.wc_operator + (size_t)xr * G, C + (size_t)row_slot(P, xr) * G, G, tid % 32);
+            if (tid % 32 == 0) S.wc_rows[xr] = s;
+        }
+    }
+    __syncthreads();       // shared memory is reused by the next row / step of this CTA
+}
+
+template <bool BATCH>
+__global__ void __launch_bounds__(kScanThreads)
+scan_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
+{
+    const StepArgs& S = BATCH ? batch[blockIdx.z] : one;
+    if (BATCH && ((int)blockIdx.x >= S.P.scan_chunks || (int)blockIdx.y >= local_rows(S.P))) return;   // batch grids are padded
+    scan_body<kScanThreads>(S, blockIdx.x, blockIdx.y, true, -1);
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+    #pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);   // fixed butterfly
+    return v;
+}
+
+// Persistent multi-step kernel (cooperative launch, one CTA per SM): all Euler steps of a solve inside one launch, for
+// grids whose rows are one chunk each.  Per step: CTAs 0..G-1 run scan_body for their row while the spare CTAs apply the
+// sparse ring correction; grid barrier; every CTA closes its share of the nodes (closure, Euler update, clamp,
+// history); grid barrier.  The tap tables and the y-side tables stay in shared memory across steps.
+__global__ void __launch_bounds__(kScanThreads)
+persistent_scan_kernel(const PersistentArgs A)
+{
+    constexpr int NT = kScanThreads;
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    __shared__ double wc_shared;
+    StepArgs S = A.step;
+    const DevProblem& P = S.P;
+    const int G = P.G, n = G * G, tid = threadIdx.x;
+    int parity = A.parity;
+    for (int k = 0; k < A.n_steps; k++) {
+        S.C = A.C[parity]; S.C_next = A.C[parity ^ 1];
+        S.N_cur = A.N + parity; S.N_next = A.N + (parity ^ 1);
+        const long long point = A.first_point + k;                 // index of the state this step starts from
+        if (blockIdx.x == 0 && tid == 0 && A.observables) {
+            A.observables[2 * point] = S.N_cur[0];                                  // Values[k][0]       (Solver.cpp:1011)
+            A.observables[2 * point + 1] = S.C[(size_t)0 * G + (G - 1)];            // Values[k][G]       (Solver.cpp:1014)
+        }
+        if ((int)blockIdx.x < G) {
+            scan_body<NT>(S, 0, blockIdx.x, k == 0, A.cached_w_rows);
+        } else {
+            const int warps = (gridDim.x - G) * (NT / 32);
+            for (int row = (blockIdx.x - G) * (NT / 32) + tid / 32; row < P.n_ring; row += warps) {
+                double acc = 0.0;
+                for (int en = P.ring_begin[row] + tid % 32; en < P.ring_begin[row + 1]; en += 32) acc += P.ring_weight[en] * S.C[P.ring_node[en]];
+                acc = warp_sum(acc);
+                if (tid % 32 == 0) S.ring[P.ring_point[row]] = acc;
+            }
+        }
+        grid.sync();
+        if (tid < 32) {
+            const double v = wc_total(S.wc_rows, G, tid);
+            if (tid == 0) wc_shared = v;
+        }
+        __syncthreads();
+        const double N = S.N_cur[0];
+        const double WC = (wc_shared + (N * N) * P.wc_outside) * P.hh;             // Solver.cpp:311, 314
+        double* values_next = A.values ? A.values + (point + 1) * A.stride : nullptr;
+        double* derivs_here = A.derivs ? A.derivs + point * A.stride : nullptr;
+        if (blockIdx.x == 0 && tid == 0) {
+            first_moment_update(P, N, WC, S.dt, S.scalars, S.N_next);
+            if (values_next) values_next[0] = S.N_next[0];
+            if (derivs_here) derivs_here[0] = S.scalars[1];
+        }
+        for (int q = blockIdx.x * NT + tid; q < n; q += gridDim.x * NT) {
+            const double inside = S.partial[q] - S.ring[q];
+            const double c = S.C[q];
+            const double mc = (inside + (N * N) * P.out_weight[q]) * P.hh;
+            const double dc = second_moment_rhs(P, mc, c, N, WC, P.m_nodes[q], P.w_nodes[q]);
+            double v = __dadd_rn(c, __dmul_rn(dc, S.dt));                          // Solver.cpp:577
+            v = v < 0.0 ? 0.0 : v;                                                 // Solver.cpp:578-580
+            S.C_next[q] = v;
+            if (values_next) values_next[1 + q] = v;
+            if (derivs_here) derivs_here[1 + q] = dc;
+        }
+        grid.sync();
+        parity ^= 1;
+    }
+}
+
+constexpr size_t kSmemBudget = 226 * 1024;
+
+void configure_once(const void* kernel, bool& done)
+{
+    if (!done) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+        done = true;
+    }
+}
+
+}  // namespace
+
+size_t scan_smem_bytes(int G, int A, int bn) { return scan_layout(G, A, bn, kScanThreads).end; }
+
+int scan_pick_bn(int G, int A)
+{
+    if (const char* env = std::getenv("LDM_SCAN_BN")) {
+        const int v = std::atoi(env);
+        if (v >= 32 && v <= kScanThreads && v % 32 == 0 && scan_smem_bytes(G, A, v) <= kSmemBudget) return v;
+    }
+    // widest chunk (a multiple of 32, at most 128 columns) whose H tile fits; then the evenest split of the row
+    int bn = 128;
+    while (bn > 32 && scan_smem_bytes(G, A, bn) > kSmemBudget) bn -= 32;
+    if (scan_smem_bytes(G, A, bn) > kSmemBudget) return 0;       // table too tall for one CTA: dense contraction instead
+    const int chunks = (G + bn - 1) / bn;
+    const int even = (((G + chunks - 1) / chunks) + 31) & ~31;
+    return even < bn ? even : bn;
+}
+
+void launch_scan(const StepArgs& one, cudaStream_t stream)
+{
+    static bool configured[64] = {};
+    int device = 0;
+    cudaGetDevice(&device);
+    configure_once((const void*)scan_kernel<false>, configured[device & 63]);
+    const DevProblem& P = one.P;
+    const size_t smem = scan_smem_bytes(P.G, P.A, P.scan_bn);
+    scan_kernel<false><<<dim3(P.scan_chunks, local_rows(P), 1), kScanThreads, smem, stream>>>(one, nullptr);
+}
+
+void launch_scan_batch(const StepArgs* d_batch, int n, int max_chunks, int max_rows, size_t max_smem, cudaStream_t stream)
+{
+    static bool configured[64] = {};
+    int device = 0;
+    cudaGetDevice(&device);
+    configure_once((const void*)scan_kernel<true>, configured[device & 63]);
+    static const StepArgs none{};
+    scan_kernel<true><<<dim3(max_chunks, max_rows, n), kScanThreads, max_smem, stream>>>(none, d_batch);
+}
+
+cudaError_t launch_persistent_scan(const PersistentArgs& args, int grid, cudaStream_t stream, int* max_grid)
+{
+    const void* kernel = (const void*)persistent_scan_kernel;
+    const DevProblem& P = args.step.P;
+    const int G = P.G, n_off = P.n_off;
+    // shared memory: the step's working set, then the 16-bit y-side index table, then as many weight rows as still fit
+    const size_t base = scan_smem_bytes(G, P.A, P.scan_bn);
+    const size_t u_bytes = align32(sizeof(unsigned short) * (size_t)n_off * G);
+    PersistentArgs with_cache = args;
+    with_cache.cached_w_rows = -1;
+    size_t smem = base;
+    if (base + u_bytes <= kSmemBudget && std::getenv("LDM_SCAN_NO_CACHE") == nullptr) {
+        const int rows = (int)std::min<size_t>((size_t)n_off, (kSmemBudget - base - u_bytes) / ((size_t)G * sizeof(double)));
+        with_cache.cached_w_rows = rows;
+        smem = base + u_bytes + (size_t)rows * G * sizeof(double);
+    }
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+    if (e != cudaSuccess) return e;
+    int device = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_scan_kernel, kScanThreads, smem);
+    if (e != cudaSuccess) return e;
+    if (max_grid) *max_grid = sms * per_sm;
+    if (grid <= 0) return cudaSuccess;                  // query only
+    if (grid > sms * per_sm) return cudaErrorCooperativeLaunchTooLarge;
+    void* params[] = {&with_cache};
+    return cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kScanThreads), params, smem, stream);
+}
+
+}  // namespace ldm

@@ -44,6 +44,9 @@ typedef struct ldm_context* ldm_handle;
 #define LDM_ALGO_AUTO      0
 #define LDM_ALGO_DIRECT    1   /* per-sample gather, the reference's sum re-ordered only */
 #define LDM_ALGO_FACTORED  2   /* interpolate - contract with the kernel table - interpolate, plus an exact cutoff correction */
+#define LDM_ALGO_PREFIX    3   /* the same with the contraction collapsed to a running sum: needs a table that is separable
+                                  inside its disc (every table of Properties::GenerateKernel, S:98-145, is); AUTO picks it
+                                  when the table passes the check at ldm_create, LDM_ALGO_FACTORED otherwise */
 
 /* history selector of ldm_solve (SolverResults, S:525-537) */
 #define LDM_RECORD_LAST        0   /* last state only (what Experiment_14_6 reads, S:1050-1055) */

@@ -59,6 +59,10 @@ def assert_states_close(got, want):
     assert np.all(err <= bound), (worst, got[worst], want[worst])
 
 
+def algo_id(ldm, algorithm):
+    return {"direct": ldm.ALGO_DIRECT, "factored": ldm.ALGO_FACTORED, "prefix": ldm.ALGO_PREFIX}[algorithm]
+
+
 ALL = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(p).startswith("large_"))
 
 
@@ -71,12 +75,12 @@ def test_kernels_at_nodes_bitwise(ldm, name):
     assert np.array_equal(m, g["m_nodes"]) and np.array_equal(w, g["w_nodes"])
 
 
-@pytest.mark.parametrize("algorithm", ["direct", "factored"])
+@pytest.mark.parametrize("algorithm", ["direct", "factored", "prefix"])
 @pytest.mark.parametrize("name", ALL)
 def test_rhs_against_golden(ldm, name, algorithm):
     g = golden(name)
     props, o = problems_from(g, name, ldm)
-    eq = ldm.Equation(props, algorithm=ldm.ALGO_DIRECT if algorithm == "direct" else ldm.ALGO_FACTORED)
+    eq = ldm.Equation(props, algorithm=algo_id(ldm, algorithm))
     if "synth" in name:
         cases = [(g["state"], g["deriv"])]
     else:
@@ -86,13 +90,13 @@ def test_rhs_against_golden(ldm, name, algorithm):
         assert_rhs_close(o, state, got, want)
 
 
-@pytest.mark.parametrize("algorithm", ["direct", "factored"])
+@pytest.mark.parametrize("algorithm", ["direct", "factored", "prefix"])
 @pytest.mark.parametrize("name", ["exp_14_4_b", "exp_14_4_c", "exp_14_6_a_080", "exp_14_6_b_000", "synth_g32", "synth_g64",
                                   "synth_g48_narrow_w"])
 def test_integrals_against_oracle(ldm, name, algorithm):
     g = golden(name)
     props, o = problems_from(g, name, ldm)
-    eq = ldm.Equation(props, algorithm=ldm.ALGO_DIRECT if algorithm == "direct" else ldm.ALGO_FACTORED)
+    eq = ldm.Equation(props, algorithm=algo_id(ldm, algorithm))
     state = g["state"] if "synth" in name else g["state_k100"]
     wc, mc = eq.integrals(state)
     wc_ref, mc_ref = (float(g["wc"]), g["mc"]) if "synth" in name else o.integrals(state)
@@ -100,12 +104,13 @@ def test_integrals_against_oracle(ldm, name, algorithm):
     assert np.all(np.abs(mc - mc_ref) <= 1e-13 * np.abs(mc_ref))
 
 
+@pytest.mark.parametrize("algorithm", ["prefix", "factored"])
 @pytest.mark.parametrize("name", ["exp_14_4_a", "exp_14_4_b", "exp_14_4_c"])
-def test_experiment_14_4_trajectory(ldm, name):
+def test_experiment_14_4_trajectory(ldm, name, algorithm):
     """CalculateFirstMoment(100) (Solver.cpp:885-906): dt 0.1, 1001 points, N0 = 200."""
     g = golden(name)
     props, _ = problems_from(g, name, ldm)
-    eq = ldm.Equation(props)
+    eq = ldm.Equation(props, algorithm=algo_id(ldm, algorithm))
     res = ldm.EulerSolver().Solve(eq, ldm.SquaredN, 100, 0.1, eq.GenerateEquilibriumValuesForNAndC(200),
                                   record=ldm.RECORD_ALL)
     assert len(res.Times) == 1001 and np.array_equal(res.Times, g["times"])
@@ -124,13 +129,14 @@ def test_experiment_14_4_trajectory(ldm, name):
     assert np.array_equal(last.Derivatives[0], res.Derivatives[-1])
 
 
+@pytest.mark.parametrize("algorithm", ["prefix", "factored"])
 @pytest.mark.parametrize("name", [n for n in ALL if "14_6" in n])
-def test_experiment_14_6_entries(ldm, name):
+def test_experiment_14_6_entries(ldm, name, algorithm):
     """One entry of CalculateWithVaryingSigma(200) (Solver.cpp:909-977): 2001 points; includes the entries where
     the clamp is active (14.6a[0], sigma_W = 1e-8) and where the population goes extinct (14.6b[0])."""
     g = golden(name)
     props, _ = problems_from(g, name, ldm)
-    eq = ldm.Equation(props)
+    eq = ldm.Equation(props, algorithm=algo_id(ldm, algorithm))
     res = ldm.EulerSolver().Solve(eq, ldm.SquaredN, 200, 0.1, eq.GenerateEquilibriumValuesForNAndC(200),
                                   record=ldm.RECORD_VALUES)
     assert len(res.Times) == 2001 and np.array_equal(res.Times, g["times"])
@@ -150,14 +156,15 @@ def test_resident_stepping_equals_solve(ldm):
     assert eq.last_elapsed_ms() > 0 and eq.launches > 0
 
 
-def test_batch_of_parameter_sets(ldm):
+@pytest.mark.parametrize("algorithm", ["prefix", "factored"])
+def test_batch_of_parameter_sets(ldm, algorithm):
     """the 14.6 loop (Solver.cpp:940-963) over a few entries at once, slot-indexed results"""
     names = ["exp_14_6_a_012", "exp_14_6_b_040", "exp_14_6_a_080", "exp_14_6_b_012"]
     eqs, inits, wants = [], [], []
     for name in names:
         g = golden(name)
         props, _ = problems_from(g, name, ldm)
-        eq = ldm.Equation(props)
+        eq = ldm.Equation(props, algorithm=algo_id(ldm, algorithm))
         eqs.append(eq)
         inits.append(eq.GenerateEquilibriumValuesForNAndC(200))
         wants.append(g["final_state"])
@@ -208,12 +215,13 @@ def test_direct_path_trajectory(ldm):
     assert_states_close(res.Values[1000], g["final_state"])
 
 
-def test_factored_equals_direct_on_the_16k_grid(ldm):
-    """BASELINE config 3 (G = 128, 16 384 xi-points): the CPU oracle needs ~10 s per evaluation there, so the two
+@pytest.mark.parametrize("algorithm", ["prefix", "factored"])
+def test_factored_equals_direct_on_the_16k_grid(ldm, algorithm):
+    """BASELINE config 3 (G = 128, 16 384 xi-points): the CPU oracle needs ~10 s per evaluation there, so the
     GPU algorithms -- each pinned to the oracle at the smaller sizes above -- are compared with each other."""
     props = ldm.Properties.Generate(1, 0.15, 0.15, 0.4, 0.2, 0.001, 128)
     direct = ldm.Equation(props, algorithm=ldm.ALGO_DIRECT)
-    factored = ldm.Equation(props, algorithm=ldm.ALGO_FACTORED)
+    factored = ldm.Equation(props, algorithm=algo_id(ldm, algorithm))
     g = props.MomentsGrid
     st = direct.GenerateEquilibriumValuesForNAndC(200)
     st[1:] *= (1 + 0.5 * np.exp(-(g[:, None] ** 2 + g[None, :] ** 2) / (2 * 0.15 ** 2))).ravel()
@@ -241,6 +249,52 @@ def test_factored_tilings_equal_direct(ldm, monkeypatch, G, bm, bn):
     (w1, m1), (w2, m2) = direct.integrals(st), factored.integrals(st)
     assert abs(w1 - w2) <= 1e-14 * abs(w1)
     assert np.all(np.abs(m1 - m2) <= 1e-13 * np.abs(m1))
+
+
+@pytest.mark.parametrize("G,bn", [(128, 0), (128, 64), (128, 32), (200, 0), (200, 96), (200, 32), (96, 0), (100, 64), (41, 32), (333, 0)])
+def test_prefix_chunkings_equal_direct(ldm, monkeypatch, G, bn):
+    """every column chunking of the prefix-sum kernel (one chunk, several chunks with pairs straddling the chunk
+    boundary, ragged last chunk, chunk wider than the grid) against the sample-by-sample path"""
+    props = ldm.Properties.Generate(1, 0.12, 0.09, 0.4, 0.2, 0.001, G)
+    direct = ldm.Equation(props, algorithm=ldm.ALGO_DIRECT)
+    if bn:
+        monkeypatch.setenv("LDM_SCAN_BN", str(bn))
+    prefix = ldm.Equation(props, algorithm=ldm.ALGO_PREFIX)
+    g = props.MomentsGrid
+    st = direct.GenerateEquilibriumValuesForNAndC(200)
+    st[1:] *= (1 + 0.5 * np.exp(-(g[:, None] ** 2 + g[None, :] ** 2) / (2 * 0.1 ** 2)) + 0.1 * np.sin(7 * g[:, None] + 3 * g[None, :])).ravel()
+    (w1, m1), (w2, m2) = direct.integrals(st), prefix.integrals(st)
+    assert abs(w1 - w2) <= 1e-14 * abs(w1)
+    assert np.all(np.abs(m1 - m2) <= 1e-13 * np.abs(m1))
+    for eq in (direct, prefix):
+        eq.upload(st)
+        eq.advance(5, 0.1)
+    assert_states_close(prefix.download(), direct.download())
+
+
+def test_table_that_is_not_separable_takes_the_dense_contraction(ldm):
+    """ldm_create accepts any K x K table; the prefix-sum path is only taken when the table passes the structure check
+    (a truncated Gaussian does).  A table with one perturbed entry must fall back to the dense contraction -- and still
+    equal the sample-by-sample sum over that very table."""
+    props = ldm.Properties.Generate(1, 0.1, 0.1, 0.45, 0.25, 0.001, 64)
+    table = np.ctypeslib.as_array(props._ptr.contents.M, (props.K, props.K))
+    table[3, 5] *= 1.01
+    table[5, 3] *= 1.01
+    eq = ldm.Equation(props)
+    with pytest.raises(ldm.LdmError):
+        eq.set_algorithm(ldm.ALGO_PREFIX)
+    direct = ldm.Equation(props, algorithm=ldm.ALGO_DIRECT)
+    g = props.MomentsGrid
+    st = eq.GenerateEquilibriumValuesForNAndC(200)
+    st[1:] *= (1 + 0.5 * np.exp(-(g[:, None] ** 2 + g[None, :] ** 2) / (2 * 0.1 ** 2))).ravel()
+    (w1, m1), (w2, m2) = direct.integrals(st), eq.integrals(st)
+    assert np.all(np.abs(m1 - m2) <= 1e-13 * np.abs(m1))
+    table[3, 5] /= 1.01
+    table[5, 3] /= 1.01
+    clean = ldm.Equation(props)
+    clean.set_algorithm(ldm.ALGO_PREFIX)
+    (_, m3) = clean.integrals(st)
+    assert np.max(np.abs(m3 - m2) / np.abs(m2)) > 1e-9      # the perturbation was visible, so the check above means something
 
 
 @pytest.mark.parametrize("name", ["large_g128", "large_g512"])
@@ -279,15 +333,15 @@ def test_alternative_contraction_kernels(ldm, monkeypatch, knob):
     props, o = problems_from(g, "synth_g64", ldm)
     name, value = knob.split("=")
     monkeypatch.setenv(name, value)
-    eq = ldm.Equation(props)
+    eq = ldm.Equation(props, algorithm=ldm.ALGO_FACTORED)
     wc, mc = eq.integrals(g["state"])
     assert abs(wc - float(g["wc"])) <= 1e-13 * abs(float(g["wc"]))
     assert np.all(np.abs(mc - g["mc"]) <= 1e-13 * np.abs(g["mc"]))
     big = ldm.Properties.Generate(1, 0.12, 0.09, 0.4, 0.2, 0.001, 200)      # two column chunks, two beta tiles
-    a, b = ldm.Equation(big), None
+    a, b = ldm.Equation(big, algorithm=ldm.ALGO_FACTORED), None
     monkeypatch.delenv(name)
     monkeypatch.delenv("LDM_FACTORED_MMA", raising=False)
-    b = ldm.Equation(big)
+    b = ldm.Equation(big, algorithm=ldm.ALGO_FACTORED)
     st = b.GenerateEquilibriumValuesForNAndC(200)
     gg = big.MomentsGrid
     st[1:] *= (1 + 0.3 * np.exp(-(gg[:, None] ** 2 + gg[None, :] ** 2) / 0.02)).ravel()
@@ -295,14 +349,15 @@ def test_alternative_contraction_kernels(ldm, monkeypatch, knob):
     assert np.all(np.abs(m1 - m2) <= 1e-13 * np.abs(m2))
 
 
-def test_persistent_kernel_equals_per_step_launches(ldm, monkeypatch):
+@pytest.mark.parametrize("algorithm", ["prefix", "factored"])
+def test_persistent_kernel_equals_per_step_launches(ldm, monkeypatch, algorithm):
     """the cooperative multi-step kernel (all Euler steps in one launch, the default where it fits) against the
     three-launches-per-step path: same arithmetic, so the same bits; and every record mode of ldm_solve agrees"""
     g = golden("exp_14_4_c")
     props, _ = problems_from(g, "exp_14_4_c", ldm)
-    persistent = ldm.Equation(props)
+    persistent = ldm.Equation(props, algorithm=algo_id(ldm, algorithm))
     monkeypatch.setenv("LDM_PERSISTENT", "0")
-    stepwise = ldm.Equation(props)
+    stepwise = ldm.Equation(props, algorithm=algo_id(ldm, algorithm))
     init = persistent.GenerateEquilibriumValuesForNAndC(200)
     runs = [ldm.EulerSolver().Solve(eq, ldm.SquaredN, 30, 0.1, init, record=ldm.RECORD_ALL) for eq in (persistent, stepwise)]
     assert persistent.launches < stepwise.launches / 50
