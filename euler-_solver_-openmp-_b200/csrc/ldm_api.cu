@@ -551,7 +551,7 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         c->d_sum = c->alloc<double>(P);
         c->d_deriv = c->alloc<double>(P);
         // structure of the m table: separable inside its disc (every table Properties::Generate builds) -> prefix sums
-        d.qvec = nullptr; d.a_star = nullptr; d.beta_range = nullptr; d.scan_ranges = nullptr; d.scan_bn = 0; d.scan_chunks = 0;
+        d.qvec = nullptr; d.a_star = nullptr; d.beta_range = nullptr; d.scan_ranges = nullptr; d.scan_bn = 0; d.scan_chunks = 0; d.scan_nt = 512; d.scan_live_rows = 0;
         {
             std::vector<unsigned short> u16(t.axisM.upper.size());
             for (int n = 0; n < d.G; n++)
@@ -572,6 +572,9 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
             d.scan_ranges = c->upload(ranges);
             d.scan_bn = scan_bn;
             d.scan_chunks = (d.G + scan_bn - 1) / scan_bn;
+            d.scan_nt = ldm::scan_pick_threads(d.G, d.A, scan_bn);
+            d.scan_live_rows = 0;
+            while (d.scan_live_rows < d.A && c->separable.a_star[(size_t)d.scan_live_rows] >= 0) d.scan_live_rows++;
             c->plan_scan = c->plan_dense;
             c->plan_scan.scan = true; c->plan_scan.use_w = false;
             c->plan_scan.tiles = 1; c->plan_scan.chunks = d.scan_chunks;
@@ -865,6 +868,7 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
                 std::vector<int> members;
                 int max_slabs = 0, max_rows = 0, max_G = 0, max_A = 0, max_ring = 0, max_points = 0;
                 size_t max_smem = 0;     // prefix-sum groups: the largest member's shared memory
+                int scan_nt = 512;
                 ldm::StepArgs* d_args[2] = {nullptr, nullptr};
             };
             std::vector<Group> groups;
@@ -874,10 +878,10 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
                 if (h->plan.use_w) ensure_w_operand(h);
                 Group* g = nullptr;
                 for (Group& cand : groups)
-                    if ((cand.shape.scan && h->plan.scan) ||       // the prefix-sum kernel takes its tile shape at run time
+                    if ((cand.shape.scan && h->plan.scan && cand.scan_nt == h->dev.scan_nt) ||   // the prefix-sum kernel takes its tile shape at run time
                         (!cand.shape.scan && !h->plan.scan && cand.shape.bm == h->plan.bm && cand.shape.bn == h->plan.bn &&
                          cand.shape.tn == h->plan.tn && cand.shape.mma == h->plan.mma && cand.shape.use_w == h->plan.use_w)) g = &cand;
-                if (!g) { groups.emplace_back(); g = &groups.back(); g->shape = h->plan; }
+                if (!g) { groups.emplace_back(); g = &groups.back(); g->shape = h->plan; g->scan_nt = h->dev.scan_nt; }
                 g->members.push_back(i);
                 g->max_slabs = std::max(g->max_slabs, h->plan.slabs());
                 g->max_rows = std::max(g->max_rows, h->dev.G);
@@ -885,7 +889,7 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
                 g->max_A = std::max(g->max_A, h->dev.A);
                 g->max_ring = std::max(g->max_ring, h->dev.n_ring);
                 g->max_points = std::max(g->max_points, h->dev.G * h->dev.G);
-                if (h->plan.scan) g->max_smem = std::max(g->max_smem, ldm::scan_smem_bytes(h->dev.G, h->dev.A, h->dev.scan_bn));
+                if (h->plan.scan) g->max_smem = std::max(g->max_smem, ldm::scan_smem_bytes(h->dev.G, h->dev.A, h->dev.scan_bn, h->dev.scan_nt));
             }
             std::vector<void*> scratch;
             try {
@@ -916,7 +920,7 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
                             ldm::launch_ring_batch(g.d_args[parity], members, g.max_ring, lead->aux_stream);
                             LDM_CUDA(cudaEventRecord(lead->ev_join, lead->aux_stream));
                         }
-                        if (g.shape.scan) ldm::launch_scan_batch(g.d_args[parity], members, g.max_slabs, g.max_rows, g.max_smem, s);
+                        if (g.shape.scan) ldm::launch_scan_batch(g.d_args[parity], members, g.scan_nt, g.max_slabs, g.max_rows, g.max_smem, s);
                         else if (g.shape.use_w) ldm::launch_factored_w_batch(g.shape, g.d_args[parity], members, g.max_slabs, g.max_rows, g.max_G, s);
                         else ldm::launch_factored_batch(g.shape, g.d_args[parity], members, g.max_slabs, g.max_rows, g.max_G, g.max_A, s);
                         if (side) LDM_CUDA(cudaStreamWaitEvent(s, lead->ev_join, 0));

@@ -38,6 +38,8 @@ struct DevProblem {
     const unsigned short* upper_t16;   // [n_off][G] upper_t in 16 bits
     const int* scan_ranges;    // [scan_chunks][ceil(G/32)][3][2] offset intervals of the y-side pass per (chunk, y block)
     int scan_bn, scan_chunks;  // column chunk width (multiple of 32) and count
+    int scan_live_rows;        // rows beta < scan_live_rows have a_star >= 0; the rest of the table is empty
+    int scan_nt;               // threads per CTA = ng * scan_bn (ng lanes of a warp share one column)
     const double* m_nodes;     // [G][G]  m(xi) at the moment nodes                        (Solver.cpp:469)
     const double* w_nodes;     // [G][G]  w(xi)                                            (Solver.cpp:490)
     const double* out_weight;  // [G][G]  sum of m over this node's samples beyond the cutoff
@@ -155,9 +157,10 @@ FactoredPlan plan_factored(const DevProblem& P);
 
 // Prefix-sum path (ldm_scan.cu).  scan_pick_bn: widest column chunk whose working set fits one CTA's shared memory.
 int scan_pick_bn(int G, int A);
+int scan_pick_threads(int G, int A, int bn);
 void launch_scan(const StepArgs& one, cudaStream_t stream);
-void launch_scan_batch(const StepArgs* d_batch, int n, int max_chunks, int max_rows, size_t max_smem, cudaStream_t stream);
-size_t scan_smem_bytes(int G, int A, int bn);
+void launch_scan_batch(const StepArgs* d_batch, int n, int nt, int max_chunks, int max_rows, size_t max_smem, cudaStream_t stream);
+size_t scan_smem_bytes(int G, int A, int bn, int nt);
 cudaError_t launch_persistent_scan(const PersistentArgs& args, int grid, cudaStream_t stream, int* max_grid);
 // single problem: `one` by value; batch: d_batch[n] in device memory, all entries sharing the plan's tile shape
 void launch_factored(const FactoredPlan& plan, const StepArgs& one, cudaStream_t stream);

@@ -17,8 +17,9 @@
 //
 // One CTA owns one row x and one chunk of bn columns q (runtime shape: the H tile is A x bn doubles in shared memory):
 //   1. tap tables of the row (time-invariant; resident across steps in the persistent kernel), q folded into the weights;
-//   2. threads = (column, alpha segment): E on the fly from C (coalesced along q), running sum, and whenever alpha is
-//      the last in-disc column of some rows beta, H[beta][col] = q[beta] * sum;  the segments' totals are added afterwards;
+//   2. threads = (column, group): E on the fly from C (coalesced along q), running sum along alpha (the groups of a column
+//      exchange block sums once per super-chunk of alphas), and whenever alpha is the last in-disc column of some rows
+//      beta, H[beta][col] = q[beta] * sum;
 //   3. y side: a warp owns 32 consecutive nodes y and walks the offset intervals that touch this chunk (scan_ranges),
 //      lanes read the transposed tables coalesced, gather the two H columns of their interpolation pair and accumulate;
 //   4. per-chunk partial sums to global memory; finish_factored_kernel adds the chunks, subtracts the ring correction
@@ -33,15 +34,27 @@
 
 namespace ldm {
 
+// Optional phase timeline (debug build `make phase-clocks`): thread 0 of every CTA stores clock64() at the phase
+// boundaries; read back by tools/phase_clocks.py.  Off in the product build.
+#ifdef LDM_PHASE_CLOCKS
+__device__ long long g_scan_clock[148 * 8][12];
+#define SCAN_MARK(i) do { if (threadIdx.x == 0) g_scan_clock[(blockIdx.y * gridDim.x + blockIdx.x) % (148 * 8)][i] = clock64(); } while (0)
+#else
+#define SCAN_MARK(i) do { } while (0)
+#endif
+
 namespace {
 
-constexpr int kScanThreads = 512;
-constexpr int kScanUnroll = 4;            // E rows whose loads are in flight together (16 global loads per thread)
-constexpr int kTapPad = 8;                // zero-weight tap rows behind the last alpha (the unrolled loop reads ahead)
+constexpr int kScanThreadsMax = 512;       // launch bound; a CTA runs ng * bn threads (scan_pick_threads)
+constexpr int kScanLead = 2;              // doubles in front of column 0 of an H row: rows start on 128-byte lines, and index
+                                          // kScanLead - 1 is the zero column that the "beyond the grid" pair reads
+// E rows whose loads are in flight together per thread (4 loads each): 4 in the 512-thread CTAs, 2 in the 256-thread
+// CTAs that small problems use (fewer registers: four of those CTAs share an SM)
+__host__ __device__ constexpr int scan_unroll(int NT) { return NT <= 256 ? 2 : 4; }
 
 struct ScanLayout {                       // byte offsets into dynamic shared memory, identical on host and device
-    int ld, a_pad, n_yblk, split, part_stride, ng, seg;
-    size_t hs, part, tot, offs, tap_w, qv, tap_row, sel, a_star, end;
+    int ld, a_pad, n_yblk, split, part_stride, ng;
+    size_t hs, part, bsum, tap_w, qv, tap_row, sel, end;
 };
 
 __host__ __device__ inline size_t align32(size_t v) { return (v + 31) & ~(size_t)31; }
@@ -49,24 +62,22 @@ __host__ __device__ inline size_t align32(size_t v) { return (v + 31) & ~(size_t
 __host__ __device__ inline ScanLayout scan_layout(int G, int A, int bn, int NT)
 {
     ScanLayout L;
-    L.ld = bn + 2;                                        // one leading zero column (the "beyond the grid" pair reads it)
-    L.a_pad = (A + kTapPad + 3) & ~3;
+    L.ld = bn + kScanLead;
     L.n_yblk = (G + 31) / 32;
     const int warps = NT / 32;
     L.split = warps / L.n_yblk > 1 ? warps / L.n_yblk : 1;    // warps sharing one block of 32 nodes y
     L.part_stride = L.n_yblk * 32;
-    L.ng = NT / bn > 1 ? NT / bn : 1;                     // alpha segments (thread groups of bn columns)
-    L.seg = (A + L.ng - 1) / L.ng;
+    L.ng = NT / bn > 1 ? NT / bn : 1;                     // thread groups of bn columns sharing the alphas of a super-chunk
+    const int span = L.ng * scan_unroll(NT);
+    L.a_pad = ((A + span - 1) / span) * span;             // whole super-chunks (zero-weight rows behind A)
     size_t at = 0;
     L.hs = at;      at = align32(at + sizeof(double) * (size_t)A * L.ld);
     L.part = at;    at = align32(at + sizeof(double) * (size_t)L.split * L.part_stride);
-    L.tot = at;     at = align32(at + sizeof(double) * (size_t)L.ng * bn);
-    L.offs = at;    at = align32(at + sizeof(double) * (size_t)L.ng * bn);
+    L.bsum = at;    at = align32(at + sizeof(double) * 2 * (size_t)L.ng * bn);
     L.tap_w = at;   at = align32(at + sizeof(double) * 4 * (size_t)L.a_pad);
     L.qv = at;      at = align32(at + sizeof(double) * (size_t)L.a_pad);
     L.tap_row = at; at = align32(at + sizeof(int) * 4 * (size_t)L.a_pad);
     L.sel = at;     at = align32(at + sizeof(int2) * (size_t)L.a_pad);
-    L.a_star = at;  at = align32(at + sizeof(int) * (size_t)L.a_pad);
     L.end = at;
     return L;
 }
@@ -93,7 +104,7 @@ __device__ __forceinline__ double y_side_interval(const DevProblem& P, const dou
         const size_t at = (size_t)o * G + y;
         const int u = CACHED ? (int)u_cache[at] : (int)P.upper_t16[at];
         const double w = (CACHED && o < cached_w_rows) ? w_cache[at] : P.weight_t[at];
-        const double* hrow = Hs + beta * ld + 1 - q0;
+        const double* hrow = Hs + beta * ld + kScanLead - q0;
         if (MASKED) {
             const bool ok_a = (unsigned)(u - 1 - q0) < (unsigned)bn, ok_b = (unsigned)(u - q0) < (unsigned)bn;
             const double a = hrow[ok_a ? u - 1 : q0], b = hrow[ok_b ? u : q0];
@@ -106,10 +117,11 @@ __device__ __forceinline__ double y_side_interval(const DevProblem& P, const dou
 }
 
 // The work of one CTA: row `lx` of this rank, column chunk `chunk`.
-template <int NT>
+template <int kScanUnroll>
 __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, const int lx, const bool build_tables,
                                           const int cached_w_rows)
 {
+    const int NT = blockDim.x;                             // = ng * bn; scan_unroll(NT) == kScanUnroll
     const DevProblem& P = S.P;
     // no __restrict__ / read-only path on the state: inside the persistent kernel other CTAs rewrite C every step
     const double* C = S.C;
@@ -124,16 +136,15 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
     extern __shared__ __align__(32) unsigned char scan_smem[];
     double* Hs = reinterpret_cast<double*>(scan_smem + L.hs);            // [A][ld]
     double* part_y = reinterpret_cast<double*>(scan_smem + L.part);      // [split][n_yblk * 32]
-    double* tot = reinterpret_cast<double*>(scan_smem + L.tot);          // [ng][bn] running sum at the end of each segment
-    double* offs = reinterpret_cast<double*>(scan_smem + L.offs);        // [ng][bn] sum of the segments before
+    double* bsum = reinterpret_cast<double*>(scan_smem + L.bsum);        // [2][ng][bn] block sums of the current super-chunk
     double* tap_w = reinterpret_cast<double*>(scan_smem + L.tap_w);      // [a_pad][4] q[alpha] * weights of the four C rows feeding E[alpha]
     double* qv = reinterpret_cast<double*>(scan_smem + L.qv);            // [a_pad]
     int* tap_row = reinterpret_cast<int*>(scan_smem + L.tap_row);        // [a_pad][4] their offsets (slot * G)
     int2* sel = reinterpret_cast<int2*>(scan_smem + L.sel);              // [a_pad] rows beta closed by alpha
-    int* a_star = reinterpret_cast<int*>(scan_smem + L.a_star);          // [a_pad]
     unsigned short* u_cache = reinterpret_cast<unsigned short*>(scan_smem + L.end);                    // [n_off][G]
     double* w_cache = reinterpret_cast<double*>(scan_smem + align32(L.end + sizeof(unsigned short) * (size_t)n_off * G));
 
+    SCAN_MARK(0);
     if (build_tables) {
         if (cached_w_rows >= 0) {
             for (int i = tid; i < n_off * G; i += NT) u_cache[i] = P.upper_t16[i];
@@ -157,61 +168,78 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
         }
         for (int a = tid; a < L.a_pad; a += NT) {
             qv[a] = a < A ? P.qvec[a] : 0.0;
-            a_star[a] = a < A ? P.a_star[a] : -1;
             sel[a] = a < A ? P.beta_range[a] : make_int2(0, 0);
         }
-        for (int b = tid; b < A; b += NT) Hs[b * ld] = 0.0;              // the leading zero column (never written again)
+        for (int b = tid; b < A; b += NT) Hs[b * ld + kScanLead - 1] = 0.0;   // the zero column (never written again)
+        // empty rows of the table (a suffix: a_star never grows with beta) are never closed: zero them once
+        for (int i = P.scan_live_rows * ld + tid; i < A * ld; i += NT) Hs[i] = 0.0;
         __syncthreads();
     }
 
+    SCAN_MARK(1);
     // ---- E on the fly, running sum along alpha, H rows closed as their last in-disc column passes ----
-    const int col = tid % bn, grp = tid / bn;
-    const bool active = grp < L.ng;
-    if (active) {
-        const int a0 = grp * L.seg, a1 = min(A, a0 + L.seg);
+    // Threads = (column, group).  The alphas are walked in super-chunks of ng * kScanUnroll: group g takes kScanUnroll
+    // consecutive alphas of every super-chunk, the groups exchange their block sums through shared memory (one barrier per
+    // super-chunk, double buffered), so every thread knows the running sum in front of its block and the H rows it closes
+    // are final -- no second sweep over the tile.  A warp reads 32 consecutive columns of one C row per load (two
+    // 128-byte lines: the L1 wavefront count matters as much as the bytes).  This phase is bound by the L2 throughput of
+    // the whole chip -- 4 loads of C per element of E and no reuse, the moment grid being finer than the quadrature near
+    // the origin -- so the raw C values of the next super-chunk are requested before the barrier.
+    {
+        const int col = tid % bn, grp = tid / bn;
+        const bool active = grp < L.ng;
+        const int span = L.ng * kScanUnroll;
+        const int n_sc = L.a_pad / span;
         const int q = q0 + col;
         const bool live = q < G;
         const double* c = C + (live ? q : G - 1);
-        double* hcol = Hs + 1 + col;
-        double run = 0.0;
-        for (int a = a0; a < a1; a += kScanUnroll) {
-            double e[kScanUnroll];
+        double* hcol = Hs + kScanLead + col;
+        double base = 0.0;                                 // sum over all alphas of the super-chunks before (same in every group)
+        // the barrier of a super-chunk only joins the ng warps that share the same 32 columns (named barriers 1..bn/32):
+        // the column sets drift apart, so the loads of one set fly while another exchanges its block sums
+        const int set_id = 1 + col / 32, set_threads = L.ng * 32;
+        double raw[kScanUnroll][4];
+        auto issue = [&](int sc) {
             #pragma unroll
             for (int k = 0; k < kScanUnroll; k++) {
-                const int4 ra = *reinterpret_cast<const int4*>(tap_row + (a + k) * 4);
-                const double4 wa = *reinterpret_cast<const double4*>(tap_w + (a + k) * 4);
-                e[k] = (c[ra.x] * wa.x + c[ra.y] * wa.y) + (c[ra.z] * wa.z + c[ra.w] * wa.w);
+                const int4 ra = *reinterpret_cast<const int4*>(tap_row + (sc * span + grp * kScanUnroll + k) * 4);
+                raw[k][0] = c[ra.x]; raw[k][1] = c[ra.y]; raw[k][2] = c[ra.z]; raw[k][3] = c[ra.w];
             }
-            #pragma unroll
-            for (int k = 0; k < kScanUnroll; k++) {
-                if (a + k < a1) {
-                    run += e[k];
-                    const int2 rows = sel[a + k];
-                    for (int b = rows.x; b < rows.y; b++) hcol[b * ld] = live ? run * qv[b] : 0.0;
+        };
+        if (active) {
+            issue(0);
+            for (int sc = 0; sc < n_sc; sc++) {
+                double prefix[kScanUnroll];
+                double* mine = bsum + (sc & 1) * L.ng * bn;
+                double run = 0.0;
+                #pragma unroll
+                for (int k = 0; k < kScanUnroll; k++) {
+                    const double4 wa = *reinterpret_cast<const double4*>(tap_w + (sc * span + grp * kScanUnroll + k) * 4);
+                    run += (raw[k][0] * wa.x + raw[k][1] * wa.y) + (raw[k][2] * wa.z + raw[k][3] * wa.w);
+                    prefix[k] = run;
                 }
+                mine[grp * bn + col] = run;
+                if (sc + 1 < n_sc) issue(sc + 1);
+                asm volatile("bar.sync %0, %1;" ::"r"(set_id), "r"(set_threads) : "memory");
+                double before = 0.0, all = 0.0;
+                for (int g = 0; g < L.ng; g++) {             // fixed order
+                    const double v = mine[g * bn + col];
+                    if (g < grp) before += v;
+                    all += v;
+                }
+                const double start = base + before;
+                #pragma unroll
+                for (int k = 0; k < kScanUnroll; k++) {
+                    const int2 rows = sel[sc * span + grp * kScanUnroll + k];       // empty beyond A
+                    const double v = live ? start + prefix[k] : 0.0;
+                    for (int r = rows.x; r < rows.y; r++) hcol[r * ld] = v * qv[r];
+                }
+                base += all;
             }
         }
-        tot[grp * bn + col] = live ? run : 0.0;
     }
     __syncthreads();
-    if (active) {
-        double before = 0.0;
-        for (int g = 0; g < grp; g++) before += tot[g * bn + col];        // fixed order
-        offs[grp * bn + col] = before;
-    }
-    __syncthreads();
-    if (active) {
-        double* hcol = Hs + 1 + col;
-        for (int b = grp; b < A; b += L.ng) {
-            const int as = a_star[b];
-            if (as < 0) hcol[b * ld] = 0.0;                               // an empty row of the table
-            else {
-                const int g = as / L.seg;
-                if (g > 0) hcol[b * ld] += qv[b] * offs[g * bn + col];
-            }
-        }
-    }
-    __syncthreads();
+    SCAN_MARK(3);
 
     // ---- y side ----
     {
@@ -232,6 +260,7 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
             part_y[part * L.part_stride + yb * 32 + lane] = s;
         }
         __syncthreads();
+        SCAN_MARK(4);
         double* out = S.partial + ((size_t)chunk * local_rows(P) + lx) * G;
         for (int y = tid; y < G; y += NT) {
             double s = 0.0;
@@ -252,15 +281,18 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
         }
     }
     __syncthreads();       // shared memory is reused by the next row / step of this CTA
+    SCAN_MARK(5);
 }
 
-template <bool BATCH>
-__global__ void __launch_bounds__(kScanThreads)
+// SMALL: 256-thread CTAs capped at 64 registers (four per SM) for problems whose working set is small; otherwise 512
+// threads with the registers they want.
+template <bool BATCH, bool SMALL>
+__global__ void __launch_bounds__(SMALL ? 256 : kScanThreadsMax, SMALL ? 4 : 1)
 scan_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
 {
     const StepArgs& S = BATCH ? batch[blockIdx.z] : one;
     if (BATCH && ((int)blockIdx.x >= S.P.scan_chunks || (int)blockIdx.y >= local_rows(S.P))) return;   // batch grids are padded
-    scan_body<kScanThreads>(S, blockIdx.x, blockIdx.y, true, -1);
+    scan_body<scan_unroll(SMALL ? 256 : kScanThreadsMax)>(S, blockIdx.x, blockIdx.y, true, -1);
 }
 
 __device__ __forceinline__ double warp_sum(double v)
@@ -274,10 +306,11 @@ __device__ __forceinline__ double warp_sum(double v)
 // grids whose rows are one chunk each.  Per step: CTAs 0..G-1 run scan_body for their row while the spare CTAs apply the
 // sparse ring correction; grid barrier; every CTA closes its share of the nodes (closure, Euler update, clamp,
 // history); grid barrier.  The tap tables and the y-side tables stay in shared memory across steps.
-__global__ void __launch_bounds__(kScanThreads)
+template <bool SMALL>
+__global__ void __launch_bounds__(SMALL ? 256 : kScanThreadsMax)
 persistent_scan_kernel(const PersistentArgs A)
 {
-    constexpr int NT = kScanThreads;
+    const int NT = blockDim.x;
     cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     __shared__ double wc_shared;
     StepArgs S = A.step;
@@ -293,7 +326,7 @@ persistent_scan_kernel(const PersistentArgs A)
             A.observables[2 * point + 1] = S.C[(size_t)0 * G + (G - 1)];            // Values[k][G]       (Solver.cpp:1014)
         }
         if ((int)blockIdx.x < G) {
-            scan_body<NT>(S, 0, blockIdx.x, k == 0, A.cached_w_rows);
+            scan_body<scan_unroll(SMALL ? 256 : kScanThreadsMax)>(S, 0, blockIdx.x, k == 0, A.cached_w_rows);
         } else {
             const int warps = (gridDim.x - G) * (NT / 32);
             for (int row = (blockIdx.x - G) * (NT / 32) + tid / 32; row < P.n_ring; row += warps) {
@@ -303,7 +336,9 @@ persistent_scan_kernel(const PersistentArgs A)
                 if (tid % 32 == 0) S.ring[P.ring_point[row]] = acc;
             }
         }
+        SCAN_MARK(6);
         grid.sync();
+        SCAN_MARK(7);
         if (tid < 32) {
             const double v = wc_total(S.wc_rows, G, tid);
             if (tid == 0) wc_shared = v;
@@ -329,7 +364,9 @@ persistent_scan_kernel(const PersistentArgs A)
             if (values_next) values_next[1 + q] = v;
             if (derivs_here) derivs_here[1 + q] = dc;
         }
+        SCAN_MARK(8);
         grid.sync();
+        SCAN_MARK(9);
         parity ^= 1;
     }
 }
@@ -346,51 +383,80 @@ void configure_once(const void* kernel, bool& done)
 
 }  // namespace
 
-size_t scan_smem_bytes(int G, int A, int bn) { return scan_layout(G, A, bn, kScanThreads).end; }
+#ifdef LDM_PHASE_CLOCKS
+extern "C" int ldm_debug_scan_clocks(long long* out, int rows)
+{
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, g_scan_clock, sizeof(long long) * 12 * (size_t)rows);
+}
+#endif
+
+size_t scan_smem_bytes(int G, int A, int bn, int nt) { return scan_layout(G, A, bn, nt).end; }
+
+// Threads per CTA = ng * bn (ng groups of bn columns).  Small working sets (several CTAs fit one SM's shared memory)
+// take 256-thread CTAs, everything else 257..512 threads.
+int scan_pick_threads(int G, int A, int bn)
+{
+    if (bn <= 64 && scan_layout(G, A, bn, 256).end <= 48 * 1024 && std::getenv("LDM_SCAN_BIG_CTA") == nullptr) return (256 / bn) * bn;
+    return (kScanThreadsMax / bn) * bn;                    // bn = 32, 64, 96, 128 -> 512, 512, 480, 512
+}
 
 int scan_pick_bn(int G, int A)
 {
+    auto fits = [&](int bn) { return scan_smem_bytes(G, A, bn, scan_pick_threads(G, A, bn)) <= kSmemBudget; };
     if (const char* env = std::getenv("LDM_SCAN_BN")) {
         const int v = std::atoi(env);
-        if (v >= 32 && v <= kScanThreads && v % 32 == 0 && scan_smem_bytes(G, A, v) <= kSmemBudget) return v;
+        if (v >= 32 && v <= 128 && v % 32 == 0 && fits(v)) return v;
     }
     // widest chunk (a multiple of 32, at most 128 columns) whose H tile fits; then the evenest split of the row
     int bn = 128;
-    while (bn > 32 && scan_smem_bytes(G, A, bn) > kSmemBudget) bn -= 32;
-    if (scan_smem_bytes(G, A, bn) > kSmemBudget) return 0;       // table too tall for one CTA: dense contraction instead
+    while (bn > 32 && !fits(bn)) bn -= 32;
+    if (!fits(bn)) return 0;                                     // table too tall for one CTA: dense contraction instead
     const int chunks = (G + bn - 1) / bn;
     const int even = (((G + chunks - 1) / chunks) + 31) & ~31;
     return even < bn ? even : bn;
 }
 
+template <bool BATCH, bool SMALL>
+static void launch_scan_shape(const StepArgs* one, const StepArgs* d_batch, dim3 grid, int nt, size_t smem, cudaStream_t stream)
+{
+    static bool configured[64] = {};
+    int device = 0;
+    cudaGetDevice(&device);
+    configure_once((const void*)scan_kernel<BATCH, SMALL>, configured[device & 63]);
+    static const StepArgs none{};
+    scan_kernel<BATCH, SMALL><<<grid, nt, smem, stream>>>(one ? *one : none, d_batch);
+}
+
+template <bool BATCH>
+static void launch_scan_variant(const StepArgs* one, const StepArgs* d_batch, dim3 grid, int nt, size_t smem, cudaStream_t stream)
+{
+    if (nt <= 256) launch_scan_shape<BATCH, true>(one, d_batch, grid, nt, smem, stream);
+    else launch_scan_shape<BATCH, false>(one, d_batch, grid, nt, smem, stream);
+}
+
 void launch_scan(const StepArgs& one, cudaStream_t stream)
 {
-    static bool configured[64] = {};
-    int device = 0;
-    cudaGetDevice(&device);
-    configure_once((const void*)scan_kernel<false>, configured[device & 63]);
     const DevProblem& P = one.P;
-    const size_t smem = scan_smem_bytes(P.G, P.A, P.scan_bn);
-    scan_kernel<false><<<dim3(P.scan_chunks, local_rows(P), 1), kScanThreads, smem, stream>>>(one, nullptr);
+    launch_scan_variant<false>(&one, nullptr, dim3(P.scan_chunks, local_rows(P), 1), P.scan_nt,
+                               scan_smem_bytes(P.G, P.A, P.scan_bn, P.scan_nt), stream);
 }
 
-void launch_scan_batch(const StepArgs* d_batch, int n, int max_chunks, int max_rows, size_t max_smem, cudaStream_t stream)
+// every member of a batch launch shares the CTA shape nt (= ng * bn); shared memory is sized for the largest member
+void launch_scan_batch(const StepArgs* d_batch, int n, int nt, int max_chunks, int max_rows, size_t max_smem, cudaStream_t stream)
 {
-    static bool configured[64] = {};
-    int device = 0;
-    cudaGetDevice(&device);
-    configure_once((const void*)scan_kernel<true>, configured[device & 63]);
-    static const StepArgs none{};
-    scan_kernel<true><<<dim3(max_chunks, max_rows, n), kScanThreads, max_smem, stream>>>(none, d_batch);
+    launch_scan_variant<true>(nullptr, d_batch, dim3(max_chunks, max_rows, n), nt, max_smem, stream);
 }
 
+// the same CTA shape as the one-launch-per-step kernel of this problem: the summation order follows the shape, and the
+// persistent, per-step, batched and sharded paths of one handle must agree bit for bit
 cudaError_t launch_persistent_scan(const PersistentArgs& args, int grid, cudaStream_t stream, int* max_grid)
 {
-    const void* kernel = (const void*)persistent_scan_kernel;
     const DevProblem& P = args.step.P;
-    const int G = P.G, n_off = P.n_off;
+    const int G = P.G, n_off = P.n_off, nt = P.scan_nt;
+    const void* kernel = nt <= 256 ? (const void*)persistent_scan_kernel<true> : (const void*)persistent_scan_kernel<false>;
     // shared memory: the step's working set, then the 16-bit y-side index table, then as many weight rows as still fit
-    const size_t base = scan_smem_bytes(G, P.A, P.scan_bn);
+    const size_t base = scan_smem_bytes(G, P.A, P.scan_bn, nt);
     const size_t u_bytes = align32(sizeof(unsigned short) * (size_t)n_off * G);
     PersistentArgs with_cache = args;
     with_cache.cached_w_rows = -1;
@@ -405,13 +471,14 @@ cudaError_t launch_persistent_scan(const PersistentArgs& args, int grid, cudaStr
     int device = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&device);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_scan_kernel, kScanThreads, smem);
+    e = nt <= 256 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_scan_kernel<true>, nt, smem)
+                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_scan_kernel<false>, nt, smem);
     if (e != cudaSuccess) return e;
     if (max_grid) *max_grid = sms * per_sm;
     if (grid <= 0) return cudaSuccess;                  // query only
     if (grid > sms * per_sm) return cudaErrorCooperativeLaunchTooLarge;
     void* params[] = {&with_cache};
-    return cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(kScanThreads), params, smem, stream);
+    return cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(nt), params, smem, stream);
 }
 
 }  // namespace ldm

@@ -1,0 +1,46 @@
+#!/usr/bin/env python
+"""Phase timeline of the prefix-sum kernels (debug build: make -C euler-_solver_-openmp-_b200 phase-clocks).
+Prints, averaged over the CTAs of the last step / launch, the SM-clock cycles spent between the phase marks.
+    python tools/scan_clocks.py [G] [sigma_w sigma_m]"""
+import ctypes as C
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+os.environ.setdefault("LDM_LIBRARY", os.path.join(ROOT, "euler-_solver_-openmp-_b200", "libldm_b200_phase.so"))
+from __graft_entry__ import load_package  # noqa: E402
+
+ldm = load_package()
+G = int(sys.argv[1]) if len(sys.argv) > 1 else 128
+sw, sm = (float(sys.argv[2]), float(sys.argv[3])) if len(sys.argv) > 3 else (0.15, 0.15)
+props = ldm.Properties.Generate(1, sw, sm, 0.4, 0.2, 0.001, G)
+eq = ldm.Equation(props)
+st = eq.GenerateEquilibriumValuesForNAndC(200)
+eq.upload(st)
+eq.advance(20, 0.1)
+eq.synchronize()
+print(f"G={G} A={(props.MaxNumForM - 1) // 2}: {eq.last_elapsed_ms() / 20 * 1e3:.1f} us per step over 20 steps")
+rows = 148 * 8
+buf = np.zeros((rows, 12), dtype=np.int64)
+lib = ldm.library()
+lib.ldm_debug_scan_clocks.argtypes = [C.c_void_p, C.c_int]
+assert lib.ldm_debug_scan_clocks(buf.ctypes.data, rows) == 0
+names = ["tables (first step only)", "E + running sum + select", "(unused)", "y side", "write-out", "WC rows",
+         "(to barrier 1)", "barrier 1", "closing phase", "barrier 2"]
+body = buf[buf[:, 1] > 0]
+print(f"{len(body)} CTAs ran the row body; body total {np.mean(body[:, 5] - body[:, 0]):.0f} cycles (max {np.max(body[:, 5] - body[:, 0])})")
+body[:, 2] = body[:, 3]
+for i, n in enumerate(names[:5]):
+    col = body[:, i + 1] - body[:, i] if i != 1 else body[:, 3] - body[:, 1]
+    print(f"  {n:28s} mean {col.mean():9.0f}  max {col.max():9.0f} cycles")
+pers = buf[buf[:, 9] > 0]
+if len(pers):
+    rowc = pers[pers[:, 1] > 0]
+    print(f"persistent kernel, {len(pers)} CTAs ({len(rowc)} row CTAs), last step:")
+    for i, n in zip(range(5, 9), names[6:]):
+        col = rowc[:, i + 1] - rowc[:, i]
+        print(f"  {n:28s} mean {col.mean():9.0f}  max {col.max():9.0f} cycles (row CTAs)")
+    print(f"  step (row CTAs, mark 0 -> 9)  mean {np.mean(rowc[:, 9] - rowc[:, 0]):9.0f} cycles")
