@@ -59,6 +59,8 @@ struct ldm_context {
     double* d_partial = nullptr;           // [tiles][P] factored path: per beta-tile sums
     double* d_ring = nullptr;              // [P] factored path: samples between the cutoff circle and the square edge
     double* d_wc_rows = nullptr;           // [G] factored path: per-row dot products of the WC operator (3-kernel path)
+    double* d_wc_rows2 = nullptr;          // [2][G] the same inside the prefix-sum persistent kernel (ping-pong with the state)
+    unsigned int* d_barrier = nullptr;     // [1 + G] arrival counter of that kernel's grid barrier, then its per-row ring counts
     // fused update + all-gather (ldm_shard_peer_*)
     double* peer_own[2] = {nullptr, nullptr};                 // this rank's two replicas of C (gathered layout)
     unsigned long long* peer_own_flags = nullptr;             // [world] last step published by every rank
@@ -145,6 +147,19 @@ void ensure_ring_operator(ldm_context* c)
     d.ring_point = up(op.point);
     d.ring_begin = up(op.row_begin);
     d.ring_row_begin = up(op.grid_row_begin);
+    {   // the CSR rows in contiguous shares of about equal entry count, one share per local grid row (= CTA of the persistent kernel)
+        const int shares = (int)op.grid_row_begin.size() - 1, rows = (int)op.point.size();
+        const long long total = (long long)op.node.size();
+        std::vector<int> cut((size_t)shares + 1, rows);
+        cut[0] = 0;
+        int row = 0;
+        for (int s = 1; s < shares; s++) {
+            const long long want = total * s / shares;
+            while (row < rows && op.row_begin[(size_t)row] < want) row++;
+            cut[(size_t)s] = row;
+        }
+        d.ring_cta_begin = up(cut);
+    }
     d.ring_node = up(op.node);
     d.ring_weight = up(op.weight);
     LDM_CUDA(cudaMemset(c->d_ring, 0, c->P() * sizeof(double)));
@@ -274,7 +289,7 @@ bool persistent_possible(ldm_context* c)
         c->persistent_grid = (e == cudaSuccess && max_grid > 0) ? max_grid : -1;
         if (e != cudaSuccess) cudaGetLastError();
     }
-    return c->persistent_grid >= c->dev.G + 1;
+    return c->persistent_grid >= c->dev.G + (p.scan ? 0 : 1);
 }
 
 // n_steps Euler steps from the resident state; history pointers (device) may be NULL.
@@ -291,12 +306,18 @@ void advance_persistent(ldm_context* c, int n_steps, double dt, long long first_
     args.first_point = first_point;
     args.stride = (long long)(1 + c->P());
     args.observables = d_obs; args.values = d_values; args.derivs = d_derivs;
+    args.wc_rows = c->d_wc_rows2; args.barrier = c->d_barrier; args.ring_done = c->d_barrier + 1;
     int device = 0, sms = 0;
     cudaGetDevice(&device);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    const int grid = std::min(c->persistent_grid, std::max(sms, c->dev.G + 1));
-    if (c->plan.scan) LDM_CUDA(ldm::launch_persistent_scan(args, grid, c->stream, nullptr));
-    else LDM_CUDA(ldm::launch_persistent(c->plan, args, grid, c->stream, nullptr));
+    if (c->plan.scan) {
+        // one CTA per moment-grid row, each closing its own row: no spare CTAs, one grid barrier per step
+        LDM_CUDA(cudaMemsetAsync(c->d_barrier, 0, (1 + (size_t)c->dev.G) * sizeof(unsigned int), c->stream));
+        LDM_CUDA(ldm::launch_persistent_scan(args, c->dev.G, c->stream, nullptr));
+    } else {
+        const int grid = std::min(c->persistent_grid, std::max(sms, c->dev.G + 1));
+        LDM_CUDA(ldm::launch_persistent(c->plan, args, grid, c->stream, nullptr));
+    }
     c->launches += 1;
     c->cur ^= (n_steps & 1);
 }
@@ -585,6 +606,8 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         c->d_partial = c->alloc<double>(P * (size_t)std::max(c->plan_dense.slabs(), c->scan_available ? c->plan_scan.slabs() : 1));
         c->d_ring = c->alloc<double>(P);
         c->d_wc_rows = c->alloc<double>((size_t)d.G);
+        c->d_wc_rows2 = c->alloc<double>(2 * (size_t)d.G);
+        c->d_barrier = c->alloc<unsigned int>(1 + (size_t)d.G);
         if (const char* env = std::getenv("LDM_PERSISTENT")) c->persistent_enabled = std::atoi(env) != 0;
         d.n_ring = 0;
         LDM_CUDA(cudaMemsetAsync(c->d_C[0], 0, P * sizeof(double), c->stream));

@@ -50,6 +50,7 @@ struct DevProblem {
     const int* ring_point;     // [n_ring] local_row * G + y
     const int* ring_begin;     // [n_ring + 1]
     const int* ring_row_begin; // [local_rows + 1] first CSR row of each local moment-grid row
+    const int* ring_cta_begin; // [local_rows + 1] the CSR rows dealt out evenly by entry count over local_rows CTAs (persistent kernel)
     const int* ring_node;      // C index (gathered layout)
     const double* ring_weight;
 };
@@ -141,6 +142,11 @@ struct PersistentArgs {
     double* values;            // may be NULL: [points][stride]
     double* derivs;            // may be NULL: [points][stride]
     int cached_w_rows;         // set by the launcher: offsets whose y-side weights stay in shared memory (-1: no cache)
+    // prefix-sum persistent kernel: [2][G] row dots of the WC functional (ping-pong with the state) and the arrival
+    // counter of its grid barrier (zeroed before every launch)
+    double* wc_rows;
+    unsigned int* barrier;
+    unsigned int* ring_done;   // [G] finished CSR rows of the ring correction per grid row, monotone over the launch (zeroed before)
 };
 
 struct FactoredPlan {

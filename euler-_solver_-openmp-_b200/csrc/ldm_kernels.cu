@@ -166,7 +166,7 @@ ring_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
     const int lane = threadIdx.x & 31;
     const int begin = P.ring_begin[row], end = P.ring_begin[row + 1];
     double acc = 0.0;
-    for (int e = begin + lane; e < end; e += kWarp) acc += P.ring_weight[e] * C[P.ring_node[e]];
+    for (int e = begin + lane; e < end; e += kWarp) acc = fma(P.ring_weight[e], C[P.ring_node[e]], acc);
     acc = warp_sum(acc);
     if (lane == 0) ring[P.ring_point[row]] = acc;
 }

@@ -27,8 +27,6 @@
 #include <algorithm>
 #include <cstdlib>
 
-#include <cooperative_groups.h>
-
 #include "ldm_device.h"
 #include "ldm_pointwise.cuh"
 
@@ -54,7 +52,7 @@ __host__ __device__ constexpr int scan_unroll(int NT) { return NT <= 256 ? 2 : 4
 
 struct ScanLayout {                       // byte offsets into dynamic shared memory, identical on host and device
     int ld, a_pad, n_yblk, split, part_stride, ng;
-    size_t hs, part, bsum, tap_w, qv, tap_row, sel, end;
+    size_t hs, part, rowbuf, bsum, tap_w, qv, tap_row, sel, end;
 };
 
 __host__ __device__ inline size_t align32(size_t v) { return (v + 31) & ~(size_t)31; }
@@ -73,6 +71,7 @@ __host__ __device__ inline ScanLayout scan_layout(int G, int A, int bn, int NT)
     size_t at = 0;
     L.hs = at;      at = align32(at + sizeof(double) * (size_t)A * L.ld);
     L.part = at;    at = align32(at + sizeof(double) * (size_t)L.split * L.part_stride);
+    L.rowbuf = at;  at = align32(at + sizeof(double) * 2 * (size_t)L.part_stride);   // persistent kernel: the new row of C, the row of the WC functional
     L.bsum = at;    at = align32(at + sizeof(double) * 2 * (size_t)L.ng * bn);
     L.tap_w = at;   at = align32(at + sizeof(double) * 4 * (size_t)L.a_pad);
     L.qv = at;      at = align32(at + sizeof(double) * (size_t)L.a_pad);
@@ -80,6 +79,29 @@ __host__ __device__ inline ScanLayout scan_layout(int G, int A, int bn, int NT)
     L.sel = at;     at = align32(at + sizeof(int2) * (size_t)L.a_pad);
     L.end = at;
     return L;
+}
+
+__device__ __forceinline__ double warp_sum(double v)
+{
+    #pragma unroll
+    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);   // fixed butterfly
+    return v;
+}
+
+// One CSR row of the ring correction (ldm_model.h RingOperator) by one warp: lanes stride the entries, four gathers in
+// flight, accumulation in entry order with explicit fma -- the same bits as ring_kernel (ldm_kernels.cu).
+__device__ __forceinline__ double ring_row_dot(const DevProblem& P, const double* C, int row, int lane)
+{
+    const int end = P.ring_begin[row + 1];
+    int en = P.ring_begin[row] + lane;
+    double acc = 0.0;
+    for (; en + 96 < end; en += 128) {
+        const double w0 = P.ring_weight[en], w1 = P.ring_weight[en + 32], w2 = P.ring_weight[en + 64], w3 = P.ring_weight[en + 96];
+        const double c0 = C[P.ring_node[en]], c1 = C[P.ring_node[en + 32]], c2 = C[P.ring_node[en + 64]], c3 = C[P.ring_node[en + 96]];
+        acc = fma(w0, c0, acc); acc = fma(w1, c1, acc); acc = fma(w2, c2, acc); acc = fma(w3, c3, acc);
+    }
+    for (; en < end; en += 32) acc = fma(P.ring_weight[en], C[P.ring_node[en]], acc);
+    return warp_sum(acc);
 }
 
 // offsets sharing kernel node alpha: (A-1-alpha, A+alpha) for an odd extent, the single offset 0 for m == 2
@@ -117,9 +139,15 @@ __device__ __forceinline__ double y_side_interval(const DevProblem& P, const dou
 }
 
 // The work of one CTA: row `lx` of this rank, column chunk `chunk`.
-template <int kScanUnroll>
+// fused (persistent kernel): the per-node sums stay in shared memory (first G doubles of the part_y region) for the
+// closing phase of the same CTA, nothing is written to global memory and the WC rows are left to the caller.
+// `mid` runs between the two phases (the persistent kernel requests there what its closing phase will need, so that
+// those loads fly under the y side).
+struct NoMid { __device__ void operator()() const {} };
+
+template <int kScanUnroll, typename Mid = NoMid>
 __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, const int lx, const bool build_tables,
-                                          const int cached_w_rows)
+                                          const int cached_w_rows, const bool fused = false, Mid mid = Mid())
 {
     const int NT = blockDim.x;                             // = ng * bn; scan_unroll(NT) == kScanUnroll
     const DevProblem& P = S.P;
@@ -240,6 +268,7 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
     }
     __syncthreads();
     SCAN_MARK(3);
+    mid();
 
     // ---- y side ----
     {
@@ -265,13 +294,14 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
         for (int y = tid; y < G; y += NT) {
             double s = 0.0;
             for (int part = 0; part < L.split; part++) s += part_y[part * L.part_stride + y];     // fixed order
-            out[y] = s;
+            if (fused) part_y[y] = s;                   // only this thread touches column y
+            else out[y] = s;
         }
     }
 
     // WC = <wc_operator, C> (Solver.cpp:265-274) row by row, folded into this launch.  Every rank reduces the FULL
     // operator (no all-reduce needed): the first-chunk CTAs of this rank share all G rows round-robin.
-    if (chunk == 0 && S.wc_rows != nullptr) {
+    if (chunk == 0 && S.wc_rows != nullptr && !fused) {
         const int n_local = local_rows(P);
         int slot = 0;
         for (int xr = lx; xr < G; xr += n_local, slot++) {
@@ -295,77 +325,145 @@ scan_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
     scan_body<scan_unroll(SMALL ? 256 : kScanThreadsMax)>(S, blockIdx.x, blockIdx.y, true, -1);
 }
 
-__device__ __forceinline__ double warp_sum(double v)
+// Spin until *counter >= target: relaxed polls (an acquire load in the loop would pay for its fence on every poll), then
+// ONE acquire load orders everything that follows behind the writers' releases (measured: cheaper than a fence here).
+__device__ __forceinline__ void wait_for_count(const unsigned int* counter, unsigned int target)
 {
-    #pragma unroll
-    for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);   // fixed butterfly
-    return v;
+    unsigned int seen;
+    do {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
+    } while (seen < target);
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
 }
 
-// Persistent multi-step kernel (cooperative launch, one CTA per SM): all Euler steps of a solve inside one launch, for
-// grids whose rows are one chunk each.  Per step: CTAs 0..G-1 run scan_body for their row while the spare CTAs apply the
-// sparse ring correction; grid barrier; every CTA closes its share of the nodes (closure, Euler update, clamp,
-// history); grid barrier.  The tap tables and the y-side tables stay in shared memory across steps.
+// Grid-wide barrier of the persistent kernel: a monotone arrival counter in global memory (zeroed before the launch; the
+// cooperative launch guarantees that every CTA is resident).  After the CTA barrier thread 0 arrives with a releasing
+// reduction (cumulative over the CTA's writes, and nothing waits for a returned value) and polls until all CTAs of
+// barrier number `index` have arrived.
+__device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int index)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
+        wait_for_count(counter, (index + 1u) * gridDim.x);
+    }
+    __syncthreads();
+}
+
+// Persistent multi-step kernel (cooperative launch, one CTA per moment-grid row): all Euler steps of a solve inside one
+// launch, for grids whose rows are one chunk each.  Per step every CTA
+//   1. sums the G row dots of the WC functional (written by the closing phases of the step before),
+//   2. computes its share of the sparse ring correction (dealt out evenly over all CTAs, counted per grid row), then runs
+//      scan_body for its row (per-node sums stay in shared memory),
+//   3. closes its own row -- closure, Euler update, clamp, history -- and forms its row dot of WC for the NEXT state,
+// and ONE grid barrier ends the step.  Tap tables and the y-side tables stay in shared memory across steps.
 template <bool SMALL>
 __global__ void __launch_bounds__(SMALL ? 256 : kScanThreadsMax)
 persistent_scan_kernel(const PersistentArgs A)
 {
     const int NT = blockDim.x;
-    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
     __shared__ double wc_shared;
     StepArgs S = A.step;
     const DevProblem& P = S.P;
-    const int G = P.G, n = G * G, tid = threadIdx.x;
+    const int G = P.G, tid = threadIdx.x, x = blockIdx.x;          // one rank, natural layout: row x = CTA x
+    const ScanLayout L = scan_layout(G, P.A, P.scan_bn, NT);
+    extern __shared__ __align__(32) unsigned char scan_smem[];
+    double* row_sum = reinterpret_cast<double*>(scan_smem + L.part);              // [G] after scan_body(fused)
     int parity = A.parity;
+    unsigned int barrier_index = 0;
+
+    // prologue: the row dots of WC for the initial state
+    if (tid < 32) {
+        const double s = wc_row_dot(P.wc_operator + (size_t)x * G, A.C[parity] + (size_t)x * G, G, tid);
+        if (tid == 0) A.wc_rows[parity * G + x] = s;
+    }
+    grid_barrier(A.barrier, barrier_index++);
+
+    double* c_new = reinterpret_cast<double*>(scan_smem + L.rowbuf);              // [G] this row at the new time
+    double* op_row = c_new + L.part_stride;                                        // [G] this row of the WC functional
+    for (int y = tid; y < G; y += NT) op_row[y] = P.wc_operator[(size_t)x * G + y];
+    const int warp = tid >> 5, lane = tid & 31, last_warp = NT / 32 - 1;
+    const bool closer = tid < G;                                                   // thread y closes node (x, y); G <= bn <= NT
+    const int q = x * G + (closer ? tid : 0);
+    const unsigned int ring_rows = (unsigned int)(P.ring_row_begin[x + 1] - P.ring_row_begin[x]);
+    const double ow = P.out_weight[q], mn = P.m_nodes[q], wn = P.w_nodes[q];      // time-invariant: registers for the whole launch
+
     for (int k = 0; k < A.n_steps; k++) {
+        SCAN_MARK(0);
         S.C = A.C[parity]; S.C_next = A.C[parity ^ 1];
         S.N_cur = A.N + parity; S.N_next = A.N + (parity ^ 1);
         const long long point = A.first_point + k;                 // index of the state this step starts from
-        if (blockIdx.x == 0 && tid == 0 && A.observables) {
+        if (x == 0 && tid == 0 && A.observables) {
             A.observables[2 * point] = S.N_cur[0];                                  // Values[k][0]       (Solver.cpp:1011)
             A.observables[2 * point + 1] = S.C[(size_t)0 * G + (G - 1)];            // Values[k][G]       (Solver.cpp:1014)
         }
-        if ((int)blockIdx.x < G) {
-            scan_body<scan_unroll(SMALL ? 256 : kScanThreadsMax)>(S, 0, blockIdx.x, k == 0, A.cached_w_rows);
-        } else {
-            const int warps = (gridDim.x - G) * (NT / 32);
-            for (int row = (blockIdx.x - G) * (NT / 32) + tid / 32; row < P.n_ring; row += warps) {
-                double acc = 0.0;
-                for (int en = P.ring_begin[row] + tid % 32; en < P.ring_begin[row + 1]; en += 32) acc += P.ring_weight[en] * S.C[P.ring_node[en]];
-                acc = warp_sum(acc);
-                if (tid % 32 == 0) S.ring[P.ring_point[row]] = acc;
+        // This CTA's share of the ring correction.  The far rows of the grid own almost all ring entries (row G-1 alone
+        // an eighth of them), so the CSR rows are dealt out evenly by entry count over ALL CTAs, whichever grid row they
+        // belong to; results go to global memory and every finished CSR row is counted on its grid row.
+        for (int row = P.ring_cta_begin[x] + warp; row < P.ring_cta_begin[x + 1]; row += NT / 32) {
+            const double acc = ring_row_dot(P, S.C, row, lane);
+            if (lane == 0) {
+                const int point_of_row = P.ring_point[row];
+                S.ring[point_of_row] = acc;
+                asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(A.ring_done + point_of_row / G), "r"(1u) : "memory");
             }
         }
+        // Everything the closing phase reads from global memory is requested between the two phases of scan_body and
+        // lands while the y side runs: the old C of this row, its ring correction (the owner first checks that all
+        // CSR rows of its grid row have been counted -- a whole E phase after they were dealt out, so no real wait),
+        // N, and the G row dots of the WC functional (written by the closing phases of the step before).
+        double c_old = 0.0, ring_v = 0.0, N = 0.0, wc_part[4] = {0.0, 0.0, 0.0, 0.0};
+        const double* wc_rows_now = A.wc_rows + parity * G;
+        auto mid = [&]() {
+            if (closer) {
+                if (ring_rows) {
+                    wait_for_count(A.ring_done + x, (unsigned int)(k + 1) * ring_rows);
+                    ring_v = __ldcg(S.ring + q);
+                }
+                c_old = S.C[q];
+            }
+            N = S.N_cur[0];
+            if (warp == last_warp) {
+                #pragma unroll
+                for (int j = 0; j < 4; j++) wc_part[j] = lane + 32 * j < G ? wc_rows_now[lane + 32 * j] : 0.0;
+            }
+        };
+        scan_body<scan_unroll(SMALL ? 256 : kScanThreadsMax)>(S, 0, x, k == 0, A.cached_w_rows, true, mid);   // ends with a CTA barrier
         SCAN_MARK(6);
-        grid.sync();
-        SCAN_MARK(7);
-        if (tid < 32) {
-            const double v = wc_total(S.wc_rows, G, tid);
-            if (tid == 0) wc_shared = v;
+        if (warp == last_warp) {                                   // wc_total(): the same order, from the registers
+            double t = 0.0;
+            #pragma unroll
+            for (int j = 0; j < 4; j++) if (lane + 32 * j < G) t += wc_part[j];
+            t = warp_sum(t);
+            if (lane == 0) wc_shared = t;
         }
         __syncthreads();
-        const double N = S.N_cur[0];
         const double WC = (wc_shared + (N * N) * P.wc_outside) * P.hh;             // Solver.cpp:311, 314
         double* values_next = A.values ? A.values + (point + 1) * A.stride : nullptr;
         double* derivs_here = A.derivs ? A.derivs + point * A.stride : nullptr;
-        if (blockIdx.x == 0 && tid == 0) {
+        if (x == 0 && tid == 0) {
             first_moment_update(P, N, WC, S.dt, S.scalars, S.N_next);
             if (values_next) values_next[0] = S.N_next[0];
             if (derivs_here) derivs_here[0] = S.scalars[1];
         }
-        for (int q = blockIdx.x * NT + tid; q < n; q += gridDim.x * NT) {
-            const double inside = S.partial[q] - S.ring[q];
-            const double c = S.C[q];
-            const double mc = (inside + (N * N) * P.out_weight[q]) * P.hh;
-            const double dc = second_moment_rhs(P, mc, c, N, WC, P.m_nodes[q], P.w_nodes[q]);
-            double v = __dadd_rn(c, __dmul_rn(dc, S.dt));                          // Solver.cpp:577
+        if (closer) {
+            const double inside = (0.0 + row_sum[tid]) - ring_v;
+            const double mc = (inside + (N * N) * ow) * P.hh;
+            const double dc = second_moment_rhs(P, mc, c_old, N, WC, mn, wn);
+            double v = __dadd_rn(c_old, __dmul_rn(dc, S.dt));                      // Solver.cpp:577
             v = v < 0.0 ? 0.0 : v;                                                 // Solver.cpp:578-580
             S.C_next[q] = v;
+            c_new[tid] = v;
             if (values_next) values_next[1 + q] = v;
             if (derivs_here) derivs_here[1 + q] = dc;
         }
+        __syncthreads();
+        if (warp == 0) {     // this row's dot of the WC functional for the next state
+            const double s = wc_row_dot(op_row, c_new, G, lane);
+            if (lane == 0) A.wc_rows[(parity ^ 1) * G + x] = s;
+        }
         SCAN_MARK(8);
-        grid.sync();
+        grid_barrier(A.barrier, barrier_index++);
         SCAN_MARK(9);
         parity ^= 1;
     }
@@ -397,7 +495,11 @@ size_t scan_smem_bytes(int G, int A, int bn, int nt) { return scan_layout(G, A, 
 // take 256-thread CTAs, everything else 257..512 threads.
 int scan_pick_threads(int G, int A, int bn)
 {
-    if (bn <= 64 && scan_layout(G, A, bn, 256).end <= 48 * 1024 && std::getenv("LDM_SCAN_BIG_CTA") == nullptr) return (256 / bn) * bn;
+    if (const char* env = std::getenv("LDM_SCAN_NT")) {          // tuning only
+        const int v = std::atoi(env);
+        if ((v == 256 || v == 512) && v >= bn) return (v / bn) * bn;
+    }
+    if (bn <= 64 && scan_layout(G, A, bn, 256).end <= 48 * 1024) return (256 / bn) * bn;
     return (kScanThreadsMax / bn) * bn;                    // bn = 32, 64, 96, 128 -> 512, 512, 480, 512
 }
 

@@ -36,11 +36,10 @@ body[:, 2] = body[:, 3]
 for i, n in enumerate(names[:5]):
     col = body[:, i + 1] - body[:, i] if i != 1 else body[:, 3] - body[:, 1]
     print(f"  {n:28s} mean {col.mean():9.0f}  max {col.max():9.0f} cycles")
-pers = buf[buf[:, 9] > 0]
+pers = buf[(buf[:, 9] > 0) & (buf[:, 1] > 0)]
 if len(pers):
-    rowc = pers[pers[:, 1] > 0]
-    print(f"persistent kernel, {len(pers)} CTAs ({len(rowc)} row CTAs), last step:")
-    for i, n in zip(range(5, 9), names[6:]):
-        col = rowc[:, i + 1] - rowc[:, i]
-        print(f"  {n:28s} mean {col.mean():9.0f}  max {col.max():9.0f} cycles (row CTAs)")
-    print(f"  step (row CTAs, mark 0 -> 9)  mean {np.mean(rowc[:, 9] - rowc[:, 0]):9.0f} cycles")
+    print(f"persistent kernel, {len(pers)} row CTAs, last step:")
+    for n, (i, j) in {"ring correction of the row": (5, 6), "closing of the row + WC row": (6, 8), "grid barrier": (8, 9)}.items():
+        col = pers[:, j] - pers[:, i]
+        print(f"  {n:28s} mean {col.mean():9.0f}  max {col.max():9.0f} cycles")
+    print(f"  step (mark 0 -> 9)            mean {np.mean(pers[:, 9] - pers[:, 0]):9.0f} cycles")
