@@ -62,11 +62,13 @@ def algorithmic_flop_per_step(props):
     return 11.0 * (P * s_nz + nz_w) + 20.0 * P, s_nz
 
 
-def executed_flop_per_step(props):
-    """FP64 operations the factored path actually issues per step (not the 11-FLOP-per-sample model): the padded dense
-    contraction on the tensor cores, the generation of E (7 per element and beta tile), the y-side contraction (6 per tap
-    pair), the closing kernel (~30 per node)."""
+def executed_flop_per_step(props, prefix):
+    """FP64 operations actually issued per step (not the 11-FLOP-per-sample model).  Prefix-sum path: the generation of E
+    (7 per element) with its running sum and the scaling of the closed H rows (2), the y side (6 per tap pair), the closing
+    phase (~30 per node).  Dense path: the same with the padded contraction on the tensor cores instead of the running sum."""
     G, A = props.G, (props.MaxNumForM - 1) // 2 if props.MaxNumForM > 2 else 1
+    if prefix:
+        return 9.0 * G * A * G + 6.0 * G * G * 2 * A + 30.0 * G * G
     bm = 40 if A <= 40 else 80
     bn = 64 if G <= 64 else 128
     tiles, chunks = -(-A // bm), -(-G // bn)
@@ -75,6 +77,14 @@ def executed_flop_per_step(props):
     e_gen = 7.0 * G * tiles * k_pad * (chunks * bn)
     y_side = 6.0 * G * chunks * G * 2 * A
     return gemm + e_gen + y_side + 30.0 * G * G
+
+
+def l2_bytes_per_step(props):
+    """Bytes the prefix-sum path pulls from L2 per step (its binding resource in the E phase): four C values per element
+    of E (no reuse: near the origin the moment grid is finer than the quadrature) -- y-side tables are resident in shared
+    memory in the persistent kernel."""
+    G, A = props.G, (props.MaxNumForM - 1) // 2 if props.MaxNumForM > 2 else 1
+    return 32.0 * G * A * G
 
 
 def measured_traffic(workload):
@@ -377,7 +387,8 @@ def main():
     P = props.G * props.G
     state0 = seeded_state(props.MomentsGrid, sm)
     flop_step, s_nz = algorithmic_flop_per_step(props)
-    flop_executed = executed_flop_per_step(props)
+    prefix = eq.algorithm == ldm.ALGO_PREFIX
+    flop_executed = executed_flop_per_step(props, prefix)
     fp64_peak = ldm.measure_fp64_peak(local_rank)
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB of L2
@@ -459,8 +470,13 @@ def main():
                          "traffic": measured_traffic(args.workload), "algorithmic_flop_per_step": flop_step,
                          "executed_flop_per_step": flop_executed, "executed_tflops": flop_executed / (ms_per_step * 1e-3) / 1e12,
                          "executed_frac": flop_executed / (ms_per_step * 1e-3) / 1e12 / fp64_peak,
-                         "note": "frac > 1 is expected: the factored algorithm issues ~14x fewer FP64 operations than the 11-FLOP-per-sample "
-                                 "model of the sample-by-sample sum (DESIGN.md 5); executed_frac is the honest pipe utilisation",
+                         "algorithm": "prefix" if prefix else "dense",
+                         "note": "frac > 1 is expected: achieved counts the 11-FLOP-per-sample model of the reference's sample-by-sample sum "
+                                 "(SURVEY 8d); the prefix-sum path issues ~120x fewer FP64 operations (executed_*), so the step is no longer bound by "
+                                 "the FP64 pipe but by L2->SM throughput in the E phase (l2_*), shared-memory wavefronts in the y phase and one "
+                                 "grid barrier (DESIGN.md 5)",
+                         "l2_bytes_per_step": l2_bytes_per_step(props) if prefix else None,
+                         "l2_GBps_over_step": l2_bytes_per_step(props) / (ms_per_step * 1e-3) / 1e9 if prefix else None,
                          "peak_source": "measured live: DFMA chain micro-benchmark (MEASURED_PEAKS.json has no FP64 figure)",
                          "hbm_GBps_algorithmic": 16.0 * P / (ms_per_step * 1e-3) / 1e9},
             "clocks": clocks.summary(),

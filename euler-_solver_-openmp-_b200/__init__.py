@@ -42,9 +42,11 @@ _SIGNATURES = {
     "ldm_problem_generate": (C.c_int, [C.c_double] * 5 + [C.c_int, C.POINTER(C.POINTER(_Problem))]),
     "ldm_problem_free": (None, [C.POINTER(_Problem)]),
     "ldm_problem_check_kernels": (C.c_int, [C.POINTER(_Problem), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
+    "ldm_problem_kernel_structure": (C.c_int, [C.POINTER(_Problem), C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "ldm_create": (C.c_int, [C.POINTER(_Problem), C.c_int, C.POINTER(C.c_void_p)]),
     "ldm_destroy": (None, [C.c_void_p]),
     "ldm_set_algorithm": (C.c_int, [C.c_void_p, C.c_int]),
+    "ldm_get_algorithm": (C.c_int, [C.c_void_p]),
     "ldm_rhs": (C.c_int, [C.c_void_p, _dp, _dp]),
     "ldm_integrals": (C.c_int, [C.c_void_p, _dp, C.POINTER(C.c_double), C.c_void_p]),
     "ldm_kernels_at_nodes": (C.c_int, [C.c_void_p, _dp, _dp]),
@@ -134,6 +136,12 @@ class Properties:
         assert abs(iw.value - 1) < 1e-8 and abs(im.value - 1) < 1e-8
         return iw.value, im.value
 
+    def KernelStructure(self):
+        """(separable, max relative deviation) of the m table: whether the prefix-sum path applies (host only)."""
+        sep, dev = C.c_int(), C.c_double()
+        _check(library().ldm_problem_kernel_structure(self._ptr, C.byref(sep), C.byref(dev)))
+        return bool(sep.value), dev.value
+
     @property
     def state_size(self):
         return 1 + self.G * self.G
@@ -159,6 +167,10 @@ class Equation:
 
     def set_algorithm(self, algorithm):
         _check(library().ldm_set_algorithm(self._h, algorithm))
+
+    @property
+    def algorithm(self):
+        return library().ldm_get_algorithm(self._h)
 
     def GenerateEquilibriumValuesForNAndC(self, value):
         """Solver.cpp:416-428: [N = value | C = value^2 everywhere]"""

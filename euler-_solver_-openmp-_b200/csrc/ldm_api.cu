@@ -20,6 +20,10 @@ namespace {
 
 thread_local std::string g_error;
 
+// |Q - q q^T| <= tolerance * q q^T decides whether a kernel table takes the prefix-sum path: libm's exp leaves ~2e-15 on
+// the reference's tables; anything beyond 1e-13 is structure, not rounding
+constexpr double kSeparableTolerance = 1e-13;
+
 int fail(int code, const std::string& what)
 {
     g_error = what;
@@ -513,6 +517,21 @@ int ldm_problem_check_kernels(const ldm_problem* p, double* integral_w, double* 
     return LDM_OK;
 }
 
+int ldm_problem_kernel_structure(const ldm_problem* p, int* separable, double* max_rel_dev)
+{
+    if (!p || !separable || !max_rel_dev) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    if (p->species != 1 || p->G < 2 || p->K < 3 || !p->moments_grid || !p->kernels_grid || !p->M || !p->W)
+        return fail(LDM_ERR_ARGUMENT, "incomplete problem description");
+    return guarded([&] {
+        ldm::Tables t;
+        ldm::build_tables(*p, t);
+        ldm::SeparableKernel k;
+        ldm::detect_separable(t.offM, kSeparableTolerance, k);
+        *separable = k.ok ? 1 : 0;
+        *max_rel_dev = k.max_rel_dev;
+    });
+}
+
 int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
 {
     if (!p || !out) return fail(LDM_ERR_ARGUMENT, "NULL argument");
@@ -572,14 +591,14 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         c->d_sum = c->alloc<double>(P);
         c->d_deriv = c->alloc<double>(P);
         // structure of the m table: separable inside its disc (every table Properties::Generate builds) -> prefix sums
-        d.qvec = nullptr; d.a_star = nullptr; d.beta_range = nullptr; d.scan_ranges = nullptr; d.scan_bn = 0; d.scan_chunks = 0; d.scan_nt = 512; d.scan_live_rows = 0;
+        d.qvec = nullptr; d.a_star = nullptr; d.beta_range = nullptr; d.scan_piece = nullptr; d.scan_chunk_begin = nullptr; d.scan_warp_begin = nullptr; d.scan_block_begin = nullptr; d.scan_max_pieces = 0; d.scan_bn = 0; d.scan_chunks = 0; d.scan_nt = 512; d.scan_live_rows = 0;
         {
             std::vector<unsigned short> u16(t.axisM.upper.size());
             for (int n = 0; n < d.G; n++)
                 for (int o = 0; o < d.n_off; o++) u16[(size_t)o * d.G + n] = (unsigned short)t.axisM.upper[(size_t)n * d.n_off + o];
             d.upper_t16 = c->upload(u16);
         }
-        ldm::detect_separable(t.offM, 1e-13, c->separable);
+        ldm::detect_separable(t.offM, kSeparableTolerance, c->separable);
         const int scan_bn = (c->separable.ok && d.G <= 65535) ? ldm::scan_pick_bn(d.G, d.A) : 0;
         c->plan_dense = ldm::plan_factored(d);
         if (scan_bn > 0 && std::getenv("LDM_SCAN_DISABLE") == nullptr) {
@@ -588,12 +607,16 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
             std::vector<int> pairs((size_t)d.A * 2);
             for (int a = 0; a < d.A; a++) { pairs[2 * (size_t)a] = c->separable.beta_lo[a]; pairs[2 * (size_t)a + 1] = c->separable.beta_hi[a]; }
             d.beta_range = reinterpret_cast<const int2*>(c->upload(pairs));
-            std::vector<int> ranges;
-            ldm::build_scan_ranges(t, scan_bn, ranges);
-            d.scan_ranges = c->upload(ranges);
             d.scan_bn = scan_bn;
             d.scan_chunks = (d.G + scan_bn - 1) / scan_bn;
             d.scan_nt = ldm::scan_pick_threads(d.G, d.A, scan_bn);
+            ldm::ScanPieces pieces;
+            ldm::build_scan_pieces(t, scan_bn, d.scan_nt / 32, pieces);
+            d.scan_piece = reinterpret_cast<const int4*>(c->upload(pieces.piece));
+            d.scan_chunk_begin = c->upload(pieces.chunk_begin);
+            d.scan_warp_begin = c->upload(pieces.warp_begin);
+            d.scan_block_begin = c->upload(pieces.block_begin);
+            d.scan_max_pieces = pieces.max_pieces;
             d.scan_live_rows = 0;
             while (d.scan_live_rows < d.A && c->separable.a_star[(size_t)d.scan_live_rows] >= 0) d.scan_live_rows++;
             c->plan_scan = c->plan_dense;
@@ -638,6 +661,8 @@ int ldm_set_algorithm(ldm_handle h, int algo)
     }
     return LDM_OK;
 }
+
+int ldm_get_algorithm(ldm_handle h) { return h ? h->algo : LDM_ERR_ARGUMENT; }
 
 int ldm_rhs(ldm_handle h, const double* state, double* deriv)
 {
@@ -912,7 +937,7 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
                 g->max_A = std::max(g->max_A, h->dev.A);
                 g->max_ring = std::max(g->max_ring, h->dev.n_ring);
                 g->max_points = std::max(g->max_points, h->dev.G * h->dev.G);
-                if (h->plan.scan) g->max_smem = std::max(g->max_smem, ldm::scan_smem_bytes(h->dev.G, h->dev.A, h->dev.scan_bn, h->dev.scan_nt));
+                if (h->plan.scan) g->max_smem = std::max(g->max_smem, ldm::scan_smem_bytes(h->dev.G, h->dev.A, h->dev.scan_bn, h->dev.scan_nt, h->dev.scan_max_pieces));
             }
             std::vector<void*> scratch;
             try {

@@ -36,7 +36,12 @@ struct DevProblem {
     const int* a_star;         // [A]
     const int2* beta_range;    // [A] rows beta with a_star[beta] == alpha: [x, y)
     const unsigned short* upper_t16;   // [n_off][G] upper_t in 16 bits
-    const int* scan_ranges;    // [scan_chunks][ceil(G/32)][3][2] offset intervals of the y-side pass per (chunk, y block)
+    // y-side work list (ldm_model.h ScanPieces): pieces (y block, first offset, end offset) dealt out to the warps
+    const int4* scan_piece;        // all chunks' pieces
+    const int* scan_chunk_begin;   // [scan_chunks + 1] first piece of each chunk
+    const int* scan_warp_begin;    // [scan_chunks][scan_nt / 32 + 1] relative to the chunk's first piece
+    const int* scan_block_begin;   // [scan_chunks][ceil(G/32) + 1] relative to the chunk's first piece
+    int scan_max_pieces;
     int scan_bn, scan_chunks;  // column chunk width (multiple of 32) and count
     int scan_live_rows;        // rows beta < scan_live_rows have a_star >= 0; the rest of the table is empty
     int scan_nt;               // threads per CTA = ng * scan_bn (ng lanes of a warp share one column)
@@ -166,7 +171,7 @@ int scan_pick_bn(int G, int A);
 int scan_pick_threads(int G, int A, int bn);
 void launch_scan(const StepArgs& one, cudaStream_t stream);
 void launch_scan_batch(const StepArgs* d_batch, int n, int nt, int max_chunks, int max_rows, size_t max_smem, cudaStream_t stream);
-size_t scan_smem_bytes(int G, int A, int bn, int nt);
+size_t scan_smem_bytes(int G, int A, int bn, int nt, int max_pieces);
 cudaError_t launch_persistent_scan(const PersistentArgs& args, int grid, cudaStream_t stream, int* max_grid);
 // single problem: `one` by value; batch: d_batch[n] in device memory, all entries sharing the plan's tile shape
 void launch_factored(const FactoredPlan& plan, const StepArgs& one, cudaStream_t stream);

@@ -319,14 +319,18 @@ void detect_separable(const OffsetSet& off, double tolerance, SeparableKernel& o
     out.ok = true;
 }
 
-void build_scan_ranges(const Tables& t, int bn, std::vector<int>& ranges)
+void build_scan_pieces(const Tables& t, int bn, int warps, ScanPieces& out)
 {
     const int G = t.G, n_off = t.offM.n_off;
     const int chunks = (G + bn - 1) / bn, blocks = (G + 31) / 32;
-    ranges.assign((size_t)chunks * blocks * kScanRanges * 2, 0);
+    out = ScanPieces();
+    out.chunk_begin.push_back(0);
     std::vector<char> hit((size_t)n_off);
     for (int c = 0; c < chunks; c++) {
         const int q0 = c * bn, q1 = std::min(G, q0 + bn);      // columns [q0, q1)
+        // the offset intervals of every y block
+        std::vector<std::vector<std::pair<int, int>>> runs_of((size_t)blocks);
+        long long total = 0;
         for (int yb = 0; yb < blocks; yb++) {
             std::fill(hit.begin(), hit.end(), 0);
             for (int y = yb * 32; y < std::min(G, yb * 32 + 32); y++)
@@ -336,7 +340,7 @@ void build_scan_ranges(const Tables& t, int bn, std::vector<int>& ranges)
                     if ((u - 1 >= q0 && u - 1 < q1) || (u >= q0 && u < q1)) hit[(size_t)o] = 1;
                 }
             // maximal runs of hit offsets; while there are too many, close the narrowest gap
-            std::vector<std::pair<int, int>> runs;
+            std::vector<std::pair<int, int>>& runs = runs_of[(size_t)yb];
             for (int o = 0; o < n_off; o++)
                 if (hit[(size_t)o]) {
                     if (!runs.empty() && runs.back().second == o) runs.back().second = o + 1;
@@ -349,9 +353,29 @@ void build_scan_ranges(const Tables& t, int bn, std::vector<int>& ranges)
                 runs[best - 1].second = runs[best].second;
                 runs.erase(runs.begin() + (long)best);
             }
-            int* dst = ranges.data() + ((size_t)c * blocks + yb) * kScanRanges * 2;
-            for (size_t r = 0; r < runs.size(); r++) { dst[2 * r] = runs[r].first; dst[2 * r + 1] = runs[r].second; }
+            for (const auto& r : runs) total += r.second - r.first;
         }
+        // cut into pieces: every warp takes the next `quota` offsets of the chunk's list
+        const int quota = (int)std::max<long long>(1, (total + warps - 1) / warps);
+        const int first = (int)out.piece.size() / 4;
+        std::vector<int> warp_begin((size_t)warps + 1, 0), block_begin((size_t)blocks + 1, 0);
+        int w = 0, load = 0, count = 0;
+        for (int yb = 0; yb < blocks; yb++) {
+            block_begin[(size_t)yb] = count;
+            for (auto [lo, hi] : runs_of[(size_t)yb])
+                while (lo < hi) {
+                    if (load == quota && w + 1 < warps) { w++; warp_begin[(size_t)w] = count; load = 0; }
+                    const int take = w + 1 < warps ? std::min(quota - load, hi - lo) : hi - lo;
+                    out.piece.insert(out.piece.end(), {yb, lo, lo + take, 0});
+                    count++; load += take; lo += take;
+                }
+        }
+        block_begin[(size_t)blocks] = count;
+        for (int v = w + 1; v <= warps; v++) warp_begin[(size_t)v] = count;
+        out.warp_begin.insert(out.warp_begin.end(), warp_begin.begin(), warp_begin.end());
+        out.block_begin.insert(out.block_begin.end(), block_begin.begin(), block_begin.end());
+        out.chunk_begin.push_back(first + count);
+        out.max_pieces = std::max(out.max_pieces, count);
     }
 }
 

@@ -81,11 +81,21 @@ struct SeparableKernel {
 };
 void detect_separable(const OffsetSet& off, double tolerance, SeparableKernel& out);
 
-// y-side work list of the prefix-sum path for column chunks of width bn: for every (chunk, block of 32 consecutive nodes
-// y) up to kScanRanges intervals [lo, hi) of signed offsets o that cover every (y, o) whose interpolation pair
-// (upper-1, upper) touches a column of the chunk.  Layout [chunks][ceil(G/32)][kScanRanges][2].
+// y-side work list of the prefix-sum path for column chunks of width bn.  For every (chunk, block of 32 consecutive
+// nodes y) the signed offsets o whose interpolation pair (upper-1, upper) touches a column of the chunk form up to
+// kScanRanges intervals; the intervals of a chunk are cut into PIECES of about equal length, dealt out to the warps of a
+// CTA in order (the far chunks of a stretched grid own most pairs of only a few y blocks: whole blocks per warp would
+// leave most warps idle).  Every piece belongs to one y block; the pieces of a block and the pieces of a warp are
+// contiguous in the list.
 constexpr int kScanRanges = 3;
-void build_scan_ranges(const Tables& t, int bn, std::vector<int>& ranges);
+struct ScanPieces {
+    std::vector<int> chunk_begin;      // chunks + 1: first piece of each chunk
+    std::vector<int> piece;            // 4 ints per piece: y block, first offset, end offset, 0
+    std::vector<int> warp_begin;       // [chunks][warps + 1], relative to the chunk's first piece
+    std::vector<int> block_begin;      // [chunks][ceil(G/32) + 1], relative to the chunk's first piece
+    int max_pieces = 0;                // largest piece count of a chunk (sizes the per-piece partial sums)
+};
+void build_scan_pieces(const Tables& t, int bn, int warps, ScanPieces& out);
 
 // The exact correction of the factored path as a sparse linear operator (time-invariant).  The factored sum
 // covers every sample inside the grid square; the reference replaces the samples beyond the cutoff circle by

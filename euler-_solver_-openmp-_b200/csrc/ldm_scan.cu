@@ -20,8 +20,9 @@
 //   2. threads = (column, group): E on the fly from C (coalesced along q), running sum along alpha (the groups of a column
 //      exchange block sums once per super-chunk of alphas), and whenever alpha is the last in-disc column of some rows
 //      beta, H[beta][col] = q[beta] * sum;
-//   3. y side: a warp owns 32 consecutive nodes y and walks the offset intervals that touch this chunk (scan_ranges),
-//      lanes read the transposed tables coalesced, gather the two H columns of their interpolation pair and accumulate;
+//   3. y side: the (y block, offset interval) pieces that touch this chunk are dealt out evenly over the warps
+//      (ldm_model.h ScanPieces); lanes = 32 consecutive nodes y read the transposed tables coalesced, gather the two H
+//      columns of their interpolation pair and accumulate; per-piece partial sums are added up in list order;
 //   4. per-chunk partial sums to global memory; finish_factored_kernel adds the chunks, subtracts the ring correction
 //      and closes the step.
 #include <algorithm>
@@ -51,26 +52,26 @@ constexpr int kScanLead = 2;              // doubles in front of column 0 of an 
 __host__ __device__ constexpr int scan_unroll(int NT) { return NT <= 256 ? 2 : 4; }
 
 struct ScanLayout {                       // byte offsets into dynamic shared memory, identical on host and device
-    int ld, a_pad, n_yblk, split, part_stride, ng;
-    size_t hs, part, rowbuf, bsum, tap_w, qv, tap_row, sel, end;
+    int ld, a_pad, n_yblk, part_stride, ng;
+    size_t hs, part, rowsum, rowbuf, bsum, tap_w, qv, tap_row, sel, end;
 };
 
 __host__ __device__ inline size_t align32(size_t v) { return (v + 31) & ~(size_t)31; }
 
-__host__ __device__ inline ScanLayout scan_layout(int G, int A, int bn, int NT)
+// `pieces`: the largest piece count of a chunk's y-side work list (one partial sum per piece and lane)
+__host__ __device__ inline ScanLayout scan_layout(int G, int A, int bn, int NT, int pieces)
 {
     ScanLayout L;
     L.ld = bn + kScanLead;
     L.n_yblk = (G + 31) / 32;
-    const int warps = NT / 32;
-    L.split = warps / L.n_yblk > 1 ? warps / L.n_yblk : 1;    // warps sharing one block of 32 nodes y
     L.part_stride = L.n_yblk * 32;
     L.ng = NT / bn > 1 ? NT / bn : 1;                     // thread groups of bn columns sharing the alphas of a super-chunk
     const int span = L.ng * scan_unroll(NT);
     L.a_pad = ((A + span - 1) / span) * span;             // whole super-chunks (zero-weight rows behind A)
     size_t at = 0;
     L.hs = at;      at = align32(at + sizeof(double) * (size_t)A * L.ld);
-    L.part = at;    at = align32(at + sizeof(double) * (size_t)L.split * L.part_stride);
+    L.part = at;    at = align32(at + sizeof(double) * 32 * (size_t)pieces);
+    L.rowsum = at;  at = align32(at + sizeof(double) * (size_t)L.part_stride);
     L.rowbuf = at;  at = align32(at + sizeof(double) * 2 * (size_t)L.part_stride);   // persistent kernel: the new row of C, the row of the WC functional
     L.bsum = at;    at = align32(at + sizeof(double) * 2 * (size_t)L.ng * bn);
     L.tap_w = at;   at = align32(at + sizeof(double) * 4 * (size_t)L.a_pad);
@@ -139,8 +140,7 @@ __device__ __forceinline__ double y_side_interval(const DevProblem& P, const dou
 }
 
 // The work of one CTA: row `lx` of this rank, column chunk `chunk`.
-// fused (persistent kernel): the per-node sums stay in shared memory (first G doubles of the part_y region) for the
-// closing phase of the same CTA, nothing is written to global memory and the WC rows are left to the caller.
+// fused (persistent kernel): the per-node sums stay in shared memory (row_sum) for the closing phase of the same CTA, nothing is written to global memory and the WC rows are left to the caller.
 // `mid` runs between the two phases (the persistent kernel requests there what its closing phase will need, so that
 // those loads fly under the y side).
 struct NoMid { __device__ void operator()() const {} };
@@ -158,12 +158,13 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
     const int x = P.rank + P.world * lx;
     const int q0 = chunk * bn;
     const int tid = threadIdx.x;
-    const ScanLayout L = scan_layout(G, A, bn, NT);
+    const ScanLayout L = scan_layout(G, A, bn, NT, P.scan_max_pieces);
     const int ld = L.ld;
 
     extern __shared__ __align__(32) unsigned char scan_smem[];
     double* Hs = reinterpret_cast<double*>(scan_smem + L.hs);            // [A][ld]
-    double* part_y = reinterpret_cast<double*>(scan_smem + L.part);      // [split][n_yblk * 32]
+    double* part_y = reinterpret_cast<double*>(scan_smem + L.part);      // [pieces][32] partial sums of the y side
+    double* row_sum = reinterpret_cast<double*>(scan_smem + L.rowsum);   // [G] fused mode: the finished per-node sums
     double* bsum = reinterpret_cast<double*>(scan_smem + L.bsum);        // [2][ng][bn] block sums of the current super-chunk
     double* tap_w = reinterpret_cast<double*>(scan_smem + L.tap_w);      // [a_pad][4] q[alpha] * weights of the four C rows feeding E[alpha]
     double* qv = reinterpret_cast<double*>(scan_smem + L.qv);            // [a_pad]
@@ -274,27 +275,25 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
     {
         const int warp = tid >> 5, lane = tid & 31, warps = NT / 32;
         const bool masked = P.scan_chunks > 1;
-        for (int item = warp; item < L.n_yblk * L.split; item += warps) {
-            const int yb = item % L.n_yblk, part = item / L.n_yblk;
-            const int y = min(yb * 32 + lane, G - 1);
-            const int* rng = P.scan_ranges + ((size_t)chunk * L.n_yblk + yb) * 6;
-            double s = 0.0;
-            #pragma unroll
-            for (int r = 0; r < 3; r++) {
-                const int lo = rng[2 * r] + part, hi = rng[2 * r + 1];
-                if (cached_w_rows >= 0) s += y_side_interval<false, true>(P, Hs, ld, q0, bn, lo, hi, L.split, y, u_cache, w_cache, cached_w_rows);
-                else if (masked) s += y_side_interval<true, false>(P, Hs, ld, q0, bn, lo, hi, L.split, y, nullptr, nullptr, 0);
-                else s += y_side_interval<false, false>(P, Hs, ld, q0, bn, lo, hi, L.split, y, nullptr, nullptr, 0);
-            }
-            part_y[part * L.part_stride + yb * 32 + lane] = s;
+        const int4* pieces = P.scan_piece + P.scan_chunk_begin[chunk];
+        const int* warp_begin = P.scan_warp_begin + chunk * (warps + 1);
+        const int* block_begin = P.scan_block_begin + chunk * (L.n_yblk + 1);
+        for (int pi = warp_begin[warp]; pi < warp_begin[warp + 1]; pi++) {
+            const int4 pc = pieces[pi];                        // y block, first offset, end offset
+            const int y = min(pc.x * 32 + lane, G - 1);
+            double s;
+            if (cached_w_rows >= 0) s = y_side_interval<false, true>(P, Hs, ld, q0, bn, pc.y, pc.z, 1, y, u_cache, w_cache, cached_w_rows);
+            else if (masked) s = y_side_interval<true, false>(P, Hs, ld, q0, bn, pc.y, pc.z, 1, y, nullptr, nullptr, 0);
+            else s = y_side_interval<false, false>(P, Hs, ld, q0, bn, pc.y, pc.z, 1, y, nullptr, nullptr, 0);
+            part_y[pi * 32 + lane] = s;
         }
         __syncthreads();
         SCAN_MARK(4);
         double* out = S.partial + ((size_t)chunk * local_rows(P) + lx) * G;
         for (int y = tid; y < G; y += NT) {
             double s = 0.0;
-            for (int part = 0; part < L.split; part++) s += part_y[part * L.part_stride + y];     // fixed order
-            if (fused) part_y[y] = s;                   // only this thread touches column y
+            for (int pi = block_begin[y >> 5]; pi < block_begin[(y >> 5) + 1]; pi++) s += part_y[pi * 32 + (y & 31)];   // fixed order
+            if (fused) row_sum[y] = s;
             else out[y] = s;
         }
     }
@@ -366,9 +365,9 @@ persistent_scan_kernel(const PersistentArgs A)
     StepArgs S = A.step;
     const DevProblem& P = S.P;
     const int G = P.G, tid = threadIdx.x, x = blockIdx.x;          // one rank, natural layout: row x = CTA x
-    const ScanLayout L = scan_layout(G, P.A, P.scan_bn, NT);
+    const ScanLayout L = scan_layout(G, P.A, P.scan_bn, NT, P.scan_max_pieces);
     extern __shared__ __align__(32) unsigned char scan_smem[];
-    double* row_sum = reinterpret_cast<double*>(scan_smem + L.part);              // [G] after scan_body(fused)
+    double* row_sum = reinterpret_cast<double*>(scan_smem + L.rowsum);            // [G] after scan_body(fused)
     int parity = A.parity;
     unsigned int barrier_index = 0;
 
@@ -489,7 +488,10 @@ extern "C" int ldm_debug_scan_clocks(long long* out, int rows)
 }
 #endif
 
-size_t scan_smem_bytes(int G, int A, int bn, int nt) { return scan_layout(G, A, bn, nt).end; }
+size_t scan_smem_bytes(int G, int A, int bn, int nt, int max_pieces) { return scan_layout(G, A, bn, nt, max_pieces).end; }
+
+// no chunk has more pieces than this (every y block at most kScanRanges intervals, every warp at most one extra cut)
+static int piece_bound(int G, int nt) { return 3 * ((G + 31) / 32) + nt / 32; }
 
 // Threads per CTA = ng * bn (ng groups of bn columns).  Small working sets (several CTAs fit one SM's shared memory)
 // take 256-thread CTAs, everything else 257..512 threads.
@@ -499,13 +501,16 @@ int scan_pick_threads(int G, int A, int bn)
         const int v = std::atoi(env);
         if ((v == 256 || v == 512) && v >= bn) return (v / bn) * bn;
     }
-    if (bn <= 64 && scan_layout(G, A, bn, 256).end <= 48 * 1024) return (256 / bn) * bn;
+    if (bn <= 64 && scan_layout(G, A, bn, 256, piece_bound(G, 256)).end <= 48 * 1024) return (256 / bn) * bn;
     return (kScanThreadsMax / bn) * bn;                    // bn = 32, 64, 96, 128 -> 512, 512, 480, 512
 }
 
 int scan_pick_bn(int G, int A)
 {
-    auto fits = [&](int bn) { return scan_smem_bytes(G, A, bn, scan_pick_threads(G, A, bn)) <= kSmemBudget; };
+    auto fits = [&](int bn) {
+        const int nt = scan_pick_threads(G, A, bn);
+        return scan_smem_bytes(G, A, bn, nt, piece_bound(G, nt)) <= kSmemBudget;
+    };
     if (const char* env = std::getenv("LDM_SCAN_BN")) {
         const int v = std::atoi(env);
         if (v >= 32 && v <= 128 && v % 32 == 0 && fits(v)) return v;
@@ -541,7 +546,7 @@ void launch_scan(const StepArgs& one, cudaStream_t stream)
 {
     const DevProblem& P = one.P;
     launch_scan_variant<false>(&one, nullptr, dim3(P.scan_chunks, local_rows(P), 1), P.scan_nt,
-                               scan_smem_bytes(P.G, P.A, P.scan_bn, P.scan_nt), stream);
+                               scan_smem_bytes(P.G, P.A, P.scan_bn, P.scan_nt, P.scan_max_pieces), stream);
 }
 
 // every member of a batch launch shares the CTA shape nt (= ng * bn); shared memory is sized for the largest member
@@ -558,7 +563,7 @@ cudaError_t launch_persistent_scan(const PersistentArgs& args, int grid, cudaStr
     const int G = P.G, n_off = P.n_off, nt = P.scan_nt;
     const void* kernel = nt <= 256 ? (const void*)persistent_scan_kernel<true> : (const void*)persistent_scan_kernel<false>;
     // shared memory: the step's working set, then the 16-bit y-side index table, then as many weight rows as still fit
-    const size_t base = scan_smem_bytes(G, P.A, P.scan_bn, nt);
+    const size_t base = scan_smem_bytes(G, P.A, P.scan_bn, nt, P.scan_max_pieces);
     const size_t u_bytes = align32(sizeof(unsigned short) * (size_t)n_off * G);
     PersistentArgs with_cache = args;
     with_cache.cached_w_rows = -1;

@@ -63,10 +63,16 @@ void ldm_problem_free(ldm_problem* p);
 /* Properties::CheckKernels (S:147-183): the two midpoint-rule integrals (each must be 1 +- 1e-8) */
 int  ldm_problem_check_kernels(const ldm_problem* p, double* integral_w, double* integral_m);
 
+/* Structure of the m table that LDM_ALGO_PREFIX needs (host only): separable inside its disc, i.e.
+ * M[2b+1][2a+1] = q[b] q[a] on a staircase region and 0 beyond, as every table of GenerateKernel (S:113-123) is.
+ * *separable = 1/0; *max_rel_dev = largest |M - q q^T| / (q q^T) over the non-zero quadrature entries. */
+int  ldm_problem_kernel_structure(const ldm_problem* p, int* separable, double* max_rel_dev);
+
 /* ---- Equation(Properties) (S:413): upload tables, build the time-invariant index/weight tables ---- */
 int  ldm_create(const ldm_problem* p, int device, ldm_handle* out);
 void ldm_destroy(ldm_handle h);
 int  ldm_set_algorithm(ldm_handle h, int algo);
+int  ldm_get_algorithm(ldm_handle h);                                /* the algorithm in force (never LDM_ALGO_AUTO) */
 
 /* ---- Equation::operator()(t, vals, SquaredN) (S:431-513): host state in, host derivative out ---- */
 int  ldm_rhs(ldm_handle h, const double* state, double* deriv);

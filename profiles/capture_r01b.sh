@@ -1,0 +1,10 @@
+set -x
+python bench.py --steps 200 --warmup 20 > gpurun_out/bench_r1b_n1.json 2> gpurun_out/bench_r1b_n1.err
+tail -c 300 gpurun_out/bench_r1b_n1.err
+python bench.py --steps 6 --warmup 3 --no-cpu-baseline --batch-sets 0 > gpurun_out/plain_a.log 2>&1 && \
+ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_prefix_persistent.csv python bench.py --steps 6 --warmup 3 --no-cpu-baseline --batch-sets 0 > gpurun_out/ncu_a.log 2>&1
+LDM_PERSISTENT=0 python bench.py --steps 6 --warmup 3 --no-cpu-baseline --batch-sets 0 --sharded none > gpurun_out/plain_b.log 2>&1 && \
+LDM_PERSISTENT=0 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches_prefix_stepwise.csv python bench.py --steps 6 --warmup 3 --no-cpu-baseline --batch-sets 0 --sharded none > gpurun_out/ncu_b.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:persistent_scan_kernel -c 1 -o gpurun_out/prof_r1b_persistent_scan -f python bench.py --steps 6 --warmup 3 --no-cpu-baseline --batch-sets 0 --sharded none > gpurun_out/ncu_c.log 2>&1
+ncu --set full --clock-control none --cache-control none --import-source on -k regex:scan_kernel -s 8 -c 1 -o gpurun_out/prof_r1b_scan_g512 -f python bench.py --steps 6 --warmup 3 --no-cpu-baseline --batch-sets 0 --workload g512 --sharded none > gpurun_out/ncu_d.log 2>&1
+ls -la gpurun_out | tail -12

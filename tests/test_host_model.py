@@ -30,6 +30,25 @@ def test_generate_matches_reference_bitwise(ldm, path):
     p.CheckKernels()       # Solver.cpp:147-183: both integrals within 1e-8 of 1
 
 
+@pytest.mark.parametrize("path", GOLDEN, ids=[os.path.basename(p)[:-4] for p in GOLDEN])
+def test_reference_kernel_tables_are_separable_inside_their_disc(ldm, path):
+    """the structure the prefix-sum path rests on: every table Properties::GenerateKernel builds (Solver.cpp:98-145) is
+    q q^T on a staircase region, up to the rounding of libm's exp (a few 1e-15), and zero beyond"""
+    g = np.load(path)
+    p = generate(ldm, g, path)
+    separable, deviation = p.KernelStructure()
+    assert separable and deviation < 1e-14
+    # the check is on the table that is passed in, not on how it was made: a perturbed entry is structure, not rounding
+    table = np.ctypeslib.as_array(p._ptr.contents.M, (p.K, p.K))
+    if table[3, 3] != 0:         # at least a full 2 x 2 block inside the disc: four entries against two parameters
+        table[1, 1] *= 1 + 1e-9
+        separable, deviation = p.KernelStructure()
+        assert not separable and deviation > 1e-10
+        table[1, 1] /= 1 + 1e-9
+        table[3, 1] *= 1 + 1e-9          # an asymmetric table is not separable either
+        assert not p.KernelStructure()[0]
+
+
 def test_header_symbols_are_exported(ldm):
     header = open(os.path.join(ROOT, "include", "ldm.h")).read()
     declared = set(re.findall(r"\b(ldm_[a-z_A-Z0-9]+)\s*\(", header))
