@@ -79,10 +79,9 @@ def executed_flop_per_step(props, prefix):
     return gemm + e_gen + y_side + 30.0 * G * G
 
 
-def l2_bytes_per_step(props):
-    """Bytes the prefix-sum path pulls from L2 per step (its binding resource in the E phase): four C values per element
-    of E (no reuse: near the origin the moment grid is finer than the quadrature) -- y-side tables are resident in shared
-    memory in the persistent kernel."""
+def requested_bytes_per_step(props):
+    """Bytes of C the E phase of the prefix-sum path requests per step: four values per element of E (ncu: two thirds of
+    them hit in L1, profiles/r01_traffic.json)."""
     G, A = props.G, (props.MaxNumForM - 1) // 2 if props.MaxNumForM > 2 else 1
     return 32.0 * G * A * G
 
@@ -473,10 +472,9 @@ def main():
                          "algorithm": "prefix" if prefix else "dense",
                          "note": "frac > 1 is expected: achieved counts the 11-FLOP-per-sample model of the reference's sample-by-sample sum "
                                  "(SURVEY 8d); the prefix-sum path issues ~120x fewer FP64 operations (executed_*), so the step is no longer bound by "
-                                 "the FP64 pipe but by L2->SM throughput in the E phase (l2_*), shared-memory wavefronts in the y phase and one "
-                                 "grid barrier (DESIGN.md 5)",
-                         "l2_bytes_per_step": l2_bytes_per_step(props) if prefix else None,
-                         "l2_GBps_over_step": l2_bytes_per_step(props) / (ms_per_step * 1e-3) / 1e9 if prefix else None,
+                                 "the FP64 pipe but by the load/store pipe (gathers of C in the E phase, shared-memory gathers in the y phase) and one "
+                                 "grid barrier per step (DESIGN.md 5)",
+                         "e_phase_requested_bytes_per_step": requested_bytes_per_step(props) if prefix else None,
                          "peak_source": "measured live: DFMA chain micro-benchmark (MEASURED_PEAKS.json has no FP64 figure)",
                          "hbm_GBps_algorithmic": 16.0 * P / (ms_per_step * 1e-3) / 1e9},
             "clocks": clocks.summary(),
