@@ -59,6 +59,7 @@ _SIGNATURES = {
     "ldm_synchronize": (C.c_int, [C.c_void_p]),
     "ldm_last_elapsed_ms": (C.c_int, [C.c_void_p, C.POINTER(C.c_float)]),
     "ldm_launch_count": (C.c_longlong, [C.c_void_p]),
+    "ldm_device_count": (C.c_int, []),
     "ldm_solve_batch": (C.c_int, [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_double, C.c_double,
                                   C.POINTER(C.c_void_p)]),
     "ldm_shard_configure": (C.c_int, [C.c_void_p, C.c_int, C.c_int]),

@@ -10,6 +10,7 @@
 #include <type_traits>
 #include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ldm.h"
@@ -591,7 +592,7 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         c->d_sum = c->alloc<double>(P);
         c->d_deriv = c->alloc<double>(P);
         // structure of the m table: separable inside its disc (every table Properties::Generate builds) -> prefix sums
-        d.qvec = nullptr; d.a_star = nullptr; d.beta_range = nullptr; d.scan_piece = nullptr; d.scan_chunk_begin = nullptr; d.scan_warp_begin = nullptr; d.scan_block_begin = nullptr; d.scan_max_pieces = 0; d.scan_bn = 0; d.scan_chunks = 0; d.scan_nt = 512; d.scan_live_rows = 0;
+        d.qvec = nullptr; d.a_star = nullptr; d.beta_range = nullptr; d.scan_piece = nullptr; d.scan_chunk_begin = nullptr; d.scan_warp_begin = nullptr; d.scan_block_begin = nullptr; d.scan_chunk_order = nullptr; d.scan_max_pieces = 0; d.scan_bn = 0; d.scan_chunks = 0; d.scan_nt = 512; d.scan_live_rows = 0;
         {
             std::vector<unsigned short> u16(t.axisM.upper.size());
             for (int n = 0; n < d.G; n++)
@@ -617,6 +618,16 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
             d.scan_warp_begin = c->upload(pieces.warp_begin);
             d.scan_block_begin = c->upload(pieces.block_begin);
             d.scan_max_pieces = pieces.max_pieces;
+            {
+                std::vector<long long> work((size_t)d.scan_chunks, 0);
+                for (int ch = 0; ch < d.scan_chunks; ch++)
+                    for (int pi = pieces.chunk_begin[(size_t)ch]; pi < pieces.chunk_begin[(size_t)ch + 1]; pi++)
+                        work[(size_t)ch] += pieces.piece[4 * (size_t)pi + 2] - pieces.piece[4 * (size_t)pi + 1];
+                std::vector<int> order((size_t)d.scan_chunks);
+                for (int ch = 0; ch < d.scan_chunks; ch++) order[(size_t)ch] = ch;
+                std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return work[(size_t)a] > work[(size_t)b]; });
+                d.scan_chunk_order = c->upload(order);
+            }
             d.scan_live_rows = 0;
             while (d.scan_live_rows < d.A && c->separable.a_star[(size_t)d.scan_live_rows] >= 0) d.scan_live_rows++;
             c->plan_scan = c->plan_dense;
@@ -640,6 +651,10 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         ldm::launch_sample_sum(d, ldm::SAMPLES_OUT_WEIGHT, c->d_C[0], out_weight, c->stream);
         c->launches += 1;
         LDM_CUDA(cudaGetLastError());
+        // the ring-correction operator of the unsharded problem, here rather than at the first step: callers create the
+        // entries of a sweep from several host threads, and this host-side build is most of an entry's set-up cost
+        // (ldm_shard_configure rebuilds it for the rank's rows)
+        if (std::getenv("LDM_LAZY_RING") == nullptr) ensure_ring_operator(c.get());
         LDM_CUDA(cudaStreamSynchronize(c->stream));
         *out = c.release();
     });
@@ -881,6 +896,100 @@ int ldm_last_elapsed_ms(ldm_handle h, float* ms)
 
 long long ldm_launch_count(ldm_handle h) { return h ? h->launches : 0; }
 
+}  // extern "C"
+
+namespace {
+
+// The members of a batch that live on ONE device: all parameter sets of one CTA shape advance in one launch per kernel
+// (blockIdx.z is the set).  Runs (points - 1) Euler steps and returns when the device is done.
+void advance_batch_on_device(const std::vector<ldm_context*>& handles, int points, double dt)
+{
+    const int n = (int)handles.size();
+    if (n == 0) return;
+        // All parameter sets of one tile shape advance in ONE launch per kernel: blockIdx.z is the set.
+        ldm_context* lead = handles[0];   // all on one device
+        LDM_CUDA(cudaSetDevice(lead->device));
+        struct Group {
+            ldm::FactoredPlan shape;
+            std::vector<int> members;
+            int max_slabs = 0, max_rows = 0, max_G = 0, max_A = 0, max_ring = 0, max_points = 0;
+            size_t max_smem = 0;     // prefix-sum groups: the largest member's shared memory
+            int scan_nt = 512;
+            ldm::StepArgs* d_args[2] = {nullptr, nullptr};
+        };
+        std::vector<Group> groups;
+        for (int i = 0; i < n; i++) {
+            ldm_context* h = handles[i];
+            ensure_ring_operator(h);
+            if (h->plan.use_w) ensure_w_operand(h);
+            Group* g = nullptr;
+            for (Group& cand : groups)
+                if ((cand.shape.scan && h->plan.scan && cand.scan_nt == h->dev.scan_nt) ||   // the prefix-sum kernel takes its tile shape at run time
+                    (!cand.shape.scan && !h->plan.scan && cand.shape.bm == h->plan.bm && cand.shape.bn == h->plan.bn &&
+                     cand.shape.tn == h->plan.tn && cand.shape.mma == h->plan.mma && cand.shape.use_w == h->plan.use_w)) g = &cand;
+            if (!g) { groups.emplace_back(); g = &groups.back(); g->shape = h->plan; g->scan_nt = h->dev.scan_nt; }
+            g->members.push_back(i);
+            g->max_slabs = std::max(g->max_slabs, h->plan.slabs());
+            g->max_rows = std::max(g->max_rows, h->dev.G);
+            g->max_G = std::max(g->max_G, h->dev.G);
+            g->max_A = std::max(g->max_A, h->dev.A);
+            g->max_ring = std::max(g->max_ring, h->dev.n_ring);
+            g->max_points = std::max(g->max_points, h->dev.G * h->dev.G);
+            if (h->plan.scan) g->max_smem = std::max(g->max_smem, ldm::scan_smem_bytes(h->dev.G, h->dev.A, h->dev.scan_bn, h->dev.scan_nt, h->dev.scan_max_pieces));
+        }
+        std::vector<void*> scratch;
+        try {
+            for (Group& g : groups)
+                for (int parity = 0; parity < 2; parity++) {
+                    std::vector<ldm::StepArgs> host;
+                    for (int i : g.members) {
+                        ldm_context* h = handles[i];
+                        host.push_back(make_step_args(h, h->d_C[parity], h->d_N + parity, h->d_N + (parity ^ 1), dt, nullptr, nullptr,
+                                                      h->d_C[parity ^ 1]));
+                    }
+                    void* p = nullptr;
+                    LDM_CUDA(cudaMalloc(&p, host.size() * sizeof(ldm::StepArgs)));
+                    scratch.push_back(p);
+                    LDM_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(ldm::StepArgs), cudaMemcpyHostToDevice));
+                    g.d_args[parity] = static_cast<ldm::StepArgs*>(p);
+                }
+            cudaStream_t s = lead->stream;
+            LDM_CUDA(cudaEventRecord(lead->ev_begin, s));
+            int parity = 0;
+            for (int k = 0; k + 1 < points; k++) {
+                for (Group& g : groups) {
+                    const int members = (int)g.members.size();
+                    const bool side = g.max_ring > 0;
+                    if (side) {
+                        LDM_CUDA(cudaEventRecord(lead->ev_fork, s));
+                        LDM_CUDA(cudaStreamWaitEvent(lead->aux_stream, lead->ev_fork, 0));
+                        ldm::launch_ring_batch(g.d_args[parity], members, g.max_ring, lead->aux_stream);
+                        LDM_CUDA(cudaEventRecord(lead->ev_join, lead->aux_stream));
+                    }
+                    if (g.shape.scan) ldm::launch_scan_batch(g.d_args[parity], members, g.scan_nt, g.max_slabs, g.max_rows, g.max_smem, s);
+                    else if (g.shape.use_w) ldm::launch_factored_w_batch(g.shape, g.d_args[parity], members, g.max_slabs, g.max_rows, g.max_G, s);
+                    else ldm::launch_factored_batch(g.shape, g.d_args[parity], members, g.max_slabs, g.max_rows, g.max_G, g.max_A, s);
+                    if (side) LDM_CUDA(cudaStreamWaitEvent(s, lead->ev_join, 0));
+                    ldm::launch_finish_factored_batch(g.d_args[parity], members, g.max_points, s);
+                    lead->launches += 2 + (side ? 1 : 0);
+                }
+                parity ^= 1;
+            }
+            LDM_CUDA(cudaEventRecord(lead->ev_end, s));
+            LDM_CUDA(cudaGetLastError());
+            LDM_CUDA(cudaStreamSynchronize(s));
+            for (int i = 0; i < n; i++) handles[i]->cur = parity;
+        } catch (...) {
+            for (void* p : scratch) cudaFree(p);
+            throw;
+        }
+        for (void* p : scratch) cudaFree(p);
+}
+
+}  // namespace
+
+extern "C" {
+
 int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits, double dt, double t_max,
                     double* const* last_states)
 {
@@ -888,104 +997,47 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
     if (!(dt > 0)) return fail(LDM_ERR_ARGUMENT, "step must be positive");
     return guarded([&] {
         const int points = ldm_count_points(t_max, dt);
-        bool one_launch = n > 0;
+        bool batched = n > 0;
         for (int i = 0; i < n; i++) {
             if (!handles[i] || !inits[i] || !last_states[i]) throw std::invalid_argument("NULL entry in batch");
             ldm_context* h = handles[i];
             LDM_CUDA(cudaSetDevice(h->device));
             upload_state(h, inits[i]);
-            one_launch = one_launch && h->algo != LDM_ALGO_DIRECT && h->device == handles[0]->device && h->dev.world == 1;
+            batched = batched && h->algo != LDM_ALGO_DIRECT && h->dev.world == 1;
         }
         for (int i = 0; i < n; i++) {
             LDM_CUDA(cudaSetDevice(handles[i]->device));
             LDM_CUDA(cudaStreamSynchronize(handles[i]->stream));
         }
-        if (!one_launch) {
-            // mixed devices / algorithms: every parameter set advances on its own stream
+        if (!batched) {
+            // sample-by-sample algorithm or sharded handles: every parameter set advances on its own stream
             for (int k = 0; k + 1 < points; k++)
                 for (int i = 0; i < n; i++) {
                     LDM_CUDA(cudaSetDevice(handles[i]->device));
                     step_resident(handles[i], dt, nullptr);
                 }
         } else {
-            // All parameter sets of one tile shape advance in ONE launch per kernel: blockIdx.z is the set.
-            ldm_context* lead = handles[0];
-            LDM_CUDA(cudaSetDevice(lead->device));
-            struct Group {
-                ldm::FactoredPlan shape;
-                std::vector<int> members;
-                int max_slabs = 0, max_rows = 0, max_G = 0, max_A = 0, max_ring = 0, max_points = 0;
-                size_t max_smem = 0;     // prefix-sum groups: the largest member's shared memory
-                int scan_nt = 512;
-                ldm::StepArgs* d_args[2] = {nullptr, nullptr};
-            };
-            std::vector<Group> groups;
+            // one slice of the batch per device (the caller decides which set lives where, ldm_create's device argument);
+            // the devices advance concurrently, one host thread each
+            std::vector<std::pair<int, std::vector<ldm_context*>>> per_device;
             for (int i = 0; i < n; i++) {
-                ldm_context* h = handles[i];
-                ensure_ring_operator(h);
-                if (h->plan.use_w) ensure_w_operand(h);
-                Group* g = nullptr;
-                for (Group& cand : groups)
-                    if ((cand.shape.scan && h->plan.scan && cand.scan_nt == h->dev.scan_nt) ||   // the prefix-sum kernel takes its tile shape at run time
-                        (!cand.shape.scan && !h->plan.scan && cand.shape.bm == h->plan.bm && cand.shape.bn == h->plan.bn &&
-                         cand.shape.tn == h->plan.tn && cand.shape.mma == h->plan.mma && cand.shape.use_w == h->plan.use_w)) g = &cand;
-                if (!g) { groups.emplace_back(); g = &groups.back(); g->shape = h->plan; g->scan_nt = h->dev.scan_nt; }
-                g->members.push_back(i);
-                g->max_slabs = std::max(g->max_slabs, h->plan.slabs());
-                g->max_rows = std::max(g->max_rows, h->dev.G);
-                g->max_G = std::max(g->max_G, h->dev.G);
-                g->max_A = std::max(g->max_A, h->dev.A);
-                g->max_ring = std::max(g->max_ring, h->dev.n_ring);
-                g->max_points = std::max(g->max_points, h->dev.G * h->dev.G);
-                if (h->plan.scan) g->max_smem = std::max(g->max_smem, ldm::scan_smem_bytes(h->dev.G, h->dev.A, h->dev.scan_bn, h->dev.scan_nt, h->dev.scan_max_pieces));
+                auto it = std::find_if(per_device.begin(), per_device.end(), [&](const auto& e) { return e.first == handles[i]->device; });
+                if (it == per_device.end()) { per_device.emplace_back(handles[i]->device, std::vector<ldm_context*>()); it = per_device.end() - 1; }
+                it->second.push_back(handles[i]);
             }
-            std::vector<void*> scratch;
-            try {
-                for (Group& g : groups)
-                    for (int parity = 0; parity < 2; parity++) {
-                        std::vector<ldm::StepArgs> host;
-                        for (int i : g.members) {
-                            ldm_context* h = handles[i];
-                            host.push_back(make_step_args(h, h->d_C[parity], h->d_N + parity, h->d_N + (parity ^ 1), dt, nullptr, nullptr,
-                                                          h->d_C[parity ^ 1]));
-                        }
-                        void* p = nullptr;
-                        LDM_CUDA(cudaMalloc(&p, host.size() * sizeof(ldm::StepArgs)));
-                        scratch.push_back(p);
-                        LDM_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(ldm::StepArgs), cudaMemcpyHostToDevice));
-                        g.d_args[parity] = static_cast<ldm::StepArgs*>(p);
-                    }
-                cudaStream_t s = lead->stream;
-                LDM_CUDA(cudaEventRecord(lead->ev_begin, s));
-                int parity = 0;
-                for (int k = 0; k + 1 < points; k++) {
-                    for (Group& g : groups) {
-                        const int members = (int)g.members.size();
-                        const bool side = g.max_ring > 0;
-                        if (side) {
-                            LDM_CUDA(cudaEventRecord(lead->ev_fork, s));
-                            LDM_CUDA(cudaStreamWaitEvent(lead->aux_stream, lead->ev_fork, 0));
-                            ldm::launch_ring_batch(g.d_args[parity], members, g.max_ring, lead->aux_stream);
-                            LDM_CUDA(cudaEventRecord(lead->ev_join, lead->aux_stream));
-                        }
-                        if (g.shape.scan) ldm::launch_scan_batch(g.d_args[parity], members, g.scan_nt, g.max_slabs, g.max_rows, g.max_smem, s);
-                        else if (g.shape.use_w) ldm::launch_factored_w_batch(g.shape, g.d_args[parity], members, g.max_slabs, g.max_rows, g.max_G, s);
-                        else ldm::launch_factored_batch(g.shape, g.d_args[parity], members, g.max_slabs, g.max_rows, g.max_G, g.max_A, s);
-                        if (side) LDM_CUDA(cudaStreamWaitEvent(s, lead->ev_join, 0));
-                        ldm::launch_finish_factored_batch(g.d_args[parity], members, g.max_points, s);
-                        lead->launches += 2 + (side ? 1 : 0);
-                    }
-                    parity ^= 1;
-                }
-                LDM_CUDA(cudaEventRecord(lead->ev_end, s));
-                LDM_CUDA(cudaGetLastError());
-                LDM_CUDA(cudaStreamSynchronize(s));
-                for (int i = 0; i < n; i++) handles[i]->cur = parity;
-            } catch (...) {
-                for (void* p : scratch) cudaFree(p);
-                throw;
+            if (per_device.size() == 1) {
+                advance_batch_on_device(per_device[0].second, points, dt);
+            } else {
+                std::vector<std::string> errors(per_device.size());
+                std::vector<std::thread> workers;
+                for (size_t d = 0; d < per_device.size(); d++)
+                    workers.emplace_back([&, d] {
+                        try { advance_batch_on_device(per_device[d].second, points, dt); }
+                        catch (const std::exception& e) { errors[d] = e.what(); if (errors[d].empty()) errors[d] = "error"; }
+                    });
+                for (std::thread& w : workers) w.join();
+                for (const std::string& e : errors) if (!e.empty()) throw CudaError(e);
             }
-            for (void* p : scratch) cudaFree(p);
         }
         for (int i = 0; i < n; i++) {
             ldm_context* h = handles[i];
@@ -999,6 +1051,12 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
             LDM_CUDA(cudaStreamSynchronize(handles[i]->stream));
         }
     });
+}
+
+int ldm_device_count(void)
+{
+    int count = 0;
+    return cudaGetDeviceCount(&count) == cudaSuccess ? count : 0;
 }
 
 int ldm_shard_configure(ldm_handle h, int rank, int world)

@@ -41,6 +41,7 @@ struct DevProblem {
     const int* scan_chunk_begin;   // [scan_chunks + 1] first piece of each chunk
     const int* scan_warp_begin;    // [scan_chunks][scan_nt / 32 + 1] relative to the chunk's first piece
     const int* scan_block_begin;   // [scan_chunks][ceil(G/32) + 1] relative to the chunk's first piece
+    const int* scan_chunk_order;   // [scan_chunks] chunks by descending y-side work (the order the CTAs are issued in)
     int scan_max_pieces;
     int scan_bn, scan_chunks;  // column chunk width (multiple of 32) and count
     int scan_live_rows;        // rows beta < scan_live_rows have a_star >= 0; the rest of the table is empty

@@ -319,9 +319,11 @@ template <bool BATCH, bool SMALL>
 __global__ void __launch_bounds__(SMALL ? 256 : kScanThreadsMax, SMALL ? 4 : 1)
 scan_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
 {
+    // grid = (rows, chunks): the CTAs are issued chunk by chunk, most expensive chunk first (on a stretched grid the far
+    // chunks own twice the y-side pairs of the near ones), so the tail of the launch is filled with the cheap ones
     const StepArgs& S = BATCH ? batch[blockIdx.z] : one;
-    if (BATCH && ((int)blockIdx.x >= S.P.scan_chunks || (int)blockIdx.y >= local_rows(S.P))) return;   // batch grids are padded
-    scan_body<scan_unroll(SMALL ? 256 : kScanThreadsMax)>(S, blockIdx.x, blockIdx.y, true, -1);
+    if (BATCH && ((int)blockIdx.y >= S.P.scan_chunks || (int)blockIdx.x >= local_rows(S.P))) return;   // batch grids are padded
+    scan_body<scan_unroll(SMALL ? 256 : kScanThreadsMax)>(S, S.P.scan_chunk_order[blockIdx.y], blockIdx.x, true, -1);
 }
 
 // Spin until *counter >= target: relaxed polls (an acquire load in the loop would pay for its fence on every poll), then
@@ -545,14 +547,14 @@ static void launch_scan_variant(const StepArgs* one, const StepArgs* d_batch, di
 void launch_scan(const StepArgs& one, cudaStream_t stream)
 {
     const DevProblem& P = one.P;
-    launch_scan_variant<false>(&one, nullptr, dim3(P.scan_chunks, local_rows(P), 1), P.scan_nt,
+    launch_scan_variant<false>(&one, nullptr, dim3(local_rows(P), P.scan_chunks, 1), P.scan_nt,
                                scan_smem_bytes(P.G, P.A, P.scan_bn, P.scan_nt, P.scan_max_pieces), stream);
 }
 
 // every member of a batch launch shares the CTA shape nt (= ng * bn); shared memory is sized for the largest member
 void launch_scan_batch(const StepArgs* d_batch, int n, int nt, int max_chunks, int max_rows, size_t max_smem, cudaStream_t stream)
 {
-    launch_scan_variant<true>(nullptr, d_batch, dim3(max_chunks, max_rows, n), nt, max_smem, stream);
+    launch_scan_variant<true>(nullptr, d_batch, dim3(max_rows, max_chunks, n), nt, max_smem, stream);
 }
 
 // the same CTA shape as the one-launch-per-step kernel of this problem: the summation order follows the shape, and the

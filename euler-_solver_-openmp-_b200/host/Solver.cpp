@@ -21,7 +21,9 @@
 #include <memory>
 #include <sstream>
 #include <stdexcept>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/ldm.h"
@@ -106,10 +108,10 @@ class Equation
     std::shared_ptr<ldm_context> handle;     // copies of an Equation share one device context
 
 public:
-    Equation(Properties p) : props(p)
+    Equation(Properties p, int device = 0) : props(p)
     {
         ldm_handle h = nullptr;
-        ldm_require(ldm_create(props.flat.get(), 0, &h), "ldm_create");
+        ldm_require(ldm_create(props.flat.get(), device, &h), "ldm_create");
         handle = std::shared_ptr<ldm_context>(h, ldm_destroy);
     }
 
@@ -410,6 +412,41 @@ public:
         single_solve_experiment("14.4", std::string("(") + files[input_data] + ")");
     }
 
+    // devices the sweep may use: all visible ones, or LDM_GPUS of them
+    static int gpu_count()
+    {
+        int count = std::max(1, ldm_device_count());
+        if (const char* env = std::getenv("LDM_GPUS")) count = std::max(1, std::min(count, std::atoi(env)));
+        return count;
+    }
+
+    // cost of one Euler step of an entry ~ G^2 * (quadrature offsets per axis): both phases of the kernel walk that many
+    // (node, offset) pairs per row.  Longest-processing-time-first onto the least loaded device.
+    static std::vector<int> assign_devices(const std::vector<Properties>& props, int devices)
+    {
+        const int n = (int)props.size();
+        std::vector<double> cost((size_t)n);
+        std::vector<int> order((size_t)n), device_of((size_t)n, 0);
+        for (int i = 0; i < n; i++) {
+            const ldm_problem& f = *props[(size_t)i].flat;
+            cost[(size_t)i] = (double)f.G * f.G * std::max(1, f.mM - 1) + 2000.0;     // + a floor for launch-bound entries
+            order[(size_t)i] = i;
+        }
+        std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return cost[(size_t)a] > cost[(size_t)b]; });
+        std::vector<double> load((size_t)devices, 0.0);
+        for (int i : order) {
+            const int d = (int)(std::min_element(load.begin(), load.end()) - load.begin());
+            device_of[(size_t)i] = d;
+            load[(size_t)d] += cost[(size_t)i];
+        }
+        if (devices > 1) {
+            std::cout << "sweep over " << devices << " devices, estimated load per device:";
+            for (double l : load) std::cout << ' ' << l / 1e6;
+            std::cout << " (1e6 pair-steps)\n";
+        }
+        return device_of;
+    }
+
     // Experiment_14_6 (S:1033-1071) over CalculateWithVaryingSigma (S:909-977): 160 independent solves of 2001 points.
     void Experiment_14_6(char SigmaType, std::string RadiusType)
     {
@@ -418,16 +455,29 @@ public:
         Vector SigmaVec = Vector::setLinSpaced(160, EPSILON, 0.2);                       // S:1042
 
         PropsVector.clear();
-        std::vector<Equation> equations;
         for (int i = 0; i < SigmaVec.size(); i++) {
             FileReader Reader(reader_file_path);
             std::cout << "ENTRY " << i << ":\n";
             PropsVector.push_back(SigmaType == 'W' ? Reader.GetWithoutSigmaW(SigmaVec[i], true) : Reader.GetWithoutSigmaM(SigmaVec[i], true));
-            equations.emplace_back(PropsVector.back());
         }
         std::cout << "\n==========================CALCULATIONS START==========================\n";
         const auto start = std::chrono::steady_clock::now();
-        const int n = (int)equations.size();
+        const int n = (int)PropsVector.size();
+        // Where the reference hands the entries to OpenMP threads in index order (static schedule: the twelve refined-grid
+        // entries, 100x the cost of the others, all land on thread 0), the entries are dealt out over the visible GPUs by
+        // estimated cost, largest first onto the least loaded device; each device then advances its slice as one batch.
+        const std::vector<int> device_of = assign_devices(PropsVector, gpu_count());
+        std::vector<Equation> equations;
+        {
+            std::vector<std::unique_ptr<Equation>> built((size_t)n);
+            std::vector<std::thread> workers;
+            const int n_workers = std::min(8, std::max(1, n));
+            for (int w = 0; w < n_workers; w++)
+                workers.emplace_back([&, w] { for (int i = w; i < n; i += n_workers) built[(size_t)i].reset(new Equation(PropsVector[(size_t)i], device_of[(size_t)i])); });
+            for (std::thread& t : workers) t.join();
+            for (int i = 0; i < n; i++) equations.push_back(*built[(size_t)i]);
+        }
+        const double setup_seconds = seconds_since(start);
         std::vector<Vector> inits, lasts;
         std::vector<ldm_handle> handles;
         std::vector<const double*> in_ptrs;
@@ -443,7 +493,9 @@ public:
         }
         ldm_require(ldm_solve_batch(n, handles.data(), in_ptrs.data(), 0.1, 200, out_ptrs.data()), "ldm_solve_batch");
         std::cout << "\n===========================CALCULATIONS END===========================\n";
-        std::cout << "TIME:  " << Time(seconds_since(start)) << '\n';
+        const double elapsed = seconds_since(start);
+        std::cout << "TIME:  " << Time(elapsed) << '\n';
+        std::cout << "SECONDS:  " << elapsed << "  (" << n << " entries; " << setup_seconds << " s of it setting the entries up on the device)\n";
 
         Vector ConvergedN, ConvergedCSquareRoot;
         for (int i = 0; i < n; i++) {

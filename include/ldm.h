@@ -102,7 +102,10 @@ int  ldm_last_elapsed_ms(ldm_handle h, float* ms);
 long long ldm_launch_count(ldm_handle h);
 
 /* ---- the sigma-sweep loop Experiments::CalculateWithVaryingSigma (S:940-963): n independent solves,
- * results slot-indexed (no shared push_back).  last_states[i] receives 1+G_i*G_i doubles. ---- */
+ * results slot-indexed (no shared push_back).  last_states[i] receives 1+G_i*G_i doubles.  The handles may live on
+ * several devices (ldm_create's device argument): every device advances its slice of the batch concurrently, one
+ * launch per kernel and step for all of its sets; ldm_device_count() = visible devices (0 without CUDA). ---- */
+int  ldm_device_count(void);
 int  ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits, double dt, double t_max,
                      double* const* last_states);
 

@@ -173,6 +173,27 @@ def test_batch_of_parameter_sets(ldm, algorithm):
         assert_states_close(got, want)
 
 
+def test_batch_spread_over_two_devices(ldm):
+    """the sweep with its entries living on two GPUs (ldm_create's device argument): every device advances its slice
+    concurrently; same bits as the same entries on one device"""
+    if ldm.library().ldm_device_count() < 2:
+        pytest.skip("needs two GPUs")
+    names = ["exp_14_6_a_012", "exp_14_6_b_040", "exp_14_6_a_080", "exp_14_6_b_012", "exp_14_6_a_159"]
+    runs = []
+    for devices in ([0] * len(names), [0, 1, 1, 0, 1]):
+        eqs, inits = [], []
+        for name, device in zip(names, devices):
+            g = golden(name)
+            props, _ = problems_from(g, name, ldm)
+            eq = ldm.Equation(props, device=device)
+            eqs.append(eq)
+            inits.append(eq.GenerateEquilibriumValuesForNAndC(200))
+        runs.append(ldm.solve_batch(eqs, inits, 0.1, 200))
+    for name, one, two in zip(names, *runs):
+        assert np.array_equal(one, two)
+        assert_states_close(two, golden(name)["final_state"])
+
+
 @pytest.mark.parametrize("world", [2, 3, 5, 7])
 def test_sharded_step_emulated_on_one_device(ldm, world):
     """xi-sharding with all ranks emulated on one GPU: each rank updates its rows of C from the
