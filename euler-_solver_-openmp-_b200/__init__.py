@@ -18,7 +18,8 @@ LIBRARY_PATH = os.environ.get("LDM_LIBRARY", os.path.join(_HERE, "libldm_b200.so
 ALGO_AUTO, ALGO_DIRECT, ALGO_FACTORED, ALGO_PREFIX = 0, 1, 2, 3
 RECORD_LAST, RECORD_OBSERVABLES, RECORD_VALUES, RECORD_ALL = 0, 1, 2, 3
 
-# enum ExtrapolationType (Solver.cpp:28); only SquaredN is reachable for C on any experiment route
+# enum ExtrapolationType (Solver.cpp:28); every experiment passes SquaredN for C; Zero and Alpha are built to the letter
+# of the reference, Exponential is not (ldm.h)
 Zero, SquaredN, Alpha, Exponential = 0, 1, 2, 3
 
 
@@ -47,6 +48,9 @@ _SIGNATURES = {
     "ldm_destroy": (None, [C.c_void_p]),
     "ldm_set_algorithm": (C.c_int, [C.c_void_p, C.c_int]),
     "ldm_get_algorithm": (C.c_int, [C.c_void_p]),
+    "ldm_set_extrapolation": (C.c_int, [C.c_void_p, C.c_int]),
+    "ldm_count_points_rk4": (C.c_int, [C.c_double, C.c_double]),
+    "ldm_solve_rk4": (C.c_int, [C.c_void_p, _dp, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "ldm_rhs": (C.c_int, [C.c_void_p, _dp, _dp]),
     "ldm_integrals": (C.c_int, [C.c_void_p, _dp, C.POINTER(C.c_double), C.c_void_p]),
     "ldm_kernels_at_nodes": (C.c_int, [C.c_void_p, _dp, _dp]),
@@ -179,9 +183,12 @@ class Equation:
         st[0] = value
         return st
 
+    def set_extrapolation(self, chosen_type):
+        """the ExtrapolationType the equation is evaluated with from here on (Solver.cpp:431: chosen_type)"""
+        _check(library().ldm_set_extrapolation(self._h, int(chosen_type)))
+
     def __call__(self, times, vals, chosen_type=SquaredN):
-        if chosen_type != SquaredN:
-            raise LdmError("only SquaredN extrapolation is reachable in the reference's experiments")
+        self.set_extrapolation(chosen_type)
         vals = np.ascontiguousarray(vals, dtype=np.float64)
         assert vals.size == self.props.state_size          # Solver.cpp:260 / types.h:782
         out = np.empty_like(vals)
@@ -253,9 +260,8 @@ class EulerSolver:
 
     def Solve(self, current_equation, type, time_max, step, initial_value, debug_print_enabled=False,
               record=RECORD_ALL):
-        if type != SquaredN:
-            raise LdmError("only SquaredN extrapolation is reachable in the reference's experiments")
         eq = current_equation
+        eq.set_extrapolation(type)
         init = np.ascontiguousarray(initial_value, dtype=np.float64)
         assert init.size == eq.props.state_size
         n = count_points(time_max, step)
@@ -279,6 +285,26 @@ class EulerSolver:
             for k in range(len(col)):
                 print(f"   t = {times[k]:g};   N = {col[k]:g}")
         return SolverResults(times, values, derivs, obs)
+
+
+class RungeKutta4thSolver:
+    """class RungeKutta4thSolver (Solver.cpp:597-654): in the reference, instantiated by none of its experiments"""
+
+    def Solve(self, current_equation, type, time_max, step, initial_value, debug_print_enabled=False):
+        eq = current_equation
+        eq.set_extrapolation(type)
+        init = np.ascontiguousarray(initial_value, dtype=np.float64)
+        assert init.size == eq.props.state_size
+        n = int(library().ldm_count_points_rk4(float(time_max), float(step)))
+        times, values, derivs = np.empty(n), np.empty((n, init.size)), np.empty((n, init.size))
+        got = C.c_int()
+        _check(library().ldm_solve_rk4(eq._h, init, float(step), float(time_max), times.ctypes.data, values.ctypes.data,
+                                       derivs.ctypes.data, C.byref(got)))
+        assert got.value == n
+        if debug_print_enabled:
+            for k in range(n):
+                print(f"   t = {times[k]:g};   N = {values[k, 0]:g}")
+        return SolverResults(times, values, derivs)
 
 
 def solve_batch(equations, inits, step, time_max):

@@ -2,6 +2,7 @@
 // S:n = "/root/reference/Euler Solver ver.5.3/Solver.cpp" line n.
 #include <cuda_runtime.h>
 
+#include <cmath>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -560,6 +561,7 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         DevProblem& d = c->dev;
         d.G = t.G; d.n_off = t.offM.n_off; d.A = t.offM.A;
         d.world = 1; d.rank = 0; d.rows_per_rank = t.G;
+        d.extrapolation = LDM_EXTRAPOLATION_SQUARED_N;
         d.hh = t.hh; d.b = t.b; d.d = t.d; d.dd = t.dd; d.s_max = t.s_max; d.wc_outside = t.wc_outside;
         d.s = c->upload(t.axisM.s);
         d.limit = c->upload(t.axisM.limit);
@@ -679,6 +681,100 @@ int ldm_set_algorithm(ldm_handle h, int algo)
 
 int ldm_get_algorithm(ldm_handle h) { return h ? h->algo : LDM_ERR_ARGUMENT; }
 
+int ldm_set_extrapolation(ldm_handle h, int type)
+{
+    if (!h) return fail(LDM_ERR_ARGUMENT, "NULL handle");
+    if (type == LDM_EXTRAPOLATION_EXPONENTIAL)
+        return fail(LDM_ERR_UNSUPPORTED, "Exponential extrapolation (Solver.cpp:392-408) is reachable from no experiment of the reference and is not built");
+    if (type != LDM_EXTRAPOLATION_ZERO && type != LDM_EXTRAPOLATION_SQUARED_N && type != LDM_EXTRAPOLATION_ALPHA)
+        return fail(LDM_ERR_ARGUMENT, "unknown extrapolation type");
+    h->dev.extrapolation = type;
+    return LDM_OK;
+}
+
+int ldm_count_points_rk4(double t_max, double dt)
+{
+    if (!(dt > 0)) return 1;
+    int n = 1;
+    double time = 0;
+    while (time < t_max) { time += dt / 2; time += dt / 2; n++; }      // S:627-635
+    return n;
+}
+
+int ldm_solve_rk4(ldm_handle h, const double* init, double dt, double t_max, double* times, double* values, double* derivs, int* n_points)
+{
+    if (!h || !init) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    if (!(dt > 0)) return fail(LDM_ERR_ARGUMENT, "step must be positive");
+    if (h->dev.world != 1) return fail(LDM_ERR_UNSUPPORTED, "the Runge-Kutta solver runs on one rank");
+    return guarded([&] {
+        LDM_CUDA(cudaSetDevice(h->device));
+        const int n = ldm_count_points_rk4(t_max, dt);
+        const size_t P = h->P(), width = 1 + P;
+        if (n_points) *n_points = n;
+        if (times) {
+            double time = 0;
+            for (int k = 0; k < n; k++) { times[k] = time; if (k + 1 < n) { time += dt / 2; time += dt / 2; } }
+        }
+        // device: the value [N | C], one stage state, four derivatives -- each laid out like the reference's Vector
+        std::vector<void*> scratch;
+        auto scratch_alloc = [&](size_t count) {
+            void* p = nullptr;
+            LDM_CUDA(cudaMalloc(&p, count * sizeof(double)));
+            scratch.push_back(p);
+            return static_cast<double*>(p);
+        };
+        try {
+            double* value[2] = {scratch_alloc(width), scratch_alloc(width)};
+            double* stage = scratch_alloc(width);
+            double* c[4] = {scratch_alloc(width), scratch_alloc(width), scratch_alloc(width), scratch_alloc(width)};
+            double* d_values = values ? scratch_alloc((size_t)n * width) : nullptr;
+            double* d_derivs = derivs ? scratch_alloc((size_t)n * width) : nullptr;
+            cudaStream_t s = h->stream;
+            LDM_CUDA(cudaMemcpyAsync(value[0], init, width * sizeof(double), cudaMemcpyHostToDevice, s));
+            // Equation::operator() at a device state [N | C]: dC straight into out + 1, dN from the step scalars
+            auto rhs = [&](const double* state, double* out) {
+                rhs_and_update(h, h->dev, state + 1, state, nullptr, 0.0, nullptr, out + 1, nullptr, s);
+                LDM_CUDA(cudaMemcpyAsync(out, h->d_scalars + 1, sizeof(double), cudaMemcpyDeviceToDevice, s));
+            };
+            LDM_CUDA(cudaEventRecord(h->ev_begin, s));
+            int cur = 0;
+            for (int k = 0; k + 1 < n; k++) {
+                if (d_values) LDM_CUDA(cudaMemcpyAsync(d_values + (size_t)k * width, value[cur], width * sizeof(double), cudaMemcpyDeviceToDevice, s));
+                rhs(value[cur], c[0]);                                                               // S:629, S:631
+                if (d_derivs) LDM_CUDA(cudaMemcpyAsync(d_derivs + (size_t)k * width, c[0], width * sizeof(double), cudaMemcpyDeviceToDevice, s));
+                ldm::launch_rk4_stage((int)width, value[cur], c[0], dt, 2.0, stage, s);              // S:633
+                rhs(stage, c[1]);
+                ldm::launch_rk4_stage((int)width, value[cur], c[1], dt, 2.0, stage, s);              // S:634
+                rhs(stage, c[2]);
+                ldm::launch_rk4_stage((int)width, value[cur], c[2], dt, 1.0, stage, s);              // S:636
+                rhs(stage, c[3]);
+                ldm::launch_rk4_close((int)width, value[cur], c[0], c[1], c[2], c[3], dt, value[cur ^ 1], s);   // S:637-645
+                h->launches += 4;
+                cur ^= 1;
+            }
+            if (d_values) LDM_CUDA(cudaMemcpyAsync(d_values + (size_t)(n - 1) * width, value[cur], width * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            if (d_derivs) {
+                rhs(value[cur], c[0]);                                                               // S:652
+                LDM_CUDA(cudaMemcpyAsync(d_derivs + (size_t)(n - 1) * width, c[0], width * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            }
+            LDM_CUDA(cudaEventRecord(h->ev_end, s));
+            LDM_CUDA(cudaGetLastError());
+            // the handle's resident state follows the solve
+            LDM_CUDA(cudaMemcpyAsync(h->d_N, value[cur], sizeof(double), cudaMemcpyDeviceToDevice, s));
+            LDM_CUDA(cudaMemcpyAsync(h->d_C[0], value[cur] + 1, P * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            h->cur = 0;
+            if (values) LDM_CUDA(cudaMemcpyAsync(values, d_values, (size_t)n * width * sizeof(double), cudaMemcpyDeviceToHost, s));
+            if (derivs) LDM_CUDA(cudaMemcpyAsync(derivs, d_derivs, (size_t)n * width * sizeof(double), cudaMemcpyDeviceToHost, s));
+            LDM_CUDA(cudaStreamSynchronize(s));
+            LDM_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev_begin, h->ev_end));
+        } catch (...) {
+            for (void* p : scratch) cudaFree(p);
+            throw;
+        }
+        for (void* p : scratch) cudaFree(p);
+    });
+}
+
 int ldm_rhs(ldm_handle h, const double* state, double* deriv)
 {
     if (!h || !state || !deriv) return fail(LDM_ERR_ARGUMENT, "NULL argument");
@@ -711,8 +807,10 @@ int ldm_integrals(ldm_handle h, const double* state, double* WC, double* MC)
         if (MC) {   // the same closing expression as the pointwise kernel
             std::vector<double> ow(h->P());
             LDM_CUDA(cudaMemcpy(ow.data(), h->dev.out_weight, h->P() * sizeof(double), cudaMemcpyDeviceToHost));
-            const double N = state[0];
-            for (size_t q = 0; q < h->P(); q++) MC[q] = (sum[q] + (N * N) * ow[q]) * h->dev.hh;
+            const double N = state[0], asymptote = N * N, last = state[h->dev.G];        // outside_value() of ldm_pointwise.cuh
+            const double beyond = (h->dev.extrapolation == LDM_EXTRAPOLATION_SQUARED_N || std::fabs(last - asymptote) < 1e-8) ? asymptote
+                                  : h->dev.extrapolation == LDM_EXTRAPOLATION_ZERO ? 0.0 : state[1];
+            for (size_t q = 0; q < h->P(); q++) MC[q] = (sum[q] + beyond * ow[q]) * h->dev.hh;
         }
     });
 }

@@ -12,6 +12,7 @@ struct DevProblem {
     // xi-sharding: this rank computes rows x = rank, rank+world, ...; the full C is held in
     // "gathered" layout, row x at slot (x % world) * rows_per_rank + x / world.  world == 1: natural layout.
     int world, rank, rows_per_rank;
+    int extrapolation;         // ExtrapolationType of C beyond the cutoff (Solver.cpp:28): 0 Zero, 1 SquaredN (default), 2 Alpha
     double hh;                 // KernelsGridStep^2 (Solver.cpp:314)
     double b, d, dd;
     double s_max;              // largest sample abscissa that is still inside the moment grid
@@ -108,6 +109,12 @@ __host__ __device__ inline int local_rows(const DevProblem& P) { return (P.G - P
 // C is always the full pair density in gathered layout; `out`, inside_sum, deriv_out, C_next are
 // shard-local [local_rows][G].
 void launch_record_observables(const DevProblem& P, const double* N_cur, const double* C, double* obs_row, cudaStream_t stream);
+
+// RungeKutta4thSolver (Solver.cpp:597-654) on [N | C] state vectors of n doubles: out = value + (c * step / divisor);
+// out = clamp(value + ((c0 + c1*2 + c2*2 + c3) * step / 6))
+void launch_rk4_stage(int n, const double* value, const double* c, double step, double divisor, double* out, cudaStream_t stream);
+void launch_rk4_close(int n, const double* value, const double* c0, const double* c1, const double* c2, const double* c3, double step,
+                      double* out, cudaStream_t stream);
 
 void launch_sample_sum(const DevProblem& P, SampleMode mode, const double* C, double* out, cudaStream_t stream);
 

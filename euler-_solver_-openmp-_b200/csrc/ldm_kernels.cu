@@ -108,7 +108,7 @@ wc_kernel(DevProblem P, const double* __restrict__ C, const double* __restrict__
         v = warp_sum(v);
         if (threadIdx.x == 0) {
             const double N = N_cur[0];
-            const double WC = (v + (N * N) * P.wc_outside) * P.hh;                  // S:311, S:314
+            const double WC = (v + outside_value(P, N, C) * P.wc_outside) * P.hh;   // S:311, S:314
             double dN = __dmul_rn(N, __dsub_rn(P.b, P.d));                          // S:446
             dN = __dsub_rn(dN, __dadd_rn(0.0, __dmul_rn(P.dd, WC)));                // S:450-451
             scalars[0] = WC;
@@ -138,7 +138,7 @@ pointwise_kernel(DevProblem P, const double* __restrict__ C, const double* __res
     const double N = N_cur[0];
     const double WC = scalars[0];
     const double c = C[(size_t)(P.rank * P.rows_per_rank + lx) * P.G + y];
-    const double mc = (inside_sum[ql] + (N * N) * P.out_weight[q]) * P.hh;          // S:311, S:314
+    const double mc = (inside_sum[ql] + outside_value(P, N, C) * P.out_weight[q]) * P.hh;   // S:311, S:314
     const double dc = second_moment_rhs(P, mc, c, N, WC, P.m_nodes[q], P.w_nodes[q]);
     if (deriv_out) deriv_out[ql] = dc;
     if (C_next) {
@@ -202,7 +202,8 @@ finish_factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
     }
     __syncthreads();
     const double N = N_cur[0];
-    const double WC = (wc_shared + (N * N) * P.wc_outside) * P.hh;                  // S:311, S:314
+    const double beyond = outside_value(P, N, C);
+    const double WC = (wc_shared + beyond * P.wc_outside) * P.hh;                   // S:311, S:314
     if (threadIdx.x == 0 && blockIdx.x == 0) first_moment_update(P, N, WC, dt, scalars, N_next);
 
     const int n = local_rows(P) * G;
@@ -216,7 +217,7 @@ finish_factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
         if (sum_out) sum_out[ql] = inside;
         const size_t slot = (size_t)(P.rank * P.rows_per_rank + lx) * G + y;          // this node in the gathered layout
         const double c = C[slot];
-        const double mc = (inside + (N * N) * P.out_weight[q]) * P.hh;
+        const double mc = (inside + beyond * P.out_weight[q]) * P.hh;
         const double dc = second_moment_rhs(P, mc, c, N, WC, P.m_nodes[q], P.w_nodes[q]);
         if (deriv_out) deriv_out[ql] = dc;
         double v = __dadd_rn(c, __dmul_rn(dc, dt));
@@ -255,6 +256,33 @@ __global__ void peer_wait_kernel(const unsigned long long* flags, int world, uns
     atomicExch(status, 1 + r);
 }
 
+// ------------------------------------------------------------------------------------------------
+// RungeKutta4thSolver::Solve (S:597-654) on state vectors laid out like the reference's, [N | C]: the stage
+// states value + (c * step / divisor) (S:633-636) and the closing combination with its clamp (S:637-645), each
+// operation rounded separately as the reference's Vector operators do (T:186-265).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+rk4_stage_kernel(int n, const double* __restrict__ value, const double* __restrict__ c, double step, double divisor,
+                 double* __restrict__ out)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q < n) out[q] = __dadd_rn(value[q], __ddiv_rn(__dmul_rn(c[q], step), divisor));
+}
+
+__global__ void __launch_bounds__(256)
+rk4_close_kernel(int n, const double* __restrict__ value, const double* __restrict__ c0, const double* __restrict__ c1,
+                 const double* __restrict__ c2, const double* __restrict__ c3, double step, double* __restrict__ out)
+{
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    double c = c0[q];                                                   // S:637
+    c = __dadd_rn(c, __dmul_rn(c1[q], 2.0));                            // S:638
+    c = __dadd_rn(c, __dmul_rn(c2[q], 2.0));                            // S:639
+    c = __dadd_rn(c, c3[q]);                                            // S:640
+    const double v = __dadd_rn(value[q], __ddiv_rn(__dmul_rn(c, step), 6.0));   // S:641
+    out[q] = v < 0.0 ? 0.0 : v;                                         // S:643-645
+}
+
 __global__ void record_observables_kernel(DevProblem P, const double* __restrict__ N_cur, const double* __restrict__ C,
                                           double* __restrict__ obs_row)
 {
@@ -272,6 +300,17 @@ void launch_peer_wait(const unsigned long long* flags, int world, unsigned long 
 void launch_record_observables(const DevProblem& P, const double* N_cur, const double* C, double* obs_row, cudaStream_t stream)
 {
     record_observables_kernel<<<1, 1, 0, stream>>>(P, N_cur, C, obs_row);
+}
+
+void launch_rk4_stage(int n, const double* value, const double* c, double step, double divisor, double* out, cudaStream_t stream)
+{
+    rk4_stage_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, value, c, step, divisor, out);
+}
+
+void launch_rk4_close(int n, const double* value, const double* c0, const double* c1, const double* c2, const double* c3, double step,
+                      double* out, cudaStream_t stream)
+{
+    rk4_close_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, value, c0, c1, c2, c3, step, out);
 }
 
 void launch_ring(const StepArgs& one, cudaStream_t stream)

@@ -29,6 +29,18 @@ __device__ __forceinline__ double wc_total(const double* wc_rows, int G, int lan
     return warp_sum_fixed(s);
 }
 
+// What the pair density is taken to be beyond the cutoff (Extrapolation, S:355-389), per step: the asymptote N^2 whenever
+// C[0][G-1] is within 1e-8 of it (S:357) or the type is SquaredN (the only type any experiment passes); else 0 (Zero) or
+// C[0][0] (Alpha: `2 / (grid.size() + 1)` is an integer division in the reference, S:377, so its exponential smoothing
+// never moves off values[0][0]).  C: the full pair density (row 0 is slot 0 in every layout).
+__device__ __forceinline__ double outside_value(const DevProblem& P, double N, const double* C)
+{
+    const double asymptote = N * N;
+    if (P.extrapolation == 1) return asymptote;
+    if (fabs(C[P.G - 1] - asymptote) < 1e-8) return asymptote;
+    return P.extrapolation == 0 ? 0.0 : C[0];
+}
+
 // dN/dt (S:446-451) and the clamped Euler update of N (S:577-580); thread 0 of one CTA
 __device__ __forceinline__ void first_moment_update(const DevProblem& P, double N, double WC, double dt, double* scalars, double* N_next)
 {

@@ -439,7 +439,8 @@ persistent_scan_kernel(const PersistentArgs A)
             if (lane == 0) wc_shared = t;
         }
         __syncthreads();
-        const double WC = (wc_shared + (N * N) * P.wc_outside) * P.hh;             // Solver.cpp:311, 314
+        const double beyond = outside_value(P, N, S.C);
+        const double WC = (wc_shared + beyond * P.wc_outside) * P.hh;              // Solver.cpp:311, 314
         double* values_next = A.values ? A.values + (point + 1) * A.stride : nullptr;
         double* derivs_here = A.derivs ? A.derivs + point * A.stride : nullptr;
         if (x == 0 && tid == 0) {
@@ -449,7 +450,7 @@ persistent_scan_kernel(const PersistentArgs A)
         }
         if (closer) {
             const double inside = (0.0 + row_sum[tid]) - ring_v;
-            const double mc = (inside + (N * N) * ow) * P.hh;
+            const double mc = (inside + beyond * ow) * P.hh;
             const double dc = second_moment_rhs(P, mc, c_old, N, WC, mn, wn);
             double v = __dadd_rn(c_old, __dmul_rn(dc, S.dt));                      // Solver.cpp:577
             v = v < 0.0 ? 0.0 : v;                                                 // Solver.cpp:578-580

@@ -74,7 +74,18 @@ void ldm_destroy(ldm_handle h);
 int  ldm_set_algorithm(ldm_handle h, int algo);
 int  ldm_get_algorithm(ldm_handle h);                                /* the algorithm in force (never LDM_ALGO_AUTO) */
 
-/* ---- Equation::operator()(t, vals, SquaredN) (S:431-513): host state in, host derivative out ---- */
+/* ExtrapolationType (S:28) that Equation::operator() and the solvers are called with: what the pair density is taken
+ * to be beyond the cutoff (S:355-389).  Every experiment of the reference passes SquaredN (the default).  Zero and
+ * Alpha follow the reference to the letter -- including Alpha's integer division (S:377), which makes it C[0][0] -- and
+ * so does the asymptote test of S:357 that precedes them.  Exponential (S:392-408) depends on every sample's own
+ * distance through a decay rate that changes each step: LDM_ERR_UNSUPPORTED. */
+#define LDM_EXTRAPOLATION_ZERO        0
+#define LDM_EXTRAPOLATION_SQUARED_N   1
+#define LDM_EXTRAPOLATION_ALPHA       2
+#define LDM_EXTRAPOLATION_EXPONENTIAL 3
+int  ldm_set_extrapolation(ldm_handle h, int type);
+
+/* ---- Equation::operator()(t, vals, type) (S:431-513): host state in, host derivative out ---- */
 int  ldm_rhs(ldm_handle h, const double* state, double* deriv);
 /* the two integrals on their own (S:265-295): WC scalar, MC G*G (MC may be NULL) */
 int  ldm_integrals(ldm_handle h, const double* state, double* WC, double* MC);
@@ -90,6 +101,14 @@ int  ldm_kernels_at_nodes(ldm_handle h, double* m_at_nodes, double* w_at_nodes);
 int  ldm_count_points(double t_max, double dt);
 int  ldm_solve(ldm_handle h, const double* init, double dt, double t_max, int record,
                double* times, double* values, double* derivs, int* n_points);
+
+/* ---- RungeKutta4thSolver::Solve (S:597-654; present in the reference, instantiated by none of its experiments) on
+ * the same right-hand-side kernels.  ldm_count_points_rk4 reproduces its `while (time < time_max)` with two half
+ * steps of the clock per iteration (S:627-635).  Full history: times n_points, values and derivs (either may be NULL)
+ * n_points*(1+G*G).  Intermediate stages are not clamped, the closed step is (S:643-645). ---- */
+int  ldm_count_points_rk4(double t_max, double dt);
+int  ldm_solve_rk4(ldm_handle h, const double* init, double dt, double t_max, double* times, double* values, double* derivs,
+                   int* n_points);
 
 /* ---- device-resident stepping (state stays in HBM between calls) ---- */
 int  ldm_state_upload(ldm_handle h, const double* state);          /* 1+G*G doubles */

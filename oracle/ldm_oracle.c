@@ -125,13 +125,24 @@ void ldmo_free(ldmo_problem* p)
     free(p->moments_grid); free(p->kernels_grid); free(p->M); free(p->W); free(p);
 }
 
-/* Extrapolation (S:355-410), the two reachable modes */
+/* Extrapolation (S:355-410): Zero, SquaredN, and Alpha as the reference computes it -- `2 / (grid.size() + 1)` is an
+ * integer division (S:377), so alpha == 0, every predicted value equals values[0][0] and the result is values[0][0].
+ * Exponential (S:392-408) is not restated. */
 static double extrapolate(const double* values, int n, int type, double asymptotic_value)
 {
     if (fabs(values[n - 1] - asymptotic_value) < LDMO_EPSILON)            /* S:357: values[0].last() */
         return asymptotic_value;
+    if (type == 2) {                                                      /* Alpha, S:375-389 */
+        const double alpha = 2 / (n + 1);                                 /* integer division, as in the reference */
+        double predicted = values[0];
+        for (int k = 1; k < n; k++) predicted = alpha * values[k] + (1 - alpha) * predicted;
+        return alpha * asymptotic_value + (1 - alpha) * predicted;
+    }
     return type == 1 ? asymptotic_value : 0.0;                            /* SquaredN : Zero */
 }
+
+static int g_c_extrapolation = 1;                                         /* what Equation::operator() is called with */
+void ldmo_set_extrapolation(int type) { g_c_extrapolation = type; }
 
 double ldmo_bilinear(const double* grid, int n, const double* values, double x, double y,
                      double max_distance, int extrapolation, double asymptotic_value)
@@ -163,7 +174,7 @@ double ldmo_pair_integral(const ldmo_problem* p, int x_shift, int y_shift, int m
         for (int j = 1 - max_non_zero_num; j < max_non_zero_num - 1; j += 2) {   /* S:302 */
             const double sum_x = fabs(mg[x_shift] + (i >= 0 ? kg[i + 1] : -kg[-i - 1]));   /* S:307 */
             const double sum_y = fabs(mg[y_shift] + (j >= 0 ? kg[j + 1] : -kg[-j - 1]));   /* S:308 */
-            double pair_density = ldmo_bilinear(mg, p->G, C, sum_x, sum_y, p->cutoff, 1, asymptotic_value);
+            double pair_density = ldmo_bilinear(mg, p->G, C, sum_x, sum_y, p->cutoff, g_c_extrapolation, asymptotic_value);
             integral += kernel[(size_t)abs(i + 1) * K + abs(j + 1)] * pair_density;       /* S:311 */
         }
     }
@@ -281,5 +292,58 @@ int ldmo_solve(const ldmo_problem* p, double t_max, double dt, const double* ini
         if (derivs) memcpy(derivs, derivative, sizeof(double) * n);
     }
     free(value); free(derivative);
+    return k + 1;
+}
+
+int ldmo_count_points_rk4(double t_max, double dt)
+{
+    int n = 1;
+    double time = 0;
+    while (time < t_max) { time += dt / 2; time += dt / 2; n++; }         /* S:627-634 */
+    return n;
+}
+
+/* RungeKutta4thSolver::Solve (S:597-654): present in the reference, never instantiated by its experiments */
+int ldmo_solve_rk4(const ldmo_problem* p, double t_max, double dt, const double* init, double* times, double* values, double* derivs)
+{
+    const int G = p->G;
+    const size_t n = 1 + (size_t)G * G;
+    double* value = (double*)malloc(sizeof(double) * n);
+    double* stage = (double*)malloc(sizeof(double) * n);
+    double* c[4];
+    for (int i = 0; i < 4; i++) c[i] = (double*)malloc(sizeof(double) * n);
+    memcpy(value, init, sizeof(double) * n);
+    double time = 0;
+    int k = 0;
+    if (times) times[0] = time;
+    if (values) memcpy(values, value, sizeof(double) * n);
+    while (time < t_max) {                                                /* S:627 */
+        ldmo_rhs(p, value, c[0]);                                         /* S:629, S:631 (evaluated twice there) */
+        if (derivs) memcpy(derivs + (size_t)k * n, c[0], sizeof(double) * n);
+        time += dt / 2;
+        for (size_t q = 0; q < n; q++) stage[q] = value[q] + c[0][q] * dt / 2;   /* S:633 */
+        ldmo_rhs(p, stage, c[1]);
+        for (size_t q = 0; q < n; q++) stage[q] = value[q] + c[1][q] * dt / 2;   /* S:634 */
+        ldmo_rhs(p, stage, c[2]);
+        time += dt / 2;
+        for (size_t q = 0; q < n; q++) stage[q] = value[q] + c[2][q] * dt;       /* S:636 */
+        ldmo_rhs(p, stage, c[3]);
+        for (size_t q = 0; q < n; q++) {
+            double sum = c[0][q];                                         /* S:637-640 */
+            sum = sum + c[1][q] * 2;
+            sum = sum + c[2][q] * 2;
+            sum = sum + c[3][q];
+            double v = value[q] + sum * dt / 6;                           /* S:641 */
+            if (v < 0) v = 0;                                             /* S:643-645 */
+            value[q] = v;
+        }
+        k++;
+        if (times) times[k] = time;
+        if (values) memcpy(values + (size_t)k * n, value, sizeof(double) * n);
+    }
+    ldmo_rhs(p, value, c[0]);                                             /* S:652 */
+    if (derivs) memcpy(derivs + (size_t)k * n, c[0], sizeof(double) * n);
+    free(value); free(stage);
+    for (int i = 0; i < 4; i++) free(c[i]);
     return k + 1;
 }

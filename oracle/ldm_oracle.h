@@ -64,6 +64,14 @@ int ldmo_count_points(double t_max, double dt);
 int ldmo_solve(const ldmo_problem* p, double t_max, double dt, const double* init, int full_history,
                double* times, double* values, double* derivs, double* observables);
 
+/* the ExtrapolationType Equation::operator() is called with for C (S:28, S:431): 0 Zero, 1 SquaredN (default; the only
+ * one any experiment passes), 2 Alpha.  Applies to ldmo_integrals / ldmo_rhs / the solvers. */
+void ldmo_set_extrapolation(int type);
+
+/* RungeKutta4thSolver::Solve (S:597-654): full history, values/derivs n_points*(1+G*G) (either may be NULL) */
+int ldmo_count_points_rk4(double t_max, double dt);
+int ldmo_solve_rk4(const ldmo_problem* p, double t_max, double dt, const double* init, double* times, double* values, double* derivs);
+
 /* threads the integrals' outer loop may use (results are identical for any count) */
 void ldmo_set_threads(int n);
 

@@ -50,6 +50,8 @@ struct RefHandle {
     SolverResults results;
 };
 
+ExtrapolationType g_type = SquaredN;      // what Equation::operator() / the solvers are called with (ref_set_extrapolation)
+
 }  // namespace
 
 extern "C" {
@@ -163,7 +165,7 @@ void ref_rhs(void* handle, const double* state, double* deriv)
     Properties& p = static_cast<RefHandle*>(handle)->props;
     const int n = p.SpeciesNumber + p.SpeciesNumber * p.SpeciesNumber * p.MomentsGrid.size() * p.MomentsGrid.size();
     Equation equation(p);
-    Vector out = equation(0, Vector(std::vector<CalcType>(state, state + n)), SquaredN);
+    Vector out = equation(0, Vector(std::vector<CalcType>(state, state + n)), g_type);
     for (int k = 0; k < n; k++) deriv[k] = out[k];
 }
 
@@ -217,7 +219,25 @@ int ref_solve(void* handle, double t_max, double dt, double n0, const double* in
     EulerSolver solver;
     Vector start = init ? Vector(std::vector<CalcType>(init, init + n))
                         : equation.GenerateEquilibriumValuesForNAndC(n0);
-    h->results = solver.Solve(equation, SquaredN, t_max, dt, start, false);
+    h->results = solver.Solve(equation, g_type, t_max, dt, start, false);
+    return (int)h->results.Values.size();
+}
+
+// ExtrapolationType (Solver.cpp:28) for ref_rhs / ref_solve / ref_solve_rk4: 0 Zero, 1 SquaredN, 2 Alpha, 3 Exponential
+void ref_set_extrapolation(int type) { g_type = (ExtrapolationType)type; }
+
+// RungeKutta4thSolver::Solve (Solver.cpp:597-654) -- present in the reference, never instantiated by its experiments
+int ref_solve_rk4(void* handle, double t_max, double dt, double n0, const double* init)
+{
+    QuietCout quiet;
+    RefHandle* h = static_cast<RefHandle*>(handle);
+    Properties& p = h->props;
+    const int n = 1 + p.MomentsGrid.size() * p.MomentsGrid.size();
+    Equation equation(p);
+    RungeKutta4thSolver solver;
+    Vector start = init ? Vector(std::vector<CalcType>(init, init + n))
+                        : equation.GenerateEquilibriumValuesForNAndC(n0);
+    h->results = solver.Solve(equation, g_type, t_max, dt, start, false);
     return (int)h->results.Values.size();
 }
 

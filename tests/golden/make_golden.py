@@ -135,7 +135,38 @@ def job_large(args):
     return f"large {name}: G={p.G} K={p.K} mM={p.mM} mW={p.mW} dN={deriv[0]!r} dC00={deriv[1]!r} ({out['seconds_byref']:.0f} s)"
 
 
+def job_extras(args):
+    """SURVEY 8f rank 3, pinned to the reference: RungeKutta4thSolver (Solver.cpp:597-654, never instantiated by the
+    reference's experiments) and the Zero / Alpha extrapolation types of C (Solver.cpp:361-389; Alpha with the integer
+    division of S:377).  Unmodified build; exp 14.4 b and c, 40 steps each."""
+    name, sw, sm = args
+    ref = Reference()
+    p = ref.from_numbers(sw, sm, 0.4, 0.2, 0.001, 0)
+    out = dict(G=p.G, sigmaW=sw, sigmaM=sm, b=0.4, d=0.2, dd=0.001)
+    base = np.load(os.path.join(HERE, f"exp_14_4_{name}.npz"))
+    mid = base["state_k100"]
+    t, v, d = p.solve(4.0, 0.1, want_derivs=True, rk4=True)
+    out.update(rk4_times=t, rk4_values=v, rk4_derivs=d)
+    for kind, label in ((0, "zero"), (2, "alpha")):
+        p.set_extrapolation(kind)
+        out[f"{label}_deriv_k0"] = p.rhs(np.concatenate([[200.0], np.full(p.P, 40000.0)]))
+        out[f"{label}_deriv_k100"] = p.rhs(mid)
+        t, v, d = p.solve(4.0, 0.1, init=mid, want_derivs=True)
+        out[f"{label}_times"], out[f"{label}_values"], out[f"{label}_derivs"] = t, v, d
+        if label == "zero":
+            t, v, d = p.solve(2.0, 0.1, init=mid, want_derivs=True, rk4=True)
+            out["zero_rk4_values"] = v
+    p.set_extrapolation(1)
+    np.savez_compressed(os.path.join(HERE, f"extras_14_4_{name}.npz"), **out)
+    return f"extras {name}: rk4 points={len(out['rk4_times'])} N_end={out['rk4_values'][-1, 0]!r} zero N_end={out['zero_values'][-1, 0]!r} alpha N_end={out['alpha_values'][-1, 0]!r}"
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--extras":
+        with ProcessPoolExecutor(max_workers=2) as pool:
+            for line in pool.map(job_extras, [("b", 0.05, 0.05), ("c", 0.015, 0.15)]):
+                print(line, flush=True)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "--large":
         with ProcessPoolExecutor(max_workers=2) as pool:
             for line in pool.map(job_large, [("g128", 0.15, 0.15, 128), ("g512", 0.10062893578616353, 0.08, 512)]):

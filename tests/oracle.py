@@ -33,6 +33,11 @@ def _load():
     lib.ldmo_solve.argtypes = [C.POINTER(_Problem), C.c_double, C.c_double, _dp, C.c_int,
                                C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.ldmo_set_threads.argtypes = [C.c_int]
+    lib.ldmo_set_extrapolation.argtypes = [C.c_int]
+    lib.ldmo_count_points_rk4.restype = C.c_int
+    lib.ldmo_count_points_rk4.argtypes = [C.c_double, C.c_double]
+    lib.ldmo_solve_rk4.restype = C.c_int
+    lib.ldmo_solve_rk4.argtypes = [C.POINTER(_Problem), C.c_double, C.c_double, _dp, C.c_void_p, C.c_void_p, C.c_void_p]
     return lib
 
 
@@ -107,6 +112,19 @@ class OracleProblem:
                                   values.ctypes.data, derivs.ctypes.data if want_derivs else None, obs.ctypes.data)
         assert got == n
         return times, values, derivs, obs
+
+    def set_extrapolation(self, kind):
+        """ExtrapolationType of the following calls (process-wide in the oracle): 0 Zero, 1 SquaredN, 2 Alpha"""
+        self.lib.ldmo_set_extrapolation(int(kind))
+
+    def solve_rk4(self, t_max, dt=0.1, init=None):
+        """RungeKutta4thSolver::Solve (Solver.cpp:597-654): full history (times, values, derivatives)"""
+        init = self.equilibrium() if init is None else np.ascontiguousarray(init, dtype=np.float64)
+        n = self.lib.ldmo_count_points_rk4(t_max, dt)
+        times, values, derivs = np.zeros(n), np.zeros((n, 1 + self.P)), np.zeros((n, 1 + self.P))
+        got = self.lib.ldmo_solve_rk4(self.p, t_max, dt, init, times.ctypes.data, values.ctypes.data, derivs.ctypes.data)
+        assert got == n
+        return times, values, derivs
 
     def close(self):
         if self.p:

@@ -30,6 +30,9 @@ def _load(name):
     lib.ref_kernels_at_nodes.argtypes = [C.c_void_p, _dp, _dp]
     lib.ref_solve.restype = C.c_int
     lib.ref_solve.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p]
+    lib.ref_solve_rk4.restype = C.c_int
+    lib.ref_solve_rk4.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p]
+    lib.ref_set_extrapolation.argtypes = [C.c_int]
     lib.ref_result_times.argtypes = [C.c_void_p, _dp]
     lib.ref_result_point.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]
     return lib
@@ -75,10 +78,15 @@ class RefProblem:
         self.lib.ref_kernels_at_nodes(self.h, m, w)
         return m, w
 
-    def solve(self, t_max, dt=0.1, n0=200.0, init=None, want_derivs=False):
+    def set_extrapolation(self, kind):
+        """ExtrapolationType (Solver.cpp:28) of the following rhs / solve calls: 0 Zero, 1 SquaredN, 2 Alpha"""
+        self.lib.ref_set_extrapolation(int(kind))
+
+    def solve(self, t_max, dt=0.1, n0=200.0, init=None, want_derivs=False, rk4=False):
         if init is not None:
             init = np.ascontiguousarray(init, dtype=np.float64)
-        n = self.lib.ref_solve(self.h, t_max, dt, n0, init.ctypes.data if init is not None else None)
+        fn = self.lib.ref_solve_rk4 if rk4 else self.lib.ref_solve
+        n = fn(self.h, t_max, dt, n0, init.ctypes.data if init is not None else None)
         times = np.zeros(n)
         self.lib.ref_result_times(self.h, times)
         values = np.zeros((n, 1 + self.P))

@@ -9,7 +9,7 @@ import pytest
 
 from oracle import OracleProblem
 
-GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if not os.path.basename(p).startswith("large_"))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if not os.path.basename(p).startswith(("large_", "extras_")))
 
 
 def make_oracle(g, name):
@@ -72,3 +72,31 @@ def test_known_answers_of_the_survey():
 def test_point_count_of_the_accumulated_clock():
     o = OracleProblem(0.05, 0.05)
     assert o.count_points(100.0) == 1001 and o.count_points(200.0) == 2001
+
+
+@pytest.mark.parametrize("name", ["b", "c"])
+def test_runge_kutta_and_extrapolation_types_bitwise(name):
+    """RungeKutta4thSolver (Solver.cpp:597-654) and the Zero / Alpha extrapolation of C
+    (Solver.cpp:361-389) as restated in the oracle, against the reference itself (tests/golden/make_golden.py --extras)"""
+    path = os.path.join(os.path.dirname(__file__), "golden", f"extras_14_4_{name}.npz")
+    if not os.path.exists(path):
+        pytest.skip("fixture not generated")
+    g = np.load(path)
+    base = np.load(os.path.join(os.path.dirname(__file__), "golden", f"exp_14_4_{name}.npz"))
+    o = OracleProblem(float(g["sigmaW"]), float(g["sigmaM"]))
+    mid = base["state_k100"]
+    try:
+        steps = 10 if name == "c" else 40              # 14.4c: 0.2 s per right-hand side on one core
+        t, v, d = o.solve_rk4(steps * 0.1 - 0.05)
+        assert np.array_equal(t, g["rk4_times"][:steps + 1]) and np.array_equal(v, g["rk4_values"][:steps + 1])
+        assert np.array_equal(d[:steps], g["rk4_derivs"][:steps])
+        for kind, label in ((0, "zero"), (2, "alpha")):
+            o.set_extrapolation(kind)
+            assert np.array_equal(o.rhs(o.equilibrium()), g[f"{label}_deriv_k0"])
+            assert np.array_equal(o.rhs(mid), g[f"{label}_deriv_k100"])
+            t, v, d, _ = o.solve(steps * 0.1 - 0.05, init=mid, want_derivs=True)
+            assert len(v) == steps and np.array_equal(v, g[f"{label}_values"][:steps])     # Euler stores one point fewer (S:574-575)
+            # the types are not a no-op: away from the uniform state the right-hand side differs from SquaredN's
+            assert not np.array_equal(g[f"{label}_deriv_k100"], base["deriv_k100"])
+    finally:
+        o.set_extrapolation(1)
