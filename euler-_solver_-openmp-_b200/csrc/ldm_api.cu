@@ -71,6 +71,7 @@ struct ldm_context {
     double* peer_own[2] = {nullptr, nullptr};                 // this rank's two replicas of C (gathered layout)
     unsigned long long* peer_own_flags = nullptr;             // [world] last step published by every rank
     unsigned int* peer_done = nullptr;
+    unsigned int* peer_sync = nullptr;                        // counters of the one-launch step (StepArgs::sync_words)
     int* peer_status = nullptr;
     double* peer_C[2][ldm::kMaxPeers] = {};                   // every rank's replicas, peer-mapped
     unsigned long long* peer_flags[ldm::kMaxPeers] = {};
@@ -116,7 +117,7 @@ struct ldm_context {
         for (void* p : ring_allocations) cudaFree(p);
         for (void* p : w_allocations) cudaFree(p);
         for (void* p : peer_opened) cudaIpcCloseMemHandle(p);
-        for (void* p : {(void*)peer_own[0], (void*)peer_own[1], (void*)peer_own_flags, (void*)peer_done, (void*)peer_status})
+        for (void* p : {(void*)peer_own[0], (void*)peer_own[1], (void*)peer_own_flags, (void*)peer_done, (void*)peer_status, (void*)peer_sync})
             if (p) cudaFree(p);
         if (ev_begin) cudaEventDestroy(ev_begin);
         if (ev_end) cudaEventDestroy(ev_end);
@@ -375,6 +376,9 @@ int ldm_shard_peer_alloc(ldm_handle h, unsigned char* handles)
         if (!h->peer_own_flags) LDM_CUDA(cudaMalloc((void**)&h->peer_own_flags, ldm::kMaxPeers * sizeof(unsigned long long)));
         if (!h->peer_done) LDM_CUDA(cudaMalloc((void**)&h->peer_done, sizeof(unsigned int)));
         if (!h->peer_status) LDM_CUDA(cudaMalloc((void**)&h->peer_status, sizeof(int)));
+        if (h->peer_sync) { cudaFree(h->peer_sync); h->peer_sync = nullptr; }
+        LDM_CUDA(cudaMalloc((void**)&h->peer_sync, (2 + 2 * (size_t)h->dev.rows_per_rank) * sizeof(unsigned int)));
+        LDM_CUDA(cudaMemset(h->peer_sync, 0, (2 + 2 * (size_t)h->dev.rows_per_rank) * sizeof(unsigned int)));
         LDM_CUDA(cudaMemset(h->peer_own_flags, 0, ldm::kMaxPeers * sizeof(unsigned long long)));
         LDM_CUDA(cudaMemset(h->peer_done, 0, sizeof(unsigned int)));
         LDM_CUDA(cudaMemset(h->peer_status, 0, sizeof(int)));
@@ -426,6 +430,7 @@ int ldm_shard_peer_upload(ldm_handle h, const double* C_gathered, double N)
         LDM_CUDA(cudaMemcpy(h->peer_own[0], C_gathered, words * sizeof(double), cudaMemcpyHostToDevice));
         LDM_CUDA(cudaMemset(h->peer_own_flags, 0, ldm::kMaxPeers * sizeof(unsigned long long)));
         LDM_CUDA(cudaMemset(h->peer_done, 0, sizeof(unsigned int)));
+        LDM_CUDA(cudaMemset(h->peer_sync, 0, (2 + 2 * (size_t)h->dev.rows_per_rank) * sizeof(unsigned int)));
         LDM_CUDA(cudaMemset(h->peer_status, 0, sizeof(int)));
         h->cur = 0;
         LDM_CUDA(cudaMemcpy(h->d_N, &N, sizeof(double), cudaMemcpyHostToDevice));
@@ -448,8 +453,6 @@ int ldm_shard_peer_step(ldm_handle h, double dt, void* cuda_stream)
         if (c->plan.use_w) ensure_w_operand(c);
         const int cur = c->cur, nxt = cur ^ 1;
         const int pb = c->peer_parity;
-        // every rank must have delivered the previous step into this rank's current replica
-        ldm::launch_peer_wait(c->peer_own_flags, c->dev.world, c->peer_epoch, c->peer_status, s);
         ldm::StepArgs args = make_step_args(c, c->peer_own[pb], c->d_N + cur, c->d_N + nxt, dt, nullptr, nullptr, nullptr);
         args.peer_count = c->dev.world;
         for (int r = 0; r < c->dev.world; r++) {
@@ -458,6 +461,23 @@ int ldm_shard_peer_step(ldm_handle h, double dt, void* cuda_stream)
         }
         args.done_counter = c->peer_done;
         args.epoch = c->peer_epoch + 1;
+        args.sync_words = c->peer_sync;
+        args.peer_status = c->peer_status;
+        if (c->plan.scan && std::getenv("LDM_SHARD_ONE_LAUNCH") != nullptr) {
+            // Option (off: measured 11 % slower at G = 512): the whole step -- WC rows, ring correction,
+            // integral, closing, exchange -- in one launch behind the one-warp wait for the peers' previous step; the last
+            // chunk CTA of a row closes and ships the row while the rows behind it are still being computed
+            ldm::launch_peer_wait(c->peer_own_flags, c->dev.world, c->peer_epoch, c->peer_status, s);
+            ldm::launch_scan_exchange(args, s);
+            c->launches += 2;
+            c->cur = nxt;
+            c->peer_parity = pb ^ 1;
+            c->peer_epoch += 1;
+            LDM_CUDA(cudaGetLastError());
+            return;
+        }
+        // every rank must have delivered the previous step into this rank's current replica
+        ldm::launch_peer_wait(c->peer_own_flags, c->dev.world, c->peer_epoch, c->peer_status, s);
         const bool side = args.P.n_ring > 0;
         if (side) {
             LDM_CUDA(cudaEventRecord(c->ev_fork, s));

@@ -87,6 +87,11 @@ struct StepArgs {
     unsigned long long* peer_flags[kMaxPeers];
     unsigned int* done_counter;
     unsigned long long epoch;
+    // one-launch sharded step (ldm_scan.cu scan_exchange_kernel): monotone counters, zeroed at ldm_shard_peer_upload --
+    // [0] WC rows done, [1] rows closed, [2 + lx] chunk CTAs of local row lx arrived, [2 + rows_per_rank + lx] ring CSR
+    // rows of local row lx done; and the status word a lost peer is reported in
+    unsigned int* sync_words;
+    int* peer_status;
     double dt;
 };
 
@@ -181,6 +186,10 @@ void launch_scan(const StepArgs& one, cudaStream_t stream);
 void launch_scan_batch(const StepArgs* d_batch, int n, int nt, int max_chunks, int max_rows, size_t max_smem, cudaStream_t stream);
 size_t scan_smem_bytes(int G, int A, int bn, int nt, int max_pieces);
 cudaError_t launch_persistent_scan(const PersistentArgs& args, int grid, cudaStream_t stream, int* max_grid);
+// xi-sharded step in ONE launch: wait for the peers' previous step, WC rows and ring correction (first CTAs), the
+// prefix-sum integral per (row, chunk), and the last chunk CTA of every row closes the row and stores it into every
+// rank's next replica -- rows travel over NVLink while the others are still computed; the last row publishes the epoch
+void launch_scan_exchange(const StepArgs& one, cudaStream_t stream);
 // single problem: `one` by value; batch: d_batch[n] in device memory, all entries sharing the plan's tile shape
 void launch_factored(const FactoredPlan& plan, const StepArgs& one, cudaStream_t stream);
 void launch_factored_batch(const FactoredPlan& shape, const StepArgs* d_batch, int n, int max_slabs, int max_rows, int max_G, int max_A,

@@ -351,6 +351,113 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
     __syncthreads();
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// xi-sharded step with the exchange fused in, ONE launch per step (ldm_shard_peer_step).  One-dimensional grid of
+// local_rows * (1 + chunks) CTAs, issued in this order:
+//   the first local_rows CTAs   CTA x: its share of the G row dots of the WC functional and of the ring correction, both
+//                               counted in global memory as they finish;
+//   then row by row             the prefix-sum integral of (local row, chunk), the chunks of a row next to each other;
+//                               the chunk CTA that arrives LAST on its row closes the row -- closure, Euler update, clamp
+//                               -- and stores it straight into the next replica of EVERY rank over NVLink (peer-mapped
+//                               memory), so rows travel while the rows behind them are still being computed; the CTA
+//                               that closes the last row publishes this rank's epoch in every rank's flag array.
+// The launch is preceded by peer_wait_kernel (one warp: all ranks have published the previous step, so this rank's current
+// replica is complete and nobody reads the replicas this step writes to any more) -- polling the flags from every CTA
+// instead costs more than that launch (measured: 8 system-scope loads per CTA, 15 CTAs per SM).
+// ------------------------------------------------------------------------------------------------------------------
+template <bool SMALL>
+__global__ void __launch_bounds__(SMALL ? 256 : kScanThreadsMax)
+scan_exchange_kernel(const StepArgs S)
+{
+    const DevProblem& P = S.P;
+    const int NT = blockDim.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int G = P.G, n_local = local_rows(P);
+    const bool helper = (int)blockIdx.x < n_local;
+    const int lx = helper ? (int)blockIdx.x : ((int)blockIdx.x - n_local) / P.scan_chunks;
+    const int chunk_slot = helper ? 0 : ((int)blockIdx.x - n_local) % P.scan_chunks;
+    const unsigned int step = (unsigned int)S.epoch;                        // 1-based count of steps since the upload
+    unsigned int* wc_done = S.sync_words;
+    unsigned int* rows_closed = S.sync_words + 1;
+    unsigned int* row_arrivals = S.sync_words + 2;
+    unsigned int* ring_done = S.sync_words + 2 + P.rows_per_rank;
+    __shared__ int closes_row;
+    __shared__ double wc_shared;
+
+    if (helper) {
+        // WC = <wc_operator, C> row by row (every rank reduces the FULL operator: no all-reduce), then this CTA's share
+        // of the ring correction (CSR rows dealt out evenly by entry count)
+        int slot = 0, mine = 0;
+        for (int xr = lx; xr < G; xr += n_local, slot++) {
+            if (slot % (NT / 32) == warp) {
+                const double s = wc_row_dot(P.wc_operator + (size_t)xr * G, S.C + (size_t)row_slot(P, xr) * G, G, lane);
+                if (lane == 0) S.wc_rows[xr] = s;
+            }
+            mine++;
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(wc_done), "r"((unsigned int)mine) : "memory");
+        for (int row = P.ring_cta_begin[lx] + warp; row < P.ring_cta_begin[lx + 1]; row += NT / 32) {
+            const double acc = ring_row_dot(P, S.C, row, lane);
+            if (lane == 0) {
+                const int point = P.ring_point[row];
+                S.ring[point] = acc;
+                asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(ring_done + point / G), "r"(1u) : "memory");
+            }
+        }
+        return;
+    }
+
+    StepArgs body = S;
+    body.wc_rows = nullptr;                                                 // the helper CTAs own the WC rows here
+    scan_body<scan_unroll(SMALL ? 256 : kScanThreadsMax)>(body, P.scan_chunk_order[chunk_slot], lx, true, -1);
+    __threadfence();                                                        // this thread's partial sums, before the arrival
+    __syncthreads();
+    if (tid == 0) closes_row = (atomicAdd(row_arrivals + lx, 1u) + 1u == step * (unsigned int)P.scan_chunks);
+    __syncthreads();
+    if (!closes_row) return;
+
+    // ---- close row lx: everything finish_factored_kernel does for it, same arithmetic ----
+    if (tid == 0) {
+        wait_for_count(wc_done, step * (unsigned int)G);
+        wait_for_count(ring_done + lx, step * (unsigned int)(P.ring_row_begin[lx + 1] - P.ring_row_begin[lx]));
+    }
+    __syncthreads();
+    if (warp == 0) {
+        double t = 0.0;
+        for (int r = lane; r < G; r += 32) t += __ldcg(S.wc_rows + r);      // wc_total(): the same order
+        t = warp_sum(t);
+        if (lane == 0) wc_shared = t;
+    }
+    __syncthreads();
+    const double N = S.N_cur[0];
+    const double beyond = outside_value(P, N, S.C);
+    const double WC = (wc_shared + beyond * P.wc_outside) * P.hh;           // Solver.cpp:311, 314
+    if (lx == 0 && tid == 0) first_moment_update(P, N, WC, S.dt, S.scalars, S.N_next);
+    const int n = n_local * G;
+    for (int y = tid; y < G; y += NT) {
+        const int ql = lx * G + y;
+        const int q = (P.rank + P.world * lx) * G + y;
+        double inside = 0.0;
+        for (int t = 0; t < P.scan_chunks; t++) inside += __ldcg(S.partial + (size_t)t * n + ql);
+        inside -= __ldcg(S.ring + ql);
+        const size_t slot = (size_t)(P.rank * P.rows_per_rank + lx) * G + y;   // this node in the gathered layout
+        const double c = S.C[slot];
+        const double mc = (inside + beyond * P.out_weight[q]) * P.hh;
+        const double dc = second_moment_rhs(P, mc, c, N, WC, P.m_nodes[q], P.w_nodes[q]);
+        double v = __dadd_rn(c, __dmul_rn(dc, S.dt));                       // Solver.cpp:577
+        v = v < 0.0 ? 0.0 : v;                                              // Solver.cpp:578-580
+        for (int r = 0; r < S.peer_count; r++) S.peer_C_next[r][slot] = v;  // the all-gather: NVLink peer stores
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (tid == 0 && atomicAdd(rows_closed, 1u) + 1u == step * (unsigned int)n_local) {
+        __threadfence_system();
+        for (int r = 0; r < S.peer_count; r++)
+            asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(S.peer_flags[r] + P.rank), "l"(S.epoch) : "memory");
+    }
+}
+
 // Persistent multi-step kernel (cooperative launch, one CTA per moment-grid row): all Euler steps of a solve inside one
 // launch, for grids whose rows are one chunk each.  Per step every CTA
 //   1. sums the G row dots of the WC functional (written by the closing phases of the step before),
@@ -560,6 +667,23 @@ void launch_scan_batch(const StepArgs* d_batch, int n, int nt, int max_chunks, i
 
 // the same CTA shape as the one-launch-per-step kernel of this problem: the summation order follows the shape, and the
 // persistent, per-step, batched and sharded paths of one handle must agree bit for bit
+void launch_scan_exchange(const StepArgs& one, cudaStream_t stream)
+{
+    const DevProblem& P = one.P;
+    const size_t smem = scan_smem_bytes(P.G, P.A, P.scan_bn, P.scan_nt, P.scan_max_pieces);
+    const dim3 grid(local_rows(P) * (1 + P.scan_chunks), 1, 1);
+    static bool configured[64][2] = {};
+    int device = 0;
+    cudaGetDevice(&device);
+    if (P.scan_nt <= 256) {
+        configure_once((const void*)scan_exchange_kernel<true>, configured[device & 63][0]);
+        scan_exchange_kernel<true><<<grid, P.scan_nt, smem, stream>>>(one);
+    } else {
+        configure_once((const void*)scan_exchange_kernel<false>, configured[device & 63][1]);
+        scan_exchange_kernel<false><<<grid, P.scan_nt, smem, stream>>>(one);
+    }
+}
+
 cudaError_t launch_persistent_scan(const PersistentArgs& args, int grid, cudaStream_t stream, int* max_grid)
 {
     const DevProblem& P = args.step.P;

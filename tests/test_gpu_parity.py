@@ -256,6 +256,41 @@ def test_sharded_step_emulated_on_one_device(ldm, world):
         assert r.get_N() == want[0]
 
 
+@pytest.mark.parametrize("knob", ["one launch", "three launches"])
+@pytest.mark.parametrize("G", [0, 200])
+def test_peer_exchange_step_on_one_rank(ldm, monkeypatch, knob, G):
+    """the sharded step with the exchange fused in (ldm_shard_peer_*), world = 1 so that one GPU can run it: the rank
+    stores its rows into its own next replica and waits on its own flag.  Three launches per step (the default), or one in
+    which the last chunk CTA of a row closes and ships it (an option: measured slower); both must equal the unsharded run
+    bit for bit.  (Two and more
+    ranks: bench.py's sharded leg compares the checksum with the NCCL variant.)"""
+    import torch
+    if knob == "one launch":
+        monkeypatch.setenv("LDM_SHARD_ONE_LAUNCH", "1")
+    if G:
+        props = ldm.Properties.Generate(1, 0.12, 0.09, 0.4, 0.2, 0.001, G)       # two column chunks
+        state = ldm.Equation(props).GenerateEquilibriumValuesForNAndC(200)
+        g = props.MomentsGrid
+        state[1:] *= (1 + 0.5 * np.exp(-(g[:, None] ** 2 + g[None, :] ** 2) / (2 * 0.1 ** 2))).ravel()
+    else:
+        base = golden("exp_14_4_c")
+        props, _ = problems_from(base, "exp_14_4_c", ldm)
+        state = base["state_k100"]
+    sh = ldm.ShardedEquation(props, 0, 1)
+    sh.peer_connect(lambda mine: mine.reshape(1, -1))
+    sh.peer_upload(state[1:], state[0])
+    steps = 7
+    stream = torch.cuda.current_stream().cuda_stream
+    for _ in range(steps):
+        sh.peer_step(0.1, stream)
+    got_C, got_N = sh.peer_download()
+    single = ldm.Equation(props)
+    single.upload(state)
+    single.advance(steps, 0.1)
+    want = single.download()
+    assert np.array_equal(got_C.ravel(), want[1:]) and got_N == want[0]
+
+
 def test_direct_path_trajectory(ldm):
     """the sample-by-sample algorithm through a whole experiment (the default is the factored one)"""
     g = golden("exp_14_4_b")
