@@ -39,6 +39,7 @@ WORKLOADS = {
     "g64": (0.1, 0.1, 0.4, 0.2, 0.001, 64),
     "g256": (0.10062893578616353, 0.08, 0.4, 0.2, 0.001, 256),
     "g512": (0.10062893578616353, 0.08, 0.4, 0.2, 0.001, 512),       # exp 14.6a entry 80 on 262 144 xi-points (config 4)
+    "g1024": (0.10062893578616353, 0.08, 0.4, 0.2, 0.001, 1024),     # the same on 1 048 576 xi-points
     "exp14_4a": (0.15, 0.15, 0.4, 0.2, 0.001, 0),
 }
 
