@@ -32,7 +32,10 @@ class _Problem(C.Structure):
                 ("h", C.c_double), ("cutoff", C.c_double), ("sigma_m", C.c_double), ("sigma_w", C.c_double),
                 ("b", C.c_double), ("d", C.c_double), ("d_prime", C.c_double),
                 ("moments_grid", C.POINTER(C.c_double)), ("kernels_grid", C.POINTER(C.c_double)),
-                ("M", C.POINTER(C.c_double)), ("W", C.POINTER(C.c_double))]
+                ("M", C.POINTER(C.c_double)), ("W", C.POINTER(C.c_double)),
+                ("mM_of", C.POINTER(C.c_int)), ("mW_of", C.POINTER(C.c_int)),
+                ("sigma_m_of", C.POINTER(C.c_double)), ("sigma_w_of", C.POINTER(C.c_double)),
+                ("b_of", C.POINTER(C.c_double)), ("d_of", C.POINTER(C.c_double)), ("d_prime_of", C.POINTER(C.c_double))]
 
 
 _dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
@@ -41,6 +44,7 @@ _lib = None
 # every symbol include/ldm.h declares: name -> (restype, argtypes)
 _SIGNATURES = {
     "ldm_problem_generate": (C.c_int, [C.c_double] * 5 + [C.c_int, C.POINTER(C.POINTER(_Problem))]),
+    "ldm_problem_generate_multi": (C.c_int, [C.c_int, _dp, _dp, _dp, _dp, _dp, C.c_int, C.POINTER(C.POINTER(_Problem))]),
     "ldm_problem_free": (None, [C.POINTER(_Problem)]),
     "ldm_problem_check_kernels": (C.c_int, [C.POINTER(_Problem), C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ldm_problem_kernel_structure": (C.c_int, [C.POINTER(_Problem), C.POINTER(C.c_int), C.POINTER(C.c_double)]),
@@ -121,14 +125,31 @@ class Properties:
         self.SigmaM, self.SigmaW, self.b, self.d, self.d_prime = c.sigma_m, c.sigma_w, c.b, c.d, c.d_prime
         self.MomentsGrid = np.ctypeslib.as_array(c.moments_grid, (c.G,)).copy()
         self.KernelsGrid = np.ctypeslib.as_array(c.kernels_grid, (c.K,)).copy()
-        self.M = np.ctypeslib.as_array(c.M, (c.K, c.K)).copy()
-        self.W = np.ctypeslib.as_array(c.W, (c.K, c.K)).copy()
+        n = c.species
+        if n == 1:
+            self.M = np.ctypeslib.as_array(c.M, (c.K, c.K)).copy()
+            self.W = np.ctypeslib.as_array(c.W, (c.K, c.K)).copy()
+        else:       # M(i), W(i, j) and the per-species values as arrays
+            self.M = np.ctypeslib.as_array(c.M, (n, c.K, c.K)).copy()
+            self.W = np.ctypeslib.as_array(c.W, (n, n, c.K, c.K)).copy()
+            self.MaxNumForM = np.ctypeslib.as_array(c.mM_of, (n,)).copy()
+            self.MaxNumForW = np.ctypeslib.as_array(c.mW_of, (n, n)).copy()
+            self.SigmaM = np.ctypeslib.as_array(c.sigma_m_of, (n,)).copy()
+            self.SigmaW = np.ctypeslib.as_array(c.sigma_w_of, (n, n)).copy()
+            self.b = np.ctypeslib.as_array(c.b_of, (n,)).copy()
+            self.d = np.ctypeslib.as_array(c.d_of, (n,)).copy()
+            self.d_prime = np.ctypeslib.as_array(c.d_prime_of, (n, n)).copy()
 
     @staticmethod
     def Generate(num, sW, sM, b, d, dd, forced_G=0):
-        """Properties::Generate(num, sW, sM, b, d, dd) (Solver.cpp:186); scalars because num must be 1."""
+        """Properties::Generate(num, sW, sM, b, d, dd) (Solver.cpp:186): scalars for one species, otherwise sW and dd
+        num x num and sM, b, d of length num."""
         if num != 1:
-            raise LdmError("ldm error -3: only one species is supported")
+            as_arr = lambda v, shape: np.ascontiguousarray(np.asarray(v, dtype=np.float64).reshape(shape))
+            ptr = C.POINTER(_Problem)()
+            _check(library().ldm_problem_generate_multi(int(num), as_arr(sW, (num * num,)), as_arr(sM, (num,)), as_arr(b, (num,)),
+                                                        as_arr(d, (num,)), as_arr(dd, (num * num,)), int(forced_G), C.byref(ptr)))
+            return Properties(ptr)
         ptr = C.POINTER(_Problem)()
         _check(library().ldm_problem_generate(float(sW), float(sM), float(b), float(d), float(dd), int(forced_G),
                                               C.byref(ptr)))
@@ -149,7 +170,8 @@ class Properties:
 
     @property
     def state_size(self):
-        return 1 + self.G * self.G
+        n = self.SpeciesNumber
+        return n + n * n * self.G * self.G
 
     def __del__(self):
         try:
@@ -180,7 +202,7 @@ class Equation:
     def GenerateEquilibriumValuesForNAndC(self, value):
         """Solver.cpp:416-428: [N = value | C = value^2 everywhere]"""
         st = np.full(self.props.state_size, float(value) * float(value))
-        st[0] = value
+        st[:self.props.SpeciesNumber] = value
         return st
 
     def set_extrapolation(self, chosen_type):

@@ -87,6 +87,13 @@ struct ldm_context {
     double w_megabytes = 0;
     int ring_rank = -1, ring_world = -1;
     long long ring_entries = 0, ring_samples = 0;
+    // several species (ldm_problem_generate_multi): species*species one-species handles -- pair (i, j) carries the tables of
+    // M(i) and W(i,j) and the pair density C_ij in its own d_C ping-pong; the first moments live here
+    int species = 1;
+    std::vector<ldm_context*> sub;
+    double* d_Nm = nullptr;                // [2][species]
+    double* d_dN = nullptr;                // [species]
+    double rate_b[ldm::kMaxSpecies] = {}, rate_d[ldm::kMaxSpecies] = {}, rate_dd[ldm::kMaxSpecies * ldm::kMaxSpecies] = {};
     int cur = 0;
     int algo = LDM_ALGO_FACTORED;
     long long launches = 0;
@@ -112,6 +119,7 @@ struct ldm_context {
     }
     ~ldm_context()
     {
+        for (ldm_context* c : sub) delete c;
         cudaSetDevice(device);
         for (void* p : allocations) cudaFree(p);
         for (void* p : ring_allocations) cudaFree(p);
@@ -280,6 +288,86 @@ void rhs_and_update(ldm_context* c, const DevProblem& P, const double* C, const 
     c->launches += 2 + (side ? 1 : 0);
 }
 
+// ---- several species ----
+size_t state_width(const ldm_context* c) { return c->species == 1 ? 1 + c->P() : (size_t)c->species + (size_t)c->species * c->species * c->P(); }
+
+// the integrals of one pair density on its one-species handle (no closing): partial sums, ring correction, WC row dots
+void multi_integrals(ldm_context* parent, cudaStream_t s)
+{
+    for (ldm_context* c : parent->sub) {
+        ensure_ring_operator(c);
+        if (c->plan.use_w) ensure_w_operand(c);
+        const ldm::StepArgs args = make_step_args(c, c->d_C[parent->cur], nullptr, nullptr, 0.0, nullptr, nullptr, nullptr);
+        const bool side = args.P.n_ring > 0;
+        if (side) {
+            LDM_CUDA(cudaEventRecord(c->ev_fork, s));
+            LDM_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+            ldm::launch_ring(args, c->aux_stream);
+            LDM_CUDA(cudaEventRecord(c->ev_join, c->aux_stream));
+        }
+        launch_integral(c, args, s);
+        if (side) LDM_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
+        parent->launches += 1 + (side ? 1 : 0);
+    }
+}
+
+// Equation::operator() for several species at the resident state, optionally with the clamped Euler update
+void multi_rhs_and_update(ldm_context* c, double dt, bool want_derivs, bool update, cudaStream_t s)
+{
+    multi_integrals(c, s);
+    const int n = c->species, cur = c->cur, nxt = cur ^ 1;
+    ldm::MultiArgs a{};
+    a.species = n; a.G = c->dev.G; a.extrapolation = c->dev.extrapolation;
+    a.hh = c->dev.hh; a.dt = dt;
+    for (int i = 0; i < n; i++) { a.b[i] = c->rate_b[i]; a.d[i] = c->rate_d[i]; }
+    for (int i = 0; i < n * n; i++) a.dd[i] = c->rate_dd[i];
+    a.N_cur = c->d_Nm + (size_t)cur * n;
+    a.N_next = update ? c->d_Nm + (size_t)nxt * n : nullptr;
+    a.dN_out = c->d_dN;
+    for (int p = 0; p < n * n; p++) {
+        ldm_context* h = c->sub[(size_t)p];
+        ldm::MultiPair& m = a.pair[p];
+        m.C = h->d_C[cur];
+        m.C_next = update ? h->d_C[nxt] : nullptr;
+        m.deriv_out = want_derivs ? h->d_deriv : nullptr;
+        m.partial = h->d_partial; m.slabs = h->plan.slabs();
+        m.ring = h->d_ring; m.wc_rows = h->d_wc_rows;
+        m.out_weight = h->dev.out_weight; m.m_nodes = h->dev.m_nodes; m.w_nodes = h->dev.w_nodes;
+        m.wc_outside = h->dev.wc_outside;
+    }
+    ldm::launch_finish_multi(a, s);
+    c->launches += 1;
+    if (update) c->cur = nxt;
+}
+
+void multi_upload(ldm_context* c, const double* state, cudaStream_t s)
+{
+    const size_t P = c->P();
+    const int n = c->species;
+    c->cur = 0;
+    LDM_CUDA(cudaMemcpyAsync(c->d_Nm, state, n * sizeof(double), cudaMemcpyHostToDevice, s));
+    for (int p = 0; p < n * n; p++)
+        LDM_CUDA(cudaMemcpyAsync(c->sub[(size_t)p]->d_C[0], state + n + (size_t)p * P, P * sizeof(double), cudaMemcpyHostToDevice, s));
+}
+
+void multi_download(ldm_context* c, double* state, cudaStream_t s)
+{
+    const size_t P = c->P();
+    const int n = c->species;
+    LDM_CUDA(cudaMemcpyAsync(state, c->d_Nm + (size_t)c->cur * n, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    for (int p = 0; p < n * n; p++)
+        LDM_CUDA(cudaMemcpyAsync(state + n + (size_t)p * P, c->sub[(size_t)p]->d_C[c->cur], P * sizeof(double), cudaMemcpyDeviceToHost, s));
+}
+
+void multi_download_derivs(ldm_context* c, double* deriv, cudaStream_t s)
+{
+    const size_t P = c->P();
+    const int n = c->species;
+    LDM_CUDA(cudaMemcpyAsync(deriv, c->d_dN, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+    for (int p = 0; p < n * n; p++)
+        LDM_CUDA(cudaMemcpyAsync(deriv + n + (size_t)p * P, c->sub[(size_t)p]->d_deriv, P * sizeof(double), cudaMemcpyDeviceToHost, s));
+}
+
 // All Euler steps of a solve inside one cooperative launch (ldm_factored.cu persistent_kernel): possible when every row
 // is one slab, on one rank, and the grid (G row CTAs + at least one spare CTA for the ring correction) is co-resident.
 bool persistent_possible(ldm_context* c)
@@ -365,6 +453,7 @@ extern "C" {
 int ldm_shard_peer_alloc(ldm_handle h, unsigned char* handles)
 {
     if (!h || !handles) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    if (h->species != 1) return fail(LDM_ERR_UNSUPPORTED, "not built for several species (ldm.h: ldm_problem_generate_multi)");
     if (h->dev.world > ldm::kMaxPeers) return fail(LDM_ERR_ARGUMENT, "at most 8 ranks");
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
@@ -527,6 +616,17 @@ int ldm_problem_generate(double sigma_w, double sigma_m, double b, double d, dou
     });
 }
 
+int ldm_problem_generate_multi(int species, const double* sigma_w, const double* sigma_m, const double* b, const double* d,
+                               const double* d_prime, int forced_G, ldm_problem** out)
+{
+    if (!out || !sigma_w || !sigma_m || !b || !d || !d_prime) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    return guarded([&] {
+        auto owned = std::make_unique<ldm::OwnedProblem>();
+        ldm::generate_problem_multi(species, sigma_w, sigma_m, b, d, d_prime, forced_G, *owned);
+        *out = &owned.release()->view;
+    });
+}
+
 void ldm_problem_free(ldm_problem* p)
 {
     if (p) delete reinterpret_cast<ldm::OwnedProblem*>(p);
@@ -557,9 +657,41 @@ int ldm_problem_kernel_structure(const ldm_problem* p, int* separable, double* m
 int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
 {
     if (!p || !out) return fail(LDM_ERR_ARGUMENT, "NULL argument");
-    if (p->species != 1) return fail(LDM_ERR_UNSUPPORTED, "only one species is supported (the reference ships multi-species inputs as UNSUPPORTED)");
+    if (p->species < 1 || p->species > LDM_MAX_SPECIES) return fail(LDM_ERR_UNSUPPORTED, "1 .. LDM_MAX_SPECIES species");
     if (p->G < 2 || p->K < 3 || !p->moments_grid || !p->kernels_grid || !p->M || !p->W)
         return fail(LDM_ERR_ARGUMENT, "incomplete problem description");
+    if (p->species > 1) {
+        if (!p->mM_of || !p->mW_of || !p->sigma_m_of || !p->sigma_w_of || !p->b_of || !p->d_of || !p->d_prime_of)
+            return fail(LDM_ERR_ARGUMENT, "a multi-species problem needs its per-species arrays (ldm_problem_generate_multi)");
+        return guarded([&] {
+            const int n = p->species;
+            auto c = std::make_unique<ldm_context>();
+            c->device = device;
+            c->species = n;
+            for (int i = 0; i < n; i++)
+                for (int j = 0; j < n; j++) {
+                    const ldm_problem view = ldm::species_view(*p, i, j);
+                    ldm_handle h = nullptr;
+                    if (ldm_create(&view, device, &h) != LDM_OK) throw CudaError(g_error);
+                    c->sub.push_back(h);
+                }
+            LDM_CUDA(cudaSetDevice(device));
+            LDM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+            LDM_CUDA(cudaEventCreate(&c->ev_begin));
+            LDM_CUDA(cudaEventCreate(&c->ev_end));
+            c->dev = c->sub[0]->dev;                 // G, hh, extrapolation (the tables stay the pairs')
+            c->algo = c->sub[0]->algo;
+            for (ldm_context* h : c->sub)
+                if (h->algo != c->algo) { h->algo = LDM_ALGO_FACTORED; h->plan = h->plan_dense; c->algo = LDM_ALGO_FACTORED; }
+            if (c->algo == LDM_ALGO_FACTORED)
+                for (ldm_context* h : c->sub) { h->algo = LDM_ALGO_FACTORED; h->plan = h->plan_dense; }
+            for (int i = 0; i < n; i++) { c->rate_b[i] = p->b_of[i]; c->rate_d[i] = p->d_of[i]; }
+            for (int i = 0; i < n * n; i++) c->rate_dd[i] = p->d_prime_of[i];
+            c->d_Nm = c->alloc<double>(2 * (size_t)n);
+            c->d_dN = c->alloc<double>((size_t)n);
+            *out = c.release();
+        });
+    }
     return guarded([&] {
         int count = 0;
         cudaError_t e = cudaGetDeviceCount(&count);
@@ -687,8 +819,21 @@ void ldm_destroy(ldm_handle h) { delete h; }
 int ldm_set_algorithm(ldm_handle h, int algo)
 {
     if (!h) return fail(LDM_ERR_ARGUMENT, "NULL handle");
-    if (algo == LDM_ALGO_AUTO) algo = h->scan_available ? LDM_ALGO_PREFIX : LDM_ALGO_FACTORED;
+    if (algo == LDM_ALGO_AUTO) {
+        bool all = h->species == 1 ? h->scan_available : true;
+        for (ldm_context* c : h->sub) all = all && c->scan_available;
+        algo = all ? LDM_ALGO_PREFIX : LDM_ALGO_FACTORED;
+    }
     if (algo != LDM_ALGO_DIRECT && algo != LDM_ALGO_FACTORED && algo != LDM_ALGO_PREFIX) return fail(LDM_ERR_ARGUMENT, "unknown algorithm");
+    if (h->species != 1) {
+        if (algo == LDM_ALGO_DIRECT) return fail(LDM_ERR_UNSUPPORTED, "several species run on the factored paths only");
+        for (ldm_context* c : h->sub)
+            if (algo == LDM_ALGO_PREFIX && !c->scan_available)
+                return fail(LDM_ERR_UNSUPPORTED, "an m table is not separable inside its disc: prefix sums do not apply");
+        for (ldm_context* c : h->sub) { c->algo = algo; c->plan = algo == LDM_ALGO_PREFIX ? c->plan_scan : c->plan_dense; }
+        h->algo = algo;
+        return LDM_OK;
+    }
     if (algo == LDM_ALGO_PREFIX && !h->scan_available)
         return fail(LDM_ERR_UNSUPPORTED, "the m table is not separable inside its disc: prefix sums do not apply");
     h->algo = algo;
@@ -724,6 +869,7 @@ int ldm_count_points_rk4(double t_max, double dt)
 int ldm_solve_rk4(ldm_handle h, const double* init, double dt, double t_max, double* times, double* values, double* derivs, int* n_points)
 {
     if (!h || !init) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    if (h->species != 1) return fail(LDM_ERR_UNSUPPORTED, "not built for several species (ldm.h: ldm_problem_generate_multi)");
     if (!(dt > 0)) return fail(LDM_ERR_ARGUMENT, "step must be positive");
     if (h->dev.world != 1) return fail(LDM_ERR_UNSUPPORTED, "the Runge-Kutta solver runs on one rank");
     return guarded([&] {
@@ -798,6 +944,15 @@ int ldm_solve_rk4(ldm_handle h, const double* init, double dt, double t_max, dou
 int ldm_rhs(ldm_handle h, const double* state, double* deriv)
 {
     if (!h || !state || !deriv) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    if (h->species != 1)
+        return guarded([&] {
+            LDM_CUDA(cudaSetDevice(h->device));
+            multi_upload(h, state, h->stream);
+            multi_rhs_and_update(h, 0.0, true, false, h->stream);
+            LDM_CUDA(cudaGetLastError());
+            multi_download_derivs(h, deriv, h->stream);
+            LDM_CUDA(cudaStreamSynchronize(h->stream));
+        });
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
         upload_state(h, state);
@@ -812,6 +967,7 @@ int ldm_rhs(ldm_handle h, const double* state, double* deriv)
 int ldm_integrals(ldm_handle h, const double* state, double* WC, double* MC)
 {
     if (!h || !state || !WC) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    if (h->species != 1) return fail(LDM_ERR_UNSUPPORTED, "not built for several species (ldm.h: ldm_problem_generate_multi)");
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
         upload_state(h, state);
@@ -838,6 +994,7 @@ int ldm_integrals(ldm_handle h, const double* state, double* WC, double* MC)
 int ldm_kernels_at_nodes(ldm_handle h, double* m_at_nodes, double* w_at_nodes)
 {
     if (!h || !m_at_nodes || !w_at_nodes) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    if (h->species != 1) return fail(LDM_ERR_UNSUPPORTED, "not built for several species (ldm.h: ldm_problem_generate_multi)");
     std::memcpy(m_at_nodes, h->tables.m_nodes.data(), h->P() * sizeof(double));
     std::memcpy(w_at_nodes, h->tables.w_nodes.data(), h->P() * sizeof(double));
     return LDM_OK;
@@ -861,6 +1018,39 @@ int ldm_solve(ldm_handle h, const double* init, double dt, double t_max, int rec
     if (!(dt > 0)) return fail(LDM_ERR_ARGUMENT, "step must be positive");
     if (record != LDM_RECORD_LAST && !values) return fail(LDM_ERR_ARGUMENT, "values is NULL");
     if (record == LDM_RECORD_ALL && !derivs) return fail(LDM_ERR_ARGUMENT, "derivs is NULL");
+    if (h->species != 1) {
+        if (record == LDM_RECORD_OBSERVABLES)
+            return fail(LDM_ERR_UNSUPPORTED, "the observables of Experiment_14_4 (N and C[0][G-1]) are defined for one species");
+        return guarded([&] {
+            LDM_CUDA(cudaSetDevice(h->device));
+            const int n = ldm_count_points(t_max, dt);
+            const size_t width = state_width(h);
+            if (n_points) *n_points = n;
+            if (times) {
+                double time = 0;
+                for (int k = 0; k < n; k++) { times[k] = time; time += dt; }
+            }
+            cudaStream_t s = h->stream;
+            multi_upload(h, init, s);
+            LDM_CUDA(cudaEventRecord(h->ev_begin, s));
+            for (int k = 0; k < n; k++) {
+                if (record >= LDM_RECORD_VALUES) multi_download(h, values + (size_t)k * width, s);
+                const bool last = (k == n - 1);
+                const bool want_deriv = (record == LDM_RECORD_ALL) || (last && derivs);
+                if (last && !want_deriv) break;
+                multi_rhs_and_update(h, dt, want_deriv, !last, s);       // S:567 / S:577-582
+                if (record == LDM_RECORD_ALL) multi_download_derivs(h, derivs + (size_t)k * width, s);
+            }
+            LDM_CUDA(cudaEventRecord(h->ev_end, s));
+            LDM_CUDA(cudaGetLastError());
+            if (record == LDM_RECORD_LAST) {
+                if (values) multi_download(h, values, s);
+                if (derivs) multi_download_derivs(h, derivs, s);
+            }
+            LDM_CUDA(cudaStreamSynchronize(s));
+            LDM_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev_begin, h->ev_end));
+        });
+    }
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
         const int n = ldm_count_points(t_max, dt);
@@ -962,7 +1152,8 @@ int ldm_state_upload(ldm_handle h, const double* state)
     if (!h || !state) return fail(LDM_ERR_ARGUMENT, "NULL argument");
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
-        upload_state(h, state);
+        if (h->species != 1) multi_upload(h, state, h->stream);
+        else upload_state(h, state);
         LDM_CUDA(cudaStreamSynchronize(h->stream));
     });
 }
@@ -970,6 +1161,12 @@ int ldm_state_upload(ldm_handle h, const double* state)
 int ldm_state_download(ldm_handle h, double* state)
 {
     if (!h || !state) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    if (h->species != 1)
+        return guarded([&] {
+            LDM_CUDA(cudaSetDevice(h->device));
+            multi_download(h, state, h->stream);
+            LDM_CUDA(cudaStreamSynchronize(h->stream));
+        });
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
         LDM_CUDA(cudaMemcpyAsync(state, h->d_N + h->cur, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
@@ -981,6 +1178,14 @@ int ldm_state_download(ldm_handle h, double* state)
 int ldm_advance(ldm_handle h, int n_steps, double dt)
 {
     if (!h || n_steps < 0) return fail(LDM_ERR_ARGUMENT, "bad argument");
+    if (h->species != 1)
+        return guarded([&] {
+            LDM_CUDA(cudaSetDevice(h->device));
+            LDM_CUDA(cudaEventRecord(h->ev_begin, h->stream));
+            for (int k = 0; k < n_steps; k++) multi_rhs_and_update(h, dt, false, true, h->stream);
+            LDM_CUDA(cudaEventRecord(h->ev_end, h->stream));
+            LDM_CUDA(cudaGetLastError());
+        });
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
         const bool persistent = persistent_possible(h);
@@ -1118,6 +1323,7 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
         bool batched = n > 0;
         for (int i = 0; i < n; i++) {
             if (!handles[i] || !inits[i] || !last_states[i]) throw std::invalid_argument("NULL entry in batch");
+            if (handles[i]->species != 1) throw std::invalid_argument("batches are built for one species per entry");
             ldm_context* h = handles[i];
             LDM_CUDA(cudaSetDevice(h->device));
             upload_state(h, inits[i]);
@@ -1180,6 +1386,7 @@ int ldm_device_count(void)
 int ldm_shard_configure(ldm_handle h, int rank, int world)
 {
     if (!h || world < 1 || rank < 0 || rank >= world) return fail(LDM_ERR_ARGUMENT, "bad rank/world");
+    if (h->species != 1) return fail(LDM_ERR_UNSUPPORTED, "not built for several species (ldm.h: ldm_problem_generate_multi)");
     if (world > h->dev.G) return fail(LDM_ERR_ARGUMENT, "more ranks than moment-grid rows");
     h->dev.world = world;
     h->dev.rank = rank;
@@ -1191,6 +1398,7 @@ int ldm_shard_rows_per_rank(ldm_handle h) { return h ? h->dev.rows_per_rank : 0;
 
 int ldm_shard_set_N(ldm_handle h, double N)
 {
+    if (h && h->species != 1) return fail(LDM_ERR_UNSUPPORTED, "not built for several species (ldm.h: ldm_problem_generate_multi)");
     if (!h) return fail(LDM_ERR_ARGUMENT, "NULL handle");
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
@@ -1201,6 +1409,7 @@ int ldm_shard_set_N(ldm_handle h, double N)
 
 int ldm_shard_get_N(ldm_handle h, double* N)
 {
+    if (h && h->species != 1) return fail(LDM_ERR_UNSUPPORTED, "not built for several species (ldm.h: ldm_problem_generate_multi)");
     if (!h || !N) return fail(LDM_ERR_ARGUMENT, "NULL argument");
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
@@ -1211,6 +1420,7 @@ int ldm_shard_get_N(ldm_handle h, double* N)
 
 int ldm_shard_step(ldm_handle h, const double* d_C_gathered, double* d_C_shard_out, double dt, void* cuda_stream)
 {
+    if (h && h->species != 1) return fail(LDM_ERR_UNSUPPORTED, "not built for several species (ldm.h: ldm_problem_generate_multi)");
     if (!h || !d_C_gathered || !d_C_shard_out) return fail(LDM_ERR_ARGUMENT, "NULL argument");
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));

@@ -137,6 +137,34 @@ void launch_pointwise(const DevProblem& P, const double* C, const double* inside
 void launch_finish_factored(const StepArgs& one, cudaStream_t stream);
 void launch_finish_factored_batch(const StepArgs* d_batch, int n, int max_points, cudaStream_t stream);
 
+// Closing kernel for several species (Solver.cpp:446-511 with SpeciesNumber > 1): every pair (i, j) has had its integrals
+// computed by the one-species kernels (partial sums, ring correction, WC row dots); this kernel forms WC_ij, MC_ij, the
+// first-moment equations and dC_ij in the reference's operation order, and optionally the clamped Euler update.
+constexpr int kMaxSpecies = 4;
+struct MultiPair {
+    const double* C;           // [P] pair density C_ij at the old time
+    double* C_next;            // may be NULL
+    double* deriv_out;         // may be NULL: dC_ij/dt
+    const double* partial;     // [slabs][P]
+    const double* ring;        // [P]
+    const double* wc_rows;     // [G]
+    const double* out_weight;  // [P] of species i
+    const double* m_nodes;     // [P] m_i at the nodes
+    const double* w_nodes;     // [P] w_ij at the nodes
+    double wc_outside;
+    int slabs;
+};
+struct MultiArgs {
+    int species, G, extrapolation;
+    double hh, dt;
+    double b[kMaxSpecies], d[kMaxSpecies], dd[kMaxSpecies * kMaxSpecies];
+    const double* N_cur;       // [species]
+    double* N_next;            // may be NULL
+    double* dN_out;            // [species]
+    MultiPair pair[kMaxSpecies * kMaxSpecies];
+};
+void launch_finish_multi(const MultiArgs& args, cudaStream_t stream);
+
 // blocks until every rank's flag has reached `epoch` (or a spin budget runs out: *status becomes non-zero)
 void launch_peer_wait(const unsigned long long* flags, int world, unsigned long long epoch, int* status, cudaStream_t stream);
 

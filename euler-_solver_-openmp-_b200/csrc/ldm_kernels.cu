@@ -242,6 +242,81 @@ finish_factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Several species (see ldm_device.h MultiArgs).  One thread per node, all pairs; the first warps of every CTA reduce
+// the pairs' WC row dots in the same fixed order, so all CTAs hold the same WC matrix; block 0 also closes the first
+// moments.  Operation order of Solver.cpp:446-508, nothing contracted.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+finish_multi_kernel(const MultiArgs A)
+{
+    const int s = A.species, G = A.G, n = G * G, pairs = s * s;
+    __shared__ double wc_raw[kMaxSpecies * kMaxSpecies];
+    for (int p = threadIdx.x >> 5; p < pairs; p += blockDim.x >> 5) {
+        const double v = wc_total(A.pair[p].wc_rows, G, threadIdx.x & 31);
+        if ((threadIdx.x & 31) == 0) wc_raw[p] = v;
+    }
+    __syncthreads();
+    double N[kMaxSpecies], WC[kMaxSpecies * kMaxSpecies], beyond[kMaxSpecies * kMaxSpecies];
+    #pragma unroll
+    for (int i = 0; i < kMaxSpecies; i++) N[i] = i < s ? A.N_cur[i] : 1.0;
+    #pragma unroll
+    for (int p = 0; p < kMaxSpecies * kMaxSpecies; p++) {
+        if (p >= pairs) { WC[p] = 0.0; beyond[p] = 0.0; continue; }
+        const int i = p / s, j = p - i * s;
+        const double asymptote = N[i] * N[j];                                       // S:271, S:289
+        double ext = asymptote;
+        if (A.extrapolation != 1 && !(fabs(A.pair[p].C[G - 1] - asymptote) < 1e-8))  // S:357; Zero / Alpha (S:361-389)
+            ext = A.extrapolation == 0 ? 0.0 : A.pair[p].C[0];
+        beyond[p] = ext;
+        WC[p] = (wc_raw[p] + ext * A.pair[p].wc_outside) * A.hh;                    // S:311, S:314
+    }
+    if (blockIdx.x == 0 && (int)threadIdx.x < s) {
+        const int i = threadIdx.x;
+        double dN = __dmul_rn(N[i], __dsub_rn(A.b[i], A.d[i]));                     // S:446
+        double d_prime_sum = 0.0;
+        for (int j = 0; j < s; j++) d_prime_sum = __dadd_rn(d_prime_sum, __dmul_rn(A.dd[i * s + j], WC[i * s + j]));   // S:448-450
+        dN = __dsub_rn(dN, d_prime_sum);                                            // S:451
+        A.dN_out[i] = dN;
+        if (A.N_next) {
+            const double v = __dadd_rn(N[i], __dmul_rn(dN, A.dt));                  // S:577
+            A.N_next[i] = v < 0.0 ? 0.0 : v;                                        // S:578-580
+        }
+    }
+    const int q = blockIdx.x * blockDim.x + threadIdx.x;
+    if (q >= n) return;
+    double MC[kMaxSpecies * kMaxSpecies], C[kMaxSpecies * kMaxSpecies];
+    #pragma unroll
+    for (int p = 0; p < kMaxSpecies * kMaxSpecies; p++) {
+        if (p >= pairs) { MC[p] = 0.0; C[p] = 0.0; continue; }
+        const MultiPair& P = A.pair[p];
+        double inside = 0.0;
+        for (int t = 0; t < P.slabs; t++) inside += P.partial[(size_t)t * n + q];
+        inside -= P.ring[q];
+        MC[p] = (inside + beyond[p] * P.out_weight[q]) * A.hh;
+        C[p] = P.C[q];
+    }
+    for (int i = 0; i < s; i++)
+        for (int j = 0; j < s; j++) {
+            const int ij = i * s + j, ji = j * s + i;
+            double r = __dadd_rn(__dmul_rn(A.b[i], MC[ij]), __dmul_rn(A.b[j], MC[ji]));             // S:464
+            if (i == j) r = __dadd_rn(r, __dmul_rn(__dmul_rn(__dmul_rn(2.0, A.b[i]), N[i]), A.pair[ij].m_nodes[q]));   // S:469
+            r = __dsub_rn(r, __dmul_rn(A.d[i], C[ij]));                                             // S:480
+            r = __dsub_rn(r, __dmul_rn(A.d[j], C[ji]));                                             // S:481
+            for (int k = 0; k < s; k++) {
+                r = __dsub_rn(r, __ddiv_rn(__dmul_rn(__dmul_rn(A.dd[i * s + k], WC[i * s + k]), C[ij]), N[i]));   // S:486
+                r = __dsub_rn(r, __ddiv_rn(__dmul_rn(__dmul_rn(A.dd[j * s + k], WC[j * s + k]), C[ji]), N[j]));   // S:487
+            }
+            r = __dsub_rn(r, __dmul_rn(__dmul_rn(A.dd[ij], C[ij]), A.pair[ij].w_nodes[q]));         // S:490
+            r = __dsub_rn(r, __dmul_rn(__dmul_rn(A.dd[ji], C[ji]), A.pair[ji].w_nodes[q]));         // S:498
+            if (A.pair[ij].deriv_out) A.pair[ij].deriv_out[q] = r;
+            if (A.pair[ij].C_next) {
+                const double v = __dadd_rn(C[ij], __dmul_rn(r, A.dt));                              // S:577
+                A.pair[ij].C_next[q] = v < 0.0 ? 0.0 : v;                                           // S:578-580
+            }
+        }
+}
+
 // One warp: lane r spins until rank r has published `epoch` (acquire, system scope).  A spin budget turns a lost peer
 // into an error status instead of a hung GPU.
 __global__ void peer_wait_kernel(const unsigned long long* flags, int world, unsigned long long epoch, int* status)
@@ -291,6 +366,12 @@ __global__ void record_observables_kernel(DevProblem P, const double* __restrict
 }
 
 }  // namespace
+
+void launch_finish_multi(const MultiArgs& args, cudaStream_t stream)
+{
+    const int n = args.G * args.G;
+    finish_multi_kernel<<<(n + 255) / 256, 256, 0, stream>>>(args);
+}
 
 void launch_peer_wait(const unsigned long long* flags, int world, unsigned long long epoch, int* status, cudaStream_t stream)
 {

@@ -172,6 +172,84 @@ void generate_problem(double sigma_w, double sigma_m, double b, double d, double
     v.W = out.W.data();
 }
 
+void generate_problem_multi(int species, const double* sigma_w, const double* sigma_m, const double* b, const double* d,
+                            const double* d_prime, int forced_G, OwnedProblem& out)
+{
+    const int s = species;
+    if (s < 1 || s > LDM_MAX_SPECIES) throw std::invalid_argument("species count out of range");
+    double max_w = 0, max_m = 0, min_sigma = 1e300;
+    for (int i = 0; i < s * s; i++) { if (!(sigma_w[i] > 0)) throw std::invalid_argument("sigma_w must be positive"); max_w = std::max(max_w, sigma_w[i]); min_sigma = std::min(min_sigma, sigma_w[i]); }
+    for (int i = 0; i < s; i++) { if (!(sigma_m[i] > 0)) throw std::invalid_argument("sigma_m must be positive"); max_m = std::max(max_m, sigma_m[i]); min_sigma = std::min(min_sigma, sigma_m[i]); }
+    if (forced_G > 0 && forced_G < 4) throw std::invalid_argument("forced_G must be at least 4");
+
+    // GenerateGrids(sW.max_value(), sM.max_value()) (S:203, S:63-95): min(sigma_w, sigma_m) of S:80 sees only those two
+    const double cutoff_distance = (max_w + max_m) * 5;
+    const double max_radius = std::max(max_w, max_m) * 5;
+    int nodes = forced_G > 0 ? forced_G : 5;
+    std::vector<double> grid = stretched_nodes(nodes);
+    if (forced_G <= 0)
+        while (grid.back() < cutoff_distance - 0.01) grid = stretched_nodes(++nodes);
+    const double scale = cutoff_distance / grid.back();
+    for (double& e : grid) e = e * scale;
+    if (!(std::abs(grid.back() - cutoff_distance) < kEpsilon))
+        throw std::invalid_argument("moment grid does not end at the cutoff (reference assert, Solver.cpp:77)");
+    int K = (nodes - 1) * 2 - 1;
+    if (std::min(max_w, max_m) < 0.015) {
+        K = (K - 2) * 4 - 1;
+        K = (K - 1) * 2 - 1;
+    }
+    if (!((K % 2 == 1) && (K >= 5))) throw std::invalid_argument("kernel grid size must be odd and >= 5 (Solver.cpp:88)");
+    (void)min_sigma;
+    out.moments_grid = grid;
+    out.kernels_grid = lin_spaced(K, 0, max_radius);
+    const double h = out.kernels_grid[2] - out.kernels_grid[0];
+
+    out.W.clear(); out.M.clear(); out.mW_of.clear(); out.mM_of.clear();
+    std::vector<double> table;
+    for (int i = 0; i < s; i++)
+        for (int j = 0; j < s; j++) {                                   // S:212-220
+            out.mW_of.push_back(fill_kernel(out.kernels_grid, h, sigma_w[i * s + j], sigma_w[i * s + j] * 3, table));
+            out.W.insert(out.W.end(), table.begin(), table.end());
+        }
+    for (int i = 0; i < s; i++) {                                       // S:229-234
+        out.mM_of.push_back(fill_kernel(out.kernels_grid, h, sigma_m[i], sigma_m[i] * 3, table));
+        out.M.insert(out.M.end(), table.begin(), table.end());
+    }
+    out.sigma_w_of.assign(sigma_w, sigma_w + s * s);
+    out.sigma_m_of.assign(sigma_m, sigma_m + s);
+    out.b_of.assign(b, b + s);
+    out.d_of.assign(d, d + s);
+    out.d_prime_of.assign(d_prime, d_prime + s * s);
+
+    ldm_problem& v = out.view;
+    v.species = s;
+    v.G = nodes; v.K = K; v.mM = out.mM_of[0]; v.mW = out.mW_of[0];
+    v.h = h; v.cutoff = grid.back();
+    v.sigma_m = sigma_m[0]; v.sigma_w = sigma_w[0]; v.b = b[0]; v.d = d[0]; v.d_prime = d_prime[0];
+    v.moments_grid = out.moments_grid.data();
+    v.kernels_grid = out.kernels_grid.data();
+    v.M = out.M.data();
+    v.W = out.W.data();
+    v.mM_of = out.mM_of.data(); v.mW_of = out.mW_of.data();
+    v.sigma_m_of = out.sigma_m_of.data(); v.sigma_w_of = out.sigma_w_of.data();
+    v.b_of = out.b_of.data(); v.d_of = out.d_of.data(); v.d_prime_of = out.d_prime_of.data();
+}
+
+ldm_problem species_view(const ldm_problem& p, int i, int j)
+{
+    ldm_problem v = p;
+    const int s = p.species;
+    const size_t KK = (size_t)p.K * p.K;
+    v.species = 1;
+    v.M = p.M + (size_t)i * KK;
+    v.W = p.W + (size_t)(i * s + j) * KK;
+    v.mM = p.mM_of[i]; v.mW = p.mW_of[i * s + j];
+    v.sigma_m = p.sigma_m_of[i]; v.sigma_w = p.sigma_w_of[i * s + j];
+    v.b = p.b_of[i]; v.d = p.d_of[i]; v.d_prime = p.d_prime_of[i * s + j];
+    v.mM_of = nullptr; v.mW_of = nullptr; v.sigma_m_of = nullptr; v.sigma_w_of = nullptr; v.b_of = nullptr; v.d_of = nullptr; v.d_prime_of = nullptr;
+    return v;
+}
+
 void check_kernels(const ldm_problem& p, double& integral_w, double& integral_m)
 {
     integral_w = midpoint_integral(p.W, p.K, p.mW, p.h);

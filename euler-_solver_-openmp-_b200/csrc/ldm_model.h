@@ -16,15 +16,25 @@
 
 namespace ldm {
 
-struct OwnedProblem {             // backing store of an ldm_problem handed out by ldm_problem_generate
+struct OwnedProblem {             // backing store of an ldm_problem handed out by ldm_problem_generate(_multi)
     ldm_problem view{};
     std::vector<double> moments_grid, kernels_grid, M, W;
+    std::vector<int> mM_of, mW_of;                                     // species > 1
+    std::vector<double> sigma_m_of, sigma_w_of, b_of, d_of, d_prime_of;
 };
 
 // Properties::Generate (Solver.cpp:186-241), one species.  Throws std::invalid_argument on the
 // reference's assert conditions (S:77, S:88, S:140).
 void generate_problem(double sigma_w, double sigma_m, double b, double d, double d_prime, int forced_G,
                       OwnedProblem& out);
+
+// The same for several species (Solver.cpp:186-241 with num > 1): grids from the largest sigmas, one W table per pair,
+// one M table per species.
+void generate_problem_multi(int species, const double* sigma_w, const double* sigma_m, const double* b, const double* d,
+                            const double* d_prime, int forced_G, OwnedProblem& out);
+
+// A one-species view of species pair (i, j) of a multi-species problem: M = M(i), W = W(i,j), rates of species i.
+ldm_problem species_view(const ldm_problem& p, int i, int j);
 
 // Properties::CheckKernels (Solver.cpp:147-183)
 void check_kernels(const ldm_problem& p, double& integral_w, double& integral_m);

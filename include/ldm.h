@@ -18,12 +18,13 @@ extern "C" {
 #define LDM_OK              0
 #define LDM_ERR_ARGUMENT   -1   /* the reference would assert (S:260, S:327, ...) */
 #define LDM_ERR_CUDA       -2   /* no device / CUDA runtime failure */
-#define LDM_ERR_UNSUPPORTED -3  /* species != 1 (the reference ships those inputs as UNSUPPORTED) */
+#define LDM_ERR_UNSUPPORTED -3  /* a combination that is not built (see the entry point's comment) */
+#define LDM_MAX_SPECIES     4
 
 /* What the reference keeps in `struct Properties` (S:40-60) for one species, flattened.
  * Tables are K x K row-major, exactly the reference's M(0) and W(0,0). */
 typedef struct ldm_problem {
-    int species;                  /* SpeciesNumber (S:42); must be 1 */
+    int species;                  /* SpeciesNumber (S:42); 1 ... LDM_MAX_SPECIES */
     int G;                        /* MomentsGrid.size() (S:57) */
     int K;                        /* KernelsGrid.size() (S:59), odd */
     int mM;                       /* MaxNumForM[0] (S:52) */
@@ -34,8 +35,16 @@ typedef struct ldm_problem {
     double b, d, d_prime;         /* S:44-46 */
     const double* moments_grid;   /* G */
     const double* kernels_grid;   /* K */
-    const double* M;              /* K*K */
-    const double* W;              /* K*K */
+    const double* M;              /* K*K; species > 1: species tables M(0), M(1), ... one after the other */
+    const double* W;              /* K*K; species > 1: species*species tables W(0,0), W(0,1), ... */
+    /* species > 1 (ldm_problem_generate_multi; NULL otherwise): the per-species / per-pair values of S:44-55 */
+    const int* mM_of;             /* species:          MaxNumForM[i] */
+    const int* mW_of;             /* species*species:  MaxNumForW[i][j] */
+    const double* sigma_m_of;     /* species */
+    const double* sigma_w_of;     /* species*species */
+    const double* b_of;           /* species */
+    const double* d_of;           /* species */
+    const double* d_prime_of;     /* species*species */
 } ldm_problem;
 
 typedef struct ldm_context* ldm_handle;
@@ -60,6 +69,13 @@ typedef struct ldm_context* ldm_handle;
 int  ldm_problem_generate(double sigma_w, double sigma_m, double b, double d, double d_prime,
                           int forced_G, ldm_problem** out);
 void ldm_problem_free(ldm_problem* p);
+/* The same for several species (S:186-241 with num > 1; the reference ships such inputs as "(UNSUPPORTED)" examples, but
+ * its Equation handles them, S:454-511).  sigma_w, d_prime: species*species row-major; sigma_m, b, d: species.  Grids
+ * come from the largest sigmas (S:203).  State vectors are [N_0..N_{s-1} | C_00 | C_01 | ... | C_{s-1,s-1}], each C_ij
+ * G*G row-major (S:255-262, T:740-806).  A handle on such a problem supports ldm_rhs, ldm_solve (LDM_RECORD_LAST /
+ * VALUES / ALL), ldm_set_algorithm and ldm_set_extrapolation; the other entry points return LDM_ERR_UNSUPPORTED. */
+int  ldm_problem_generate_multi(int species, const double* sigma_w, const double* sigma_m, const double* b, const double* d,
+                                const double* d_prime, int forced_G, ldm_problem** out);
 /* Properties::CheckKernels (S:147-183): the two midpoint-rule integrals (each must be 1 +- 1e-8) */
 int  ldm_problem_check_kernels(const ldm_problem* p, double* integral_w, double* integral_m);
 

@@ -122,6 +122,23 @@ void* ref_props_from_numbers(double sigma_w, double sigma_m, double b, double d,
 
 void ref_props_free(void* handle) { delete static_cast<RefHandle*>(handle); }
 
+// several species: MaxNumForM[i] (s), MaxNumForW[i][j] (s*s), and the tables M(i) (s*K*K), W(i,j) (s*s*K*K)
+void ref_props_multi(void* handle, int* mM, int* mW, double* M, double* W)
+{
+    Properties& p = static_cast<RefHandle*>(handle)->props;
+    const int s = p.SpeciesNumber, K = p.KernelsGrid.size();
+    for (int i = 0; i < s; i++) {
+        mM[i] = (int)p.MaxNumForM[i];
+        for (int x = 0; x < K; x++)
+            for (int y = 0; y < K; y++) M[((size_t)i * K + x) * K + y] = p.M(i)[x][y];
+        for (int j = 0; j < s; j++) {
+            mW[i * s + j] = (int)p.MaxNumForW[i][j];
+            for (int x = 0; x < K; x++)
+                for (int y = 0; y < K; y++) W[(((size_t)i * s + j) * K + x) * K + y] = p.W(i, j)[x][y];
+        }
+    }
+}
+
 // ints: [species, G, K, MaxNumForM[0], MaxNumForW[0][0]]; reals: [h, cutoff, sigmaM, sigmaW, b, d, d']
 void ref_props_scalars(void* handle, int* ints, double* reals)
 {
@@ -214,7 +231,7 @@ int ref_solve(void* handle, double t_max, double dt, double n0, const double* in
     QuietCout quiet;
     RefHandle* h = static_cast<RefHandle*>(handle);
     Properties& p = h->props;
-    const int n = 1 + p.MomentsGrid.size() * p.MomentsGrid.size();
+    const int n = p.SpeciesNumber + p.SpeciesNumber * p.SpeciesNumber * p.MomentsGrid.size() * p.MomentsGrid.size();
     Equation equation(p);
     EulerSolver solver;
     Vector start = init ? Vector(std::vector<CalcType>(init, init + n))

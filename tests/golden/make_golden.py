@@ -161,7 +161,48 @@ def job_extras(args):
     return f"extras {name}: rk4 points={len(out['rk4_times'])} N_end={out['rk4_values'][-1, 0]!r} zero N_end={out['zero_values'][-1, 0]!r} alpha N_end={out['alpha_values'][-1, 0]!r}"
 
 
+MULTI = {
+    # the reference's own "(UNSUPPORTED)" example inputs (Data/Custom/): name -> (file, species)
+    "2_species": ("(UNSUPPORTED)example_2_species.csv", 2),
+    "3_species": ("(UNSUPPORTED)example_3_species.csv", 3),
+}
+
+
+def job_multi(name):
+    """SURVEY 8f rank 4, pinned to the reference: Equation and EulerSolver with SpeciesNumber > 1 (Solver.cpp:265-295,
+    446-511) on the example inputs the reference ships as "(UNSUPPORTED)" -- its FileReader, Properties::Generate and
+    Equation do handle them.  Unmodified build."""
+    fname, s = MULTI[name]
+    ref = Reference()
+    p = ref.from_file(os.path.join(REF_DATA, "Custom", fname), 0)
+    assert p.species == s
+    g, k = p.grids()
+    mM, mW, M, W = p.multi_tables()
+    P = p.P
+    n0 = 200.0 - 25.0 * np.arange(s)                                     # distinct densities per species
+    state = np.empty(p.width)
+    state[:s] = n0
+    r2 = g[:, None] ** 2 + g[None, :] ** 2
+    for i in range(s):
+        for j in range(s):
+            bump = 1 + (0.3 + 0.05 * i - 0.04 * j) * np.exp(-r2 / (2 * 0.05 ** 2)) + 0.02 * (i - j) * np.sin(9 * g[:, None] + 4 * g[None, :])
+            state[s + (i * s + j) * P: s + (i * s + j + 1) * P] = (n0[i] * n0[j] * bump).ravel()
+    out = dict(species=s, G=p.G, K=p.K, mM=mM, mW=mW, moments_grid=g, kernels_grid=k, M=M, W=W, state=state,
+               deriv=p.rhs(state), deriv_equilibrium=p.rhs(np.concatenate([np.full(s, 200.0), np.full(s * s * P, 40000.0)])))
+    t, v, d = p.solve(3.05, 0.1, init=state, want_derivs=True)
+    out.update(times=t, values=v, derivs=d)
+    p.set_extrapolation(0)
+    out["zero_deriv"] = p.rhs(state)
+    p.set_extrapolation(1)
+    np.savez_compressed(os.path.join(HERE, f"multi_{name}.npz"), **out)
+    return f"multi {name}: G={p.G} K={p.K} mM={list(mM)} points={len(t)} N_end={list(v[-1, :s])}"
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--multi":
+        for name in MULTI:
+            print(job_multi(name), flush=True)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "--extras":
         with ProcessPoolExecutor(max_workers=2) as pool:
             for line in pool.map(job_extras, [("b", 0.05, 0.05), ("c", 0.015, 0.15)]):

@@ -25,6 +25,7 @@ def _load(name):
     lib.ref_props_scalars.argtypes = [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_double)]
     lib.ref_props_grids.argtypes = [C.c_void_p, _dp, _dp]
     lib.ref_props_tables.argtypes = [C.c_void_p, _dp, _dp]
+    lib.ref_props_multi.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, _dp, _dp]
     lib.ref_rhs.argtypes = [C.c_void_p, _dp, _dp]
     lib.ref_integrals.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_double), C.c_void_p]
     lib.ref_kernels_at_nodes.argtypes = [C.c_void_p, _dp, _dp]
@@ -49,6 +50,7 @@ class RefProblem:
         self.species, self.G, self.K, self.mM, self.mW = list(ints)
         self.h_step, self.cutoff, self.sigmaM, self.sigmaW, self.b, self.d, self.dd = list(reals)
         self.P = self.G * self.G
+        self.width = self.species + self.species ** 2 * self.P          # state vector length (Solver.cpp:260)
 
     def grids(self):
         g, k = np.zeros(self.G), np.zeros(self.K)
@@ -59,6 +61,14 @@ class RefProblem:
         M, W = np.zeros((self.K, self.K)), np.zeros((self.K, self.K))
         self.lib.ref_props_tables(self.h, M, W)
         return M, W
+
+    def multi_tables(self):
+        """several species: MaxNumForM (s), MaxNumForW (s, s), M (s, K, K), W (s, s, K, K)"""
+        s, K = self.species, self.K
+        mM, mW = np.zeros(s, dtype=np.int32), np.zeros((s, s), dtype=np.int32)
+        M, W = np.zeros((s, K, K)), np.zeros((s, s, K, K))
+        self.lib.ref_props_multi(self.h, mM.ctypes.data, mW.ctypes.data, M, W)
+        return mM, mW, M, W
 
     def rhs(self, state):
         state = np.ascontiguousarray(state, dtype=np.float64)
@@ -89,8 +99,8 @@ class RefProblem:
         n = fn(self.h, t_max, dt, n0, init.ctypes.data if init is not None else None)
         times = np.zeros(n)
         self.lib.ref_result_times(self.h, times)
-        values = np.zeros((n, 1 + self.P))
-        derivs = np.zeros((n, 1 + self.P)) if want_derivs else None
+        values = np.zeros((n, self.width))
+        derivs = np.zeros((n, self.width)) if want_derivs else None
         for k in range(n):
             self.lib.ref_result_point(self.h, k, values[k].ctypes.data,
                                       derivs[k].ctypes.data if want_derivs else None)

@@ -63,7 +63,7 @@ def algo_id(ldm, algorithm):
     return {"direct": ldm.ALGO_DIRECT, "factored": ldm.ALGO_FACTORED, "prefix": ldm.ALGO_PREFIX}[algorithm]
 
 
-ALL = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(p).startswith(("large_", "extras_")))
+ALL = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(p).startswith(("large_", "extras_", "multi_")))
 
 
 @pytest.mark.parametrize("name", ALL)
@@ -202,6 +202,42 @@ def test_runge_kutta_and_extrapolation_types(ldm, name, algorithm):
     # and back: the default type still reproduces the experiment's numbers
     run = ldm.EulerSolver().Solve(eq, ldm.SquaredN, 10.0, 0.1, eq.GenerateEquilibriumValuesForNAndC(200), record=ldm.RECORD_VALUES)
     assert_states_close(run.Values[100], base["state_k100"])
+
+
+@pytest.mark.parametrize("algorithm", ["prefix", "factored"])
+@pytest.mark.parametrize("name", ["2_species", "3_species"])
+def test_several_species(ldm, name, algorithm):
+    """Equation and EulerSolver with SpeciesNumber > 1 (Solver.cpp:265-295, 446-511) on the reference's
+    own multi-species example inputs, against fixtures computed by the reference itself: one right-hand side at a state
+    with distinct densities and asymmetric pair densities, the uniform state, Zero extrapolation, and 30 Euler steps"""
+    g = golden(f"multi_{name}")
+    s = int(g["species"])
+    sw = {2: [[0.05, 0.06], [0.06, 0.05]], 3: [[0.05, 0.06, 0.07], [0.06, 0.05, 0.04], [0.07, 0.04, 0.05]]}[s]
+    props = ldm.Properties.Generate(s, sw, [0.05] * s, [0.4, 0.401, 0.4001][:s], [0.2] * s, np.full((s, s), 0.001))
+    eq = ldm.Equation(props, algorithm=algo_id(ldm, algorithm))
+    P = props.G ** 2
+
+    def assert_deriv_close(got, want):
+        # blockwise: the far field of every dC_ij is a cancellation residue of terms as large as the block's largest entry
+        for lo, hi in [(0, s)] + [(s + k * P, s + (k + 1) * P) for k in range(s * s)]:
+            scale = np.max(np.abs(want[lo:hi])) + 1.0
+            assert np.max(np.abs(got[lo:hi] - want[lo:hi])) <= 1e-11 * scale, (lo, np.max(np.abs(got[lo:hi] - want[lo:hi])) / scale)
+
+    assert_deriv_close(eq(0.0, g["state"], ldm.SquaredN), g["deriv"])
+    assert_deriv_close(eq(0.0, eq.GenerateEquilibriumValuesForNAndC(200), ldm.SquaredN), g["deriv_equilibrium"])
+    assert_deriv_close(eq(0.0, g["state"], ldm.Zero), g["zero_deriv"])
+    assert not np.array_equal(g["zero_deriv"], g["deriv"])
+    res = ldm.EulerSolver().Solve(eq, ldm.SquaredN, 3.05, 0.1, g["state"], record=ldm.RECORD_ALL)
+    assert np.array_equal(res.Times, g["times"])
+    assert_states_close(res.Values, g["values"])
+    assert_deriv_close(res.Derivatives[-1], g["derivs"][-1])
+    last = ldm.EulerSolver().Solve(eq, ldm.SquaredN, 3.05, 0.1, g["state"], record=ldm.RECORD_LAST)
+    assert np.array_equal(last.Values[0], res.Values[-1])
+    eq.upload(g["state"])
+    eq.advance(30, 0.1)
+    assert np.array_equal(eq.download(), res.Values[-1])
+    with pytest.raises(ldm.LdmError):
+        eq.integrals(g["state"])                  # one-species entry points say so instead of misreading the state
 
 
 def test_batch_spread_over_two_devices(ldm):

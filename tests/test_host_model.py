@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GOLDEN = sorted(p for p in glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")) if not os.path.basename(p).startswith(("large_", "extras_")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")) if not os.path.basename(p).startswith(("large_", "extras_", "multi_")))
 
 
 def generate(ldm, g, name):
@@ -49,6 +49,21 @@ def test_reference_kernel_tables_are_separable_inside_their_disc(ldm, path):
         assert not p.KernelStructure()[0]
 
 
+@pytest.mark.parametrize("name", ["2_species", "3_species"])
+def test_generate_several_species_matches_reference_bitwise(ldm, name):
+    """Properties::Generate with num > 1 (Solver.cpp:186-241) on the reference's own multi-species example inputs: grids
+    from the largest sigmas, one W table per pair, one M table per species -- bit for bit"""
+    g = np.load(os.path.join(ROOT, "tests", "golden", f"multi_{name}.npz"))
+    s = int(g["species"])
+    sw = {2: [[0.05, 0.06], [0.06, 0.05]], 3: [[0.05, 0.06, 0.07], [0.06, 0.05, 0.04], [0.07, 0.04, 0.05]]}[s]
+    p = ldm.Properties.Generate(s, sw, [0.05] * s, [0.4, 0.401, 0.4001][:s], [0.2] * s, np.full((s, s), 0.001))
+    assert (p.SpeciesNumber, p.G, p.K) == (s, int(g["G"]), int(g["K"]))
+    assert np.array_equal(p.MaxNumForM, g["mM"]) and np.array_equal(p.MaxNumForW, g["mW"])
+    assert np.array_equal(p.MomentsGrid, g["moments_grid"]) and np.array_equal(p.KernelsGrid, g["kernels_grid"])
+    assert np.array_equal(p.M, g["M"]) and np.array_equal(p.W, g["W"])
+    assert p.state_size == g["state"].size
+
+
 def test_header_symbols_are_exported(ldm):
     header = open(os.path.join(ROOT, "include", "ldm.h")).read()
     declared = set(re.findall(r"\b(ldm_[a-z_A-Z0-9]+)\s*\(", header))
@@ -67,7 +82,7 @@ def test_point_count(ldm):
 
 def test_bad_arguments_are_reported(ldm):
     with pytest.raises(ldm.LdmError):
-        ldm.Properties.Generate(2, 0.1, 0.1, 0.4, 0.2, 0.001)       # species != 1: UNSUPPORTED in the reference's Data/
+        ldm.Properties.Generate(5, np.full((5, 5), 0.1), [0.1] * 5, [0.4] * 5, [0.2] * 5, np.full((5, 5), 0.001))   # > LDM_MAX_SPECIES
     with pytest.raises(ldm.LdmError):
         ldm.Properties.Generate(1, -1.0, 0.1, 0.4, 0.2, 0.001)
 

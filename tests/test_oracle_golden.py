@@ -9,7 +9,7 @@ import pytest
 
 from oracle import OracleProblem
 
-GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if not os.path.basename(p).startswith(("large_", "extras_")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if not os.path.basename(p).startswith(("large_", "extras_", "multi_")))
 
 
 def make_oracle(g, name):
