@@ -61,13 +61,21 @@ struct Properties
 
     std::shared_ptr<ldm_problem> flat;   // what the kernels consume
 
-    // Properties::Generate (S:186-241).  One species: the reference's own multi-species inputs are marked UNSUPPORTED.
+    // Properties::Generate (S:186-241), one or several species.
     static Properties Generate(int num, Matrix sW, Vector sM, Vector b, Vector d, Matrix dd,
                                KernelType = Normal, KernelType = Normal)
     {
-        if (num != 1) throw std::invalid_argument("only one species is supported");
         ldm_problem* raw = nullptr;
-        ldm_require(ldm_problem_generate(sW[0][0], sM[0], b[0], d[0], dd[0][0], 0, &raw), "ldm_problem_generate");
+        if (num == 1) {
+            ldm_require(ldm_problem_generate(sW[0][0], sM[0], b[0], d[0], dd[0][0], 0, &raw), "ldm_problem_generate");
+        } else {
+            std::vector<double> w, m, vb, vd, vdd;
+            for (int i = 0; i < num; i++) {
+                m.push_back(sM[i]); vb.push_back(b[i]); vd.push_back(d[i]);
+                for (int j = 0; j < num; j++) { w.push_back(sW[i][j]); vdd.push_back(dd[i][j]); }
+            }
+            ldm_require(ldm_problem_generate_multi(num, w.data(), m.data(), vb.data(), vd.data(), vdd.data(), 0, &raw), "ldm_problem_generate_multi");
+        }
         Properties p;
         p.flat = std::shared_ptr<ldm_problem>(raw, ldm_problem_free);
         p.SpeciesNumber = num;
@@ -79,13 +87,24 @@ struct Properties
         std::cout << "number of mid-points for pair density grid: " << raw->G
                   << "\nnumber of mid-points for kernels grid:      " << raw->K << "\n\n";        // S:85-86
         const int K = raw->K;
-        Matrix m(K), w(K);
-        for (int x = 0; x < K; x++)
-            for (int y = 0; y < K; y++) { m[x][y] = raw->M[(size_t)x * K + y]; w[x][y] = raw->W[(size_t)x * K + y]; }
-        p.M = VectorOfMatrix(1); p.M(0) = m;
-        p.W = MatrixOfMatrix(1); p.W(0, 0) = w;
-        p.MaxNumForM = Vector(1, (CalcType)raw->mM);
-        p.MaxNumForW = Matrix(1, (CalcType)raw->mW);
+        p.M = VectorOfMatrix(num);
+        p.W = MatrixOfMatrix(num);
+        p.MaxNumForM = Vector(num);
+        p.MaxNumForW = Matrix(num);
+        for (int i = 0; i < num; i++) {
+            Matrix m(K);
+            for (int x = 0; x < K; x++)
+                for (int y = 0; y < K; y++) m[x][y] = raw->M[((size_t)i * K + x) * K + y];
+            p.M(i) = m;
+            p.MaxNumForM[i] = num == 1 ? (CalcType)raw->mM : (CalcType)raw->mM_of[i];
+            for (int j = 0; j < num; j++) {
+                Matrix w(K);
+                for (int x = 0; x < K; x++)
+                    for (int y = 0; y < K; y++) w[x][y] = raw->W[(((size_t)i * num + j) * K + x) * K + y];
+                p.W(i, j) = w;
+                p.MaxNumForW[i][j] = num == 1 ? (CalcType)raw->mW : (CalcType)raw->mW_of[i * num + j];
+            }
+        }
         return p;
     }
 
@@ -115,14 +134,14 @@ public:
         handle = std::shared_ptr<ldm_context>(h, ldm_destroy);
     }
 
-    int state_size() const { return 1 + props.flat->G * props.flat->G; }
+    int state_size() const { const int n = props.flat->species; return n + n * n * props.flat->G * props.flat->G; }   // S:260
     ldm_handle raw() const { return handle.get(); }
     const Properties& properties() const { return props; }
 
     Vector GenerateEquilibriumValuesForNAndC(CalcType value)     // S:416-428
     {
         Vector out(state_size(), value * value);
-        out[0] = value;
+        for (int i = 0; i < props.flat->species; i++) out[i] = value;
         return out;
     }
 
@@ -387,7 +406,23 @@ class Experiments
         std::cout << "\n==========================CALCULATIONS START==========================\n";
         const auto start = std::chrono::steady_clock::now();
         Vector c_cut;
-        solver.SolveObservables(equation, t_max, 0.1, equation.GenerateEquilibriumValuesForNAndC(200), times, N, c_cut, true);
+        if (Props.SpeciesNumber == 1) {
+            solver.SolveObservables(equation, t_max, 0.1, equation.GenerateEquilibriumValuesForNAndC(200), times, N, c_cut, true);
+        } else {
+            // several species: the reference plots Values[k].first() and Values[k][MomentsGrid.size()] whatever the species
+            // count (S:1080-1087), i.e. N of the first species and entry G of the state vector
+            const int n = ldm_count_points(t_max, 0.1), width = equation.state_size(), G = Props.MomentsGrid.size();
+            Vector init = equation.GenerateEquilibriumValuesForNAndC(200);
+            std::vector<double> t((size_t)n), values((size_t)n * width);
+            int got = 0;
+            ldm_require(ldm_solve(equation.raw(), init.raw(), 0.1, t_max, LDM_RECORD_VALUES, t.data(), values.data(), nullptr, &got), "ldm_solve");
+            for (int k = 0; k < got; k++) {
+                times.add(t[(size_t)k]);
+                N.add(values[(size_t)k * width]);
+                c_cut.add(values[(size_t)k * width + G]);
+                std::cout << "   t = " << t[(size_t)k] << ";   N = " << values[(size_t)k * width] << '\n';
+            }
+        }
         std::cout << "\n===========================CALCULATIONS END===========================\n";
         std::cout << "TIME:  " << Time(seconds_since(start)) << '\n';
         for (int k = 0; k < c_cut.size(); k++) CSquareRoot.add(std::sqrt(c_cut[k]));     // S:1014-1015

@@ -347,3 +347,91 @@ int ldmo_solve_rk4(const ldmo_problem* p, double t_max, double dt, const double*
     for (int i = 0; i < 4; i++) free(c[i]);
     return k + 1;
 }
+
+
+/* ---- several species ---- */
+void ldmo_rhs_multi(const ldmo_multi* p, const double* state, double* deriv)
+{
+    const int s = p->species, G = p->G, K = p->K;
+    const size_t P = (size_t)G * G, KK = (size_t)K * K;
+    const double* N = state;
+    ldmo_problem shared;                                   /* what ldmo_pair_integral / ldmo_bilinear read: the grids */
+    memset(&shared, 0, sizeof shared);
+    shared.G = G; shared.K = K; shared.h = p->h; shared.cutoff = p->cutoff;
+    shared.moments_grid = (double*)p->moments_grid; shared.kernels_grid = (double*)p->kernels_grid;
+
+    double* WC = (double*)malloc(sizeof(double) * (size_t)s * s);
+    double* MC = (double*)malloc(sizeof(double) * (size_t)s * s * P);
+    for (int i = 0; i < s; i++)                                                          /* S:265-274 */
+        for (int j = 0; j < s; j++)
+            WC[i * s + j] = ldmo_pair_integral(&shared, 0, 0, p->mW[i * s + j], p->W + (size_t)(i * s + j) * KK,
+                                               state + s + (size_t)(i * s + j) * P, N[i] * N[j]);
+    for (int i = 0; i < s; i++)                                                          /* S:277-295 */
+        for (int j = 0; j < s; j++) {
+            const double* C = state + s + (size_t)(i * s + j) * P;
+            double* out = MC + (size_t)(i * s + j) * P;
+            #pragma omp parallel for collapse(2) schedule(dynamic, 4)
+            for (int x = 0; x < G; x++)
+                for (int y = 0; y < G; y++)
+                    out[(size_t)x * G + y] = ldmo_pair_integral(&shared, x, y, p->mM[i], p->M + (size_t)i * KK, C, N[i] * N[j]);
+        }
+    for (int i = 0; i < s; i++) {                                                        /* S:446-451 */
+        double dN = N[i] * (p->b[i] - p->d[i]);
+        double d_prime_sum = 0;
+        for (int j = 0; j < s; j++) d_prime_sum = d_prime_sum + p->dd[i * s + j] * WC[i * s + j];
+        deriv[i] = dN - d_prime_sum;
+    }
+    for (int i = 0; i < s; i++)                                                          /* S:454-508 */
+        for (int j = 0; j < s; j++) {
+            const double* Cij = state + s + (size_t)(i * s + j) * P;
+            const double* Cji = state + s + (size_t)(j * s + i) * P;
+            const double* MCij = MC + (size_t)(i * s + j) * P;
+            const double* MCji = MC + (size_t)(j * s + i) * P;
+            for (int x = 0; x < G; x++)
+                for (int y = 0; y < G; y++) {
+                    const size_t q = (size_t)x * G + y;
+                    double result = p->b[i] * MCij[q] + p->b[j] * MCji[q];
+                    if (i == j)
+                        result += 2 * p->b[i] * N[i] * ldmo_bilinear(p->kernels_grid, K, p->M + (size_t)i * KK,
+                            p->moments_grid[x], p->moments_grid[y], p->sigmaM[i] * 3, 0, 0.0);
+                    result -= p->d[i] * Cij[q];
+                    result -= p->d[j] * Cji[q];
+                    for (int k = 0; k < s; k++) {
+                        result -= p->dd[i * s + k] * WC[i * s + k] * Cij[q] / N[i];
+                        result -= p->dd[j * s + k] * WC[j * s + k] * Cji[q] / N[j];
+                    }
+                    result -= p->dd[i * s + j] * Cij[q] * ldmo_bilinear(p->kernels_grid, K, p->W + (size_t)(i * s + j) * KK,
+                        p->moments_grid[x], p->moments_grid[y], p->sigmaW[i * s + j] * 3, 0, 0.0);
+                    result -= p->dd[j * s + i] * Cji[q] * ldmo_bilinear(p->kernels_grid, K, p->W + (size_t)(j * s + i) * KK,
+                        p->moments_grid[x], p->moments_grid[y], p->sigmaW[j * s + i] * 3, 0, 0.0);
+                    deriv[s + (size_t)(i * s + j) * P + q] = result;
+                }
+        }
+    free(WC); free(MC);
+}
+
+int ldmo_solve_multi(const ldmo_multi* p, double t_max, double dt, const double* init, double* times, double* values)
+{
+    const size_t n = (size_t)p->species + (size_t)p->species * p->species * p->G * p->G;
+    double* value = (double*)malloc(sizeof(double) * n);
+    double* derivative = (double*)malloc(sizeof(double) * n);
+    memcpy(value, init, sizeof(double) * n);
+    double time = 0;
+    ldmo_rhs_multi(p, value, derivative);
+    int k = 0;
+    for (;;) {
+        if (times) times[k] = time;
+        if (values) memcpy(values + (size_t)k * n, value, sizeof(double) * n);
+        time += dt;
+        if (!(time < t_max)) break;
+        for (size_t q = 0; q < n; q++) {
+            double v = value[q] + derivative[q] * dt;
+            if (v < 0) v = 0;
+            value[q] = v;
+        }
+        ldmo_rhs_multi(p, value, derivative);
+        k++;
+    }
+    free(value); free(derivative);
+    return k + 1;
+}

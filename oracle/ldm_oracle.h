@@ -72,6 +72,28 @@ void ldmo_set_extrapolation(int type);
 int ldmo_count_points_rk4(double t_max, double dt);
 int ldmo_solve_rk4(const ldmo_problem* p, double t_max, double dt, const double* init, double* times, double* values, double* derivs);
 
+/* ---- several species (S:265-295, S:446-511 with SpeciesNumber > 1).  State: [N_0..N_{s-1} | C_00 | C_01 | ...], each C_ij
+ * G*G row-major (S:255-262).  Tables and grids as the reference's Properties holds them (shared grids; M(i): s tables,
+ * W(i,j): s*s tables, K*K row-major each). ---- */
+typedef struct ldmo_multi {
+    int species, G, K;
+    double h, cutoff;
+    const int* mM;             /* s     MaxNumForM[i]    */
+    const int* mW;             /* s*s   MaxNumForW[i][j] */
+    const double* sigmaM;      /* s */
+    const double* sigmaW;      /* s*s */
+    const double* b;           /* s */
+    const double* d;           /* s */
+    const double* dd;          /* s*s */
+    const double* moments_grid;
+    const double* kernels_grid;
+    const double* M;           /* s * K*K */
+    const double* W;           /* s*s * K*K */
+} ldmo_multi;
+void ldmo_rhs_multi(const ldmo_multi* p, const double* state, double* deriv);
+/* EulerSolver::Solve (S:557-592) on such a state: full history, values n_points * width; returns the number of points */
+int ldmo_solve_multi(const ldmo_multi* p, double t_max, double dt, const double* init, double* times, double* values);
+
 /* threads the integrals' outer loop may use (results are identical for any count) */
 void ldmo_set_threads(int n);
 

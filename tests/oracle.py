@@ -41,6 +41,44 @@ def _load():
     return lib
 
 
+class _Multi(C.Structure):
+    _fields_ = [("species", C.c_int), ("G", C.c_int), ("K", C.c_int), ("h", C.c_double), ("cutoff", C.c_double),
+                ("mM", C.c_void_p), ("mW", C.c_void_p), ("sigmaM", C.c_void_p), ("sigmaW", C.c_void_p), ("b", C.c_void_p),
+                ("d", C.c_void_p), ("dd", C.c_void_p), ("moments_grid", C.c_void_p), ("kernels_grid", C.c_void_p),
+                ("M", C.c_void_p), ("W", C.c_void_p)]
+
+
+class OracleMulti:
+    """several species (ldm_oracle.h ldmo_multi): the tables are handed in (from the product's host generator or a fixture)"""
+
+    def __init__(self, mM, mW, sigmaM, sigmaW, b, d, dd, moments_grid, kernels_grid, M, W):
+        self.lib = lib()
+        self.lib.ldmo_rhs_multi.argtypes = [C.POINTER(_Multi), _dp, _dp]
+        self.lib.ldmo_solve_multi.restype = C.c_int
+        self.lib.ldmo_solve_multi.argtypes = [C.POINTER(_Multi), C.c_double, C.c_double, _dp, C.c_void_p, C.c_void_p]
+        f64 = lambda v: np.ascontiguousarray(v, dtype=np.float64)
+        i32 = lambda v: np.ascontiguousarray(v, dtype=np.int32)
+        self.keep = [i32(mM), i32(mW), f64(sigmaM), f64(sigmaW), f64(b), f64(d), f64(dd), f64(moments_grid), f64(kernels_grid), f64(M), f64(W)]
+        self.s, self.G, self.K = len(self.keep[0]), len(self.keep[7]), len(self.keep[8])
+        kg = self.keep[8]
+        self.p = _Multi(self.s, self.G, self.K, kg[2] - kg[0], self.keep[7][-1], *[a.ctypes.data for a in self.keep])
+        self.width = self.s + self.s ** 2 * self.G ** 2
+
+    def rhs(self, state):
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        out = np.zeros_like(state)
+        self.lib.ldmo_rhs_multi(C.byref(self.p), state, out)
+        return out
+
+    def solve(self, t_max, dt, init):
+        n = self.lib.ldmo_count_points(t_max, dt)
+        times, values = np.zeros(n), np.zeros((n, self.width))
+        got = self.lib.ldmo_solve_multi(C.byref(self.p), t_max, dt, np.ascontiguousarray(init, dtype=np.float64),
+                                        times.ctypes.data, values.ctypes.data)
+        assert got == n
+        return times, values
+
+
 _LIB = None
 
 

@@ -84,6 +84,24 @@ def test_experiment_14_4_writes_visdata(tmp_path, choice, golden, title):
 
 
 @pytest.mark.gpu
+def test_custom_experiment_with_two_species(tmp_path):
+    """Custom_Experiment (Solver.cpp:1073-1103) on the reference's own two-species example input, copied to where the
+    experiment reads it: same positional parser, Properties::Generate with num = 2, 1001 points, and the two columns the
+    reference plots whatever the species count -- Values[k][0] and Values[k][G]"""
+    solver = build_solver()
+    os.makedirs(tmp_path / "Data" / "Custom")
+    with open(tmp_path / "Data" / "Custom" / "experiment.csv", "w", newline="") as fh:       # the reference ships CRLF files
+        fh.write("Number of,2,\r\nspecies,,\r\n,,\r\nSigma W,0.05,0.06\r\n,0.06,0.05\r\n,,\r\nSigma M,0.05,0.05\r\n,,\r\n"
+                 "b,0.4,0.401\r\nd,0.2,0.2\r\nd',0.001,0.001\r\n,0.001,0.001\r\n")
+    subprocess.check_call([solver, "custom"], cwd=tmp_path, stdout=subprocess.DEVNULL, timeout=600)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "multi_2_species.npz"))
+    number, title, labels, data = read_visdata(tmp_path / "Data" / "VisData.csv")
+    assert number == 1 and title == "My experiment" and data.shape == (1001, 3)
+    want = np.stack([g["custom_times"], g["custom_columns"][:, 0], np.sqrt(g["custom_columns"][:, 1])], 1)
+    assert np.allclose(data, want, rtol=1e-5, atol=0)
+
+
+@pytest.mark.gpu
 def test_experiment_14_6_b_sweep(tmp_path):
     """the whole 160-entry sweep of Experiment_14_6('M') (Solver.cpp:1033-1071) as one batched call"""
     solver = build_solver()

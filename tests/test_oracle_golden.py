@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from oracle import OracleProblem
+from oracle import OracleMulti, OracleProblem
 
 GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if not os.path.basename(p).startswith(("large_", "extras_", "multi_")))
 
@@ -100,3 +100,19 @@ def test_runge_kutta_and_extrapolation_types_bitwise(name):
             assert not np.array_equal(g[f"{label}_deriv_k100"], base["deriv_k100"])
     finally:
         o.set_extrapolation(1)
+
+
+@pytest.mark.parametrize("name", ["2_species", "3_species"])
+def test_several_species_bitwise(name):
+    """SURVEY 8f rank 4: Equation::operator() and EulerSolver with SpeciesNumber > 1 (Solver.cpp:265-295, 446-511) as
+    restated in the oracle, against the reference itself on its own multi-species example inputs"""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", f"multi_{name}.npz"))
+    s = int(g["species"])
+    sw = {2: [[0.05, 0.06], [0.06, 0.05]], 3: [[0.05, 0.06, 0.07], [0.06, 0.05, 0.04], [0.07, 0.04, 0.05]]}[s]
+    o = OracleMulti(g["mM"], g["mW"], [0.05] * s, sw, [0.4, 0.401, 0.4001][:s], [0.2] * s, np.full((s, s), 0.001),
+                    g["moments_grid"], g["kernels_grid"], g["M"], g["W"])
+    assert np.array_equal(o.rhs(g["state"]), g["deriv"])
+    assert np.array_equal(o.rhs(np.concatenate([np.full(s, 200.0), np.full(s * s * o.G ** 2, 40000.0)])), g["deriv_equilibrium"])
+    steps = 10
+    t, v = o.solve(steps * 0.1 + 0.05, 0.1, g["state"])
+    assert np.array_equal(t, g["times"][:steps + 1]) and np.array_equal(v, g["values"][:steps + 1])
