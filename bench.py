@@ -348,6 +348,31 @@ def run_batch(ldm, torch, dist, rank, world, local_rank, per_gpu, steps, G=64):
             "checksum": float(sum(o.sum() for o in outs))}
 
 
+def run_sweep(ldm, torch, local_rank):
+    """Experiment 14.6 a as the reference defines it (Solver.cpp:909-977, 1033-1071): 160 entries, sigma_W = linspace(1e-8, 0.2),
+    sigma_M = 0.08, 2000 Euler steps each, every entry with its own grids (G 11..39, K 23..227) -- set up on the host,
+    advanced as ONE batch (ldm_solve_batch), last states read back.  Wall clock, set-up included: what a user waits for."""
+    sigmas = np.linspace(1e-8, 0.2, 160)          # Vector::setLinSpaced(160, EPSILON, 0.2): same values to the last bit but one
+    sigmas[-1] = 0.2
+    t0 = time.perf_counter()
+    eqs, inits = [], []
+    for sw in sigmas:
+        props = ldm.Properties.Generate(1, float(sw), 0.08, 0.4, 0.2, 0.001)
+        eq = ldm.Equation(props, device=local_rank)
+        eqs.append(eq)
+        inits.append(eq.GenerateEquilibriumValuesForNAndC(200))
+    setup_s = time.perf_counter() - t0
+    outs = ldm.solve_batch(eqs, inits, DT, 200)
+    total_s = time.perf_counter() - t0
+    points = sum(e.props.G ** 2 for e in eqs)
+    assert all(np.all(np.isfinite(o)) for o in outs)
+    return {"workload": "experiment 14.6 a: 160 entries x 2000 Euler steps, one batched call", "entries": 160, "steps": 2000,
+            "xi_points_total": points, "seconds_total": total_s, "seconds_setup": setup_s,
+            "value": points * 2000 / total_s, "unit": UNIT, "stepping_ms": eqs[0].last_elapsed_ms(),
+            "N_end": [float(outs[i][0]) for i in (0, 12, 80, 159)],
+            "reference": "estimated >= 15 h on 8 cores (SURVEY 6): entries i = 12 and 80 alone take 141 s and 20 s of one core"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -362,6 +387,7 @@ def main():
                     help="sharded leg at N > 1: all-gather fused into the update over NVLink peer stores, or an NCCL all-gather per step")
     ap.add_argument("--batch-sets", type=int, default=128, help="parameter sets per GPU of the batched leg (0 to skip)")
     ap.add_argument("--batch-steps", type=int, default=50)
+    ap.add_argument("--no-sweep", action="store_true", help="skip the experiment-14.6 sweep leg (N = 1 only)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -453,6 +479,8 @@ def main():
     if args.batch_sets > 0:
         batch = run_batch(ldm, torch, dist, rank, world, local_rank, args.batch_sets, args.batch_steps)
 
+    sweep = run_sweep(ldm, torch, local_rank) if (world == 1 and not args.no_sweep) else None
+
     if rank == 0:
         ms_per_step = total_ms / args.steps
         achieved = flop_step / (ms_per_step * 1e-3) / 1e12
@@ -484,6 +512,8 @@ def main():
             line["sharded"] = sharded
         if batch is not None:
             line["batch"] = batch
+        if sweep is not None:
+            line["sweep"] = sweep
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload)
         print(json.dumps(line))

@@ -395,6 +395,29 @@ def test_prefix_chunkings_equal_direct(ldm, monkeypatch, G, bn):
     assert_states_close(prefix.download(), direct.download())
 
 
+@pytest.mark.parametrize("G,sw,sm", [(4, 0.1, 0.1), (7, 0.05, 0.12), (33, 0.2, 0.02), (31, 0.012, 0.1), (12, 0.05, 1e-8)])
+def test_tiny_and_degenerate_grids_equal_direct(ldm, G, sw, sm):
+    """edges of the table shapes: the smallest grids forced_G admits, one y block that is not full, a refined kernel grid
+    (sigma < 0.015, S:80-84), and the degenerate m-kernel of experiment 14.6 b entry 0 (sigma_M -> 0: one quadrature node,
+    MaxNumForM == 2, S:131-132) -- every algorithm against the sample-by-sample sum, through a few Euler steps"""
+    props = ldm.Properties.Generate(1, sw, sm, 0.4, 0.2, 0.001, G)
+    direct = ldm.Equation(props, algorithm=ldm.ALGO_DIRECT)
+    g = props.MomentsGrid
+    st = direct.GenerateEquilibriumValuesForNAndC(200)
+    st[1:] *= (1 + 0.4 * np.exp(-(g[:, None] ** 2 + g[None, :] ** 2) / (2 * (sw + sm) ** 2)) + 0.05 * np.cos(5 * g[:, None] - 2 * g[None, :])).ravel()
+    w1, m1 = direct.integrals(st)
+    direct.upload(st)
+    direct.advance(6, 0.1)
+    want = direct.download()
+    for algorithm in ("prefix", "factored"):
+        eq = ldm.Equation(props, algorithm=algo_id(ldm, algorithm))
+        w2, m2 = eq.integrals(st)
+        assert abs(w1 - w2) <= 1e-14 * abs(w1) and np.all(np.abs(m1 - m2) <= 1e-13 * np.abs(m1)), algorithm
+        eq.upload(st)
+        eq.advance(6, 0.1)
+        assert_states_close(eq.download(), want)
+
+
 def test_table_that_is_not_separable_takes_the_dense_contraction(ldm):
     """ldm_create accepts any K x K table; the prefix-sum path is only taken when the table passes the structure check
     (a truncated Gaussian does).  A table with one perturbed entry must fall back to the dense contraction -- and still
