@@ -201,9 +201,25 @@ def cpu_baseline(workload, budget_s=25.0):
         sec = time.perf_counter() - t0
         if sec * (n + 1) / n > budget_s or n >= 50:
             break
-    return {"value": p.P * n / sec, "unit": UNIT, "cores": 1, "kind": "reference",
-            "sample": f"{n} Euler step(s) in {sec:.1f} s, single thread (the reference is serial on this route); "
-                      "reference source built by-reference (bit-identical to the shipped build, which is ~30x slower)"}
+    out = {"value": p.P * n / sec, "unit": UNIT, "cores": 1, "kind": "reference",
+           "sample": f"{n} Euler step(s) in {sec:.1f} s, single thread (the reference is serial on this route); "
+                     "reference source built by-reference (bit-identical to the shipped build, which is ~30x slower)"}
+    # beside it: what the host could do at best with the same algorithm -- the C restatement (oracle/, bit-identical to the
+    # reference) with its outer node loop spread over every core the box has
+    try:
+        from oracle import OracleProblem, lib as oracle_lib
+        cores = len(os.sched_getaffinity(0))
+        oracle_lib().ldmo_set_threads(cores)
+        o = OracleProblem(sw, sm, b, d, dd, G)
+        st = seeded_state(grid, sm)
+        t0 = time.perf_counter()
+        o.rhs(st)
+        sec_port = time.perf_counter() - t0
+        out["all_cores_port"] = {"value": p.P / sec_port, "unit": UNIT, "cores": cores, "kind": "port",
+                                 "sample": f"1 right-hand side (> 99.9 % of a step) in {sec_port:.2f} s, OpenMP over the grid nodes"}
+    except Exception as e:           # the baseline must not take the bench line down
+        out["all_cores_port"] = {"error": str(e)}
+    return out
 
 
 def run_sharded_peer(ldm, torch, dist, workload, rank, world, local_rank, steps, warmup):
