@@ -31,6 +31,10 @@
 #include "ldm_device.h"
 #include "ldm_pointwise.cuh"
 
+#ifndef LDM_Y_UNROLL
+#define LDM_Y_UNROLL 4
+#endif
+
 namespace ldm {
 
 // Optional phase timeline (debug build `make phase-clocks`): thread 0 of every CTA stores clock64() at the phase
@@ -111,6 +115,11 @@ __device__ __forceinline__ int folded_offset(int A, int n_fold, int alpha, int f
     return n_fold == 1 ? 0 : (f == 0 ? A - 1 - alpha : A + alpha);
 }
 
+#ifndef LDM_Y_UNROLL
+#define LDM_Y_UNROLL 4
+#endif
+constexpr int kYUnroll = LDM_Y_UNROLL;      // (node, offset) pairs whose table reads are in flight together per lane
+
 // y side over one interval of offsets for one lane's node y.  MASKED: the chunk holds only columns [q0, q0 + bn), the
 // two taps of a pair are taken separately.  CACHED (persistent kernel): 16-bit interval indices and the first
 // cached_w_rows weight rows live in shared memory.
@@ -121,7 +130,7 @@ __device__ __forceinline__ double y_side_interval(const DevProblem& P, const dou
     const int G = P.G, A = P.A;
     const bool single = P.n_off == 1;
     double s = 0.0;
-    #pragma unroll 4
+    #pragma unroll kYUnroll
     for (int o = lo; o < hi; o += step) {
         const int beta = single ? 0 : (o < A ? A - 1 - o : o - A);
         const size_t at = (size_t)o * G + y;
