@@ -64,6 +64,7 @@ struct ldm_context {
     double* d_deriv = nullptr;             // [P] dC/dt
     double* d_partial = nullptr;           // [tiles][P] factored path: per beta-tile sums
     double* d_ring = nullptr;              // [P] factored path: samples between the cutoff circle and the square edge
+    double* d_out_exp = nullptr;           // [P] Exponential extrapolation: per-node sum over the outside samples, this step's decay
     double* d_wc_rows = nullptr;           // [G] factored path: per-row dot products of the WC operator (3-kernel path)
     double* d_wc_rows2 = nullptr;          // [2][G] the same inside the prefix-sum persistent kernel (ping-pong with the state)
     unsigned int* d_barrier = nullptr;     // [1 + G] arrival counter of that kernel's grid barrier, then its per-row ring counts
@@ -246,6 +247,7 @@ ldm::StepArgs make_step_args(ldm_context* c, const double* C, const double* N_cu
     a.C = C; a.N_cur = N_cur; a.N_next = N_next;
     a.partial = c->d_partial; a.ring = c->d_ring; a.wc_rows = c->d_wc_rows; a.scalars = c->d_scalars;
     a.sum_out = sum_out; a.deriv_out = deriv_out; a.C_next = C_next;
+    a.out_exp = nullptr;
     a.tiles = c->plan.tiles; a.chunks = c->plan.chunks;
     a.peer_count = 0; a.done_counter = nullptr; a.epoch = 0;
     a.dt = dt;
@@ -263,16 +265,27 @@ void launch_integral(ldm_context* c, const ldm::StepArgs& args, cudaStream_t s)
 void rhs_and_update(ldm_context* c, const DevProblem& P, const double* C, const double* N_cur, double* N_next, double dt,
                     double* sum_out, double* deriv_out, double* C_next, cudaStream_t s)
 {
+    const double* out_exp = nullptr;
+    if (P.extrapolation == LDM_EXTRAPOLATION_EXPONENTIAL) {
+        // the one type whose outside value depends on each sample's own distance, through a decay rate that changes every
+        // step (S:392-408): the per-step scalars, then the outside samples of every node enumerated one by one
+        if (!c->d_out_exp) c->d_out_exp = c->alloc<double>(c->P());
+        ldm::launch_exponential_prepare(P, C, N_cur, c->d_scalars, s);
+        ldm::launch_sample_sum(P, ldm::SAMPLES_OUT_EXP, C, c->d_out_exp, s, c->d_scalars);
+        c->launches += 2;
+        out_exp = c->d_out_exp;
+    }
     if (c->algo == LDM_ALGO_DIRECT) {
         ldm::launch_sample_sum(P, ldm::SAMPLES_INSIDE, C, c->d_sum, s);
         ldm::launch_wc(P, C, N_cur, N_next, c->d_scalars, dt, s);
-        ldm::launch_pointwise(P, C, c->d_sum, N_cur, c->d_scalars, dt, deriv_out, C_next, s);
+        ldm::launch_pointwise(P, C, c->d_sum, N_cur, c->d_scalars, dt, deriv_out, C_next, s, out_exp);
         c->launches += 3;
         return;
     }
     ensure_ring_operator(c);
     if (c->plan.use_w) ensure_w_operand(c);
-    const ldm::StepArgs args = make_step_args(c, C, N_cur, N_next, dt, sum_out, deriv_out, C_next);
+    ldm::StepArgs args = make_step_args(c, C, N_cur, N_next, dt, sum_out, deriv_out, C_next);
+    args.out_exp = out_exp;
     // the sparse ring correction only reads C: it runs on a side stream beside the (register-bound, one CTA per
     // SM) factored kernel and joins before the closing kernel
     const bool side = args.P.n_ring > 0;
@@ -373,6 +386,7 @@ void multi_download_derivs(ldm_context* c, double* deriv, cudaStream_t s)
 bool persistent_possible(ldm_context* c)
 {
     if (!c->persistent_enabled || c->algo == LDM_ALGO_DIRECT || c->dev.world != 1) return false;
+    if (c->dev.extrapolation == LDM_EXTRAPOLATION_EXPONENTIAL) return false;        // needs its own launches every step
     const ldm::FactoredPlan& p = c->plan;
     if (p.slabs() != 1 || p.use_w || (!p.scan && !p.mma)) return false;
     if (c->persistent_grid == 0) {
@@ -534,6 +548,7 @@ int ldm_shard_peer_step(ldm_handle h, double dt, void* cuda_stream)
     if (!h) return fail(LDM_ERR_ARGUMENT, "NULL handle");
     if (!h->peer_connected) return fail(LDM_ERR_ARGUMENT, "peers are not connected");
     if (h->algo == LDM_ALGO_DIRECT) return fail(LDM_ERR_UNSUPPORTED, "the fused exchange rides on the factored path");
+    if (h->dev.extrapolation == LDM_EXTRAPOLATION_EXPONENTIAL) return fail(LDM_ERR_UNSUPPORTED, "Exponential extrapolation: use ldm_shard_step");
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
         cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
@@ -714,6 +729,11 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         d.G = t.G; d.n_off = t.offM.n_off; d.A = t.offM.A;
         d.world = 1; d.rank = 0; d.rows_per_rank = t.G;
         d.extrapolation = LDM_EXTRAPOLATION_SQUARED_N;
+        d.cutoff = p->cutoff;
+        for (int k = 1; k < 5; k++) d.tail_gap[k - 1] = p->G > k ? p->cutoff - p->moments_grid[p->G - 1 - k] : 1.0;   // S:397
+        d.wc_out_w = c->upload(t.wc_out_w);
+        d.wc_out_distance = c->upload(t.wc_out_distance);
+        d.wc_out_n = (int)t.wc_out_w.size();
         d.hh = t.hh; d.b = t.b; d.d = t.d; d.dd = t.dd; d.s_max = t.s_max; d.wc_outside = t.wc_outside;
         d.s = c->upload(t.axisM.s);
         d.limit = c->upload(t.axisM.limit);
@@ -849,10 +869,9 @@ int ldm_get_algorithm(ldm_handle h) { return h ? h->algo : LDM_ERR_ARGUMENT; }
 int ldm_set_extrapolation(ldm_handle h, int type)
 {
     if (!h) return fail(LDM_ERR_ARGUMENT, "NULL handle");
-    if (type == LDM_EXTRAPOLATION_EXPONENTIAL)
-        return fail(LDM_ERR_UNSUPPORTED, "Exponential extrapolation (Solver.cpp:392-408) is reachable from no experiment of the reference and is not built");
-    if (type != LDM_EXTRAPOLATION_ZERO && type != LDM_EXTRAPOLATION_SQUARED_N && type != LDM_EXTRAPOLATION_ALPHA)
-        return fail(LDM_ERR_ARGUMENT, "unknown extrapolation type");
+    if (type == LDM_EXTRAPOLATION_EXPONENTIAL && (h->species != 1 || h->dev.G < 5))
+        return fail(LDM_ERR_UNSUPPORTED, "Exponential extrapolation is built for one species on grids of at least 5 nodes (it reads the last 5 of row 0, Solver.cpp:394-401)");
+    if (type < LDM_EXTRAPOLATION_ZERO || type > LDM_EXTRAPOLATION_EXPONENTIAL) return fail(LDM_ERR_ARGUMENT, "unknown extrapolation type");
     h->dev.extrapolation = type;
     return LDM_OK;
 }
@@ -983,10 +1002,18 @@ int ldm_integrals(ldm_handle h, const double* state, double* WC, double* MC)
         if (MC) {   // the same closing expression as the pointwise kernel
             std::vector<double> ow(h->P());
             LDM_CUDA(cudaMemcpy(ow.data(), h->dev.out_weight, h->P() * sizeof(double), cudaMemcpyDeviceToHost));
-            const double N = state[0], asymptote = N * N, last = state[h->dev.G];        // outside_value() of ldm_pointwise.cuh
-            const double beyond = (h->dev.extrapolation == LDM_EXTRAPOLATION_SQUARED_N || std::fabs(last - asymptote) < 1e-8) ? asymptote
-                                  : h->dev.extrapolation == LDM_EXTRAPOLATION_ZERO ? 0.0 : state[1];
-            for (size_t q = 0; q < h->P(); q++) MC[q] = (sum[q] + beyond * ow[q]) * h->dev.hh;
+            const double N = state[0], asymptote = N * N, last = state[h->dev.G];        // outside_value() / outside_sum() of ldm_pointwise.cuh
+            if (h->dev.extrapolation == LDM_EXTRAPOLATION_EXPONENTIAL) {
+                std::vector<double> ex(h->P());
+                double sc[ldm::kScalars];
+                LDM_CUDA(cudaMemcpy(ex.data(), h->d_out_exp, h->P() * sizeof(double), cudaMemcpyDeviceToHost));
+                LDM_CUDA(cudaMemcpy(sc, h->d_scalars, sizeof sc, cudaMemcpyDeviceToHost));
+                for (size_t q = 0; q < h->P(); q++) MC[q] = (sum[q] + (asymptote * ow[q] + sc[3] * ex[q])) * h->dev.hh;
+            } else {
+                const double beyond = (h->dev.extrapolation == LDM_EXTRAPOLATION_SQUARED_N || std::fabs(last - asymptote) < 1e-8) ? asymptote
+                                      : h->dev.extrapolation == LDM_EXTRAPOLATION_ZERO ? 0.0 : state[1];
+                for (size_t q = 0; q < h->P(); q++) MC[q] = (sum[q] + beyond * ow[q]) * h->dev.hh;
+            }
         }
     });
 }
@@ -1327,7 +1354,7 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
             ldm_context* h = handles[i];
             LDM_CUDA(cudaSetDevice(h->device));
             upload_state(h, inits[i]);
-            batched = batched && h->algo != LDM_ALGO_DIRECT && h->dev.world == 1;
+            batched = batched && h->algo != LDM_ALGO_DIRECT && h->dev.world == 1 && h->dev.extrapolation != LDM_EXTRAPOLATION_EXPONENTIAL;
         }
         for (int i = 0; i < n; i++) {
             LDM_CUDA(cudaSetDevice(handles[i]->device));

@@ -12,7 +12,13 @@ struct DevProblem {
     // xi-sharding: this rank computes rows x = rank, rank+world, ...; the full C is held in
     // "gathered" layout, row x at slot (x % world) * rows_per_rank + x / world.  world == 1: natural layout.
     int world, rank, rows_per_rank;
-    int extrapolation;         // ExtrapolationType of C beyond the cutoff (Solver.cpp:28): 0 Zero, 1 SquaredN (default), 2 Alpha
+    int extrapolation;         // ExtrapolationType of C beyond the cutoff (Solver.cpp:28): 0 Zero, 1 SquaredN (default), 2 Alpha, 3 Exponential
+    // Exponential only (Solver.cpp:392-408): the cutoff, its distance to the four moment nodes before the last, and the
+    // WC samples beyond the cutoff one by one
+    double cutoff, tail_gap[4];
+    const double* wc_out_w;
+    const double* wc_out_distance;
+    int wc_out_n;
     double hh;                 // KernelsGridStep^2 (Solver.cpp:314)
     double b, d, dd;
     double s_max;              // largest sample abscissa that is still inside the moment grid
@@ -78,6 +84,8 @@ struct StepArgs {
     double* sum_out;           // may be NULL: inside-sample sums
     double* deriv_out;         // may be NULL: dC/dt of this rank's rows
     double* C_next;            // may be NULL: updated rows
+    const double* out_exp;     // Exponential extrapolation: [local_rows][G] sum of m * exp(-decay (distance - cutoff)) over the
+                               // node's samples beyond the cutoff, this step's decay rate
     int tiles, chunks;         // factored plan: slab = tile * chunks + chunk
     // fused update + all-gather over NVLink (xi-sharded runs, ldm_shard_peer_*): when peer_count > 0 the closing kernel
     // stores every updated value straight into the next-step replica of EVERY rank (peer-mapped memory, own rank
@@ -99,11 +107,13 @@ struct StepArgs {
 enum SampleMode {
     SAMPLES_INSIDE = 0,        // sum m * bilinear(C) over samples inside the cutoff circle  -> the direct algorithm
     SAMPLES_RING = 1,          // ... over samples inside the grid square but outside the circle -> correction of the factored path
-    SAMPLES_OUT_WEIGHT = 2     // sum m over every sample outside the circle (time-invariant, run once at create)
+    SAMPLES_OUT_WEIGHT = 2,    // sum m over every sample outside the circle (time-invariant, run once at create)
+    SAMPLES_OUT_EXP = 3        // sum m * exp(-decay * (hypot(sx, sy) - cutoff)) over them, decay = scalars[2] (Exponential extrapolation)
 };
 
-// Scalars of one step, device resident: [0] WC, [1] dN/dt
-constexpr int kScalars = 4;
+// Scalars of one step, device resident: [0] WC, [1] dN/dt; Exponential extrapolation: [2] decay rate of this step,
+// [3] C[0][G-1] - N^2 (0 when the asymptote test of S:357 holds), [4] sum of w * exp(...) over the WC samples beyond the cutoff
+constexpr int kScalars = 8;
 
 __host__ __device__ inline int row_slot(const DevProblem& P, int x)
 {
@@ -121,7 +131,11 @@ void launch_rk4_stage(int n, const double* value, const double* c, double step, 
 void launch_rk4_close(int n, const double* value, const double* c0, const double* c1, const double* c2, const double* c3, double step,
                       double* out, cudaStream_t stream);
 
-void launch_sample_sum(const DevProblem& P, SampleMode mode, const double* C, double* out, cudaStream_t stream);
+void launch_sample_sum(const DevProblem& P, SampleMode mode, const double* C, double* out, cudaStream_t stream,
+                       const double* scalars = nullptr);
+// Exponential extrapolation, once per right-hand side: decay rate from row 0 of C (S:392-405), the factor C[0][G-1] - N^2
+// and the WC sum over the outside samples -> scalars[2..4]
+void launch_exponential_prepare(const DevProblem& P, const double* C, const double* N_cur, double* scalars, cudaStream_t stream);
 
 void launch_wc(const DevProblem& P, const double* C, const double* N_cur, double* N_next, double* scalars,
                double dt, cudaStream_t stream);
@@ -129,7 +143,8 @@ void launch_wc(const DevProblem& P, const double* C, const double* N_cur, double
 // Pointwise assembly (Solver.cpp:459-508) + optional explicit-Euler update and clamp (Solver.cpp:577-580).
 // inside_sum: per node sum over inside samples of m*C~ (unscaled).  deriv_out / C_next may be NULL.
 void launch_pointwise(const DevProblem& P, const double* C, const double* inside_sum, const double* N_cur,
-                      const double* scalars, double dt, double* deriv_out, double* C_next, cudaStream_t stream);
+                      const double* scalars, double dt, double* deriv_out, double* C_next, cudaStream_t stream,
+                      const double* out_exp = nullptr);
 
 // Closing kernel of the factored path: inside_sum = sum_tiles partial - ring, WC from the per-row dot products,
 // the first-moment equation with its update (block 0), then the same pointwise assembly/update as above.

@@ -448,8 +448,7 @@ persistent_kernel(const PersistentArgs A)
         }
         __syncthreads();
         const double N = S.N_cur[0];
-        const double beyond = outside_value(P, N, S.C);
-        const double WC = (wc_shared + beyond * P.wc_outside) * P.hh;              // Solver.cpp:311, 314
+        const double WC = __dmul_rn(add_outside(P, wc_shared, N, S.C, S.scalars, P.wc_outside, 0.0), P.hh);   // Solver.cpp:311, 314
         double* values_next = A.values ? A.values + (point + 1) * A.stride : nullptr;
         double* derivs_here = A.derivs ? A.derivs + point * A.stride : nullptr;
         if (blockIdx.x == 0 && tid == 0) {
@@ -460,7 +459,7 @@ persistent_kernel(const PersistentArgs A)
         for (int q = blockIdx.x * NT + tid; q < n; q += gridDim.x * NT) {
             const double inside = S.partial[q] - S.ring[q];
             const double c = S.C[q];
-            const double mc = (inside + beyond * P.out_weight[q]) * P.hh;
+            const double mc = __dmul_rn(add_outside(P, inside, N, S.C, S.scalars, P.out_weight[q], 0.0), P.hh);
             const double dc = second_moment_rhs(P, mc, c, N, WC, P.m_nodes[q], P.w_nodes[q]);
             double v = __dadd_rn(c, __dmul_rn(dc, S.dt));                          // Solver.cpp:577
             v = v < 0.0 ? 0.0 : v;                                                 // Solver.cpp:578-580

@@ -29,7 +29,7 @@ __device__ __forceinline__ double warp_sum(double v)
 // ------------------------------------------------------------------------------------------------
 template <int MODE>
 __global__ void __launch_bounds__(kWarp * kRowsPerBlock)
-sample_sum_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__ out)
+sample_sum_kernel(DevProblem P, const double* __restrict__ C, double* __restrict__ out, const double* __restrict__ scalars)
 {
     const int G = P.G, n_off = P.n_off, A = P.A;
     const int x = P.rank + P.world * blockIdx.y;       // this rank's rows (all rows when world == 1)
@@ -41,6 +41,8 @@ sample_sum_kernel(DevProblem P, const double* __restrict__ C, double* __restrict
     const double* wx_row = P.weight + (size_t)x * n_off;
     const int* ux_row = P.upper + (size_t)x * n_off;
     const double* sy_row = P.s + (size_t)y * n_off;
+    const double* sx_row = P.s + (size_t)x * n_off;
+    const double decay = MODE == SAMPLES_OUT_EXP ? scalars[2] : 0.0;
     const double* wy_row = P.weight + (size_t)y * n_off;
     const int* uy_row = P.upper + (size_t)y * n_off;
 
@@ -62,6 +64,10 @@ sample_sum_kernel(DevProblem P, const double* __restrict__ C, double* __restrict
             const double m = q_row[P.alpha[oj]];
             if (MODE == SAMPLES_OUT_WEIGHT) {
                 if (!(sy <= lim)) acc += m;
+                continue;
+            }
+            if (MODE == SAMPLES_OUT_EXP) {          // S:406: exp(-1 * decay_avg * (distance - max_distance)), distance = hypot (S:329)
+                if (!(sy <= lim) && m != 0.0) acc += m * exp(-1 * decay * (hypot(sx_row[oi], sy) - P.cutoff));
                 continue;
             }
             const int uy = uy_row[oj];
@@ -108,7 +114,7 @@ wc_kernel(DevProblem P, const double* __restrict__ C, const double* __restrict__
         v = warp_sum(v);
         if (threadIdx.x == 0) {
             const double N = N_cur[0];
-            const double WC = (v + outside_value(P, N, C) * P.wc_outside) * P.hh;   // S:311, S:314
+            const double WC = __dmul_rn(add_outside(P, v, N, C, scalars, P.wc_outside, scalars[4]), P.hh);   // S:311, S:314
             double dN = __dmul_rn(N, __dsub_rn(P.b, P.d));                          // S:446
             dN = __dsub_rn(dN, __dadd_rn(0.0, __dmul_rn(P.dd, WC)));                // S:450-451
             scalars[0] = WC;
@@ -128,7 +134,7 @@ wc_kernel(DevProblem P, const double* __restrict__ C, const double* __restrict__
 __global__ void __launch_bounds__(256)
 pointwise_kernel(DevProblem P, const double* __restrict__ C, const double* __restrict__ inside_sum,
                  const double* __restrict__ N_cur, const double* __restrict__ scalars, double dt,
-                 double* __restrict__ deriv_out, double* __restrict__ C_next)
+                 double* __restrict__ deriv_out, double* __restrict__ C_next, const double* __restrict__ out_exp)
 {
     const int n = local_rows(P) * P.G;
     const int ql = blockIdx.x * blockDim.x + threadIdx.x;       // shard-local index
@@ -138,7 +144,7 @@ pointwise_kernel(DevProblem P, const double* __restrict__ C, const double* __res
     const double N = N_cur[0];
     const double WC = scalars[0];
     const double c = C[(size_t)(P.rank * P.rows_per_rank + lx) * P.G + y];
-    const double mc = (inside_sum[ql] + outside_value(P, N, C) * P.out_weight[q]) * P.hh;   // S:311, S:314
+    const double mc = __dmul_rn(add_outside(P, inside_sum[ql], N, C, scalars, P.out_weight[q], out_exp ? out_exp[ql] : 0.0), P.hh);   // S:311, S:314
     const double dc = second_moment_rhs(P, mc, c, N, WC, P.m_nodes[q], P.w_nodes[q]);
     if (deriv_out) deriv_out[ql] = dc;
     if (C_next) {
@@ -202,8 +208,7 @@ finish_factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
     }
     __syncthreads();
     const double N = N_cur[0];
-    const double beyond = outside_value(P, N, C);
-    const double WC = (wc_shared + beyond * P.wc_outside) * P.hh;                   // S:311, S:314
+    const double WC = __dmul_rn(add_outside(P, wc_shared, N, C, scalars, P.wc_outside, scalars[4]), P.hh);   // S:311, S:314
     if (threadIdx.x == 0 && blockIdx.x == 0) first_moment_update(P, N, WC, dt, scalars, N_next);
 
     const int n = local_rows(P) * G;
@@ -217,7 +222,7 @@ finish_factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
         if (sum_out) sum_out[ql] = inside;
         const size_t slot = (size_t)(P.rank * P.rows_per_rank + lx) * G + y;          // this node in the gathered layout
         const double c = C[slot];
-        const double mc = (inside + beyond * P.out_weight[q]) * P.hh;
+        const double mc = __dmul_rn(add_outside(P, inside, N, C, scalars, P.out_weight[q], S.out_exp ? S.out_exp[ql] : 0.0), P.hh);
         const double dc = second_moment_rhs(P, mc, c, N, WC, P.m_nodes[q], P.w_nodes[q]);
         if (deriv_out) deriv_out[ql] = dc;
         double v = __dadd_rn(c, __dmul_rn(dc, dt));
@@ -358,6 +363,45 @@ rk4_close_kernel(int n, const double* __restrict__ value, const double* __restri
     out[q] = v < 0.0 ? 0.0 : v;                                         // S:643-645
 }
 
+// ------------------------------------------------------------------------------------------------
+// Exponential extrapolation (S:392-408), the per-step scalars: the decay rate averaged over the four nodes before the
+// last of row 0 of C, the factor C[0][G-1] - N^2 (0 when the asymptote test of S:357 holds: the reference then returns
+// the asymptote), and the sum over the WC samples beyond the cutoff.  One CTA.
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+exponential_prepare_kernel(DevProblem P, const double* __restrict__ C, const double* __restrict__ N_cur, double* __restrict__ scalars)
+{
+    __shared__ double part[8];
+    __shared__ double decay_shared;
+    const double N = N_cur[0], asymptote = N * N;
+    const double last = C[P.G - 1];                                     // values[0].last(): row 0 is slot 0 in every layout
+    const bool at_asymptote = fabs(last - asymptote) < 1e-8;            // S:357
+    if (threadIdx.x == 0) {
+        double decay_avg = 0.0;
+        for (int k = 1; k < 5; k++) {                                   // accuracy = 5 (S:394-404)
+            double value = fabs((C[P.G - 1 - k] - asymptote) / (last - asymptote));
+            value = log(value) / P.tail_gap[k - 1];
+            decay_avg += value;
+        }
+        decay_avg = decay_avg / 4;
+        decay_shared = at_asymptote ? 0.0 : decay_avg;
+    }
+    __syncthreads();
+    const double decay = decay_shared;
+    double acc = 0.0;
+    for (int e = threadIdx.x; e < P.wc_out_n; e += blockDim.x) acc += P.wc_out_w[e] * exp(-1 * decay * (P.wc_out_distance[e] - P.cutoff));
+    acc = warp_sum(acc);
+    if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double total = 0.0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); w++) total += part[w];
+        scalars[2] = decay;
+        scalars[3] = at_asymptote ? 0.0 : last - asymptote;
+        scalars[4] = total;
+    }
+}
+
 __global__ void record_observables_kernel(DevProblem P, const double* __restrict__ N_cur, const double* __restrict__ C,
                                           double* __restrict__ obs_row)
 {
@@ -419,14 +463,20 @@ void launch_finish_factored_batch(const StepArgs* d_batch, int n, int max_points
     finish_factored_kernel<true><<<dim3((max_points + 255) / 256, 1, n), 256, 0, stream>>>(none, d_batch);
 }
 
-void launch_sample_sum(const DevProblem& P, SampleMode mode, const double* C, double* out, cudaStream_t stream)
+void launch_exponential_prepare(const DevProblem& P, const double* C, const double* N_cur, double* scalars, cudaStream_t stream)
+{
+    exponential_prepare_kernel<<<1, 256, 0, stream>>>(P, C, N_cur, scalars);
+}
+
+void launch_sample_sum(const DevProblem& P, SampleMode mode, const double* C, double* out, cudaStream_t stream, const double* scalars)
 {
     dim3 block(kWarp, kRowsPerBlock);
     dim3 grid((P.G + kRowsPerBlock - 1) / kRowsPerBlock, local_rows(P));
     switch (mode) {
-        case SAMPLES_INSIDE: sample_sum_kernel<SAMPLES_INSIDE><<<grid, block, 0, stream>>>(P, C, out); break;
-        case SAMPLES_RING: sample_sum_kernel<SAMPLES_RING><<<grid, block, 0, stream>>>(P, C, out); break;
-        case SAMPLES_OUT_WEIGHT: sample_sum_kernel<SAMPLES_OUT_WEIGHT><<<grid, block, 0, stream>>>(P, C, out); break;
+        case SAMPLES_INSIDE: sample_sum_kernel<SAMPLES_INSIDE><<<grid, block, 0, stream>>>(P, C, out, scalars); break;
+        case SAMPLES_RING: sample_sum_kernel<SAMPLES_RING><<<grid, block, 0, stream>>>(P, C, out, scalars); break;
+        case SAMPLES_OUT_WEIGHT: sample_sum_kernel<SAMPLES_OUT_WEIGHT><<<grid, block, 0, stream>>>(P, C, out, scalars); break;
+        case SAMPLES_OUT_EXP: sample_sum_kernel<SAMPLES_OUT_EXP><<<grid, block, 0, stream>>>(P, C, out, scalars); break;
     }
 }
 
@@ -437,10 +487,10 @@ void launch_wc(const DevProblem& P, const double* C, const double* N_cur, double
 }
 
 void launch_pointwise(const DevProblem& P, const double* C, const double* inside_sum, const double* N_cur,
-                      const double* scalars, double dt, double* deriv_out, double* C_next, cudaStream_t stream)
+                      const double* scalars, double dt, double* deriv_out, double* C_next, cudaStream_t stream, const double* out_exp)
 {
     const int n = local_rows(P) * P.G;
-    pointwise_kernel<<<(n + 255) / 256, 256, 0, stream>>>(P, C, inside_sum, N_cur, scalars, dt, deriv_out, C_next);
+    pointwise_kernel<<<(n + 255) / 256, 256, 0, stream>>>(P, C, inside_sum, N_cur, scalars, dt, deriv_out, C_next, out_exp);
 }
 
 }  // namespace ldm

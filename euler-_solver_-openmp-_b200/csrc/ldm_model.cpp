@@ -330,12 +330,17 @@ void build_tables(const ldm_problem& p, Tables& t)
     const OffsetSet offW = make_offsets(p, p.W, p.mW);
     t.wc_operator.assign((size_t)G * G, 0.0);
     t.wc_outside = 0;
+    t.wc_out_w.clear(); t.wc_out_distance.clear();
     for (int oi = 0; oi < offW.n_off; oi++) {
         const double sx = std::abs(g[0] + offW.offset[oi]);
         for (int oj = 0; oj < offW.n_off; oj++) {
             const double sy = std::abs(g[0] + offW.offset[oj]);
             const double w = offW.quadrant[(size_t)offW.alpha[oi] * offW.A + offW.alpha[oj]];
-            if (std::hypot(sx, sy) > p.cutoff) { t.wc_outside += w; continue; }
+            if (std::hypot(sx, sy) > p.cutoff) {
+                t.wc_outside += w;
+                if (w != 0.0) { t.wc_out_w.push_back(w); t.wc_out_distance.push_back(std::hypot(sx, sy)); }
+                continue;
+            }
             const int i = upper_node(g, G, sx), j = upper_node(g, G, sy);
             const double wx = (sx - g[i - 1]) / (g[i] - g[i - 1]);
             const double wy = (sy - g[j - 1]) / (g[j] - g[j - 1]);

@@ -70,6 +70,8 @@ struct Tables {
     std::vector<double> w_nodes;   // G*G: same for W (S:490)
     std::vector<double> wc_operator;   // G*G: WC = h^2 * (sum wc_operator .* C + N^2 * wc_outside)   (S:265-274)
     double wc_outside = 0;
+    std::vector<double> wc_out_w, wc_out_distance;   // the samples behind wc_outside one by one: weight and hypot(sx, sy) (S:329),
+                                                     // for the one extrapolation type that looks at the distance (Exponential, S:392-408)
     std::string census;            // diagnostics: how close any sample comes to the cutoff circle
 };
 

@@ -36,9 +36,22 @@ __device__ __forceinline__ double wc_total(const double* wc_rows, int G, int lan
 __device__ __forceinline__ double outside_value(const DevProblem& P, double N, const double* C)
 {
     const double asymptote = N * N;
-    if (P.extrapolation == 1) return asymptote;
+    if (P.extrapolation == 1 || P.extrapolation == 3) return asymptote;      // (Exponential goes through outside_sum)
     if (fabs(C[P.G - 1] - asymptote) < 1e-8) return asymptote;
     return P.extrapolation == 0 ? 0.0 : C[0];
+}
+
+// `inside` plus what the samples beyond the cutoff contribute, their kernel weights adding up to `weight`: a constant times
+// the weight for Zero / SquaredN / Alpha; for Exponential (S:392-408) the asymptote times the weight plus
+// (C[0][G-1] - N^2) * sum of kernel * exp(-decay * (distance - cutoff)), the latter sum in `exp_sum` (scalars[3] is 0 when
+// the asymptote test of S:357 holds).  Every operation is rounded on its own: all kernels that close a step -- persistent,
+// per-step, sharded -- go through here and must agree bit for bit.
+__device__ __forceinline__ double add_outside(const DevProblem& P, double inside, double N, const double* C, const double* scalars,
+                                              double weight, double exp_sum)
+{
+    if (P.extrapolation == 3)
+        return __dadd_rn(inside, __dadd_rn(__dmul_rn(__dmul_rn(N, N), weight), __dmul_rn(scalars[3], exp_sum)));
+    return __dadd_rn(inside, __dmul_rn(outside_value(P, N, C), weight));
 }
 
 // dN/dt (S:446-451) and the clamped Euler update of N (S:577-580); thread 0 of one CTA

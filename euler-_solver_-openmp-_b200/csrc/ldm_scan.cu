@@ -440,8 +440,7 @@ scan_exchange_kernel(const StepArgs S)
     }
     __syncthreads();
     const double N = S.N_cur[0];
-    const double beyond = outside_value(P, N, S.C);
-    const double WC = (wc_shared + beyond * P.wc_outside) * P.hh;           // Solver.cpp:311, 314
+    const double WC = __dmul_rn(add_outside(P, wc_shared, N, S.C, S.scalars, P.wc_outside, 0.0), P.hh);   // Solver.cpp:311, 314
     if (lx == 0 && tid == 0) first_moment_update(P, N, WC, S.dt, S.scalars, S.N_next);
     const int n = n_local * G;
     for (int y = tid; y < G; y += NT) {
@@ -452,7 +451,7 @@ scan_exchange_kernel(const StepArgs S)
         inside -= __ldcg(S.ring + ql);
         const size_t slot = (size_t)(P.rank * P.rows_per_rank + lx) * G + y;   // this node in the gathered layout
         const double c = S.C[slot];
-        const double mc = (inside + beyond * P.out_weight[q]) * P.hh;
+        const double mc = __dmul_rn(add_outside(P, inside, N, S.C, S.scalars, P.out_weight[q], 0.0), P.hh);
         const double dc = second_moment_rhs(P, mc, c, N, WC, P.m_nodes[q], P.w_nodes[q]);
         double v = __dadd_rn(c, __dmul_rn(dc, S.dt));                       // Solver.cpp:577
         v = v < 0.0 ? 0.0 : v;                                              // Solver.cpp:578-580
@@ -555,8 +554,7 @@ persistent_scan_kernel(const PersistentArgs A)
             if (lane == 0) wc_shared = t;
         }
         __syncthreads();
-        const double beyond = outside_value(P, N, S.C);
-        const double WC = (wc_shared + beyond * P.wc_outside) * P.hh;              // Solver.cpp:311, 314
+        const double WC = __dmul_rn(add_outside(P, wc_shared, N, S.C, S.scalars, P.wc_outside, 0.0), P.hh);   // Solver.cpp:311, 314
         double* values_next = A.values ? A.values + (point + 1) * A.stride : nullptr;
         double* derivs_here = A.derivs ? A.derivs + point * A.stride : nullptr;
         if (x == 0 && tid == 0) {
@@ -566,7 +564,7 @@ persistent_scan_kernel(const PersistentArgs A)
         }
         if (closer) {
             const double inside = (0.0 + row_sum[tid]) - ring_v;
-            const double mc = (inside + beyond * ow) * P.hh;
+            const double mc = __dmul_rn(add_outside(P, inside, N, S.C, S.scalars, ow, 0.0), P.hh);
             const double dc = second_moment_rhs(P, mc, c_old, N, WC, mn, wn);
             double v = __dadd_rn(c_old, __dmul_rn(dc, S.dt));                      // Solver.cpp:577
             v = v < 0.0 ? 0.0 : v;                                                 // Solver.cpp:578-580

@@ -94,7 +94,8 @@ int  ldm_get_algorithm(ldm_handle h);                                /* the algo
  * to be beyond the cutoff (S:355-389).  Every experiment of the reference passes SquaredN (the default).  Zero and
  * Alpha follow the reference to the letter -- including Alpha's integer division (S:377), which makes it C[0][0] -- and
  * so does the asymptote test of S:357 that precedes them.  Exponential (S:392-408) depends on every sample's own
- * distance through a decay rate that changes each step: LDM_ERR_UNSUPPORTED. */
+ * distance through a decay rate that changes each step, so it costs one enumeration of the outside samples per
+ * right-hand side (three more launches per step, no persistent kernel, no batching); one species, G >= 5. */
 #define LDM_EXTRAPOLATION_ZERO        0
 #define LDM_EXTRAPOLATION_SQUARED_N   1
 #define LDM_EXTRAPOLATION_ALPHA       2

@@ -125,10 +125,11 @@ void ldmo_free(ldmo_problem* p)
     free(p->moments_grid); free(p->kernels_grid); free(p->M); free(p->W); free(p);
 }
 
-/* Extrapolation (S:355-410): Zero, SquaredN, and Alpha as the reference computes it -- `2 / (grid.size() + 1)` is an
- * integer division (S:377), so alpha == 0, every predicted value equals values[0][0] and the result is values[0][0].
- * Exponential (S:392-408) is not restated. */
-static double extrapolate(const double* values, int n, int type, double asymptotic_value)
+/* Extrapolation (S:355-410): Zero, SquaredN, Alpha as the reference computes it -- `2 / (grid.size() + 1)` is an integer
+ * division (S:377), so alpha == 0, every predicted value equals values[0][0] and the result is values[0][0] -- and
+ * Exponential (S:392-408). */
+static double extrapolate(const double* values, int n, int type, double asymptotic_value, const double* grid, double distance,
+                          double max_distance)
 {
     if (fabs(values[n - 1] - asymptotic_value) < LDMO_EPSILON)            /* S:357: values[0].last() */
         return asymptotic_value;
@@ -137,6 +138,18 @@ static double extrapolate(const double* values, int n, int type, double asymptot
         double predicted = values[0];
         for (int k = 1; k < n; k++) predicted = alpha * values[k] + (1 - alpha) * predicted;
         return alpha * asymptotic_value + (1 - alpha) * predicted;
+    }
+    if (type == 3) {                                                      /* Exponential, S:392-408 */
+        const int accuracy = 5;
+        double decay_avg = 0;
+        for (int k = 1; k < accuracy; k++) {
+            double pair_distance = max_distance - grid[n - 1 - k];
+            double new_decay_value = fabs((values[n - 1 - k] - asymptotic_value) / (values[n - 1] - asymptotic_value));
+            new_decay_value = log(new_decay_value) / pair_distance;
+            decay_avg += new_decay_value;
+        }
+        decay_avg = decay_avg / (accuracy - 1);
+        return asymptotic_value + (values[n - 1] - asymptotic_value) * exp(-1 * decay_avg * (distance - max_distance));
     }
     return type == 1 ? asymptotic_value : 0.0;                            /* SquaredN : Zero */
 }
@@ -149,7 +162,7 @@ double ldmo_bilinear(const double* grid, int n, const double* values, double x, 
 {
     double distance = hypot(x, y);                                        /* S:329 */
     if (distance > max_distance)
-        return extrapolate(values, n, extrapolation, asymptotic_value);
+        return extrapolate(values, n, extrapolation, asymptotic_value, grid, distance, max_distance);
     int i = 1, j = 1;                                                     /* S:334-336 */
     while (x > grid[i]) i++;
     while (y > grid[j]) j++;

@@ -65,7 +65,7 @@ int ldmo_solve(const ldmo_problem* p, double t_max, double dt, const double* ini
                double* times, double* values, double* derivs, double* observables);
 
 /* the ExtrapolationType Equation::operator() is called with for C (S:28, S:431): 0 Zero, 1 SquaredN (default; the only
- * one any experiment passes), 2 Alpha.  Applies to ldmo_integrals / ldmo_rhs / the solvers. */
+ * one any experiment passes), 2 Alpha, 3 Exponential.  Applies to ldmo_integrals / ldmo_rhs / the solvers. */
 void ldmo_set_extrapolation(int type);
 
 /* RungeKutta4thSolver::Solve (S:597-654): full history, values/derivs n_points*(1+G*G) (either may be NULL) */

@@ -147,7 +147,7 @@ def job_extras(args):
     mid = base["state_k100"]
     t, v, d = p.solve(4.0, 0.1, want_derivs=True, rk4=True)
     out.update(rk4_times=t, rk4_values=v, rk4_derivs=d)
-    for kind, label in ((0, "zero"), (2, "alpha")):
+    for kind, label in ((0, "zero"), (2, "alpha"), (3, "exponential")):
         p.set_extrapolation(kind)
         out[f"{label}_deriv_k0"] = p.rhs(np.concatenate([[200.0], np.full(p.P, 40000.0)]))
         out[f"{label}_deriv_k100"] = p.rhs(mid)
@@ -210,8 +210,10 @@ def main():
             print(job_multi(name), flush=True)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "--extras":
+        which = sys.argv[2:] or ["b", "c"]
+        cases = {"b": ("b", 0.05, 0.05), "c": ("c", 0.015, 0.15)}
         with ProcessPoolExecutor(max_workers=2) as pool:
-            for line in pool.map(job_extras, [("b", 0.05, 0.05), ("c", 0.015, 0.15)]):
+            for line in pool.map(job_extras, [cases[w] for w in which]):
                 print(line, flush=True)
         return
     if len(sys.argv) > 1 and sys.argv[1] == "--large":

@@ -90,7 +90,9 @@ def test_runge_kutta_and_extrapolation_types_bitwise(name):
         t, v, d = o.solve_rk4(steps * 0.1 - 0.05)
         assert np.array_equal(t, g["rk4_times"][:steps + 1]) and np.array_equal(v, g["rk4_values"][:steps + 1])
         assert np.array_equal(d[:steps], g["rk4_derivs"][:steps])
-        for kind, label in ((0, "zero"), (2, "alpha")):
+        for kind, label in ((0, "zero"), (2, "alpha"), (3, "exponential")):
+            if f"{label}_deriv_k0" not in g.files:
+                continue
             o.set_extrapolation(kind)
             assert np.array_equal(o.rhs(o.equilibrium()), g[f"{label}_deriv_k0"])
             assert np.array_equal(o.rhs(mid), g[f"{label}_deriv_k100"])
