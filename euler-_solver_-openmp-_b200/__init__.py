@@ -18,8 +18,8 @@ LIBRARY_PATH = os.environ.get("LDM_LIBRARY", os.path.join(_HERE, "libldm_b200.so
 ALGO_AUTO, ALGO_DIRECT, ALGO_FACTORED, ALGO_PREFIX = 0, 1, 2, 3
 RECORD_LAST, RECORD_OBSERVABLES, RECORD_VALUES, RECORD_ALL = 0, 1, 2, 3
 
-# enum ExtrapolationType (Solver.cpp:28); every experiment passes SquaredN for C; Zero and Alpha are built to the letter
-# of the reference, Exponential is not (ldm.h)
+# enum ExtrapolationType (Solver.cpp:28); every experiment passes SquaredN for C; the other three are built to the letter
+# of the reference (ldm.h)
 Zero, SquaredN, Alpha, Exponential = 0, 1, 2, 3
 
 
