@@ -67,6 +67,7 @@ struct ldm_context {
     double* d_out_exp = nullptr;           // [P] Exponential extrapolation: per-node sum over the outside samples, this step's decay
     double* d_wc_rows = nullptr;           // [G] factored path: per-row dot products of the WC operator (3-kernel path)
     double* d_wc_rows2 = nullptr;          // [2][G] the same inside the prefix-sum persistent kernel (ping-pong with the state)
+    double* d_ring2 = nullptr;             // [2][P] ring values of even / odd steps inside that kernel (PersistentArgs::ring_pingpong)
     unsigned int* d_barrier = nullptr;     // [1 + G] arrival counter of that kernel's grid barrier, then its per-row ring counts
     // fused update + all-gather (ldm_shard_peer_*)
     double* peer_own[2] = {nullptr, nullptr};                 // this rank's two replicas of C (gathered layout)
@@ -163,6 +164,11 @@ void ensure_ring_operator(ldm_context* c)
     d.ring_point = up(op.point);
     d.ring_begin = up(op.row_begin);
     d.ring_row_begin = up(op.grid_row_begin);
+    {
+        std::vector<unsigned char> present((size_t)ldm::local_rows(d) * d.G, 0);
+        for (int point : op.point) present[(size_t)point] = 1;
+        d.ring_present = up(present);
+    }
     {   // the CSR rows in contiguous shares of about equal entry count, one share per local grid row (= CTA of the persistent kernel)
         const int shares = (int)op.grid_row_begin.size() - 1, rows = (int)op.point.size();
         const long long total = (long long)op.node.size();
@@ -175,6 +181,15 @@ void ensure_ring_operator(ldm_context* c)
             cut[(size_t)s] = row;
         }
         d.ring_cta_begin = up(cut);
+        // shape of the shares, for the persistent kernel's shared-memory copy of its share: the most entries, CSR rows and
+        // entries per row any share holds
+        d.ring_share_entries = 0; d.ring_share_rows = 0; d.ring_share_row_len = 0;
+        for (int s = 0; s < shares; s++) {
+            const int r0 = cut[(size_t)s], r1 = cut[(size_t)s + 1];
+            d.ring_share_entries = std::max(d.ring_share_entries, op.row_begin[(size_t)r1] - op.row_begin[(size_t)r0]);
+            d.ring_share_rows = std::max(d.ring_share_rows, r1 - r0);
+            for (int r = r0; r < r1; r++) d.ring_share_row_len = std::max(d.ring_share_row_len, op.row_begin[(size_t)r + 1] - op.row_begin[(size_t)r]);
+        }
     }
     d.ring_node = up(op.node);
     d.ring_weight = up(op.weight);
@@ -415,7 +430,12 @@ void advance_persistent(ldm_context* c, int n_steps, double dt, long long first_
     args.first_point = first_point;
     args.stride = (long long)(1 + c->P());
     args.observables = d_obs; args.values = d_values; args.derivs = d_derivs;
-    args.wc_rows = c->d_wc_rows2; args.barrier = c->d_barrier; args.ring_done = c->d_barrier + 1;
+    args.wc_rows = c->d_wc_rows2; args.barrier = c->d_barrier;
+    if (c->plan.scan) {
+        if (!c->d_ring2) c->d_ring2 = c->alloc<double>(2 * c->P());
+        LDM_CUDA(cudaMemsetAsync(c->d_ring2, 0xFF, 2 * c->P() * sizeof(double), c->stream));      // every entry: not yet published
+    }
+    args.ring_pingpong = c->d_ring2;
     int device = 0, sms = 0;
     cudaGetDevice(&device);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);

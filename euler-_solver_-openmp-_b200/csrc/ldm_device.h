@@ -63,7 +63,9 @@ struct DevProblem {
     const int* ring_point;     // [n_ring] local_row * G + y
     const int* ring_begin;     // [n_ring + 1]
     const int* ring_row_begin; // [local_rows + 1] first CSR row of each local moment-grid row
+    const unsigned char* ring_present;   // [local_rows * G] 1 where the node owns ring samples (has a CSR row)
     const int* ring_cta_begin; // [local_rows + 1] the CSR rows dealt out evenly by entry count over local_rows CTAs (persistent kernel)
+    int ring_share_entries, ring_share_rows, ring_share_row_len;   // the largest share: entries, CSR rows, entries of one row
     const int* ring_node;      // C index (gathered layout)
     const double* ring_weight;
 };
@@ -207,7 +209,9 @@ struct PersistentArgs {
     // counter of its grid barrier (zeroed before every launch)
     double* wc_rows;
     unsigned int* barrier;
-    unsigned int* ring_done;   // [G] finished CSR rows of the ring correction per grid row, monotone over the launch (zeroed before)
+    double* ring_pingpong;     // [2][G*G] ring values of even / odd steps; every byte 0xFF (an all-ones NaN) = not yet published
+    long long ring_cache_offset;   // set by the launcher: byte offset in shared memory of this CTA's copy of its ring share (nodes, then
+                                   // weights), or -1 when the shares do not have the one-row-per-warp shape
 };
 
 struct FactoredPlan {

@@ -346,6 +346,25 @@ __device__ __forceinline__ void wait_for_count(const unsigned int* counter, unsi
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(seen) : "l"(counter) : "memory");
 }
 
+// Hand-over of one ring value between CTAs without a fence (see persistent_scan_kernel): the slot holds kRingEmpty until
+// the value is published.  A computed NaN never has this bit pattern, so a state that has gone NaN does not hang the poll
+// (and the poll is bounded anyway).
+constexpr unsigned long long kRingEmpty = ~0ULL;
+
+__device__ __forceinline__ void publish_ring(double* slot, double value)
+{
+    asm volatile("st.relaxed.gpu.global.f64 [%0], %1;" ::"l"(slot), "d"(value) : "memory");
+}
+
+__device__ __forceinline__ double take_ring(double* slot)
+{
+    unsigned long long bits = kRingEmpty;
+    for (long long spin = 0; spin < 400000000LL && bits == kRingEmpty; spin++)
+        asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(bits) : "l"(slot) : "memory");
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(slot), "l"(kRingEmpty) : "memory");
+    return __longlong_as_double((long long)bits);
+}
+
 // Grid-wide barrier of the persistent kernel: a monotone arrival counter in global memory (zeroed before the launch; the
 // cooperative launch guarantees that every CTA is resident).  After the CTA barrier thread 0 arrives with a releasing
 // reduction (cumulative over the CTA's writes, and nothing waits for a returned value) and polls until all CTAs of
@@ -501,11 +520,29 @@ persistent_scan_kernel(const PersistentArgs A)
     const int warp = tid >> 5, lane = tid & 31, last_warp = NT / 32 - 1;
     const bool closer = tid < G;                                                   // thread y closes node (x, y); G <= bn <= NT
     const int q = x * G + (closer ? tid : 0);
-    const unsigned int ring_rows = (unsigned int)(P.ring_row_begin[x + 1] - P.ring_row_begin[x]);
+    const bool has_ring = closer && P.ring_present[q] != 0;                       // node (x, y) owns ring samples
     const double ow = P.out_weight[q], mn = P.m_nodes[q], wn = P.w_nodes[q];      // time-invariant: registers for the whole launch
 
+    // This CTA's share of the ring correction (the far rows of the grid own almost all ring entries -- row G-1 alone an
+    // eighth of them -- so the CSR rows are dealt out evenly by entry count over ALL CTAs, whichever grid row they belong
+    // to).  The share is time-invariant: its node indices and weights are copied to shared memory once, one CSR row per
+    // warp, so that a step costs ONE round trip to L2 (the gathers of C) instead of a chain of four.
+    constexpr int kRingPerLane = 8;
+    const int share_r0 = P.ring_cta_begin[x], share_r1 = P.ring_cta_begin[x + 1];
+    const int share_e0 = P.ring_begin[share_r0];
+    const bool ring_cached = A.ring_cache_offset >= 0;
+    int* rc_node = reinterpret_cast<int*>(scan_smem + (ring_cached ? A.ring_cache_offset : 0));
+    double* rc_weight = reinterpret_cast<double*>(rc_node + ((P.ring_share_entries + 1) & ~1));
+    const int my_row = share_r0 + warp;
+    int my_begin = 0, my_end = 0, my_point = 0;
+    if (ring_cached) {
+        for (int e = tid; e < P.ring_begin[share_r1] - share_e0; e += NT) { rc_node[e] = P.ring_node[share_e0 + e]; rc_weight[e] = P.ring_weight[share_e0 + e]; }
+        if (my_row < share_r1) { my_begin = P.ring_begin[my_row] - share_e0; my_end = P.ring_begin[my_row + 1] - share_e0; my_point = P.ring_point[my_row]; }
+        __syncthreads();
+    }
+
     for (int k = 0; k < A.n_steps; k++) {
-        SCAN_MARK(0);
+        SCAN_MARK(10);
         S.C = A.C[parity]; S.C_next = A.C[parity ^ 1];
         S.N_cur = A.N + parity; S.N_next = A.N + (parity ^ 1);
         const long long point = A.first_point + k;                 // index of the state this step starts from
@@ -513,17 +550,33 @@ persistent_scan_kernel(const PersistentArgs A)
             A.observables[2 * point] = S.N_cur[0];                                  // Values[k][0]       (Solver.cpp:1011)
             A.observables[2 * point + 1] = S.C[(size_t)0 * G + (G - 1)];            // Values[k][G]       (Solver.cpp:1014)
         }
-        // This CTA's share of the ring correction.  The far rows of the grid own almost all ring entries (row G-1 alone
-        // an eighth of them), so the CSR rows are dealt out evenly by entry count over ALL CTAs, whichever grid row they
-        // belong to; results go to global memory and every finished CSR row is counted on its grid row.
-        for (int row = P.ring_cta_begin[x] + warp; row < P.ring_cta_begin[x + 1]; row += NT / 32) {
-            const double acc = ring_row_dot(P, S.C, row, lane);
-            if (lane == 0) {
-                const int point_of_row = P.ring_point[row];
-                S.ring[point_of_row] = acc;
-                asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(A.ring_done + point_of_row / G), "r"(1u) : "memory");
+        // The ring share.  Hand-over without fences or counters (a releasing reduction costs ~4 k cycles here): the values go
+        // to this step's half of a ping-pong buffer whose entries hold an all-ones NaN until they are written; the owner
+        // of a node polls its entry, takes the value and puts the NaN back for the step after next (two grid barriers lie
+        // between that store and the next write of the entry).  One 8-byte relaxed store, one 8-byte relaxed load.
+        double* ring_slot = A.ring_pingpong + (size_t)(k & 1) * G * G;
+        if (ring_cached) {
+            double cv[kRingPerLane];
+            #pragma unroll
+            for (int j = 0; j < kRingPerLane; j++) {                 // all gathers of the row in flight at once
+                const int e = my_begin + lane + 32 * j;
+                cv[j] = e < my_end ? S.C[rc_node[e]] : 0.0;
+            }
+            double acc = 0.0;
+            #pragma unroll
+            for (int j = 0; j < kRingPerLane; j++) {                 // the accumulation order of ring_row_dot / ring_kernel
+                const int e = my_begin + lane + 32 * j;
+                if (e < my_end) acc = fma(rc_weight[e], cv[j], acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0 && my_row < share_r1) publish_ring(ring_slot + my_point, acc);
+        } else {
+            for (int row = share_r0 + warp; row < share_r1; row += NT / 32) {
+                const double acc = ring_row_dot(P, S.C, row, lane);
+                if (lane == 0) publish_ring(ring_slot + P.ring_point[row], acc);
             }
         }
+        SCAN_MARK(11);
         // Everything the closing phase reads from global memory is requested between the two phases of scan_body and
         // lands while the y side runs: the old C of this row, its ring correction (the owner first checks that all
         // CSR rows of its grid row have been counted -- a whole E phase after they were dealt out, so no real wait),
@@ -532,10 +585,7 @@ persistent_scan_kernel(const PersistentArgs A)
         const double* wc_rows_now = A.wc_rows + parity * G;
         auto mid = [&]() {
             if (closer) {
-                if (ring_rows) {
-                    wait_for_count(A.ring_done + x, (unsigned int)(k + 1) * ring_rows);
-                    ring_v = __ldcg(S.ring + q);
-                }
+                if (has_ring) ring_v = take_ring(ring_slot + q);
                 c_old = S.C[q];
             }
             N = S.N_cur[0];
@@ -701,11 +751,23 @@ cudaError_t launch_persistent_scan(const PersistentArgs& args, int grid, cudaStr
     const size_t u_bytes = align32(sizeof(unsigned short) * (size_t)n_off * G);
     PersistentArgs with_cache = args;
     with_cache.cached_w_rows = -1;
+    with_cache.ring_cache_offset = -1;
+    // the CTA's ring share (one CSR row per warp, at most 8 entries per lane): 4-byte node indices, then 8-byte weights
+    size_t ring_bytes = 0;
+    if (P.ring_share_rows <= nt / 32 && P.ring_share_row_len <= 32 * 8 && std::getenv("LDM_SCAN_NO_RING_CACHE") == nullptr)
+        ring_bytes = align32(sizeof(int) * (size_t)((P.ring_share_entries + 1) & ~1) + sizeof(double) * (size_t)P.ring_share_entries + 8);
     size_t smem = base;
-    if (base + u_bytes <= kSmemBudget && std::getenv("LDM_SCAN_NO_CACHE") == nullptr) {
-        const int rows = (int)std::min<size_t>((size_t)n_off, (kSmemBudget - base - u_bytes) / ((size_t)G * sizeof(double)));
+    if (base + ring_bytes <= kSmemBudget && ring_bytes > 0) {
+        with_cache.ring_cache_offset = (long long)base;
+        smem = base + ring_bytes;
+    } else {
+        ring_bytes = 0;
+    }
+    if (base + ring_bytes + u_bytes <= kSmemBudget && std::getenv("LDM_SCAN_NO_CACHE") == nullptr) {
+        const int rows = (int)std::min<size_t>((size_t)n_off, (kSmemBudget - base - ring_bytes - u_bytes) / ((size_t)G * sizeof(double)));
         with_cache.cached_w_rows = rows;
-        smem = base + u_bytes + (size_t)rows * G * sizeof(double);
+        with_cache.ring_cache_offset = ring_bytes > 0 ? (long long)(base + u_bytes + (size_t)rows * G * sizeof(double)) : -1;
+        smem = base + ring_bytes + u_bytes + (size_t)rows * G * sizeof(double);
     }
     cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
     if (e != cudaSuccess) return e;

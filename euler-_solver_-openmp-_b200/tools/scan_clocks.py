@@ -22,7 +22,9 @@ st = eq.GenerateEquilibriumValuesForNAndC(200)
 eq.upload(st)
 eq.advance(20, 0.1)
 eq.synchronize()
-print(f"G={G} A={(props.MaxNumForM - 1) // 2}: {eq.last_elapsed_ms() / 20 * 1e3:.1f} us per step over 20 steps")
+eq.advance(200, 0.1)
+eq.synchronize()
+print(f"G={G} A={(props.MaxNumForM - 1) // 2}: {eq.last_elapsed_ms() / 200 * 1e3:.2f} us per step over 200 steps (this debug build)")
 rows = 148 * 8
 buf = np.zeros((rows, 12), dtype=np.int64)
 lib = ldm.library()
@@ -42,4 +44,6 @@ if len(pers):
     for n, (i, j) in {"ring correction of the row": (5, 6), "closing of the row + WC row": (6, 8), "grid barrier": (8, 9)}.items():
         col = pers[:, j] - pers[:, i]
         print(f"  {n:28s} mean {col.mean():9.0f}  max {col.max():9.0f} cycles")
-    print(f"  step (mark 0 -> 9)            mean {np.mean(pers[:, 9] - pers[:, 0]):9.0f} cycles")
+    col = pers[:, 11] - pers[:, 10]
+    print(f"  {'ring share (step start)':28s} mean {col.mean():9.0f}  max {col.max():9.0f} cycles")
+    print(f"  step (ring share + mark 0 -> 9) mean {np.mean(pers[:, 9] - pers[:, 0] + col):9.0f} cycles")
