@@ -908,13 +908,13 @@ int ldm_count_points_rk4(double t_max, double dt)
 int ldm_solve_rk4(ldm_handle h, const double* init, double dt, double t_max, double* times, double* values, double* derivs, int* n_points)
 {
     if (!h || !init) return fail(LDM_ERR_ARGUMENT, "NULL argument");
-    if (h->species != 1) return fail(LDM_ERR_UNSUPPORTED, "not built for several species (ldm.h: ldm_problem_generate_multi)");
     if (!(dt > 0)) return fail(LDM_ERR_ARGUMENT, "step must be positive");
-    if (h->dev.world != 1) return fail(LDM_ERR_UNSUPPORTED, "the Runge-Kutta solver runs on one rank");
+    if (h->species == 1 && h->dev.world != 1) return fail(LDM_ERR_UNSUPPORTED, "the Runge-Kutta solver runs on one rank");
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
         const int n = ldm_count_points_rk4(t_max, dt);
-        const size_t P = h->P(), width = 1 + P;
+        const size_t P = h->P(), width = state_width(h);
+        const int species = h->species;
         if (n_points) *n_points = n;
         if (times) {
             double time = 0;
@@ -936,10 +936,22 @@ int ldm_solve_rk4(ldm_handle h, const double* init, double dt, double t_max, dou
             double* d_derivs = derivs ? scratch_alloc((size_t)n * width) : nullptr;
             cudaStream_t s = h->stream;
             LDM_CUDA(cudaMemcpyAsync(value[0], init, width * sizeof(double), cudaMemcpyHostToDevice, s));
-            // Equation::operator() at a device state [N | C]: dC straight into out + 1, dN from the step scalars
+            // Equation::operator() at a device state [N | C]: dC straight into out + 1, dN from the step scalars.  Several
+            // species: the state is dealt out to the pairs' handles, evaluated there, and the derivative gathered again
             auto rhs = [&](const double* state, double* out) {
-                rhs_and_update(h, h->dev, state + 1, state, nullptr, 0.0, nullptr, out + 1, nullptr, s);
-                LDM_CUDA(cudaMemcpyAsync(out, h->d_scalars + 1, sizeof(double), cudaMemcpyDeviceToDevice, s));
+                if (species == 1) {
+                    rhs_and_update(h, h->dev, state + 1, state, nullptr, 0.0, nullptr, out + 1, nullptr, s);
+                    LDM_CUDA(cudaMemcpyAsync(out, h->d_scalars + 1, sizeof(double), cudaMemcpyDeviceToDevice, s));
+                    return;
+                }
+                h->cur = 0;
+                LDM_CUDA(cudaMemcpyAsync(h->d_Nm, state, species * sizeof(double), cudaMemcpyDeviceToDevice, s));
+                for (int p = 0; p < species * species; p++)
+                    LDM_CUDA(cudaMemcpyAsync(h->sub[(size_t)p]->d_C[0], state + species + (size_t)p * P, P * sizeof(double), cudaMemcpyDeviceToDevice, s));
+                multi_rhs_and_update(h, 0.0, true, false, s);
+                LDM_CUDA(cudaMemcpyAsync(out, h->d_dN, species * sizeof(double), cudaMemcpyDeviceToDevice, s));
+                for (int p = 0; p < species * species; p++)
+                    LDM_CUDA(cudaMemcpyAsync(out + species + (size_t)p * P, h->sub[(size_t)p]->d_deriv, P * sizeof(double), cudaMemcpyDeviceToDevice, s));
             };
             LDM_CUDA(cudaEventRecord(h->ev_begin, s));
             int cur = 0;
@@ -965,9 +977,15 @@ int ldm_solve_rk4(ldm_handle h, const double* init, double dt, double t_max, dou
             LDM_CUDA(cudaEventRecord(h->ev_end, s));
             LDM_CUDA(cudaGetLastError());
             // the handle's resident state follows the solve
-            LDM_CUDA(cudaMemcpyAsync(h->d_N, value[cur], sizeof(double), cudaMemcpyDeviceToDevice, s));
-            LDM_CUDA(cudaMemcpyAsync(h->d_C[0], value[cur] + 1, P * sizeof(double), cudaMemcpyDeviceToDevice, s));
             h->cur = 0;
+            if (species == 1) {
+                LDM_CUDA(cudaMemcpyAsync(h->d_N, value[cur], sizeof(double), cudaMemcpyDeviceToDevice, s));
+                LDM_CUDA(cudaMemcpyAsync(h->d_C[0], value[cur] + 1, P * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            } else {
+                LDM_CUDA(cudaMemcpyAsync(h->d_Nm, value[cur], species * sizeof(double), cudaMemcpyDeviceToDevice, s));
+                for (int p = 0; p < species * species; p++)
+                    LDM_CUDA(cudaMemcpyAsync(h->sub[(size_t)p]->d_C[0], value[cur] + species + (size_t)p * P, P * sizeof(double), cudaMemcpyDeviceToDevice, s));
+            }
             if (values) LDM_CUDA(cudaMemcpyAsync(values, d_values, (size_t)n * width * sizeof(double), cudaMemcpyDeviceToHost, s));
             if (derivs) LDM_CUDA(cudaMemcpyAsync(derivs, d_derivs, (size_t)n * width * sizeof(double), cudaMemcpyDeviceToHost, s));
             LDM_CUDA(cudaStreamSynchronize(s));

@@ -249,7 +249,7 @@ int ref_solve_rk4(void* handle, double t_max, double dt, double n0, const double
     QuietCout quiet;
     RefHandle* h = static_cast<RefHandle*>(handle);
     Properties& p = h->props;
-    const int n = 1 + p.MomentsGrid.size() * p.MomentsGrid.size();
+    const int n = p.SpeciesNumber + p.SpeciesNumber * p.SpeciesNumber * p.MomentsGrid.size() * p.MomentsGrid.size();
     Equation equation(p);
     RungeKutta4thSolver solver;
     Vector start = init ? Vector(std::vector<CalcType>(init, init + n))

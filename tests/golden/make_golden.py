@@ -191,6 +191,8 @@ def job_multi(name):
                deriv=p.rhs(state), deriv_equilibrium=p.rhs(np.concatenate([np.full(s, 200.0), np.full(s * s * P, 40000.0)])))
     t, v, d = p.solve(3.05, 0.1, init=state, want_derivs=True)
     out.update(times=t, values=v, derivs=d)
+    t, v, d = p.solve(1.0, 0.1, init=state, want_derivs=True, rk4=True)      # RungeKutta4thSolver on the same equations
+    out.update(rk4_times=t, rk4_values=v, rk4_last_deriv=d[-1])
     p.set_extrapolation(0)
     out["zero_deriv"] = p.rhs(state)
     p.set_extrapolation(1)

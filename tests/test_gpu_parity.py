@@ -236,6 +236,10 @@ def test_several_species(ldm, name, algorithm):
     eq.upload(g["state"])
     eq.advance(30, 0.1)
     assert np.array_equal(eq.download(), res.Values[-1])
+    rk = ldm.RungeKutta4thSolver().Solve(eq, ldm.SquaredN, 1.0, 0.1, g["state"])       # S:597-654 on the same equations
+    assert np.array_equal(rk.Times, g["rk4_times"])
+    assert_states_close(rk.Values, g["rk4_values"])
+    assert_deriv_close(rk.Derivatives[-1], g["rk4_last_deriv"])
     with pytest.raises(ldm.LdmError):
         eq.integrals(g["state"])                  # one-species entry points say so instead of misreading the state
 
