@@ -231,11 +231,12 @@ finish_factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
         for (int r = 0; r < S.peer_count; r++) S.peer_C_next[r][slot] = v;           // the all-gather: NVLink peer stores
     }
     if (S.peer_count > 0) {
-        // release: every thread's peer stores are made visible system-wide, then the last CTA of the grid publishes
-        // this rank's epoch in every rank's flag array (the classic threadfence-reduction hand-off)
-        __threadfence_system();
+        // release: the CTA's peer stores are made visible system-wide -- ONE fence per CTA, by thread 0 behind the CTA
+        // barrier (a fence is cumulative over what the barrier ordered before it, and fences are the expensive part of
+        // any hand-over on this chip) -- then the last CTA of the grid publishes this rank's epoch in every rank's flag array
         __syncthreads();
         if (threadIdx.x == 0) {
+            __threadfence_system();
             const unsigned int arrived = atomicAdd(S.done_counter, 1u);
             if (arrived == gridDim.x - 1) {
                 *S.done_counter = 0u;
