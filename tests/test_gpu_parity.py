@@ -331,6 +331,30 @@ def test_peer_exchange_step_on_one_rank(ldm, monkeypatch, knob, G):
     assert np.array_equal(got_C.ravel(), want[1:]) and got_N == want[0]
 
 
+def test_degenerate_solves(ldm):
+    """a solve that stores the initial point only (time_max below one step, S:574-575), in every record mode and for the
+    Runge-Kutta solver; zero steps of resident stepping; the derivative asked for at the only point"""
+    g = golden("exp_14_4_b")
+    props, o = problems_from(g, "exp_14_4_b", ldm)
+    eq = ldm.Equation(props)
+    init = g["state_k100"]
+    for record in (ldm.RECORD_LAST, ldm.RECORD_OBSERVABLES, ldm.RECORD_VALUES, ldm.RECORD_ALL):
+        res = ldm.EulerSolver().Solve(eq, ldm.SquaredN, 0.05, 0.1, init, record=record)
+        assert len(res.Times) == 1 and res.Times[0] == 0.0
+        if res.Values is not None:
+            assert np.array_equal(res.Values[0], init)
+        if res.Observables is not None:
+            assert np.array_equal(res.Observables[0], init[[0, props.G]])
+        if res.Derivatives is not None:
+            assert_rhs_close(o, init, res.Derivatives[0], g["deriv_k100"])
+    rk = ldm.RungeKutta4thSolver().Solve(eq, ldm.SquaredN, 0.0, 0.1, init)
+    assert len(rk.Times) == 1 and np.array_equal(rk.Values[0], init)
+    assert_rhs_close(o, init, rk.Derivatives[0], g["deriv_k100"])
+    eq.upload(init)
+    eq.advance(0, 0.1)
+    assert np.array_equal(eq.download(), init)
+
+
 def test_direct_path_trajectory(ldm):
     """the sample-by-sample algorithm through a whole experiment (the default is the factored one)"""
     g = golden("exp_14_4_b")
