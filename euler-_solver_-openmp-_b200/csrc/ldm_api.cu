@@ -96,6 +96,15 @@ struct ldm_context {
     double* d_Nm = nullptr;                // [2][species]
     double* d_dN = nullptr;                // [species]
     double rate_b[ldm::kMaxSpecies] = {}, rate_d[ldm::kMaxSpecies] = {}, rate_dd[ldm::kMaxSpecies * ldm::kMaxSpecies] = {};
+    // the pairs grouped by kernel shape: one batched launch per group and kernel (blockIdx.z = pair), argument arrays for
+    // both parities of the state ping-pong kept on the device; rebuilt when the algorithm changes
+    struct PairGroup {
+        ldm::FactoredPlan shape;
+        int scan_nt = 512, members = 0, max_slabs = 0, max_rows = 0, max_G = 0, max_A = 0, max_ring = 0;
+        size_t max_smem = 0;
+        ldm::StepArgs* d_args[2] = {nullptr, nullptr};
+    };
+    std::vector<PairGroup> pair_groups;
     int cur = 0;
     int algo = LDM_ALGO_FACTORED;
     long long launches = 0;
@@ -123,6 +132,7 @@ struct ldm_context {
     {
         for (ldm_context* c : sub) delete c;
         cudaSetDevice(device);
+        for (PairGroup& g : pair_groups) { cudaFree(g.d_args[0]); cudaFree(g.d_args[1]); }
         for (void* p : allocations) cudaFree(p);
         for (void* p : ring_allocations) cudaFree(p);
         for (void* p : w_allocations) cudaFree(p);
@@ -319,22 +329,66 @@ void rhs_and_update(ldm_context* c, const DevProblem& P, const double* C, const 
 // ---- several species ----
 size_t state_width(const ldm_context* c) { return c->species == 1 ? 1 + c->P() : (size_t)c->species + (size_t)c->species * c->species * c->P(); }
 
-// the integrals of one pair density on its one-species handle (no closing): partial sums, ring correction, WC row dots
+// the integrals of all pair densities (no closing): partial sums, ring correction, WC row dots -- the pairs' one-species
+// handles are grouped by kernel shape and every group advances in one launch per kernel (blockIdx.z = pair)
+void multi_build_groups(ldm_context* parent)
+{
+    for (ldm_context::PairGroup& g : parent->pair_groups) { cudaFree(g.d_args[0]); cudaFree(g.d_args[1]); }
+    parent->pair_groups.clear();
+    std::vector<std::vector<ldm_context*>> members;
+    for (ldm_context* h : parent->sub) {
+        ensure_ring_operator(h);
+        if (h->plan.use_w) ensure_w_operand(h);
+        size_t at = parent->pair_groups.size();
+        for (size_t k = 0; k < parent->pair_groups.size(); k++) {
+            const ldm_context::PairGroup& cand = parent->pair_groups[k];
+            if ((cand.shape.scan && h->plan.scan && cand.scan_nt == h->dev.scan_nt) ||
+                (!cand.shape.scan && !h->plan.scan && cand.shape.bm == h->plan.bm && cand.shape.bn == h->plan.bn &&
+                 cand.shape.tn == h->plan.tn && cand.shape.mma == h->plan.mma && cand.shape.use_w == h->plan.use_w)) at = k;
+        }
+        if (at == parent->pair_groups.size()) {
+            parent->pair_groups.emplace_back();
+            parent->pair_groups.back().shape = h->plan;
+            parent->pair_groups.back().scan_nt = h->dev.scan_nt;
+            members.emplace_back();
+        }
+        ldm_context::PairGroup& g = parent->pair_groups[at];
+        members[at].push_back(h);
+        g.members++;
+        g.max_slabs = std::max(g.max_slabs, h->plan.slabs());
+        g.max_rows = std::max(g.max_rows, h->dev.G);
+        g.max_G = std::max(g.max_G, h->dev.G);
+        g.max_A = std::max(g.max_A, h->dev.A);
+        g.max_ring = std::max(g.max_ring, h->dev.n_ring);
+        if (h->plan.scan) g.max_smem = std::max(g.max_smem, ldm::scan_smem_bytes(h->dev.G, h->dev.A, h->dev.scan_bn, h->dev.scan_nt, h->dev.scan_max_pieces));
+    }
+    for (size_t k = 0; k < parent->pair_groups.size(); k++)
+        for (int parity = 0; parity < 2; parity++) {
+            std::vector<ldm::StepArgs> host;
+            for (ldm_context* h : members[k]) host.push_back(make_step_args(h, h->d_C[parity], nullptr, nullptr, 0.0, nullptr, nullptr, nullptr));
+            void* p = nullptr;
+            LDM_CUDA(cudaMalloc(&p, host.size() * sizeof(ldm::StepArgs)));
+            LDM_CUDA(cudaMemcpy(p, host.data(), host.size() * sizeof(ldm::StepArgs), cudaMemcpyHostToDevice));
+            parent->pair_groups[k].d_args[parity] = static_cast<ldm::StepArgs*>(p);
+        }
+}
+
 void multi_integrals(ldm_context* parent, cudaStream_t s)
 {
-    for (ldm_context* c : parent->sub) {
-        ensure_ring_operator(c);
-        if (c->plan.use_w) ensure_w_operand(c);
-        const ldm::StepArgs args = make_step_args(c, c->d_C[parent->cur], nullptr, nullptr, 0.0, nullptr, nullptr, nullptr);
-        const bool side = args.P.n_ring > 0;
+    if (parent->pair_groups.empty()) multi_build_groups(parent);
+    for (ldm_context::PairGroup& g : parent->pair_groups) {
+        const ldm::StepArgs* args = g.d_args[parent->cur];
+        const bool side = g.max_ring > 0;
         if (side) {
-            LDM_CUDA(cudaEventRecord(c->ev_fork, s));
-            LDM_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
-            ldm::launch_ring(args, c->aux_stream);
-            LDM_CUDA(cudaEventRecord(c->ev_join, c->aux_stream));
+            LDM_CUDA(cudaEventRecord(parent->ev_fork, s));
+            LDM_CUDA(cudaStreamWaitEvent(parent->aux_stream, parent->ev_fork, 0));
+            ldm::launch_ring_batch(args, g.members, g.max_ring, parent->aux_stream);
+            LDM_CUDA(cudaEventRecord(parent->ev_join, parent->aux_stream));
         }
-        launch_integral(c, args, s);
-        if (side) LDM_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
+        if (g.shape.scan) ldm::launch_scan_batch(args, g.members, g.scan_nt, g.max_slabs, g.max_rows, g.max_smem, s);
+        else if (g.shape.use_w) ldm::launch_factored_w_batch(g.shape, args, g.members, g.max_slabs, g.max_rows, g.max_G, s);
+        else ldm::launch_factored_batch(g.shape, args, g.members, g.max_slabs, g.max_rows, g.max_G, g.max_A, s);
+        if (side) LDM_CUDA(cudaStreamWaitEvent(s, parent->ev_join, 0));
         parent->launches += 1 + (side ? 1 : 0);
     }
 }
@@ -712,8 +766,11 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
                 }
             LDM_CUDA(cudaSetDevice(device));
             LDM_CUDA(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+            LDM_CUDA(cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
             LDM_CUDA(cudaEventCreate(&c->ev_begin));
             LDM_CUDA(cudaEventCreate(&c->ev_end));
+            LDM_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+            LDM_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
             c->dev = c->sub[0]->dev;                 // G, hh, extrapolation (the tables stay the pairs')
             c->algo = c->sub[0]->algo;
             for (ldm_context* h : c->sub)
@@ -872,6 +929,9 @@ int ldm_set_algorithm(ldm_handle h, int algo)
                 return fail(LDM_ERR_UNSUPPORTED, "an m table is not separable inside its disc: prefix sums do not apply");
         for (ldm_context* c : h->sub) { c->algo = algo; c->plan = algo == LDM_ALGO_PREFIX ? c->plan_scan : c->plan_dense; }
         h->algo = algo;
+        cudaSetDevice(h->device);
+        for (ldm_context::PairGroup& g : h->pair_groups) { cudaFree(g.d_args[0]); cudaFree(g.d_args[1]); }
+        h->pair_groups.clear();            // rebuilt for the new kernel shapes at the next right-hand side
         return LDM_OK;
     }
     if (algo == LDM_ALGO_PREFIX && !h->scan_available)
