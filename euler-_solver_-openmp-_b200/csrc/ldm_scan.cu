@@ -38,7 +38,7 @@
 namespace ldm {
 
 // Optional phase timeline (debug build `make phase-clocks`): thread 0 of every CTA stores clock64() at the phase
-// boundaries; read back by tools/phase_clocks.py.  Off in the product build.
+// boundaries; read back by tools/scan_clocks.py.  Off in the product build.
 #ifdef LDM_PHASE_CLOCKS
 __device__ long long g_scan_clock[148 * 8][12];
 #define SCAN_MARK(i) do { if (threadIdx.x == 0) g_scan_clock[(blockIdx.y * gridDim.x + blockIdx.x) % (148 * 8)][i] = clock64(); } while (0)
@@ -49,7 +49,7 @@ __device__ long long g_scan_clock[148 * 8][12];
 namespace {
 
 constexpr int kScanThreadsMax = 512;       // launch bound; a CTA runs ng * bn threads (scan_pick_threads)
-constexpr int kScanLead = 2;              // doubles in front of column 0 of an H row: rows start on 128-byte lines, and index
+constexpr int kScanLead = 2;              // doubles in front of column 0 of an H row (keeps column 0 16-byte aligned); index
                                           // kScanLead - 1 is the zero column that the "beyond the grid" pair reads
 // E rows whose loads are in flight together per thread (4 loads each): 4 in the 512-thread CTAs, 2 in the 256-thread
 // CTAs that small problems use (fewer registers: four of those CTAs share an SM)
