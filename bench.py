@@ -474,6 +474,24 @@ def main():
     final = eq.download()
     assert np.all(np.isfinite(final)) and final[0] > 0
 
+    # ---- the same step with L2 flushed before EVERY step (one launch per step, each starting from HBM): the other reading
+    # of the timing rule.  A solve never runs like this -- step k+1 consumes what step k left in L2 -- so it is reported
+    # beside `value`, not instead of it.  CUDA events of the handle's own stream around each one-step advance. ----
+    cold_steps = min(args.steps, 50)
+    cold_ms = 0.0
+    for _ in range(cold_steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        eq.advance(1, DT)
+        eq.synchronize()
+        cold_ms += eq.last_elapsed_ms()
+    if world > 1:
+        t = torch.tensor([cold_ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        cold_ms = float(t.item())
+    cold = {"value": world * P * cold_steps / (cold_ms * 1e-3), "unit": UNIT, "steps": cold_steps, "ms_per_step": cold_ms / cold_steps,
+            "how": "256 MiB fill + synchronize before every step, one launch per step (ldm_advance(1)), CUDA events on the launching stream"}
+
     # ---- end to end through the reference-facing call: EulerSolver::Solve with host buffers ----
     init_pinned = torch.from_numpy(state0).pin_memory().numpy()
     solver = ldm.EulerSolver()
@@ -536,6 +554,7 @@ def main():
                              "frac": 16.0 * P / (ms_per_step * 1e-3) / 1e9 / measured_hbm_peak(), "traffic": measured_traffic(args.workload),
                              "peak_source": "MEASURED_PEAKS.json hbm_gbs (fallback 6549.8)"},
             "clocks": clocks.summary(),
+            "l2_flushed_every_step": cold,
         }
         if sharded is not None:
             line["sharded"] = sharded
