@@ -377,13 +377,16 @@ def run_sweep(ldm, torch, local_rank):
     advanced as ONE batch (ldm_solve_batch), last states read back.  Wall clock, set-up included: what a user waits for."""
     sigmas = np.linspace(1e-8, 0.2, 160)          # Vector::setLinSpaced(160, EPSILON, 0.2): same values to the last bit but one
     sigmas[-1] = 0.2
+    from concurrent.futures import ThreadPoolExecutor
     t0 = time.perf_counter()
-    eqs, inits = [], []
-    for sw in sigmas:
+
+    def create(sw):                               # host tables + upload; ctypes drops the GIL inside the library calls
         props = ldm.Properties.Generate(1, float(sw), 0.08, 0.4, 0.2, 0.001)
-        eq = ldm.Equation(props, device=local_rank)
-        eqs.append(eq)
-        inits.append(eq.GenerateEquilibriumValuesForNAndC(200))
+        return ldm.Equation(props, device=local_rank)
+
+    with ThreadPoolExecutor(max_workers=min(8, len(os.sched_getaffinity(0)))) as pool:   # as the front-end does (host/Solver.cpp)
+        eqs = list(pool.map(create, sigmas))
+    inits = [eq.GenerateEquilibriumValuesForNAndC(200) for eq in eqs]
     setup_s = time.perf_counter() - t0
     outs = ldm.solve_batch(eqs, inits, DT, 200)
     total_s = time.perf_counter() - t0
