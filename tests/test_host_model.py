@@ -94,3 +94,25 @@ def test_no_cpu_fallback(ldm):
     p = ldm.Properties.Generate(1, 0.05, 0.05, 0.4, 0.2, 0.001)
     with pytest.raises(ldm.LdmError, match="no CUDA device"):
         ldm.Equation(p)
+
+
+def test_bench_work_model_matches_the_survey(ldm):
+    """bench.py's roofline numerator: S_nz (offsets with non-zero m weight) and F_step = 11 (P S_nz + nzW) + 20 P as
+    SURVEY 8d counts them on the reference's own grids (1708 of 2116 at 14.4a, 284 of 400 at b, 648 of 784 at c) and on
+    the headline grid (S_m = 23 104 at G = 128)."""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    for (sw, sm), (s_m, s_nz) in {(0.15, 0.15): (2116, 1708), (0.05, 0.05): (400, 284), (0.015, 0.15): (784, 648)}.items():
+        p = ldm.Properties.Generate(1, sw, sm, 0.4, 0.2, 0.001)
+        assert (p.MaxNumForM - 1) ** 2 == s_m
+        flop, got = bench.algorithmic_flop_per_step(p)
+        assert got == s_nz
+        P = p.G * p.G
+        assert flop >= 11.0 * P * s_nz + 20.0 * P and flop <= 11.0 * (P * s_nz + (p.MaxNumForW - 1) ** 2) + 20.0 * P
+    p = ldm.Properties.Generate(1, *bench.WORKLOADS["g128"][:5], 128)
+    flop, s_nz = bench.algorithmic_flop_per_step(p)
+    assert (p.G, p.K, p.MaxNumForM, (p.MaxNumForM - 1) ** 2) == (128, 253, 153, 23104) and s_nz == 17956
+    assert abs(flop - 3.2366e9) < 1e6
+    sets = bench.lattice_parameter_sets(1024)
+    assert len(set(sets)) == 1024 and all(0.05 <= s <= 0.15 + 1e-12 and 0.3 <= b <= 0.5 + 1e-12 and 0.1 <= d <= 0.3 + 1e-12 for s, b, d in sets)
