@@ -120,30 +120,56 @@ __device__ __forceinline__ int folded_offset(int A, int n_fold, int alpha, int f
 #endif
 constexpr int kYUnroll = LDM_Y_UNROLL;      // (node, offset) pairs whose table reads are in flight together per lane
 
-// y side over one interval of offsets for one lane's node y.  MASKED: the chunk holds only columns [q0, q0 + bn), the
-// two taps of a pair are taken separately.  CACHED (persistent kernel): 16-bit interval indices and the first
-// cached_w_rows weight rows live in shared memory.
-template <bool MASKED, bool CACHED>
-__device__ __forceinline__ double y_side_interval(const DevProblem& P, const double* Hs, int ld, int q0, int bn, int lo, int hi, int step,
-                                                  int y, const unsigned short* u_cache, const double* w_cache, int cached_w_rows)
+// One run of consecutive offsets of the y side in which nothing changes but the position: the H row moves by dh doubles
+// per offset (-ld on the minus side, where beta falls as the offset grows, +ld on the plus side, 0 for the single offset
+// of m == 2), the tables by one row of G entries.  Pointer increments only; the weight source (shared-memory cache or
+// global table) is a template parameter so that every load knows its address space.
+template <bool MASKED, typename WPtr>
+__device__ __forceinline__ double y_side_run(double s, const double* hrow, int dh, const unsigned short* up, WPtr wp, int G, int n,
+                                             int q0, int bn)
 {
-    const int G = P.G, A = P.A;
-    const bool single = P.n_off == 1;
-    double s = 0.0;
     #pragma unroll kYUnroll
-    for (int o = lo; o < hi; o += step) {
-        const int beta = single ? 0 : (o < A ? A - 1 - o : o - A);
-        const size_t at = (size_t)o * G + y;
-        const int u = CACHED ? (int)u_cache[at] : (int)P.upper_t16[at];
-        const double w = (CACHED && o < cached_w_rows) ? w_cache[at] : P.weight_t[at];
-        const double* hrow = Hs + beta * ld + kScanLead - q0;
+    for (int i = 0; i < n; i++) {
+        const int u = (int)*up;
+        const double w = *wp;
         if (MASKED) {
             const bool ok_a = (unsigned)(u - 1 - q0) < (unsigned)bn, ok_b = (unsigned)(u - q0) < (unsigned)bn;
             const double a = hrow[ok_a ? u - 1 : q0], b = hrow[ok_b ? u : q0];
             s += (ok_a ? a * (1.0 - w) : 0.0) + (ok_b ? b * w : 0.0);
         } else {
-            s += hrow[u - 1] * (1.0 - w) + hrow[u] * w;
+            // hrow[u - 1] * (1 - w) + hrow[u] * w, the roundings spelled out (product, complement, fma, sum)
+            s = __dadd_rn(s, __fma_rn(hrow[u - 1], __dadd_rn(1.0, -w), __dmul_rn(hrow[u], w)));
         }
+        hrow += dh; up += G; wp += G;
+    }
+    return s;
+}
+
+// y side over one interval of offsets [lo, hi) for one lane's node y, accumulated in offset order.  MASKED: the chunk holds
+// only columns [q0, q0 + bn), the two taps of a pair are taken separately.  CACHED (persistent kernel): 16-bit interval
+// indices and the first cached_w_rows weight rows live in shared memory.  The interval is cut where the side changes
+// (offset A) and where the cached weight rows end, so that the loops themselves carry no selects.
+template <bool MASKED, bool CACHED>
+__device__ __forceinline__ double y_side_interval(const DevProblem& P, const double* Hs, int ld, int q0, int bn, int lo, int hi,
+                                                  int y, const unsigned short* u_cache, const double* w_cache, int cached_w_rows)
+{
+    const int G = P.G, A = P.A;
+    const bool single = P.n_off == 1;
+    double s = 0.0;
+    for (int o = lo; o < hi;) {
+        const bool minus = !single && o < A;
+        const bool w_shared = CACHED && o < cached_w_rows;
+        int end = hi;
+        if (minus) end = min(end, A);
+        if (w_shared) end = min(end, cached_w_rows);
+        const int beta = single ? 0 : (minus ? A - 1 - o : o - A);
+        const int dh = single ? 0 : (minus ? -ld : ld);
+        const size_t at = (size_t)o * G + y;
+        const double* hrow = Hs + beta * ld + kScanLead - q0;
+        const unsigned short* up = (CACHED ? u_cache : P.upper_t16) + at;
+        if (w_shared) s = y_side_run<MASKED>(s, hrow, dh, up, w_cache + at, G, end - o, q0, bn);
+        else s = y_side_run<MASKED>(s, hrow, dh, up, P.weight_t + at, G, end - o, q0, bn);
+        o = end;
     }
     return s;
 }
@@ -291,9 +317,9 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
             const int4 pc = pieces[pi];                        // y block, first offset, end offset
             const int y = min(pc.x * 32 + lane, G - 1);
             double s;
-            if (cached_w_rows >= 0) s = y_side_interval<false, true>(P, Hs, ld, q0, bn, pc.y, pc.z, 1, y, u_cache, w_cache, cached_w_rows);
-            else if (masked) s = y_side_interval<true, false>(P, Hs, ld, q0, bn, pc.y, pc.z, 1, y, nullptr, nullptr, 0);
-            else s = y_side_interval<false, false>(P, Hs, ld, q0, bn, pc.y, pc.z, 1, y, nullptr, nullptr, 0);
+            if (cached_w_rows >= 0) s = y_side_interval<false, true>(P, Hs, ld, q0, bn, pc.y, pc.z, y, u_cache, w_cache, cached_w_rows);
+            else if (masked) s = y_side_interval<true, false>(P, Hs, ld, q0, bn, pc.y, pc.z, y, nullptr, nullptr, 0);
+            else s = y_side_interval<false, false>(P, Hs, ld, q0, bn, pc.y, pc.z, y, nullptr, nullptr, 0);
             part_y[pi * 32 + lane] = s;
         }
         __syncthreads();
@@ -394,7 +420,7 @@ __device__ __forceinline__ void grid_barrier(unsigned int* counter, unsigned int
 // instead costs more than that launch (measured: 8 system-scope loads per CTA, 15 CTAs per SM).
 // ------------------------------------------------------------------------------------------------------------------
 template <bool SMALL>
-__global__ void __launch_bounds__(SMALL ? 256 : kScanThreadsMax)
+__global__ void __launch_bounds__(SMALL ? 256 : kScanThreadsMax, 1)
 scan_exchange_kernel(const StepArgs S)
 {
     const DevProblem& P = S.P;
@@ -493,7 +519,7 @@ scan_exchange_kernel(const StepArgs S)
 //   3. closes its own row -- closure, Euler update, clamp, history -- and forms its row dot of WC for the NEXT state,
 // and ONE grid barrier ends the step.  Tap tables and the y-side tables stay in shared memory across steps.
 template <bool SMALL>
-__global__ void __launch_bounds__(SMALL ? 256 : kScanThreadsMax)
+__global__ void __launch_bounds__(SMALL ? 256 : kScanThreadsMax, 1)
 persistent_scan_kernel(const PersistentArgs A)
 {
     const int NT = blockDim.x;
