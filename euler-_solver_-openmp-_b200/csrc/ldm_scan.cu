@@ -296,7 +296,9 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
                 for (int k = 0; k < kScanUnroll; k++) {
                     const int2 rows = sel[sc * span + grp * kScanUnroll + k];       // empty beyond A
                     const double v = live ? start + prefix[k] : 0.0;
-                    for (int r = rows.x; r < rows.y; r++) hcol[r * ld] = v * qv[r];
+                    double* hp = hcol + rows.x * ld;
+                    #pragma unroll 1                           // one row per alpha on average: no unrolled body, no remainder logic
+                    for (int r = rows.x; r < rows.y; r++, hp += ld) *hp = v * qv[r];
                 }
                 base += all;
             }
