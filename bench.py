@@ -148,7 +148,7 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def reference_arm(args, rank, world):
+def reference_arm(args, rank, world, emit):
     """The reference's own CPU implementation of the same step on the host cores (single-threaded: the
     reference has no parallel construct on this route, Solver.cpp:885-906)."""
     if rank != 0:
@@ -158,7 +158,7 @@ def reference_arm(args, rank, world):
     big = G == 0 or G > 48
     ref = Reference(byref=big)
     if not ref.available:
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref was not built (needs /root/reference at build time)"}))
+        emit({"impl": "reference", "unavailable": "oracle/_ref was not built (needs /root/reference at build time)"})
         return
     p = ref.from_numbers(sw, sm, b, d, dd, G)
     grid, _ = p.grids()
@@ -181,7 +181,7 @@ def reference_arm(args, rank, world):
             "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
                              "sample": f"{steps} full Euler step(s) of the workload; {kind}"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line))
+    emit(line)
 
 
 def cpu_baseline(workload, budget_s=25.0):
@@ -419,8 +419,20 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # stdout carries the ONE JSON line and nothing else: whatever libraries print on file descriptor 1 while the run lasts
+    # (NCCL announces its version there, the reference narrates its grids) goes to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+
     if args.impl == "reference":
-        reference_arm(args, rank, world)
+        reference_arm(args, rank, world, emit)
         return
 
     import torch
@@ -567,7 +579,7 @@ def main():
             line["sweep"] = sweep
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload)
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 

@@ -116,3 +116,20 @@ def test_bench_work_model_matches_the_survey(ldm):
     assert abs(flop - 3.2366e9) < 1e6
     sets = bench.lattice_parameter_sets(1024)
     assert len(set(sets)) == 1024 and all(0.05 <= s <= 0.15 + 1e-12 and 0.3 <= b <= 0.5 + 1e-12 and 0.1 <= d <= 0.3 + 1e-12 for s, b, d in sets)
+
+
+def test_bench_prints_exactly_one_json_line():
+    """the driver parses bench.py's stdout: whatever the libraries print on the way (the reference narrates its grids, NCCL
+    its version) must not land there.  The reference arm on the reference's own 14.4a grid runs without a device."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "exp14_4a",
+                          "--steps", "1", "--warmup", "0"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = out.stdout.splitlines()
+    assert len(lines) == 1, out.stdout[:500]
+    line = json.loads(lines[0])
+    assert line["impl"] == "reference"
+    if "unavailable" not in line:
+        assert line["config"]["xi_points"] == 41 * 41 and line["value"] > 0 and line["e2e"]["value"] == line["value"]
