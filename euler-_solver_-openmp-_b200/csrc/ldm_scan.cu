@@ -257,6 +257,10 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
         const int q = q0 + col;
         const bool live = q < G;
         const double* c = C + (live ? q : G - 1);
+        // keep the column pointer as ONE 64-bit value (the compiler otherwise folds the column into every tap offset and
+        // spends four integer instructions per load on 64-bit sums); it still points to global memory
+        asm volatile("" : "+l"(c));
+        __builtin_assume(__isGlobal(c));
         double* hcol = Hs + kScanLead + col;
         double base = 0.0;                                 // sum over all alphas of the super-chunks before (same in every group)
         // the barrier of a super-chunk only joins the ng warps that share the same 32 columns (named barriers 1..bn/32):
@@ -267,7 +271,7 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
             #pragma unroll
             for (int k = 0; k < kScanUnroll; k++) {
                 const int4 ra = *reinterpret_cast<const int4*>(tap_row + (sc * span + grp * kScanUnroll + k) * 4);
-                raw[k][0] = c[ra.x]; raw[k][1] = c[ra.y]; raw[k][2] = c[ra.z]; raw[k][3] = c[ra.w];
+                raw[k][0] = c[(unsigned)ra.x]; raw[k][1] = c[(unsigned)ra.y]; raw[k][2] = c[(unsigned)ra.z]; raw[k][3] = c[(unsigned)ra.w];   // unsigned: one IMAD.WIDE.U32 per address
             }
         };
         if (active) {
