@@ -51,9 +51,17 @@ namespace {
 constexpr int kScanThreadsMax = 512;       // launch bound; a CTA runs ng * bn threads (scan_pick_threads)
 constexpr int kScanLead = 2;              // doubles in front of column 0 of an H row (keeps column 0 16-byte aligned); index
                                           // kScanLead - 1 is the zero column that the "beyond the grid" pair reads
-// E rows whose loads are in flight together per thread (4 loads each): 4 in the 512-thread CTAs, 2 in the 256-thread
-// CTAs that small problems use (fewer registers: four of those CTAs share an SM)
-__host__ __device__ constexpr int scan_unroll(int NT) { return NT <= 256 ? 2 : 4; }
+// E rows whose loads are in flight together per thread (4 loads each): 2 in the 256-thread CTAs that small problems use
+// (fewer registers: four of those CTAs share an SM); in the 512-thread CTAs 4 or 5 -- whichever pads the A alphas to
+// fewer whole super-chunks of ng * unroll, and 5 on a tie (one block-sum exchange fewer: A = 76, ng = 4 takes 4 super-chunks
+// of 20 instead of 5 of 16; A = 245, ng = 8 stays with 8 of 32, where 5 would pad to 280).  A function of the CTA shape and A
+// alone, so host and device agree and every path of a handle sums in the same order.
+__host__ __device__ inline int scan_unroll(int NT, int A, int ng)
+{
+    if (NT <= 256) return 2;
+    const int pad4 = ((A + ng * 4 - 1) / (ng * 4)) * ng * 4, pad5 = ((A + ng * 5 - 1) / (ng * 5)) * ng * 5;
+    return pad5 <= pad4 ? 5 : 4;
+}
 
 struct ScanLayout {                       // byte offsets into dynamic shared memory, identical on host and device
     int ld, a_pad, n_yblk, part_stride, ng;
@@ -70,7 +78,7 @@ __host__ __device__ inline ScanLayout scan_layout(int G, int A, int bn, int NT, 
     L.n_yblk = (G + 31) / 32;
     L.part_stride = L.n_yblk * 32;
     L.ng = NT / bn > 1 ? NT / bn : 1;                     // thread groups of bn columns sharing the alphas of a super-chunk
-    const int span = L.ng * scan_unroll(NT);
+    const int span = L.ng * scan_unroll(NT, A, L.ng);
     L.a_pad = ((A + span - 1) / span) * span;             // whole super-chunks (zero-weight rows behind A)
     size_t at = 0;
     L.hs = at;      at = align32(at + sizeof(double) * (size_t)A * L.ld);
@@ -184,7 +192,7 @@ template <int kScanUnroll, typename Mid = NoMid>
 __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, const int lx, const bool build_tables,
                                           const int cached_w_rows, const bool fused = false, Mid mid = Mid())
 {
-    const int NT = blockDim.x;                             // = ng * bn; scan_unroll(NT) == kScanUnroll
+    const int NT = blockDim.x;                             // = ng * bn; scan_unroll(NT, A, ng) == kScanUnroll
     const DevProblem& P = S.P;
     // no __restrict__ / read-only path on the state: inside the persistent kernel other CTAs rewrite C every step
     const double* C = S.C;
@@ -354,9 +362,23 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
     SCAN_MARK(5);
 }
 
+// scan_body with the unroll factor of this CTA shape: U = 4 or 5 when the launch picked the kernel instance by it (the
+// single-problem kernels: each instance keeps its own register allocation), U = 0 to decide here by a uniform branch (batch
+// launches, whose members may differ, and the one-launch exchange option)
+template <bool SMALL, int U, typename Mid = NoMid>
+__device__ __forceinline__ void scan_body_of(const StepArgs& S, const int chunk, const int lx, const bool build_tables,
+                                             const int cached_w_rows, const bool fused = false, Mid mid = Mid())
+{
+    if (SMALL) { scan_body<2>(S, chunk, lx, build_tables, cached_w_rows, fused, mid); return; }
+    if (U != 0) { scan_body<(U == 0 ? 4 : U)>(S, chunk, lx, build_tables, cached_w_rows, fused, mid); return; }
+    const int ng = (int)blockDim.x / S.P.scan_bn > 1 ? (int)blockDim.x / S.P.scan_bn : 1;
+    if (scan_unroll((int)blockDim.x, S.P.A, ng) == 5) scan_body<5>(S, chunk, lx, build_tables, cached_w_rows, fused, mid);
+    else scan_body<4>(S, chunk, lx, build_tables, cached_w_rows, fused, mid);
+}
+
 // SMALL: 256-thread CTAs capped at 64 registers (four per SM) for problems whose working set is small; otherwise 512
 // threads with the registers they want.
-template <bool BATCH, bool SMALL>
+template <bool BATCH, bool SMALL, int U>
 __global__ void __launch_bounds__(SMALL ? 256 : kScanThreadsMax, SMALL ? 4 : 1)
 scan_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
 {
@@ -364,7 +386,7 @@ scan_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
     // chunks own twice the y-side pairs of the near ones), so the tail of the launch is filled with the cheap ones
     const StepArgs& S = BATCH ? batch[blockIdx.z] : one;
     if (BATCH && ((int)blockIdx.y >= S.P.scan_chunks || (int)blockIdx.x >= local_rows(S.P))) return;   // batch grids are padded
-    scan_body<scan_unroll(SMALL ? 256 : kScanThreadsMax)>(S, S.P.scan_chunk_order[blockIdx.y], blockIdx.x, true, -1);
+    scan_body_of<SMALL, U>(S, S.P.scan_chunk_order[blockIdx.y], blockIdx.x, true, -1);
 }
 
 // Spin until *counter >= target: relaxed polls (an acquire load in the loop would pay for its fence on every poll), then
@@ -470,7 +492,7 @@ scan_exchange_kernel(const StepArgs S)
 
     StepArgs body = S;
     body.wc_rows = nullptr;                                                 // the helper CTAs own the WC rows here
-    scan_body<scan_unroll(SMALL ? 256 : kScanThreadsMax)>(body, P.scan_chunk_order[chunk_slot], lx, true, -1);
+    scan_body_of<SMALL, 0>(body, P.scan_chunk_order[chunk_slot], lx, true, -1);
     __threadfence();                                                        // this thread's partial sums, before the arrival
     __syncthreads();
     if (tid == 0) closes_row = (atomicAdd(row_arrivals + lx, 1u) + 1u == step * (unsigned int)P.scan_chunks);
@@ -524,7 +546,7 @@ scan_exchange_kernel(const StepArgs S)
 //      scan_body for its row (per-node sums stay in shared memory),
 //   3. closes its own row -- closure, Euler update, clamp, history -- and forms its row dot of WC for the NEXT state,
 // and ONE grid barrier ends the step.  Tap tables and the y-side tables stay in shared memory across steps.
-template <bool SMALL>
+template <bool SMALL, int U>
 __global__ void __launch_bounds__(SMALL ? 256 : kScanThreadsMax, 1)
 persistent_scan_kernel(const PersistentArgs A)
 {
@@ -626,7 +648,7 @@ persistent_scan_kernel(const PersistentArgs A)
                 for (int j = 0; j < 4; j++) wc_part[j] = lane + 32 * j < G ? wc_rows_now[lane + 32 * j] : 0.0;
             }
         };
-        scan_body<scan_unroll(SMALL ? 256 : kScanThreadsMax)>(S, 0, x, k == 0, A.cached_w_rows, true, mid);   // ends with a CTA barrier
+        scan_body_of<SMALL, U>(S, 0, x, k == 0, A.cached_w_rows, true, mid);   // ends with a CTA barrier
         SCAN_MARK(6);
         if (warp == last_warp) {                                   // wc_total(): the same order, from the registers
             double t = 0.0;
@@ -723,35 +745,44 @@ int scan_pick_bn(int G, int A)
     return even < bn ? even : bn;
 }
 
-template <bool BATCH, bool SMALL>
+template <bool BATCH, bool SMALL, int U>
 static void launch_scan_shape(const StepArgs* one, const StepArgs* d_batch, dim3 grid, int nt, size_t smem, cudaStream_t stream)
 {
     static bool configured[64] = {};
     int device = 0;
     cudaGetDevice(&device);
-    configure_once((const void*)scan_kernel<BATCH, SMALL>, configured[device & 63]);
+    configure_once((const void*)scan_kernel<BATCH, SMALL, U>, configured[device & 63]);
     static const StepArgs none{};
-    scan_kernel<BATCH, SMALL><<<grid, nt, smem, stream>>>(one ? *one : none, d_batch);
+    scan_kernel<BATCH, SMALL, U><<<grid, nt, smem, stream>>>(one ? *one : none, d_batch);
 }
 
+// unroll: 4 or 5 for a single problem (scan_unroll of its shape), 0 for a batch (decided per member inside the kernel)
 template <bool BATCH>
-static void launch_scan_variant(const StepArgs* one, const StepArgs* d_batch, dim3 grid, int nt, size_t smem, cudaStream_t stream)
+static void launch_scan_variant(const StepArgs* one, const StepArgs* d_batch, dim3 grid, int nt, int unroll, size_t smem, cudaStream_t stream)
 {
-    if (nt <= 256) launch_scan_shape<BATCH, true>(one, d_batch, grid, nt, smem, stream);
-    else launch_scan_shape<BATCH, false>(one, d_batch, grid, nt, smem, stream);
+    if (nt <= 256) launch_scan_shape<BATCH, true, 0>(one, d_batch, grid, nt, smem, stream);
+    else if (BATCH || unroll == 0) launch_scan_shape<BATCH, false, 0>(one, d_batch, grid, nt, smem, stream);
+    else if (unroll == 5) launch_scan_shape<false, false, 5>(one, d_batch, grid, nt, smem, stream);
+    else launch_scan_shape<false, false, 4>(one, d_batch, grid, nt, smem, stream);
+}
+
+static int scan_unroll_of(const DevProblem& P)
+{
+    const int ng = P.scan_nt / P.scan_bn > 1 ? P.scan_nt / P.scan_bn : 1;
+    return scan_unroll(P.scan_nt, P.A, ng);
 }
 
 void launch_scan(const StepArgs& one, cudaStream_t stream)
 {
     const DevProblem& P = one.P;
-    launch_scan_variant<false>(&one, nullptr, dim3(local_rows(P), P.scan_chunks, 1), P.scan_nt,
+    launch_scan_variant<false>(&one, nullptr, dim3(local_rows(P), P.scan_chunks, 1), P.scan_nt, scan_unroll_of(P),
                                scan_smem_bytes(P.G, P.A, P.scan_bn, P.scan_nt, P.scan_max_pieces), stream);
 }
 
 // every member of a batch launch shares the CTA shape nt (= ng * bn); shared memory is sized for the largest member
 void launch_scan_batch(const StepArgs* d_batch, int n, int nt, int max_chunks, int max_rows, size_t max_smem, cudaStream_t stream)
 {
-    launch_scan_variant<true>(nullptr, d_batch, dim3(max_rows, max_chunks, n), nt, max_smem, stream);
+    launch_scan_variant<true>(nullptr, d_batch, dim3(max_rows, max_chunks, n), nt, 0, max_smem, stream);
 }
 
 // the same CTA shape as the one-launch-per-step kernel of this problem: the summation order follows the shape, and the
@@ -777,7 +808,8 @@ cudaError_t launch_persistent_scan(const PersistentArgs& args, int grid, cudaStr
 {
     const DevProblem& P = args.step.P;
     const int G = P.G, n_off = P.n_off, nt = P.scan_nt;
-    const void* kernel = nt <= 256 ? (const void*)persistent_scan_kernel<true> : (const void*)persistent_scan_kernel<false>;
+    const void* kernel = nt <= 256 ? (const void*)persistent_scan_kernel<true, 0>
+                       : scan_unroll_of(P) == 5 ? (const void*)persistent_scan_kernel<false, 5> : (const void*)persistent_scan_kernel<false, 4>;
     // shared memory: the step's working set, then the 16-bit y-side index table, then as many weight rows as still fit
     const size_t base = scan_smem_bytes(G, P.A, P.scan_bn, nt, P.scan_max_pieces);
     const size_t u_bytes = align32(sizeof(unsigned short) * (size_t)n_off * G);
@@ -806,8 +838,7 @@ cudaError_t launch_persistent_scan(const PersistentArgs& args, int grid, cudaStr
     int device = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&device);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-    e = nt <= 256 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_scan_kernel<true>, nt, smem)
-                  : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, persistent_scan_kernel<false>, nt, smem);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem);
     if (e != cudaSuccess) return e;
     if (max_grid) *max_grid = sms * per_sm;
     if (grid <= 0) return cudaSuccess;                  // query only
