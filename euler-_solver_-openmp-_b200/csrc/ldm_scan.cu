@@ -34,6 +34,9 @@
 #ifndef LDM_Y_UNROLL
 #define LDM_Y_UNROLL 4
 #endif
+#ifndef LDM_Y_UNROLL_WIDE
+#define LDM_Y_UNROLL_WIDE 6
+#endif
 
 namespace ldm {
 
@@ -132,11 +135,11 @@ constexpr int kYUnroll = LDM_Y_UNROLL;      // (node, offset) pairs whose table 
 // per offset (-ld on the minus side, where beta falls as the offset grows, +ld on the plus side, 0 for the single offset
 // of m == 2), the tables by one row of G entries.  Pointer increments only; the weight source (shared-memory cache or
 // global table) is a template parameter so that every load knows its address space.
-template <bool MASKED, typename WPtr>
+template <bool MASKED, int YU, typename WPtr>
 __device__ __forceinline__ double y_side_run(double s, const double* hrow, int dh, const unsigned short* up, WPtr wp, int G, int n,
                                              int q0, int bn)
 {
-    #pragma unroll kYUnroll
+    #pragma unroll YU
     for (int i = 0; i < n; i++) {
         const int u = (int)*up;
         const double w = *wp;
@@ -157,7 +160,7 @@ __device__ __forceinline__ double y_side_run(double s, const double* hrow, int d
 // only columns [q0, q0 + bn), the two taps of a pair are taken separately.  CACHED (persistent kernel): 16-bit interval
 // indices and the first cached_w_rows weight rows live in shared memory.  The interval is cut where the side changes
 // (offset A) and where the cached weight rows end, so that the loops themselves carry no selects.
-template <bool MASKED, bool CACHED>
+template <bool MASKED, bool CACHED, int YU>
 __device__ __forceinline__ double y_side_interval(const DevProblem& P, const double* Hs, int ld, int q0, int bn, int lo, int hi,
                                                   int y, const unsigned short* u_cache, const double* w_cache, int cached_w_rows)
 {
@@ -175,8 +178,8 @@ __device__ __forceinline__ double y_side_interval(const DevProblem& P, const dou
         const size_t at = (size_t)o * G + y;
         const double* hrow = Hs + beta * ld + kScanLead - q0;
         const unsigned short* up = (CACHED ? u_cache : P.upper_t16) + at;
-        if (w_shared) s = y_side_run<MASKED>(s, hrow, dh, up, w_cache + at, G, end - o, q0, bn);
-        else s = y_side_run<MASKED>(s, hrow, dh, up, P.weight_t + at, G, end - o, q0, bn);
+        if (w_shared) s = y_side_run<MASKED, YU>(s, hrow, dh, up, w_cache + at, G, end - o, q0, bn);
+        else s = y_side_run<MASKED, YU>(s, hrow, dh, up, P.weight_t + at, G, end - o, q0, bn);
         o = end;
     }
     return s;
@@ -324,6 +327,8 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
     {
         const int warp = tid >> 5, lane = tid & 31, warps = NT / 32;
         const bool masked = P.scan_chunks > 1;
+        // (node, offset) pairs in flight per lane: the 256-thread CTAs live within 64 registers, the 512-thread ones can afford more
+        constexpr int kYU = kScanUnroll == 2 ? kYUnroll : LDM_Y_UNROLL_WIDE;
         const int4* pieces = P.scan_piece + P.scan_chunk_begin[chunk];
         const int* warp_begin = P.scan_warp_begin + chunk * (warps + 1);
         const int* block_begin = P.scan_block_begin + chunk * (L.n_yblk + 1);
@@ -331,9 +336,9 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
             const int4 pc = pieces[pi];                        // y block, first offset, end offset
             const int y = min(pc.x * 32 + lane, G - 1);
             double s;
-            if (cached_w_rows >= 0) s = y_side_interval<false, true>(P, Hs, ld, q0, bn, pc.y, pc.z, y, u_cache, w_cache, cached_w_rows);
-            else if (masked) s = y_side_interval<true, false>(P, Hs, ld, q0, bn, pc.y, pc.z, y, nullptr, nullptr, 0);
-            else s = y_side_interval<false, false>(P, Hs, ld, q0, bn, pc.y, pc.z, y, nullptr, nullptr, 0);
+            if (cached_w_rows >= 0) s = y_side_interval<false, true, kYU>(P, Hs, ld, q0, bn, pc.y, pc.z, y, u_cache, w_cache, cached_w_rows);
+            else if (masked) s = y_side_interval<true, false, kYU>(P, Hs, ld, q0, bn, pc.y, pc.z, y, nullptr, nullptr, 0);
+            else s = y_side_interval<false, false, kYU>(P, Hs, ld, q0, bn, pc.y, pc.z, y, nullptr, nullptr, 0);
             part_y[pi * 32 + lane] = s;
         }
         __syncthreads();
