@@ -126,10 +126,9 @@ __device__ __forceinline__ int folded_offset(int A, int n_fold, int alpha, int f
     return n_fold == 1 ? 0 : (f == 0 ? A - 1 - alpha : A + alpha);
 }
 
-#ifndef LDM_Y_UNROLL
-#define LDM_Y_UNROLL 4
-#endif
-constexpr int kYUnroll = LDM_Y_UNROLL;      // (node, offset) pairs whose table reads are in flight together per lane
+// (node, offset) pairs of the y side whose table reads are in flight together per lane: LDM_Y_UNROLL in the 256-thread CTAs
+// (64 registers), LDM_Y_UNROLL_WIDE in the 512-thread ones (measured: 4 and 6)
+constexpr int kYUnroll = LDM_Y_UNROLL;
 
 // One run of consecutive offsets of the y side in which nothing changes but the position: the H row moves by dh doubles
 // per offset (-ld on the minus side, where beta falls as the offset grows, +ld on the plus side, 0 for the single offset
