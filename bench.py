@@ -80,6 +80,23 @@ def executed_flop_per_step(props, prefix):
     return gemm + e_gen + y_side + 30.0 * G * G
 
 
+def minimal_wavefronts_per_step(props):
+    """Load/store data-pipe wavefronts (128 bytes of L1 / shared memory per clock and SM) that the prefix-sum algorithm
+    cannot avoid, per Euler step -- the resource model of DESIGN.md 5:
+      E phase   4 values of C per element of E (G rows x A quadrature nodes x G columns); a warp load of 32 consecutive
+                columns is 256 bytes = 2 wavefronts;
+      H tile    every element of the A x G tile of a row written once (2 wavefronts per 32 columns);
+      y side    per (32 nodes y, signed offset): the 16-bit interval indices (1 wavefront), the weights (2) and two
+                8-byte gathers per lane from the H tile (2 each when free of bank conflicts)."""
+    G, m = props.G, props.MaxNumForM
+    A, n_off = ((m - 1) // 2, m - 1) if m > 2 else (1, 1)
+    col_blocks = -(-G // 32)
+    e_phase = G * A * 4 * col_blocks * 2
+    h_tile = G * A * col_blocks * 2
+    y_side = G * n_off * col_blocks * 7
+    return float(e_phase + h_tile + y_side)
+
+
 def requested_bytes_per_step(props):
     """Bytes of C the E phase of the prefix-sum path requests per step: four values per element of E (ncu: two thirds of
     them hit in L1, profiles/r01_traffic.json)."""
@@ -87,14 +104,34 @@ def requested_bytes_per_step(props):
     return 32.0 * G * A * G
 
 
-def measured_traffic(workload):
-    """dram__bytes_read.sum + dram__bytes_write.sum of the dominant kernel per step, from the committed ncu capture
-    (profiles/r01_traffic.json says which launch and how many steps it held)"""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+def source_sha():
+    """sha256 over the kernel sources: a counter file captured from other sources is refused"""
+    import hashlib
+    h = hashlib.sha256()
+    csrc = os.path.join(ROOT, "euler-_solver_-openmp-_b200", "csrc")
+    for name in sorted(os.listdir(csrc)):
+        if name.endswith((".cu", ".cuh", ".h", ".cpp")):
+            h.update(name.encode())
+            h.update(open(os.path.join(csrc, name), "rb").read())
+    return h.hexdigest()
+
+
+def measured_counters(workload, kernel_prefix):
+    """Per-step counters of the dominant kernel from the committed `ncu --set full` capture of THIS build
+    (profiles/r02_counters.json, written by profiles/ncu_to_counters.py from the capture of profiles/capture_r02.sh): DRAM
+    bytes, L2 -> L1 bytes, load/store wavefronts, executed FP64 operations.  Refused (None, with the reason) when the file was
+    captured from other kernel sources or names another kernel."""
+    path = os.path.join(ROOT, "profiles", "r02_counters.json")
     if not os.path.exists(path):
-        return None
+        return None, "profiles/r02_counters.json is missing"
     entry = json.load(open(path)).get(workload)
-    return float(entry["dram_bytes_per_step"]) if entry else None
+    if not entry:
+        return None, f"no capture of workload {workload}"
+    if entry.get("source_sha") != source_sha():
+        return None, "the capture was taken from other kernel sources (source_sha differs): counters refused"
+    if not str(entry.get("kernel", "")).startswith(kernel_prefix):
+        return None, f"the capture names kernel {entry.get('kernel')!r}, the bench ran {kernel_prefix!r}"
+    return entry, None
 
 
 def measured_hbm_peak():
@@ -148,6 +185,19 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def workload_config(name, G, K, mM, mW, s_nz, world):
+    """`config` of the JSON line, the same keys and values in both arms"""
+    return {"workload": name, "G": int(G), "xi_points": int(G) * int(G), "K": int(K), "mM": int(mM), "mW": int(mW), "S_nz": int(s_nz),
+            "dt": DT, "parallelism": f"replicas x{world}" if world > 1 else "single",
+            "l2": "flushed once immediately before the timed region (256 MiB fill); the K timed steps are consecutive steps of one trajectory",
+            "seed": "C = N^2 (1 + 0.5 exp(-r^2/2 sigma^2)), N = 200"}
+
+
+def nonzero_samples(table, extent):
+    idx = [abs(i + 1) for i in range(1 - extent, extent - 1, 2)]
+    return int(np.count_nonzero(table[np.ix_(idx, idx)]))
+
+
 def reference_arm(args, rank, world, emit):
     """The reference's own CPU implementation of the same step on the host cores (single-threaded: the
     reference has no parallel construct on this route, Solver.cpp:885-906)."""
@@ -163,23 +213,47 @@ def reference_arm(args, rank, world, emit):
     p = ref.from_numbers(sw, sm, b, d, dd, G)
     grid, _ = p.grids()
     state = seeded_state(grid, sm)
-    steps = max(1, min(args.steps, 2 if p.P >= 4096 else args.steps))
-    for _ in range(min(args.warmup, 0 if p.P >= 4096 else 1)):
-        p.rhs(state)
+    M, _ = p.tables()
+    config = workload_config(args.workload, p.G, p.K, p.mM, p.mW, nonzero_samples(M, p.mM), args.gpus)
+    # One step = the hot loop of one right-hand side (Solver.cpp:277-316, > 99.9 % of a step) on a BOUNDED SAMPLE of the
+    # moment grid: every `stride`-th row (near and far rows alike -- the cost of a node grows with its distance from the
+    # origin), sized so that --steps K --warmup W ends within a few minutes; the sampled rows are then advanced like
+    # EulerSolver::Solve does (update + clamp).  value = sampled grid points x steps / seconds.
+    stride = 1 if p.P < 4096 else max(1, p.G // 8)
+    rows = np.arange(0, p.G, stride)
+    C = state[1:].reshape(p.G, p.G)
+    m_nodes, w_nodes = (p.kernels_at_nodes() if stride > 1 else (None, None))
+    wc = p.integrals(state, want_mc=False)[0] if stride > 1 else None
+
+    def step():
+        nonlocal state
+        if stride == 1:
+            deriv = p.rhs(state)                                  # Equation::operator()
+            state = np.maximum(state + deriv * DT, 0.0)           # EulerSolver::Solve's update and clamp (S:577-580)
+            return
+        mc = p.mc_rows(state, 0, stride)                          # MakeIntegralWithPairDensity at every node of the sampled rows
+        c = C[rows]
+        dc = 2 * b * mc + 2 * b * state[0] * m_nodes[rows] - 2 * d * c - 2 * dd * wc * c / state[0] - 2 * dd * w_nodes[rows] * c
+        C[rows] = np.maximum(c + dc * DT, 0.0)
+
+    for _ in range(args.warmup):
+        step()
     t0 = time.perf_counter()
-    for _ in range(steps):
-        deriv = p.rhs(state)                                   # Equation::operator() -- >99.9 % of a step
-        state = np.maximum(state + deriv * DT, 0.0)            # EulerSolver::Solve's update and clamp
+    for _ in range(args.steps):
+        step()
     sec = time.perf_counter() - t0
-    value = p.P * steps / sec
+    points = len(rows) * p.G
+    value = points * args.steps / sec
     kind = ("reference source with its five by-value matrix parameters turned into references (oracle/Makefile; "
             "bit-identical results, the shipped build needs ~1 h per step at this size)") if big else "unmodified reference build"
-    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * sec / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f64", "data": "synthetic", "impl": "reference",
-            "config": {"workload": args.workload, "G": p.G, "xi_points": p.P, "K": p.K, "dt": DT},
-            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference",
-                             "sample": f"{steps} full Euler step(s) of the workload; {kind}"},
+    sample = (f"{args.steps} steps, each the reference's per-node integral on {len(rows)} of the {p.G} grid rows (every {stride}-th row, "
+              f"{points} of {p.P} grid points) plus their update; {kind}") if stride > 1 else f"{args.steps} full Euler steps; {kind}"
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * sec / args.steps * (p.P / points), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic", "impl": "reference", "config": config,
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": 1, "kind": "reference", "sample": sample,
+                             "threads": "the reference runs a single solve on one thread (Solver.cpp:885-906); its only parallel "
+                                        "construct is over independent parameter sets (S:940)"},
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     emit(line)
 
@@ -223,52 +297,74 @@ def cpu_baseline(workload, budget_s=25.0):
 
 
 def run_sharded_peer(ldm, torch, dist, workload, rank, world, local_rank, steps, warmup):
-    """BASELINE config 4 with the all-gather FUSED into the update: the closing kernel of every rank stores its updated
-    rows straight into all ranks' next replica over NVLink (CUDA IPC peer mappings) and publishes a per-rank epoch flag;
-    the next step starts with a device-side wait on the flags.  No NCCL call on the data path (NCCL only carried the
-    64-byte IPC handles at set-up and the timing reduction)."""
+    """BASELINE config 4 with the all-gather FUSED into the update: ONE launch per rank for all the steps (persistent
+    work-list kernel); the CTA that completes a row stores it straight into every rank's next replica over NVLink (CUDA IPC
+    peer mappings) and a step ends with per-rank epoch flags.  No NCCL call on the data path (NCCL only carries the 64-byte
+    IPC handles at set-up and the timing reduction).  Every rank then repeats the same steps ALONE on its own GPU (one
+    rank, same kernel) and compares its replica with that run element by element; the one-rank time measured there, in
+    the same run on the same GPU, is the denominator of `speedup_vs_1gpu`."""
     sw, sm, b, d, dd, G = WORKLOADS[workload]
     props = ldm.Properties.Generate(1, sw, sm, b, d, dd, G)
     sh = ldm.ShardedEquation(props, rank, world, device=local_rank)
 
     def all_gather_bytes(mine):
+        if world == 1:
+            return mine.reshape(1, -1)
         t = torch.from_numpy(mine).cuda()
         out = torch.empty(world * t.numel(), dtype=torch.uint8, device="cuda")
         dist.all_gather_into_tensor(out, t)
         return out.cpu().numpy().reshape(world, -1)
 
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
     sh.peer_connect(all_gather_bytes)
     state0 = seeded_state(props.MomentsGrid, sm)
     sh.peer_upload(state0[1:], state0[0])
-    dist.barrier()
-    torch.cuda.synchronize()
+    barrier()
     stream = torch.cuda.current_stream()
-    for _ in range(warmup):
-        sh.peer_step(DT, stream.cuda_stream)
+    sh.peer_advance(warmup, DT, stream.cuda_stream)
     torch.cuda.synchronize()
-    dist.barrier()
-    torch.cuda.synchronize()
+    barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     launches0 = sh.eq.launches
     e0.record(stream)
-    for _ in range(steps):
-        sh.peer_step(DT, stream.cuda_stream)
+    sh.peer_advance(steps, DT, stream.cuda_stream)
     e1.record(stream)
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
-    t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-    dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item())
+    launches = int(sh.eq.launches - launches0)
     final_C, N_end = sh.peer_download()
-    dist.barrier()
+    barrier()
+    # the same steps on ONE rank (this GPU alone), timed the same way: element-wise reference and speed-up denominator
+    one = ldm.ShardedEquation(props, 0, 1, device=local_rank)
+    one.peer_connect(lambda mine: mine.reshape(1, -1))
+    one.peer_upload(state0[1:], state0[0])
+    one.peer_advance(warmup, DT, stream.cuda_stream)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    one.peer_advance(steps, DT, stream.cuda_stream)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    one_ms = e0.elapsed_time(e1)
+    want_C, want_N = one.peer_download()
+    diff = max(float(np.max(np.abs(final_C - want_C))), abs(N_end - want_N))
+    stats = torch.tensor([ms, one_ms, diff], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(stats, op=dist.ReduceOp.MAX)
+    ms, one_ms, diff = (float(v) for v in stats)
     assert np.all(np.isfinite(final_C)) and N_end > 0
     flop_step, s_nz = algorithmic_flop_per_step(props)
     P = G * G
     return {"workload": workload, "G": G, "xi_points": P, "S_nz": s_nz, "scaling": "strong", "steps": steps, "warmup": warmup,
             "value": P * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
-            "collective": "fused into the closing kernel: NVLink peer stores of the updated rows into every rank's replica + epoch flags "
+            "one_gpu_ms_per_step": one_ms / steps, "speedup_vs_1gpu": one_ms / ms,
+            "max_abs_diff": diff, "elementwise": "every rank's replica against the same steps on one rank, all G*G values and N; max over ranks",
+            "collective": "fused into the persistent kernel: NVLink peer stores of every row as it closes into every rank's replica + per-rank epoch flags "
                           "(%d bytes to each of %d peers per rank per step); no NCCL on the data path" % (sh.rows_per_rank * G * 8, world - 1),
-            "gpu_launches": int(sh.eq.launches - launches0), "algorithmic_tflops": flop_step * steps / (ms * 1e-3) / 1e12,
+            "gpu_launches": launches, "algorithmic_tflops": flop_step * steps / (ms * 1e-3) / 1e12,
             "checksum": float(final_C.sum() + N_end)}
 
 
@@ -408,7 +504,7 @@ def main():
     ap.add_argument("--workload", default="g128", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--sharded", default="g512", help="workload of the xi-sharded strong-scaling leg ('none' to skip)")
-    ap.add_argument("--sharded-steps", type=int, default=10)
+    ap.add_argument("--sharded-steps", type=int, default=50)
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="sharded leg at N > 1: all-gather fused into the update over NVLink peer stores, or an NCCL all-gather per step")
     ap.add_argument("--batch-sets", type=int, default=128, help="parameter sets per GPU of the batched leg (0 to skip)")
@@ -454,6 +550,7 @@ def main():
     prefix = eq.algorithm == ldm.ALGO_PREFIX
     flop_executed = executed_flop_per_step(props, prefix)
     fp64_peak = ldm.measure_fp64_peak(local_rank)
+    lsu_peak, l2_peak = ldm.measure_memory_pipes(local_rank)       # wavefronts/s over the whole device, GB/s
 
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")   # > 126 MB of L2
 
@@ -507,27 +604,41 @@ def main():
     cold = {"value": world * P * cold_steps / (cold_ms * 1e-3), "unit": UNIT, "steps": cold_steps, "ms_per_step": cold_ms / cold_steps,
             "how": "256 MiB fill + synchronize before every step, one launch per step (ldm_advance(1)), CUDA events on the launching stream"}
 
-    # ---- end to end through the reference-facing call: EulerSolver::Solve with host buffers ----
+    # ---- end to end through the reference-facing call: EulerSolver::Solve with host buffers.  The headline is the
+    # reference's own contract -- SolverResults holds Values AND Derivatives of every point (Solver.cpp:546-553), so both
+    # cross PCIe, segment by segment under the computation; beside it the observables-only mode (what Experiment_14_4
+    # reads off the result, S:1011-1015).  Pinned host buffers, wall clock around the call. ----
     init_pinned = torch.from_numpy(state0).pin_memory().numpy()
     solver = ldm.EulerSolver()
     t_max = (args.steps + 0.5) * DT             # exactly args.steps Euler steps
-    solver.Solve(eq, ldm.SquaredN, (args.warmup + 0.5) * DT, DT, init_pinned, record=ldm.RECORD_OBSERVABLES)
-    barrier()
-    t0 = time.perf_counter()
-    res = solver.Solve(eq, ldm.SquaredN, t_max, DT, init_pinned, record=ldm.RECORD_OBSERVABLES)
-    e2e_s = time.perf_counter() - t0
-    assert len(res.Times) == args.steps + 1
-    if world > 1:
-        t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        e2e_s = float(t.item())
-    e2e_value = world * P * args.steps / e2e_s
+    width = 1 + P
+    values_pinned = torch.empty((args.steps + 1) * width, dtype=torch.float64).pin_memory().numpy()
+    derivs_pinned = torch.empty((args.steps + 1) * width, dtype=torch.float64).pin_memory().numpy()
+
+    def timed_solve(record):
+        kw = dict(values_out=values_pinned, derivs_out=derivs_pinned) if record == ldm.RECORD_ALL else {}
+        solver.Solve(eq, ldm.SquaredN, (args.warmup + 0.5) * DT, DT, init_pinned, record=record, **kw)
+        barrier()
+        t0 = time.perf_counter()
+        res = solver.Solve(eq, ldm.SquaredN, t_max, DT, init_pinned, record=record, **kw)
+        sec = time.perf_counter() - t0
+        assert len(res.Times) == args.steps + 1
+        if world > 1:
+            t = torch.tensor([sec], dtype=torch.float64, device="cuda")
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            sec = float(t.item())
+        return world * P * args.steps / sec, res
+
+    e2e_value, res_all = timed_solve(ldm.RECORD_ALL)
+    e2e_observables, res_obs = timed_solve(ldm.RECORD_OBSERVABLES)
+    assert np.array_equal(res_obs.Observables, res_all.Values[:, [0, props.G]])
 
     sharded = None
     if args.sharded != "none":
-        if world > 1 and args.exchange == "peer":
-            sharded = run_sharded_peer(ldm, torch, dist, args.sharded, rank, world, local_rank, args.sharded_steps, 2)
-            sharded["nccl_variant"] = run_sharded(ldm, torch, dist, args.sharded, rank, world, local_rank, args.sharded_steps, 2)
+        if args.exchange == "peer":
+            sharded = run_sharded_peer(ldm, torch, dist, args.sharded, rank, world, local_rank, args.sharded_steps, 5)
+            if world > 1:
+                sharded["nccl_variant"] = run_sharded(ldm, torch, dist, args.sharded, rank, world, local_rank, min(args.sharded_steps, 20), 2)
         else:
             sharded = run_sharded(ldm, torch, dist, args.sharded, rank, world, local_rank, args.sharded_steps, 2)
 
@@ -540,34 +651,56 @@ def main():
     if rank == 0:
         ms_per_step = total_ms / args.steps
         achieved = flop_step / (ms_per_step * 1e-3) / 1e12
+        kernel_name = ("persistent_scan_kernel" if props.G <= 128 else "persistent_chunks_kernel") if prefix else "persistent_kernel"
+        counters, refused = measured_counters(args.workload, kernel_name)
+        wf_min = minimal_wavefronts_per_step(props)
+        roofline = {
+            # the contract's figure: the 11-FLOP-per-sample model of the reference's sum over the measured DFMA peak
+            "bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
+            "traffic": counters["dram_bytes_per_step"] if counters else None,
+            "algorithmic_flop_per_step": flop_step, "algorithm": "prefix" if prefix else "dense",
+            "peak_source": "measured live: DFMA chain micro-benchmark (MEASURED_PEAKS.json has no FP64 figure)",
+            "note": "frac > 1: `achieved` counts the reference's sample-by-sample work (11 FLOP per sample); the prefix-sum path issues ~120x "
+                    "fewer FP64 operations, so the FP64 pipe no longer bounds the step.  What does is the load/store data pipe (gathers "
+                    "of C and of the H tile) and the L2 -> SM path: lsu_frac and l2_frac below measure the machine against those",
+            # the resources that bound the prefix-sum path, each against a peak measured live on this device
+            "lsu_peak_wavefronts_per_s": lsu_peak, "l2_peak_GBps": l2_peak,
+            "lsu_wavefronts_min_per_step": wf_min,
+            "lsu_frac": wf_min / (ms_per_step * 1e-3) / lsu_peak,
+            "hbm_GBps_algorithmic": 16.0 * P / (ms_per_step * 1e-3) / 1e9,
+            "executed_flop_per_step_model": flop_executed,
+        }
+        if counters:
+            roofline.update({
+                "counters_from": "profiles/r02_counters.json: ncu --set full of this build's " + counters["kernel"] + ", per step of its launch",
+                "lsu_wavefronts_executed_per_step": counters["lsu_wavefronts_per_step"],
+                "lsu_frac_executed": counters["lsu_wavefronts_per_step"] / (ms_per_step * 1e-3) / lsu_peak,
+                "l2_bytes_per_step": counters["l2_to_l1_bytes_per_step"],
+                "l2_frac": counters["l2_to_l1_bytes_per_step"] / (ms_per_step * 1e-3) / 1e9 / l2_peak,
+                "executed_flop_per_step": counters["fp64_flop_per_step"],
+                "executed_frac": counters["fp64_flop_per_step"] / (ms_per_step * 1e-3) / 1e12 / fp64_peak,
+                "waves_per_sm": counters.get("waves_per_sm"),
+            })
+        else:
+            roofline["counters_refused"] = refused
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f64", "data": "synthetic",
-            "config": {"workload": args.workload, "G": props.G, "xi_points": P, "K": props.K, "mM": props.MaxNumForM,
-                       "mW": props.MaxNumForW, "S_nz": s_nz, "dt": DT, "parallelism": f"replicas x{world}" if world > 1 else "single",
-                       "l2": "flushed once immediately before the timed region (256 MiB fill); the K timed steps are consecutive steps of one trajectory", "seed": "C = N^2 (1 + 0.5 exp(-r^2/2 sigma^2)), N = 200"},
+            "config": workload_config(args.workload, props.G, props.K, props.MaxNumForM, props.MaxNumForW, s_nz, world),
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": 8.0 * (1 + P) / args.steps,
-                    "d2h_bytes_per_step": 16.0, "call": "EulerSolver::Solve twin (ldm_solve, record = observables), pinned host buffers, wall clock"},
+                    "d2h_bytes_per_step": 16.0 * (1 + P) * (args.steps + 1) / args.steps,
+                    "call": "EulerSolver::Solve twin (ldm_solve, record = all: Values and Derivatives of every point, the reference's SolverResults), "
+                            "pinned host buffers, history copied out in segments under the computation, wall clock",
+                    "observables_only": {"value": e2e_observables, "unit": UNIT, "d2h_bytes_per_step": 16.0,
+                                         "call": "the same with record = observables (N and C[0][G-1] per point, what Experiment_14_4 reads)"}},
             "gpu_launches": int(launches),
-            "roofline": {"bound": "fp64", "achieved": achieved, "peak": fp64_peak, "unit": "TFLOP/s", "frac": achieved / fp64_peak,
-                         "traffic": measured_traffic(args.workload), "algorithmic_flop_per_step": flop_step,
-                         "executed_flop_per_step": flop_executed, "executed_tflops": flop_executed / (ms_per_step * 1e-3) / 1e12,
-                         "executed_frac": flop_executed / (ms_per_step * 1e-3) / 1e12 / fp64_peak,
-                         "algorithm": "prefix" if prefix else "dense",
-                         "note": "frac > 1 is expected: achieved counts the 11-FLOP-per-sample model of the reference's sample-by-sample sum "
-                                 "(SURVEY 8d); the prefix-sum path issues ~120x fewer FP64 operations (executed_*), so the step is no longer bound by "
-                                 "the FP64 pipe but by the load/store pipe (gathers of C in the E phase, shared-memory gathers in the y phase) and one "
-                                 "grid barrier per step (DESIGN.md 5)",
-                         "e_phase_requested_bytes_per_step": requested_bytes_per_step(props) if prefix else None,
-                         "peak_source": "measured live: DFMA chain micro-benchmark (MEASURED_PEAKS.json has no FP64 figure)",
-                         "hbm_GBps_algorithmic": 16.0 * P / (ms_per_step * 1e-3) / 1e9},
-            # the same step against the HBM roofline the contract's default asks for: algorithmic bytes (C read once and written
-            # once per step) over the step time -- three orders of magnitude under the measured copy bandwidth,
-            # which is the point: this path is not HBM bound, C never leaves L2 between steps
+            "roofline": roofline,
             "roofline_hbm": {"bound": "hbm", "achieved": 16.0 * P / (ms_per_step * 1e-3) / 1e9, "peak": measured_hbm_peak(), "unit": "GB/s",
-                             "frac": 16.0 * P / (ms_per_step * 1e-3) / 1e9 / measured_hbm_peak(), "traffic": measured_traffic(args.workload),
-                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (fallback 6549.8)"},
+                             "frac": 16.0 * P / (ms_per_step * 1e-3) / 1e9 / measured_hbm_peak(), "traffic": roofline["traffic"],
+                             "peak_source": "MEASURED_PEAKS.json hbm_gbs (fallback 6549.8)",
+                             "note": "algorithmic bytes (C read once and written once per step, SURVEY 8d) over the step time: three orders of "
+                                     "magnitude under the copy bandwidth -- this path is not HBM bound, C never leaves L2 between steps"},
             "clocks": clocks.summary(),
             "l2_flushed_every_step": cold,
         }

@@ -79,8 +79,12 @@ _SIGNATURES = {
     "ldm_shard_peer_connect": (C.c_int, [C.c_void_p, C.c_void_p]),
     "ldm_shard_peer_upload": (C.c_int, [C.c_void_p, _dp, C.c_double]),
     "ldm_shard_peer_step": (C.c_int, [C.c_void_p, C.c_double, C.c_void_p]),
+    "ldm_shard_peer_advance": (C.c_int, [C.c_void_p, C.c_int, C.c_double, C.c_void_p]),
+    "ldm_shard_peer_connect_local": (C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    "ldm_tuning_set": (C.c_int, [C.c_char_p, C.c_int]),
     "ldm_shard_peer_download": (C.c_int, [C.c_void_p, _dp, C.POINTER(C.c_double)]),
     "ldm_measure_fp64_peak": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.c_void_p]),
+    "ldm_measure_memory_pipes": (C.c_int, [C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double)]),
     "ldm_last_error": (C.c_char_p, []),
     "ldm_version": (C.c_char_p, []),
 }
@@ -105,11 +109,23 @@ def _check(code):
         raise LdmError(f"ldm error {code}: {library().ldm_last_error().decode()}")
 
 
+def tuning_set(name, value=0):
+    """test hook (ldm.h ldm_tuning_set): force a kernel shape for the handles created from here on; tuning_set("reset")"""
+    _check(library().ldm_tuning_set(name.encode(), int(value)))
+
+
 def measure_fp64_peak(device=0):
     """DFMA peak of the device in TFLOP/s (live micro-benchmark; the FP64 roofline denominator)."""
     v = C.c_double()
     _check(library().ldm_measure_fp64_peak(int(device), C.byref(v), None))
     return v.value
+
+
+def measure_memory_pipes(device=0):
+    """(load/store data-pipe wavefronts per second over the whole device, L2 -> SM read bandwidth in GB/s), measured live"""
+    wf, l2 = C.c_double(), C.c_double()
+    _check(library().ldm_measure_memory_pipes(int(device), C.byref(wf), C.byref(l2)))
+    return wf.value, l2.value
 
 
 class Properties:
@@ -281,7 +297,9 @@ class EulerSolver:
     """class EulerSolver (Solver.cpp:541-593)"""
 
     def Solve(self, current_equation, type, time_max, step, initial_value, debug_print_enabled=False,
-              record=RECORD_ALL):
+              record=RECORD_ALL, values_out=None, derivs_out=None):
+        """values_out / derivs_out: optional caller-owned float64 arrays (e.g. pinned host memory) that receive
+        SolverResults::Values / Derivatives instead of freshly allocated ones"""
         eq = current_equation
         eq.set_extrapolation(type)
         init = np.ascontiguousarray(initial_value, dtype=np.float64)
@@ -295,8 +313,10 @@ class EulerSolver:
         elif record == RECORD_OBSERVABLES:
             obs = np.empty((n, 2))
         else:
-            values = np.empty((n, width))
-            derivs = np.empty((n, width)) if record == RECORD_ALL else None
+            values = np.empty((n, width)) if values_out is None else values_out.reshape(-1)[:n * width].reshape(n, width)
+            derivs = None
+            if record == RECORD_ALL:
+                derivs = np.empty((n, width)) if derivs_out is None else derivs_out.reshape(-1)[:n * width].reshape(n, width)
         got = C.c_int()
         vals_ptr = (obs if record == RECORD_OBSERVABLES else values).ctypes.data
         _check(library().ldm_solve(eq._h, init, float(step), float(time_max), int(record), times.ctypes.data, vals_ptr,
@@ -384,6 +404,17 @@ class ShardedEquation:
 
     def peer_step(self, dt, stream_ptr=0):
         _check(library().ldm_shard_peer_step(self.eq._h, float(dt), C.c_void_p(stream_ptr)))
+
+    def peer_advance(self, n_steps, dt, stream_ptr=0):
+        """n Euler steps with the exchange fused in; on the prefix-sum path ONE launch per rank for all of them"""
+        _check(library().ldm_shard_peer_advance(self.eq._h, int(n_steps), float(dt), C.c_void_p(stream_ptr)))
+
+    @staticmethod
+    def connect_local(ranks):
+        """one process driving all ranks (several devices, or several ranks on one device in tests): replaces
+        peer_connect and the exchange of IPC handles"""
+        handles = (C.c_void_p * len(ranks))(*[r.eq._h for r in ranks])
+        _check(library().ldm_shard_peer_connect_local(len(ranks), handles))
 
     def peer_download(self):
         out = np.empty((self.world * self.rows_per_rank, self.G))

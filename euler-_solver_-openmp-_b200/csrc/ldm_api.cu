@@ -14,9 +14,7 @@
 #include <thread>
 #include <vector>
 
-#include "../../include/ldm.h"
-#include "ldm_device.h"
-#include "ldm_model.h"
+#include "ldm_context.h"
 
 namespace {
 
@@ -26,131 +24,22 @@ thread_local std::string g_error;
 // the reference's tables; anything beyond 1e-13 is structure, not rounding
 constexpr double kSeparableTolerance = 1e-13;
 
+}  // namespace
+
+namespace ldm {
+
 int fail(int code, const std::string& what)
 {
     g_error = what;
     return code;
 }
 
-struct CudaError : std::runtime_error {
-    using std::runtime_error::runtime_error;
-};
+Tuning& tuning()
+{
+    static Tuning t;
+    return t;
+}
 
-#define LDM_CUDA(expr)                                                                                    \
-    do {                                                                                                  \
-        cudaError_t e_ = (expr);                                                                          \
-        if (e_ != cudaSuccess)                                                                            \
-            throw CudaError(std::string(#expr) + ": " + cudaGetErrorString(e_));                          \
-    } while (0)
-
-}  // namespace
-
-struct ldm_context {
-    int device = 0;
-    cudaStream_t stream = nullptr;
-    cudaStream_t aux_stream = nullptr;     // the ring correction runs beside the factored kernel
-    cudaEvent_t ev_begin = nullptr, ev_end = nullptr, ev_fork = nullptr, ev_join = nullptr;
-    ldm::Tables tables;
-    ldm::DevProblem dev{};
-    ldm::FactoredPlan plan;                // the active plan: plan_scan or plan_dense
-    ldm::FactoredPlan plan_dense, plan_scan;
-    ldm::SeparableKernel separable;        // structure of the m table (prefix-sum path when .ok)
-    bool scan_available = false;
-    std::vector<void*> allocations;
-    double* d_C[2] = {nullptr, nullptr};   // ping-pong pair density, natural layout
-    double* d_N = nullptr;                 // [2] ping-pong first moment
-    double* d_scalars = nullptr;           // [kScalars]
-    double* d_sum = nullptr;               // [P] per-node inside-sample sum
-    double* d_deriv = nullptr;             // [P] dC/dt
-    double* d_partial = nullptr;           // [tiles][P] factored path: per beta-tile sums
-    double* d_ring = nullptr;              // [P] factored path: samples between the cutoff circle and the square edge
-    double* d_out_exp = nullptr;           // [P] Exponential extrapolation: per-node sum over the outside samples, this step's decay
-    double* d_wc_rows = nullptr;           // [G] factored path: per-row dot products of the WC operator (3-kernel path)
-    double* d_wc_rows2 = nullptr;          // [2][G] the same inside the prefix-sum persistent kernel (ping-pong with the state)
-    double* d_ring2 = nullptr;             // [2][P] ring values of even / odd steps inside that kernel (PersistentArgs::ring_pingpong)
-    unsigned int* d_barrier = nullptr;     // [1 + G] arrival counter of that kernel's grid barrier, then its per-row ring counts
-    // fused update + all-gather (ldm_shard_peer_*)
-    double* peer_own[2] = {nullptr, nullptr};                 // this rank's two replicas of C (gathered layout)
-    unsigned long long* peer_own_flags = nullptr;             // [world] last step published by every rank
-    unsigned int* peer_done = nullptr;
-    unsigned int* peer_sync = nullptr;                        // counters of the one-launch step (StepArgs::sync_words)
-    int* peer_status = nullptr;
-    double* peer_C[2][ldm::kMaxPeers] = {};                   // every rank's replicas, peer-mapped
-    unsigned long long* peer_flags[ldm::kMaxPeers] = {};
-    std::vector<void*> peer_opened;
-    unsigned long long peer_epoch = 0;
-    int peer_parity = 0;
-    bool peer_connected = false;
-    int persistent_grid = 0;               // co-resident CTAs of the persistent kernel (0: not queried yet, -1: unavailable)
-    bool persistent_enabled = true;
-    std::vector<void*> ring_allocations;   // the ring-correction CSR of the current (rank, world)
-    std::vector<void*> w_allocations;      // W_x = Q . L_x of the current (rank, world)
-    int w_rank = -1, w_world = -1;
-    double w_megabytes = 0;
-    int ring_rank = -1, ring_world = -1;
-    long long ring_entries = 0, ring_samples = 0;
-    // several species (ldm_problem_generate_multi): species*species one-species handles -- pair (i, j) carries the tables of
-    // M(i) and W(i,j) and the pair density C_ij in its own d_C ping-pong; the first moments live here
-    int species = 1;
-    std::vector<ldm_context*> sub;
-    double* d_Nm = nullptr;                // [2][species]
-    double* d_dN = nullptr;                // [species]
-    double rate_b[ldm::kMaxSpecies] = {}, rate_d[ldm::kMaxSpecies] = {}, rate_dd[ldm::kMaxSpecies * ldm::kMaxSpecies] = {};
-    // the pairs grouped by kernel shape: one batched launch per group and kernel (blockIdx.z = pair), argument arrays for
-    // both parities of the state ping-pong kept on the device; rebuilt when the algorithm changes
-    struct PairGroup {
-        ldm::FactoredPlan shape;
-        int scan_nt = 512, members = 0, max_slabs = 0, max_rows = 0, max_G = 0, max_A = 0, max_ring = 0;
-        size_t max_smem = 0;
-        ldm::StepArgs* d_args[2] = {nullptr, nullptr};
-    };
-    std::vector<PairGroup> pair_groups;
-    int cur = 0;
-    int algo = LDM_ALGO_FACTORED;
-    long long launches = 0;
-    float last_ms = 0.f;
-    double shard_N[2] = {0, 0};
-
-    size_t P() const { return (size_t)dev.G * dev.G; }
-
-    template <typename T>
-    T* alloc(size_t count)
-    {
-        void* p = nullptr;
-        LDM_CUDA(cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T)));
-        allocations.push_back(p);
-        return static_cast<T*>(p);
-    }
-    template <typename T>
-    T* upload(const std::vector<T>& v)
-    {
-        T* p = alloc<T>(v.size());
-        if (!v.empty()) LDM_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-        return p;
-    }
-    ~ldm_context()
-    {
-        for (ldm_context* c : sub) delete c;
-        cudaSetDevice(device);
-        for (PairGroup& g : pair_groups) { cudaFree(g.d_args[0]); cudaFree(g.d_args[1]); }
-        for (void* p : allocations) cudaFree(p);
-        for (void* p : ring_allocations) cudaFree(p);
-        for (void* p : w_allocations) cudaFree(p);
-        for (void* p : peer_opened) cudaIpcCloseMemHandle(p);
-        for (void* p : {(void*)peer_own[0], (void*)peer_own[1], (void*)peer_own_flags, (void*)peer_done, (void*)peer_status, (void*)peer_sync})
-            if (p) cudaFree(p);
-        if (ev_begin) cudaEventDestroy(ev_begin);
-        if (ev_end) cudaEventDestroy(ev_end);
-        if (ev_fork) cudaEventDestroy(ev_fork);
-        if (ev_join) cudaEventDestroy(ev_join);
-        if (aux_stream) cudaStreamDestroy(aux_stream);
-        if (stream) cudaStreamDestroy(stream);
-    }
-};
-
-namespace {
-
-using ldm::DevProblem;
 
 // The ring-correction operator of the factored path for this rank's rows (time-invariant; rebuilt when the
 // sharding changes).  Built lazily: the direct algorithm never needs it.
@@ -208,58 +97,8 @@ void ensure_ring_operator(ldm_context* c)
     c->ring_world = d.world;
     c->ring_entries = (long long)op.node.size();
     c->ring_samples = op.samples;
+    c->ring_row_begin_host = op.row_begin;
     LDM_CUDA(cudaDeviceSynchronize());      // one-time setup: everything above is visible to every stream
-}
-
-// W_x = Q . L_x for this rank's rows (time-invariant; rebuilt when the sharding changes), see ldm_factored_w.cu.
-void ensure_w_operand(ldm_context* c)
-{
-    DevProblem& d = c->dev;
-    if (c->w_rank == d.rank && c->w_world == d.world) return;
-    const ldm::Tables& t = c->tables;
-    const int G = d.G, n_off = d.n_off;
-    const int a_pad = c->plan.tiles * c->plan.bm;
-    std::vector<long long> offset((size_t)G, -1);
-    std::vector<int> k_of((size_t)G, 16), plo((size_t)G, 0);
-    long long total = 0;
-    for (int x = d.rank; x < G; x += d.world) {
-        int lo = G, hi = -1;
-        for (int o = 0; o < n_off; o++) {
-            const int u = t.axisM.upper[(size_t)x * n_off + o];
-            if (u != 0) { lo = std::min(lo, u - 1); hi = std::max(hi, u); }
-        }
-        if (hi < 0) { lo = 0; hi = 0; }
-        plo[(size_t)x] = lo;
-        k_of[(size_t)x] = ((hi - lo + 1 + 15) / 16) * 16;
-        offset[(size_t)x] = total;
-        total += (long long)a_pad * k_of[(size_t)x];
-    }
-    for (void* p : c->w_allocations) cudaFree(p);
-    c->w_allocations.clear();
-    auto up = [&](const auto& v) {
-        using T = typename std::decay_t<decltype(v)>::value_type;
-        void* p = nullptr;
-        LDM_CUDA(cudaMalloc(&p, std::max<size_t>(v.size(), 1) * sizeof(T)));
-        c->w_allocations.push_back(p);
-        LDM_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
-        return static_cast<const T*>(p);
-    };
-    d.w_offset = up(offset);
-    d.w_k = up(k_of);
-    d.w_plo = up(plo);
-    void* w = nullptr;
-    LDM_CUDA(cudaMalloc(&w, std::max<long long>(total, 1) * sizeof(double)));
-    c->w_allocations.push_back(w);
-    LDM_CUDA(cudaMemset(w, 0, std::max<long long>(total, 1) * sizeof(double)));
-    d.W = static_cast<const double*>(w);
-    // build only this rank's rows: the kernel skips rows whose offset is negative
-    ldm::launch_build_w(d, static_cast<double*>(w), a_pad, c->stream);
-    c->launches += 1;
-    LDM_CUDA(cudaGetLastError());
-    LDM_CUDA(cudaDeviceSynchronize());
-    c->w_rank = d.rank;
-    c->w_world = d.world;
-    c->w_megabytes = (double)total * sizeof(double) / 1e6;
 }
 
 // One right-hand side at the state (N_cur, C) for this rank's rows: scalars <- WC, dN; optional outputs:
@@ -283,7 +122,6 @@ ldm::StepArgs make_step_args(ldm_context* c, const double* C, const double* N_cu
 void launch_integral(ldm_context* c, const ldm::StepArgs& args, cudaStream_t s)
 {
     if (c->plan.scan) ldm::launch_scan(args, s);
-    else if (c->plan.use_w) ldm::launch_factored_w(c->plan, args, s);
     else ldm::launch_factored(c->plan, args, s);
 }
 
@@ -308,7 +146,6 @@ void rhs_and_update(ldm_context* c, const DevProblem& P, const double* C, const 
         return;
     }
     ensure_ring_operator(c);
-    if (c->plan.use_w) ensure_w_operand(c);
     ldm::StepArgs args = make_step_args(c, C, N_cur, N_next, dt, sum_out, deriv_out, C_next);
     args.out_exp = out_exp;
     // the sparse ring correction only reads C: it runs on a side stream beside the (register-bound, one CTA per
@@ -338,13 +175,12 @@ void multi_build_groups(ldm_context* parent)
     std::vector<std::vector<ldm_context*>> members;
     for (ldm_context* h : parent->sub) {
         ensure_ring_operator(h);
-        if (h->plan.use_w) ensure_w_operand(h);
         size_t at = parent->pair_groups.size();
         for (size_t k = 0; k < parent->pair_groups.size(); k++) {
             const ldm_context::PairGroup& cand = parent->pair_groups[k];
             if ((cand.shape.scan && h->plan.scan && cand.scan_nt == h->dev.scan_nt) ||
                 (!cand.shape.scan && !h->plan.scan && cand.shape.bm == h->plan.bm && cand.shape.bn == h->plan.bn &&
-                 cand.shape.tn == h->plan.tn && cand.shape.mma == h->plan.mma && cand.shape.use_w == h->plan.use_w)) at = k;
+                 cand.shape.tn == h->plan.tn)) at = k;
         }
         if (at == parent->pair_groups.size()) {
             parent->pair_groups.emplace_back();
@@ -386,7 +222,6 @@ void multi_integrals(ldm_context* parent, cudaStream_t s)
             LDM_CUDA(cudaEventRecord(parent->ev_join, parent->aux_stream));
         }
         if (g.shape.scan) ldm::launch_scan_batch(args, g.members, g.scan_nt, g.max_slabs, g.max_rows, g.max_smem, s);
-        else if (g.shape.use_w) ldm::launch_factored_w_batch(g.shape, args, g.members, g.max_slabs, g.max_rows, g.max_G, s);
         else ldm::launch_factored_batch(g.shape, args, g.members, g.max_slabs, g.max_rows, g.max_G, g.max_A, s);
         if (side) LDM_CUDA(cudaStreamWaitEvent(s, parent->ev_join, 0));
         parent->launches += 1 + (side ? 1 : 0);
@@ -457,7 +292,7 @@ bool persistent_possible(ldm_context* c)
     if (!c->persistent_enabled || c->algo == LDM_ALGO_DIRECT || c->dev.world != 1) return false;
     if (c->dev.extrapolation == LDM_EXTRAPOLATION_EXPONENTIAL) return false;        // needs its own launches every step
     const ldm::FactoredPlan& p = c->plan;
-    if (p.slabs() != 1 || p.use_w || (!p.scan && !p.mma)) return false;
+    if (p.slabs() != 1) return false;
     if (c->persistent_grid == 0) {
         ldm::PersistentArgs probe{};
         probe.step = make_step_args(c, c->d_C[0], c->d_N, c->d_N + 1, 0.0, nullptr, nullptr, c->d_C[1]);
@@ -485,6 +320,7 @@ void advance_persistent(ldm_context* c, int n_steps, double dt, long long first_
     args.stride = (long long)(1 + c->P());
     args.observables = d_obs; args.values = d_values; args.derivs = d_derivs;
     args.wc_rows = c->d_wc_rows2; args.barrier = c->d_barrier;
+    args.status = c->d_status;
     if (c->plan.scan) {
         if (!c->d_ring2) c->d_ring2 = c->alloc<double>(2 * c->P());
         LDM_CUDA(cudaMemsetAsync(c->d_ring2, 0xFF, 2 * c->P() * sizeof(double), c->stream));      // every entry: not yet published
@@ -505,6 +341,59 @@ void advance_persistent(ldm_context* c, int n_steps, double dt, long long first_
     c->cur ^= (n_steps & 1);
 }
 
+// Which multi-step kernel, if any, carries the Euler loop of this handle: one CTA per row (rows of one chunk, G <= 128),
+// the work-list kernel (prefix-sum path with rows of several chunks), or neither (one launch per kernel and step).
+enum class Resident { None, Rows, Chunks };
+
+Resident resident_mode(ldm_context* c)
+{
+    if (persistent_possible(c)) return Resident::Rows;
+    if (c->dev.world == 1 && chunked_possible(c)) return Resident::Chunks;
+    return Resident::None;
+}
+
+void advance_resident(ldm_context* c, Resident mode, int n_steps, double dt, double* d_obs, double* d_values, double* d_derivs)
+{
+    if (mode == Resident::Rows) advance_persistent(c, n_steps, dt, 0, d_obs, d_values, d_derivs);
+    else advance_chunked(c, n_steps, dt, c->stream, 0, d_obs, d_values, d_derivs);
+}
+
+void check_device_status(ldm_context* c)
+{
+    int status = 0;
+    LDM_CUDA(cudaMemcpy(&status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost));
+    if (status == 0) return;
+    cudaMemset(c->d_status, 0, sizeof(int));
+    static const char* what[] = {"", "a grid barrier of the persistent kernel timed out", "a ring value was never handed over",
+                                 "a rank never published its step (peer exchange timed out)"};
+    throw CudaError(std::string("device status ") + std::to_string(status) + ": " + (status > 0 && status < 4 ? what[status] : "unknown") +
+                    " -- the results of this call are not valid");
+}
+
+// Device-side history of ldm_solve: two segment buffers per handle, kept between calls (grown when a call needs more), so
+// that a solve neither allocates inside its timed region nor holds the whole trajectory on the device -- one segment is
+// copied out on the copy stream while the next one is being computed.
+constexpr size_t kHistorySegmentBytes = 16u << 20;      // small enough that a 200-step solve of the 16 384-point grid overlaps (4 segments)
+
+void ensure_history(ldm_context* c, size_t doubles)
+{
+    if (!c->copy_stream) {
+        LDM_CUDA(cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking));
+        for (int b = 0; b < 2; b++) {
+            LDM_CUDA(cudaEventCreateWithFlags(&c->ev_segment[b], cudaEventDisableTiming));
+            LDM_CUDA(cudaEventCreateWithFlags(&c->ev_copied[b], cudaEventDisableTiming));
+        }
+    }
+    if (doubles <= c->hist_capacity) return;
+    LDM_CUDA(cudaStreamSynchronize(c->copy_stream));
+    for (int b = 0; b < 2; b++) {
+        if (c->d_hist[b]) cudaFree(c->d_hist[b]);
+        c->d_hist[b] = nullptr;
+        LDM_CUDA(cudaMalloc((void**)&c->d_hist[b], doubles * sizeof(double)));
+    }
+    c->hist_capacity = doubles;
+}
+
 void step_resident(ldm_context* c, double dt, double* deriv_out)
 {
     const int cur = c->cur, nxt = cur ^ 1;
@@ -519,178 +408,37 @@ void upload_state(ldm_context* c, const double* state)
     LDM_CUDA(cudaMemcpyAsync(c->d_C[0], state + 1, c->P() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 }
 
-template <typename F>
-int guarded(F&& body)
-{
-    try {
-        body();
-        return LDM_OK;
-    } catch (const CudaError& e) {
-        return fail(LDM_ERR_CUDA, e.what());
-    } catch (const std::invalid_argument& e) {
-        return fail(LDM_ERR_ARGUMENT, e.what());
-    } catch (const std::exception& e) {
-        return fail(LDM_ERR_ARGUMENT, e.what());
-    }
-}
+}  // namespace ldm
 
-}  // namespace
+using namespace ldm;
+
+// What the reference asserts on its own tables (S:77 grid end = cutoff, S:88 K odd, S:303-304 quadrature extent within the
+// table) plus what the index arithmetic of build_tables needs from a table that did not come from ldm_problem_generate.
+// Empty string: fine.
+static std::string problem_defect(const ldm_problem* p)
+{
+    auto finite = [](double v) { return std::isfinite(v); };
+    if (p->K % 2 == 0) return "K (kernel-grid nodes) must be odd (Solver.cpp:88)";
+    if (!(p->h > 0) || !finite(p->h)) return "KernelsGridStep must be positive";
+    if (!(p->cutoff > 0) || !finite(p->cutoff)) return "CutoffDistance must be positive";
+    auto extent_ok = [&](int m) { return m >= 2 && m <= p->K && (m == 2 || m % 2 == 1); };
+    if (!extent_ok(p->mM)) return "MaxNumForM must be 2 or an odd number in [3, K] (Solver.cpp:125-132)";
+    if (!extent_ok(p->mW)) return "MaxNumForW must be 2 or an odd number in [3, K] (Solver.cpp:125-132)";
+    if (p->species > 1) {
+        for (int i = 0; i < p->species; i++) if (!extent_ok(p->mM_of[i])) return "an entry of MaxNumForM is not 2 or an odd number in [3, K]";
+        for (int i = 0; i < p->species * p->species; i++) if (!extent_ok(p->mW_of[i])) return "an entry of MaxNumForW is not 2 or an odd number in [3, K]";
+    }
+    if (p->moments_grid[0] != 0.0) return "MomentsGrid must start at 0";
+    for (int k = 1; k < p->G; k++)
+        if (!(p->moments_grid[k] > p->moments_grid[k - 1]) || !finite(p->moments_grid[k])) return "MomentsGrid must be strictly increasing";
+    if (!(std::fabs(p->moments_grid[p->G - 1] - p->cutoff) < 1e-8)) return "MomentsGrid must end at the cutoff (Solver.cpp:77)";
+    if (p->kernels_grid[0] != 0.0) return "KernelsGrid must start at 0";
+    for (int k = 1; k < p->K; k++)
+        if (!(p->kernels_grid[k] > p->kernels_grid[k - 1]) || !finite(p->kernels_grid[k])) return "KernelsGrid must be strictly increasing";
+    return "";
+}
 
 extern "C" {
-
-int ldm_shard_peer_alloc(ldm_handle h, unsigned char* handles)
-{
-    if (!h || !handles) return fail(LDM_ERR_ARGUMENT, "NULL argument");
-    if (h->species != 1) return fail(LDM_ERR_UNSUPPORTED, "not built for several species (ldm.h: ldm_problem_generate_multi)");
-    if (h->dev.world > ldm::kMaxPeers) return fail(LDM_ERR_ARGUMENT, "at most 8 ranks");
-    return guarded([&] {
-        LDM_CUDA(cudaSetDevice(h->device));
-        const size_t words = (size_t)h->dev.world * h->dev.rows_per_rank * h->dev.G;
-        for (int b = 0; b < 2; b++) {
-            if (!h->peer_own[b]) LDM_CUDA(cudaMalloc((void**)&h->peer_own[b], words * sizeof(double)));
-            LDM_CUDA(cudaMemset(h->peer_own[b], 0, words * sizeof(double)));
-        }
-        if (!h->peer_own_flags) LDM_CUDA(cudaMalloc((void**)&h->peer_own_flags, ldm::kMaxPeers * sizeof(unsigned long long)));
-        if (!h->peer_done) LDM_CUDA(cudaMalloc((void**)&h->peer_done, sizeof(unsigned int)));
-        if (!h->peer_status) LDM_CUDA(cudaMalloc((void**)&h->peer_status, sizeof(int)));
-        if (h->peer_sync) { cudaFree(h->peer_sync); h->peer_sync = nullptr; }
-        LDM_CUDA(cudaMalloc((void**)&h->peer_sync, (2 + 2 * (size_t)h->dev.rows_per_rank) * sizeof(unsigned int)));
-        LDM_CUDA(cudaMemset(h->peer_sync, 0, (2 + 2 * (size_t)h->dev.rows_per_rank) * sizeof(unsigned int)));
-        LDM_CUDA(cudaMemset(h->peer_own_flags, 0, ldm::kMaxPeers * sizeof(unsigned long long)));
-        LDM_CUDA(cudaMemset(h->peer_done, 0, sizeof(unsigned int)));
-        LDM_CUDA(cudaMemset(h->peer_status, 0, sizeof(int)));
-        static_assert(sizeof(cudaIpcMemHandle_t) == LDM_IPC_HANDLE_BYTES, "IPC handle size");
-        cudaIpcMemHandle_t ipc;
-        void* exported[3] = {h->peer_own[0], h->peer_own[1], h->peer_own_flags};
-        for (int i = 0; i < 3; i++) {
-            LDM_CUDA(cudaIpcGetMemHandle(&ipc, exported[i]));
-            std::memcpy(handles + (size_t)i * LDM_IPC_HANDLE_BYTES, &ipc, LDM_IPC_HANDLE_BYTES);
-        }
-        LDM_CUDA(cudaDeviceSynchronize());
-    });
-}
-
-int ldm_shard_peer_connect(ldm_handle h, const unsigned char* all_handles)
-{
-    if (!h || !all_handles) return fail(LDM_ERR_ARGUMENT, "NULL argument");
-    if (!h->peer_own[0]) return fail(LDM_ERR_ARGUMENT, "call ldm_shard_peer_alloc first");
-    return guarded([&] {
-        LDM_CUDA(cudaSetDevice(h->device));
-        for (void* p : h->peer_opened) cudaIpcCloseMemHandle(p);
-        h->peer_opened.clear();
-        for (int r = 0; r < h->dev.world; r++) {
-            void* mapped[3] = {h->peer_own[0], h->peer_own[1], h->peer_own_flags};
-            if (r != h->dev.rank) {
-                for (int i = 0; i < 3; i++) {
-                    cudaIpcMemHandle_t ipc;
-                    std::memcpy(&ipc, all_handles + ((size_t)r * 3 + i) * LDM_IPC_HANDLE_BYTES, LDM_IPC_HANDLE_BYTES);
-                    LDM_CUDA(cudaIpcOpenMemHandle(&mapped[i], ipc, cudaIpcMemLazyEnablePeerAccess));
-                    h->peer_opened.push_back(mapped[i]);
-                }
-            }
-            h->peer_C[0][r] = static_cast<double*>(mapped[0]);
-            h->peer_C[1][r] = static_cast<double*>(mapped[1]);
-            h->peer_flags[r] = static_cast<unsigned long long*>(mapped[2]);
-        }
-        h->peer_connected = true;
-    });
-}
-
-int ldm_shard_peer_upload(ldm_handle h, const double* C_gathered, double N)
-{
-    if (!h || !C_gathered) return fail(LDM_ERR_ARGUMENT, "NULL argument");
-    if (!h->peer_connected) return fail(LDM_ERR_ARGUMENT, "peers are not connected");
-    return guarded([&] {
-        LDM_CUDA(cudaSetDevice(h->device));
-        const size_t words = (size_t)h->dev.world * h->dev.rows_per_rank * h->dev.G;
-        LDM_CUDA(cudaDeviceSynchronize());
-        LDM_CUDA(cudaMemcpy(h->peer_own[0], C_gathered, words * sizeof(double), cudaMemcpyHostToDevice));
-        LDM_CUDA(cudaMemset(h->peer_own_flags, 0, ldm::kMaxPeers * sizeof(unsigned long long)));
-        LDM_CUDA(cudaMemset(h->peer_done, 0, sizeof(unsigned int)));
-        LDM_CUDA(cudaMemset(h->peer_sync, 0, (2 + 2 * (size_t)h->dev.rows_per_rank) * sizeof(unsigned int)));
-        LDM_CUDA(cudaMemset(h->peer_status, 0, sizeof(int)));
-        h->cur = 0;
-        LDM_CUDA(cudaMemcpy(h->d_N, &N, sizeof(double), cudaMemcpyHostToDevice));
-        h->peer_epoch = 0;
-        h->peer_parity = 0;
-        LDM_CUDA(cudaDeviceSynchronize());
-    });
-}
-
-int ldm_shard_peer_step(ldm_handle h, double dt, void* cuda_stream)
-{
-    if (!h) return fail(LDM_ERR_ARGUMENT, "NULL handle");
-    if (!h->peer_connected) return fail(LDM_ERR_ARGUMENT, "peers are not connected");
-    if (h->algo == LDM_ALGO_DIRECT) return fail(LDM_ERR_UNSUPPORTED, "the fused exchange rides on the factored path");
-    if (h->dev.extrapolation == LDM_EXTRAPOLATION_EXPONENTIAL) return fail(LDM_ERR_UNSUPPORTED, "Exponential extrapolation: use ldm_shard_step");
-    return guarded([&] {
-        LDM_CUDA(cudaSetDevice(h->device));
-        cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
-        ldm_context* c = h;
-        ensure_ring_operator(c);
-        if (c->plan.use_w) ensure_w_operand(c);
-        const int cur = c->cur, nxt = cur ^ 1;
-        const int pb = c->peer_parity;
-        ldm::StepArgs args = make_step_args(c, c->peer_own[pb], c->d_N + cur, c->d_N + nxt, dt, nullptr, nullptr, nullptr);
-        args.peer_count = c->dev.world;
-        for (int r = 0; r < c->dev.world; r++) {
-            args.peer_C_next[r] = c->peer_C[pb ^ 1][r];
-            args.peer_flags[r] = c->peer_flags[r];
-        }
-        args.done_counter = c->peer_done;
-        args.epoch = c->peer_epoch + 1;
-        args.sync_words = c->peer_sync;
-        args.peer_status = c->peer_status;
-        if (c->plan.scan && std::getenv("LDM_SHARD_ONE_LAUNCH") != nullptr) {
-            // Option (off: measured 11 % slower at G = 512): the whole step -- WC rows, ring correction,
-            // integral, closing, exchange -- in one launch behind the one-warp wait for the peers' previous step; the last
-            // chunk CTA of a row closes and ships the row while the rows behind it are still being computed
-            ldm::launch_peer_wait(c->peer_own_flags, c->dev.world, c->peer_epoch, c->peer_status, s);
-            ldm::launch_scan_exchange(args, s);
-            c->launches += 2;
-            c->cur = nxt;
-            c->peer_parity = pb ^ 1;
-            c->peer_epoch += 1;
-            LDM_CUDA(cudaGetLastError());
-            return;
-        }
-        // every rank must have delivered the previous step into this rank's current replica
-        ldm::launch_peer_wait(c->peer_own_flags, c->dev.world, c->peer_epoch, c->peer_status, s);
-        const bool side = args.P.n_ring > 0;
-        if (side) {
-            LDM_CUDA(cudaEventRecord(c->ev_fork, s));
-            LDM_CUDA(cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
-            ldm::launch_ring(args, c->aux_stream);
-            LDM_CUDA(cudaEventRecord(c->ev_join, c->aux_stream));
-        }
-        launch_integral(c, args, s);
-        if (side) LDM_CUDA(cudaStreamWaitEvent(s, c->ev_join, 0));
-        ldm::launch_finish_factored(args, s);
-        c->launches += 3 + (side ? 1 : 0);
-        c->cur = nxt;
-        c->peer_parity = pb ^ 1;
-        c->peer_epoch += 1;
-        LDM_CUDA(cudaGetLastError());
-    });
-}
-
-int ldm_shard_peer_download(ldm_handle h, double* C_gathered, double* N)
-{
-    if (!h || !C_gathered) return fail(LDM_ERR_ARGUMENT, "NULL argument");
-    if (!h->peer_connected) return fail(LDM_ERR_ARGUMENT, "peers are not connected");
-    return guarded([&] {
-        LDM_CUDA(cudaSetDevice(h->device));
-        const size_t words = (size_t)h->dev.world * h->dev.rows_per_rank * h->dev.G;
-        // the current replica is complete once every rank has published the last step
-        ldm::launch_peer_wait(h->peer_own_flags, h->dev.world, h->peer_epoch, h->peer_status, h->stream);
-        LDM_CUDA(cudaDeviceSynchronize());
-        int status = 0;
-        LDM_CUDA(cudaMemcpy(&status, h->peer_status, sizeof(int), cudaMemcpyDeviceToHost));
-        if (status != 0) throw CudaError("rank " + std::to_string(status - 1) + " never published its step (peer exchange timed out)");
-        LDM_CUDA(cudaMemcpy(C_gathered, h->peer_own[h->peer_parity], words * sizeof(double), cudaMemcpyDeviceToHost));
-        if (N) LDM_CUDA(cudaMemcpy(N, h->d_N + h->cur, sizeof(double), cudaMemcpyDeviceToHost));
-    });
-}
 
 const char* ldm_last_error(void) { return g_error.c_str(); }
 const char* ldm_version(void) { return "ldm_b200 0.1 (sm_100a)"; }
@@ -733,6 +481,7 @@ int ldm_problem_kernel_structure(const ldm_problem* p, int* separable, double* m
     if (!p || !separable || !max_rel_dev) return fail(LDM_ERR_ARGUMENT, "NULL argument");
     if (p->species != 1 || p->G < 2 || p->K < 3 || !p->moments_grid || !p->kernels_grid || !p->M || !p->W)
         return fail(LDM_ERR_ARGUMENT, "incomplete problem description");
+    if (const std::string defect = problem_defect(p); !defect.empty()) return fail(LDM_ERR_ARGUMENT, defect);
     return guarded([&] {
         ldm::Tables t;
         ldm::build_tables(*p, t);
@@ -743,12 +492,33 @@ int ldm_problem_kernel_structure(const ldm_problem* p, int* separable, double* m
     });
 }
 
+int ldm_tuning_set(const char* name, int value)
+{
+    if (!name) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    ldm::Tuning& t = tuning();
+    const std::string key(name);
+    if (key == "reset") t = ldm::Tuning();
+    else if (key == "scan_bn") t.scan_bn = value;
+    else if (key == "scan_nt") t.scan_nt = value;
+    else if (key == "factored_bm") t.factored_bm = value;
+    else if (key == "factored_bn") t.factored_bn = value;
+    else if (key == "factored_tn") t.factored_tn = value;
+    else if (key == "persistent") t.persistent = value;
+    else if (key == "scan") t.scan = value;
+    else if (key == "chunk_grid") t.chunk_grid = value;
+    else return fail(LDM_ERR_ARGUMENT, "unknown tuning key");
+    return LDM_OK;
+}
+
 int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
 {
     if (!p || !out) return fail(LDM_ERR_ARGUMENT, "NULL argument");
     if (p->species < 1 || p->species > LDM_MAX_SPECIES) return fail(LDM_ERR_UNSUPPORTED, "1 .. LDM_MAX_SPECIES species");
     if (p->G < 2 || p->K < 3 || !p->moments_grid || !p->kernels_grid || !p->M || !p->W)
         return fail(LDM_ERR_ARGUMENT, "incomplete problem description");
+    if (p->species > 1 && (!p->mM_of || !p->mW_of || !p->sigma_m_of || !p->sigma_w_of || !p->b_of || !p->d_of || !p->d_prime_of))
+        return fail(LDM_ERR_ARGUMENT, "a multi-species problem needs its per-species arrays (ldm_problem_generate_multi)");
+    if (const std::string defect = problem_defect(p); !defect.empty()) return fail(LDM_ERR_ARGUMENT, defect);
     if (p->species > 1) {
         if (!p->mM_of || !p->mW_of || !p->sigma_m_of || !p->sigma_w_of || !p->b_of || !p->d_of || !p->d_prime_of)
             return fail(LDM_ERR_ARGUMENT, "a multi-species problem needs its per-species arrays (ldm_problem_generate_multi)");
@@ -836,9 +606,13 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         const size_t P = c->P();
         double* out_weight = c->alloc<double>(P);
         d.out_weight = out_weight;
-        c->d_C[0] = c->alloc<double>(P);
-        c->d_C[1] = c->alloc<double>(P);
+        c->d_C[0] = c->alloc<double>(P + (size_t)d.G);     // + the tail of WC row dots (persistent_chunks_kernel)
+        c->d_C[1] = c->alloc<double>(P + (size_t)d.G);
         c->d_N = c->alloc<double>(2);
+        c->d_status = c->alloc<int>(1);
+        c->d_flags = c->alloc<unsigned long long>(ldm::kMaxPeers);
+        LDM_CUDA(cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream));
+        LDM_CUDA(cudaMemsetAsync(c->d_flags, 0, ldm::kMaxPeers * sizeof(unsigned long long), c->stream));
         c->d_scalars = c->alloc<double>(ldm::kScalars);
         c->d_sum = c->alloc<double>(P);
         c->d_deriv = c->alloc<double>(P);
@@ -853,7 +627,7 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         ldm::detect_separable(t.offM, kSeparableTolerance, c->separable);
         const int scan_bn = (c->separable.ok && d.G <= 65535) ? ldm::scan_pick_bn(d.G, d.A) : 0;
         c->plan_dense = ldm::plan_factored(d);
-        if (scan_bn > 0 && std::getenv("LDM_SCAN_DISABLE") == nullptr) {
+        if (scan_bn > 0 && tuning().scan != 0) {
             d.qvec = c->upload(c->separable.q);
             d.a_star = c->upload(c->separable.a_star);
             std::vector<int> pairs((size_t)d.A * 2);
@@ -878,11 +652,12 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
                 for (int ch = 0; ch < d.scan_chunks; ch++) order[(size_t)ch] = ch;
                 std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return work[(size_t)a] > work[(size_t)b]; });
                 d.scan_chunk_order = c->upload(order);
+                c->chunk_order_host = order;
             }
             d.scan_live_rows = 0;
             while (d.scan_live_rows < d.A && c->separable.a_star[(size_t)d.scan_live_rows] >= 0) d.scan_live_rows++;
             c->plan_scan = c->plan_dense;
-            c->plan_scan.scan = true; c->plan_scan.use_w = false;
+            c->plan_scan.scan = true;
             c->plan_scan.tiles = 1; c->plan_scan.chunks = d.scan_chunks;
             c->scan_available = true;
         }
@@ -893,7 +668,8 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         c->d_wc_rows = c->alloc<double>((size_t)d.G);
         c->d_wc_rows2 = c->alloc<double>(2 * (size_t)d.G);
         c->d_barrier = c->alloc<unsigned int>(1 + (size_t)d.G);
-        if (const char* env = std::getenv("LDM_PERSISTENT")) c->persistent_enabled = std::atoi(env) != 0;
+        if (tuning().persistent >= 0) c->persistent_enabled = tuning().persistent != 0;
+        c->chunk_grid_limit = tuning().chunk_grid;
         d.n_ring = 0;
         LDM_CUDA(cudaMemsetAsync(c->d_C[0], 0, P * sizeof(double), c->stream));
         LDM_CUDA(cudaMemsetAsync(c->d_C[1], 0, P * sizeof(double), c->stream));
@@ -905,7 +681,7 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         // the ring-correction operator of the unsharded problem, here rather than at the first step: callers create the
         // entries of a sweep from several host threads, and this host-side build is most of an entry's set-up cost
         // (ldm_shard_configure rebuilds it for the rank's rows)
-        if (std::getenv("LDM_LAZY_RING") == nullptr) ensure_ring_operator(c.get());
+        ensure_ring_operator(c.get());
         LDM_CUDA(cudaStreamSynchronize(c->stream));
         *out = c.release();
     });
@@ -1070,6 +846,7 @@ int ldm_rhs(ldm_handle h, const double* state, double* deriv)
             multi_download_derivs(h, deriv, h->stream);
             LDM_CUDA(cudaStreamSynchronize(h->stream));
         });
+    if (h->dev.world != 1) return fail(LDM_ERR_UNSUPPORTED, "the handle is configured as one rank of several (ldm_shard_configure): use the ldm_shard_* entry points, or ldm_shard_configure(h, 0, 1) to go back");
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
         upload_state(h, state);
@@ -1085,6 +862,7 @@ int ldm_integrals(ldm_handle h, const double* state, double* WC, double* MC)
 {
     if (!h || !state || !WC) return fail(LDM_ERR_ARGUMENT, "NULL argument");
     if (h->species != 1) return fail(LDM_ERR_UNSUPPORTED, "not built for several species (ldm.h: ldm_problem_generate_multi)");
+    if (h->dev.world != 1) return fail(LDM_ERR_UNSUPPORTED, "the handle is configured as one rank of several (ldm_shard_configure): use the ldm_shard_* entry points, or ldm_shard_configure(h, 0, 1) to go back");
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
         upload_state(h, state);
@@ -1176,6 +954,7 @@ int ldm_solve(ldm_handle h, const double* init, double dt, double t_max, int rec
             LDM_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev_begin, h->ev_end));
         });
     }
+    if (h->dev.world != 1) return fail(LDM_ERR_UNSUPPORTED, "the handle is configured as one rank of several (ldm_shard_configure): use the ldm_shard_* entry points, or ldm_shard_configure(h, 0, 1) to go back");
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
         const int n = ldm_count_points(t_max, dt);
@@ -1185,96 +964,86 @@ int ldm_solve(ldm_handle h, const double* init, double dt, double t_max, int rec
             double time = 0;
             for (int k = 0; k < n; k++) { times[k] = time; time += dt; }   // the accumulated clock of S:565-588
         }
-        double* d_hist = nullptr;        // device-side history, copied out once at the end
-        double* d_dhist = nullptr;
-        std::vector<void*> scratch;
-        auto scratch_alloc = [&](size_t count) {
-            void* p = nullptr;
-            LDM_CUDA(cudaMalloc(&p, count * sizeof(double)));
-            scratch.push_back(p);
-            return static_cast<double*>(p);
-        };
-        try {
-            if (record == LDM_RECORD_OBSERVABLES) d_hist = scratch_alloc((size_t)n * 2);
-            if (record >= LDM_RECORD_VALUES) d_hist = scratch_alloc((size_t)n * width);
-            if (record == LDM_RECORD_ALL) d_dhist = scratch_alloc((size_t)n * width);
-            upload_state(h, init);
-            const bool persistent = persistent_possible(h);
-            LDM_CUDA(cudaEventRecord(h->ev_begin, h->stream));
-            if (persistent) {
-                // every step but the closing evaluation inside ONE launch; the kernel records the history itself
-                if (record >= LDM_RECORD_VALUES) {
-                    LDM_CUDA(cudaMemcpyAsync(d_hist, h->d_N + h->cur, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-                    LDM_CUDA(cudaMemcpyAsync(d_hist + 1, h->d_C[h->cur], P * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-                }
-                advance_persistent(h, n - 1, dt, 0, record == LDM_RECORD_OBSERVABLES ? d_hist : nullptr,
-                                   record >= LDM_RECORD_VALUES ? d_hist : nullptr, record == LDM_RECORD_ALL ? d_dhist : nullptr);
-                if (record == LDM_RECORD_OBSERVABLES) {
-                    ldm::launch_record_observables(h->dev, h->d_N + h->cur, h->d_C[h->cur], d_hist + (size_t)(n - 1) * 2, h->stream);
-                    h->launches += 1;
-                }
-                if (record == LDM_RECORD_ALL || derivs) {   // the reference evaluates the equation once more at the final point (S:582-583)
-                    rhs_and_update(h, h->dev, h->d_C[h->cur], h->d_N + h->cur, nullptr, dt, nullptr, h->d_deriv, nullptr, h->stream);
-                    if (record == LDM_RECORD_ALL) {
-                        LDM_CUDA(cudaMemcpyAsync(d_dhist + (size_t)(n - 1) * width, h->d_scalars + 1, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-                        LDM_CUDA(cudaMemcpyAsync(d_dhist + (size_t)(n - 1) * width + 1, h->d_deriv, P * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
+        cudaStream_t s = h->stream;
+        upload_state(h, init);
+        const Resident mode = resident_mode(h);
+        // History leaves the device segment by segment: `seg_len` steps per segment, two buffers, the copy of one segment
+        // under the computation of the next.  Per step a segment holds the observables recorded when the step begins
+        // (OBSERVABLES), or the state behind the step (VALUES) and the derivative that produced it (ALL).
+        const size_t per_step = record == LDM_RECORD_OBSERVABLES ? 2 : record == LDM_RECORD_VALUES ? width : record == LDM_RECORD_ALL ? 2 * width : 0;
+        int seg_len = std::max(1, n - 1);
+        if (per_step != 0) {
+            seg_len = (int)std::min<size_t>((size_t)seg_len, std::max<size_t>(1, kHistorySegmentBytes / (per_step * sizeof(double))));
+            ensure_history(h, (size_t)seg_len * per_step);
+        }
+        if (record >= LDM_RECORD_VALUES) std::memcpy(values, init, width * sizeof(double));      // Values[0] (S:568)
+        LDM_CUDA(cudaEventRecord(h->ev_begin, s));
+        for (int k0 = 0, seg = 0; k0 < n - 1; k0 += seg_len, seg++) {
+            const int len = std::min(seg_len, n - 1 - k0), b = seg & 1;
+            double* buf = per_step != 0 ? h->d_hist[b] : nullptr;
+            if (buf && seg >= 2) LDM_CUDA(cudaStreamWaitEvent(s, h->ev_copied[b], 0));          // the buffer's previous segment has left
+            double* d_obs = record == LDM_RECORD_OBSERVABLES ? buf : nullptr;
+            double* d_val = record >= LDM_RECORD_VALUES ? buf : nullptr;                         // [len][width]: the states behind the steps
+            double* d_der = record == LDM_RECORD_ALL ? buf + (size_t)len * width : nullptr;      // [len][width]
+            if (mode != Resident::None) {
+                // all steps of the segment inside ONE launch; the kernel records the history itself (it stores the state
+                // behind step j at values + (j + 1) * width, hence the shifted base)
+                advance_resident(h, mode, len, dt, d_obs, d_val ? d_val - width : nullptr, d_der);
+            } else {
+                for (int j = 0; j < len; j++) {
+                    if (d_obs) {
+                        ldm::launch_record_observables(h->dev, h->d_N + h->cur, h->d_C[h->cur], d_obs + (size_t)j * 2, s);
+                        h->launches += 1;
+                    }
+                    step_resident(h, dt, d_der ? h->d_deriv : nullptr);                          // S:567 / S:577-582
+                    if (d_val) {
+                        LDM_CUDA(cudaMemcpyAsync(d_val + (size_t)j * width, h->d_N + h->cur, sizeof(double), cudaMemcpyDeviceToDevice, s));
+                        LDM_CUDA(cudaMemcpyAsync(d_val + (size_t)j * width + 1, h->d_C[h->cur], P * sizeof(double), cudaMemcpyDeviceToDevice, s));
+                    }
+                    if (d_der) {
+                        LDM_CUDA(cudaMemcpyAsync(d_der + (size_t)j * width, h->d_scalars + 1, sizeof(double), cudaMemcpyDeviceToDevice, s));
+                        LDM_CUDA(cudaMemcpyAsync(d_der + (size_t)j * width + 1, h->d_deriv, P * sizeof(double), cudaMemcpyDeviceToDevice, s));
                     }
                 }
             }
-            for (int k = 0; k < n && !persistent; k++) {
-                const double* Ncur = h->d_N + h->cur;
-                const double* Ccur = h->d_C[h->cur];
-                if (record == LDM_RECORD_OBSERVABLES) {
-                    ldm::launch_record_observables(h->dev, Ncur, Ccur, d_hist + (size_t)k * 2, h->stream);
-                    h->launches += 1;
-                } else if (record >= LDM_RECORD_VALUES) {
-                    LDM_CUDA(cudaMemcpyAsync(d_hist + (size_t)k * width, Ncur, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-                    LDM_CUDA(cudaMemcpyAsync(d_hist + (size_t)k * width + 1, Ccur, P * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-                }
-                const bool last = (k == n - 1);
-                const bool want_deriv = (record == LDM_RECORD_ALL) || (last && derivs);
-                if (last && !want_deriv) break;
-                if (last) {       // the reference evaluates the equation once more at the final point (S:582-583)
-                    rhs_and_update(h, h->dev, Ccur, Ncur, nullptr, dt, nullptr, h->d_deriv, nullptr, h->stream);
-                } else {
-                    step_resident(h, dt, want_deriv ? h->d_deriv : nullptr);
-                }
-                if (record == LDM_RECORD_ALL) {
-                    LDM_CUDA(cudaMemcpyAsync(d_dhist + (size_t)k * width, h->d_scalars + 1, sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-                    LDM_CUDA(cudaMemcpyAsync(d_dhist + (size_t)k * width + 1, h->d_deriv, P * sizeof(double), cudaMemcpyDeviceToDevice, h->stream));
-                }
+            if (buf) {
+                LDM_CUDA(cudaEventRecord(h->ev_segment[b], s));
+                LDM_CUDA(cudaStreamWaitEvent(h->copy_stream, h->ev_segment[b], 0));
+                if (d_obs) LDM_CUDA(cudaMemcpyAsync(values + (size_t)k0 * 2, d_obs, (size_t)len * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+                if (d_val) LDM_CUDA(cudaMemcpyAsync(values + (size_t)(k0 + 1) * width, d_val, (size_t)len * width * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+                if (d_der) LDM_CUDA(cudaMemcpyAsync(derivs + (size_t)k0 * width, d_der, (size_t)len * width * sizeof(double), cudaMemcpyDeviceToHost, h->copy_stream));
+                LDM_CUDA(cudaEventRecord(h->ev_copied[b], h->copy_stream));
             }
-            LDM_CUDA(cudaEventRecord(h->ev_end, h->stream));
-            LDM_CUDA(cudaGetLastError());
-            if (record == LDM_RECORD_LAST) {
-                if (values) {
-                    LDM_CUDA(cudaMemcpyAsync(values, h->d_N + h->cur, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-                    LDM_CUDA(cudaMemcpyAsync(values + 1, h->d_C[h->cur], P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-                }
-                if (derivs) {
-                    LDM_CUDA(cudaMemcpyAsync(derivs, h->d_scalars + 1, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-                    LDM_CUDA(cudaMemcpyAsync(derivs + 1, h->d_deriv, P * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-                }
-            } else if (record == LDM_RECORD_OBSERVABLES) {
-                LDM_CUDA(cudaMemcpyAsync(values, d_hist, (size_t)n * 2 * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-            } else {
-                LDM_CUDA(cudaMemcpyAsync(values, d_hist, (size_t)n * width * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-                if (record == LDM_RECORD_ALL)
-                    LDM_CUDA(cudaMemcpyAsync(derivs, d_dhist, (size_t)n * width * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-            }
-            LDM_CUDA(cudaStreamSynchronize(h->stream));
-            LDM_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev_begin, h->ev_end));
-        } catch (...) {
-            for (void* p : scratch) cudaFree(p);
-            throw;
         }
-        for (void* p : scratch) cudaFree(p);
+        // the last point: its observables; and the reference evaluates the equation once more there (S:582-583)
+        if (record == LDM_RECORD_OBSERVABLES) {
+            ldm::launch_record_observables(h->dev, h->d_N + h->cur, h->d_C[h->cur], h->d_scalars + 5, s);
+            h->launches += 1;
+            LDM_CUDA(cudaMemcpyAsync(values + (size_t)(n - 1) * 2, h->d_scalars + 5, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
+        }
+        if (record == LDM_RECORD_ALL || derivs) {
+            rhs_and_update(h, h->dev, h->d_C[h->cur], h->d_N + h->cur, nullptr, dt, nullptr, h->d_deriv, nullptr, s);
+            double* out = record == LDM_RECORD_ALL ? derivs + (size_t)(n - 1) * width : derivs;
+            LDM_CUDA(cudaMemcpyAsync(out, h->d_scalars + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
+            LDM_CUDA(cudaMemcpyAsync(out + 1, h->d_deriv, P * sizeof(double), cudaMemcpyDeviceToHost, s));
+        }
+        LDM_CUDA(cudaEventRecord(h->ev_end, s));
+        LDM_CUDA(cudaGetLastError());
+        if (record == LDM_RECORD_LAST && values) {
+            LDM_CUDA(cudaMemcpyAsync(values, h->d_N + h->cur, sizeof(double), cudaMemcpyDeviceToHost, s));
+            LDM_CUDA(cudaMemcpyAsync(values + 1, h->d_C[h->cur], P * sizeof(double), cudaMemcpyDeviceToHost, s));
+        }
+        LDM_CUDA(cudaStreamSynchronize(s));
+        if (h->copy_stream) LDM_CUDA(cudaStreamSynchronize(h->copy_stream));
+        check_device_status(h);
+        LDM_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev_begin, h->ev_end));
     });
 }
 
 int ldm_state_upload(ldm_handle h, const double* state)
 {
     if (!h || !state) return fail(LDM_ERR_ARGUMENT, "NULL argument");
+    if (h->species == 1 && h->dev.world != 1) return fail(LDM_ERR_UNSUPPORTED, "the handle is configured as one rank of several (ldm_shard_configure): use the ldm_shard_* entry points, or ldm_shard_configure(h, 0, 1) to go back");
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
         if (h->species != 1) multi_upload(h, state, h->stream);
@@ -1292,17 +1061,20 @@ int ldm_state_download(ldm_handle h, double* state)
             multi_download(h, state, h->stream);
             LDM_CUDA(cudaStreamSynchronize(h->stream));
         });
+    if (h->dev.world != 1) return fail(LDM_ERR_UNSUPPORTED, "the handle is configured as one rank of several (ldm_shard_configure): use the ldm_shard_* entry points, or ldm_shard_configure(h, 0, 1) to go back");
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
         LDM_CUDA(cudaMemcpyAsync(state, h->d_N + h->cur, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         LDM_CUDA(cudaMemcpyAsync(state + 1, h->d_C[h->cur], h->P() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         LDM_CUDA(cudaStreamSynchronize(h->stream));
+        check_device_status(h);
     });
 }
 
 int ldm_advance(ldm_handle h, int n_steps, double dt)
 {
     if (!h || n_steps < 0) return fail(LDM_ERR_ARGUMENT, "bad argument");
+    if (h->species == 1 && h->dev.world != 1) return fail(LDM_ERR_UNSUPPORTED, "the handle is configured as one rank of several (ldm_shard_configure): use the ldm_shard_* entry points, or ldm_shard_configure(h, 0, 1) to go back");
     if (h->species != 1)
         return guarded([&] {
             LDM_CUDA(cudaSetDevice(h->device));
@@ -1313,9 +1085,9 @@ int ldm_advance(ldm_handle h, int n_steps, double dt)
         });
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
-        const bool persistent = persistent_possible(h);
+        const Resident mode = resident_mode(h);
         LDM_CUDA(cudaEventRecord(h->ev_begin, h->stream));
-        if (persistent) advance_persistent(h, n_steps, dt, 0, nullptr, nullptr, nullptr);
+        if (mode != Resident::None) advance_resident(h, mode, n_steps, dt, nullptr, nullptr, nullptr);
         else for (int k = 0; k < n_steps; k++) step_resident(h, dt, nullptr);
         LDM_CUDA(cudaEventRecord(h->ev_end, h->stream));
         LDM_CUDA(cudaGetLastError());
@@ -1328,6 +1100,7 @@ int ldm_synchronize(ldm_handle h)
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
         LDM_CUDA(cudaStreamSynchronize(h->stream));
+        if (h->species == 1) check_device_status(h);
     });
 }
 
@@ -1369,12 +1142,11 @@ void advance_batch_on_device(const std::vector<ldm_context*>& handles, int point
         for (int i = 0; i < n; i++) {
             ldm_context* h = handles[i];
             ensure_ring_operator(h);
-            if (h->plan.use_w) ensure_w_operand(h);
-            Group* g = nullptr;
+                Group* g = nullptr;
             for (Group& cand : groups)
                 if ((cand.shape.scan && h->plan.scan && cand.scan_nt == h->dev.scan_nt) ||   // the prefix-sum kernel takes its tile shape at run time
                     (!cand.shape.scan && !h->plan.scan && cand.shape.bm == h->plan.bm && cand.shape.bn == h->plan.bn &&
-                     cand.shape.tn == h->plan.tn && cand.shape.mma == h->plan.mma && cand.shape.use_w == h->plan.use_w)) g = &cand;
+                     cand.shape.tn == h->plan.tn)) g = &cand;
             if (!g) { groups.emplace_back(); g = &groups.back(); g->shape = h->plan; g->scan_nt = h->dev.scan_nt; }
             g->members.push_back(i);
             g->max_slabs = std::max(g->max_slabs, h->plan.slabs());
@@ -1415,7 +1187,6 @@ void advance_batch_on_device(const std::vector<ldm_context*>& handles, int point
                         LDM_CUDA(cudaEventRecord(lead->ev_join, lead->aux_stream));
                     }
                     if (g.shape.scan) ldm::launch_scan_batch(g.d_args[parity], members, g.scan_nt, g.max_slabs, g.max_rows, g.max_smem, s);
-                    else if (g.shape.use_w) ldm::launch_factored_w_batch(g.shape, g.d_args[parity], members, g.max_slabs, g.max_rows, g.max_G, s);
                     else ldm::launch_factored_batch(g.shape, g.d_args[parity], members, g.max_slabs, g.max_rows, g.max_G, g.max_A, s);
                     if (side) LDM_CUDA(cudaStreamWaitEvent(s, lead->ev_join, 0));
                     ldm::launch_finish_factored_batch(g.d_args[parity], members, g.max_points, s);
@@ -1449,6 +1220,7 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
         for (int i = 0; i < n; i++) {
             if (!handles[i] || !inits[i] || !last_states[i]) throw std::invalid_argument("NULL entry in batch");
             if (handles[i]->species != 1) throw std::invalid_argument("batches are built for one species per entry");
+            if (handles[i]->dev.world != 1) throw std::invalid_argument("a batch entry is configured as one rank of several (ldm_shard_configure)");
             ldm_context* h = handles[i];
             LDM_CUDA(cudaSetDevice(h->device));
             upload_state(h, inits[i]);
@@ -1506,55 +1278,6 @@ int ldm_device_count(void)
 {
     int count = 0;
     return cudaGetDeviceCount(&count) == cudaSuccess ? count : 0;
-}
-
-int ldm_shard_configure(ldm_handle h, int rank, int world)
-{
-    if (!h || world < 1 || rank < 0 || rank >= world) return fail(LDM_ERR_ARGUMENT, "bad rank/world");
-    if (h->species != 1) return fail(LDM_ERR_UNSUPPORTED, "not built for several species (ldm.h: ldm_problem_generate_multi)");
-    if (world > h->dev.G) return fail(LDM_ERR_ARGUMENT, "more ranks than moment-grid rows");
-    h->dev.world = world;
-    h->dev.rank = rank;
-    h->dev.rows_per_rank = (h->dev.G + world - 1) / world;
-    return LDM_OK;
-}
-
-int ldm_shard_rows_per_rank(ldm_handle h) { return h ? h->dev.rows_per_rank : 0; }
-
-int ldm_shard_set_N(ldm_handle h, double N)
-{
-    if (h && h->species != 1) return fail(LDM_ERR_UNSUPPORTED, "not built for several species (ldm.h: ldm_problem_generate_multi)");
-    if (!h) return fail(LDM_ERR_ARGUMENT, "NULL handle");
-    return guarded([&] {
-        LDM_CUDA(cudaSetDevice(h->device));
-        h->cur = 0;
-        LDM_CUDA(cudaMemcpy(h->d_N, &N, sizeof(double), cudaMemcpyHostToDevice));
-    });
-}
-
-int ldm_shard_get_N(ldm_handle h, double* N)
-{
-    if (h && h->species != 1) return fail(LDM_ERR_UNSUPPORTED, "not built for several species (ldm.h: ldm_problem_generate_multi)");
-    if (!h || !N) return fail(LDM_ERR_ARGUMENT, "NULL argument");
-    return guarded([&] {
-        LDM_CUDA(cudaSetDevice(h->device));
-        LDM_CUDA(cudaDeviceSynchronize());
-        LDM_CUDA(cudaMemcpy(N, h->d_N + h->cur, sizeof(double), cudaMemcpyDeviceToHost));
-    });
-}
-
-int ldm_shard_step(ldm_handle h, const double* d_C_gathered, double* d_C_shard_out, double dt, void* cuda_stream)
-{
-    if (h && h->species != 1) return fail(LDM_ERR_UNSUPPORTED, "not built for several species (ldm.h: ldm_problem_generate_multi)");
-    if (!h || !d_C_gathered || !d_C_shard_out) return fail(LDM_ERR_ARGUMENT, "NULL argument");
-    return guarded([&] {
-        LDM_CUDA(cudaSetDevice(h->device));
-        cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);
-        const int cur = h->cur, nxt = cur ^ 1;
-        rhs_and_update(h, h->dev, d_C_gathered, h->d_N + cur, h->d_N + nxt, dt, nullptr, nullptr, d_C_shard_out, s);
-        h->cur = nxt;
-        LDM_CUDA(cudaGetLastError());
-    });
 }
 
 }  // extern "C"

@@ -31,12 +31,6 @@ struct DevProblem {
     const double* weight_t;
     const int* alpha;          // [n_off]
     const double* quadrant;    // [A][A] odd-node quadrant of the m table
-    // W_x = Q . L_x (ldm_factored_w.cu): for every row x of this rank a_pad rows of w_k[x] doubles at W + w_offset[x],
-    // covering the moment-grid rows w_plo[x] .. w_plo[x] + w_k[x] - 1
-    const double* W;
-    const long long* w_offset; // [G] (-1: row not held by this rank)
-    const int* w_k;            // [G] multiple of 16
-    const int* w_plo;          // [G]
     // prefix-sum path (ldm_scan.cu; ldm_model.h SeparableKernel): Q[beta][alpha] = qvec[beta] qvec[alpha] for
     // alpha <= a_star[beta], 0 beyond.  NULL qvec: the table is not separable, the dense contraction is used.
     const double* qvec;        // [A]
@@ -97,11 +91,7 @@ struct StepArgs {
     unsigned long long* peer_flags[kMaxPeers];
     unsigned int* done_counter;
     unsigned long long epoch;
-    // one-launch sharded step (ldm_scan.cu scan_exchange_kernel): monotone counters, zeroed at ldm_shard_peer_upload --
-    // [0] WC rows done, [1] rows closed, [2 + lx] chunk CTAs of local row lx arrived, [2 + rows_per_rank + lx] ring CSR
-    // rows of local row lx done; and the status word a lost peer is reported in
-    unsigned int* sync_words;
-    int* peer_status;
+    int* peer_status;          // the status word a lost peer is reported in
     double dt;
 };
 
@@ -210,16 +200,15 @@ struct PersistentArgs {
     double* wc_rows;
     unsigned int* barrier;
     double* ring_pingpong;     // [2][G*G] ring values of even / odd steps; every byte 0xFF (an all-ones NaN) = not yet published
+    int* status;               // the handle's device status word (ldm_scan_body.cuh: bounded waits)
     long long ring_cache_offset;   // set by the launcher: byte offset in shared memory of this CTA's copy of its ring share (nodes, then
                                    // weights), or -1 when the shares do not have the one-row-per-warp shape
 };
 
 struct FactoredPlan {
     int bm = 80, bn = 64;      // CTA tile: beta rows x columns
-    bool mma = true;           // contraction on the FP64 tensor cores (mma.sync m8n8k4) instead of DFMA register tiles
-    bool use_w = false;        // contraction against the precomputed W_x = Q . L_x (ldm_factored_w.cu) instead of regenerating E_x:
-                               // measured slower (K_x averages 1.35-1.65 x A), LDM_FACTORED_W=1 enables
-    int tn = 8;                // columns per thread (8: 5x8 register tile, 4: 5x4 with twice the threads)
+    int tn = 8;                // columns per thread (8: 8-warp tiles, 4: twice the threads); the contraction runs on the FP64
+                               // tensor cores (mma.sync m8n8k4)
     bool scan = false;         // prefix-sum path (separable kernel table): tiles = 1, chunks = P.scan_chunks, runtime tile shape
     int tiles = 1, chunks = 1; // beta tiles x column chunks; slabs = tiles * chunks partial sums per node
     int slabs() const { return tiles * chunks; }
@@ -233,10 +222,6 @@ void launch_scan(const StepArgs& one, cudaStream_t stream);
 void launch_scan_batch(const StepArgs* d_batch, int n, int nt, int max_chunks, int max_rows, size_t max_smem, cudaStream_t stream);
 size_t scan_smem_bytes(int G, int A, int bn, int nt, int max_pieces);
 cudaError_t launch_persistent_scan(const PersistentArgs& args, int grid, cudaStream_t stream, int* max_grid);
-// xi-sharded step in ONE launch: wait for the peers' previous step, WC rows and ring correction (first CTAs), the
-// prefix-sum integral per (row, chunk), and the last chunk CTA of every row closes the row and stores it into every
-// rank's next replica -- rows travel over NVLink while the others are still computed; the last row publishes the epoch
-void launch_scan_exchange(const StepArgs& one, cudaStream_t stream);
 // single problem: `one` by value; batch: d_batch[n] in device memory, all entries sharing the plan's tile shape
 void launch_factored(const FactoredPlan& plan, const StepArgs& one, cudaStream_t stream);
 void launch_factored_batch(const FactoredPlan& shape, const StepArgs* d_batch, int n, int max_slabs, int max_rows, int max_G, int max_A,
@@ -244,9 +229,45 @@ void launch_factored_batch(const FactoredPlan& shape, const StepArgs* d_batch, i
 
 // grid <= 0: only report the largest co-resident grid in *max_grid
 cudaError_t launch_persistent(const FactoredPlan& plan, const PersistentArgs& args, int grid, cudaStream_t stream, int* max_grid);
-void launch_factored_w(const FactoredPlan& plan, const StepArgs& one, cudaStream_t stream);
-void launch_factored_w_batch(const FactoredPlan& shape, const StepArgs* d_batch, int n, int max_slabs, int max_rows, int max_G,
-                             cudaStream_t stream);
-void launch_build_w(const DevProblem& P, double* W, int a_pad, cudaStream_t stream);
+
+// Arguments of the persistent work-list kernel (ldm_persist.cu persistent_chunks_kernel): n_steps Euler steps of one
+// problem on `world` ranks in ONE launch per rank.  The pair density lives in two replicas per rank (ping-pong), each
+// `words` doubles in gathered layout followed by a tail of G doubles: the row dots of the WC functional for that state.
+// Rank r's closing code stores its updated rows -- and their row dots -- straight into replica[parity ^ 1][*] of EVERY
+// rank (peer-mapped memory over NVLink, own rank included) and, once all its rows are out, publishes the number of steps
+// it has completed in flags[*][r].  A step begins when this rank's own flag array shows that step for every rank.
+struct ChunkedArgs {
+    StepArgs step;             // the problem and its scratch (partial sums, scalars); C and N are set per step by the kernel
+    int n_steps, parity, world, rank;
+    unsigned long long epoch;  // steps taken since the upload: what every rank has published when this launch may begin
+    long long words;           // doubles of a replica in front of its WC tail
+    double* replica[2][kMaxPeers];
+    unsigned long long* flags[kMaxPeers];
+    double* N;                 // [2] first moment, ping-pong with the replicas (every rank advances its own copy: no all-reduce)
+    const int2* items;         // (local row, chunk) in the order they are handed out: most expensive first
+    int n_items;
+    unsigned int* counters;    // zeroed before the launch: [0] item fetch counter, [1] rows closed, [2] prologue barrier,
+                               // [3 + lx] chunk arrivals of local row lx; all monotone over the steps of the launch
+    double* ring_pingpong;     // [2][local_rows * G] ring values of even / odd steps; all-ones NaN = not yet published
+    const int* ring_cta_begin; // [grid + 1] the ring CSR rows dealt out evenly by entry count over the CTAs of this launch
+    int* status;
+    // history, one rank only (may be NULL): as PersistentArgs
+    long long first_point, stride;
+    double* observables;
+    double* values;
+    double* derivs;
+};
+// grid <= 0: only report the largest co-resident grid in *max_grid
+cudaError_t launch_persistent_chunks(const ChunkedArgs& args, int grid, cudaStream_t stream, int* max_grid);
+
+// Shape overrides for tests (ldm_tuning_set): 0 / -1 = the library decides.  Read when a handle is created.
+struct Tuning {
+    int scan_bn = 0, scan_nt = 0;              // prefix-sum path: chunk width, threads per CTA
+    int factored_bm = 0, factored_bn = 0, factored_tn = 0;   // dense contraction: tile shape
+    int persistent = -1;                       // 0: one launch per step even where a persistent kernel applies
+    int scan = -1;                             // 0: never take the prefix-sum path
+    int chunk_grid = 0;                        // persistent_chunks_kernel: CTAs per launch (tests run two ranks on one device)
+};
+Tuning& tuning();
 
 }  // namespace ldm

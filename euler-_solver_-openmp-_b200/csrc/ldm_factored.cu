@@ -19,10 +19,9 @@
 // generates its E chunk on the fly from C (4 taps per element), accumulates the BM x BN tile of H in registers
 // (plus the single halo column q0-1 that the first tap pairs of the chunk need), stages it in shared memory and
 // contracts it with the y-side interpolation rows.  Slabs are independent; finish_factored_kernel adds them up.
-#include <cstdlib>
-
 #include <cooperative_groups.h>
 
+#include "../../include/ldm.h"
 #include "ldm_device.h"
 #include "ldm_pointwise.cuh"
 
@@ -491,29 +490,19 @@ void launch_variant(const StepArgs* one, const StepArgs* d_batch, dim3 grid, int
 template <bool BATCH>
 void dispatch(const FactoredPlan& shape, const StepArgs* one, const StepArgs* d_batch, dim3 grid, int G, int A, cudaStream_t stream)
 {
-    if (shape.mma && shape.tn == 4) {   // FP64 tensor cores with twice the threads per tile (16 warps on an 80 x 128 tile)
+    // the contraction runs on the FP64 tensor cores (mma.sync m8n8k4); the DFMA register-tile instances of factored_body
+    // (template parameter MMA = false) were measured slower and are not built
+    if (shape.tn == 4) {          // twice the threads per tile (16 warps on an 80 x 128 tile)
         if (shape.bm == 128 && shape.bn == 128) return launch_variant<128, 128, 8, 4, 16, BATCH, true, false>(one, d_batch, grid, G, A, stream);
         if (shape.bm == 80 && shape.bn == 128) return launch_variant<80, 128, 5, 4, 16, BATCH, true, false>(one, d_batch, grid, G, A, stream);
         if (shape.bm == 80 && shape.bn == 64) return launch_variant<80, 64, 5, 4, 16, BATCH, true, false>(one, d_batch, grid, G, A, stream);
         if (shape.bm == 40 && shape.bn == 128) return launch_variant<40, 128, 5, 4, 16, BATCH, true, false>(one, d_batch, grid, G, A, stream);
         return launch_variant<40, 64, 5, 4, 16, BATCH, true, false>(one, d_batch, grid, G, A, stream);
     }
-    if (shape.mma) {              // FP64 tensor cores, every thread both producing and consuming
-        if (shape.bm == 80 && shape.bn == 128) return launch_variant<80, 128, 5, 8, 16, BATCH, true, false>(one, d_batch, grid, G, A, stream);
-        if (shape.bm == 80 && shape.bn == 64) return launch_variant<80, 64, 5, 8, 16, BATCH, true, false>(one, d_batch, grid, G, A, stream);
-        if (shape.bm == 40 && shape.bn == 128) return launch_variant<40, 128, 5, 8, 16, BATCH, true, false>(one, d_batch, grid, G, A, stream);
-        return launch_variant<40, 64, 5, 8, 16, BATCH, true, false>(one, d_batch, grid, G, A, stream);
-    }
-    if (shape.tn == 4) {          // twice the threads per tile: more warps to hide the gather phases
-        if (shape.bm == 80 && shape.bn == 128) return launch_variant<80, 128, 5, 4, 16, BATCH, false, false>(one, d_batch, grid, G, A, stream);
-        if (shape.bm == 80 && shape.bn == 64) return launch_variant<80, 64, 5, 4, 16, BATCH, false, false>(one, d_batch, grid, G, A, stream);
-        if (shape.bm == 40 && shape.bn == 128) return launch_variant<40, 128, 5, 4, 16, BATCH, false, false>(one, d_batch, grid, G, A, stream);
-        return launch_variant<40, 64, 5, 4, 16, BATCH, false, false>(one, d_batch, grid, G, A, stream);
-    }
-    if (shape.bm == 80 && shape.bn == 128) return launch_variant<80, 128, 5, 8, 16, BATCH, false, false>(one, d_batch, grid, G, A, stream);
-    if (shape.bm == 80 && shape.bn == 64) return launch_variant<80, 64, 5, 8, 16, BATCH, false, false>(one, d_batch, grid, G, A, stream);
-    if (shape.bm == 40 && shape.bn == 128) return launch_variant<40, 128, 5, 8, 16, BATCH, false, false>(one, d_batch, grid, G, A, stream);
-    return launch_variant<40, 64, 5, 8, 16, BATCH, false, false>(one, d_batch, grid, G, A, stream);
+    if (shape.bm == 80 && shape.bn == 128) return launch_variant<80, 128, 5, 8, 16, BATCH, true, false>(one, d_batch, grid, G, A, stream);
+    if (shape.bm == 80 && shape.bn == 64) return launch_variant<80, 64, 5, 8, 16, BATCH, true, false>(one, d_batch, grid, G, A, stream);
+    if (shape.bm == 40 && shape.bn == 128) return launch_variant<40, 128, 5, 8, 16, BATCH, true, false>(one, d_batch, grid, G, A, stream);
+    return launch_variant<40, 64, 5, 8, 16, BATCH, true, false>(one, d_batch, grid, G, A, stream);
 }
 
 }  // namespace
@@ -569,7 +558,7 @@ FactoredPlan plan_factored(const DevProblem& P)
 {
     FactoredPlan plan;
     // one column chunk when the grid allows it, because every
-    // chunk's CTA scans the whole y-side table (LDM_FACTORED_BM / LDM_FACTORED_BN override, for tuning)
+    // chunk's CTA scans the whole y-side table
     const int A = P.A;
     // Tile height: every beta tile regenerates E and re-scans the y-side table, a fixed cost of roughly 40 rows' worth of
     // contraction, so taller tiles win unless they pad too much (measured at G = 512, A = 243: 4 x 80 rows 2.9 ms,
@@ -577,33 +566,23 @@ FactoredPlan plan_factored(const DevProblem& P)
     plan.bm = A <= 40 ? 40 : 80;
     if (P.G > 64 && A > 80) {
         const int cost80 = ((A + 79) / 80) * (80 + 40), cost128 = ((A + 127) / 128) * (128 + 40);
-        if (cost128 < cost80 && std::getenv("LDM_FACTORED_NO_BM128") == nullptr) plan.bm = 128;
+        if (cost128 < cost80) plan.bm = 128;
     }
     plan.bn = P.G <= 64 ? 64 : 128;
-    if (const char* env = std::getenv("LDM_FACTORED_BN")) {
-        const int v = std::atoi(env);
-        if (v == 64 || v == 128) plan.bn = v;
-    }
-    if (const char* env = std::getenv("LDM_FACTORED_MMA")) plan.mma = std::atoi(env) != 0;
-    if (const char* env = std::getenv("LDM_FACTORED_W")) plan.use_w = std::atoi(env) != 0;
-    if (!plan.mma) plan.use_w = false;
     plan.tn = 4;       // 16 warps on an 80 x 128 tile: twice the table reads in flight in the y-side phase (12.4 k -> 8.9 k cycles)
-    if (const char* env = std::getenv("LDM_FACTORED_TN")) {
-        const int v = std::atoi(env);
-        if (v == 4 || v == 8) plan.tn = v;
-    }
-    if (const char* env = std::getenv("LDM_FACTORED_BM")) {
-        const int v = std::atoi(env);
-        if (v == 40 || v == 80 || (v == 128 && P.G > 64)) plan.bm = v;
-    }
-    if (plan.bm == 128) { plan.mma = true; plan.tn = 4; plan.use_w = false; plan.bn = 128; }   // the only 128-row kernel
+    // shape overrides of the tests (ldm_tuning_set)
+    const Tuning& t = tuning();
+    if (t.factored_bn == 64 || t.factored_bn == 128) plan.bn = t.factored_bn;
+    if (t.factored_tn == 4 || t.factored_tn == 8) plan.tn = t.factored_tn;
+    if (t.factored_bm == 40 || t.factored_bm == 80 || (t.factored_bm == 128 && P.G > 64)) plan.bm = t.factored_bm;
+    if (plan.bm == 128) { plan.tn = 4; plan.bn = 128; }   // the only 128-row kernel
     plan.tiles = (A + plan.bm - 1) / plan.bm;
     plan.chunks = (P.G + plan.bn - 1) / plan.bn;
     return plan;
 }
 
 #ifdef LDM_PHASE_CLOCKS
-extern "C" int ldm_debug_phase_clocks(long long* out, int rows)
+extern "C" LDM_API int ldm_debug_phase_clocks(long long* out, int rows)
 {
     cudaDeviceSynchronize();
     return (int)cudaMemcpyFromSymbol(out, g_phase_clock, sizeof(long long) * 12 * (size_t)rows);

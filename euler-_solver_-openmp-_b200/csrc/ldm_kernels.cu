@@ -323,16 +323,18 @@ finish_multi_kernel(const MultiArgs A)
         }
 }
 
-// One warp: lane r spins until rank r has published `epoch` (acquire, system scope).  A spin budget turns a lost peer
-// into an error status instead of a hung GPU.
+// One warp: lane r spins until rank r has published `epoch` (acquire, system scope).  A time budget (~9 s) turns a lost
+// peer into an error status instead of a hung GPU.
 __global__ void peer_wait_kernel(const unsigned long long* flags, int world, unsigned long long epoch, int* status)
 {
     const int r = threadIdx.x;
     if (r >= world) return;
     unsigned long long seen = 0;
-    for (long long spin = 0; spin < 40000000LL; spin++) {       // ~10-20 s
+    const long long t0 = clock64();
+    for (unsigned int polls = 1;; polls++) {
         asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flags + r) : "memory");
         if (seen >= epoch) return;
+        if ((polls & 0x3ffu) == 0 && clock64() - t0 > (1LL << 34)) break;
     }
     atomicExch(status, 1 + r);
 }

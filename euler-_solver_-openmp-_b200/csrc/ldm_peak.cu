@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(256) dfma_chain_kernel(double* sink, double a,
 
 }  // namespace
 
-extern "C" int ldm_measure_fp64_peak(int device, double* tflops, double* sm_clock_mhz_unused)
+extern "C" LDM_API int ldm_measure_fp64_peak(int device, double* tflops, double* sm_clock_mhz_unused)
 {
     (void)sm_clock_mhz_unused;
     if (!tflops) return LDM_ERR_ARGUMENT;
@@ -62,5 +62,99 @@ extern "C" int ldm_measure_fp64_peak(int device, double* tflops, double* sm_cloc
     cudaEventDestroy(e1);
     cudaFree(sink);
     *tflops = best;
+    return LDM_OK;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// The two resources that bound the prefix-sum path, measured the same way: the load/store data pipe of an
+// SM in wavefronts (one wavefront = up to 128 bytes of shared memory or L1 per clock) and the L2 -> SM read bandwidth.
+// ------------------------------------------------------------------------------------------------------------------
+namespace {
+
+constexpr int kLsuThreads = 1024;
+constexpr int kLsuInner = 256;
+
+// conflict-free 8-byte shared-memory loads: a warp instruction moves 256 bytes = 2 wavefronts; 8 independent loads in
+// flight per thread, addresses rotating through the tile so nothing is hoisted
+__global__ void __launch_bounds__(kLsuThreads) lsu_wavefront_kernel(double* sink, int outer)
+{
+    __shared__ double tile[kLsuThreads * 2];
+    for (int i = threadIdx.x; i < kLsuThreads * 2; i += kLsuThreads) tile[i] = (double)i;
+    __syncthreads();
+    double acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int at = threadIdx.x;
+    for (int o = 0; o < outer; o++) {
+        #pragma unroll 1
+        for (int i = 0; i < kLsuInner; i++) {
+            #pragma unroll
+            for (int r = 0; r < 8; r++) acc[r] += tile[(at + 32 * r) & (kLsuThreads * 2 - 1)];
+            at += 256;
+        }
+    }
+    double s = 0;
+    #pragma unroll
+    for (int r = 0; r < 8; r++) s += acc[r];
+    if (s == 12345.678) sink[0] = s;
+}
+
+// every SM streams the same L2-resident buffer with 16-byte loads that bypass L1 (ld.global.cg)
+__global__ void __launch_bounds__(512) l2_read_kernel(const double2* __restrict__ data, size_t n, int passes, double* sink)
+{
+    double acc = 0;
+    const size_t stride = (size_t)gridDim.x * blockDim.x;
+    for (int p = 0; p < passes; p++)
+        for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i + 3 * stride < n; i += 4 * stride) {
+            const double2 a = __ldcg(data + i), b = __ldcg(data + i + stride), c = __ldcg(data + i + 2 * stride), d = __ldcg(data + i + 3 * stride);
+            acc += (a.x + a.y) + (b.x + b.y) + (c.x + c.y) + (d.x + d.y);
+        }
+    if (acc == 12345.678) sink[0] = acc;
+}
+
+}  // namespace
+
+// wavefronts_per_s: load/store data-pipe wavefronts per second, whole device (shared-memory loads, every SM busy);
+// l2_gbs: L2 -> SM read bandwidth in GB/s over a 48 MiB buffer (resident in the 126 MB L2 after the first pass)
+extern "C" LDM_API int ldm_measure_memory_pipes(int device, double* wavefronts_per_s, double* l2_gbs)
+{
+    if (!wavefronts_per_s || !l2_gbs) return LDM_ERR_ARGUMENT;
+    if (cudaSetDevice(device) != cudaSuccess) return LDM_ERR_CUDA;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return LDM_ERR_CUDA;
+    const size_t n = (48u << 20) / sizeof(double2);
+    double* sink = nullptr;
+    double2* data = nullptr;
+    if (cudaMalloc(&sink, sizeof(double)) != cudaSuccess || cudaMalloc(&data, n * sizeof(double2)) != cudaSuccess) return LDM_ERR_CUDA;
+    cudaMemset(data, 0, n * sizeof(double2));
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    const int sms = prop.multiProcessorCount;
+    double best_wf = 0, best_l2 = 0;
+    for (int rep = 0; rep < 6; rep++) {
+        const int outer = 16;
+        cudaEventRecord(e0);
+        lsu_wavefront_kernel<<<sms, kLsuThreads>>>(sink, outer);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(sink); cudaFree(data); return LDM_ERR_CUDA; }
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double wavefronts = 2.0 * (double)sms * (kLsuThreads / 32) * 8.0 * kLsuInner * outer;
+        if (rep >= 2) best_wf = wavefronts / (ms * 1e-3) > best_wf ? wavefronts / (ms * 1e-3) : best_wf;
+        const int passes = 8;
+        cudaEventRecord(e0);
+        l2_read_kernel<<<sms * 4, 512>>>(data, n, passes, sink);
+        cudaEventRecord(e1);
+        if (cudaEventSynchronize(e1) != cudaSuccess) { cudaFree(sink); cudaFree(data); return LDM_ERR_CUDA; }
+        cudaEventElapsedTime(&ms, e0, e1);
+        const size_t per_pass = (n / ((size_t)sms * 4 * 512 * 4)) * ((size_t)sms * 4 * 512 * 4);
+        const double gbs = (double)per_pass * sizeof(double2) * passes / (ms * 1e-3) / 1e9;
+        if (rep >= 2) best_l2 = gbs > best_l2 ? gbs : best_l2;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(sink);
+    cudaFree(data);
+    *wavefronts_per_s = best_wf;
+    *l2_gbs = best_l2;
     return LDM_OK;
 }

@@ -1,0 +1,424 @@
+// Persistent multi-step kernels of the prefix-sum path for sm_100a: all Euler steps of a solve (EulerSolver::Solve,
+// Solver.cpp:557-592) inside ONE cooperative launch.
+//
+//   persistent_scan_kernel     grids whose rows are one chunk each (G <= 128), one rank: one CTA per moment-grid row, one
+//                              grid barrier per step, tables resident in shared memory across steps;
+//   persistent_chunks_kernel   everything else on the prefix-sum path -- rows of several chunks (G > 128) and the xi-sharded
+//                              step of SURVEY 8e on 1..8 ranks: one CTA per SM pulls (row, chunk) items from a list ordered by
+//                              cost, the CTA that completes a row closes it and stores it straight into every rank's next
+//                              replica over NVLink, and a step ends with per-rank epoch flags instead of a barrier.
+//
+// Both run scan_body (ldm_scan_body.cuh) unchanged and close a node with the arithmetic of finish_factored_kernel
+// (ldm_kernels.cu), so every path of a handle -- per-step launches, persistent, sharded -- produces the same bits.
+#include "../../include/ldm.h"
+#include "ldm_scan_body.cuh"
+
+namespace ldm {
+
+namespace {
+
+// Persistent multi-step kernel (cooperative launch, one CTA per moment-grid row): all Euler steps of a solve inside one
+// launch, for grids whose rows are one chunk each.  Per step every CTA
+//   1. sums the G row dots of the WC functional (written by the closing phases of the step before),
+//   2. computes its share of the sparse ring correction (dealt out evenly over all CTAs, counted per grid row), then runs
+//      scan_body for its row (per-node sums stay in shared memory),
+//   3. closes its own row -- closure, Euler update, clamp, history -- and forms its row dot of WC for the NEXT state,
+// and ONE grid barrier ends the step.  Tap tables and the y-side tables stay in shared memory across steps.
+template <bool SMALL, int U>
+__global__ void __launch_bounds__(SMALL ? 256 : kScanThreadsMax, 1)
+persistent_scan_kernel(const PersistentArgs A)
+{
+    const int NT = blockDim.x;
+    __shared__ double wc_shared;
+    StepArgs S = A.step;
+    const DevProblem& P = S.P;
+    const int G = P.G, tid = threadIdx.x, x = blockIdx.x;          // one rank, natural layout: row x = CTA x
+    const ScanLayout L = scan_layout(G, P.A, P.scan_bn, NT, P.scan_max_pieces);
+    extern __shared__ __align__(32) unsigned char scan_smem[];
+    double* row_sum = reinterpret_cast<double*>(scan_smem + L.rowsum);            // [G] after scan_body(fused)
+    int parity = A.parity;
+    unsigned int barrier_index = 0;
+
+    // prologue: the row dots of WC for the initial state
+    if (tid < 32) {
+        const double s = wc_row_dot(P.wc_operator + (size_t)x * G, A.C[parity] + (size_t)x * G, G, tid);
+        if (tid == 0) A.wc_rows[parity * G + x] = s;
+    }
+    if (!grid_barrier(A.barrier, barrier_index++, A.status)) return;
+
+    double* c_new = reinterpret_cast<double*>(scan_smem + L.rowbuf);              // [G] this row at the new time
+    double* op_row = c_new + L.part_stride;                                        // [G] this row of the WC functional
+    for (int y = tid; y < G; y += NT) op_row[y] = P.wc_operator[(size_t)x * G + y];
+    const int warp = tid >> 5, lane = tid & 31, last_warp = NT / 32 - 1;
+    const bool closer = tid < G;                                                   // thread y closes node (x, y); G <= bn <= NT
+    const int q = x * G + (closer ? tid : 0);
+    const bool has_ring = closer && P.ring_present[q] != 0;                       // node (x, y) owns ring samples
+    const double ow = P.out_weight[q], mn = P.m_nodes[q], wn = P.w_nodes[q];      // time-invariant: registers for the whole launch
+
+    // This CTA's share of the ring correction (the far rows of the grid own almost all ring entries -- row G-1 alone an
+    // eighth of them -- so the CSR rows are dealt out evenly by entry count over ALL CTAs, whichever grid row they belong
+    // to).  The share is time-invariant: its node indices and weights are copied to shared memory once, one CSR row per
+    // warp, so that a step costs ONE round trip to L2 (the gathers of C) instead of a chain of four.
+    constexpr int kRingPerLane = 8;
+    const int share_r0 = P.ring_cta_begin[x], share_r1 = P.ring_cta_begin[x + 1];
+    const int share_e0 = P.ring_begin[share_r0];
+    const bool ring_cached = A.ring_cache_offset >= 0;
+    int* rc_node = reinterpret_cast<int*>(scan_smem + (ring_cached ? A.ring_cache_offset : 0));
+    double* rc_weight = reinterpret_cast<double*>(rc_node + ((P.ring_share_entries + 1) & ~1));
+    const int my_row = share_r0 + warp;
+    int my_begin = 0, my_end = 0, my_point = 0;
+    if (ring_cached) {
+        for (int e = tid; e < P.ring_begin[share_r1] - share_e0; e += NT) { rc_node[e] = P.ring_node[share_e0 + e]; rc_weight[e] = P.ring_weight[share_e0 + e]; }
+        if (my_row < share_r1) { my_begin = P.ring_begin[my_row] - share_e0; my_end = P.ring_begin[my_row + 1] - share_e0; my_point = P.ring_point[my_row]; }
+        __syncthreads();
+    }
+
+    for (int k = 0; k < A.n_steps; k++) {
+        SCAN_MARK(10);
+        S.C = A.C[parity]; S.C_next = A.C[parity ^ 1];
+        S.N_cur = A.N + parity; S.N_next = A.N + (parity ^ 1);
+        const long long point = A.first_point + k;                 // index of the state this step starts from
+        if (x == 0 && tid == 0 && A.observables) {
+            A.observables[2 * point] = S.N_cur[0];                                  // Values[k][0]       (Solver.cpp:1011)
+            A.observables[2 * point + 1] = S.C[(size_t)0 * G + (G - 1)];            // Values[k][G]       (Solver.cpp:1014)
+        }
+        // The ring share.  Hand-over without fences or counters (a releasing reduction costs ~4 k cycles here): the values go
+        // to this step's half of a ping-pong buffer whose entries hold an all-ones NaN until they are written; the owner
+        // of a node polls its entry, takes the value and puts the NaN back for the step after next (two grid barriers lie
+        // between that store and the next write of the entry).  One 8-byte relaxed store, one 8-byte relaxed load.
+        double* ring_slot = A.ring_pingpong + (size_t)(k & 1) * G * G;
+        if (ring_cached) {
+            double cv[kRingPerLane];
+            #pragma unroll
+            for (int j = 0; j < kRingPerLane; j++) {                 // all gathers of the row in flight at once
+                const int e = my_begin + lane + 32 * j;
+                cv[j] = e < my_end ? S.C[rc_node[e]] : 0.0;
+            }
+            double acc = 0.0;
+            #pragma unroll
+            for (int j = 0; j < kRingPerLane; j++) {                 // the accumulation order of ring_row_dot / ring_kernel
+                const int e = my_begin + lane + 32 * j;
+                if (e < my_end) acc = fma(rc_weight[e], cv[j], acc);
+            }
+            acc = warp_sum(acc);
+            if (lane == 0 && my_row < share_r1) publish_ring(ring_slot + my_point, acc);
+        } else {
+            for (int row = share_r0 + warp; row < share_r1; row += NT / 32) {
+                const double acc = ring_row_dot(P, S.C, row, lane);
+                if (lane == 0) publish_ring(ring_slot + P.ring_point[row], acc);
+            }
+        }
+        SCAN_MARK(11);
+        // Everything the closing phase reads from global memory is requested between the two phases of scan_body and
+        // lands while the y side runs: the old C of this row, its ring correction (the owner first checks that all
+        // CSR rows of its grid row have been counted -- a whole E phase after they were dealt out, so no real wait),
+        // N, and the G row dots of the WC functional (written by the closing phases of the step before).
+        double c_old = 0.0, ring_v = 0.0, N = 0.0, wc_part[4] = {0.0, 0.0, 0.0, 0.0};
+        const double* wc_rows_now = A.wc_rows + parity * G;
+        auto mid = [&]() {
+            if (closer) {
+                if (has_ring) ring_v = take_ring(ring_slot + q, A.status);
+                c_old = S.C[q];
+            }
+            N = S.N_cur[0];
+            if (warp == last_warp) {
+                #pragma unroll
+                for (int j = 0; j < 4; j++) wc_part[j] = lane + 32 * j < G ? wc_rows_now[lane + 32 * j] : 0.0;
+            }
+        };
+        scan_body_of<SMALL, U>(S, 0, x, k == 0, A.cached_w_rows, true, mid);   // ends with a CTA barrier
+        SCAN_MARK(6);
+        if (warp == last_warp) {                                   // wc_total(): the same order, from the registers
+            double t = 0.0;
+            #pragma unroll
+            for (int j = 0; j < 4; j++) if (lane + 32 * j < G) t += wc_part[j];
+            t = warp_sum(t);
+            if (lane == 0) wc_shared = t;
+        }
+        __syncthreads();
+        const double WC = __dmul_rn(add_outside(P, wc_shared, N, S.C, S.scalars, P.wc_outside, 0.0), P.hh);   // Solver.cpp:311, 314
+        double* values_next = A.values ? A.values + (point + 1) * A.stride : nullptr;
+        double* derivs_here = A.derivs ? A.derivs + point * A.stride : nullptr;
+        if (x == 0 && tid == 0) {
+            first_moment_update(P, N, WC, S.dt, S.scalars, S.N_next);
+            if (values_next) values_next[0] = S.N_next[0];
+            if (derivs_here) derivs_here[0] = S.scalars[1];
+        }
+        if (closer) {
+            const double inside = (0.0 + row_sum[tid]) - ring_v;
+            const double mc = __dmul_rn(add_outside(P, inside, N, S.C, S.scalars, ow, 0.0), P.hh);
+            const double dc = second_moment_rhs(P, mc, c_old, N, WC, mn, wn);
+            double v = __dadd_rn(c_old, __dmul_rn(dc, S.dt));                      // Solver.cpp:577
+            v = v < 0.0 ? 0.0 : v;                                                 // Solver.cpp:578-580
+            S.C_next[q] = v;
+            c_new[tid] = v;
+            if (values_next) values_next[1 + q] = v;
+            if (derivs_here) derivs_here[1 + q] = dc;
+        }
+        __syncthreads();
+        if (warp == 0) {     // this row's dot of the WC functional for the next state
+            const double s = wc_row_dot(op_row, c_new, G, lane);
+            if (lane == 0) A.wc_rows[(parity ^ 1) * G + x] = s;
+        }
+        SCAN_MARK(8);
+        if (!grid_barrier(A.barrier, barrier_index++, A.status)) return;     // a lost partner: stop stepping (the host reports the status word)
+        SCAN_MARK(9);
+        parity ^= 1;
+    }
+}
+
+// Spin until every rank has published `need` steps in this rank's flag array (lane r of one warp polls rank r; the
+// flags are written by the peers over NVLink with a system-scope release).  Relaxed polls of local memory, then one
+// system-scope acquire per lane; the CTA barrier that follows hands the ordering on to the other threads.
+__device__ __forceinline__ bool wait_for_ranks(const unsigned long long* flags, int world, unsigned long long need, int* status)
+{
+    const int r = threadIdx.x;
+    bool ok = true;
+    if (r < world) {
+        unsigned long long seen;
+        Spin spin;
+        for (;;) {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flags + r) : "memory");
+            if (seen >= need) break;
+            if (spin.give_up(status)) { atomicCAS(status, kStatusOk, kStatusPeerTimeout); ok = false; break; }
+        }
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flags + r) : "memory");
+    }
+    return ok;
+}
+
+// Persistent work-list kernel (cooperative launch, one CTA per SM or fewer): see ChunkedArgs in ldm_device.h.
+// Per step every CTA
+//   1. waits until every rank has published the previous step (own flag array, local polls),
+//   2. computes its share of the sparse ring correction of this rank's rows (CSR rows dealt out by entry count) and hands
+//      the values over without fences (ping-pong slots holding an all-ones NaN until written, as in persistent_scan_kernel),
+//   3. pulls (local row, chunk) items off a list ordered by cost -- one atomic per item, fetched under the item before --
+//      and runs scan_body on each; the chunk sums go to global memory, the row's arrival counter is bumped, and the CTA
+//      that brings the last chunk of a row CLOSES it: chunk sums added in chunk order, ring correction, closure, Euler
+//      update, clamp -- the arithmetic of finish_factored_kernel -- then the new row and its dot with the WC functional
+//      are stored into the next replica of every rank (peer stores over NVLink: the all-gather of SURVEY 8e, row by row,
+//      while the other rows are still being computed), one system fence per closing CTA,
+//   4. and whoever closes the rank's last row publishes the step in every rank's flag array.
+// No barrier anywhere but in the prologue: the flags of step k order everything of step k before anything of step k + 1.
+template <bool SMALL, int U>
+__global__ void __launch_bounds__(SMALL ? 256 : kScanThreadsMax, SMALL ? 4 : 1)
+persistent_chunks_kernel(const ChunkedArgs A)
+{
+    const int NT = blockDim.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, warps = NT / 32;
+    __shared__ double wc_shared;
+    __shared__ unsigned int next_item[2];
+    __shared__ int closes_row, step_ok;
+    StepArgs S = A.step;
+    const DevProblem& P = S.P;
+    const int G = P.G, n_local = local_rows(P), chunks = P.scan_chunks, n = n_local * G;
+    const ScanLayout L = scan_layout(G, P.A, P.scan_bn, NT, P.scan_max_pieces);
+    extern __shared__ __align__(32) unsigned char scan_smem[];
+    double* c_new = reinterpret_cast<double*>(scan_smem + L.rowbuf);              // [G] the row being closed, at the new time
+    unsigned int* fetch_counter = A.counters;
+    unsigned int* rows_closed = A.counters + 1;
+    unsigned int* row_arrivals = A.counters + 3;
+    const unsigned long long* own_flags = A.flags[A.rank];
+    int parity = A.parity;
+
+    // prologue: the state this launch starts from must be complete in this rank's replica; then the row dots of the WC
+    // functional for it, all G rows on every rank (no exchange), dealt out over the warps of the grid
+    if (tid < 32) {
+        const bool ok = wait_for_ranks(own_flags, A.world, A.epoch, A.status);
+        if (__any_sync(0xffffffffu, !ok) && tid == 0) atomicCAS(A.status, kStatusOk, kStatusPeerTimeout);
+    }
+    __syncthreads();
+    {
+        const double* C0 = A.replica[parity][A.rank];
+        double* tail = A.replica[parity][A.rank] + A.words;
+        for (int xr = blockIdx.x * warps + warp; xr < G; xr += gridDim.x * warps) {
+            const double s = wc_row_dot(P.wc_operator + (size_t)xr * G, C0 + (size_t)row_slot(P, xr) * G, G, lane);
+            if (lane == 0) tail[xr] = s;
+        }
+    }
+    if (tid == 0) next_item[0] = atomicAdd(fetch_counter, 1u);                     // this CTA's first item
+    if (!grid_barrier(A.counters + 2, 0, A.status)) return;
+    unsigned int item = next_item[0];
+    unsigned int turn = 0;                                                         // items this CTA has taken so far
+
+    for (int k = 0; k < A.n_steps; k++) {
+        SCAN_MARK(10);
+        const unsigned long long done = A.epoch + (unsigned long long)k;           // steps every rank must have published
+        if (tid < 32) {
+            const bool ok = wait_for_ranks(own_flags, A.world, done, A.status);
+            const bool all = !__any_sync(0xffffffffu, !ok);
+            if (tid == 0) step_ok = all && load_status(A.status) == kStatusOk;
+        }
+        __syncthreads();
+        if (!step_ok) return;                                                      // a lost partner: the host reports the status word
+        double* const C_cur = A.replica[parity][A.rank];
+        S.C = C_cur;
+        S.N_cur = A.N + parity;
+        S.N_next = A.N + (parity ^ 1);
+        const double* wc_tail = C_cur + A.words;
+        const long long point = A.first_point + k;
+        if (blockIdx.x == 0 && tid == 0 && A.observables) {
+            A.observables[2 * point] = S.N_cur[0];                                  // Values[k][0]       (Solver.cpp:1011)
+            A.observables[2 * point + 1] = C_cur[G - 1];                            // Values[k][G]       (Solver.cpp:1014); row 0 is slot 0
+        }
+        double* values_next = A.values ? A.values + (point + 1) * A.stride : nullptr;
+        double* derivs_here = A.derivs ? A.derivs + point * A.stride : nullptr;
+
+        // the ring share of this CTA
+        double* ring_slot = A.ring_pingpong + (size_t)(k & 1) * n;
+        for (int row = A.ring_cta_begin[blockIdx.x] + warp; row < A.ring_cta_begin[blockIdx.x + 1]; row += warps) {
+            const double acc = ring_row_dot(P, C_cur, row, lane);
+            if (lane == 0) publish_ring(ring_slot + P.ring_point[row], acc);
+        }
+        SCAN_MARK(11);
+
+        const unsigned int step_end = (unsigned int)(k + 1) * (unsigned int)A.n_items;
+        while (item < step_end) {
+            const int2 it = A.items[item - (unsigned int)k * (unsigned int)A.n_items];   // (local row, chunk)
+            const int lx = it.x;
+            if (tid == 0) next_item[(turn + 1) & 1] = atomicAdd(fetch_counter, 1u);  // the next item, fetched under this one's work
+            scan_body_of<SMALL, U>(S, it.y, lx, true, -1);                           // chunk sums -> S.partial; ends with a CTA barrier
+            if (tid == 0) {
+                __threadfence();                                                     // the CTA's chunk sums, before the arrival
+                const unsigned int arrived = atomicAdd(row_arrivals + lx, 1u) + 1u;
+                __threadfence();                                                     // the other chunks' sums, after it
+                closes_row = arrived == (unsigned int)(k + 1) * (unsigned int)chunks;
+            }
+            __syncthreads();
+            turn++;
+            item = next_item[turn & 1];
+            if (!closes_row) continue;
+
+            // ---- close local row lx: everything finish_factored_kernel does for it, same arithmetic ----
+            const int x = P.rank + P.world * lx;
+            if (warp == 0) {
+                const double t = wc_total(wc_tail, G, lane);
+                if (lane == 0) wc_shared = t;
+            }
+            __syncthreads();
+            const double N = S.N_cur[0];
+            const double WC = __dmul_rn(add_outside(P, wc_shared, N, C_cur, S.scalars, P.wc_outside, 0.0), P.hh);   // Solver.cpp:311, 314
+            if (lx == 0 && tid == 0) {
+                first_moment_update(P, N, WC, S.dt, S.scalars, S.N_next);
+                if (values_next) values_next[0] = S.N_next[0];
+                if (derivs_here) derivs_here[0] = S.scalars[1];
+            }
+            for (int y = tid; y < G; y += NT) {
+                const int ql = lx * G + y;
+                const int q = x * G + y;
+                double inside = 0.0;
+                for (int t = 0; t < chunks; t++) inside += __ldcg(S.partial + (size_t)t * n + ql);
+                const double ring_v = P.ring_present[ql] != 0 ? take_ring(ring_slot + ql, A.status) : 0.0;
+                inside -= ring_v;
+                const size_t slot = (size_t)(P.rank * P.rows_per_rank + lx) * G + y;   // this node in the gathered layout
+                const double c = C_cur[slot];
+                const double mc = __dmul_rn(add_outside(P, inside, N, C_cur, S.scalars, P.out_weight[q], 0.0), P.hh);
+                const double dc = second_moment_rhs(P, mc, c, N, WC, P.m_nodes[q], P.w_nodes[q]);
+                double v = __dadd_rn(c, __dmul_rn(dc, S.dt));                       // Solver.cpp:577
+                v = v < 0.0 ? 0.0 : v;                                              // Solver.cpp:578-580
+                for (int r = 0; r < A.world; r++) A.replica[parity ^ 1][r][slot] = v;   // the all-gather: NVLink peer stores
+                c_new[y] = v;
+                if (values_next) values_next[1 + q] = v;
+                if (derivs_here) derivs_here[1 + q] = dc;
+            }
+            __syncthreads();
+            if (warp == 0) {     // this row's dot with the WC functional for the next state, to every rank's tail
+                const double s = wc_row_dot(P.wc_operator + (size_t)x * G, c_new, G, lane);
+                if (lane == 0) {
+                    for (int r = 0; r < A.world; r++) A.replica[parity ^ 1][r][A.words + x] = s;
+                }
+            }
+            __syncthreads();
+            if (tid == 0) {
+                // release: ONE system fence per closing CTA, behind the CTA barrier (cumulative over what the barrier ordered
+                // before it); the CTA that closes the rank's last row publishes the step in every rank's flag array
+                __threadfence_system();
+                const unsigned int closed = atomicAdd(rows_closed, 1u) + 1u;
+                if (closed == (unsigned int)(k + 1) * (unsigned int)n_local) {
+                    __threadfence_system();
+                    for (int r = 0; r < A.world; r++)
+                        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.flags[r] + A.rank), "l"(done + 1ULL) : "memory");
+                }
+            }
+        }
+        SCAN_MARK(8);
+        __syncthreads();           // step_ok is rewritten at the top of the next step
+        parity ^= 1;
+    }
+}
+
+}  // namespace
+
+cudaError_t launch_persistent_scan(const PersistentArgs& args, int grid, cudaStream_t stream, int* max_grid)
+{
+    const DevProblem& P = args.step.P;
+    const int G = P.G, n_off = P.n_off, nt = P.scan_nt;
+    const void* kernel = nt <= 256 ? (const void*)persistent_scan_kernel<true, 0>
+                       : scan_unroll_of(P) == 5 ? (const void*)persistent_scan_kernel<false, 5> : (const void*)persistent_scan_kernel<false, 4>;
+    // shared memory: the step's working set, then the 16-bit y-side index table, then as many weight rows as still fit
+    const size_t base = scan_smem_bytes(G, P.A, P.scan_bn, nt, P.scan_max_pieces);
+    const size_t u_bytes = align32(sizeof(unsigned short) * (size_t)n_off * G);
+    PersistentArgs with_cache = args;
+    with_cache.cached_w_rows = -1;
+    with_cache.ring_cache_offset = -1;
+    // the CTA's ring share (one CSR row per warp, at most 8 entries per lane): 4-byte node indices, then 8-byte weights
+    size_t ring_bytes = 0;
+    if (P.ring_share_rows <= nt / 32 && P.ring_share_row_len <= 32 * 8)
+        ring_bytes = align32(sizeof(int) * (size_t)((P.ring_share_entries + 1) & ~1) + sizeof(double) * (size_t)P.ring_share_entries + 8);
+    size_t smem = base;
+    if (base + ring_bytes <= kSmemBudget && ring_bytes > 0) {
+        with_cache.ring_cache_offset = (long long)base;
+        smem = base + ring_bytes;
+    } else {
+        ring_bytes = 0;
+    }
+    if (base + ring_bytes + u_bytes <= kSmemBudget) {
+        const int rows = (int)std::min<size_t>((size_t)n_off, (kSmemBudget - base - ring_bytes - u_bytes) / ((size_t)G * sizeof(double)));
+        with_cache.cached_w_rows = rows;
+        with_cache.ring_cache_offset = ring_bytes > 0 ? (long long)(base + u_bytes + (size_t)rows * G * sizeof(double)) : -1;
+        smem = base + ring_bytes + u_bytes + (size_t)rows * G * sizeof(double);
+    }
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+    if (e != cudaSuccess) return e;
+    int device = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem);
+    if (e != cudaSuccess) return e;
+    if (max_grid) *max_grid = sms * per_sm;
+    if (grid <= 0) return cudaSuccess;                  // query only
+    if (grid > sms * per_sm) return cudaErrorCooperativeLaunchTooLarge;
+    void* params[] = {&with_cache};
+    return cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(nt), params, smem, stream);
+}
+
+cudaError_t launch_persistent_chunks(const ChunkedArgs& args, int grid, cudaStream_t stream, int* max_grid)
+{
+    const DevProblem& P = args.step.P;
+    const int nt = P.scan_nt;
+    const void* kernel = nt <= 256 ? (const void*)persistent_chunks_kernel<true, 0>
+                       : scan_unroll_of(P) == 5 ? (const void*)persistent_chunks_kernel<false, 5> : (const void*)persistent_chunks_kernel<false, 4>;
+    const size_t smem = scan_smem_bytes(P.G, P.A, P.scan_bn, nt, P.scan_max_pieces);
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+    if (e != cudaSuccess) return e;
+    int device = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem);
+    if (e != cudaSuccess) return e;
+    if (max_grid) *max_grid = sms * per_sm;
+    if (grid <= 0) return cudaSuccess;                  // query only
+    if (grid > sms * per_sm) return cudaErrorCooperativeLaunchTooLarge;
+    ChunkedArgs a = args;
+    void* params[] = {&a};
+    return cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(nt), params, smem, stream);
+}
+
+#ifdef LDM_PHASE_CLOCKS
+extern "C" LDM_API int ldm_debug_persist_clocks(long long* out, int rows)
+{
+    cudaDeviceSynchronize();
+    return (int)cudaMemcpyFromSymbol(out, g_scan_clock, sizeof(long long) * 12 * (size_t)rows);
+}
+#endif
+
+}  // namespace ldm

@@ -15,6 +15,13 @@
 extern "C" {
 #endif
 
+/* the library is built with -fvisibility=hidden: only what this header declares is exported */
+#if defined(__GNUC__)
+#define LDM_API __attribute__((visibility("default")))
+#else
+#define LDM_API
+#endif
+
 #define LDM_OK              0
 #define LDM_ERR_ARGUMENT   -1   /* the reference would assert (S:260, S:327, ...) */
 #define LDM_ERR_CUDA       -2   /* no device / CUDA runtime failure */
@@ -66,29 +73,29 @@ typedef struct ldm_context* ldm_handle;
 /* ---- model setup: replaces Properties::Generate / GenerateGrids / GenerateKernel (S:63-241), host only ----
  * forced_G > 0 pins the moment-grid node count (the synthetic grids of BASELINE.json); <= 0 = the
  * reference's search (S:68-74).  The returned problem owns its arrays; free with ldm_problem_free. */
-int  ldm_problem_generate(double sigma_w, double sigma_m, double b, double d, double d_prime,
+LDM_API int  ldm_problem_generate(double sigma_w, double sigma_m, double b, double d, double d_prime,
                           int forced_G, ldm_problem** out);
-void ldm_problem_free(ldm_problem* p);
+LDM_API void ldm_problem_free(ldm_problem* p);
 /* The same for several species (S:186-241 with num > 1; the reference ships such inputs as "(UNSUPPORTED)" examples, but
  * its Equation handles them, S:454-511).  sigma_w, d_prime: species*species row-major; sigma_m, b, d: species.  Grids
  * come from the largest sigmas (S:203).  State vectors are [N_0..N_{s-1} | C_00 | C_01 | ... | C_{s-1,s-1}], each C_ij
  * G*G row-major (S:255-262, T:740-806).  A handle on such a problem supports ldm_rhs, ldm_solve (LDM_RECORD_LAST /
  * VALUES / ALL), ldm_set_algorithm and ldm_set_extrapolation; the other entry points return LDM_ERR_UNSUPPORTED. */
-int  ldm_problem_generate_multi(int species, const double* sigma_w, const double* sigma_m, const double* b, const double* d,
+LDM_API int  ldm_problem_generate_multi(int species, const double* sigma_w, const double* sigma_m, const double* b, const double* d,
                                 const double* d_prime, int forced_G, ldm_problem** out);
 /* Properties::CheckKernels (S:147-183): the two midpoint-rule integrals (each must be 1 +- 1e-8) */
-int  ldm_problem_check_kernels(const ldm_problem* p, double* integral_w, double* integral_m);
+LDM_API int  ldm_problem_check_kernels(const ldm_problem* p, double* integral_w, double* integral_m);
 
 /* Structure of the m table that LDM_ALGO_PREFIX needs (host only): separable inside its disc, i.e.
  * M[2b+1][2a+1] = q[b] q[a] on a staircase region and 0 beyond, as every table of GenerateKernel (S:113-123) is.
  * *separable = 1/0; *max_rel_dev = largest |M - q q^T| / (q q^T) over the non-zero quadrature entries. */
-int  ldm_problem_kernel_structure(const ldm_problem* p, int* separable, double* max_rel_dev);
+LDM_API int  ldm_problem_kernel_structure(const ldm_problem* p, int* separable, double* max_rel_dev);
 
 /* ---- Equation(Properties) (S:413): upload tables, build the time-invariant index/weight tables ---- */
-int  ldm_create(const ldm_problem* p, int device, ldm_handle* out);
-void ldm_destroy(ldm_handle h);
-int  ldm_set_algorithm(ldm_handle h, int algo);
-int  ldm_get_algorithm(ldm_handle h);                                /* the algorithm in force (never LDM_ALGO_AUTO) */
+LDM_API int  ldm_create(const ldm_problem* p, int device, ldm_handle* out);
+LDM_API void ldm_destroy(ldm_handle h);
+LDM_API int  ldm_set_algorithm(ldm_handle h, int algo);
+LDM_API int  ldm_get_algorithm(ldm_handle h);                                /* the algorithm in force (never LDM_ALGO_AUTO) */
 
 /* ExtrapolationType (S:28) that Equation::operator() and the solvers are called with: what the pair density is taken
  * to be beyond the cutoff (S:355-389).  Every experiment of the reference passes SquaredN (the default).  Zero and
@@ -100,14 +107,14 @@ int  ldm_get_algorithm(ldm_handle h);                                /* the algo
 #define LDM_EXTRAPOLATION_SQUARED_N   1
 #define LDM_EXTRAPOLATION_ALPHA       2
 #define LDM_EXTRAPOLATION_EXPONENTIAL 3
-int  ldm_set_extrapolation(ldm_handle h, int type);
+LDM_API int  ldm_set_extrapolation(ldm_handle h, int type);
 
 /* ---- Equation::operator()(t, vals, type) (S:431-513): host state in, host derivative out ---- */
-int  ldm_rhs(ldm_handle h, const double* state, double* deriv);
+LDM_API int  ldm_rhs(ldm_handle h, const double* state, double* deriv);
 /* the two integrals on their own (S:265-295): WC scalar, MC G*G (MC may be NULL) */
-int  ldm_integrals(ldm_handle h, const double* state, double* WC, double* MC);
+LDM_API int  ldm_integrals(ldm_handle h, const double* state, double* WC, double* MC);
 /* the time-invariant kernel look-ups of S:469-476 / S:490-497 at the moment nodes (G*G each) */
-int  ldm_kernels_at_nodes(ldm_handle h, double* m_at_nodes, double* w_at_nodes);
+LDM_API int  ldm_kernels_at_nodes(ldm_handle h, double* m_at_nodes, double* w_at_nodes);
 
 /* ---- EulerSolver::Solve (S:557-592) ----
  * ldm_count_points reproduces `time += step; while (time < time_max)` (S:574-589).
@@ -115,34 +122,34 @@ int  ldm_kernels_at_nodes(ldm_handle h, double* m_at_nodes, double* w_at_nodes);
  *   LAST: values = 1+G*G (derivs, if non-NULL, = derivative at the last point);
  *   OBSERVABLES: values = n_points*2; VALUES: values = n_points*(1+G*G); ALL: derivs likewise.
  * Host buffers; the copies in and out are part of the call. */
-int  ldm_count_points(double t_max, double dt);
-int  ldm_solve(ldm_handle h, const double* init, double dt, double t_max, int record,
+LDM_API int  ldm_count_points(double t_max, double dt);
+LDM_API int  ldm_solve(ldm_handle h, const double* init, double dt, double t_max, int record,
                double* times, double* values, double* derivs, int* n_points);
 
 /* ---- RungeKutta4thSolver::Solve (S:597-654; present in the reference, instantiated by none of its experiments) on
  * the same right-hand-side kernels.  ldm_count_points_rk4 reproduces its `while (time < time_max)` with two half
  * steps of the clock per iteration (S:627-635).  Full history: times n_points, values and derivs (either may be NULL)
  * n_points*(1+G*G).  Intermediate stages are not clamped, the closed step is (S:643-645). ---- */
-int  ldm_count_points_rk4(double t_max, double dt);
-int  ldm_solve_rk4(ldm_handle h, const double* init, double dt, double t_max, double* times, double* values, double* derivs,
+LDM_API int  ldm_count_points_rk4(double t_max, double dt);
+LDM_API int  ldm_solve_rk4(ldm_handle h, const double* init, double dt, double t_max, double* times, double* values, double* derivs,
                    int* n_points);
 
 /* ---- device-resident stepping (state stays in HBM between calls) ---- */
-int  ldm_state_upload(ldm_handle h, const double* state);          /* 1+G*G doubles */
-int  ldm_state_download(ldm_handle h, double* state);
-int  ldm_advance(ldm_handle h, int n_steps, double dt);            /* n Euler steps, asynchronous */
-int  ldm_synchronize(ldm_handle h);
+LDM_API int  ldm_state_upload(ldm_handle h, const double* state);          /* 1+G*G doubles */
+LDM_API int  ldm_state_download(ldm_handle h, double* state);
+LDM_API int  ldm_advance(ldm_handle h, int n_steps, double dt);            /* n Euler steps, asynchronous */
+LDM_API int  ldm_synchronize(ldm_handle h);
 /* device time of the last ldm_advance / ldm_solve stepping loop in ms (CUDA events on the stream) */
-int  ldm_last_elapsed_ms(ldm_handle h, float* ms);
+LDM_API int  ldm_last_elapsed_ms(ldm_handle h, float* ms);
 /* number of kernels launched by this handle since creation */
-long long ldm_launch_count(ldm_handle h);
+LDM_API long long ldm_launch_count(ldm_handle h);
 
 /* ---- the sigma-sweep loop Experiments::CalculateWithVaryingSigma (S:940-963): n independent solves,
  * results slot-indexed (no shared push_back).  last_states[i] receives 1+G_i*G_i doubles.  The handles may live on
  * several devices (ldm_create's device argument): every device advances its slice of the batch concurrently, one
  * launch per kernel and step for all of its sets; ldm_device_count() = visible devices (0 without CUDA). ---- */
-int  ldm_device_count(void);
-int  ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits, double dt, double t_max,
+LDM_API int  ldm_device_count(void);
+LDM_API int  ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits, double dt, double t_max,
                      double* const* last_states);
 
 /* ---- xi-sharded stepping for one large problem: this rank owns moment-grid rows
@@ -152,11 +159,11 @@ int  ldm_solve_batch(int n, const ldm_handle* handles, const double* const* init
  * ldm_shard_step: d_C_gathered (device) is the full C in gathered layout at the old time; on return
  * (stream-ordered) d_C_shard_out (device, rows_per_rank*G) holds this rank's new rows and the handle's N is
  * advanced (every rank recomputes N redundantly, so no all-reduce is needed). */
-int  ldm_shard_configure(ldm_handle h, int rank, int world);
-int  ldm_shard_rows_per_rank(ldm_handle h);
-int  ldm_shard_step(ldm_handle h, const double* d_C_gathered, double* d_C_shard_out, double dt, void* cuda_stream);
-int  ldm_shard_set_N(ldm_handle h, double N);
-int  ldm_shard_get_N(ldm_handle h, double* N);
+LDM_API int  ldm_shard_configure(ldm_handle h, int rank, int world);
+LDM_API int  ldm_shard_rows_per_rank(ldm_handle h);
+LDM_API int  ldm_shard_step(ldm_handle h, const double* d_C_gathered, double* d_C_shard_out, double dt, void* cuda_stream);
+LDM_API int  ldm_shard_set_N(ldm_handle h, double N);
+LDM_API int  ldm_shard_get_N(ldm_handle h, double* N);
 
 /* ---- xi-sharded stepping with the all-gather fused into the update (NVLink peer stores, no NCCL on the data path).
  * One process per GPU.  ldm_shard_peer_alloc: after ldm_shard_configure; allocates this rank's two replicas of C
@@ -167,18 +174,37 @@ int  ldm_shard_get_N(ldm_handle h, double* N);
  * previous step, updates this rank's rows and stores them into EVERY rank's next replica, publishes the step.
  * ldm_shard_peer_download: this rank's current replica.  Returns LDM_ERR_CUDA if a peer never showed up. ---- */
 #define LDM_IPC_HANDLE_BYTES 64
-int  ldm_shard_peer_alloc(ldm_handle h, unsigned char* handles /* 3 * LDM_IPC_HANDLE_BYTES */);
-int  ldm_shard_peer_connect(ldm_handle h, const unsigned char* all_handles /* world * 3 * LDM_IPC_HANDLE_BYTES, rank-major */);
-int  ldm_shard_peer_upload(ldm_handle h, const double* C_gathered, double N);
-int  ldm_shard_peer_step(ldm_handle h, double dt, void* cuda_stream);
-int  ldm_shard_peer_download(ldm_handle h, double* C_gathered, double* N);
+LDM_API int  ldm_shard_peer_alloc(ldm_handle h, unsigned char* handles /* 3 * LDM_IPC_HANDLE_BYTES */);
+LDM_API int  ldm_shard_peer_connect(ldm_handle h, const unsigned char* all_handles /* world * 3 * LDM_IPC_HANDLE_BYTES, rank-major */);
+LDM_API int  ldm_shard_peer_upload(ldm_handle h, const double* C_gathered, double N);
+LDM_API int  ldm_shard_peer_step(ldm_handle h, double dt, void* cuda_stream);          /* = ldm_shard_peer_advance(h, 1, ...) */
+/* n_steps Euler steps, asynchronous on cuda_stream.  On the prefix-sum path all of them run inside ONE launch per rank
+ * (a persistent kernel: rows are stored into every rank's next replica as they close, a step ends with per-rank epoch
+ * flags instead of a barrier); every rank must make the same call.  A rank that never shows up turns into LDM_ERR_CUDA
+ * at the next ldm_shard_peer_download / ldm_synchronize (bounded waits on the device, ~9 s), not into a hang. */
+LDM_API int  ldm_shard_peer_advance(ldm_handle h, int n_steps, double dt, void* cuda_stream);
+/* The same peer group inside ONE process that drives several devices (or, for tests, several ranks on one device):
+ * handles[r] is configured as rank r of `world`; allocates the replicas and wires them up through peer access --
+ * replaces ldm_shard_peer_alloc + the exchange of IPC handles + ldm_shard_peer_connect. */
+LDM_API int  ldm_shard_peer_connect_local(int world, const ldm_handle* handles);
+LDM_API int  ldm_shard_peer_download(ldm_handle h, double* C_gathered, double* N);
+
+/* ---- test hook: forces shapes the library would otherwise choose itself, so that tests reach the chunked and tiled code
+ * paths on small grids.  Read when a handle is created.  Keys: "scan_bn", "scan_nt" (prefix-sum path: chunk width, threads),
+ * "factored_bm", "factored_bn", "factored_tn" (dense contraction tiles), "persistent" (0: one launch per kernel and
+ * step), "scan" (0: never the prefix-sum path), "chunk_grid" (CTAs of the persistent work-list kernel), "reset". ---- */
+LDM_API int  ldm_tuning_set(const char* name, int value);
 
 /* ---- measurement support: FP64 (DFMA) peak of `device` in TFLOP/s, measured live by a register-resident
  * FMA chain; MEASURED_PEAKS.json has no FP64 figure, this is the roofline denominator bench.py reports. ---- */
-int  ldm_measure_fp64_peak(int device, double* tflops, double* reserved);
+LDM_API int  ldm_measure_fp64_peak(int device, double* tflops, double* reserved);
+/* the two resources that bound the prefix-sum path instead, measured live: the load/store data pipe in
+ * wavefronts per second over the whole device (conflict-free shared-memory loads; one wavefront = up to 128 bytes per
+ * clock and SM), and the L2 -> SM read bandwidth in GB/s (16-byte loads bypassing L1 over an L2-resident buffer) */
+LDM_API int  ldm_measure_memory_pipes(int device, double* wavefronts_per_s, double* l2_gbs);
 
-const char* ldm_last_error(void);
-const char* ldm_version(void);
+LDM_API const char* ldm_last_error(void);
+LDM_API const char* ldm_version(void);
 
 #ifdef __cplusplus
 }

@@ -208,6 +208,26 @@ void ref_integrals(void* handle, const double* state, double* WC, double* MC)
     }
 }
 
+// A bounded sample of the hot loop (Solver.cpp:277-295): the reference's own per-node integral
+// MakeIntegralWithPairDensity (Solver.cpp:297-316) at the nodes of the rows first, first + stride, ... -- what
+// CalculateIntegralOfMAndC does for them, nothing else.  out: one row of G values per sampled row.  Returns the row count.
+// (bench.py's reference arm: a full right-hand side on the synthetic grids takes tens of seconds.)
+int ref_mc_rows(void* handle, const double* state, int first, int stride, double* out)
+{
+    Properties& p = static_cast<RefHandle*>(handle)->props;
+    const int G = p.MomentsGrid.size();
+    Equation equation(p);
+    equation.C_extrapolation_type = g_type;
+    Matrix c(G);
+    for (int x = 0; x < G; x++)
+        for (int y = 0; y < G; y++) c[x][y] = state[1 + (size_t)x * G + y];
+    int rows = 0;
+    for (int x = first; x < G; x += stride, rows++)
+        for (int y = 0; y < G; y++)
+            out[(size_t)rows * G + y] = equation.MakeIntegralWithPairDensity(x, y, p.MaxNumForM[0], p.M(0), c, state[0] * state[0]);
+    return rows;
+}
+
 // The time-invariant kernel look-ups at the moment nodes (Solver.cpp:469-476, 490-497): G*G each.
 void ref_kernels_at_nodes(void* handle, double* m_at_nodes, double* w_at_nodes)
 {

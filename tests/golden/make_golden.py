@@ -96,6 +96,66 @@ def job_14_6(args):
     return f"14.6{which}[{i}]: sigma={sig!r} G={p.G} K={p.K} mM={p.mM} mW={p.mW} N_end={values[-1, 0]!r}"
 
 
+def job_sweep_entry(args):
+    """One entry of Experiment_14_6 (S:1033-1071) through the by-reference build: what the experiment plots for it --
+    the last state's N and C[0][G-1] (S:1050-1055) -- plus the grid sizes and the sum of the last state."""
+    which, i = args
+    sig = sigma_vec()[i]
+    p = Reference(byref=True).from_file(f"{REF_DATA}/14/6/{which}.csv", 1 if which == "a" else 2, float(sig))
+    t0 = time.time()
+    times, values, _ = p.solve(200.0)
+    last = values[-1]
+    return dict(which=which, entry=i, sigma=sig, G=p.G, K=p.K, mM=p.mM, mW=p.mW, points=len(times), N_end=last[0],
+                C_end=last[p.G], state_sum=float(last.sum()), C00_end=last[1], seconds=time.time() - t0)
+
+
+def make_sweep(workers):
+    """ALL 160 entries of both sweeps of Experiment_14_6, pinned to the reference (by-reference build, bit-identical to the
+    shipped one on every configuration both were run on): tests/golden/exp_14_6_sweep.npz"""
+    jobs = [(w, i) for w in "ab" for i in range(160)]
+    jobs.sort(key=lambda j: j[1])                    # the refined-grid entries (sigma < 0.015, ~100x the cost) first
+    rows = []
+    with ProcessPoolExecutor(max_workers=workers) as pool:
+        for r in pool.map(job_sweep_entry, jobs):
+            rows.append(r)
+            print(f"14.6{r['which']}[{r['entry']}] G={r['G']} K={r['K']} N_end={r['N_end']!r} ({r['seconds']:.0f} s)", flush=True)
+    out = {}
+    for w in "ab":
+        mine = sorted((r for r in rows if r["which"] == w), key=lambda r: r["entry"])
+        for key in ("sigma", "G", "K", "mM", "mW", "points", "N_end", "C_end", "state_sum", "C00_end", "seconds"):
+            out[f"{w}_{key}"] = np.array([r[key] for r in mine])
+    np.savez_compressed(os.path.join(HERE, "exp_14_6_sweep.npz"), **out)
+
+
+def run_reference_menu(exe, keys, data_dir, workdir):
+    """the reference's own program (menu and all) in `workdir`: its relative paths use backslashes (Solver.cpp:983, 993),
+    which on Linux are literal file names -- symlinks named `Data\\14\\4\\b.csv` make the unmodified binary run.  Returns
+    the text of the `Data\\VisData.csv` it writes."""
+    import subprocess
+    for root, _, files in os.walk(data_dir):
+        for f in files:
+            if f.endswith(".csv"):
+                rel = os.path.relpath(os.path.join(root, f), os.path.dirname(data_dir))
+                link = os.path.join(workdir, rel.replace("/", "\\"))
+                if not os.path.lexists(link):
+                    os.symlink(os.path.join(root, f), link)
+    subprocess.run([exe], cwd=workdir, env=dict(os.environ, LDM_REF_KEYS=keys, TERM="dumb"), stdout=subprocess.DEVNULL,
+                   stderr=subprocess.DEVNULL, check=True, timeout=3600)
+    return open(os.path.join(workdir, "Data\\VisData.csv")).read()
+
+
+def make_visdata():
+    """Experiment 14.4 (b) through the UNMODIFIED reference program, its own menu driven by scripted keys (down, enter, esc):
+    the file it writes, byte for byte -> tests/golden/VisData_14_4_b_reference.csv (48 s of one core)"""
+    import tempfile
+    exe = os.path.join(os.path.dirname(os.path.dirname(HERE)), "oracle", "_ref", "solver_ref")
+    with tempfile.TemporaryDirectory() as tmp:
+        text = run_reference_menu(exe, "80,13,27", REF_DATA, tmp)
+    with open(os.path.join(HERE, "VisData_14_4_b_reference.csv"), "w") as fh:
+        fh.write(text)
+    print("VisData 14.4 (b):", len(text.splitlines()), "lines, last:", text.splitlines()[-1])
+
+
 def job_synth(args):
     """Forced-G grids (BASELINE.json configs 3-5): problem tables + one RHS on a non-trivial state."""
     name, sw, sm, G, b, d = args
@@ -207,6 +267,12 @@ def job_multi(name):
 
 
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "--visdata":
+        make_visdata()
+        return
+    if len(sys.argv) > 1 and sys.argv[1] == "--sweep":
+        make_sweep(int(sys.argv[2]) if len(sys.argv) > 2 else 6)
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "--multi":
         for name in MULTI:
             print(job_multi(name), flush=True)

@@ -29,6 +29,9 @@ def _load(name):
     lib.ref_rhs.argtypes = [C.c_void_p, _dp, _dp]
     lib.ref_integrals.argtypes = [C.c_void_p, _dp, C.POINTER(C.c_double), C.c_void_p]
     lib.ref_kernels_at_nodes.argtypes = [C.c_void_p, _dp, _dp]
+    if hasattr(lib, "ref_mc_rows"):
+        lib.ref_mc_rows.restype = C.c_int
+        lib.ref_mc_rows.argtypes = [C.c_void_p, _dp, C.c_int, C.c_int, _dp]
     lib.ref_solve.restype = C.c_int
     lib.ref_solve.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_void_p]
     lib.ref_solve_rk4.restype = C.c_int
@@ -82,6 +85,14 @@ class RefProblem:
         mc = np.zeros((self.G, self.G)) if want_mc else None
         self.lib.ref_integrals(self.h, state, C.byref(wc), mc.ctypes.data if want_mc else None)
         return wc.value, mc
+
+    def mc_rows(self, state, first, stride):
+        """the reference's per-node integral (Solver.cpp:297-316) on the rows first, first + stride, ...: [rows, G]"""
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        out = np.zeros((len(range(first, self.G, stride)), self.G))
+        n = self.lib.ref_mc_rows(self.h, state, int(first), int(stride), out)
+        assert n == out.shape[0]
+        return out
 
     def kernels_at_nodes(self):
         m, w = np.zeros((self.G, self.G)), np.zeros((self.G, self.G))

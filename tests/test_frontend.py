@@ -14,8 +14,10 @@ CXX = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
 
 
 def build_solver():
-    subprocess.check_call(["make", "-C", PKG, "host"], stdout=subprocess.DEVNULL)
-    return os.path.join(HOST, "solver")
+    exe = os.path.join(HOST, "solver")
+    if not os.path.exists(exe):           # __graft_entry__.build() makes it; the binary travels to the GPU box
+        subprocess.check_call(["make", "-C", PKG, "host"], stdout=subprocess.DEVNULL)
+    return exe
 
 
 def test_own_container_test_passes(tmp_path):

@@ -16,6 +16,14 @@ from oracle import OracleProblem
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(autouse=True)
+def default_shapes(ldm):
+    """shape overrides (ldm_tuning_set) never outlive the test that set them"""
+    yield
+    ldm.tuning_set("reset")
+
 RTOL_TRAJECTORY = 1e-10
 RTOL_RHS_TERMS = 1e-12
 
@@ -63,7 +71,7 @@ def algo_id(ldm, algorithm):
     return {"direct": ldm.ALGO_DIRECT, "factored": ldm.ALGO_FACTORED, "prefix": ldm.ALGO_PREFIX}[algorithm]
 
 
-ALL = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(p).startswith(("large_", "extras_", "multi_")))
+ALL = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(HERE, "golden", "*.npz")) if not os.path.basename(p).startswith(("large_", "extras_", "multi_", "exp_14_6_sweep")))
 
 
 @pytest.mark.parametrize("name", ALL)
@@ -244,6 +252,27 @@ def test_several_species(ldm, name, algorithm):
         eq.integrals(g["state"])                  # one-species entry points say so instead of misreading the state
 
 
+@pytest.mark.parametrize("which", ["a", "b"])
+def test_whole_sweep_against_the_reference(ldm, which):
+    """Experiment 14.6 a / b (S:1033-1071) entry by entry: ALL 160 entries of each sweep, 2000 Euler steps each, advanced
+    as one batch (ldm_solve_batch) -- what the experiment plots per entry (N and C[0][G-1] of the last state, S:1050-1055)
+    and C[0][0] within 1e-10 of the reference's own numbers (tests/golden/exp_14_6_sweep.npz, by-reference build), clamped
+    zeros exactly zero"""
+    g = golden("exp_14_6_sweep")
+    sigmas = g[f"{which}_sigma"]
+    eqs = []
+    for i, sig in enumerate(sigmas):
+        sw, sm = (float(sig), 0.08) if which == "a" else (0.05, float(sig))       # Data/14/6/a.csv: sigma_M = 0.08; b.csv: sigma_W = 0.05
+        props = ldm.Properties.Generate(1, sw, sm, 0.4, 0.2, 0.001)
+        assert (props.G, props.K, props.MaxNumForM, props.MaxNumForW) == (g[f"{which}_G"][i], g[f"{which}_K"][i], g[f"{which}_mM"][i], g[f"{which}_mW"][i])
+        eqs.append(ldm.Equation(props))
+    inits = [eq.GenerateEquilibriumValuesForNAndC(200) for eq in eqs]
+    outs = ldm.solve_batch(eqs, inits, 0.1, 200)
+    got = np.array([[o[0], o[e.props.G], o[1]] for o, e in zip(outs, eqs)])
+    want = np.stack([g[f"{which}_N_end"], g[f"{which}_C_end"], g[f"{which}_C00_end"]], 1)
+    assert_states_close(got, want)
+
+
 def test_batch_spread_over_two_devices(ldm):
     """the sweep with its entries living on two GPUs (ldm_create's device argument): every device advances its slice
     concurrently; same bits as the same entries on one device"""
@@ -296,17 +325,14 @@ def test_sharded_step_emulated_on_one_device(ldm, world):
         assert r.get_N() == want[0]
 
 
-@pytest.mark.parametrize("knob", ["one launch", "three launches"])
+@pytest.mark.parametrize("how", ["one step per launch", "all steps in one launch", "dense contraction"])
 @pytest.mark.parametrize("G", [0, 200])
-def test_peer_exchange_step_on_one_rank(ldm, monkeypatch, knob, G):
+def test_peer_exchange_step_on_one_rank(ldm, how, G):
     """the sharded step with the exchange fused in (ldm_shard_peer_*), world = 1 so that one GPU can run it: the rank
-    stores its rows into its own next replica and waits on its own flag.  Three launches per step (the default), or one in
-    which the last chunk CTA of a row closes and ships it (an option: measured slower); both must equal the unsharded run
-    bit for bit.  (Two and more
-    ranks: bench.py's sharded leg compares the checksum with the NCCL variant.)"""
+    stores its rows into its own next replica and waits on its own flag.  Prefix-sum path: the persistent work-list
+    kernel, one launch per step or one launch for all steps; dense contraction: three launches per step with the stores
+    in the closing kernel.  All must equal the unsharded run bit for bit."""
     import torch
-    if knob == "one launch":
-        monkeypatch.setenv("LDM_SHARD_ONE_LAUNCH", "1")
     if G:
         props = ldm.Properties.Generate(1, 0.12, 0.09, 0.4, 0.2, 0.001, G)       # two column chunks
         state = ldm.Equation(props).GenerateEquilibriumValuesForNAndC(200)
@@ -317,18 +343,112 @@ def test_peer_exchange_step_on_one_rank(ldm, monkeypatch, knob, G):
         props, _ = problems_from(base, "exp_14_4_c", ldm)
         state = base["state_k100"]
     sh = ldm.ShardedEquation(props, 0, 1)
+    if how == "dense contraction":
+        sh.eq.set_algorithm(ldm.ALGO_FACTORED)
     sh.peer_connect(lambda mine: mine.reshape(1, -1))
     sh.peer_upload(state[1:], state[0])
     steps = 7
     stream = torch.cuda.current_stream().cuda_stream
-    for _ in range(steps):
-        sh.peer_step(0.1, stream)
+    launches0 = sh.eq.launches
+    if how == "all steps in one launch":
+        sh.peer_advance(4, 0.1, stream)
+        sh.peer_advance(3, 0.1, stream)            # odd + even: the replica parity must come out right
+        assert sh.eq.launches - launches0 == 2
+    else:
+        for _ in range(steps):
+            sh.peer_step(0.1, stream)
     got_C, got_N = sh.peer_download()
-    single = ldm.Equation(props)
+    single = ldm.Equation(props, algorithm=sh.eq.algorithm)
     single.upload(state)
     single.advance(steps, 0.1)
     want = single.download()
     assert np.array_equal(got_C.ravel(), want[1:]) and got_N == want[0]
+
+
+@pytest.mark.parametrize("world,G", [(2, 200), (3, 200), (2, 0), (4, 333)])
+def test_ranks_on_one_device_elementwise(ldm, world, G):
+    """SURVEY 8e at world > 1 on ONE GPU: every rank is a handle of its own on device 0 with its own stream and its own
+    launch of the persistent work-list kernel (grids capped so that all of them are resident together); rows travel
+    between the ranks' replicas through the same peer stores and epoch flags a multi-GPU run uses (wired up by
+    ldm_shard_peer_connect_local instead of CUDA IPC).  Every rank's replica must equal the unsharded run ELEMENT BY
+    ELEMENT -- a permutation bug in the gathered layout would keep a checksum, not this."""
+    import torch
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    if G:
+        props = ldm.Properties.Generate(1, 0.12, 0.09, 0.4, 0.2, 0.001, G)       # several column chunks, uneven row counts
+        state = ldm.Equation(props).GenerateEquilibriumValuesForNAndC(200)
+        g = props.MomentsGrid
+        state[1:] *= (1 + 0.5 * np.exp(-(g[:, None] ** 2 + g[None, :] ** 2) / (2 * 0.1 ** 2)) + 0.1 * np.sin(7 * g[:, None] + 3 * g[None, :])).ravel()
+    else:
+        base = golden("exp_14_4_c")                                             # one chunk per row, 256-thread CTAs
+        props, _ = problems_from(base, "exp_14_4_c", ldm)
+        state = base["state_k100"]
+    ldm.tuning_set("chunk_grid", max(1, (sms - 8) // world))
+    ranks = [ldm.ShardedEquation(props, r, world) for r in range(world)]
+    ldm.ShardedEquation.connect_local(ranks)
+    for r in ranks:
+        r.peer_upload(state[1:], state[0])
+    streams = [torch.cuda.Stream() for _ in ranks]
+    steps = 9
+    for n in (4, 5):                                # two launches per rank; all ranks of a launch run side by side
+        for r, st in zip(ranks, streams):
+            r.peer_advance(n, 0.1, st.cuda_stream)
+    torch.cuda.synchronize()
+    single = ldm.Equation(props)
+    single.upload(state)
+    single.advance(steps, 0.1)
+    want = single.download()
+    for r in ranks:
+        got_C, got_N = r.peer_download()
+        assert np.array_equal(got_C.ravel(), want[1:]), f"rank {r.rank}: max |diff| {np.max(np.abs(got_C.ravel() - want[1:]))}"
+        assert got_N == want[0]
+
+
+def test_two_processes_two_gpus_elementwise(ldm):
+    """the same check across two processes and two GPUs (CUDA IPC mappings, NVLink peer stores): tests/mp_shard_check.py
+    under torchrun; every rank compares its replica element-wise with its own one-rank run"""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29731", os.path.join(HERE, "mp_shard_check.py"), "--G", "256", "--steps", "12"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    assert out.stdout.count("max_abs_diff 0.0") == 2, out.stdout[-2000:]
+
+
+def test_lost_rank_is_reported_not_hung(ldm):
+    """a peer group of two in which only rank 0 ever steps: its kernel gives up after the bounded wait (~9 s) and the
+    next download reports the error instead of handing back an incomplete replica"""
+    import torch
+    base = golden("exp_14_4_b")
+    props, _ = problems_from(base, "exp_14_4_b", ldm)
+    ranks = [ldm.ShardedEquation(props, r, 2) for r in range(2)]
+    ldm.ShardedEquation.connect_local(ranks)
+    for r in ranks:
+        r.peer_upload(base["state_k100"][1:], base["state_k100"][0])
+    ranks[0].peer_advance(3, 0.1, torch.cuda.current_stream().cuda_stream)
+    with pytest.raises(ldm.LdmError, match="never published|timed out"):
+        ranks[0].peer_download()
+
+
+def test_natural_layout_entry_points_refuse_a_sharded_handle(ldm):
+    """after ldm_shard_configure(world > 1) the kernels index C through the gathered layout and compute this rank's rows
+    only: the natural-layout entry points must say so instead of returning partial results"""
+    base = golden("exp_14_4_b")
+    props, _ = problems_from(base, "exp_14_4_b", ldm)
+    sh = ldm.ShardedEquation(props, 1, 2)
+    eq, state = sh.eq, base["state_k100"]
+    for call in (lambda: eq(0.0, state), lambda: eq.integrals(state), lambda: eq.upload(state), lambda: eq.advance(1, 0.1),
+                 lambda: eq.download(), lambda: ldm.EulerSolver().Solve(eq, ldm.SquaredN, 1.0, 0.1, state, record=ldm.RECORD_LAST),
+                 lambda: ldm.RungeKutta4thSolver().Solve(eq, ldm.SquaredN, 1.0, 0.1, state), lambda: ldm.solve_batch([eq], [state], 0.1, 1.0)):
+        with pytest.raises(ldm.LdmError):
+            call()
+    ldm.library().ldm_shard_configure(eq._h, 0, 1)          # the way back
+    single = ldm.Equation(props)
+    assert np.array_equal(eq(0.0, state), single(0.0, state))
 
 
 def test_degenerate_solves(ldm):
@@ -386,13 +506,13 @@ def test_factored_equals_direct_on_the_16k_grid(ldm, algorithm):
 
 
 @pytest.mark.parametrize("G,bm,bn", [(128, 40, 64), (200, 80, 128), (200, 40, 64), (96, 80, 64), (200, 128, 128), (100, 128, 128)])
-def test_factored_tilings_equal_direct(ldm, monkeypatch, G, bm, bn):
+def test_factored_tilings_equal_direct(ldm, G, bm, bn):
     """every tiling of the factored kernel (several beta tiles, several column chunks with their halo column, ragged
     edges) against the sample-by-sample path on grids the CPU oracle cannot reach in a test"""
     props = ldm.Properties.Generate(1, 0.12, 0.09, 0.4, 0.2, 0.001, G)
     direct = ldm.Equation(props, algorithm=ldm.ALGO_DIRECT)
-    monkeypatch.setenv("LDM_FACTORED_BM", str(bm))
-    monkeypatch.setenv("LDM_FACTORED_BN", str(bn))
+    ldm.tuning_set("factored_bm", bm)
+    ldm.tuning_set("factored_bn", bn)
     factored = ldm.Equation(props, algorithm=ldm.ALGO_FACTORED)
     g = props.MomentsGrid
     st = direct.GenerateEquilibriumValuesForNAndC(200)
@@ -403,13 +523,13 @@ def test_factored_tilings_equal_direct(ldm, monkeypatch, G, bm, bn):
 
 
 @pytest.mark.parametrize("G,bn", [(128, 0), (128, 64), (128, 32), (200, 0), (200, 96), (200, 32), (96, 0), (100, 64), (41, 32), (333, 0)])
-def test_prefix_chunkings_equal_direct(ldm, monkeypatch, G, bn):
+def test_prefix_chunkings_equal_direct(ldm, G, bn):
     """every column chunking of the prefix-sum kernel (one chunk, several chunks with pairs straddling the chunk
     boundary, ragged last chunk, chunk wider than the grid) against the sample-by-sample path"""
     props = ldm.Properties.Generate(1, 0.12, 0.09, 0.4, 0.2, 0.001, G)
     direct = ldm.Equation(props, algorithm=ldm.ALGO_DIRECT)
     if bn:
-        monkeypatch.setenv("LDM_SCAN_BN", str(bn))
+        ldm.tuning_set("scan_bn", bn)
     prefix = ldm.Equation(props, algorithm=ldm.ALGO_PREFIX)
     g = props.MomentsGrid
     st = direct.GenerateEquilibriumValuesForNAndC(200)
@@ -499,22 +619,18 @@ def test_headline_grids_against_the_reference(ldm, name):
     assert np.all(err <= RTOL_RHS_TERMS * scale), (worst, got[worst], g["deriv"][worst], err[worst] / scale[worst])
 
 
-@pytest.mark.parametrize("knob", ["LDM_FACTORED_W=1", "LDM_FACTORED_MMA=0", "LDM_FACTORED_TN=8"])
-def test_alternative_contraction_kernels(ldm, monkeypatch, knob):
-    """the optional variants of the contraction (precomputed W_x = Q.L_x with cp.async, DFMA register tiles instead of
-    tensor cores, 8-warp instead of 16-warp tiles) compute the same integrals as the default"""
+def test_eight_warp_contraction_tiles(ldm):
+    """the 8-warp tiles of the dense contraction (the default runs 16 warps per tile) compute the same integrals"""
     g = golden("synth_g64")
     props, o = problems_from(g, "synth_g64", ldm)
-    name, value = knob.split("=")
-    monkeypatch.setenv(name, value)
+    ldm.tuning_set("factored_tn", 8)
     eq = ldm.Equation(props, algorithm=ldm.ALGO_FACTORED)
     wc, mc = eq.integrals(g["state"])
     assert abs(wc - float(g["wc"])) <= 1e-13 * abs(float(g["wc"]))
     assert np.all(np.abs(mc - g["mc"]) <= 1e-13 * np.abs(g["mc"]))
     big = ldm.Properties.Generate(1, 0.12, 0.09, 0.4, 0.2, 0.001, 200)      # two column chunks, two beta tiles
-    a, b = ldm.Equation(big, algorithm=ldm.ALGO_FACTORED), None
-    monkeypatch.delenv(name)
-    monkeypatch.delenv("LDM_FACTORED_MMA", raising=False)
+    a = ldm.Equation(big, algorithm=ldm.ALGO_FACTORED)
+    ldm.tuning_set("reset")
     b = ldm.Equation(big, algorithm=ldm.ALGO_FACTORED)
     st = b.GenerateEquilibriumValuesForNAndC(200)
     gg = big.MomentsGrid
@@ -524,13 +640,13 @@ def test_alternative_contraction_kernels(ldm, monkeypatch, knob):
 
 
 @pytest.mark.parametrize("algorithm", ["prefix", "factored"])
-def test_persistent_kernel_equals_per_step_launches(ldm, monkeypatch, algorithm):
+def test_persistent_kernel_equals_per_step_launches(ldm, algorithm):
     """the cooperative multi-step kernel (all Euler steps in one launch, the default where it fits) against the
     three-launches-per-step path: same arithmetic, so the same bits; and every record mode of ldm_solve agrees"""
     g = golden("exp_14_4_c")
     props, _ = problems_from(g, "exp_14_4_c", ldm)
     persistent = ldm.Equation(props, algorithm=algo_id(ldm, algorithm))
-    monkeypatch.setenv("LDM_PERSISTENT", "0")
+    ldm.tuning_set("persistent", 0)
     stepwise = ldm.Equation(props, algorithm=algo_id(ldm, algorithm))
     init = persistent.GenerateEquilibriumValuesForNAndC(200)
     runs = [ldm.EulerSolver().Solve(eq, ldm.SquaredN, 30, 0.1, init, record=ldm.RECORD_ALL) for eq in (persistent, stepwise)]
@@ -545,6 +661,55 @@ def test_persistent_kernel_equals_per_step_launches(ldm, monkeypatch, algorithm)
         eq.advance(4, 0.1)
     assert np.array_equal(persistent.download(), stepwise.download())
     assert np.array_equal(persistent.download(), runs[0].Values[11])
+
+
+@pytest.mark.parametrize("G,bn", [(200, 0), (200, 32), (333, 0), (41, 32)])
+def test_work_list_kernel_equals_per_step_launches(ldm, G, bn):
+    """grids whose rows span several chunks: the persistent work-list kernel (all steps of ldm_advance / of a history
+    segment of ldm_solve in one launch) against one launch per kernel and step -- same arithmetic, same bits, in every
+    record mode; several history segments per solve at the larger sizes"""
+    props = ldm.Properties.Generate(1, 0.12, 0.09, 0.4, 0.2, 0.001, G)
+    if bn:
+        ldm.tuning_set("scan_bn", bn)
+    persistent = ldm.Equation(props)
+    ldm.tuning_set("persistent", 0)
+    stepwise = ldm.Equation(props)
+    g = props.MomentsGrid
+    init = persistent.GenerateEquilibriumValuesForNAndC(200)
+    init[1:] *= (1 + 0.5 * np.exp(-(g[:, None] ** 2 + g[None, :] ** 2) / (2 * 0.1 ** 2)) + 0.1 * np.sin(7 * g[:, None] + 3 * g[None, :])).ravel()
+    points = 13
+    runs = [ldm.EulerSolver().Solve(eq, ldm.SquaredN, (points - 0.5) * 0.1, 0.1, init, record=ldm.RECORD_ALL) for eq in (persistent, stepwise)]
+    assert len(runs[0].Times) == points
+    assert persistent.launches < stepwise.launches / 4
+    assert np.array_equal(runs[0].Values, runs[1].Values)
+    assert np.array_equal(runs[0].Derivatives, runs[1].Derivatives)
+    obs = ldm.EulerSolver().Solve(persistent, ldm.SquaredN, (points - 0.5) * 0.1, 0.1, init, record=ldm.RECORD_OBSERVABLES)
+    assert np.array_equal(obs.Observables, runs[0].Values[:, [0, props.G]])
+    last = ldm.EulerSolver().Solve(persistent, ldm.SquaredN, (points - 0.5) * 0.1, 0.1, init, record=ldm.RECORD_LAST)
+    assert np.array_equal(last.Values[0], runs[0].Values[-1]) and np.array_equal(last.Derivatives[0], runs[0].Derivatives[-1])
+    for eq in (persistent, stepwise):
+        eq.upload(init)
+        eq.advance(7, 0.1)      # odd step count: the ping-pong parity must come out right
+        eq.advance(4, 0.1)
+    assert np.array_equal(persistent.download(), stepwise.download())
+    assert np.array_equal(persistent.download(), runs[0].Values[11])
+
+
+def test_history_leaves_in_segments(ldm):
+    """a solve whose history spans many device segments (16 MiB each): Values and Derivatives of every point arrive,
+    identical to a solve that stores the observables only"""
+    props = ldm.Properties.Generate(1, 0.15, 0.15, 0.4, 0.2, 0.001, 128)
+    eq = ldm.Equation(props)
+    init = eq.GenerateEquilibriumValuesForNAndC(200)
+    points = 700                                   # 700 x 16385 x 8 B x 2 = 183 MB of history
+    full = ldm.EulerSolver().Solve(eq, ldm.SquaredN, (points - 0.5) * 0.1, 0.1, init, record=ldm.RECORD_ALL)
+    obs = ldm.EulerSolver().Solve(eq, ldm.SquaredN, (points - 0.5) * 0.1, 0.1, init, record=ldm.RECORD_OBSERVABLES)
+    assert np.array_equal(full.Values[:, [0, props.G]], obs.Observables)
+    assert np.array_equal(full.Values[0], init)
+    eq.upload(full.Values[400])
+    eq.advance(1, 0.1)
+    assert np.array_equal(eq.download(), full.Values[401])
+    assert np.array_equal(eq(0.0, full.Values[650]), full.Derivatives[650])
 
 
 def test_large_grid_properties(ldm):

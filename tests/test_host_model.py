@@ -9,7 +9,7 @@ import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-GOLDEN = sorted(p for p in glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")) if not os.path.basename(p).startswith(("large_", "extras_", "multi_")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(ROOT, "tests", "golden", "*.npz")) if not os.path.basename(p).startswith(("large_", "extras_", "multi_", "exp_14_6_sweep")))
 
 
 def generate(ldm, g, name):
@@ -133,3 +133,50 @@ def test_bench_prints_exactly_one_json_line():
     assert line["impl"] == "reference"
     if "unavailable" not in line:
         assert line["config"]["xi_points"] == 41 * 41 and line["value"] > 0 and line["e2e"]["value"] == line["value"]
+
+
+def _corrupted(ldm, props, **changes):
+    """a copy of the ldm_problem behind `props` with fields replaced; array fields take numpy arrays (kept alive on the copy)"""
+    bad = ldm._Problem.from_buffer_copy(props._ptr.contents)
+    bad._keep = []
+    for name, value in changes.items():
+        if isinstance(value, np.ndarray):
+            arr = np.ascontiguousarray(value, dtype=np.float64)
+            bad._keep.append(arr)
+            setattr(bad, name, arr.ctypes.data_as(ctypes.POINTER(ctypes.c_double)))
+        else:
+            setattr(bad, name, value)
+    return bad
+
+
+@pytest.mark.parametrize("case", ["mM above K", "mW above K", "even mM", "even K", "grid not increasing", "grid does not start at 0",
+                                  "grid does not end at the cutoff", "kernel grid not increasing", "zero step", "mM of 1"])
+def test_create_rejects_tables_the_reference_asserts_on(ldm, case):
+    """ldm_create accepts any caller-built table, so it checks what the reference asserts (S:77, S:88, S:125-132,
+    S:303-304) BEFORE anything indexes with it: LDM_ERR_ARGUMENT (-1), on the host, with or without a GPU"""
+    props = ldm.Properties.Generate(1, 0.05, 0.05, 0.4, 0.2, 0.001)
+    g, k = props.MomentsGrid.copy(), props.KernelsGrid.copy()
+    changes = {
+        "mM above K": dict(mM=props.K + 2), "mW above K": dict(mW=props.K + 2), "even mM": dict(mM=4), "mM of 1": dict(mM=1),
+        "even K": dict(K=props.K - 1),
+        "grid not increasing": dict(moments_grid=np.concatenate([g[:3], g[2:3], g[4:]])),
+        "grid does not start at 0": dict(moments_grid=np.concatenate([[1e-3], g[1:]])),
+        "grid does not end at the cutoff": dict(moments_grid=np.concatenate([g[:-1], [g[-1] * 1.01]])),
+        "kernel grid not increasing": dict(kernels_grid=k[::-1].copy()),
+        "zero step": dict(h=0.0),
+    }[case]
+    bad = _corrupted(ldm, props, **changes)
+    handle = ctypes.c_void_p()
+    code = ldm.library().ldm_create(ctypes.byref(bad), 0, ctypes.byref(handle))
+    assert code == -1 and not handle.value, (case, code, ldm.library().ldm_last_error())
+    assert ldm.library().ldm_last_error()          # says what is wrong
+    sep, dev = ctypes.c_int(), ctypes.c_double()
+    assert ldm.library().ldm_problem_kernel_structure(ctypes.byref(bad), ctypes.byref(sep), ctypes.byref(dev)) == -1
+
+
+def test_tuning_keys(ldm):
+    for key in ("scan_bn", "scan_nt", "factored_bm", "factored_bn", "factored_tn", "persistent", "scan", "chunk_grid"):
+        ldm.tuning_set(key, 0)
+    ldm.tuning_set("reset")
+    with pytest.raises(ldm.LdmError):
+        ldm.tuning_set("no such key", 1)

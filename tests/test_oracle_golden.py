@@ -9,7 +9,7 @@ import pytest
 
 from oracle import OracleMulti, OracleProblem
 
-GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if not os.path.basename(p).startswith(("large_", "extras_", "multi_")))
+GOLDEN = sorted(p for p in glob.glob(os.path.join(os.path.dirname(__file__), "golden", "*.npz")) if not os.path.basename(p).startswith(("large_", "extras_", "multi_", "exp_14_6_sweep")))
 
 
 def make_oracle(g, name):
