@@ -41,7 +41,7 @@ def test_patch_recipe_adds_four_lines():
     patched = subprocess.check_output(["python", os.path.join(ROOT, "oracle", "patch_binding.py"), ref], text=True).split("\n")
     original = open(ref, newline="").read().split("\n")
     assert len(patched) == len(original) + 4
-    added = [l for l in patched if "ldm_binding" in l or "LdmProps() {" in l]
+    added = [l for l in patched if "ldm_binding" in l or "LdmProps() {" in l or "ldm_reference_binding" in l]
     assert len(added) == 4 and sorted(set(patched) - set(original)) == sorted(added)
 
 
