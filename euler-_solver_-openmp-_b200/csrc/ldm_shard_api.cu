@@ -98,6 +98,23 @@ bool chunked_possible(ldm_context* c)
     return c->chunk_grid > 0;
 }
 
+// Everything a launch of the work-list kernel needs besides the state, built once per (rank, world): ring operator, work
+// list, ring shares, counters.  Some of it synchronises the device (cudaFree, the ring operator's upload), so a peer
+// group sets it up BEFORE anybody steps (ldm_shard_peer_upload) -- several ranks may share one device in one process,
+// and a rank that synchronises the device while another rank's kernel waits for it would never come back.
+int prepare_chunked(ldm_context* c)
+{
+    const DevProblem& d = c->dev;
+    ensure_ring_operator(c);
+    ensure_items(c);
+    int grid = std::min(c->chunk_grid, c->n_items);
+    if (c->chunk_grid_limit > 0) grid = std::min(grid, c->chunk_grid_limit);
+    ensure_ring_cut(c, grid);
+    if (!c->d_counters) c->d_counters = c->alloc<unsigned int>(3 + (size_t)d.G);
+    if (!c->d_ring2) c->d_ring2 = c->alloc<double>(2 * c->P());
+    return grid;
+}
+
 void advance_chunked(ldm_context* c, int n_steps, double dt, cudaStream_t s, long long first_point, double* d_obs, double* d_values,
                      double* d_derivs)
 {
@@ -105,15 +122,9 @@ void advance_chunked(ldm_context* c, int n_steps, double dt, cudaStream_t s, lon
     const DevProblem& d = c->dev;
     const bool peers = c->peer_connected;
     if (!peers && d.world != 1) throw std::invalid_argument("a sharded handle steps through its peer group (ldm_shard_peer_connect)");
-    ensure_ring_operator(c);
-    ensure_items(c);
-    int grid = std::min(c->chunk_grid, c->n_items);
-    if (c->chunk_grid_limit > 0) grid = std::min(grid, c->chunk_grid_limit);
-    ensure_ring_cut(c, grid);
+    const int grid = prepare_chunked(c);
     const int n_local = local_rows(d);
     const size_t P_local = (size_t)n_local * d.G;
-    if (!c->d_counters) c->d_counters = c->alloc<unsigned int>(3 + (size_t)d.G);
-    if (!c->d_ring2) c->d_ring2 = c->alloc<double>(2 * c->P());
 
     ChunkedArgs a{};
     a.world = d.world; a.rank = d.rank;
@@ -310,6 +321,8 @@ int ldm_shard_peer_upload(ldm_handle h, const double* C_gathered, double N)
         LDM_CUDA(cudaMemcpy(h->d_N, &N, sizeof(double), cudaMemcpyHostToDevice));
         h->peer_epoch = 0;
         h->peer_parity = 0;
+        if (chunked_possible(h)) prepare_chunked(h);       // before anybody steps (see prepare_chunked)
+        else ensure_ring_operator(h);
         LDM_CUDA(cudaDeviceSynchronize());
     });
 }

@@ -38,7 +38,7 @@ def test_patch_recipe_adds_four_lines():
     ref = "/root/reference/Euler Solver ver.5.3/Solver.cpp"
     if not os.path.exists(ref):
         pytest.skip("the reference is mounted only in the build container")
-    patched = subprocess.check_output(["python", os.path.join(ROOT, "oracle", "patch_binding.py"), ref], text=True).split("\n")
+    patched = subprocess.check_output(["python", os.path.join(ROOT, "oracle", "patch_binding.py"), ref]).decode().split("\n")
     original = open(ref, newline="").read().split("\n")
     assert len(patched) == len(original) + 4
     added = [l for l in patched if "ldm_binding" in l or "LdmProps() {" in l or "ldm_reference_binding" in l]
