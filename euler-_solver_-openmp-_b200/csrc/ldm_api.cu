@@ -1136,6 +1136,7 @@ void advance_batch_on_device(const std::vector<ldm_context*>& handles, int point
             int max_slabs = 0, max_rows = 0, max_G = 0, max_A = 0, max_ring = 0, max_points = 0;
             size_t max_smem = 0;     // prefix-sum groups: the largest member's shared memory
             int scan_nt = 512;
+            bool persistent = false;   // all steps inside one launch (persistent_batch_kernel)
             ldm::StepArgs* d_args[2] = {nullptr, nullptr};
         };
         std::vector<Group> groups;
@@ -1175,9 +1176,86 @@ void advance_batch_on_device(const std::vector<ldm_context*>& handles, int point
                 }
             cudaStream_t s = lead->stream;
             LDM_CUDA(cudaEventRecord(lead->ev_begin, s));
+            // Prefix-sum groups whose rows are one chunk each: ALL steps of all their sets in one launch per wave of the
+            // persistent batch kernel, every set with a team of CTAs sized by its cost.  Everything else: one launch per
+            // kernel and step, below.
+            for (Group& g : groups) {
+                g.persistent = lead->persistent_enabled && g.shape.scan && points > 1;
+                for (int i : g.members)
+                    g.persistent = g.persistent && handles[i]->dev.scan_chunks == 1 && handles[i]->persistent_enabled;
+                if (!g.persistent) continue;
+                int capacity = 0;
+                ldm::BatchArgs probe{};
+                if (ldm::launch_persistent_batch(probe, 0, g.scan_nt, g.max_smem, s, &capacity) != cudaSuccess || capacity < 1) {
+                    cudaGetLastError();
+                    g.persistent = false;
+                    continue;
+                }
+                const int members = (int)g.members.size();
+                // cost model (SM cycles): per row ~3 k of tables, closing and barriers plus ~6.4 per (quadrature node x column)
+                // of E and y-side work; a step of a set with a team of T costs ceil(G / T) rows (+ the team barrier)
+                std::vector<double> row_cost((size_t)members);
+                std::vector<int> rows((size_t)members);
+                for (int m = 0; m < members; m++) {
+                    const ldm::DevProblem& d = handles[g.members[(size_t)m]]->dev;
+                    rows[(size_t)m] = d.G;
+                    row_cost[(size_t)m] = 3000.0 + 6.4 * d.A * d.G;
+                }
+                std::vector<int> order((size_t)members);
+                for (int m = 0; m < members; m++) order[(size_t)m] = m;
+                std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return row_cost[(size_t)a] * rows[(size_t)a] > row_cost[(size_t)b] * rows[(size_t)b]; });
+                const int waves = (members + capacity - 1) / capacity;
+                std::vector<double*> wc_ptr((size_t)members);
+                for (int m = 0; m < members; m++) wc_ptr[(size_t)m] = handles[g.members[(size_t)m]]->d_wc_rows2;
+                auto device_copy = [&](const void* host, size_t bytes) {
+                    void* p = nullptr;
+                    LDM_CUDA(cudaMalloc(&p, std::max<size_t>(bytes, 8)));
+                    scratch.push_back(p);
+                    LDM_CUDA(cudaMemcpyAsync(p, host, bytes, cudaMemcpyHostToDevice, s));
+                    return p;
+                };
+                double* const* d_wc_ptr = static_cast<double* const*>(device_copy(wc_ptr.data(), wc_ptr.size() * sizeof(double*)));
+                unsigned int* d_barriers = nullptr;
+                LDM_CUDA(cudaMalloc((void**)&d_barriers, (size_t)members * sizeof(unsigned int)));
+                scratch.push_back(d_barriers);
+                LDM_CUDA(cudaMemsetAsync(d_barriers, 0, (size_t)members * sizeof(unsigned int), s));
+                for (int w = 0; w < waves; w++) {
+                    std::vector<int> mine;                        // members of this wave: dealt out round-robin by cost
+                    for (int at = w; at < members; at += waves) mine.push_back(order[(size_t)at]);
+                    std::vector<int> team(mine.size(), 1);
+                    int spare = capacity - (int)mine.size();
+                    auto step_time = [&](size_t j) {
+                        const int m = mine[j], T = team[j];
+                        return ((rows[(size_t)m] + T - 1) / T) * row_cost[(size_t)m] + (T > 1 ? 2000.0 : 0.0);
+                    };
+                    while (spare > 0) {                           // one more CTA to the set whose step is the longest
+                        size_t worst = mine.size();
+                        double worst_time = -1;
+                        for (size_t j = 0; j < mine.size(); j++)
+                            if (team[j] < rows[(size_t)mine[j]] && step_time(j) > worst_time) { worst_time = step_time(j); worst = j; }
+                        if (worst == mine.size()) break;
+                        team[worst]++;
+                        spare--;
+                    }
+                    std::vector<int> cta;                         // int4 per CTA
+                    for (size_t j = 0; j < mine.size(); j++)
+                        for (int r = 0; r < team[j]; r++) { cta.push_back(mine[j]); cta.push_back(r); cta.push_back(team[j]); cta.push_back(0); }
+                    ldm::BatchArgs a{};
+                    a.args[0] = g.d_args[0]; a.args[1] = g.d_args[1];
+                    a.cta = static_cast<const int4*>(device_copy(cta.data(), cta.size() * sizeof(int)));
+                    a.wc_rows = d_wc_ptr;
+                    a.barriers = d_barriers;
+                    a.n_steps = points - 1;
+                    a.parity = 0;
+                    a.status = lead->d_status;
+                    LDM_CUDA(ldm::launch_persistent_batch(a, (int)(cta.size() / 4), g.scan_nt, g.max_smem, s, nullptr));
+                    lead->launches += 1;
+                }
+            }
             int parity = 0;
             for (int k = 0; k + 1 < points; k++) {
                 for (Group& g : groups) {
+                    if (g.persistent) continue;
                     const int members = (int)g.members.size();
                     const bool side = g.max_ring > 0;
                     if (side) {
@@ -1197,7 +1275,8 @@ void advance_batch_on_device(const std::vector<ldm_context*>& handles, int point
             LDM_CUDA(cudaEventRecord(lead->ev_end, s));
             LDM_CUDA(cudaGetLastError());
             LDM_CUDA(cudaStreamSynchronize(s));
-            for (int i = 0; i < n; i++) handles[i]->cur = parity;
+            check_device_status(lead);
+            for (int i = 0; i < n; i++) handles[i]->cur = (points - 1) & 1;
         } catch (...) {
             for (void* p : scratch) cudaFree(p);
             throw;

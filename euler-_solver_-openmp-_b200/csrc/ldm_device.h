@@ -260,6 +260,21 @@ struct ChunkedArgs {
 // grid <= 0: only report the largest co-resident grid in *max_grid
 cudaError_t launch_persistent_chunks(const ChunkedArgs& args, int grid, cudaStream_t stream, int* max_grid);
 
+// Arguments of the persistent batch kernel (ldm_persist.cu persistent_batch_kernel): n_steps Euler steps of MANY independent
+// parameter sets -- the loop of Experiments::CalculateWithVaryingSigma (Solver.cpp:940-963) -- in ONE launch.  Every set
+// owns a team of consecutive CTAs (sized by its cost on the host); the CTAs of a team deal the set's rows out among
+// themselves and meet at a per-set barrier once per step.  No grid-wide barrier: the sets never wait for each other.
+struct BatchArgs {
+    const StepArgs* args[2];   // [parity][sets] the sets' arguments for both parities of their state ping-pong
+    const int4* cta;           // [grid] (set, rank within its team, team size, 0)
+    double* const* wc_rows;    // [sets] -> [2][G] row dots of the WC functional, ping-pong with the state
+    unsigned int* barriers;    // [sets] arrival counters of the team barriers (zeroed before the launch)
+    int n_steps, parity;
+    int* status;
+};
+// grid <= 0: only report the largest co-resident grid in *max_grid (for CTAs of `nt` threads with `smem` bytes)
+cudaError_t launch_persistent_batch(const BatchArgs& args, int grid, int nt, size_t smem, cudaStream_t stream, int* max_grid);
+
 // Shape overrides for tests (ldm_tuning_set): 0 / -1 = the library decides.  Read when a handle is created.
 struct Tuning {
     int scan_bn = 0, scan_nt = 0;              // prefix-sum path: chunk width, threads per CTA

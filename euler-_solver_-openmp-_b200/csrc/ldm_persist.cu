@@ -346,6 +346,99 @@ persistent_chunks_kernel(const ChunkedArgs A)
     }
 }
 
+
+// Barrier among the T CTAs of one team (see grid_barrier): a monotone arrival counter per team.  T == 1: the CTA barrier alone.
+__device__ __forceinline__ bool team_barrier(unsigned int* counter, unsigned int index, int T, int* status)
+{
+    __shared__ int team_ok;
+    __syncthreads();
+    if (T == 1) return true;
+    if (threadIdx.x == 0) {
+        asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(counter), "r"(1u) : "memory");
+        const bool arrived = wait_for_count(counter, (index + 1u) * (unsigned int)T, status);
+        team_ok = arrived && load_status(status) == kStatusOk;
+    }
+    __syncthreads();
+    return team_ok != 0;
+}
+
+// Persistent batch kernel (cooperative launch): see BatchArgs in ldm_device.h.  The sets' rows are one chunk each (G <= 128).
+// Per step a CTA sums the G row dots of the WC functional of its set (written by the team's closing phases of the step
+// before), then for each of its rows runs scan_body (per-node sums stay in shared memory), applies the ring correction
+// of that row's nodes itself (ring_row_dot: the bits of ring_kernel), closes the row -- closure, Euler update, clamp, the
+// arithmetic of finish_factored_kernel -- and forms the row's dot with the WC functional for the next state.  One team
+// barrier per step; a team of one needs none.
+template <bool SMALL>
+__global__ void __launch_bounds__(SMALL ? 256 : kScanThreadsMax, SMALL ? 4 : 1)
+persistent_batch_kernel(const BatchArgs A)
+{
+    const int NT = blockDim.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, warps = NT / 32;
+    __shared__ double wc_shared;
+    const int4 me = A.cta[blockIdx.x];
+    const int set = me.x, r = me.y, T = me.z;
+    const StepArgs* const args[2] = {A.args[0] + set, A.args[1] + set};
+    const DevProblem& P = args[0]->P;                                   // the same problem in both
+    const int G = P.G;
+    const ScanLayout L = scan_layout(G, P.A, P.scan_bn, NT, P.scan_max_pieces);
+    extern __shared__ __align__(32) unsigned char scan_smem[];
+    double* row_sum = reinterpret_cast<double*>(scan_smem + L.rowsum);  // [G] after scan_body(fused)
+    double* c_new = reinterpret_cast<double*>(scan_smem + L.rowbuf);    // [G] the row being closed, at the new time
+    double* ring_buf = c_new + L.part_stride;                           // [G] its ring correction
+    double* wc_rows = A.wc_rows[set];
+    unsigned int* barrier = A.barriers + set;
+    int parity = A.parity;
+    unsigned int barrier_index = 0;
+
+    // prologue: the row dots of WC for the initial state, this CTA's rows
+    if (warp == 0) {
+        for (int lx = r; lx < G; lx += T) {
+            const double s = wc_row_dot(P.wc_operator + (size_t)lx * G, args[parity]->C + (size_t)lx * G, G, lane);
+            if (lane == 0) wc_rows[parity * G + lx] = s;
+        }
+    }
+    if (!team_barrier(barrier, barrier_index++, T, A.status)) return;
+
+    for (int k = 0; k < A.n_steps; k++) {
+        const StepArgs& S = *args[parity];
+        if (warp == 0) {
+            const double t = wc_total(wc_rows + parity * G, G, lane);
+            if (lane == 0) wc_shared = t;
+        }
+        __syncthreads();
+        const double N = S.N_cur[0];
+        const double WC = __dmul_rn(add_outside(P, wc_shared, N, S.C, S.scalars, P.wc_outside, 0.0), P.hh);   // Solver.cpp:311, 314
+        for (int lx = r; lx < G; lx += T) {
+            scan_body_of<SMALL, 0>(S, 0, lx, true, -1, true);           // per-node sums -> row_sum; ends with a CTA barrier
+            for (int y = tid; y < G; y += NT) ring_buf[y] = 0.0;
+            __syncthreads();
+            for (int row = P.ring_row_begin[lx] + warp; row < P.ring_row_begin[lx + 1]; row += warps) {
+                const double acc = ring_row_dot(P, S.C, row, lane);
+                if (lane == 0) ring_buf[P.ring_point[row] - lx * G] = acc;
+            }
+            __syncthreads();
+            for (int y = tid; y < G; y += NT) {
+                const int q = lx * G + y;
+                const double inside = (0.0 + row_sum[y]) - ring_buf[y];
+                const double c = S.C[q];
+                const double mc = __dmul_rn(add_outside(P, inside, N, S.C, S.scalars, P.out_weight[q], 0.0), P.hh);
+                const double dc = second_moment_rhs(P, mc, c, N, WC, P.m_nodes[q], P.w_nodes[q]);
+                double v = __dadd_rn(c, __dmul_rn(dc, S.dt));           // Solver.cpp:577
+                v = v < 0.0 ? 0.0 : v;                                  // Solver.cpp:578-580
+                S.C_next[q] = v;
+                c_new[y] = v;
+            }
+            __syncthreads();
+            if (warp == 0) {     // this row's dot with the WC functional for the next state
+                const double s = wc_row_dot(P.wc_operator + (size_t)lx * G, c_new, G, lane);
+                if (lane == 0) wc_rows[(parity ^ 1) * G + lx] = s;
+            }
+        }
+        if (r == 0 && tid == 0) first_moment_update(P, N, WC, S.dt, S.scalars, S.N_next);
+        if (!team_barrier(barrier, barrier_index++, T, A.status)) return;    // a lost partner: the host reports the status word
+        parity ^= 1;
+    }
+}
+
 }  // namespace
 
 cudaError_t launch_persistent_scan(const PersistentArgs& args, int grid, cudaStream_t stream, int* max_grid)
@@ -409,6 +502,24 @@ cudaError_t launch_persistent_chunks(const ChunkedArgs& args, int grid, cudaStre
     if (grid <= 0) return cudaSuccess;                  // query only
     if (grid > sms * per_sm) return cudaErrorCooperativeLaunchTooLarge;
     ChunkedArgs a = args;
+    void* params[] = {&a};
+    return cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(nt), params, smem, stream);
+}
+
+cudaError_t launch_persistent_batch(const BatchArgs& args, int grid, int nt, size_t smem, cudaStream_t stream, int* max_grid)
+{
+    const void* kernel = nt <= 256 ? (const void*)persistent_batch_kernel<true> : (const void*)persistent_batch_kernel<false>;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBudget);
+    if (e != cudaSuccess) return e;
+    int device = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&device);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, nt, smem);
+    if (e != cudaSuccess) return e;
+    if (max_grid) *max_grid = sms * per_sm;
+    if (grid <= 0) return cudaSuccess;                  // query only
+    if (grid > sms * per_sm) return cudaErrorCooperativeLaunchTooLarge;
+    BatchArgs a = args;
     void* params[] = {&a};
     return cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(nt), params, smem, stream);
 }
