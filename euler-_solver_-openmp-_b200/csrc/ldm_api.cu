@@ -506,6 +506,7 @@ int ldm_tuning_set(const char* name, int value)
     else if (key == "persistent") t.persistent = value;
     else if (key == "scan") t.scan = value;
     else if (key == "chunk_grid") t.chunk_grid = value;
+    else if (key == "batch_capacity") t.batch_capacity = value;
     else return fail(LDM_ERR_ARGUMENT, "unknown tuning key");
     return LDM_OK;
 }
@@ -1191,6 +1192,7 @@ void advance_batch_on_device(const std::vector<ldm_context*>& handles, int point
                     g.persistent = false;
                     continue;
                 }
+                if (tuning().batch_capacity > 0) capacity = std::min(capacity, tuning().batch_capacity);
                 const int members = (int)g.members.size();
                 // cost model (SM cycles): per row ~3 k of tables, closing and barriers plus ~6.4 per (quadrature node x column)
                 // of E and y-side work; a step of a set with a team of T costs ceil(G / T) rows (+ the team barrier)

@@ -282,6 +282,7 @@ struct Tuning {
     int persistent = -1;                       // 0: one launch per step even where a persistent kernel applies
     int scan = -1;                             // 0: never take the prefix-sum path
     int chunk_grid = 0;                        // persistent_chunks_kernel: CTAs per launch (tests run two ranks on one device)
+    int batch_capacity = 0;                    // persistent_batch_kernel: CTA budget of a launch (tests: several waves of sets)
 };
 Tuning& tuning();
 

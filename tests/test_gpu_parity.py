@@ -181,6 +181,37 @@ def test_batch_of_parameter_sets(ldm, algorithm):
         assert_states_close(got, want)
 
 
+@pytest.mark.parametrize("capacity", [0, 7])
+def test_persistent_batch_equals_per_step_batch(ldm, capacity):
+    """the batch of independent parameter sets with ALL steps in one launch (persistent_batch_kernel: a team of CTAs per
+    set, per-set barriers) against one launch per kernel and step: the same bits for every set -- teams of many CTAs
+    (few sets on a whole GPU), teams of one, a set whose rows outnumber... and, with the CTA budget capped at 7, several
+    waves of sets that queue for the device"""
+    names = ["exp_14_6_a_012", "exp_14_6_b_040", "exp_14_6_a_080", "exp_14_6_b_012", "exp_14_6_b_000", "exp_14_6_a_159", "exp_14_4_b",
+             "exp_14_6_a_000", "synth_g64", "exp_14_4_c", "exp_14_6_b_159"]
+    runs = []
+    for persistent in (1, 0):
+        ldm.tuning_set("reset")
+        ldm.tuning_set("persistent", persistent)
+        if capacity:
+            ldm.tuning_set("batch_capacity", capacity)
+        eqs, inits = [], []
+        for name in names:
+            g = golden(name)
+            props, _ = problems_from(g, name, ldm)
+            eq = ldm.Equation(props)
+            eqs.append(eq)
+            inits.append(g["state_k100"] if "state_k100" in g.files else g["state"])
+        launches0 = sum(e.launches for e in eqs)
+        runs.append(ldm.solve_batch(eqs, inits, 0.1, 3.75))           # 37 steps: an odd count, the ping-pong parity must come out right
+        launches = sum(e.launches for e in eqs) - launches0
+        assert (launches <= 4) if persistent else (launches >= 37 * 2)
+        again = ldm.solve_batch(eqs, inits, 0.1, 3.75)                 # the handles are reusable: counters and parity start over
+        assert all(np.array_equal(a, b) for a, b in zip(runs[-1], again))
+    for name, one, two in zip(names, *runs):
+        assert np.array_equal(one, two), name
+
+
 @pytest.mark.parametrize("algorithm", ["prefix", "factored", "direct"])
 @pytest.mark.parametrize("name", ["b", "c"])
 def test_runge_kutta_and_extrapolation_types(ldm, name, algorithm):
