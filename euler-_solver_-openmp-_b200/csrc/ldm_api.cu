@@ -611,9 +611,9 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         c->d_C[1] = c->alloc<double>(P + (size_t)d.G);
         c->d_N = c->alloc<double>(2);
         c->d_status = c->alloc<int>(1);
-        c->d_flags = c->alloc<unsigned long long>(ldm::kMaxPeers);
+        c->d_flags = c->alloc<unsigned long long>(ldm::kFlagWords(d.G));
         LDM_CUDA(cudaMemsetAsync(c->d_status, 0, sizeof(int), c->stream));
-        LDM_CUDA(cudaMemsetAsync(c->d_flags, 0, ldm::kMaxPeers * sizeof(unsigned long long), c->stream));
+        LDM_CUDA(cudaMemsetAsync(c->d_flags, 0, ldm::kFlagWords(d.G) * sizeof(unsigned long long), c->stream));
         c->d_scalars = c->alloc<double>(ldm::kScalars);
         c->d_sum = c->alloc<double>(P);
         c->d_deriv = c->alloc<double>(P);

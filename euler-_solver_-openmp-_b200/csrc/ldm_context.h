@@ -61,7 +61,7 @@ struct ldm_context {
     unsigned int* d_barrier = nullptr;     // [1 + G] arrival counter of that kernel's grid barrier, then its per-row ring counts
     // fused update + all-gather (ldm_shard_peer_*)
     double* peer_own[2] = {nullptr, nullptr};                 // this rank's two replicas of C (gathered layout)
-    unsigned long long* peer_own_flags = nullptr;             // [world] last step published by every rank
+    unsigned long long* peer_own_flags = nullptr;             // [kFlagWords(G)] last step published by every rank, newest state of every row
     unsigned int* peer_done = nullptr;
     int* peer_status = nullptr;
     double* peer_C[2][ldm::kMaxPeers] = {};                   // every rank's replicas, peer-mapped
@@ -75,7 +75,8 @@ struct ldm_context {
     // persistent work-list kernel (ldm_persist.cu persistent_chunks_kernel): rows of several chunks and the xi-sharded step
     int chunk_grid = 0;                    // co-resident CTAs of that kernel (0: not queried yet, -1: unavailable)
     int chunk_grid_limit = 0;              // > 0: launch at most this many CTAs (ldm_tuning_set chunk_grid; two ranks on one device in tests)
-    int2* d_items = nullptr;               // (local row, chunk) work list of the current (rank, world), most expensive first
+    int2* d_items = nullptr;               // (local row, chunk) work list of the current (rank, world): rows ascending
+    int2* d_row_window = nullptr;          // [G] rows that the E phase of row x reads (ChunkedArgs::row_window)
     int n_items = 0;
     int items_rank = -1, items_world = -1;
     int* d_ring_cut = nullptr;             // [cut_grid + 1] ring CSR rows dealt out over the CTAs of a launch
@@ -83,7 +84,7 @@ struct ldm_context {
     std::vector<int> chunk_order_host;     // the column chunks by descending y-side work (DevProblem::scan_chunk_order)
     std::vector<int> ring_row_begin_host;  // CSR row starts of the current ring operator (to deal the rows out by entry count)
     unsigned int* d_counters = nullptr;    // [3 + rows] ChunkedArgs::counters
-    unsigned long long* d_flags = nullptr; // [kMaxPeers] one rank without peers: its own flag array
+    unsigned long long* d_flags = nullptr; // [kFlagWords(G)] one rank without peers: its own flag array
     unsigned long long local_epoch = 0;    // steps that kernel has taken on this handle outside a peer group
     int* d_status = nullptr;               // sticky device status word of the bounded waits (ldm_scan_body.cuh); 0 = fine
     std::vector<void*> ring_allocations;   // the ring-correction CSR of the current (rank, world)

@@ -234,8 +234,10 @@ cudaError_t launch_persistent(const FactoredPlan& plan, const PersistentArgs& ar
 // problem on `world` ranks in ONE launch per rank.  The pair density lives in two replicas per rank (ping-pong), each
 // `words` doubles in gathered layout followed by a tail of G doubles: the row dots of the WC functional for that state.
 // Rank r's closing code stores its updated rows -- and their row dots -- straight into replica[parity ^ 1][*] of EVERY
-// rank (peer-mapped memory over NVLink, own rank included) and, once all its rows are out, publishes the number of steps
-// it has completed in flags[*][r].  A step begins when this rank's own flag array shows that step for every rank.
+// rank (peer-mapped memory over NVLink, own rank included), then the number of the new state into the row's flag
+// flags[*][kMaxPeers + x] and, once all its rows are out, the number of steps it has completed into flags[*][r].  An item of
+// the next step starts when the rows its E phase reads have arrived (row_window), a closing when every rank has published.
+constexpr int kFlagWords(int G) { return kMaxPeers + G; }     // a rank's flag array: [kMaxPeers] steps per rank, [G] states per row
 struct ChunkedArgs {
     StepArgs step;             // the problem and its scratch (partial sums, scalars); C and N are set per step by the kernel
     int n_steps, parity, world, rank;
@@ -244,8 +246,9 @@ struct ChunkedArgs {
     double* replica[2][kMaxPeers];
     unsigned long long* flags[kMaxPeers];
     double* N;                 // [2] first moment, ping-pong with the replicas (every rank advances its own copy: no all-reduce)
-    const int2* items;         // (local row, chunk) in the order they are handed out: most expensive first
+    const int2* items;         // (local row, chunk) in the order they are handed out: rows ascending, a row's chunks by descending cost
     int n_items;
+    const int2* row_window;    // [G] first and last moment-grid row that the E phase of row x reads
     unsigned int* counters;    // zeroed before the launch: [0] item fetch counter, [1] rows closed, [2] prologue barrier,
                                // [3 + lx] chunk arrivals of local row lx; all monotone over the steps of the launch
     double* ring_pingpong;     // [2][local_rows * G] ring values of even / odd steps; all-ones NaN = not yet published

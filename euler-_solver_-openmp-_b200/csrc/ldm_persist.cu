@@ -187,19 +187,66 @@ __device__ __forceinline__ bool wait_for_ranks(const unsigned long long* flags, 
     return ok;
 }
 
+// Non-blocking form of wait_for_ranks (one warp): true when this rank's flag array already shows `need` steps for every rank.
+__device__ __forceinline__ bool ranks_have_published(const unsigned long long* flags, int world, unsigned long long need)
+{
+    const int r = threadIdx.x;
+    bool here = true;
+    if (r < world) {
+        unsigned long long seen;
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flags + r) : "memory");
+        here = seen >= need;
+    }
+    const bool all = __all_sync(0xffffffffu, here);
+    if (all && r < world) {
+        unsigned long long again;
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(again) : "l"(flags + r) : "memory");
+        here = again >= need;
+    }
+    return __all_sync(0xffffffffu, here);
+}
+
+// Spin (one warp) until rows lo..hi of state `need` have arrived in this rank's replica: the closing code of a row stores
+// the state's number into the row's flag on every rank behind a system fence.  Relaxed polls of local memory, one
+// acquiring fence per lane at the end; the CTA barrier that follows hands the ordering on to the other threads.
+__device__ __forceinline__ bool wait_for_rows(const unsigned long long* row_flags, int lo, int hi, unsigned long long need, int* status)
+{
+    bool ok = true;
+    Spin spin;
+    for (int r = lo + (int)threadIdx.x; r <= hi && ok; r += 32) {
+        unsigned long long seen;
+        for (;;) {
+            asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(row_flags + r) : "memory");
+            if (seen >= need) break;
+            if (spin.give_up(status)) { atomicCAS(status, kStatusOk, kStatusPeerTimeout); ok = false; break; }
+        }
+    }
+    asm volatile("fence.acq_rel.sys;" ::: "memory");
+    return !__any_sync(0xffffffffu, !ok);
+}
+
 // Persistent work-list kernel (cooperative launch, one CTA per SM or fewer): see ChunkedArgs in ldm_device.h.
-// Per step every CTA
-//   1. waits until every rank has published the previous step (own flag array, local polls),
-//   2. computes its share of the sparse ring correction of this rank's rows (CSR rows dealt out by entry count) and hands
-//      the values over without fences (ping-pong slots holding an all-ones NaN until written, as in persistent_scan_kernel),
-//   3. pulls (local row, chunk) items off a list ordered by cost -- one atomic per item, fetched under the item before --
-//      and runs scan_body on each; the chunk sums go to global memory, the row's arrival counter is bumped, and the CTA
-//      that brings the last chunk of a row CLOSES it: chunk sums added in chunk order, ring correction, closure, Euler
-//      update, clamp -- the arithmetic of finish_factored_kernel -- then the new row and its dot with the WC functional
-//      are stored into the next replica of every rank (peer stores over NVLink: the all-gather of SURVEY 8e, row by row,
-//      while the other rows are still being computed), one system fence per closing CTA,
-//   4. and whoever closes the rank's last row publishes the step in every rank's flag array.
-// No barrier anywhere but in the prologue: the flags of step k order everything of step k before anything of step k + 1.
+// The CTAs pull (step, local row, chunk) items off ONE list that runs through all steps of the launch -- rows in ascending
+// order, the chunks of a row by descending cost, one atomic per item, fetched under the item before -- and nothing but data
+// dependencies orders the steps:
+//   * an item of step k (state e = epoch + k -> e + 1) starts when the rows of state e that its E phase reads -- the window
+//     of moment-grid rows around x that the kernel's support reaches (ChunkedArgs::row_window) -- have arrived in this rank's
+//     replica (per-row flags), so the first rows of step k + 1 are under way while the last rows of step k are still being
+//     computed, closed and shipped, here and on the other ranks;
+//   * the chunk sums go to global memory, the row's arrival counter is bumped, and the CTA that brings the last chunk of a
+//     row CLOSES it.  A closing reads the whole state (WC, the ring correction), so it waits until every rank has
+//     published state e; then chunk sums in chunk order, ring correction, closure, Euler update, clamp -- the
+//     arithmetic of finish_factored_kernel -- and the new row and its dot with the WC functional are stored into the next
+//     replica of every rank (peer stores over NVLink: the all-gather of SURVEY 8e, row by row), one system fence, the row's
+//     flag on every rank; whoever closes the rank's last row of a step publishes the step in every rank's flag array;
+//   * the CTA's share of the sparse ring correction of state e (CSR rows dealt out by entry count; handed over without
+//     fences through ping-pong slots holding an all-ones NaN until written, as in persistent_scan_kernel) is computed at
+//     the first item boundary at which state e is complete, and at the latest before the CTA closes a row of step k or
+//     turns to an item of step k + 1 -- so every share of step k is out before anybody can wait for anything of state
+//     e + 1, and no wait can close a cycle.
+// A buffer is only ever rewritten by closings, a closing of step k + 1 needs state e + 1 complete, and every read of state
+// e (E phases, ring shares, closings of step k) precedes the flag that completes state e + 1: the two replicas, the one
+// set of chunk sums (row x lies in its own window) and the two halves of the ring hand-over suffice.
 template <bool SMALL, int U>
 __global__ void __launch_bounds__(SMALL ? 256 : kScanThreadsMax, SMALL ? 4 : 1)
 persistent_chunks_kernel(const ChunkedArgs A)
@@ -207,7 +254,7 @@ persistent_chunks_kernel(const ChunkedArgs A)
     const int NT = blockDim.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, warps = NT / 32;
     __shared__ double wc_shared;
     __shared__ unsigned int next_item[2];
-    __shared__ int closes_row, step_ok;
+    __shared__ int closes_row, gate;
     StepArgs S = A.step;
     const DevProblem& P = S.P;
     const int G = P.G, n_local = local_rows(P), chunks = P.scan_chunks, n = n_local * G;
@@ -217,8 +264,8 @@ persistent_chunks_kernel(const ChunkedArgs A)
     unsigned int* fetch_counter = A.counters;
     unsigned int* rows_closed = A.counters + 1;
     unsigned int* row_arrivals = A.counters + 3;
-    const unsigned long long* own_flags = A.flags[A.rank];
-    int parity = A.parity;
+    const unsigned long long* own_flags = A.flags[A.rank];                         // [kMaxPeers] steps published by every rank ...
+    const unsigned long long* own_row_flags = own_flags + kMaxPeers;               // ... then [G] newest state of every row that has arrived here
 
     // prologue: the state this launch starts from must be complete in this rank's replica; then the row dots of the WC
     // functional for it, all G rows on every rank (no exchange), dealt out over the warps of the grid
@@ -228,8 +275,8 @@ persistent_chunks_kernel(const ChunkedArgs A)
     }
     __syncthreads();
     {
-        const double* C0 = A.replica[parity][A.rank];
-        double* tail = A.replica[parity][A.rank] + A.words;
+        const double* C0 = A.replica[A.parity][A.rank];
+        double* tail = A.replica[A.parity][A.rank] + A.words;
         for (int xr = blockIdx.x * warps + warp; xr < G; xr += gridDim.x * warps) {
             const double s = wc_row_dot(P.wc_operator + (size_t)xr * G, C0 + (size_t)row_slot(P, xr) * G, G, lane);
             if (lane == 0) tail[xr] = s;
@@ -239,110 +286,157 @@ persistent_chunks_kernel(const ChunkedArgs A)
     if (!grid_barrier(A.counters + 2, 0, A.status)) return;
     unsigned int item = next_item[0];
     unsigned int turn = 0;                                                         // items this CTA has taken so far
+    const unsigned int total = (unsigned int)A.n_steps * (unsigned int)A.n_items;
+    int k = 0;                                                                     // the step `item` belongs to
+    unsigned int step_begin = 0;                                                   // its first item
+    int complete = 0;            // states epoch .. epoch + complete are known to be complete in this rank's replica
+    int ring_done = -1;          // newest step whose ring share this CTA has handed over
 
-    for (int k = 0; k < A.n_steps; k++) {
-        SCAN_MARK(10);
-        const unsigned long long done = A.epoch + (unsigned long long)k;           // steps every rank must have published
+    // this CTA's share of the ring correction of step kk (state epoch + kk must be complete here)
+    auto ring_share = [&](int kk) {
+        const double* C_of = A.replica[A.parity ^ (kk & 1)][A.rank];
+        double* slot = A.ring_pingpong + (size_t)(kk & 1) * n;
+        for (int row = A.ring_cta_begin[blockIdx.x] + warp; row < A.ring_cta_begin[blockIdx.x + 1]; row += warps) {
+            const double acc = ring_row_dot(P, C_of, row, lane);
+            if (lane == 0) publish_ring(slot + P.ring_point[row], acc);
+        }
+        ring_done = kk;
+    };
+    // all threads: wait until every rank has published state epoch + kk; false: a lost partner (status word set)
+    auto await_state = [&](int kk) -> bool {
+        if (complete >= kk) return true;
         if (tid < 32) {
-            const bool ok = wait_for_ranks(own_flags, A.world, done, A.status);
+            const bool ok = wait_for_ranks(own_flags, A.world, A.epoch + (unsigned long long)kk, A.status);
             const bool all = !__any_sync(0xffffffffu, !ok);
-            if (tid == 0) step_ok = all && load_status(A.status) == kStatusOk;
+            if (tid == 0) gate = all && load_status(A.status) == kStatusOk;
         }
         __syncthreads();
-        if (!step_ok) return;                                                      // a lost partner: the host reports the status word
+        const bool ok = gate != 0;
+        __syncthreads();                                                           // `gate` is rewritten by the next wait
+        if (ok) complete = kk;
+        return ok;
+    };
+
+    while (item < total) {
+        while (item >= step_begin + (unsigned int)A.n_items) { k++; step_begin += (unsigned int)A.n_items; }
+        SCAN_MARK(10);
+        // shares of earlier steps that this CTA still owes (it took no item boundary at which their state was complete)
+        while (ring_done < k - 1) {
+            if (!await_state(ring_done + 1)) return;
+            ring_share(ring_done + 1);
+        }
+        const int2 it = A.items[item - step_begin];                                // (local row, chunk)
+        const int lx = it.x;
+        const int x = P.rank + P.world * lx;
+        if (complete < k) {
+            // state epoch + k complete already?  Otherwise: the rows this item's E phase reads
+            if (tid < 32) {
+                int g = ranks_have_published(own_flags, A.world, A.epoch + (unsigned long long)k) ? 2 : 0;
+                if (g == 0) {
+                    const int2 w = A.row_window[x];
+                    g = wait_for_rows(own_row_flags, w.x, w.y, A.epoch + (unsigned long long)k, A.status) ? 1 : 0;
+                    if (load_status(A.status) != kStatusOk) g = 0;
+                }
+                if (tid == 0) gate = g;
+            }
+            __syncthreads();
+            const int g = gate;
+            __syncthreads();
+            if (g == 0) return;                                                    // a lost partner: the host reports the status word
+            if (g == 2) complete = k;
+        }
+        if (complete >= k && ring_done < k) ring_share(k);
+        const int parity = A.parity ^ (k & 1);
         double* const C_cur = A.replica[parity][A.rank];
         S.C = C_cur;
         S.N_cur = A.N + parity;
         S.N_next = A.N + (parity ^ 1);
-        const double* wc_tail = C_cur + A.words;
-        const long long point = A.first_point + k;
-        if (blockIdx.x == 0 && tid == 0 && A.observables) {
-            A.observables[2 * point] = S.N_cur[0];                                  // Values[k][0]       (Solver.cpp:1011)
-            A.observables[2 * point + 1] = C_cur[G - 1];                            // Values[k][G]       (Solver.cpp:1014); row 0 is slot 0
-        }
-        double* values_next = A.values ? A.values + (point + 1) * A.stride : nullptr;
-        double* derivs_here = A.derivs ? A.derivs + point * A.stride : nullptr;
-
-        // the ring share of this CTA
-        double* ring_slot = A.ring_pingpong + (size_t)(k & 1) * n;
-        for (int row = A.ring_cta_begin[blockIdx.x] + warp; row < A.ring_cta_begin[blockIdx.x + 1]; row += warps) {
-            const double acc = ring_row_dot(P, C_cur, row, lane);
-            if (lane == 0) publish_ring(ring_slot + P.ring_point[row], acc);
-        }
         SCAN_MARK(11);
 
-        const unsigned int step_end = (unsigned int)(k + 1) * (unsigned int)A.n_items;
-        while (item < step_end) {
-            const int2 it = A.items[item - (unsigned int)k * (unsigned int)A.n_items];   // (local row, chunk)
-            const int lx = it.x;
-            if (tid == 0) next_item[(turn + 1) & 1] = atomicAdd(fetch_counter, 1u);  // the next item, fetched under this one's work
-            scan_body_of<SMALL, U>(S, it.y, lx, true, -1);                           // chunk sums -> S.partial; ends with a CTA barrier
-            if (tid == 0) {
-                __threadfence();                                                     // the CTA's chunk sums, before the arrival
-                const unsigned int arrived = atomicAdd(row_arrivals + lx, 1u) + 1u;
-                __threadfence();                                                     // the other chunks' sums, after it
-                closes_row = arrived == (unsigned int)(k + 1) * (unsigned int)chunks;
-            }
-            __syncthreads();
-            turn++;
-            item = next_item[turn & 1];
-            if (!closes_row) continue;
+        if (tid == 0) next_item[(turn + 1) & 1] = atomicAdd(fetch_counter, 1u);      // the next item, fetched under this one's work
+        scan_body_of<SMALL, U>(S, it.y, lx, true, -1);                               // chunk sums -> S.partial; ends with a CTA barrier
+        if (tid == 0) {
+            __threadfence();                                                         // the CTA's chunk sums, before the arrival
+            const unsigned int arrived = atomicAdd(row_arrivals + lx, 1u) + 1u;
+            __threadfence();                                                         // the other chunks' sums, after it
+            closes_row = arrived == (unsigned int)(k + 1) * (unsigned int)chunks;
+        }
+        __syncthreads();
+        turn++;
+        item = next_item[turn & 1];
+        if (!closes_row) continue;
 
-            // ---- close local row lx: everything finish_factored_kernel does for it, same arithmetic ----
-            const int x = P.rank + P.world * lx;
-            if (warp == 0) {
-                const double t = wc_total(wc_tail, G, lane);
-                if (lane == 0) wc_shared = t;
+        // ---- close local row lx: everything finish_factored_kernel does for it, same arithmetic ----
+        if (!await_state(k)) return;
+        if (ring_done < k) ring_share(k);
+        const double* wc_tail = C_cur + A.words;
+        const long long point = A.first_point + k;
+        double* values_next = A.values ? A.values + (point + 1) * A.stride : nullptr;
+        double* derivs_here = A.derivs ? A.derivs + point * A.stride : nullptr;
+        double* ring_slot = A.ring_pingpong + (size_t)(k & 1) * n;
+        if (warp == 0) {
+            const double t = wc_total(wc_tail, G, lane);
+            if (lane == 0) wc_shared = t;
+        }
+        __syncthreads();
+        const double N = S.N_cur[0];
+        const double WC = __dmul_rn(add_outside(P, wc_shared, N, C_cur, S.scalars, P.wc_outside, 0.0), P.hh);   // Solver.cpp:311, 314
+        if (lx == 0 && tid == 0) {
+            first_moment_update(P, N, WC, S.dt, S.scalars, S.N_next);
+            if (values_next) values_next[0] = S.N_next[0];
+            if (derivs_here) derivs_here[0] = S.scalars[1];
+            if (A.observables && x == 0) {
+                A.observables[2 * point] = N;                                       // Values[k][0]       (Solver.cpp:1011)
+                A.observables[2 * point + 1] = C_cur[G - 1];                        // Values[k][G]       (Solver.cpp:1014); row 0 is slot 0
             }
-            __syncthreads();
-            const double N = S.N_cur[0];
-            const double WC = __dmul_rn(add_outside(P, wc_shared, N, C_cur, S.scalars, P.wc_outside, 0.0), P.hh);   // Solver.cpp:311, 314
-            if (lx == 0 && tid == 0) {
-                first_moment_update(P, N, WC, S.dt, S.scalars, S.N_next);
-                if (values_next) values_next[0] = S.N_next[0];
-                if (derivs_here) derivs_here[0] = S.scalars[1];
+        }
+        for (int y = tid; y < G; y += NT) {
+            const int ql = lx * G + y;
+            const int q = x * G + y;
+            double inside = 0.0;
+            for (int t = 0; t < chunks; t++) inside += __ldcg(S.partial + (size_t)t * n + ql);
+            const double ring_v = P.ring_present[ql] != 0 ? take_ring(ring_slot + ql, A.status) : 0.0;
+            inside -= ring_v;
+            const size_t slot = (size_t)(P.rank * P.rows_per_rank + lx) * G + y;   // this node in the gathered layout
+            const double c = C_cur[slot];
+            const double mc = __dmul_rn(add_outside(P, inside, N, C_cur, S.scalars, P.out_weight[q], 0.0), P.hh);
+            const double dc = second_moment_rhs(P, mc, c, N, WC, P.m_nodes[q], P.w_nodes[q]);
+            double v = __dadd_rn(c, __dmul_rn(dc, S.dt));                       // Solver.cpp:577
+            v = v < 0.0 ? 0.0 : v;                                              // Solver.cpp:578-580
+            for (int r = 0; r < A.world; r++) A.replica[parity ^ 1][r][slot] = v;   // the all-gather: NVLink peer stores
+            c_new[y] = v;
+            if (values_next) values_next[1 + q] = v;
+            if (derivs_here) derivs_here[1 + q] = dc;
+        }
+        __syncthreads();
+        if (warp == 0) {     // this row's dot with the WC functional for the next state, to every rank's tail
+            const double s = wc_row_dot(P.wc_operator + (size_t)x * G, c_new, G, lane);
+            if (lane == 0) {
+                for (int r = 0; r < A.world; r++) A.replica[parity ^ 1][r][A.words + x] = s;
             }
-            for (int y = tid; y < G; y += NT) {
-                const int ql = lx * G + y;
-                const int q = x * G + y;
-                double inside = 0.0;
-                for (int t = 0; t < chunks; t++) inside += __ldcg(S.partial + (size_t)t * n + ql);
-                const double ring_v = P.ring_present[ql] != 0 ? take_ring(ring_slot + ql, A.status) : 0.0;
-                inside -= ring_v;
-                const size_t slot = (size_t)(P.rank * P.rows_per_rank + lx) * G + y;   // this node in the gathered layout
-                const double c = C_cur[slot];
-                const double mc = __dmul_rn(add_outside(P, inside, N, C_cur, S.scalars, P.out_weight[q], 0.0), P.hh);
-                const double dc = second_moment_rhs(P, mc, c, N, WC, P.m_nodes[q], P.w_nodes[q]);
-                double v = __dadd_rn(c, __dmul_rn(dc, S.dt));                       // Solver.cpp:577
-                v = v < 0.0 ? 0.0 : v;                                              // Solver.cpp:578-580
-                for (int r = 0; r < A.world; r++) A.replica[parity ^ 1][r][slot] = v;   // the all-gather: NVLink peer stores
-                c_new[y] = v;
-                if (values_next) values_next[1 + q] = v;
-                if (derivs_here) derivs_here[1 + q] = dc;
-            }
-            __syncthreads();
-            if (warp == 0) {     // this row's dot with the WC functional for the next state, to every rank's tail
-                const double s = wc_row_dot(P.wc_operator + (size_t)x * G, c_new, G, lane);
-                if (lane == 0) {
-                    for (int r = 0; r < A.world; r++) A.replica[parity ^ 1][r][A.words + x] = s;
-                }
-            }
-            __syncthreads();
-            if (tid == 0) {
-                // release: ONE system fence per closing CTA, behind the CTA barrier (cumulative over what the barrier ordered
-                // before it); the CTA that closes the rank's last row publishes the step in every rank's flag array
+        }
+        __syncthreads();
+        if (tid == 0) {
+            // release: ONE system fence per closing CTA, behind the CTA barrier (cumulative over what the barrier ordered
+            // before it), then the row's flag on every rank; the CTA that closes the rank's last row of the step publishes
+            // the step in every rank's flag array
+            const unsigned long long state = A.epoch + (unsigned long long)k + 1ULL;
+            __threadfence_system();
+            for (int r = 0; r < A.world; r++)
+                asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(A.flags[r] + kMaxPeers + x), "l"(state) : "memory");
+            const unsigned int closed = atomicAdd(rows_closed, 1u) + 1u;
+            if (closed == (unsigned int)(k + 1) * (unsigned int)n_local) {
                 __threadfence_system();
-                const unsigned int closed = atomicAdd(rows_closed, 1u) + 1u;
-                if (closed == (unsigned int)(k + 1) * (unsigned int)n_local) {
-                    __threadfence_system();
-                    for (int r = 0; r < A.world; r++)
-                        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.flags[r] + A.rank), "l"(done + 1ULL) : "memory");
-                }
+                for (int r = 0; r < A.world; r++)
+                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.flags[r] + A.rank), "l"(state) : "memory");
             }
         }
         SCAN_MARK(8);
-        __syncthreads();           // step_ok is rewritten at the top of the next step
-        parity ^= 1;
+    }
+    // the shares this CTA still owes: the closings of the last steps wait for them
+    while (ring_done < A.n_steps - 1) {
+        if (!await_state(ring_done + 1)) return;
+        ring_share(ring_done + 1);
     }
 }
 

@@ -16,18 +16,33 @@ namespace ldm {
 
 namespace {
 
-// (local row, chunk) items of this rank in the order they are handed out: chunk by chunk, the chunk with the most y-side
-// work first (on a stretched grid the far chunks own twice the pairs of the near ones), all local rows of a chunk together
-// (they read the same y-side tables).  Dynamic hand-out in this order is longest-processing-time-first scheduling.
+// (local row, chunk) items of this rank in the order they are handed out: rows in ascending order -- so that rows close, and
+// ship, progressively and the next step's first rows find their windows complete while this step's last rows are still
+// under way -- and within a row the chunk with the most y-side work first (on a stretched grid the far chunks own twice the
+// pairs of the near ones).  Also the window of rows each row's E phase reads: the interpolation pairs of all its offsets.
 void ensure_items(ldm_context* c)
 {
     const DevProblem& d = c->dev;
+    if (!c->d_row_window) {
+        const std::vector<int>& upper = c->tables.axisM.upper;                    // [G][n_off]; 0: the sample lies beyond the grid
+        std::vector<int> window((size_t)2 * d.G);
+        for (int x = 0; x < d.G; x++) {
+            int lo = x, hi = x;                                                   // a row always waits for itself: its chunk sums and
+                                                                                  // arrival counter are reused step after step
+            for (int o = 0; o < d.n_off; o++) {
+                const int u = upper[(size_t)x * d.n_off + o];
+                if (u != 0) { lo = std::min(lo, u - 1); hi = std::max(hi, u); }
+            }
+            window[2 * (size_t)x] = lo; window[2 * (size_t)x + 1] = std::min(hi, d.G - 1);
+        }
+        c->d_row_window = reinterpret_cast<int2*>(c->upload(window));
+    }
     if (c->d_items && c->items_rank == d.rank && c->items_world == d.world) return;
     const int n_local = local_rows(d);
     std::vector<int> items;
     items.reserve((size_t)2 * n_local * d.scan_chunks);
-    for (int k = 0; k < d.scan_chunks; k++)
-        for (int lx = 0; lx < n_local; lx++) { items.push_back(lx); items.push_back(c->chunk_order_host[(size_t)k]); }
+    for (int lx = 0; lx < n_local; lx++)
+        for (int k = 0; k < d.scan_chunks; k++) { items.push_back(lx); items.push_back(c->chunk_order_host[(size_t)k]); }
     if (c->d_items) cudaFree(c->d_items);
     c->d_items = nullptr;
     LDM_CUDA(cudaMalloc((void**)&c->d_items, items.size() * sizeof(int)));
@@ -71,10 +86,10 @@ void peer_buffers_alloc(ldm_context* h)
         LDM_CUDA(cudaMalloc((void**)&h->peer_own[b], words * sizeof(double)));
         LDM_CUDA(cudaMemset(h->peer_own[b], 0, words * sizeof(double)));
     }
-    if (!h->peer_own_flags) LDM_CUDA(cudaMalloc((void**)&h->peer_own_flags, kMaxPeers * sizeof(unsigned long long)));
+    if (!h->peer_own_flags) LDM_CUDA(cudaMalloc((void**)&h->peer_own_flags, kFlagWords(h->dev.G) * sizeof(unsigned long long)));
     if (!h->peer_done) LDM_CUDA(cudaMalloc((void**)&h->peer_done, sizeof(unsigned int)));
     if (!h->peer_status) LDM_CUDA(cudaMalloc((void**)&h->peer_status, sizeof(int)));
-    LDM_CUDA(cudaMemset(h->peer_own_flags, 0, kMaxPeers * sizeof(unsigned long long)));
+    LDM_CUDA(cudaMemset(h->peer_own_flags, 0, kFlagWords(h->dev.G) * sizeof(unsigned long long)));
     LDM_CUDA(cudaMemset(h->peer_done, 0, sizeof(unsigned int)));
     LDM_CUDA(cudaMemset(h->peer_status, 0, sizeof(int)));
 }
@@ -130,6 +145,7 @@ void advance_chunked(ldm_context* c, int n_steps, double dt, cudaStream_t s, lon
     a.world = d.world; a.rank = d.rank;
     a.N = c->d_N;
     a.items = c->d_items; a.n_items = c->n_items;
+    a.row_window = c->d_row_window;
     a.counters = c->d_counters;
     a.ring_pingpong = c->d_ring2;
     a.ring_cta_begin = c->d_ring_cut;
@@ -313,7 +329,7 @@ int ldm_shard_peer_upload(ldm_handle h, const double* C_gathered, double N)
         const size_t words = (size_t)h->dev.world * h->dev.rows_per_rank * h->dev.G;
         LDM_CUDA(cudaDeviceSynchronize());
         LDM_CUDA(cudaMemcpy(h->peer_own[0], C_gathered, words * sizeof(double), cudaMemcpyHostToDevice));
-        LDM_CUDA(cudaMemset(h->peer_own_flags, 0, ldm::kMaxPeers * sizeof(unsigned long long)));
+        LDM_CUDA(cudaMemset(h->peer_own_flags, 0, ldm::kFlagWords(h->dev.G) * sizeof(unsigned long long)));
         LDM_CUDA(cudaMemset(h->peer_done, 0, sizeof(unsigned int)));
         LDM_CUDA(cudaMemset(h->peer_status, 0, sizeof(int)));
         LDM_CUDA(cudaMemset(h->d_status, 0, sizeof(int)));

@@ -35,7 +35,7 @@ def main():
             assert default is not None, f"{name} is not in the capture"
             return default
         value, unit = number(row[head.index(name)]), units[head.index(name)]
-        scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0, "nsecond": 1e-9}.get(unit, 1.0)
+        scale = {"Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "byte": 1.0, "usecond": 1e-6, "msecond": 1e-3, "second": 1.0, "nsecond": 1e-9, "us": 1e-6, "ms": 1e-3, "s": 1.0, "ns": 1e-9}.get(unit, 1.0)
         return value * scale
 
     from bench import source_sha
