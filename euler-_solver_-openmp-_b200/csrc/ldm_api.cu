@@ -98,6 +98,7 @@ void ensure_ring_operator(ldm_context* c)
     c->ring_entries = (long long)op.node.size();
     c->ring_samples = op.samples;
     c->ring_row_begin_host = op.row_begin;
+    c->ring_grid_row_begin_host = op.grid_row_begin;
     LDM_CUDA(cudaDeviceSynchronize());      // one-time setup: everything above is visible to every stream
 }
 
@@ -507,6 +508,7 @@ int ldm_tuning_set(const char* name, int value)
     else if (key == "scan") t.scan = value;
     else if (key == "chunk_grid") t.chunk_grid = value;
     else if (key == "batch_capacity") t.batch_capacity = value;
+    else if (key == "item_order") t.item_order = value;
     else return fail(LDM_ERR_ARGUMENT, "unknown tuning key");
     return LDM_OK;
 }

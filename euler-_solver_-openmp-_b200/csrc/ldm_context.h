@@ -70,6 +70,7 @@ struct ldm_context {
     unsigned long long peer_epoch = 0;
     int peer_parity = 0;
     bool peer_connected = false;
+    bool peer_solo = false;                // debug build only (ldm_debug_shard_solo): this rank steps alone, the others count as done
     int persistent_grid = 0;               // co-resident CTAs of the persistent kernel (0: not queried yet, -1: unavailable)
     bool persistent_enabled = true;
     // persistent work-list kernel (ldm_persist.cu persistent_chunks_kernel): rows of several chunks and the xi-sharded step
@@ -77,12 +78,16 @@ struct ldm_context {
     int chunk_grid_limit = 0;              // > 0: launch at most this many CTAs (ldm_tuning_set chunk_grid; two ranks on one device in tests)
     int2* d_items = nullptr;               // (local row, chunk) work list of the current (rank, world): rows ascending
     int2* d_row_window = nullptr;          // [G] rows that the E phase of row x reads (ChunkedArgs::row_window)
+    int4* d_block_window = nullptr;        // [G][blocks_per_row] ... per block of alphas (ChunkedArgs::block_window)
+    int blocks_per_row = 0;
     int n_items = 0;
     int items_rank = -1, items_world = -1;
     int* d_ring_cut = nullptr;             // [cut_grid + 1] ring CSR rows dealt out over the CTAs of a launch
     int cut_grid = 0, cut_rank = -1, cut_world = -1;
     std::vector<int> chunk_order_host;     // the column chunks by descending y-side work (DevProblem::scan_chunk_order)
     std::vector<int> ring_row_begin_host;  // CSR row starts of the current ring operator (to deal the rows out by entry count)
+    std::vector<int> ring_grid_row_begin_host;   // first CSR row of each local moment-grid row
+    int self_ring_rows = 0, self_ring_capacity = -1;   // ChunkedArgs: the leading light rows close with their own ring correction
     unsigned int* d_counters = nullptr;    // [3 + rows] ChunkedArgs::counters
     unsigned long long* d_flags = nullptr; // [kFlagWords(G)] one rank without peers: its own flag array
     unsigned long long local_epoch = 0;    // steps that kernel has taken on this handle outside a peer group

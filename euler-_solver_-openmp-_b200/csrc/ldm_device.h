@@ -249,10 +249,15 @@ struct ChunkedArgs {
     const int2* items;         // (local row, chunk) in the order they are handed out: rows ascending, a row's chunks by descending cost
     int n_items;
     const int2* row_window;    // [G] first and last moment-grid row that the E phase of row x reads
+    const int4* block_window;  // [G][blocks_per_row] the same per block of alphas that one thread group takes in one super-chunk of the E
+                               // phase (block = super-chunk * groups + group): rows lo..hi of the minus side, lo..hi of the plus side
+    int blocks_per_row;
     unsigned int* counters;    // zeroed before the launch: [0] item fetch counter, [1] rows closed, [2] prologue barrier,
                                // [3 + lx] chunk arrivals of local row lx; all monotone over the steps of the launch
     double* ring_pingpong;     // [2][local_rows * G] ring values of even / odd steps; all-ones NaN = not yet published
-    const int* ring_cta_begin; // [grid + 1] the ring CSR rows dealt out evenly by entry count over the CTAs of this launch
+    const int* ring_cta_begin; // [grid + 1] the ring CSR rows of the HEAVY grid rows dealt out evenly by entry count over the CTAs of this launch
+    int self_ring_rows;        // local rows lx < self_ring_rows are light: their closing CTA forms their ring correction itself (at most
+    int self_ring_capacity;    // self_ring_capacity entries per grid row, staged in the idle H tile); the rest goes through the shares
     int* status;
     // history, one rank only (may be NULL): as PersistentArgs
     long long first_point, stride;
@@ -260,6 +265,8 @@ struct ChunkedArgs {
     double* values;
     double* derivs;
 };
+// the E phase's block structure for this problem's CTA shape: alphas per block, thread groups, padded alpha count
+void chunk_block_shape(const DevProblem& P, int* alphas_per_block, int* groups, int* padded_alphas);
 // grid <= 0: only report the largest co-resident grid in *max_grid
 cudaError_t launch_persistent_chunks(const ChunkedArgs& args, int grid, cudaStream_t stream, int* max_grid);
 
@@ -286,6 +293,7 @@ struct Tuning {
     int scan = -1;                             // 0: never take the prefix-sum path
     int chunk_grid = 0;                        // persistent_chunks_kernel: CTAs per launch (tests run two ranks on one device)
     int batch_capacity = 0;                    // persistent_batch_kernel: CTA budget of a launch (tests: several waves of sets)
+    int item_order = 0;                        // persistent_chunks_kernel, experiments: 0 rows ascending (default), 1 chunk by chunk, 2 rows descending
 };
 Tuning& tuning();
 

@@ -242,7 +242,7 @@ finish_factored_kernel(const StepArgs one, const StepArgs* __restrict__ batch)
                 *S.done_counter = 0u;
                 __threadfence_system();
                 for (int r = 0; r < S.peer_count; r++)
-                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(S.peer_flags[r] + P.rank), "l"(S.epoch) : "memory");
+                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(S.peer_flags[r] + P.rank), "l"(S.epoch) : "memory");
             }
         }
     }

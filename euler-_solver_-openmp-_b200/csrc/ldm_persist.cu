@@ -17,6 +17,27 @@ namespace ldm {
 
 namespace {
 
+// Optional event trace of the work-list kernel (debug build `make phase-clocks`; tools/chunk_trace.py): thread 0 of every CTA
+// logs (globaltimer, event, step, local row, chunk).  Off in the product build.
+#ifdef LDM_PHASE_CLOCKS
+constexpr int kTraceCtas = 148, kTraceEvents = 4096;
+__device__ ulonglong2 g_trace[kTraceCtas][kTraceEvents];
+__device__ unsigned int g_trace_n[kTraceCtas];
+__device__ __forceinline__ void trace_event(int type, int k, int lx, int chunk)
+{
+    if (threadIdx.x != 0 || blockIdx.x >= kTraceCtas) return;
+    const unsigned int n = g_trace_n[blockIdx.x];
+    if (n >= kTraceEvents) return;
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    g_trace[blockIdx.x][n] = make_ulonglong2(t, ((unsigned long long)type << 48) | ((unsigned long long)(k & 0xffff) << 32) | ((unsigned long long)(lx & 0xffff) << 16) | (unsigned long long)(chunk & 0xffff));
+    g_trace_n[blockIdx.x] = n + 1;
+}
+#define TRACE(type, k, lx, chunk) trace_event(type, k, lx, chunk)
+#else
+#define TRACE(type, k, lx, chunk) do { } while (0)
+#endif
+
 // Persistent multi-step kernel (cooperative launch, one CTA per moment-grid row): all Euler steps of a solve inside one
 // launch, for grids whose rows are one chunk each.  Per step every CTA
 //   1. sums the G row dots of the WC functional (written by the closing phases of the step before),
@@ -225,6 +246,64 @@ __device__ __forceinline__ bool wait_for_rows(const unsigned long long* row_flag
     return !__any_sync(0xffffffffu, !ok);
 }
 
+// The gate of an item that starts before its state is complete (scan_body's Gate): before a thread group requests the rows of
+// C that its next block of alphas reads, its warps wait -- each for itself, lanes striding the rows -- until those rows have
+// arrived.  The item's E phase then follows the closings of the step before it row by row instead of waiting for the last
+// row of its window, and the rows are requested past L1 (no L1 invalidation on this SM lies between their arrival and the
+// loads; the relaxed poll of a flag that the writer stored behind its system fence orders the L2 reads that follow it).
+struct RowGate {
+    const unsigned long long* row_flags;   // this rank's
+    const int4* blocks;                    // this row's windows, [super-chunk * groups + group]: rows lo..hi of the minus side, of the plus side
+    unsigned long long need;
+    int* status;
+    int groups, bn, super_chunks;
+    bool active;
+    // the flags of the next block are requested one super-chunk ahead, so that a block whose rows are already there costs
+    // no round trip to L2 (lane l holds the flags of row lo + l on either side)
+    unsigned long long ahead_minus = 0, ahead_plus = 0;
+    int ahead_of = -1;
+
+    __device__ bool bypass() const { return active; }
+    __device__ static unsigned long long peek(const unsigned long long* flag)
+    {
+        unsigned long long seen;
+        asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(flag) : "memory");
+        return seen;
+    }
+    __device__ void request(int sc)
+    {
+        const int lane = threadIdx.x & 31;
+        const int4 w = blocks[sc * groups + (int)threadIdx.x / bn];
+        ahead_minus = ~0ULL; ahead_plus = ~0ULL;
+        if (w.x + lane <= w.y) ahead_minus = peek(row_flags + w.x + lane);
+        if (w.z + lane <= w.w) ahead_plus = peek(row_flags + w.z + lane);
+        ahead_of = sc;
+    }
+    __device__ void operator()(int sc)
+    {
+        if (!active) return;
+        const int lane = threadIdx.x & 31;
+        if (ahead_of != sc) request(sc);
+        const int4 w = blocks[sc * groups + (int)threadIdx.x / bn];
+        Spin spin;
+        bool ok = true;
+        #pragma unroll 1
+        for (int side = 0; side < 2 && ok; side++) {
+            const int lo = side == 0 ? w.x : w.z, hi = side == 0 ? w.y : w.w;
+            unsigned long long seen = side == 0 ? ahead_minus : ahead_plus;    // of row lo + lane (all ones: none)
+            for (int r = lo + lane; r <= hi && ok; r += 32) {
+                while (seen < need) {
+                    if (spin.give_up(status)) { atomicCAS(status, kStatusOk, kStatusPeerTimeout); ok = false; break; }
+                    seen = peek(row_flags + r);
+                }
+                if (r + 32 <= hi) seen = peek(row_flags + r + 32);
+            }
+        }
+        __syncwarp();
+        if (sc + 1 < super_chunks) request(sc + 1);
+    }
+};
+
 // Persistent work-list kernel (cooperative launch, one CTA per SM or fewer): see ChunkedArgs in ldm_device.h.
 // The CTAs pull (step, local row, chunk) items off ONE list that runs through all steps of the launch -- rows in ascending
 // order, the chunks of a row by descending cost, one atomic per item, fetched under the item before -- and nothing but data
@@ -301,6 +380,7 @@ persistent_chunks_kernel(const ChunkedArgs A)
             if (lane == 0) publish_ring(slot + P.ring_point[row], acc);
         }
         ring_done = kk;
+        TRACE(7, kk, 0, 0);
     };
     // all threads: wait until every rank has published state epoch + kk; false: a lost partner (status word set)
     auto await_state = [&](int kk) -> bool {
@@ -320,6 +400,7 @@ persistent_chunks_kernel(const ChunkedArgs A)
     while (item < total) {
         while (item >= step_begin + (unsigned int)A.n_items) { k++; step_begin += (unsigned int)A.n_items; }
         SCAN_MARK(10);
+        TRACE(1, k, 0, 0);
         // shares of earlier steps that this CTA still owes (it took no item boundary at which their state was complete)
         while (ring_done < k - 1) {
             if (!await_state(ring_done + 1)) return;
@@ -328,13 +409,29 @@ persistent_chunks_kernel(const ChunkedArgs A)
         const int2 it = A.items[item - step_begin];                                // (local row, chunk)
         const int lx = it.x;
         const int x = P.rank + P.world * lx;
+        bool gated = false;
         if (complete < k) {
-            // state epoch + k complete already?  Otherwise: the rows this item's E phase reads
+            // state epoch + k complete already?  Otherwise the item goes ahead behind a gate (RowGate) as soon as the step
+            // before has closed this very row: its chunk sums and arrival counter are reused step after step
             if (tid < 32) {
                 int g = ranks_have_published(own_flags, A.world, A.epoch + (unsigned long long)k) ? 2 : 0;
                 if (g == 0) {
+                    // every row of the item's window here already?  (one round of independent polls.)  Then the item runs like any
+                    // other.  Otherwise it goes ahead behind the gate once the step before has closed this very row (a shape
+                    // whose block windows do not fit the row buffers waits for the whole window instead).
+                    const unsigned long long need = A.epoch + (unsigned long long)k;
                     const int2 w = A.row_window[x];
-                    g = wait_for_rows(own_row_flags, w.x, w.y, A.epoch + (unsigned long long)k, A.status) ? 1 : 0;
+                    bool here = true;
+                    for (int r = w.x + tid; r <= w.y; r += 32) here = here && RowGate::peek(own_row_flags + r) >= need;
+                    const bool can_gate = A.blocks_per_row <= L.part_stride;
+                    if (__all_sync(0xffffffffu, here)) {
+                        asm volatile("fence.acq_rel.sys;" ::: "memory");
+                        g = 3;
+                    } else if (can_gate) {
+                        g = wait_for_rows(own_row_flags, x, x, need, A.status) ? 1 : 0;
+                    } else {
+                        g = wait_for_rows(own_row_flags, w.x, w.y, need, A.status) ? 3 : 0;
+                    }
                     if (load_status(A.status) != kStatusOk) g = 0;
                 }
                 if (tid == 0) gate = g;
@@ -344,17 +441,45 @@ persistent_chunks_kernel(const ChunkedArgs A)
             __syncthreads();
             if (g == 0) return;                                                    // a lost partner: the host reports the status word
             if (g == 2) complete = k;
+            gated = g == 1;
         }
         if (complete >= k && ring_done < k) ring_share(k);
+        // the same check between the two phases of the item and behind it: a share that comes an item late keeps the
+        // closings of this step waiting (take_ring), and with them everything that depends on the rows they publish
+        auto ring_if_complete = [&]() {
+            if (ring_done >= k) return;
+            if (complete < k) {
+                if (tid < 32) {
+                    const bool all = ranks_have_published(own_flags, A.world, A.epoch + (unsigned long long)k);
+                    if (tid == 0) gate = all ? 1 : 0;
+                }
+                __syncthreads();
+                const int g = gate;
+                __syncthreads();
+                if (g == 0) return;
+                complete = k;
+            }
+            ring_share(k);
+        };
         const int parity = A.parity ^ (k & 1);
         double* const C_cur = A.replica[parity][A.rank];
         S.C = C_cur;
         S.N_cur = A.N + parity;
         S.N_next = A.N + (parity ^ 1);
         SCAN_MARK(11);
+        TRACE(2, k, lx, it.y);
 
         if (tid == 0) next_item[(turn + 1) & 1] = atomicAdd(fetch_counter, 1u);      // the next item, fetched under this one's work
-        scan_body_of<SMALL, U>(S, it.y, lx, true, -1);                               // chunk sums -> S.partial; ends with a CTA barrier
+        // the row's block windows, from shared memory (the closing's row buffers are idle while an item runs)
+        int4* const windows = reinterpret_cast<int4*>(scan_smem + L.rowbuf);
+        if (gated) {
+            for (int b = tid; b < A.blocks_per_row; b += NT) windows[b] = A.block_window[(size_t)x * A.blocks_per_row + b];
+            __syncthreads();
+        }
+        const RowGate row_gate{own_row_flags, windows, A.epoch + (unsigned long long)k, A.status, L.ng, P.scan_bn, A.blocks_per_row / L.ng, gated};
+        scan_body_of<SMALL, U>(S, it.y, lx, true, -1, false, ring_if_complete, row_gate);   // chunk sums -> S.partial; ends with a CTA barrier
+        ring_if_complete();
+        TRACE(3, k, lx, it.y);
         if (tid == 0) {
             __threadfence();                                                         // the CTA's chunk sums, before the arrival
             const unsigned int arrived = atomicAdd(row_arrivals + lx, 1u) + 1u;
@@ -367,8 +492,73 @@ persistent_chunks_kernel(const ChunkedArgs A)
         if (!closes_row) continue;
 
         // ---- close local row lx: everything finish_factored_kernel does for it, same arithmetic ----
+        // What does not need the complete state comes first, so that it flies while the state completes: the ring correction
+        // of a light row (its samples read rows of the row's own window, which the E phases have waited for) and the
+        // operands of the closure.  Behind the wait there is one round of loads (WC row dots, N) between the CTA and its stores.
+        TRACE(4, k, lx, 0);
+        double* const scratch = reinterpret_cast<double*>(scan_smem + L.hs);         // the H tile is free between items
+        double* const ring_buf = c_new + L.part_stride;                              // [G] ring correction of a light row
+        const bool self_ring = lx < A.self_ring_rows;
+        const int cr0 = P.ring_row_begin[lx], cr1 = P.ring_row_begin[lx + 1];
+        const int e0 = P.ring_begin[cr0], n_entries = self_ring ? P.ring_begin[cr1] - e0 : 0;
+        const bool staged = A.self_ring_capacity >= 0;                                // the tile has room for the staging (tiny tables: no)
+        const int capacity = staged ? A.self_ring_capacity : 0;
+        double* const gathered = scratch;                                             // [n_entries] C at the entries' nodes
+        double* const weights = scratch + capacity;                                   // [n_entries]
+        double* const op_stage = scratch + 2 * capacity;                              // [G] this row of the WC functional
+        const double* const op_row = staged ? op_stage : P.wc_operator + (size_t)x * G;
+        {
+            constexpr int kStage = 8;                                                 // entries per thread in flight (capacity 4096 = 8 x 512)
+            for (int first = 0; first < n_entries; first += NT * kStage) {
+                int node[kStage];
+                double value[kStage], weight[kStage];
+                #pragma unroll
+                for (int j = 0; j < kStage; j++) {
+                    const int e = first + tid + j * NT;
+                    node[j] = e < n_entries ? P.ring_node[e0 + e] : -1;
+                    weight[j] = e < n_entries ? P.ring_weight[e0 + e] : 0.0;
+                }
+                #pragma unroll
+                for (int j = 0; j < kStage; j++) value[j] = node[j] >= 0 ? C_cur[node[j]] : 0.0;
+                #pragma unroll
+                for (int j = 0; j < kStage; j++) {
+                    const int e = first + tid + j * NT;
+                    if (e < n_entries) { gathered[e] = value[j]; weights[e] = weight[j]; }
+                }
+            }
+        }
+        for (int y = tid; y < G; y += NT) {
+            if (staged) op_stage[y] = P.wc_operator[(size_t)x * G + y];
+            if (self_ring) ring_buf[y] = 0.0;
+        }
+        constexpr int kPre = 2;                                                       // nodes per thread whose operands are requested ahead
+        const bool ahead = G <= kPre * NT;
+        double pre_sum[kPre], pre_c[kPre], pre_ow[kPre], pre_mn[kPre], pre_wn[kPre];
+        #pragma unroll
+        for (int j = 0; j < kPre; j++) {
+            const int y = tid + j * NT;
+            pre_sum[j] = 0.0; pre_c[j] = 0.0; pre_ow[j] = 0.0; pre_mn[j] = 0.0; pre_wn[j] = 0.0;
+            if (ahead && y < G) {
+                #pragma unroll 8
+                for (int t = 0; t < chunks; t++) pre_sum[j] += __ldcg(S.partial + (size_t)t * n + lx * G + y);
+                pre_c[j] = C_cur[(size_t)(P.rank * P.rows_per_rank + lx) * G + y];
+                pre_ow[j] = P.out_weight[(size_t)x * G + y]; pre_mn[j] = P.m_nodes[(size_t)x * G + y]; pre_wn[j] = P.w_nodes[(size_t)x * G + y];
+            }
+        }
+        __syncthreads();
+        if (self_ring) {
+            // the dots in the order of ring_row_dot / ring_kernel (lanes stride the entries, fma in entry order, butterfly)
+            for (int row = cr0 + warp; row < cr1; row += warps) {
+                const int b = P.ring_begin[row] - e0, e = P.ring_begin[row + 1] - e0;
+                double acc = 0.0;
+                for (int en = b + lane; en < e; en += 32) acc = fma(weights[en], gathered[en], acc);
+                acc = warp_sum(acc);
+                if (lane == 0) ring_buf[P.ring_point[row] - lx * G] = acc;
+            }
+        }
         if (!await_state(k)) return;
         if (ring_done < k) ring_share(k);
+        TRACE(5, k, lx, 0);
         const double* wc_tail = C_cur + A.words;
         const long long point = A.first_point + k;
         double* values_next = A.values ? A.values + (point + 1) * A.stride : nullptr;
@@ -378,7 +568,7 @@ persistent_chunks_kernel(const ChunkedArgs A)
             const double t = wc_total(wc_tail, G, lane);
             if (lane == 0) wc_shared = t;
         }
-        __syncthreads();
+        __syncthreads();                                                             // also: ring_buf is complete
         const double N = S.N_cur[0];
         const double WC = __dmul_rn(add_outside(P, wc_shared, N, C_cur, S.scalars, P.wc_outside, 0.0), P.hh);   // Solver.cpp:311, 314
         if (lx == 0 && tid == 0) {
@@ -390,27 +580,38 @@ persistent_chunks_kernel(const ChunkedArgs A)
                 A.observables[2 * point + 1] = C_cur[G - 1];                        // Values[k][G]       (Solver.cpp:1014); row 0 is slot 0
             }
         }
-        for (int y = tid; y < G; y += NT) {
+        auto close_node = [&](int y, double inside, double c, double ow, double mn, double wn) {
             const int ql = lx * G + y;
             const int q = x * G + y;
-            double inside = 0.0;
-            for (int t = 0; t < chunks; t++) inside += __ldcg(S.partial + (size_t)t * n + ql);
-            const double ring_v = P.ring_present[ql] != 0 ? take_ring(ring_slot + ql, A.status) : 0.0;
+            const double ring_v = self_ring ? ring_buf[y] : (P.ring_present[ql] != 0 ? take_ring(ring_slot + ql, A.status) : 0.0);
             inside -= ring_v;
             const size_t slot = (size_t)(P.rank * P.rows_per_rank + lx) * G + y;   // this node in the gathered layout
-            const double c = C_cur[slot];
-            const double mc = __dmul_rn(add_outside(P, inside, N, C_cur, S.scalars, P.out_weight[q], 0.0), P.hh);
-            const double dc = second_moment_rhs(P, mc, c, N, WC, P.m_nodes[q], P.w_nodes[q]);
-            double v = __dadd_rn(c, __dmul_rn(dc, S.dt));                       // Solver.cpp:577
-            v = v < 0.0 ? 0.0 : v;                                              // Solver.cpp:578-580
+            const double mc = __dmul_rn(add_outside(P, inside, N, C_cur, S.scalars, ow, 0.0), P.hh);
+            const double dc = second_moment_rhs(P, mc, c, N, WC, mn, wn);
+            double v = __dadd_rn(c, __dmul_rn(dc, S.dt));                           // Solver.cpp:577
+            v = v < 0.0 ? 0.0 : v;                                                  // Solver.cpp:578-580
             for (int r = 0; r < A.world; r++) A.replica[parity ^ 1][r][slot] = v;   // the all-gather: NVLink peer stores
             c_new[y] = v;
             if (values_next) values_next[1 + q] = v;
             if (derivs_here) derivs_here[1 + q] = dc;
+        };
+        if (ahead) {
+            #pragma unroll
+            for (int j = 0; j < kPre; j++) {
+                const int y = tid + j * NT;
+                if (y < G) close_node(y, pre_sum[j], pre_c[j], pre_ow[j], pre_mn[j], pre_wn[j]);
+            }
+        } else {
+            for (int y = tid; y < G; y += NT) {
+                double inside = 0.0;
+                for (int t = 0; t < chunks; t++) inside += __ldcg(S.partial + (size_t)t * n + lx * G + y);
+                close_node(y, inside, C_cur[(size_t)(P.rank * P.rows_per_rank + lx) * G + y], P.out_weight[(size_t)x * G + y],
+                           P.m_nodes[(size_t)x * G + y], P.w_nodes[(size_t)x * G + y]);
+            }
         }
         __syncthreads();
         if (warp == 0) {     // this row's dot with the WC functional for the next state, to every rank's tail
-            const double s = wc_row_dot(P.wc_operator + (size_t)x * G, c_new, G, lane);
+            const double s = wc_row_dot(op_row, c_new, G, lane);
             if (lane == 0) {
                 for (int r = 0; r < A.world; r++) A.replica[parity ^ 1][r][A.words + x] = s;
             }
@@ -420,18 +621,22 @@ persistent_chunks_kernel(const ChunkedArgs A)
             // release: ONE system fence per closing CTA, behind the CTA barrier (cumulative over what the barrier ordered
             // before it), then the row's flag on every rank; the CTA that closes the rank's last row of the step publishes
             // the step in every rank's flag array
+            // (a system fence takes ~4 us on this machine -- measured with tools/chunk_trace.py: eight releasing stores, each
+            // with its own fence, kept every step's completion waiting for 30 us -- so the flags are relaxed stores behind ONE
+            // fence, and one rank alone fences at device scope)
             const unsigned long long state = A.epoch + (unsigned long long)k + 1ULL;
-            __threadfence_system();
+            if (A.world == 1) __threadfence(); else __threadfence_system();
             for (int r = 0; r < A.world; r++)
                 asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(A.flags[r] + kMaxPeers + x), "l"(state) : "memory");
             const unsigned int closed = atomicAdd(rows_closed, 1u) + 1u;
             if (closed == (unsigned int)(k + 1) * (unsigned int)n_local) {
-                __threadfence_system();
+                if (A.world == 1) __threadfence(); else __threadfence_system();   // behind the other closers' fences and arrivals
                 for (int r = 0; r < A.world; r++)
-                    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(A.flags[r] + A.rank), "l"(state) : "memory");
+                    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(A.flags[r] + A.rank), "l"(state) : "memory");
             }
         }
         SCAN_MARK(8);
+        TRACE(6, k, lx, 0);
     }
     // the shares this CTA still owes: the closings of the last steps wait for them
     while (ring_done < A.n_steps - 1) {
@@ -578,6 +783,14 @@ cudaError_t launch_persistent_scan(const PersistentArgs& args, int grid, cudaStr
     return cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(nt), params, smem, stream);
 }
 
+void chunk_block_shape(const DevProblem& P, int* alphas_per_block, int* groups, int* padded_alphas)
+{
+    const ScanLayout L = scan_layout(P.G, P.A, P.scan_bn, P.scan_nt, P.scan_max_pieces);
+    *alphas_per_block = scan_unroll(P.scan_nt, P.A, L.ng);
+    *groups = L.ng;
+    *padded_alphas = L.a_pad;
+}
+
 cudaError_t launch_persistent_chunks(const ChunkedArgs& args, int grid, cudaStream_t stream, int* max_grid)
 {
     const DevProblem& P = args.step.P;
@@ -619,6 +832,20 @@ cudaError_t launch_persistent_batch(const BatchArgs& args, int grid, int nt, siz
 }
 
 #ifdef LDM_PHASE_CLOCKS
+extern "C" LDM_API int ldm_debug_trace_reset()
+{
+    cudaDeviceSynchronize();
+    void* p = nullptr;
+    if (cudaGetSymbolAddress(&p, g_trace_n) != cudaSuccess) return 1;
+    return (int)cudaMemset(p, 0, sizeof(unsigned int) * kTraceCtas);
+}
+// events: [148][4096][2] 64-bit words (globaltimer ns; type << 48 | step << 32 | local row << 16 | chunk), counts: [148]
+extern "C" LDM_API int ldm_debug_trace_read(unsigned long long* events, unsigned int* counts)
+{
+    cudaDeviceSynchronize();
+    if (cudaMemcpyFromSymbol(counts, g_trace_n, sizeof(unsigned int) * kTraceCtas) != cudaSuccess) return 1;
+    return (int)cudaMemcpyFromSymbol(events, g_trace, sizeof(ulonglong2) * kTraceCtas * kTraceEvents);
+}
 extern "C" LDM_API int ldm_debug_persist_clocks(long long* out, int rows)
 {
     cudaDeviceSynchronize();

@@ -200,10 +200,17 @@ __device__ __forceinline__ double y_side_interval(const DevProblem& P, const dou
 // `mid` runs between the two phases (the persistent kernel requests there what its closing phase will need, so that
 // those loads fly under the y side).
 struct NoMid { __device__ void operator()() const {} };
+// `gate(sc)` runs in every thread before the rows of C that super-chunk sc of the E phase reads are requested (the work-list
+// kernel waits there, warp by warp, until those rows of the state have arrived: persistent_chunks_kernel); gate.bypass():
+// request them past L1 (rows that arrive while the item runs were never covered by an L1 invalidation on this SM).
+struct NoGate {
+    __device__ void operator()(int) const {}
+    __device__ bool bypass() const { return false; }
+};
 
-template <int kScanUnroll, typename Mid = NoMid>
+template <int kScanUnroll, typename Mid = NoMid, typename Gate = NoGate>
 __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, const int lx, const bool build_tables,
-                                          const int cached_w_rows, const bool fused = false, Mid mid = Mid())
+                                          const int cached_w_rows, const bool fused = false, Mid mid = Mid(), Gate gate = Gate())
 {
     const int NT = blockDim.x;                             // = ng * bn; scan_unroll(NT, A, ng) == kScanUnroll
     const DevProblem& P = S.P;
@@ -295,8 +302,17 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
                 raw[k][0] = c[(unsigned)ra.x]; raw[k][1] = c[(unsigned)ra.y]; raw[k][2] = c[(unsigned)ra.z]; raw[k][3] = c[(unsigned)ra.w];   // unsigned: one IMAD.WIDE.U32 per address
             }
         };
+        auto issue_past_l1 = [&](int sc) {
+            #pragma unroll
+            for (int k = 0; k < kScanUnroll; k++) {
+                const int4 ra = *reinterpret_cast<const int4*>(tap_row + (sc * span + grp * kScanUnroll + k) * 4);
+                raw[k][0] = __ldcg(c + (unsigned)ra.x); raw[k][1] = __ldcg(c + (unsigned)ra.y); raw[k][2] = __ldcg(c + (unsigned)ra.z); raw[k][3] = __ldcg(c + (unsigned)ra.w);
+            }
+        };
+        const bool past_l1 = gate.bypass();
         if (active) {
-            issue(0);
+            gate(0);
+            if (past_l1) issue_past_l1(0); else issue(0);
             for (int sc = 0; sc < n_sc; sc++) {
                 double prefix[kScanUnroll];
                 double* mine = bsum + (sc & 1) * L.ng * bn;
@@ -308,7 +324,10 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
                     prefix[k] = run;
                 }
                 mine[grp * bn + col] = run;
-                if (sc + 1 < n_sc) issue(sc + 1);
+                if (sc + 1 < n_sc) {
+                    gate(sc + 1);
+                    if (past_l1) issue_past_l1(sc + 1); else issue(sc + 1);
+                }
                 asm volatile("bar.sync %0, %1;" ::"r"(set_id), "r"(set_threads) : "memory");
                 double before = 0.0, all = 0.0;
                 for (int g = 0; g < L.ng; g++) {             // fixed order
@@ -380,15 +399,15 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
 // scan_body with the unroll factor of this CTA shape: U = 4 or 5 when the launch picked the kernel instance by it (the
 // single-problem kernels: each instance keeps its own register allocation), U = 0 to decide here by a uniform branch (batch
 // launches, whose members may differ)
-template <bool SMALL, int U, typename Mid = NoMid>
+template <bool SMALL, int U, typename Mid = NoMid, typename Gate = NoGate>
 __device__ __forceinline__ void scan_body_of(const StepArgs& S, const int chunk, const int lx, const bool build_tables,
-                                             const int cached_w_rows, const bool fused = false, Mid mid = Mid())
+                                             const int cached_w_rows, const bool fused = false, Mid mid = Mid(), Gate gate = Gate())
 {
-    if (SMALL) { scan_body<2>(S, chunk, lx, build_tables, cached_w_rows, fused, mid); return; }
-    if (U != 0) { scan_body<(U == 0 ? 4 : U)>(S, chunk, lx, build_tables, cached_w_rows, fused, mid); return; }
+    if (SMALL) { scan_body<2>(S, chunk, lx, build_tables, cached_w_rows, fused, mid, gate); return; }
+    if (U != 0) { scan_body<(U == 0 ? 4 : U)>(S, chunk, lx, build_tables, cached_w_rows, fused, mid, gate); return; }
     const int ng = (int)blockDim.x / S.P.scan_bn > 1 ? (int)blockDim.x / S.P.scan_bn : 1;
-    if (scan_unroll((int)blockDim.x, S.P.A, ng) == 5) scan_body<5>(S, chunk, lx, build_tables, cached_w_rows, fused, mid);
-    else scan_body<4>(S, chunk, lx, build_tables, cached_w_rows, fused, mid);
+    if (scan_unroll((int)blockDim.x, S.P.A, ng) == 5) scan_body<5>(S, chunk, lx, build_tables, cached_w_rows, fused, mid, gate);
+    else scan_body<4>(S, chunk, lx, build_tables, cached_w_rows, fused, mid, gate);
 }
 
 // ---- hand-overs between CTAs (persistent kernels) ----

@@ -36,13 +36,38 @@ void ensure_items(ldm_context* c)
             window[2 * (size_t)x] = lo; window[2 * (size_t)x + 1] = std::min(hi, d.G - 1);
         }
         c->d_row_window = reinterpret_cast<int2*>(c->upload(window));
+        // the same per block of alphas: an item that starts before the state is complete waits block by block
+        int U = 0, ng = 0, a_pad = 0;
+        chunk_block_shape(d, &U, &ng, &a_pad);
+        const int blocks = a_pad / U, n_fold = d.n_off / d.A;
+        std::vector<int> bw((size_t)4 * d.G * blocks);
+        for (int x = 0; x < d.G; x++)
+            for (int b = 0; b < blocks; b++) {
+                int range[2][2] = {{d.G, -1}, {d.G, -1}};                         // empty: lo > hi
+                for (int alpha = b * U; alpha < std::min((b + 1) * U, d.A); alpha++)
+                    for (int f = 0; f < n_fold; f++) {
+                        const int o = n_fold == 1 ? 0 : (f == 0 ? d.A - 1 - alpha : d.A + alpha);
+                        const int u = upper[(size_t)x * d.n_off + o];
+                        if (u != 0) { range[f][0] = std::min(range[f][0], u - 1); range[f][1] = std::max(range[f][1], u); }
+                    }
+                int* out = &bw[((size_t)x * blocks + b) * 4];
+                out[0] = range[0][0]; out[1] = range[0][1]; out[2] = range[1][0]; out[3] = range[1][1];
+            }
+        c->d_block_window = reinterpret_cast<int4*>(c->upload(bw));
+        c->blocks_per_row = blocks;
     }
     if (c->d_items && c->items_rank == d.rank && c->items_world == d.world) return;
     const int n_local = local_rows(d);
     std::vector<int> items;
     items.reserve((size_t)2 * n_local * d.scan_chunks);
-    for (int lx = 0; lx < n_local; lx++)
-        for (int k = 0; k < d.scan_chunks; k++) { items.push_back(lx); items.push_back(c->chunk_order_host[(size_t)k]); }
+    const int order = tuning().item_order;
+    if (order == 1) {
+        for (int k = 0; k < d.scan_chunks; k++)
+            for (int lx = 0; lx < n_local; lx++) { items.push_back(lx); items.push_back(c->chunk_order_host[(size_t)k]); }
+    } else {
+        for (int i = 0; i < n_local; i++)
+            for (int k = 0; k < d.scan_chunks; k++) { items.push_back(order == 2 ? n_local - 1 - i : i); items.push_back(c->chunk_order_host[(size_t)k]); }
+    }
     if (c->d_items) cudaFree(c->d_items);
     c->d_items = nullptr;
     LDM_CUDA(cudaMalloc((void**)&c->d_items, items.size() * sizeof(int)));
@@ -52,19 +77,32 @@ void ensure_items(ldm_context* c)
     c->items_world = d.world;
 }
 
-// the ring CSR rows of the current (rank, world) in `grid` contiguous shares of about equal entry count
+// The ring correction inside the work-list kernel.  Light grid rows -- a prefix of this rank's rows, as long as a row's
+// entries fit the staging area in the idle H tile -- are corrected by the CTA that closes them; the CSR rows of the heavy
+// rows behind them (on a stretched grid the last few rows own most samples beyond the circle) are dealt out over the `grid`
+// CTAs of a launch in contiguous shares of about equal entry count.
 void ensure_ring_cut(ldm_context* c, int grid)
 {
     const DevProblem& d = c->dev;
     if (c->d_ring_cut && c->cut_grid == grid && c->cut_rank == d.rank && c->cut_world == d.world) return;
     const std::vector<int>& begin = c->ring_row_begin_host;
-    const int rows = (int)begin.size() - 1;
-    const long long total = rows > 0 ? begin[(size_t)rows] : 0;
+    const std::vector<int>& grid_row = c->ring_grid_row_begin_host;
+    const int rows = (int)begin.size() - 1, n_local = (int)grid_row.size() - 1;
+    int U = 0, ng = 0, a_pad = 0;
+    chunk_block_shape(d, &U, &ng, &a_pad);
+    const long long tile = (long long)d.A * (d.scan_bn + 2);                       // doubles of the H tile (ldm_scan_body.cuh ScanLayout::hs)
+    c->self_ring_capacity = tile >= d.G ? (int)std::min<long long>(4096, (tile - d.G) / 2) : -1;
+    c->self_ring_rows = 0;
+    while (c->self_ring_rows < n_local && c->self_ring_capacity >= 0 &&
+           begin[(size_t)grid_row[(size_t)c->self_ring_rows + 1]] - begin[(size_t)grid_row[(size_t)c->self_ring_rows]] <= c->self_ring_capacity)
+        c->self_ring_rows++;
+    const int first = n_local > 0 ? grid_row[(size_t)c->self_ring_rows] : 0;    // first CSR row that goes through the shares
+    const long long base = rows > 0 ? begin[(size_t)first] : 0, total = rows > 0 ? begin[(size_t)rows] - base : 0;
     std::vector<int> cut((size_t)grid + 1, std::max(rows, 0));
-    cut[0] = 0;
-    int row = 0;
+    cut[0] = first;
+    int row = first;
     for (int s = 1; s < grid; s++) {
-        const long long want = total * s / grid;
+        const long long want = base + total * s / grid;
         while (row < rows && begin[(size_t)row] < want) row++;
         cut[(size_t)s] = row;
     }
@@ -146,9 +184,11 @@ void advance_chunked(ldm_context* c, int n_steps, double dt, cudaStream_t s, lon
     a.N = c->d_N;
     a.items = c->d_items; a.n_items = c->n_items;
     a.row_window = c->d_row_window;
+    a.block_window = c->d_block_window; a.blocks_per_row = c->blocks_per_row;
     a.counters = c->d_counters;
     a.ring_pingpong = c->d_ring2;
     a.ring_cta_begin = c->d_ring_cut;
+    a.self_ring_rows = c->self_ring_rows; a.self_ring_capacity = c->self_ring_capacity;
     a.status = c->d_status;
     a.stride = (long long)(1 + c->P());
     if (peers) {
@@ -320,6 +360,29 @@ int ldm_shard_peer_connect_local(int world, const ldm_handle* handles)
     });
 }
 
+#ifdef LDM_PHASE_CLOCKS
+// Measurement aid of the debug build (tools/shard_rank_timing.py): rank `rank` of `world` steps ALONE -- every peer's
+// replica is this rank's own, the other ranks' flags count as published -- so that one GPU shows what a rank of a
+// W-rank run computes and how its items and closings schedule, without the exchange.  The other ranks' rows stay stale.
+LDM_API int ldm_debug_shard_solo(ldm_handle h)
+{
+    if (!h) return fail(LDM_ERR_ARGUMENT, "NULL handle");
+    return guarded([&] {
+        LDM_CUDA(cudaSetDevice(h->device));
+        peer_buffers_alloc(h);
+        unsigned long long* scratch = h->alloc<unsigned long long>((size_t)ldm::kFlagWords(h->dev.G));
+        for (int q = 0; q < h->dev.world; q++) {
+            h->peer_C[0][q] = h->peer_own[0];
+            h->peer_C[1][q] = h->peer_own[1];
+            h->peer_flags[q] = q == h->dev.rank ? h->peer_own_flags : scratch;
+        }
+        h->peer_connected = true;
+        h->peer_solo = true;
+        LDM_CUDA(cudaDeviceSynchronize());
+    });
+}
+#endif
+
 int ldm_shard_peer_upload(ldm_handle h, const double* C_gathered, double N)
 {
     if (!h || !C_gathered) return fail(LDM_ERR_ARGUMENT, "NULL argument");
@@ -337,6 +400,13 @@ int ldm_shard_peer_upload(ldm_handle h, const double* C_gathered, double N)
         LDM_CUDA(cudaMemcpy(h->d_N, &N, sizeof(double), cudaMemcpyHostToDevice));
         h->peer_epoch = 0;
         h->peer_parity = 0;
+        if (h->peer_solo) {                                 // the other ranks and their rows count as published, for ever
+            LDM_CUDA(cudaMemcpy(h->peer_own[1], C_gathered, words * sizeof(double), cudaMemcpyHostToDevice));
+            std::vector<unsigned long long> flags((size_t)ldm::kFlagWords(h->dev.G), 0ULL);
+            for (int q = 0; q < h->dev.world; q++) if (q != h->dev.rank) flags[(size_t)q] = 1ULL << 62;
+            for (int x = 0; x < h->dev.G; x++) if (x % h->dev.world != h->dev.rank) flags[(size_t)ldm::kMaxPeers + x] = 1ULL << 62;
+            LDM_CUDA(cudaMemcpy(h->peer_own_flags, flags.data(), flags.size() * sizeof(unsigned long long), cudaMemcpyHostToDevice));
+        }
         if (chunked_possible(h)) prepare_chunked(h);       // before anybody steps (see prepare_chunked)
         else ensure_ring_operator(h);
         LDM_CUDA(cudaDeviceSynchronize());
