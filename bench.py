@@ -510,6 +510,7 @@ def main():
     ap.add_argument("--batch-sets", type=int, default=128, help="parameter sets per GPU of the batched leg (0 to skip)")
     ap.add_argument("--batch-steps", type=int, default=50)
     ap.add_argument("--no-sweep", action="store_true", help="skip the experiment-14.6 sweep leg (N = 1 only)")
+    ap.add_argument("--item-order", type=int, default=None, help="measurements: hand-out order of the work-list kernel (ldm_tuning_set item_order)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -535,6 +536,8 @@ def main():
     import torch.distributed as dist
     from __graft_entry__ import load_package
     ldm = load_package()
+    if args.item_order is not None:
+        ldm.tuning_set("item_order", args.item_order)
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU fallback")
     torch.cuda.set_device(local_rank)

@@ -76,7 +76,7 @@ struct ldm_context {
     // persistent work-list kernel (ldm_persist.cu persistent_chunks_kernel): rows of several chunks and the xi-sharded step
     int chunk_grid = 0;                    // co-resident CTAs of that kernel (0: not queried yet, -1: unavailable)
     int chunk_grid_limit = 0;              // > 0: launch at most this many CTAs (ldm_tuning_set chunk_grid; two ranks on one device in tests)
-    int2* d_items = nullptr;               // (local row, chunk) work list of the current (rank, world): rows ascending
+    int4* d_items = nullptr;               // (local row, chunk) work list of the current (rank, world): rows ascending
     int2* d_row_window = nullptr;          // [G] rows that the E phase of row x reads (ChunkedArgs::row_window)
     int4* d_block_window = nullptr;        // [G][blocks_per_row] ... per block of alphas (ChunkedArgs::block_window)
     int blocks_per_row = 0;

@@ -246,7 +246,8 @@ struct ChunkedArgs {
     double* replica[2][kMaxPeers];
     unsigned long long* flags[kMaxPeers];
     double* N;                 // [2] first moment, ping-pong with the replicas (every rank advances its own copy: no all-reduce)
-    const int2* items;         // (local row, chunk) in the order they are handed out: rows ascending, a row's chunks by descending cost
+    const int4* items;         // (local row, chunk, first and last moment-grid row that the row's E phase reads) in the order they are
+                               // handed out: rows ascending, a row's chunks by descending cost
     int n_items;
     const int2* row_window;    // [G] first and last moment-grid row that the E phase of row x reads
     const int4* block_window;  // [G][blocks_per_row] the same per block of alphas that one thread group takes in one super-chunk of the E

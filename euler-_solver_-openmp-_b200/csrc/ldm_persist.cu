@@ -333,7 +333,8 @@ persistent_chunks_kernel(const ChunkedArgs A)
     const int NT = blockDim.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, warps = NT / 32;
     __shared__ double wc_shared;
     __shared__ unsigned int next_item[2];
-    __shared__ int closes_row, gate;
+    __shared__ int4 next_record[2];
+    __shared__ int gate;
     StepArgs S = A.step;
     const DevProblem& P = S.P;
     const int G = P.G, n_local = local_rows(P), chunks = P.scan_chunks, n = n_local * G;
@@ -361,7 +362,10 @@ persistent_chunks_kernel(const ChunkedArgs A)
             if (lane == 0) tail[xr] = s;
         }
     }
-    if (tid == 0) next_item[0] = atomicAdd(fetch_counter, 1u);                     // this CTA's first item
+    if (tid == 0) {                                                                // this CTA's first item
+        next_item[0] = atomicAdd(fetch_counter, 1u);
+        next_record[0] = A.items[next_item[0] % (unsigned int)A.n_items];
+    }
     if (!grid_barrier(A.counters + 2, 0, A.status)) return;
     unsigned int item = next_item[0];
     unsigned int turn = 0;                                                         // items this CTA has taken so far
@@ -406,35 +410,38 @@ persistent_chunks_kernel(const ChunkedArgs A)
             if (!await_state(ring_done + 1)) return;
             ring_share(ring_done + 1);
         }
-        const int2 it = A.items[item - step_begin];                                // (local row, chunk)
+        const int4 it = next_record[turn & 1];                                     // (local row, chunk, first and last row of the row's window)
         const int lx = it.x;
         const int x = P.rank + P.world * lx;
         bool gated = false;
         if (complete < k) {
-            // state epoch + k complete already?  Otherwise the item goes ahead behind a gate (RowGate) as soon as the step
-            // before has closed this very row: its chunk sums and arrival counter are reused step after step
+            // Is state epoch + k complete, or at least every row of the item's window here?  (One round of independent polls.)
+            // Then the item runs like any other.  Otherwise it goes ahead behind the gate (RowGate) once the step before has
+            // closed this very row -- its chunk sums and arrival counter are reused step after step (a shape whose block
+            // windows do not fit the row buffers waits for the whole window instead).
             if (tid < 32) {
-                int g = ranks_have_published(own_flags, A.world, A.epoch + (unsigned long long)k) ? 2 : 0;
-                if (g == 0) {
-                    // every row of the item's window here already?  (one round of independent polls.)  Then the item runs like any
-                    // other.  Otherwise it goes ahead behind the gate once the step before has closed this very row (a shape
-                    // whose block windows do not fit the row buffers waits for the whole window instead).
-                    const unsigned long long need = A.epoch + (unsigned long long)k;
-                    const int2 w = A.row_window[x];
-                    bool here = true;
-                    for (int r = w.x + tid; r <= w.y; r += 32) here = here && RowGate::peek(own_row_flags + r) >= need;
-                    const bool can_gate = A.blocks_per_row <= L.part_stride;
-                    if (__all_sync(0xffffffffu, here)) {
-                        asm volatile("fence.acq_rel.sys;" ::: "memory");
-                        g = 3;
-                    } else if (can_gate) {
-                        g = wait_for_rows(own_row_flags, x, x, need, A.status) ? 1 : 0;
-                    } else {
-                        g = wait_for_rows(own_row_flags, w.x, w.y, need, A.status) ? 3 : 0;
-                    }
-                    if (load_status(A.status) != kStatusOk) g = 0;
+                const unsigned long long need = A.epoch + (unsigned long long)k;
+                bool published = true, here = true;
+                if (tid < A.world) published = RowGate::peek(own_flags + tid) >= need;
+                for (int r = it.z + tid; r <= it.w; r += 32) here = here && RowGate::peek(own_row_flags + r) >= need;
+                published = __all_sync(0xffffffffu, published);
+                here = __all_sync(0xffffffffu, here);
+                const bool can_gate = A.blocks_per_row <= L.part_stride;
+                int g;
+                if (published || here) {
+                    asm volatile("fence.acq_rel.sys;" ::: "memory");
+                    g = published ? 2 : 3;
+                } else if (can_gate) {
+                    g = wait_for_rows(own_row_flags, x, x, need, A.status) ? 1 : 0;
+                } else {
+                    g = wait_for_rows(own_row_flags, it.z, it.w, need, A.status) ? 3 : 0;
                 }
+                if (load_status(A.status) != kStatusOk) g = 0;
                 if (tid == 0) gate = g;
+            } else if (A.blocks_per_row <= L.part_stride) {
+                // meanwhile: the row's block windows into shared memory (the closing's row buffers are idle while an item runs)
+                int4* const windows = reinterpret_cast<int4*>(scan_smem + L.rowbuf);
+                for (int b = tid - 32; b < A.blocks_per_row; b += NT - 32) windows[b] = A.block_window[(size_t)x * A.blocks_per_row + b];
             }
             __syncthreads();
             const int g = gate;
@@ -469,24 +476,28 @@ persistent_chunks_kernel(const ChunkedArgs A)
         SCAN_MARK(11);
         TRACE(2, k, lx, it.y);
 
-        if (tid == 0) next_item[(turn + 1) & 1] = atomicAdd(fetch_counter, 1u);      // the next item, fetched under this one's work
-        // the row's block windows, from shared memory (the closing's row buffers are idle while an item runs)
-        int4* const windows = reinterpret_cast<int4*>(scan_smem + L.rowbuf);
-        if (gated) {
-            for (int b = tid; b < A.blocks_per_row; b += NT) windows[b] = A.block_window[(size_t)x * A.blocks_per_row + b];
-            __syncthreads();
+        if (tid == 0) {                                                              // the next item, fetched under this one's work
+            const unsigned int next = atomicAdd(fetch_counter, 1u);
+            next_item[(turn + 1) & 1] = next;
+            next_record[(turn + 1) & 1] = A.items[next % (unsigned int)A.n_items];
         }
+        const int4* const windows = reinterpret_cast<const int4*>(scan_smem + L.rowbuf);
         const RowGate row_gate{own_row_flags, windows, A.epoch + (unsigned long long)k, A.status, L.ng, P.scan_bn, A.blocks_per_row / L.ng, gated};
         scan_body_of<SMALL, U>(S, it.y, lx, true, -1, false, ring_if_complete, row_gate);   // chunk sums -> S.partial; ends with a CTA barrier
         ring_if_complete();
         TRACE(3, k, lx, it.y);
+        // Arrival: ONE read-modify-write that releases this CTA's chunk sums and acquires the others' (behind the CTA barrier at
+        // the end of scan_body, in front of the one below); the CTA that brings a row's last chunk closes the row.  (A closer
+        // fixed in advance -- the row's last chunk in the list -- was measured: it waits for chunks that are themselves held
+        // up behind gates, and the convoy costs a fifth of the step.)
         if (tid == 0) {
-            __threadfence();                                                         // the CTA's chunk sums, before the arrival
-            const unsigned int arrived = atomicAdd(row_arrivals + lx, 1u) + 1u;
-            __threadfence();                                                         // the other chunks' sums, after it
-            closes_row = arrived == (unsigned int)(k + 1) * (unsigned int)chunks;
+            unsigned int before;
+            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(before) : "l"(row_arrivals + lx), "r"(1u) : "memory");
+            gate = before + 1u == (unsigned int)(k + 1) * (unsigned int)chunks;
         }
         __syncthreads();
+        const bool closes_row = gate != 0;
+        __syncthreads();                                 // `gate` is rewritten by the next wait
         turn++;
         item = next_item[turn & 1];
         if (!closes_row) continue;

@@ -58,15 +58,25 @@ void ensure_items(ldm_context* c)
     }
     if (c->d_items && c->items_rank == d.rank && c->items_world == d.world) return;
     const int n_local = local_rows(d);
+    const std::vector<int>& upper = c->tables.axisM.upper;
     std::vector<int> items;
-    items.reserve((size_t)2 * n_local * d.scan_chunks);
+    items.reserve((size_t)4 * n_local * d.scan_chunks);
+    auto push = [&](int lx, int chunk) {
+        const int x = d.rank + d.world * lx;
+        int lo = x, hi = x;
+        for (int o = 0; o < d.n_off; o++) {
+            const int u = upper[(size_t)x * d.n_off + o];
+            if (u != 0) { lo = std::min(lo, u - 1); hi = std::max(hi, u); }
+        }
+        items.push_back(lx); items.push_back(chunk); items.push_back(lo); items.push_back(std::min(hi, d.G - 1));
+    };
     const int order = tuning().item_order;
     if (order == 1) {
         for (int k = 0; k < d.scan_chunks; k++)
-            for (int lx = 0; lx < n_local; lx++) { items.push_back(lx); items.push_back(c->chunk_order_host[(size_t)k]); }
+            for (int lx = 0; lx < n_local; lx++) push(lx, c->chunk_order_host[(size_t)k]);
     } else {
         for (int i = 0; i < n_local; i++)
-            for (int k = 0; k < d.scan_chunks; k++) { items.push_back(order == 2 ? n_local - 1 - i : i); items.push_back(c->chunk_order_host[(size_t)k]); }
+            for (int k = 0; k < d.scan_chunks; k++) push(order == 2 ? n_local - 1 - i : i, c->chunk_order_host[(size_t)k]);
     }
     if (c->d_items) cudaFree(c->d_items);
     c->d_items = nullptr;

@@ -193,7 +193,8 @@ LDM_API int  ldm_shard_peer_download(ldm_handle h, double* C_gathered, double* N
  * paths on small grids.  Read when a handle is created.  Keys: "scan_bn", "scan_nt" (prefix-sum path: chunk width, threads),
  * "factored_bm", "factored_bn", "factored_tn" (dense contraction tiles), "persistent" (0: one launch per kernel and
  * step), "scan" (0: never the prefix-sum path), "chunk_grid" (CTAs of the persistent work-list kernel), "batch_capacity" (CTA budget of
- * the persistent batch kernel), "reset". ---- */
+ * the persistent batch kernel), "item_order" (work-list kernel, measurements: 0 rows ascending, 1 chunk by chunk, 2 rows descending),
+ * "reset". ---- */
 LDM_API int  ldm_tuning_set(const char* name, int value);
 
 /* ---- measurement support: FP64 (DFMA) peak of `device` in TFLOP/s, measured live by a register-resident

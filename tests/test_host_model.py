@@ -175,7 +175,7 @@ def test_create_rejects_tables_the_reference_asserts_on(ldm, case):
 
 
 def test_tuning_keys(ldm):
-    for key in ("scan_bn", "scan_nt", "factored_bm", "factored_bn", "factored_tn", "persistent", "scan", "chunk_grid", "batch_capacity"):
+    for key in ("scan_bn", "scan_nt", "factored_bm", "factored_bn", "factored_tn", "persistent", "scan", "chunk_grid", "batch_capacity", "item_order"):
         ldm.tuning_set(key, 0)
     ldm.tuning_set("reset")
     with pytest.raises(ldm.LdmError):
