@@ -299,7 +299,7 @@ def cpu_baseline(workload, budget_s=25.0):
 def run_sharded_peer(ldm, torch, dist, workload, rank, world, local_rank, steps, warmup):
     """BASELINE config 4 with the all-gather FUSED into the update: ONE launch per rank for all the steps (persistent
     work-list kernel); the CTA that completes a row stores it straight into every rank's next replica over NVLink (CUDA IPC
-    peer mappings) and a step ends with per-rank epoch flags.  No NCCL call on the data path (NCCL only carries the 64-byte
+    peer mappings) and sets the row's arrival flag there -- the steps of a launch are ordered by those data dependencies alone.  No NCCL call on the data path (NCCL only carries the 64-byte
     IPC handles at set-up and the timing reduction).  Every rank then repeats the same steps ALONE on its own GPU (one
     rank, same kernel) and compares its replica with that run element by element; the one-rank time measured there, in
     the same run on the same GPU, is the denominator of `speedup_vs_1gpu`."""
@@ -362,7 +362,8 @@ def run_sharded_peer(ldm, torch, dist, workload, rank, world, local_rank, steps,
             "value": P * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
             "one_gpu_ms_per_step": one_ms / steps, "speedup_vs_1gpu": one_ms / ms,
             "max_abs_diff": diff, "elementwise": "every rank's replica against the same steps on one rank, all G*G values and N; max over ranks",
-            "collective": "fused into the persistent kernel: NVLink peer stores of every row as it closes into every rank's replica + per-rank epoch flags "
+            "collective": "fused into the persistent kernel: NVLink peer stores of every row as it closes into every rank's replica, per-row arrival "
+                          "flags (the next step's first rows start while this step's last rows are still computed and shipped) and per-rank step flags "
                           "(%d bytes to each of %d peers per rank per step); no NCCL on the data path" % (sh.rows_per_rank * G * 8, world - 1),
             "gpu_launches": launches, "algorithmic_tflops": flop_step * steps / (ms * 1e-3) / 1e12,
             "checksum": float(final_C.sum() + N_end)}
@@ -508,7 +509,7 @@ def main():
     ap.add_argument("--exchange", default="peer", choices=["peer", "nccl"],
                     help="sharded leg at N > 1: all-gather fused into the update over NVLink peer stores, or an NCCL all-gather per step")
     ap.add_argument("--batch-sets", type=int, default=128, help="parameter sets per GPU of the batched leg (0 to skip)")
-    ap.add_argument("--batch-steps", type=int, default=50)
+    ap.add_argument("--batch-steps", type=int, default=200)
     ap.add_argument("--no-sweep", action="store_true", help="skip the experiment-14.6 sweep leg (N = 1 only)")
     ap.add_argument("--item-order", type=int, default=None, help="measurements: hand-out order of the work-list kernel (ldm_tuning_set item_order)")
     args = ap.parse_args()

@@ -82,7 +82,7 @@ __host__ __device__ inline size_t align32(size_t v) { return (v + 31) & ~(size_t
 __host__ __device__ inline ScanLayout scan_layout(int G, int A, int bn, int NT, int pieces)
 {
     ScanLayout L;
-    L.ld = bn + kScanLead;
+    L.ld = bn + kScanLead + (G > bn ? 1 : 0);             // several chunks per row: one more zero column behind the last (y_side_run)
     L.n_yblk = (G + 31) / 32;
     L.part_stride = L.n_yblk * 32;
     L.ng = NT / bn > 1 ? NT / bn : 1;                     // thread groups of bn columns sharing the alphas of a super-chunk
@@ -154,9 +154,11 @@ __device__ __forceinline__ double y_side_run(double s, const double* hrow, int d
         const int u = (int)*up;
         const double w = *wp;
         if (MASKED) {
-            const bool ok_a = (unsigned)(u - 1 - q0) < (unsigned)bn, ok_b = (unsigned)(u - q0) < (unsigned)bn;
-            const double a = hrow[ok_a ? u - 1 : q0], b = hrow[ok_b ? u : q0];
-            s += (ok_a ? a * (1.0 - w) : 0.0) + (ok_b ? b * w : 0.0);
+            // the chunk holds columns [q0, q0 + bn): a tap outside them reads one of the two zero columns that flank the tile
+            // (index clamped to -1 .. bn), so a pair that straddles a chunk boundary is taken tap by tap in both chunks
+            // without a select
+            const int ia = min(max(u - 1 - q0, -1), bn), ib = min(max(u - q0, -1), bn);
+            s = __dadd_rn(s, __fma_rn(hrow[q0 + ia], __dadd_rn(1.0, -w), __dmul_rn(hrow[q0 + ib], w)));
         } else {
             // hrow[u - 1] * (1 - w) + hrow[u] * w, the roundings spelled out (product, complement, fma, sum)
             s = __dadd_rn(s, __fma_rn(hrow[u - 1], __dadd_rn(1.0, -w), __dmul_rn(hrow[u], w)));
@@ -262,7 +264,10 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
             qv[a] = a < A ? P.qvec[a] : 0.0;
             sel[a] = a < A ? P.beta_range[a] : make_int2(0, 0);
         }
-        for (int b = tid; b < A; b += NT) Hs[b * ld + kScanLead - 1] = 0.0;   // the zero column (never written again)
+        for (int b = tid; b < A; b += NT) {
+            Hs[b * ld + kScanLead - 1] = 0.0;                                 // the zero column (never written again)
+            if (P.scan_chunks > 1) Hs[b * ld + kScanLead + bn] = 0.0;         // and the one behind the chunk's last column
+        }
         // empty rows of the table (a suffix: a_star never grows with beta) are never closed: zero them once
         for (int i = P.scan_live_rows * ld + tid; i < A * ld; i += NT) Hs[i] = 0.0;
         __syncthreads();

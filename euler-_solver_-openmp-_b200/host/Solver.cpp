@@ -23,6 +23,7 @@
 #include <stdexcept>
 #include <algorithm>
 #include <string>
+#include <exception>
 #include <thread>
 #include <vector>
 
@@ -507,9 +508,19 @@ public:
             std::vector<std::unique_ptr<Equation>> built((size_t)n);
             std::vector<std::thread> workers;
             const int n_workers = std::min(8, std::max(1, n));
+            // a library error inside a worker (no device, out of memory, an entry the library rejects) is carried back to
+            // this thread and thrown here; an exception that escaped a worker would end the program without its message
+            std::vector<std::exception_ptr> failure((size_t)n_workers);
             for (int w = 0; w < n_workers; w++)
-                workers.emplace_back([&, w] { for (int i = w; i < n; i += n_workers) built[(size_t)i].reset(new Equation(PropsVector[(size_t)i], device_of[(size_t)i])); });
+                workers.emplace_back([&, w] {
+                    try {
+                        for (int i = w; i < n; i += n_workers) built[(size_t)i].reset(new Equation(PropsVector[(size_t)i], device_of[(size_t)i]));
+                    } catch (...) {
+                        failure[(size_t)w] = std::current_exception();
+                    }
+                });
             for (std::thread& t : workers) t.join();
+            for (const std::exception_ptr& e : failure) if (e) std::rethrow_exception(e);
             for (int i = 0; i < n; i++) equations.push_back(*built[(size_t)i]);
         }
         const double setup_seconds = seconds_since(start);

@@ -396,14 +396,18 @@ def test_peer_exchange_step_on_one_rank(ldm, how, G):
     assert np.array_equal(got_C.ravel(), want[1:]) and got_N == want[0]
 
 
-@pytest.mark.parametrize("world,G", [(2, 200), (3, 200), (2, 0), (4, 333)])
-def test_ranks_on_one_device_elementwise(ldm, world, G):
+@pytest.mark.parametrize("world,G,order", [(2, 200, 0), (3, 200, 0), (2, 0, 0), (4, 333, 0), (2, 200, 1), (3, 200, 2)])
+def test_ranks_on_one_device_elementwise(ldm, world, G, order):
     """SURVEY 8e at world > 1 on ONE GPU: every rank is a handle of its own on device 0 with its own stream and its own
     launch of the persistent work-list kernel (grids capped so that all of them are resident together); rows travel
     between the ranks' replicas through the same peer stores and epoch flags a multi-GPU run uses (wired up by
     ldm_shard_peer_connect_local instead of CUDA IPC).  Every rank's replica must equal the unsharded run ELEMENT BY
-    ELEMENT -- a permutation bug in the gathered layout would keep a checksum, not this."""
+    ELEMENT -- a permutation bug in the gathered layout would keep a checksum, not this.  The steps of a launch are ordered
+    by data dependencies alone (per-row arrival flags; items that start before their state is complete run behind row
+    gates), so the hand-out order of the items must not matter either: rows ascending (0, the default), chunk by chunk (1),
+    rows descending (2)."""
     import torch
+    ldm.tuning_set("item_order", order)
     sms = torch.cuda.get_device_properties(0).multi_processor_count
     if G:
         props = ldm.Properties.Generate(1, 0.12, 0.09, 0.4, 0.2, 0.001, G)       # several column chunks, uneven row counts
