@@ -173,6 +173,7 @@ void multi_build_groups(ldm_context* parent)
 {
     for (ldm_context::PairGroup& g : parent->pair_groups) { cudaFree(g.d_args[0]); cudaFree(g.d_args[1]); }
     parent->pair_groups.clear();
+    if (parent->multi_graph) { cudaGraphExecDestroy(parent->multi_graph); parent->multi_graph = nullptr; }   // it holds the old argument arrays
     std::vector<std::vector<ldm_context*>> members;
     for (ldm_context* h : parent->sub) {
         ensure_ring_operator(h);
@@ -256,6 +257,49 @@ void multi_rhs_and_update(ldm_context* c, double dt, bool want_derivs, bool upda
     ldm::launch_finish_multi(a, s);
     c->launches += 1;
     if (update) c->cur = nxt;
+}
+
+// n_steps clamped Euler steps (Solver.cpp:577-582) of a multi-species handle at its resident state.  A step is three to
+// five small launches on two streams; the launches of TWO consecutive steps -- both parities of the state ping-pong -- are
+// captured once into a CUDA graph and replayed, the odd steps at either end run as ordinary launches (same kernels, same
+// arguments: the same bits either way).
+void multi_advance(ldm_context* c, int n_steps, double dt, cudaStream_t s)
+{
+    if (n_steps <= 0) return;
+    if (c->pair_groups.empty()) multi_build_groups(c);                       // allocates: never inside a capture
+    auto step = [&] { multi_rhs_and_update(c, dt, false, true, s); n_steps--; };
+    if (c->cur & 1) step();                                                  // the graph starts at parity 0
+    const bool fresh = c->multi_graph && c->multi_graph_dt == dt && c->multi_graph_extrapolation == c->dev.extrapolation;
+    if (!fresh && n_steps >= 8 && tuning().multi_graph != 0) {
+        if (c->multi_graph) { cudaGraphExecDestroy(c->multi_graph); c->multi_graph = nullptr; }
+        step(); step();                                                      // first use of every kernel outside the capture
+        const long long before = c->launches;
+        cudaGraph_t graph = nullptr;
+        LDM_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+        try {
+            multi_rhs_and_update(c, dt, false, true, s);
+            multi_rhs_and_update(c, dt, false, true, s);
+        } catch (...) {
+            cudaStreamEndCapture(s, &graph);
+            if (graph) cudaGraphDestroy(graph);
+            c->cur = 0;
+            throw;
+        }
+        LDM_CUDA(cudaStreamEndCapture(s, &graph));
+        c->multi_graph_launches = c->launches - before;
+        c->launches = before;
+        const cudaError_t e = cudaGraphInstantiate(&c->multi_graph, graph, 0);
+        cudaGraphDestroy(graph);
+        LDM_CUDA(e);
+        c->multi_graph_dt = dt;
+        c->multi_graph_extrapolation = c->dev.extrapolation;
+    }
+    if (c->multi_graph && c->multi_graph_dt == dt && c->multi_graph_extrapolation == c->dev.extrapolation && tuning().multi_graph != 0)
+        for (; n_steps >= 2; n_steps -= 2) {
+            LDM_CUDA(cudaGraphLaunch(c->multi_graph, s));
+            c->launches += c->multi_graph_launches;
+        }
+    while (n_steps > 0) step();
 }
 
 void multi_upload(ldm_context* c, const double* state, cudaStream_t s)
@@ -509,6 +553,7 @@ int ldm_tuning_set(const char* name, int value)
     else if (key == "chunk_grid") t.chunk_grid = value;
     else if (key == "batch_capacity") t.batch_capacity = value;
     else if (key == "item_order") t.item_order = value;
+    else if (key == "multi_graph") t.multi_graph = value;
     else return fail(LDM_ERR_ARGUMENT, "unknown tuning key");
     return LDM_OK;
 }
@@ -939,7 +984,11 @@ int ldm_solve(ldm_handle h, const double* init, double dt, double t_max, int rec
             cudaStream_t s = h->stream;
             multi_upload(h, init, s);
             LDM_CUDA(cudaEventRecord(h->ev_begin, s));
-            for (int k = 0; k < n; k++) {
+            if (record == LDM_RECORD_LAST) {                                 // nothing leaves the device on the way: replayed as a graph
+                multi_advance(h, n - 1, dt, s);
+                if (derivs) multi_rhs_and_update(h, dt, true, false, s);
+            }
+            for (int k = 0; k < n && record != LDM_RECORD_LAST; k++) {
                 if (record >= LDM_RECORD_VALUES) multi_download(h, values + (size_t)k * width, s);
                 const bool last = (k == n - 1);
                 const bool want_deriv = (record == LDM_RECORD_ALL) || (last && derivs);
@@ -1082,7 +1131,7 @@ int ldm_advance(ldm_handle h, int n_steps, double dt)
         return guarded([&] {
             LDM_CUDA(cudaSetDevice(h->device));
             LDM_CUDA(cudaEventRecord(h->ev_begin, h->stream));
-            for (int k = 0; k < n_steps; k++) multi_rhs_and_update(h, dt, false, true, h->stream);
+            multi_advance(h, n_steps, dt, h->stream);
             LDM_CUDA(cudaEventRecord(h->ev_end, h->stream));
             LDM_CUDA(cudaGetLastError());
         });
@@ -1299,14 +1348,39 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
     if (!(dt > 0)) return fail(LDM_ERR_ARGUMENT, "step must be positive");
     return guarded([&] {
         const int points = ldm_count_points(t_max, dt);
-        bool batched = n > 0;
+        // entries of several species advance beside the batch, each on its own stream (its step is a replayed graph of a
+        // few launches over all its pairs: multi_advance); the one-species entries form the batch proper
+        std::vector<ldm_context*> several;
+        std::vector<int> several_slot;
+        std::vector<ldm_handle> one_species;
+        std::vector<const double*> one_inits;
+        std::vector<double*> one_last;
         for (int i = 0; i < n; i++) {
             if (!handles[i] || !inits[i] || !last_states[i]) throw std::invalid_argument("NULL entry in batch");
-            if (handles[i]->species != 1) throw std::invalid_argument("batches are built for one species per entry");
+            if (handles[i]->species != 1) { several.push_back(handles[i]); several_slot.push_back(i); }
+            else { one_species.push_back(handles[i]); one_inits.push_back(inits[i]); one_last.push_back(last_states[i]); }
+        }
+        for (size_t j = 0; j < several.size(); j++) {
+            ldm_context* h = several[j];
+            LDM_CUDA(cudaSetDevice(h->device));
+            multi_upload(h, inits[several_slot[j]], h->stream);
+            multi_advance(h, points - 1, dt, h->stream);
+            multi_download(h, last_states[several_slot[j]], h->stream);
+        }
+        struct Drain {                                   // whatever happens to the batch: the entries beside it are waited for
+            std::vector<ldm_context*>& entries;
+            ~Drain() { for (ldm_context* h : entries) { cudaSetDevice(h->device); cudaStreamSynchronize(h->stream); } }
+        } drain{several};
+        n = (int)one_species.size();
+        handles = one_species.data();
+        const double* const* inits_of = one_inits.data();
+        double* const* last_of = one_last.data();
+        bool batched = n > 0;
+        for (int i = 0; i < n; i++) {
             if (handles[i]->dev.world != 1) throw std::invalid_argument("a batch entry is configured as one rank of several (ldm_shard_configure)");
             ldm_context* h = handles[i];
             LDM_CUDA(cudaSetDevice(h->device));
-            upload_state(h, inits[i]);
+            upload_state(h, inits_of[i]);
             batched = batched && h->algo != LDM_ALGO_DIRECT && h->dev.world == 1 && h->dev.extrapolation != LDM_EXTRAPOLATION_EXPONENTIAL;
         }
         for (int i = 0; i < n; i++) {
@@ -1347,8 +1421,8 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
             ldm_context* h = handles[i];
             LDM_CUDA(cudaSetDevice(h->device));
             LDM_CUDA(cudaGetLastError());
-            LDM_CUDA(cudaMemcpyAsync(last_states[i], h->d_N + h->cur, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-            LDM_CUDA(cudaMemcpyAsync(last_states[i] + 1, h->d_C[h->cur], h->P() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            LDM_CUDA(cudaMemcpyAsync(last_of[i], h->d_N + h->cur, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+            LDM_CUDA(cudaMemcpyAsync(last_of[i] + 1, h->d_C[h->cur], h->P() * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         }
         for (int i = 0; i < n; i++) {
             LDM_CUDA(cudaSetDevice(handles[i]->device));

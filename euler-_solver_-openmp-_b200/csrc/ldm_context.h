@@ -111,6 +111,13 @@ struct ldm_context {
         ldm::StepArgs* d_args[2] = {nullptr, nullptr};
     };
     std::vector<PairGroup> pair_groups;
+    // the launches of two consecutive Euler steps (both parities of the state ping-pong) as an instantiated CUDA graph: a
+    // multi-species step is three to five small launches, so the loop of ldm_advance / ldm_solve / ldm_solve_batch replays
+    // it; rebuilt when the step size, the extrapolation type or the pair groups change
+    cudaGraphExec_t multi_graph = nullptr;
+    double multi_graph_dt = 0;
+    int multi_graph_extrapolation = -1;
+    long long multi_graph_launches = 0;
     int cur = 0;
     int algo = LDM_ALGO_FACTORED;
     long long launches = 0;
@@ -139,6 +146,7 @@ struct ldm_context {
         for (ldm_context* c : sub) delete c;
         cudaSetDevice(device);
         for (PairGroup& g : pair_groups) { cudaFree(g.d_args[0]); cudaFree(g.d_args[1]); }
+        if (multi_graph) cudaGraphExecDestroy(multi_graph);
         for (void* p : allocations) cudaFree(p);
         for (void* p : ring_allocations) cudaFree(p);
         for (void* p : peer_opened) cudaIpcCloseMemHandle(p);

@@ -294,6 +294,7 @@ struct Tuning {
     int scan = -1;                             // 0: never take the prefix-sum path
     int chunk_grid = 0;                        // persistent_chunks_kernel: CTAs per launch (tests run two ranks on one device)
     int batch_capacity = 0;                    // persistent_batch_kernel: CTA budget of a launch (tests: several waves of sets)
+    int multi_graph = -1;                      // 0: the multi-species loop as ordinary launches (timing comparisons)
     int item_order = 0;                        // persistent_chunks_kernel, experiments: 0 rows ascending (default), 1 chunk by chunk, 2 rows descending
 };
 Tuning& tuning();

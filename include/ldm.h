@@ -145,9 +145,12 @@ LDM_API int  ldm_last_elapsed_ms(ldm_handle h, float* ms);
 LDM_API long long ldm_launch_count(ldm_handle h);
 
 /* ---- the sigma-sweep loop Experiments::CalculateWithVaryingSigma (S:940-963): n independent solves,
- * results slot-indexed (no shared push_back).  last_states[i] receives 1+G_i*G_i doubles.  The handles may live on
- * several devices (ldm_create's device argument): every device advances its slice of the batch concurrently, one
- * launch per kernel and step for all of its sets; ldm_device_count() = visible devices (0 without CUDA). ---- */
+ * results slot-indexed (no shared push_back).  last_states[i] receives 1+G_i*G_i doubles (an entry of s species: its
+ * whole state vector, s + s*s*G_i*G_i).  The handles may live on several devices (ldm_create's device argument): every
+ * device advances its slice of the batch concurrently -- the one-species entries whose rows are one chunk inside ONE
+ * persistent launch (a team of CTAs per set), the others with one launch per kernel and step for all of the device's
+ * sets, entries of several species beside them as replayed CUDA graphs on their own streams;
+ * ldm_device_count() = visible devices (0 without CUDA). ---- */
 LDM_API int  ldm_device_count(void);
 LDM_API int  ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits, double dt, double t_max,
                      double* const* last_states);

@@ -283,6 +283,47 @@ def test_several_species(ldm, name, algorithm):
         eq.integrals(g["state"])                  # one-species entry points say so instead of misreading the state
 
 
+def test_several_species_replayed_steps_and_batch(ldm):
+    """the Euler loop of a multi-species handle replayed as a CUDA graph of two steps (ldm_advance, ldm_solve with record =
+    last) and such handles as entries of a batch beside one-species entries: bit for bit what one launch sequence per step
+    gives (record = all takes that route), for even and odd step counts and from either parity of the state ping-pong"""
+    g = golden("multi_2_species")
+    props = ldm.Properties.Generate(2, [[0.05, 0.06], [0.06, 0.05]], [0.05] * 2, [0.4, 0.401], [0.2] * 2, np.full((2, 2), 0.001))
+    eq = ldm.Equation(props)
+    init = g["state"]
+    points = 41
+    ref = ldm.EulerSolver().Solve(eq, ldm.SquaredN, (points - 0.5) * 0.1, 0.1, init, record=ldm.RECORD_ALL)
+    before = eq.launches
+    last = ldm.EulerSolver().Solve(eq, ldm.SquaredN, (points - 0.5) * 0.1, 0.1, init, record=ldm.RECORD_LAST)
+    assert np.array_equal(last.Values[0], ref.Values[-1]) and np.array_equal(last.Derivatives[0], ref.Derivatives[-1])
+    assert eq.launches - before >= 3 * (points - 1)            # the replayed launches are counted
+    eq.upload(init)
+    eq.advance(13, 0.1)                                        # odd: ends at parity 1 ...
+    assert np.array_equal(eq.download(), ref.Values[13])
+    eq.advance(20, 0.1)                                        # ... and goes on from there
+    eq.advance(7, 0.1)
+    assert np.array_equal(eq.download(), ref.Values[40])
+    eq.upload(init)
+    eq.advance(12, 0.05)                                       # another step size: another graph
+    other = ldm.EulerSolver().Solve(eq, ldm.SquaredN, 12.5 * 0.05, 0.05, init, record=ldm.RECORD_VALUES)
+    eq.upload(init); eq.advance(12, 0.05)
+    assert np.array_equal(eq.download(), other.Values[12])
+    # a batch of two multi-species entries and three one-species entries
+    single_props = [ldm.Properties.Generate(1, sw, 0.08, 0.4, 0.2, 0.001) for sw in (0.05, 0.1, 0.15)]
+    singles = [ldm.Equation(p) for p in single_props]
+    single_inits = [e.GenerateEquilibriumValuesForNAndC(200) for e in singles]
+    eq2 = ldm.Equation(props)
+    init2 = init.copy(); init2[:2] *= 1.1
+    want2 = ldm.EulerSolver().Solve(eq2, ldm.SquaredN, (points - 0.5) * 0.1, 0.1, init2, record=ldm.RECORD_VALUES).Values[-1]
+    want_single = [ldm.EulerSolver().Solve(e, ldm.SquaredN, (points - 0.5) * 0.1, 0.1, v, record=ldm.RECORD_LAST).Values[0]
+                   for e, v in zip(singles, single_inits)]
+    outs = ldm.solve_batch([singles[0], eq, singles[1], eq2, singles[2]], [single_inits[0], init, single_inits[1], init2, single_inits[2]],
+                           0.1, (points - 0.5) * 0.1)
+    assert np.array_equal(outs[1], ref.Values[-1]) and np.array_equal(outs[3], want2)
+    for got, want in zip((outs[0], outs[2], outs[4]), want_single):
+        assert np.array_equal(got, want)
+
+
 @pytest.mark.parametrize("which", ["a", "b"])
 def test_whole_sweep_against_the_reference(ldm, which):
     """Experiment 14.6 a / b (S:1033-1071) entry by entry: ALL 160 entries of each sweep, 2000 Euler steps each, advanced
