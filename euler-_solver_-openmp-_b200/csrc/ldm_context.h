@@ -114,6 +114,11 @@ struct ldm_context {
     // the launches of two consecutive Euler steps (both parities of the state ping-pong) as an instantiated CUDA graph: a
     // multi-species step is three to five small launches, so the loop of ldm_advance / ldm_solve / ldm_solve_batch replays
     // it; rebuilt when the step size, the extrapolation type or the pair groups change
+    // ldm_solve_batch, on the first member of a device's slice: pinned host and device staging for the states of all members
+    // (+ their move descriptors), kept between calls
+    void* batch_stage_host = nullptr;
+    void* batch_stage_device = nullptr;
+    size_t batch_stage_bytes = 0;
     cudaGraphExec_t multi_graph = nullptr;
     double multi_graph_dt = 0;
     int multi_graph_extrapolation = -1;
@@ -147,6 +152,8 @@ struct ldm_context {
         cudaSetDevice(device);
         for (PairGroup& g : pair_groups) { cudaFree(g.d_args[0]); cudaFree(g.d_args[1]); }
         if (multi_graph) cudaGraphExecDestroy(multi_graph);
+        if (batch_stage_host) cudaFreeHost(batch_stage_host);
+        if (batch_stage_device) cudaFree(batch_stage_device);
         for (void* p : allocations) cudaFree(p);
         for (void* p : ring_allocations) cudaFree(p);
         for (void* p : peer_opened) cudaIpcCloseMemHandle(p);

@@ -178,6 +178,14 @@ void launch_peer_wait(const unsigned long long* flags, int world, unsigned long 
 // ring[lx][y] for the nodes of the ring CSR (other entries of `ring` stay zero)
 void launch_ring(const StepArgs& one, cudaStream_t stream);
 void launch_ring_batch(const StepArgs* d_batch, int n, int max_ring_rows, cudaStream_t stream);
+// The states of a batch between ONE staging buffer and the members' own buffers (ldm_solve_batch: one host <-> device copy
+// for all members instead of two per member).  Member i's state [N | C] lies at stage + offset doubles.
+struct StateMove {
+    long long offset, count;   // doubles in front of the member's state; doubles of its C
+    double* N;                 // the member's first moment (this parity)
+    double* C;                 // its pair density (this parity)
+};
+void launch_state_moves(const StateMove* d_moves, int n, double* stage, bool to_members, cudaStream_t stream);
 
 // Factored path (ldm_factored.cu): partial[slab][local_rows][G] <- per-slab sums over all samples inside the grid
 // square; the closing kernel forms inside_sum = sum_slabs partial - ring.

@@ -466,6 +466,23 @@ void launch_finish_factored_batch(const StepArgs* d_batch, int n, int max_points
     finish_factored_kernel<true><<<dim3((max_points + 255) / 256, 1, n), 256, 0, stream>>>(none, d_batch);
 }
 
+namespace {
+__global__ void __launch_bounds__(256) state_moves_kernel(const StateMove* __restrict__ moves, double* stage, const bool to_members)
+{
+    const StateMove m = moves[blockIdx.y];
+    double* at = stage + m.offset;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < m.count + 1; i += (long long)gridDim.x * blockDim.x) {
+        double* mine = i == 0 ? m.N : m.C + (i - 1);
+        if (to_members) *mine = at[i]; else at[i] = *mine;
+    }
+}
+}  // namespace
+
+void launch_state_moves(const StateMove* d_moves, int n, double* stage, bool to_members, cudaStream_t stream)
+{
+    if (n > 0) state_moves_kernel<<<dim3(8, n), 256, 0, stream>>>(d_moves, stage, to_members);
+}
+
 void launch_exponential_prepare(const DevProblem& P, const double* C, const double* N_cur, double* scalars, cudaStream_t stream)
 {
     exponential_prepare_kernel<<<1, 256, 0, stream>>>(P, C, N_cur, scalars);
