@@ -717,8 +717,9 @@ persistent_batch_kernel(const BatchArgs A)
         __syncthreads();
         const double N = S.N_cur[0];
         const double WC = __dmul_rn(add_outside(P, wc_shared, N, S.C, S.scalars, P.wc_outside, 0.0), P.hh);   // Solver.cpp:311, 314
+        const bool one_row = r + T >= G;                                // this CTA owns a single row: its tap tables stay in shared memory
         for (int lx = r; lx < G; lx += T) {
-            scan_body_of<SMALL, 0>(S, 0, lx, true, -1, true);           // per-node sums -> row_sum; ends with a CTA barrier
+            scan_body_of<SMALL, 0>(S, 0, lx, !one_row || k == 0, -1, true);   // per-node sums -> row_sum; ends with a CTA barrier
             for (int y = tid; y < G; y += NT) ring_buf[y] = 0.0;
             __syncthreads();
             for (int row = P.ring_row_begin[lx] + warp; row < P.ring_row_begin[lx + 1]; row += warps) {

@@ -48,7 +48,7 @@ static int piece_bound(int G, int nt) { return 3 * ((G + 31) / 32) + nt / 32; }
 // take 256-thread CTAs, everything else 257..512 threads.
 int scan_pick_threads(int G, int A, int bn)
 {
-    if (const int v = tuning().scan_nt; (v == 128 || v == 256 || v == 512) && v >= bn) return (v / bn) * bn;      // ldm_tuning_set: tests
+    if (const int v = tuning().scan_nt; (v == 256 || v == 512) && v >= bn) return (v / bn) * bn;      // ldm_tuning_set: tests
     if (bn <= 64 && scan_layout(G, A, bn, 256, piece_bound(G, 256)).end <= 48 * 1024) return (256 / bn) * bn;
     return (kScanThreadsMax / bn) * bn;                    // bn = 32, 64, 96, 128 -> 512, 512, 480, 512
 }
