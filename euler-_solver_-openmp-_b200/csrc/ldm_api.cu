@@ -1025,8 +1025,12 @@ int ldm_solve(ldm_handle h, const double* init, double dt, double t_max, int rec
         const size_t per_step = record == LDM_RECORD_OBSERVABLES ? 2 : record == LDM_RECORD_VALUES ? width : record == LDM_RECORD_ALL ? 2 * width : 0;
         int seg_len = std::max(1, n - 1);
         if (per_step != 0) {
-            seg_len = (int)std::min<size_t>((size_t)seg_len, std::max<size_t>(1, kHistorySegmentBytes / (per_step * sizeof(double))));
-            ensure_history(h, (size_t)seg_len * per_step);
+            const size_t longest = std::max<size_t>(1, kHistorySegmentBytes / (per_step * sizeof(double)));   // steps of a full segment
+            seg_len = (int)std::min<size_t>((size_t)seg_len, longest);
+            // sized for the longest segment this record mode can ask for (at most 4096 steps' worth), not for this call: a short
+            // solve followed by a long one must not re-allocate (measured: a 20-step warm-up in front of a 200-step solve put 4 ms
+            // of cudaFree / cudaMalloc into the second call -- 36 instead of 15 us per step end to end)
+            ensure_history(h, std::max((size_t)seg_len, std::min<size_t>(longest, 4096)) * per_step);
         }
         if (record >= LDM_RECORD_VALUES) std::memcpy(values, init, width * sizeof(double));      // Values[0] (S:568)
         LDM_CUDA(cudaEventRecord(h->ev_begin, s));
