@@ -28,8 +28,12 @@ print(f"G={G} A={(props.MaxNumForM - 1) // 2}: {eq.last_elapsed_ms() / 200 * 1e3
 rows = 148 * 8
 buf = np.zeros((rows, 12), dtype=np.int64)
 lib = ldm.library()
+# one timeline per translation unit: the persistent kernels' (ldm_persist.cu) where one ran, else the per-step kernel's
+lib.ldm_debug_persist_clocks.argtypes = [C.c_void_p, C.c_int]
 lib.ldm_debug_scan_clocks.argtypes = [C.c_void_p, C.c_int]
-assert lib.ldm_debug_scan_clocks(buf.ctypes.data, rows) == 0
+assert lib.ldm_debug_persist_clocks(buf.ctypes.data, rows) == 0
+if not np.any(buf[:, 1] > 0):
+    assert lib.ldm_debug_scan_clocks(buf.ctypes.data, rows) == 0
 names = ["tables (first step only)", "E + running sum + select", "(unused)", "y side", "write-out", "WC rows",
          "(to barrier 1)", "barrier 1", "closing phase", "barrier 2"]
 body = buf[buf[:, 1] > 0]
