@@ -51,3 +51,9 @@ if len(pers):
     col = pers[:, 11] - pers[:, 10]
     print(f"  {'ring share (step start)':28s} mean {col.mean():9.0f}  max {col.max():9.0f} cycles")
     print(f"  step (ring share + mark 0 -> 9) mean {np.mean(pers[:, 9] - pers[:, 0] + col):9.0f} cycles")
+if len(pers) and os.environ.get("LDM_CLOCKS_PER_ROW"):
+    # per row CTA: ring share, E, y side, write-out + closing, barrier wait (cycles of the last step)
+    print("row   ring     E      y    close  barrier")
+    for x in range(len(pers)):
+        r = pers[x]
+        print(f"{x:3d} {r[11] - r[10]:6d} {r[3] - r[1]:6d} {r[4] - r[3]:6d} {r[8] - r[4]:6d} {r[9] - r[8]:6d}")
