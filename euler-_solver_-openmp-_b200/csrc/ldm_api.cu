@@ -68,16 +68,41 @@ void ensure_ring_operator(ldm_context* c)
         for (int point : op.point) present[(size_t)point] = 1;
         d.ring_present = up(present);
     }
-    {   // the CSR rows in contiguous shares of about equal entry count, one share per local grid row (= CTA of the persistent kernel)
+    {   // the CSR rows in contiguous shares of about equal entry count, one share per local grid row (= CTA of the persistent
+        // kernel) -- and of at most one CSR row per warp of that CTA, the shape its shared-memory copy of the share needs (cut by
+        // entries alone, the shares in front of the far rows collect up to 23 short CSR rows at 16 384 points and the copy was
+        // off for every CTA): the smallest entry budget with which the rows fit the shares under both limits
         const int shares = (int)op.grid_row_begin.size() - 1, rows = (int)op.point.size();
         const long long total = (long long)op.node.size();
+        const int cap = d.scan_bn > 0 ? std::max(1, d.scan_nt / 32) : 16;
+        auto length = [&](int r) { return (long long)(op.row_begin[(size_t)r + 1] - op.row_begin[(size_t)r]); };
         std::vector<int> cut((size_t)shares + 1, rows);
         cut[0] = 0;
-        int row = 0;
-        for (int s = 1; s < shares; s++) {
-            const long long want = total * s / shares;
-            while (row < rows && op.row_begin[(size_t)row] < want) row++;
-            cut[(size_t)s] = row;
+        auto deal = [&](long long budget, bool keep) {              // shares the rows take with this entry budget
+            int count = 0, r = 0;
+            while (r < rows) {
+                int n = 0;
+                long long e = 0;
+                while (r < rows && n < cap && (n == 0 || e + length(r) <= budget)) { e += length(r); n++; r++; }
+                count++;
+                if (keep && count < shares) cut[(size_t)count] = r;
+            }
+            return count;
+        };
+        if (rows > 0 && deal(total, false) <= shares) {
+            long long lo = 1, hi = total;                               // smallest budget that needs no more than `shares` shares
+            while (lo < hi) {
+                const long long mid = lo + (hi - lo) / 2;
+                if (deal(mid, false) <= shares) hi = mid; else lo = mid + 1;
+            }
+            deal(lo, true);
+        } else {                                                        // more CSR rows than warps in all CTAs together: by entries alone
+            int row = 0;
+            for (int s = 1; s < shares; s++) {
+                const long long want = total * s / shares;
+                while (row < rows && op.row_begin[(size_t)row] < want) row++;
+                cut[(size_t)s] = row;
+            }
         }
         d.ring_cta_begin = up(cut);
         // shape of the shares, for the persistent kernel's shared-memory copy of its share: the most entries, CSR rows and
@@ -90,6 +115,10 @@ void ensure_ring_operator(ldm_context* c)
             for (int r = r0; r < r1; r++) d.ring_share_row_len = std::max(d.ring_share_row_len, op.row_begin[(size_t)r + 1] - op.row_begin[(size_t)r]);
         }
     }
+#ifdef LDM_PHASE_CLOCKS
+    std::fprintf(stderr, "ring operator: G %d, %d CSR rows, %zu entries; shares: most entries %d, most rows %d, longest row %d\n", d.G,
+                 (int)op.point.size(), op.node.size(), d.ring_share_entries, d.ring_share_rows, d.ring_share_row_len);
+#endif
     d.ring_node = up(op.node);
     d.ring_weight = up(op.weight);
     LDM_CUDA(cudaMemset(c->d_ring, 0, c->P() * sizeof(double)));

@@ -94,6 +94,14 @@ persistent_scan_kernel(const PersistentArgs A)
         __syncthreads();
     }
 
+#ifdef LDM_PHASE_CLOCKS
+    if (tid == 0) {                                  // which SM, and the shape of this CTA's ring share: CSR rows << 32 | entries
+        unsigned int smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_scan_clock[blockIdx.x % (148 * 8)][7] = smid;
+        g_scan_clock[blockIdx.x % (148 * 8)][2] = ((long long)(share_r1 - share_r0) << 32) | (long long)(P.ring_begin[share_r1] - share_e0);
+    }
+#endif
     for (int k = 0; k < A.n_steps; k++) {
         SCAN_MARK(10);
         S.C = A.C[parity]; S.C_next = A.C[parity ^ 1];

@@ -38,7 +38,6 @@ names = ["tables (first step only)", "E + running sum + select", "(unused)", "y 
          "(to barrier 1)", "barrier 1", "closing phase", "barrier 2"]
 body = buf[buf[:, 1] > 0]
 print(f"{len(body)} CTAs ran the row body; body total {np.mean(body[:, 5] - body[:, 0]):.0f} cycles (max {np.max(body[:, 5] - body[:, 0])})")
-body[:, 2] = body[:, 3]
 for i, n in enumerate(names[:5]):
     col = body[:, i + 1] - body[:, i] if i != 1 else body[:, 3] - body[:, 1]
     print(f"  {n:28s} mean {col.mean():9.0f}  max {col.max():9.0f} cycles")
@@ -53,7 +52,7 @@ if len(pers):
     print(f"  step (ring share + mark 0 -> 9) mean {np.mean(pers[:, 9] - pers[:, 0] + col):9.0f} cycles")
 if len(pers) and os.environ.get("LDM_CLOCKS_PER_ROW"):
     # per row CTA: ring share, E, y side, write-out + closing, barrier wait (cycles of the last step)
-    print("row   ring     E      y    close  barrier")
+    print("row   ring     E      y    close  barrier   SM  share: CSR rows, entries")
     for x in range(len(pers)):
         r = pers[x]
-        print(f"{x:3d} {r[11] - r[10]:6d} {r[3] - r[1]:6d} {r[4] - r[3]:6d} {r[8] - r[4]:6d} {r[9] - r[8]:6d}")
+        print(f"{x:3d} {r[11] - r[10]:6d} {r[3] - r[1]:6d} {r[4] - r[3]:6d} {r[8] - r[4]:6d} {r[9] - r[8]:6d}  {r[7]:4d}  {r[2] >> 32:3d} {r[2] & 0xffffffff:6d}")
