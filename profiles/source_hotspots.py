@@ -13,7 +13,7 @@ stalls = [h for h in hdr if h.startswith("stall_") and "Not Issued" not in h]
 agg = {}
 fname = "?"
 for r in rows:
-    if r and r[0] == "File Name":
+    if r and r[0] in ("File Name", "File Path") and len(r) > 1:
         fname = r[1].split("/")[-1]
     if len(r) <= samp or r[2] != "-" or not r[0].isdigit():
         continue
