@@ -97,7 +97,7 @@ __host__ __device__ inline ScanLayout scan_layout(int G, int A, int bn, int NT, 
     L.tap_w = at;   at = align32(at + sizeof(double) * 4 * (size_t)L.a_pad);
     L.qv = at;      at = align32(at + sizeof(double) * (size_t)L.a_pad);
     L.tap_row = at; at = align32(at + sizeof(int) * 4 * (size_t)L.a_pad);
-    L.sel = at;     at = align32(at + sizeof(int2) * (size_t)L.a_pad);
+    L.sel = at;     at = align32(at + sizeof(int4) * (size_t)L.a_pad);                       // rows closed by alpha + q of the first of them
     L.end = at;
     return L;
 }
@@ -234,7 +234,7 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
     double* tap_w = reinterpret_cast<double*>(scan_smem + L.tap_w);      // [a_pad][4] q[alpha] * weights of the four C rows feeding E[alpha]
     double* qv = reinterpret_cast<double*>(scan_smem + L.qv);            // [a_pad]
     int* tap_row = reinterpret_cast<int*>(scan_smem + L.tap_row);        // [a_pad][4] their offsets (slot * G)
-    int2* sel = reinterpret_cast<int2*>(scan_smem + L.sel);              // [a_pad] rows beta closed by alpha
+    int4* sel = reinterpret_cast<int4*>(scan_smem + L.sel);              // [a_pad] rows beta closed by alpha: [x, y), and q[x] (its bits in z, w)
     unsigned short* u_cache = reinterpret_cast<unsigned short*>(scan_smem + L.end);                    // [n_off][G]
     double* w_cache = reinterpret_cast<double*>(scan_smem + align32(L.end + sizeof(unsigned short) * (size_t)n_off * G));
 
@@ -262,7 +262,9 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
         }
         for (int a = tid; a < L.a_pad; a += NT) {
             qv[a] = a < A ? P.qvec[a] : 0.0;
-            sel[a] = a < A ? P.beta_range[a] : make_int2(0, 0);
+            const int2 range = a < A ? P.beta_range[a] : make_int2(0, 0);
+            const double q_first = range.x < range.y ? P.qvec[range.x] : 0.0;    // most alphas close one row: its q comes with the record
+            sel[a] = make_int4(range.x, range.y, __double2loint(q_first), __double2hiint(q_first));
         }
         for (int b = tid; b < A; b += NT) {
             Hs[b * ld + kScanLead - 1] = 0.0;                                 // the zero column (never written again)
@@ -343,11 +345,15 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
                 const double start = base + before;
                 #pragma unroll
                 for (int k = 0; k < kScanUnroll; k++) {
-                    const int2 rows = sel[sc * span + grp * kScanUnroll + k];       // empty beyond A
+                    const int4 rows = sel[sc * span + grp * kScanUnroll + k];       // empty beyond A
                     const double v = live ? start + prefix[k] : 0.0;
                     double* hp = hcol + rows.x * ld;
-                    #pragma unroll 1                           // one row per alpha on average: no unrolled body, no remainder logic
-                    for (int r = rows.x; r < rows.y; r++, hp += ld) *hp = v * qv[r];
+                    if (rows.x < rows.y) {
+                        *hp = v * __hiloint2double(rows.w, rows.z);               // = v * qv[rows.x], without the dependent load
+                        hp += ld;
+                        #pragma unroll 1                       // one row per alpha on average: no unrolled body, no remainder logic
+                        for (int r = rows.x + 1; r < rows.y; r++, hp += ld) *hp = v * qv[r];
+                    }
                 }
                 base += all;
             }
