@@ -695,11 +695,18 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         c->d_deriv = c->alloc<double>(P);
         // structure of the m table: separable inside its disc (every table Properties::Generate builds) -> prefix sums
         d.qvec = nullptr; d.a_star = nullptr; d.beta_range = nullptr; d.scan_piece = nullptr; d.scan_chunk_begin = nullptr; d.scan_warp_begin = nullptr; d.scan_block_begin = nullptr; d.scan_chunk_order = nullptr; d.scan_max_pieces = 0; d.scan_bn = 0; d.scan_chunks = 0; d.scan_nt = 512; d.scan_live_rows = 0;
-        {
-            std::vector<unsigned short> u16(t.axisM.upper.size());
+        {   // the y-side tables of the prefix-sum path, offsets two by two (ldm_scan_body.cuh y_table_index)
+            const int n_even = (d.n_off + 1) & ~1;
+            std::vector<unsigned short> u16((size_t)n_even * d.G, 0);
+            std::vector<double> wp((size_t)n_even * d.G, 0.0);
             for (int n = 0; n < d.G; n++)
-                for (int o = 0; o < d.n_off; o++) u16[(size_t)o * d.G + n] = (unsigned short)t.axisM.upper[(size_t)n * d.n_off + o];
-            d.upper_t16 = c->upload(u16);
+                for (int o = 0; o < d.n_off; o++) {
+                    const size_t at = ((size_t)(o >> 1) * d.G + n) * 2 + (o & 1);
+                    u16[at] = (unsigned short)t.axisM.upper[(size_t)n * d.n_off + o];
+                    wp[at] = t.axisM.weight[(size_t)n * d.n_off + o];
+                }
+            d.upper_p16 = c->upload(u16);
+            d.weight_p = c->upload(wp);
         }
         ldm::detect_separable(t.offM, kSeparableTolerance, c->separable);
         const int scan_bn = (c->separable.ok && d.G <= 65535) ? ldm::scan_pick_bn(d.G, d.A) : 0;

@@ -36,7 +36,8 @@ struct DevProblem {
     const double* qvec;        // [A]
     const int* a_star;         // [A]
     const int2* beta_range;    // [A] rows beta with a_star[beta] == alpha: [x, y)
-    const unsigned short* upper_t16;   // [n_off][G] upper_t in 16 bits
+    const unsigned short* upper_p16;   // upper_t in 16 bits and the weights with the offsets two by two: entry (o, y) at
+    const double* weight_p;            // ((o >> 1) * G + y) * 2 + (o & 1)  (ldm_scan_body.cuh y_table_index); n_off rounded up to even
     // y-side work list (ldm_model.h ScanPieces): pieces (y block, first offset, end offset) dealt out to the warps
     const int4* scan_piece;        // all chunks' pieces
     const int* scan_chunk_begin;   // [scan_chunks + 1] first piece of each chunk

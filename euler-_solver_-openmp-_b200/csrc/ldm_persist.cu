@@ -768,7 +768,7 @@ cudaError_t launch_persistent_scan(const PersistentArgs& args, int grid, cudaStr
                        : scan_unroll_of(P) == 5 ? (const void*)persistent_scan_kernel<false, 5> : (const void*)persistent_scan_kernel<false, 4>;
     // shared memory: the step's working set, then the 16-bit y-side index table, then as many weight rows as still fit
     const size_t base = scan_smem_bytes(G, P.A, P.scan_bn, nt, P.scan_max_pieces);
-    const size_t u_bytes = align32(sizeof(unsigned short) * (size_t)n_off * G);
+    const size_t u_bytes = align32(sizeof(unsigned short) * (size_t)((n_off + 1) & ~1) * G);   // offsets two by two
     PersistentArgs with_cache = args;
     with_cache.cached_w_rows = -1;
     with_cache.ring_cache_offset = -1;
@@ -784,7 +784,7 @@ cudaError_t launch_persistent_scan(const PersistentArgs& args, int grid, cudaStr
         ring_bytes = 0;
     }
     if (base + ring_bytes + u_bytes <= kSmemBudget) {
-        const int rows = (int)std::min<size_t>((size_t)n_off, (kSmemBudget - base - ring_bytes - u_bytes) / ((size_t)G * sizeof(double)));
+        const int rows = (int)std::min<size_t>((size_t)((n_off + 1) & ~1), (kSmemBudget - base - ring_bytes - u_bytes) / ((size_t)G * sizeof(double))) & ~1;
         with_cache.cached_w_rows = rows;
         with_cache.ring_cache_offset = ring_bytes > 0 ? (long long)(base + u_bytes + (size_t)rows * G * sizeof(double)) : -1;
         smem = base + ring_bytes + u_bytes + (size_t)rows * G * sizeof(double);

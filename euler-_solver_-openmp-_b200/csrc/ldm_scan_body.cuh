@@ -141,29 +141,54 @@ __device__ __forceinline__ int folded_offset(int A, int n_fold, int alpha, int f
 // (64 registers), LDM_Y_UNROLL_WIDE in the 512-thread ones (measured: 4 and 6)
 constexpr int kYUnroll = LDM_Y_UNROLL;
 
-// One run of consecutive offsets of the y side in which nothing changes but the position: the H row moves by dh doubles
-// per offset (-ld on the minus side, where beta falls as the offset grows, +ld on the plus side, 0 for the single offset
-// of m == 2), the tables by one row of G entries.  Pointer increments only; the weight source (shared-memory cache or
-// global table) is a template parameter so that every load knows its address space.
-template <bool MASKED, int YU, typename WPtr>
-__device__ __forceinline__ double y_side_run(double s, const double* hrow, int dh, const unsigned short* up, WPtr wp, int G, int n,
-                                             int q0, int bn)
+// One (node y, offset) pair of the y side: hrow[u - 1] * (1 - w) + hrow[u] * w added to s, the roundings spelled out (product,
+// complement, fma, sum).  MASKED: the chunk holds columns [q0, q0 + bn) only; a tap outside them reads one of the two zero
+// columns that flank the tile (index clamped to -1 .. bn), so a pair that straddles a chunk boundary is taken tap by tap in
+// both chunks without a select.
+template <bool MASKED>
+__device__ __forceinline__ double y_side_pair(double s, const double* hrow, int u, double w, int q0, int bn)
 {
-    #pragma unroll YU
-    for (int i = 0; i < n; i++) {
-        const int u = (int)*up;
-        const double w = *wp;
-        if (MASKED) {
-            // the chunk holds columns [q0, q0 + bn): a tap outside them reads one of the two zero columns that flank the tile
-            // (index clamped to -1 .. bn), so a pair that straddles a chunk boundary is taken tap by tap in both chunks
-            // without a select
-            const int ia = min(max(u - 1 - q0, -1), bn), ib = min(max(u - q0, -1), bn);
-            s = __dadd_rn(s, __fma_rn(hrow[q0 + ia], __dadd_rn(1.0, -w), __dmul_rn(hrow[q0 + ib], w)));
-        } else {
-            // hrow[u - 1] * (1 - w) + hrow[u] * w, the roundings spelled out (product, complement, fma, sum)
-            s = __dadd_rn(s, __fma_rn(hrow[u - 1], __dadd_rn(1.0, -w), __dmul_rn(hrow[u], w)));
-        }
-        hrow += dh; up += G; wp += G;
+    if (MASKED) {
+        const int ia = min(max(u - 1 - q0, -1), bn), ib = min(max(u - q0, -1), bn);
+        return __dadd_rn(s, __fma_rn(hrow[q0 + ia], __dadd_rn(1.0, -w), __dmul_rn(hrow[q0 + ib], w)));
+    }
+    return __dadd_rn(s, __fma_rn(hrow[u - 1], __dadd_rn(1.0, -w), __dmul_rn(hrow[u], w)));
+}
+
+// The y-side tables (16-bit interval indices, FP64 weights) hold the offsets two by two: entry (o, y) at
+// ((o >> 1) * G + y) * 2 + (o & 1), so one 4-byte and one 16-byte load fetch a node's entries of two consecutive offsets --
+// three load/store instructions per pair and lane instead of four where the phase is bound by the shared-memory queue.
+__host__ __device__ inline size_t y_table_index(int o, int G, int y) { return ((size_t)(o >> 1) * G + y) * 2 + (o & 1); }
+
+// One run of consecutive offsets [o, o + n) of the y side in which nothing changes but the position: the H row moves by dh
+// doubles per offset (-ld on the minus side, where beta falls as the offset grows, +ld on the plus side, 0 for the single
+// offset of m == 2).  Offsets in order, the same accumulation whichever way the entries were fetched.  U_SHARED / W_SHARED:
+// the table lives in shared memory (the persistent kernel's copies) or in global memory, so every load knows its space.
+template <bool MASKED, bool U_SHARED, bool W_SHARED, int YU>
+__device__ __forceinline__ double y_side_run(double s, const double* hrow, int dh, const unsigned short* u_table, const double* w_table,
+                                             int G, int y, int o, int n, int q0, int bn)
+{
+    __builtin_assume(U_SHARED ? __isShared(u_table) : __isGlobal(u_table));
+    __builtin_assume(W_SHARED ? __isShared(w_table) : __isGlobal(w_table));
+    if ((o & 1) && n > 0) {                                    // the second entry of a pair of offsets first
+        const size_t at = y_table_index(o, G, y);
+        s = y_side_pair<MASKED>(s, hrow, (int)u_table[at], w_table[at], q0, bn);
+        hrow += dh; o++; n--;
+    }
+    const size_t at = y_table_index(o, G, y);                  // o is even
+    const unsigned int* up = reinterpret_cast<const unsigned int*>(u_table + at);
+    const double2* wp = reinterpret_cast<const double2*>(w_table + at);
+    #pragma unroll (YU / 2)
+    for (int i = 0; i < (n >> 1); i++) {
+        const unsigned int uu = *up;
+        const double2 ww = *wp;
+        s = y_side_pair<MASKED>(s, hrow, (int)(uu & 0xffffu), ww.x, q0, bn);
+        s = y_side_pair<MASKED>(s, hrow + dh, (int)(uu >> 16), ww.y, q0, bn);
+        hrow += 2 * dh; up += G; wp += G;
+    }
+    if (n & 1) {                                               // and the first entry of the last pair
+        const size_t last = y_table_index(o + n - 1, G, y);
+        s = y_side_pair<MASKED>(s, hrow, (int)u_table[last], w_table[last], q0, bn);
     }
     return s;
 }
@@ -187,11 +212,10 @@ __device__ __forceinline__ double y_side_interval(const DevProblem& P, const dou
         if (w_shared) end = min(end, cached_w_rows);
         const int beta = single ? 0 : (minus ? A - 1 - o : o - A);
         const int dh = single ? 0 : (minus ? -ld : ld);
-        const size_t at = (size_t)o * G + y;
         const double* hrow = Hs + beta * ld + kScanLead - q0;
-        const unsigned short* up = (CACHED ? u_cache : P.upper_t16) + at;
-        if (w_shared) s = y_side_run<MASKED, YU>(s, hrow, dh, up, w_cache + at, G, end - o, q0, bn);
-        else s = y_side_run<MASKED, YU>(s, hrow, dh, up, P.weight_t + at, G, end - o, q0, bn);
+        if (w_shared) s = y_side_run<MASKED, true, true, YU>(s, hrow, dh, u_cache, w_cache, G, y, o, end - o, q0, bn);
+        else if (CACHED) s = y_side_run<MASKED, true, false, YU>(s, hrow, dh, u_cache, P.weight_p, G, y, o, end - o, q0, bn);
+        else s = y_side_run<MASKED, false, false, YU>(s, hrow, dh, P.upper_p16, P.weight_p, G, y, o, end - o, q0, bn);
         o = end;
     }
     return s;
@@ -236,13 +260,14 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
     int* tap_row = reinterpret_cast<int*>(scan_smem + L.tap_row);        // [a_pad][4] their offsets (slot * G)
     int4* sel = reinterpret_cast<int4*>(scan_smem + L.sel);              // [a_pad] rows beta closed by alpha: [x, y), and q[x] (its bits in z, w)
     unsigned short* u_cache = reinterpret_cast<unsigned short*>(scan_smem + L.end);                    // [n_off][G]
-    double* w_cache = reinterpret_cast<double*>(scan_smem + align32(L.end + sizeof(unsigned short) * (size_t)n_off * G));
+    double* w_cache = reinterpret_cast<double*>(scan_smem + align32(L.end + sizeof(unsigned short) * (size_t)((n_off + 1) & ~1) * G));
 
     SCAN_MARK(0);
     if (build_tables) {
         if (cached_w_rows >= 0) {
-            for (int i = tid; i < n_off * G; i += NT) u_cache[i] = P.upper_t16[i];
-            for (int i = tid; i < cached_w_rows * G; i += NT) w_cache[i] = P.weight_t[i];
+            const int n_even = (n_off + 1) & ~1;                              // the tables hold the offsets two by two
+            for (int i = tid; i < n_even * G; i += NT) u_cache[i] = P.upper_p16[i];
+            for (int i = tid; i < cached_w_rows * G; i += NT) w_cache[i] = P.weight_p[i];   // cached_w_rows is even
         }
         for (int t = tid; t < L.a_pad * 2; t += NT) {
             const int alpha = t >> 1, f = t & 1;
