@@ -73,7 +73,7 @@ constexpr size_t kSmemBudget = 226 * 1024; // dynamic shared memory a CTA of thi
 
 struct ScanLayout {                       // byte offsets into dynamic shared memory, identical on host and device
     int ld, a_pad, n_yblk, part_stride, ng;
-    size_t hs, part, rowsum, rowbuf, bsum, tap_w, qv, tap_row, sel, end;
+    size_t hs, part, rowsum, rowbuf, bsum, tap_w, qv, tap_row, sel, work, end;
 };
 
 __host__ __device__ inline size_t align32(size_t v) { return (v + 31) & ~(size_t)31; }
@@ -98,6 +98,9 @@ __host__ __device__ inline ScanLayout scan_layout(int G, int A, int bn, int NT, 
     L.qv = at;      at = align32(at + sizeof(double) * (size_t)L.a_pad);
     L.tap_row = at; at = align32(at + sizeof(int) * 4 * (size_t)L.a_pad);
     L.sel = at;     at = align32(at + sizeof(int4) * (size_t)L.a_pad);                       // rows closed by alpha + q of the first of them
+    // the chunk's y-side work list (pieces, first piece of every warp and of every y block): read once per table build instead
+    // of from global memory in front of every piece
+    L.work = at;    at = align32(at + sizeof(int4) * (size_t)pieces + sizeof(int) * (size_t)(NT / 32 + 1 + L.n_yblk + 1));
     L.end = at;
     return L;
 }
@@ -259,6 +262,9 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
     double* qv = reinterpret_cast<double*>(scan_smem + L.qv);            // [a_pad]
     int* tap_row = reinterpret_cast<int*>(scan_smem + L.tap_row);        // [a_pad][4] their offsets (slot * G)
     int4* sel = reinterpret_cast<int4*>(scan_smem + L.sel);              // [a_pad] rows beta closed by alpha: [x, y), and q[x] (its bits in z, w)
+    int4* work_piece = reinterpret_cast<int4*>(scan_smem + L.work);      // [pieces] this chunk's y-side pieces (y block, first offset, end offset)
+    int* work_warp_begin = reinterpret_cast<int*>(work_piece + P.scan_max_pieces);   // [warps + 1] first piece of every warp
+    int* work_block_begin = work_warp_begin + NT / 32 + 1;               // [n_yblk + 1] first piece of every y block
     unsigned short* u_cache = reinterpret_cast<unsigned short*>(scan_smem + L.end);                    // [n_off][G]
     double* w_cache = reinterpret_cast<double*>(scan_smem + align32(L.end + sizeof(unsigned short) * (size_t)((n_off + 1) & ~1) * G));
 
@@ -284,6 +290,12 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
             }
             tap_w[alpha * 4 + f * 2] = w_lo; tap_w[alpha * 4 + f * 2 + 1] = w_hi;
             tap_row[alpha * 4 + f * 2] = r_lo; tap_row[alpha * 4 + f * 2 + 1] = r_hi;
+        }
+        if (cached_w_rows >= 0) {                                             // tables built once per launch (the one-chunk persistent kernel)
+            const int first = P.scan_chunk_begin[chunk], n_pieces = P.scan_chunk_begin[chunk + 1] - first, warps = NT / 32;
+            for (int i = tid; i < n_pieces; i += NT) work_piece[i] = P.scan_piece[first + i];
+            for (int i = tid; i <= warps; i += NT) work_warp_begin[i] = P.scan_warp_begin[chunk * (warps + 1) + i];
+            for (int i = tid; i <= L.n_yblk; i += NT) work_block_begin[i] = P.scan_block_begin[chunk * (L.n_yblk + 1) + i];
         }
         for (int a = tid; a < L.a_pad; a += NT) {
             qv[a] = a < A ? P.qvec[a] : 0.0;
@@ -390,13 +402,16 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
 
     // ---- y side ----
     {
-        const int warp = tid >> 5, lane = tid & 31, warps = NT / 32;
+        const int warp = tid >> 5, lane = tid & 31;
         const bool masked = P.scan_chunks > 1;
         // (node, offset) pairs in flight per lane: the 256-thread CTAs live within 64 registers, the 512-thread ones can afford more
         constexpr int kYU = kScanUnroll == 2 ? kYUnroll : LDM_Y_UNROLL_WIDE;
-        const int4* pieces = P.scan_piece + P.scan_chunk_begin[chunk];
-        const int* warp_begin = P.scan_warp_begin + chunk * (warps + 1);
-        const int* block_begin = P.scan_block_begin + chunk * (L.n_yblk + 1);
+        // the work list: from shared memory where the tables are built once per launch (no global round trip in front of every
+        // piece); a kernel that rebuilds its tables per item reads it where it lies (measured: staging it per item gains nothing)
+        const bool staged = cached_w_rows >= 0;
+        const int4* pieces = staged ? work_piece : P.scan_piece + P.scan_chunk_begin[chunk];
+        const int* warp_begin = staged ? work_warp_begin : P.scan_warp_begin + chunk * (NT / 32 + 1);
+        const int* block_begin = staged ? work_block_begin : P.scan_block_begin + chunk * (L.n_yblk + 1);
         for (int pi = warp_begin[warp]; pi < warp_begin[warp + 1]; pi++) {
             const int4 pc = pieces[pi];                        // y block, first offset, end offset
             const int y = min(pc.x * 32 + lane, G - 1);
