@@ -155,7 +155,7 @@ persistent_scan_kernel(const PersistentArgs A)
                 for (int j = 0; j < 4; j++) wc_part[j] = lane + 32 * j < G ? wc_rows_now[lane + 32 * j] : 0.0;
             }
         };
-        scan_body_of<SMALL, U>(S, 0, x, k == 0, A.cached_w_rows, true, mid);   // ends with a CTA barrier
+        scan_body_of<SMALL, U, decltype(mid), NoGate, true>(S, 0, x, k == 0, A.cached_w_rows, true, mid);   // ends with a CTA barrier
         SCAN_MARK(6);
         if (warp == last_warp) {                                   // wc_total(): the same order, from the registers
             double t = 0.0;

@@ -237,7 +237,9 @@ struct NoGate {
     __device__ bool bypass() const { return false; }
 };
 
-template <int kScanUnroll, typename Mid = NoMid, typename Gate = NoGate>
+// STAGED_WORK: the chunk's y-side work list is copied to shared memory when the tables are built (kernels that build them once
+// per launch); otherwise it is read where it lies.
+template <int kScanUnroll, typename Mid = NoMid, typename Gate = NoGate, bool STAGED_WORK = false>
 __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, const int lx, const bool build_tables,
                                           const int cached_w_rows, const bool fused = false, Mid mid = Mid(), Gate gate = Gate())
 {
@@ -291,7 +293,7 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
             tap_w[alpha * 4 + f * 2] = w_lo; tap_w[alpha * 4 + f * 2 + 1] = w_hi;
             tap_row[alpha * 4 + f * 2] = r_lo; tap_row[alpha * 4 + f * 2 + 1] = r_hi;
         }
-        if (cached_w_rows >= 0) {                                             // tables built once per launch (the one-chunk persistent kernel)
+        if (STAGED_WORK) {                                                    // tables built once per launch (the one-chunk persistent kernel)
             const int first = P.scan_chunk_begin[chunk], n_pieces = P.scan_chunk_begin[chunk + 1] - first, warps = NT / 32;
             for (int i = tid; i < n_pieces; i += NT) work_piece[i] = P.scan_piece[first + i];
             for (int i = tid; i <= warps; i += NT) work_warp_begin[i] = P.scan_warp_begin[chunk * (warps + 1) + i];
@@ -408,10 +410,9 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
         constexpr int kYU = kScanUnroll == 2 ? kYUnroll : LDM_Y_UNROLL_WIDE;
         // the work list: from shared memory where the tables are built once per launch (no global round trip in front of every
         // piece); a kernel that rebuilds its tables per item reads it where it lies (measured: staging it per item gains nothing)
-        const bool staged = cached_w_rows >= 0;
-        const int4* pieces = staged ? work_piece : P.scan_piece + P.scan_chunk_begin[chunk];
-        const int* warp_begin = staged ? work_warp_begin : P.scan_warp_begin + chunk * (NT / 32 + 1);
-        const int* block_begin = staged ? work_block_begin : P.scan_block_begin + chunk * (L.n_yblk + 1);
+        const int4* pieces = STAGED_WORK ? work_piece : P.scan_piece + P.scan_chunk_begin[chunk];
+        const int* warp_begin = STAGED_WORK ? work_warp_begin : P.scan_warp_begin + chunk * (NT / 32 + 1);
+        const int* block_begin = STAGED_WORK ? work_block_begin : P.scan_block_begin + chunk * (L.n_yblk + 1);
         for (int pi = warp_begin[warp]; pi < warp_begin[warp + 1]; pi++) {
             const int4 pc = pieces[pi];                        // y block, first offset, end offset
             const int y = min(pc.x * 32 + lane, G - 1);
@@ -450,15 +451,15 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
 // scan_body with the unroll factor of this CTA shape: U = 4 or 5 when the launch picked the kernel instance by it (the
 // single-problem kernels: each instance keeps its own register allocation), U = 0 to decide here by a uniform branch (batch
 // launches, whose members may differ)
-template <bool SMALL, int U, typename Mid = NoMid, typename Gate = NoGate>
+template <bool SMALL, int U, typename Mid = NoMid, typename Gate = NoGate, bool STAGED_WORK = false>
 __device__ __forceinline__ void scan_body_of(const StepArgs& S, const int chunk, const int lx, const bool build_tables,
                                              const int cached_w_rows, const bool fused = false, Mid mid = Mid(), Gate gate = Gate())
 {
-    if (SMALL) { scan_body<2>(S, chunk, lx, build_tables, cached_w_rows, fused, mid, gate); return; }
-    if (U != 0) { scan_body<(U == 0 ? 4 : U)>(S, chunk, lx, build_tables, cached_w_rows, fused, mid, gate); return; }
+    if (SMALL) { scan_body<2, Mid, Gate, STAGED_WORK>(S, chunk, lx, build_tables, cached_w_rows, fused, mid, gate); return; }
+    if (U != 0) { scan_body<(U == 0 ? 4 : U), Mid, Gate, STAGED_WORK>(S, chunk, lx, build_tables, cached_w_rows, fused, mid, gate); return; }
     const int ng = (int)blockDim.x / S.P.scan_bn > 1 ? (int)blockDim.x / S.P.scan_bn : 1;
-    if (scan_unroll((int)blockDim.x, S.P.A, ng) == 5) scan_body<5>(S, chunk, lx, build_tables, cached_w_rows, fused, mid, gate);
-    else scan_body<4>(S, chunk, lx, build_tables, cached_w_rows, fused, mid, gate);
+    if (scan_unroll((int)blockDim.x, S.P.A, ng) == 5) scan_body<5, Mid, Gate, STAGED_WORK>(S, chunk, lx, build_tables, cached_w_rows, fused, mid, gate);
+    else scan_body<4, Mid, Gate, STAGED_WORK>(S, chunk, lx, build_tables, cached_w_rows, fused, mid, gate);
 }
 
 // ---- hand-overs between CTAs (persistent kernels) ----
