@@ -783,8 +783,13 @@ cudaError_t launch_persistent_scan(const PersistentArgs& args, int grid, cudaStr
     } else {
         ring_bytes = 0;
     }
-    if (base + ring_bytes + u_bytes <= kSmemBudget) {
-        const int rows = (int)std::min<size_t>((size_t)((n_off + 1) & ~1), (kSmemBudget - base - ring_bytes - u_bytes) / ((size_t)G * sizeof(double))) & ~1;
+    // The weight rows do not get all that is left: shared memory and L1 share the SM's 256 KB, and the E phase lives on L1 hits
+    // for the tap rows that neighbouring alphas share.  Measured at 16 384 points (us per step against the budget of this
+    // launch's shared memory): 226 KB 12.01, 196 KB 11.73, 164 KB 11.77, 132 KB and less 12.30 (the index table no longer fits).
+    constexpr size_t kCachedRowsBudget = 196 * 1024;
+    const size_t budget = std::min(kSmemBudget, kCachedRowsBudget);
+    if (base + ring_bytes + u_bytes <= budget) {
+        const int rows = (int)std::min<size_t>((size_t)((n_off + 1) & ~1), (budget - base - ring_bytes - u_bytes) / ((size_t)G * sizeof(double))) & ~1;
         with_cache.cached_w_rows = rows;
         with_cache.ring_cache_offset = ring_bytes > 0 ? (long long)(base + u_bytes + (size_t)rows * G * sizeof(double)) : -1;
         smem = base + ring_bytes + u_bytes + (size_t)rows * G * sizeof(double);
