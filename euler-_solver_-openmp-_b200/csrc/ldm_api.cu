@@ -694,7 +694,7 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         c->d_sum = c->alloc<double>(P);
         c->d_deriv = c->alloc<double>(P);
         // structure of the m table: separable inside its disc (every table Properties::Generate builds) -> prefix sums
-        d.qvec = nullptr; d.a_star = nullptr; d.beta_range = nullptr; d.scan_piece = nullptr; d.scan_chunk_begin = nullptr; d.scan_warp_begin = nullptr; d.scan_block_begin = nullptr; d.scan_chunk_order = nullptr; d.scan_max_pieces = 0; d.scan_bn = 0; d.scan_chunks = 0; d.scan_nt = 512; d.scan_live_rows = 0;
+        d.qvec = nullptr; d.a_star = nullptr; d.beta_range = nullptr; d.scan_piece = nullptr; d.scan_chunk_begin = nullptr; d.scan_warp_begin = nullptr; d.scan_block_begin = nullptr; d.scan_chunk_order = nullptr; d.upper_c16 = nullptr; d.scan_max_pieces = 0; d.scan_bn = 0; d.scan_chunks = 0; d.scan_nt = 512; d.scan_live_rows = 0;
         {   // the y-side tables of the prefix-sum path, offsets two by two (ldm_scan_body.cuh y_table_index)
             const int n_even = (d.n_off + 1) & ~1;
             std::vector<unsigned short> u16((size_t)n_even * d.G, 0);
@@ -727,6 +727,19 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
             d.scan_warp_begin = c->upload(pieces.warp_begin);
             d.scan_block_begin = c->upload(pieces.block_begin);
             d.scan_max_pieces = pieces.max_pieces;
+            if (d.scan_chunks > 1) {
+                // per chunk: where a pair lies in a row of the chunk's H tile (lead columns included), clamped to the zero columns
+                const int n_even = (d.n_off + 1) & ~1, lead = ldm::scan_lead_columns();
+                std::vector<unsigned short> pos((size_t)d.scan_chunks * n_even * d.G, 0);
+                for (int ch = 0; ch < d.scan_chunks; ch++)
+                    for (int n = 0; n < d.G; n++)
+                        for (int o = 0; o < d.n_off; o++) {
+                            const int at_column = t.axisM.upper[(size_t)n * d.n_off + o] - ch * scan_bn;     // the pair reads columns at_column - 1, at_column
+                            const int clamped = std::min(std::max(at_column, -1), scan_bn + 1);
+                            pos[(size_t)ch * n_even * d.G + ((size_t)(o >> 1) * d.G + n) * 2 + (o & 1)] = (unsigned short)(lead - 1 + clamped);
+                        }
+                d.upper_c16 = c->upload(pos);
+            }
             {
                 std::vector<long long> work((size_t)d.scan_chunks, 0);
                 for (int ch = 0; ch < d.scan_chunks; ch++)

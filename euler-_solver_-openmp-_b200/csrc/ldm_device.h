@@ -38,6 +38,8 @@ struct DevProblem {
     const int2* beta_range;    // [A] rows beta with a_star[beta] == alpha: [x, y)
     const unsigned short* upper_p16;   // upper_t in 16 bits and the weights with the offsets two by two: entry (o, y) at
     const double* weight_p;            // ((o >> 1) * G + y) * 2 + (o & 1)  (ldm_scan_body.cuh y_table_index); n_off rounded up to even
+    const unsigned short* upper_c16;   // rows of several chunks: [scan_chunks] tables like upper_p16 holding the pair's position in the
+                                       // chunk's H tile row, clamped to its zero columns (ldm_scan_body.cuh y_side_pair); else NULL
     // y-side work list (ldm_model.h ScanPieces): pieces (y block, first offset, end offset) dealt out to the warps
     const int4* scan_piece;        // all chunks' pieces
     const int* scan_chunk_begin;   // [scan_chunks + 1] first piece of each chunk
@@ -230,6 +232,7 @@ int scan_pick_threads(int G, int A, int bn);
 void launch_scan(const StepArgs& one, cudaStream_t stream);
 void launch_scan_batch(const StepArgs* d_batch, int n, int nt, int max_chunks, int max_rows, size_t max_smem, cudaStream_t stream);
 size_t scan_smem_bytes(int G, int A, int bn, int nt, int max_pieces);
+int scan_lead_columns();                       // doubles in front of column 0 of a row of the H tile
 cudaError_t launch_persistent_scan(const PersistentArgs& args, int grid, cudaStream_t stream, int* max_grid);
 // single problem: `one` by value; batch: d_batch[n] in device memory, all entries sharing the plan's tile shape
 void launch_factored(const FactoredPlan& plan, const StepArgs& one, cudaStream_t stream);

@@ -69,6 +69,8 @@ int scan_pick_bn(int G, int A)
     return even < bn ? even : bn;
 }
 
+int scan_lead_columns() { return kScanLead; }
+
 template <bool BATCH, bool SMALL, int U>
 static void launch_scan_shape(const StepArgs* one, const StepArgs* d_batch, dim3 grid, int nt, size_t smem, cudaStream_t stream)
 {

@@ -89,7 +89,7 @@ __host__ __device__ inline ScanLayout scan_layout(int G, int A, int bn, int NT, 
     const int span = L.ng * scan_unroll(NT, A, L.ng);
     L.a_pad = ((A + span - 1) / span) * span;             // whole super-chunks (zero-weight rows behind A)
     size_t at = 0;
-    L.hs = at;      at = align32(at + sizeof(double) * (size_t)A * L.ld);
+    L.hs = at;      at = align32(at + sizeof(double) * ((size_t)A * L.ld + 1));             // + the zero behind the last row's right zero column
     L.part = at;    at = align32(at + sizeof(double) * 32 * (size_t)pieces);
     L.rowsum = at;  at = align32(at + sizeof(double) * (size_t)L.part_stride);
     L.rowbuf = at;  at = align32(at + sizeof(double) * 2 * (size_t)L.part_stride);   // persistent kernel: the new row of C, the row of the WC functional
@@ -145,16 +145,15 @@ __device__ __forceinline__ int folded_offset(int A, int n_fold, int alpha, int f
 constexpr int kYUnroll = LDM_Y_UNROLL;
 
 // One (node y, offset) pair of the y side: hrow[u - 1] * (1 - w) + hrow[u] * w added to s, the roundings spelled out (product,
-// complement, fma, sum).  MASKED: the chunk holds columns [q0, q0 + bn) only; a tap outside them reads one of the two zero
-// columns that flank the tile (index clamped to -1 .. bn), so a pair that straddles a chunk boundary is taken tap by tap in
-// both chunks without a select.
+// complement, fma, sum).  MASKED (rows of several chunks): the tile holds columns [q0, q0 + bn) only, and `u` is the pair's
+// POSITION in the tile's row -- kScanLead - 1 + (upper - q0), clamped on the host to [0, kScanLead + bn] (DevProblem
+// upper_c16, one table per chunk) -- so that a tap outside the chunk's columns reads one of the zero columns that flank the tile
+// (two on either side: a pair that lies outside altogether reads two of them) and a pair that straddles a chunk boundary is
+// taken tap by tap in both chunks, without a clamp or a select on the device; hrow then points at the row's first lead column.
 template <bool MASKED>
-__device__ __forceinline__ double y_side_pair(double s, const double* hrow, int u, double w, int q0, int bn)
+__device__ __forceinline__ double y_side_pair(double s, const double* hrow, int u, double w)
 {
-    if (MASKED) {
-        const int ia = min(max(u - 1 - q0, -1), bn), ib = min(max(u - q0, -1), bn);
-        return __dadd_rn(s, __fma_rn(hrow[q0 + ia], __dadd_rn(1.0, -w), __dmul_rn(hrow[q0 + ib], w)));
-    }
+    if (MASKED) return __dadd_rn(s, __fma_rn(hrow[u], __dadd_rn(1.0, -w), __dmul_rn(hrow[u + 1], w)));
     return __dadd_rn(s, __fma_rn(hrow[u - 1], __dadd_rn(1.0, -w), __dmul_rn(hrow[u], w)));
 }
 
@@ -169,13 +168,13 @@ __host__ __device__ inline size_t y_table_index(int o, int G, int y) { return ((
 // the table lives in shared memory (the persistent kernel's copies) or in global memory, so every load knows its space.
 template <bool MASKED, bool U_SHARED, bool W_SHARED, int YU>
 __device__ __forceinline__ double y_side_run(double s, const double* hrow, int dh, const unsigned short* u_table, const double* w_table,
-                                             int G, int y, int o, int n, int q0, int bn)
+                                             int G, int y, int o, int n)
 {
     __builtin_assume(U_SHARED ? __isShared(u_table) : __isGlobal(u_table));
     __builtin_assume(W_SHARED ? __isShared(w_table) : __isGlobal(w_table));
     if ((o & 1) && n > 0) {                                    // the second entry of a pair of offsets first
         const size_t at = y_table_index(o, G, y);
-        s = y_side_pair<MASKED>(s, hrow, (int)u_table[at], w_table[at], q0, bn);
+        s = y_side_pair<MASKED>(s, hrow, (int)u_table[at], w_table[at]);
         hrow += dh; o++; n--;
     }
     const size_t at = y_table_index(o, G, y);                  // o is even
@@ -185,13 +184,13 @@ __device__ __forceinline__ double y_side_run(double s, const double* hrow, int d
     for (int i = 0; i < (n >> 1); i++) {
         const unsigned int uu = *up;
         const double2 ww = *wp;
-        s = y_side_pair<MASKED>(s, hrow, (int)(uu & 0xffffu), ww.x, q0, bn);
-        s = y_side_pair<MASKED>(s, hrow + dh, (int)(uu >> 16), ww.y, q0, bn);
+        s = y_side_pair<MASKED>(s, hrow, (int)(uu & 0xffffu), ww.x);
+        s = y_side_pair<MASKED>(s, hrow + dh, (int)(uu >> 16), ww.y);
         hrow += 2 * dh; up += G; wp += G;
     }
     if (n & 1) {                                               // and the first entry of the last pair
         const size_t last = y_table_index(o + n - 1, G, y);
-        s = y_side_pair<MASKED>(s, hrow, (int)u_table[last], w_table[last], q0, bn);
+        s = y_side_pair<MASKED>(s, hrow, (int)u_table[last], w_table[last]);
     }
     return s;
 }
@@ -215,10 +214,12 @@ __device__ __forceinline__ double y_side_interval(const DevProblem& P, const dou
         if (w_shared) end = min(end, cached_w_rows);
         const int beta = single ? 0 : (minus ? A - 1 - o : o - A);
         const int dh = single ? 0 : (minus ? -ld : ld);
-        const double* hrow = Hs + beta * ld + kScanLead - q0;
-        if (w_shared) s = y_side_run<MASKED, true, true, YU>(s, hrow, dh, u_cache, w_cache, G, y, o, end - o, q0, bn);
-        else if (CACHED) s = y_side_run<MASKED, true, false, YU>(s, hrow, dh, u_cache, P.weight_p, G, y, o, end - o, q0, bn);
-        else s = y_side_run<MASKED, false, false, YU>(s, hrow, dh, P.upper_p16, P.weight_p, G, y, o, end - o, q0, bn);
+        // MASKED: positions in the tile's row from this chunk's table; otherwise interval indices, the row shifted to column 0
+        const double* hrow = Hs + beta * ld + (MASKED ? 0 : kScanLead - q0);
+        const unsigned short* u_global = MASKED ? P.upper_c16 + (size_t)(q0 / bn) * ((P.n_off + 1) & ~1) * G : P.upper_p16;
+        if (w_shared) s = y_side_run<MASKED, true, true, YU>(s, hrow, dh, u_cache, w_cache, G, y, o, end - o);
+        else if (CACHED) s = y_side_run<MASKED, true, false, YU>(s, hrow, dh, u_cache, P.weight_p, G, y, o, end - o);
+        else s = y_side_run<MASKED, false, false, YU>(s, hrow, dh, u_global, P.weight_p, G, y, o, end - o);
         o = end;
     }
     return s;
@@ -307,8 +308,12 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
         }
         for (int b = tid; b < A; b += NT) {
             Hs[b * ld + kScanLead - 1] = 0.0;                                 // the zero column (never written again)
-            if (P.scan_chunks > 1) Hs[b * ld + kScanLead + bn] = 0.0;         // and the one behind the chunk's last column
+            if (P.scan_chunks > 1) {                                          // several chunks: two zero columns on either side (y_side_pair)
+                Hs[b * ld] = 0.0;
+                Hs[b * ld + kScanLead + bn] = 0.0;                            // its right neighbour is the next row's first lead column
+            }
         }
+        if (tid == 0 && P.scan_chunks > 1) Hs[A * ld] = 0.0;                 // ... or, behind the last row, this
         // empty rows of the table (a suffix: a_star never grows with beta) are never closed: zero them once
         for (int i = P.scan_live_rows * ld + tid; i < A * ld; i += NT) Hs[i] = 0.0;
         __syncthreads();
