@@ -38,7 +38,7 @@
 #define LDM_Y_UNROLL 4
 #endif
 #ifndef LDM_Y_UNROLL_WIDE
-#define LDM_Y_UNROLL_WIDE 6
+#define LDM_Y_UNROLL_WIDE 8
 #endif
 
 namespace ldm {
@@ -141,7 +141,7 @@ __device__ __forceinline__ int folded_offset(int A, int n_fold, int alpha, int f
 }
 
 // (node, offset) pairs of the y side whose table reads are in flight together per lane: LDM_Y_UNROLL in the 256-thread CTAs
-// (64 registers), LDM_Y_UNROLL_WIDE in the 512-thread ones (measured: 4 and 6)
+// (64 registers), LDM_Y_UNROLL_WIDE in the 512-thread ones (measured: 4 and, with the offsets fetched two by two, 8: 6 and 12 are slower)
 constexpr int kYUnroll = LDM_Y_UNROLL;
 
 // One (node y, offset) pair of the y side: hrow[u - 1] * (1 - w) + hrow[u] * w added to s, the roundings spelled out (product,
