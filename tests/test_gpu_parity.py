@@ -788,6 +788,31 @@ def test_history_leaves_in_segments(ldm):
     assert np.array_equal(eq(0.0, full.Values[650]), full.Derivatives[650])
 
 
+@pytest.mark.parametrize("G", [0, 200])
+def test_history_straight_into_pinned_host_buffers(ldm, G):
+    """Values / Derivatives / observables buffers in pinned, mapped host memory: the persistent kernel stores the history
+    straight into them (one launch for the whole solve); identical to the route through device-side segments that pageable
+    buffers take, in every record mode, for a one-chunk grid and a chunked one"""
+    import torch
+    props = ldm.Properties.Generate(1, 0.12, 0.09, 0.4, 0.2, 0.001, G)
+    eq = ldm.Equation(props)
+    g = props.MomentsGrid
+    init = eq.GenerateEquilibriumValuesForNAndC(200)
+    init[1:] *= (1 + 0.5 * np.exp(-(g[:, None] ** 2 + g[None, :] ** 2) / (2 * 0.1 ** 2))).ravel()
+    points, width = 23, 1 + props.G ** 2
+    t_max = (points - 0.5) * 0.1
+    want = ldm.EulerSolver().Solve(eq, ldm.SquaredN, t_max, 0.1, init, record=ldm.RECORD_ALL)
+    values = torch.full((points * width,), float("nan"), dtype=torch.float64).pin_memory().numpy()
+    derivs = torch.full((points * width,), float("nan"), dtype=torch.float64).pin_memory().numpy()
+    before = eq.launches
+    got = ldm.EulerSolver().Solve(eq, ldm.SquaredN, t_max, 0.1, init, record=ldm.RECORD_ALL, values_out=values, derivs_out=derivs)
+    assert eq.launches - before <= 6                            # the stepping is one launch (+ the last derivative's three)
+    assert np.array_equal(got.Values, want.Values) and np.array_equal(got.Derivatives, want.Derivatives)
+    values[:] = np.nan
+    got = ldm.EulerSolver().Solve(eq, ldm.SquaredN, t_max, 0.1, init, record=ldm.RECORD_VALUES, values_out=values)
+    assert np.array_equal(got.Values, want.Values)
+
+
 def test_large_grid_properties(ldm):
     """BASELINE config 3 (G = 128): too slow for the CPU oracle in a test, so check what the domain offers:
     the spatially uniform state C = N^2 must give dC ~ 2bN m(xi) - 2d'N^2 w(xi)... exactly the structure of the
