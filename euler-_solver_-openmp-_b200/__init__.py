@@ -311,7 +311,7 @@ class EulerSolver:
         if record == RECORD_LAST:
             values, derivs = np.empty((1, width)), np.empty((1, width))
         elif record == RECORD_OBSERVABLES:
-            obs = np.empty((n, 2))
+            obs = np.empty((n, 2)) if values_out is None else values_out.reshape(-1)[:n * 2].reshape(n, 2)
         else:
             values = np.empty((n, width)) if values_out is None else values_out.reshape(-1)[:n * width].reshape(n, width)
             derivs = None

@@ -380,7 +380,10 @@ bool persistent_possible(ldm_context* c)
 }
 
 // n_steps Euler steps from the resident state; history pointers (device) may be NULL.
-void advance_persistent(ldm_context* c, int n_steps, double dt, long long first_point, double* d_obs, double* d_values, double* d_derivs)
+// rhs_only_last (prefix-sum path): the last of the n_steps only evaluates the right-hand side at its state -- the derivative of
+// the last point of a solve (S:582-583) inside the same launch -- and advances nothing.
+void advance_persistent(ldm_context* c, int n_steps, double dt, long long first_point, double* d_obs, double* d_values, double* d_derivs,
+                        bool rhs_only_last = false)
 {
     if (n_steps <= 0) return;
     ensure_ring_operator(c);
@@ -395,9 +398,20 @@ void advance_persistent(ldm_context* c, int n_steps, double dt, long long first_
     args.observables = d_obs; args.values = d_values; args.derivs = d_derivs;
     args.wc_rows = c->d_wc_rows2; args.barrier = c->d_barrier;
     args.status = c->d_status;
+    const int advanced = n_steps - (rhs_only_last && c->plan.scan ? 1 : 0);
     if (c->plan.scan) {
-        if (!c->d_ring2) c->d_ring2 = c->alloc<double>(2 * c->P());
-        LDM_CUDA(cudaMemsetAsync(c->d_ring2, 0xFF, 2 * c->P() * sizeof(double), c->stream));      // every entry: not yet published
+        // The arrival counter of the grid barrier is monotone and the ring hand-over slots are back at "not yet published" when a
+        // launch has run to its end, so neither is reset per launch (two memsets in front of every launch cost 5 us of a
+        // 20-step solve): only before the first launch, after one that timed out, and long before the counter could wrap.
+        if (!c->d_ring2) { c->d_ring2 = c->alloc<double>(2 * c->P()); c->persistent_dirty = true; }
+        if (c->persistent_dirty || c->barriers_done > (1u << 24)) {
+            LDM_CUDA(cudaMemsetAsync(c->d_ring2, 0xFF, 2 * c->P() * sizeof(double), c->stream));      // every entry: not yet published
+            LDM_CUDA(cudaMemsetAsync(c->d_barrier, 0, (1 + (size_t)c->dev.G) * sizeof(unsigned int), c->stream));
+            c->barriers_done = 0;
+            c->persistent_dirty = false;
+        }
+        args.barriers_done = c->barriers_done;
+        args.last_is_rhs_only = rhs_only_last ? 1 : 0;
     }
     args.ring_pingpong = c->d_ring2;
     int device = 0, sms = 0;
@@ -405,14 +419,14 @@ void advance_persistent(ldm_context* c, int n_steps, double dt, long long first_
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
     if (c->plan.scan) {
         // one CTA per moment-grid row, each closing its own row: no spare CTAs, one grid barrier per step
-        LDM_CUDA(cudaMemsetAsync(c->d_barrier, 0, (1 + (size_t)c->dev.G) * sizeof(unsigned int), c->stream));
         LDM_CUDA(ldm::launch_persistent_scan(args, c->dev.G, c->stream, nullptr));
+        c->barriers_done += 1u + (unsigned int)advanced;          // the prologue's, then one per step that advanced
     } else {
         const int grid = std::min(c->persistent_grid, std::max(sms, c->dev.G + 1));
         LDM_CUDA(ldm::launch_persistent(c->plan, args, grid, c->stream, nullptr));
     }
     c->launches += 1;
-    c->cur ^= (n_steps & 1);
+    c->cur ^= (advanced & 1);
 }
 
 // Which multi-step kernel, if any, carries the Euler loop of this handle: one CTA per row (rows of one chunk, G <= 128),
@@ -426,9 +440,10 @@ Resident resident_mode(ldm_context* c)
     return Resident::None;
 }
 
-void advance_resident(ldm_context* c, Resident mode, int n_steps, double dt, double* d_obs, double* d_values, double* d_derivs)
+void advance_resident(ldm_context* c, Resident mode, int n_steps, double dt, double* d_obs, double* d_values, double* d_derivs,
+                      bool rhs_only_last = false)
 {
-    if (mode == Resident::Rows) advance_persistent(c, n_steps, dt, 0, d_obs, d_values, d_derivs);
+    if (mode == Resident::Rows) advance_persistent(c, n_steps, dt, 0, d_obs, d_values, d_derivs, rhs_only_last);
     else advance_chunked(c, n_steps, dt, c->stream, 0, d_obs, d_values, d_derivs);
 }
 
@@ -438,6 +453,7 @@ void check_device_status(ldm_context* c)
     LDM_CUDA(cudaMemcpy(&status, c->d_status, sizeof(int), cudaMemcpyDeviceToHost));
     if (status == 0) return;
     cudaMemset(c->d_status, 0, sizeof(int));
+    c->persistent_dirty = true;                     // arrival counter and hand-over slots of the persistent kernel: start over
     static const char* what[] = {"", "a grid barrier of the persistent kernel timed out", "a ring value was never handed over",
                                  "a rank never published its step (peer exchange timed out)"};
     throw CudaError(std::string("device status ") + std::to_string(status) + ": " + (status > 0 && status < 4 ? what[status] : "unknown") +
@@ -1100,9 +1116,11 @@ int ldm_solve(ldm_handle h, const double* init, double dt, double t_max, int rec
         }
         if (record >= LDM_RECORD_VALUES) std::memcpy(values, init, width * sizeof(double));      // Values[0] (S:568)
         LDM_CUDA(cudaEventRecord(h->ev_begin, s));
+        // ... and the derivative at the last point (S:582-583) as one more step of the same launch that advances nothing
+        const bool fold_last = direct && record == LDM_RECORD_ALL && mode == Resident::Rows && h->plan.scan;
         if (direct)
-            advance_resident(h, mode, n - 1, dt, record == LDM_RECORD_OBSERVABLES ? direct_values : nullptr,
-                             record >= LDM_RECORD_VALUES ? direct_values : nullptr, direct_derivs);
+            advance_resident(h, mode, fold_last ? n : n - 1, dt, record == LDM_RECORD_OBSERVABLES ? direct_values : nullptr,
+                             record >= LDM_RECORD_VALUES ? direct_values : nullptr, direct_derivs, fold_last);
         for (int k0 = 0, seg = 0; k0 < n - 1 && !direct; k0 += seg_len, seg++) {
             const int len = std::min(seg_len, n - 1 - k0), b = seg & 1;
             double* buf = per_step != 0 ? h->d_hist[b] : nullptr;
@@ -1146,7 +1164,7 @@ int ldm_solve(ldm_handle h, const double* init, double dt, double t_max, int rec
             h->launches += 1;
             LDM_CUDA(cudaMemcpyAsync(values + (size_t)(n - 1) * 2, h->d_scalars + 5, 2 * sizeof(double), cudaMemcpyDeviceToHost, s));
         }
-        if (record == LDM_RECORD_ALL || derivs) {
+        if ((record == LDM_RECORD_ALL || derivs) && !fold_last) {
             rhs_and_update(h, h->dev, h->d_C[h->cur], h->d_N + h->cur, nullptr, dt, nullptr, h->d_deriv, nullptr, s);
             double* out = record == LDM_RECORD_ALL ? derivs + (size_t)(n - 1) * width : derivs;
             LDM_CUDA(cudaMemcpyAsync(out, h->d_scalars + 1, sizeof(double), cudaMemcpyDeviceToHost, s));
@@ -1158,9 +1176,11 @@ int ldm_solve(ldm_handle h, const double* init, double dt, double t_max, int rec
             LDM_CUDA(cudaMemcpyAsync(values, h->d_N + h->cur, sizeof(double), cudaMemcpyDeviceToHost, s));
             LDM_CUDA(cudaMemcpyAsync(values + 1, h->d_C[h->cur], P * sizeof(double), cudaMemcpyDeviceToHost, s));
         }
+        if (!h->h_status) LDM_CUDA(cudaHostAlloc((void**)&h->h_status, sizeof(int), cudaHostAllocDefault));
+        LDM_CUDA(cudaMemcpyAsync(h->h_status, h->d_status, sizeof(int), cudaMemcpyDeviceToHost, s));     // the status word, behind the work
         LDM_CUDA(cudaStreamSynchronize(s));
         if (h->copy_stream) LDM_CUDA(cudaStreamSynchronize(h->copy_stream));
-        check_device_status(h);
+        if (*h->h_status != 0) check_device_status(h);
         LDM_CUDA(cudaEventElapsedTime(&h->last_ms, h->ev_begin, h->ev_end));
     });
 }

@@ -119,6 +119,9 @@ struct ldm_context {
     void* batch_stage_host = nullptr;
     void* batch_stage_device = nullptr;
     size_t batch_stage_bytes = 0;
+    unsigned int barriers_done = 0;        // grid barriers the arrival counter of the one-chunk persistent kernel has seen (monotone across launches)
+    bool persistent_dirty = true;          // counter and ring hand-over slots need their initial values (first launch, or a launch that timed out)
+    int* h_status = nullptr;               // pinned: the status word read back behind the work of a call, without a round trip of its own
     cudaGraphExec_t multi_graph = nullptr;
     double multi_graph_dt = 0;
     int multi_graph_extrapolation = -1;
@@ -152,6 +155,7 @@ struct ldm_context {
         cudaSetDevice(device);
         for (PairGroup& g : pair_groups) { cudaFree(g.d_args[0]); cudaFree(g.d_args[1]); }
         if (multi_graph) cudaGraphExecDestroy(multi_graph);
+        if (h_status) cudaFreeHost(h_status);
         if (batch_stage_host) cudaFreeHost(batch_stage_host);
         if (batch_stage_device) cudaFree(batch_stage_device);
         for (void* p : allocations) cudaFree(p);

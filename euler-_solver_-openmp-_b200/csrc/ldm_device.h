@@ -205,6 +205,8 @@ struct PersistentArgs {
     double* observables;       // may be NULL: [points][2]
     double* values;            // may be NULL: [points][stride]
     double* derivs;            // may be NULL: [points][stride]
+    unsigned int barriers_done; // prefix-sum persistent kernel: grid barriers the counter has seen in earlier launches (it is monotone: no reset per launch)
+    int last_is_rhs_only;      // the last of the n_steps only evaluates the right-hand side at its state (derivs, scalars): nothing is advanced
     int cached_w_rows;         // set by the launcher: offsets whose y-side weights stay in shared memory (-1: no cache)
     // prefix-sum persistent kernel: [2][G] row dots of the WC functional (ping-pong with the state) and the arrival
     // counter of its grid barrier (zeroed before every launch)

@@ -58,7 +58,7 @@ persistent_scan_kernel(const PersistentArgs A)
     extern __shared__ __align__(32) unsigned char scan_smem[];
     double* row_sum = reinterpret_cast<double*>(scan_smem + L.rowsum);            // [G] after scan_body(fused)
     int parity = A.parity;
-    unsigned int barrier_index = 0;
+    unsigned int barrier_index = A.barriers_done;      // the arrival counter runs on from launch to launch
 
     // prologue: the row dots of WC for the initial state
     if (tid < 32) {
@@ -168,9 +168,10 @@ persistent_scan_kernel(const PersistentArgs A)
         const double WC = __dmul_rn(add_outside(P, wc_shared, N, S.C, S.scalars, P.wc_outside, 0.0), P.hh);   // Solver.cpp:311, 314
         double* values_next = A.values ? A.values + (point + 1) * A.stride : nullptr;
         double* derivs_here = A.derivs ? A.derivs + point * A.stride : nullptr;
+        const bool rhs_only = A.last_is_rhs_only && k == A.n_steps - 1;      // the right-hand side at the last state: nothing is advanced
         if (x == 0 && tid == 0) {
-            first_moment_update(P, N, WC, S.dt, S.scalars, S.N_next);
-            if (values_next) values_next[0] = S.N_next[0];
+            first_moment_update(P, N, WC, S.dt, S.scalars, rhs_only ? nullptr : S.N_next);
+            if (values_next && !rhs_only) values_next[0] = S.N_next[0];
             if (derivs_here) derivs_here[0] = S.scalars[1];
         }
         if (closer) {
@@ -179,11 +180,14 @@ persistent_scan_kernel(const PersistentArgs A)
             const double dc = second_moment_rhs(P, mc, c_old, N, WC, mn, wn);
             double v = __dadd_rn(c_old, __dmul_rn(dc, S.dt));                      // Solver.cpp:577
             v = v < 0.0 ? 0.0 : v;                                                 // Solver.cpp:578-580
-            S.C_next[q] = v;
-            c_new[tid] = v;
-            if (values_next) values_next[1 + q] = v;
+            if (!rhs_only) {
+                S.C_next[q] = v;
+                c_new[tid] = v;
+                if (values_next) values_next[1 + q] = v;
+            }
             if (derivs_here) derivs_here[1 + q] = dc;
         }
+        if (rhs_only) break;                                                       // (uniform: the launch ends here)
         __syncthreads();
         if (warp == 0) {     // this row's dot of the WC functional for the next state
             const double s = wc_row_dot(op_row, c_new, G, lane);
