@@ -121,7 +121,9 @@ LDM_API int  ldm_kernels_at_nodes(ldm_handle h, double* m_at_nodes, double* w_at
  * ldm_solve: init/1+G*G doubles.  times: n_points.  values/derivs by `record`:
  *   LAST: values = 1+G*G (derivs, if non-NULL, = derivative at the last point);
  *   OBSERVABLES: values = n_points*2; VALUES: values = n_points*(1+G*G); ALL: derivs likewise.
- * Host buffers; the copies in and out are part of the call. */
+ * Host buffers; the copies in and out are part of the call.  values / derivs in pinned, mapped host memory (cudaHostAlloc,
+ * cudaHostRegister) are written by the kernel itself, point by point, in one launch for the whole solve; pageable buffers
+ * receive the history through two device-side segments that are copied out under the computation. */
 LDM_API int  ldm_count_points(double t_max, double dt);
 LDM_API int  ldm_solve(ldm_handle h, const double* init, double dt, double t_max, int record,
                double* times, double* values, double* derivs, int* n_points);
