@@ -1114,13 +1114,14 @@ int ldm_solve(ldm_handle h, const double* init, double dt, double t_max, int rec
             // of cudaFree / cudaMalloc into the second call -- 36 instead of 15 us per step end to end)
             ensure_history(h, std::max((size_t)seg_len, std::min<size_t>(longest, 4096)) * per_step);
         }
-        if (record >= LDM_RECORD_VALUES) std::memcpy(values, init, width * sizeof(double));      // Values[0] (S:568)
         LDM_CUDA(cudaEventRecord(h->ev_begin, s));
         // ... and the derivative at the last point (S:582-583) as one more step of the same launch that advances nothing
         const bool fold_last = direct && record == LDM_RECORD_ALL && mode == Resident::Rows && h->plan.scan;
         if (direct)
             advance_resident(h, mode, fold_last ? n : n - 1, dt, record == LDM_RECORD_OBSERVABLES ? direct_values : nullptr,
                              record >= LDM_RECORD_VALUES ? direct_values : nullptr, direct_derivs, fold_last);
+        // Values[0] (S:568): a host copy, made while the device is already at work (the kernels write from Values[1] on)
+        if (record >= LDM_RECORD_VALUES && direct) std::memcpy(values, init, width * sizeof(double));
         for (int k0 = 0, seg = 0; k0 < n - 1 && !direct; k0 += seg_len, seg++) {
             const int len = std::min(seg_len, n - 1 - k0), b = seg & 1;
             double* buf = per_step != 0 ? h->d_hist[b] : nullptr;
@@ -1158,6 +1159,7 @@ int ldm_solve(ldm_handle h, const double* init, double dt, double t_max, int rec
                 LDM_CUDA(cudaEventRecord(h->ev_copied[b], h->copy_stream));
             }
         }
+        if (record >= LDM_RECORD_VALUES && !direct) std::memcpy(values, init, width * sizeof(double));   // Values[0] (S:568)
         // the last point: its observables; and the reference evaluates the equation once more there (S:582-583)
         if (record == LDM_RECORD_OBSERVABLES) {
             ldm::launch_record_observables(h->dev, h->d_N + h->cur, h->d_C[h->cur], h->d_scalars + 5, s);
