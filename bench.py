@@ -105,12 +105,13 @@ def requested_bytes_per_step(props):
 
 
 def source_sha():
-    """sha256 over the kernel sources: a counter file captured from other sources is refused"""
+    """sha256 over the kernel sources (the peak micro-benchmarks of ldm_peak.cu are not among the profiled kernels): a counter
+    file captured from other sources is refused"""
     import hashlib
     h = hashlib.sha256()
     csrc = os.path.join(ROOT, "euler-_solver_-openmp-_b200", "csrc")
     for name in sorted(os.listdir(csrc)):
-        if name.endswith((".cu", ".cuh", ".h", ".cpp")):
+        if name.endswith((".cu", ".cuh", ".h", ".cpp")) and name != "ldm_peak.cu":
             h.update(name.encode())
             h.update(open(os.path.join(csrc, name), "rb").read())
     return h.hexdigest()
