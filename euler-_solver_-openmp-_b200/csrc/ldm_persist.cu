@@ -59,6 +59,21 @@ persistent_scan_kernel(const PersistentArgs A)
     double* row_sum = reinterpret_cast<double*>(scan_smem + L.rowsum);            // [G] after scan_body(fused)
     int parity = A.parity;
     unsigned int barrier_index = A.barriers_done;      // the arrival counter runs on from launch to launch
+    // The resident y-side tables -- all 16-bit interval indices, the first cached_w_rows rows of weights (behind the step's
+    // working set: scan_body) -- by two bulk asynchronous copies (TMA): requested now, waited for in front of the first y side.
+    __shared__ __align__(8) unsigned long long tables_landed;
+    const bool resident_tables = A.cached_w_rows >= 0;
+    if (resident_tables && tid == 0) {
+        const size_t n_even = (size_t)((P.n_off + 1) & ~1);
+        unsigned char* u_cache = scan_smem + L.end;
+        unsigned char* w_cache = scan_smem + align32(L.end + sizeof(unsigned short) * n_even * G);
+        const unsigned int u_bytes = (unsigned int)((sizeof(unsigned short) * n_even * G + 15) & ~(size_t)15);   // (both ends are padded)
+        const unsigned int w_bytes = (unsigned int)(sizeof(double) * (size_t)A.cached_w_rows * G);              // an even number of rows
+        bulk_barrier_init(&tables_landed);
+        bulk_barrier_expect(&tables_landed, u_bytes + w_bytes);
+        bulk_copy_to_shared(u_cache, P.upper_p16, u_bytes, &tables_landed);
+        if (w_bytes) bulk_copy_to_shared(w_cache, P.weight_p, w_bytes, &tables_landed);
+    }
 
     // prologue: the row dots of WC for the initial state
     if (tid < 32) {
@@ -145,6 +160,7 @@ persistent_scan_kernel(const PersistentArgs A)
         double c_old = 0.0, ring_v = 0.0, N = 0.0, wc_part[4] = {0.0, 0.0, 0.0, 0.0};
         const double* wc_rows_now = A.wc_rows + parity * G;
         auto mid = [&]() {
+            if (k == 0 && resident_tables) bulk_barrier_wait(&tables_landed, 0);     // issued at the kernel's first instruction: long there
             if (closer) {
                 if (has_ring) ring_v = take_ring(ring_slot + q, A.status);
                 c_old = S.C[q];

@@ -273,7 +273,7 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
 
     SCAN_MARK(0);
     if (build_tables) {
-        if (cached_w_rows >= 0) {
+        if (cached_w_rows >= 0 && !STAGED_WORK) {                             // (the one-chunk persistent kernel fills them itself: bulk copies)
             const int n_even = (n_off + 1) & ~1;                              // the tables hold the offsets two by two
             for (int i = tid; i < n_even * G; i += NT) u_cache[i] = P.upper_p16[i];
             for (int i = tid; i < cached_w_rows * G; i += NT) w_cache[i] = P.weight_p[i];   // cached_w_rows is even
@@ -465,6 +465,36 @@ __device__ __forceinline__ void scan_body_of(const StepArgs& S, const int chunk,
     const int ng = (int)blockDim.x / S.P.scan_bn > 1 ? (int)blockDim.x / S.P.scan_bn : 1;
     if (scan_unroll((int)blockDim.x, S.P.A, ng) == 5) scan_body<5, Mid, Gate, STAGED_WORK>(S, chunk, lx, build_tables, cached_w_rows, fused, mid, gate);
     else scan_body<4, Mid, Gate, STAGED_WORK>(S, chunk, lx, build_tables, cached_w_rows, fused, mid, gate);
+}
+
+// ---- bulk asynchronous copies into shared memory (TMA, cp.async.bulk): one thread issues, completion is counted in bytes on an
+// mbarrier, nobody spends registers or instructions on the bytes.  Used for the resident y-side tables of the one-chunk
+// persistent kernel: they land under the kernel's prologue and the first E phase. ----
+__device__ __forceinline__ unsigned int shared_address(const void* p) { return (unsigned int)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void bulk_barrier_init(unsigned long long* bar)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(shared_address(bar)) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_barrier_expect(unsigned long long* bar, unsigned int bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(shared_address(bar)), "r"(bytes) : "memory");
+}
+// bytes: a multiple of 16; both addresses 16-byte aligned
+__device__ __forceinline__ void bulk_copy_to_shared(void* dst, const void* src, unsigned int bytes, unsigned long long* bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(shared_address(dst)), "l"(src), "r"(bytes), "r"(shared_address(bar)) : "memory");
+}
+__device__ __forceinline__ void bulk_barrier_wait(unsigned long long* bar, unsigned int parity)
+{
+    unsigned int done;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(done) : "r"(shared_address(bar)), "r"(parity) : "memory");
+    } while (!done);
 }
 
 // ---- hand-overs between CTAs (persistent kernels) ----
