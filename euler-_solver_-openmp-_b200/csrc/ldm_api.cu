@@ -720,7 +720,7 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         c->d_sum = c->alloc<double>(P);
         c->d_deriv = c->alloc<double>(P);
         // structure of the m table: separable inside its disc (every table Properties::Generate builds) -> prefix sums
-        d.qvec = nullptr; d.a_star = nullptr; d.beta_range = nullptr; d.scan_piece = nullptr; d.scan_chunk_begin = nullptr; d.scan_warp_begin = nullptr; d.scan_block_begin = nullptr; d.scan_chunk_order = nullptr; d.upper_c16 = nullptr; d.scan_max_pieces = 0; d.scan_bn = 0; d.scan_chunks = 0; d.scan_nt = 512; d.scan_live_rows = 0;
+        d.qvec = nullptr; d.a_star = nullptr; d.beta_record = nullptr; d.scan_piece = nullptr; d.scan_chunk_begin = nullptr; d.scan_warp_begin = nullptr; d.scan_block_begin = nullptr; d.scan_chunk_order = nullptr; d.upper_c16 = nullptr; d.scan_max_pieces = 0; d.scan_bn = 0; d.scan_chunks = 0; d.scan_nt = 512; d.scan_live_rows = 0;
         {   // the y-side tables of the prefix-sum path, offsets two by two (ldm_scan_body.cuh y_table_index)
             const int n_even = (d.n_off + 1) & ~1;
             std::vector<unsigned short> u16((size_t)n_even * d.G, 0);
@@ -740,9 +740,14 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         if (scan_bn > 0 && tuning().scan != 0) {
             d.qvec = c->upload(c->separable.q);
             d.a_star = c->upload(c->separable.a_star);
-            std::vector<int> pairs((size_t)d.A * 2);
-            for (int a = 0; a < d.A; a++) { pairs[2 * (size_t)a] = c->separable.beta_lo[a]; pairs[2 * (size_t)a + 1] = c->separable.beta_hi[a]; }
-            d.beta_range = reinterpret_cast<const int2*>(c->upload(pairs));
+            std::vector<int> records((size_t)d.A * 4, 0);
+            for (int a = 0; a < d.A; a++) {
+                const int lo = c->separable.beta_lo[a], hi = c->separable.beta_hi[a];
+                const double q_first = lo < hi ? c->separable.q[(size_t)lo] : 0.0;
+                records[4 * (size_t)a] = lo; records[4 * (size_t)a + 1] = hi;
+                std::memcpy(&records[4 * (size_t)a + 2], &q_first, sizeof(double));         // low word, high word (little endian)
+            }
+            d.beta_record = reinterpret_cast<const int4*>(c->upload(records));
             d.scan_bn = scan_bn;
             d.scan_chunks = (d.G + scan_bn - 1) / scan_bn;
             d.scan_nt = ldm::scan_pick_threads(d.G, d.A, scan_bn);

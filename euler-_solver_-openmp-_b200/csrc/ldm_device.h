@@ -35,7 +35,7 @@ struct DevProblem {
     // alpha <= a_star[beta], 0 beyond.  NULL qvec: the table is not separable, the dense contraction is used.
     const double* qvec;        // [A]
     const int* a_star;         // [A]
-    const int2* beta_range;    // [A] rows beta with a_star[beta] == alpha: [x, y)
+    const int4* beta_record;   // [A] rows beta with a_star[beta] == alpha: [x, y), and the bits of qvec[x] in z (low) and w (high)
     const unsigned short* upper_p16;   // upper_t in 16 bits and the weights with the offsets two by two: entry (o, y) at
     const double* weight_p;            // ((o >> 1) * G + y) * 2 + (o & 1)  (ldm_scan_body.cuh y_table_index); n_off rounded up to even
     const unsigned short* upper_c16;   // rows of several chunks: [scan_chunks] tables like upper_p16 holding the pair's position in the

@@ -282,11 +282,14 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
             const int alpha = t >> 1, f = t & 1;
             double w_lo = 0.0, w_hi = 0.0;
             int r_lo = 0, r_hi = 0;
-            if (alpha < A && f < n_fold) {
-                const int o = folded_offset(A, n_fold, alpha, f);
-                const int u = P.upper[(size_t)x * n_off + o];
-                if (u != 0) {
-                    const double w = P.weight[(size_t)x * n_off + o], qa = P.qvec[alpha];
+            {
+                // the three table words requested together (a load behind `u != 0` would wait for u first: one more round trip
+                // to L2 in front of every item of the work-list kernel)
+                const bool valid = alpha < A && f < n_fold;
+                const size_t at = (size_t)x * n_off + (valid ? folded_offset(A, n_fold, alpha, f) : 0);
+                const int u = P.upper[at];
+                const double w = P.weight[at], qa = P.qvec[valid ? alpha : 0];
+                if (valid && u != 0) {
                     w_lo = qa * (1.0 - w); w_hi = qa * w;
                     r_lo = row_slot(P, u - 1) * G; r_hi = row_slot(P, u) * G;
                 }
@@ -302,9 +305,7 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
         }
         for (int a = tid; a < L.a_pad; a += NT) {
             qv[a] = a < A ? P.qvec[a] : 0.0;
-            const int2 range = a < A ? P.beta_range[a] : make_int2(0, 0);
-            const double q_first = range.x < range.y ? P.qvec[range.x] : 0.0;    // most alphas close one row: its q comes with the record
-            sel[a] = make_int4(range.x, range.y, __double2loint(q_first), __double2hiint(q_first));
+            sel[a] = a < A ? P.beta_record[a] : make_int4(0, 0, 0, 0);           // rows [x, y) and q[x]: most alphas close one row
         }
         for (int b = tid; b < A; b += NT) {
             Hs[b * ld + kScanLead - 1] = 0.0;                                 // the zero column (never written again)
