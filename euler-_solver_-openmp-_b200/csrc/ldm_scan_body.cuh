@@ -21,8 +21,9 @@
 //      exchange block sums once per super-chunk of alphas), and whenever alpha is the last in-disc column of some rows
 //      beta, H[beta][col] = q[beta] * sum;
 //   3. y side: the (y block, offset interval) pieces that touch this chunk are dealt out evenly over the warps
-//      (ldm_model.h ScanPieces); lanes = 32 consecutive nodes y read the transposed tables coalesced, gather the two H
-//      columns of their interpolation pair and accumulate; per-piece partial sums are added up in list order;
+//      (ldm_model.h ScanPieces); lanes = 32 consecutive nodes y read the node-contiguous tables coalesced -- two consecutive
+//      offsets per load (y_table_index) --, gather the two H columns of their interpolation pair and accumulate; per-piece
+//      partial sums are added up in list order;
 //   4. per-chunk partial sums to global memory; the closing code (finish_factored_kernel, or the closing phase of a
 //      persistent kernel) adds the chunks, subtracts the ring correction and closes the step.
 //
@@ -268,7 +269,7 @@ __device__ __forceinline__ void scan_body(const StepArgs& S, const int chunk, co
     int4* work_piece = reinterpret_cast<int4*>(scan_smem + L.work);      // [pieces] this chunk's y-side pieces (y block, first offset, end offset)
     int* work_warp_begin = reinterpret_cast<int*>(work_piece + P.scan_max_pieces);   // [warps + 1] first piece of every warp
     int* work_block_begin = work_warp_begin + NT / 32 + 1;               // [n_yblk + 1] first piece of every y block
-    unsigned short* u_cache = reinterpret_cast<unsigned short*>(scan_smem + L.end);                    // [n_off][G]
+    unsigned short* u_cache = reinterpret_cast<unsigned short*>(scan_smem + L.end);                    // as DevProblem::upper_p16 (offsets two by two)
     double* w_cache = reinterpret_cast<double*>(scan_smem + align32(L.end + sizeof(unsigned short) * (size_t)((n_off + 1) & ~1) * G));
 
     SCAN_MARK(0);
