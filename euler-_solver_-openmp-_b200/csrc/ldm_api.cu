@@ -436,7 +436,11 @@ enum class Resident { None, Rows, Chunks };
 Resident resident_mode(ldm_context* c)
 {
     if (persistent_possible(c)) return Resident::Rows;
-    if (c->dev.world == 1 && chunked_possible(c)) return Resident::Chunks;
+    // Rows of several chunks on ONE rank: one launch per kernel and step.  The work-list kernel (what the xi-sharded ranks run) pays
+    // about 2 us per item for what kernel boundaries give for free -- an arrival with its fence per item, closings and ring shares
+    // in line, waits for rows of the step before -- and measured 10 % slower at every size (G = 200: 58.2 against 51.6 us per
+    // step, 256: 81.3 / 73.8, 333: 172 / 154, 512: 609 / 555; tools/chunked_modes.py); it is taken only where it is asked for.
+    if (c->dev.world == 1 && c->work_list_on_one_rank && chunked_possible(c)) return Resident::Chunks;
     return Resident::None;
 }
 
@@ -797,6 +801,7 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         c->d_wc_rows2 = c->alloc<double>(2 * (size_t)d.G);
         c->d_barrier = c->alloc<unsigned int>(1 + (size_t)d.G);
         if (tuning().persistent >= 0) c->persistent_enabled = tuning().persistent != 0;
+        c->work_list_on_one_rank = tuning().persistent == 1;
         c->chunk_grid_limit = tuning().chunk_grid;
         d.n_ring = 0;
         LDM_CUDA(cudaMemsetAsync(c->d_C[0], 0, P * sizeof(double), c->stream));

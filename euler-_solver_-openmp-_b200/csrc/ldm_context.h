@@ -73,6 +73,7 @@ struct ldm_context {
     bool peer_solo = false;                // debug build only (ldm_debug_shard_solo): this rank steps alone, the others count as done
     int persistent_grid = 0;               // co-resident CTAs of the persistent kernel (0: not queried yet, -1: unavailable)
     bool persistent_enabled = true;
+    bool work_list_on_one_rank = false;    // ldm_tuning_set("persistent", 1): the work-list kernel also for unsharded chunked grids (tests, measurements)
     // persistent work-list kernel (ldm_persist.cu persistent_chunks_kernel): rows of several chunks and the xi-sharded step
     int chunk_grid = 0;                    // co-resident CTAs of that kernel (0: not queried yet, -1: unavailable)
     int chunk_grid_limit = 0;              // > 0: launch at most this many CTAs (ldm_tuning_set chunk_grid; two ranks on one device in tests)

@@ -18,6 +18,7 @@ for label, bn in (("one chunk of 128 columns, 128 CTAs + grid barrier", 0), ("2 
     ldm.tuning_set("reset")
     if bn:
         ldm.tuning_set("scan_bn", bn)
+        ldm.tuning_set("persistent", 1)       # the work-list kernel (not the default on one rank)
     eq = ldm.Equation(props)
     eq.upload(state)
     eq.advance(20, 0.1); eq.synchronize()

@@ -17,6 +17,8 @@ ldm = load_package()
 G = int(sys.argv[1]) if len(sys.argv) > 1 else 128
 sw, sm = (float(sys.argv[2]), float(sys.argv[3])) if len(sys.argv) > 3 else (0.15, 0.15)
 props = ldm.Properties.Generate(1, sw, sm, 0.4, 0.2, 0.001, G)
+if os.environ.get("LDM_CLOCKS_PER_STEP_LAUNCHES"):      # the per-step kernel instead of the persistent ones
+    ldm.tuning_set("persistent", 0)
 eq = ldm.Equation(props)
 st = eq.GenerateEquilibriumValuesForNAndC(200)
 eq.upload(st)

@@ -747,6 +747,7 @@ def test_work_list_kernel_equals_per_step_launches(ldm, G, bn):
     props = ldm.Properties.Generate(1, 0.12, 0.09, 0.4, 0.2, 0.001, G)
     if bn:
         ldm.tuning_set("scan_bn", bn)
+    ldm.tuning_set("persistent", 1)       # the work-list kernel on one rank (the default there is one launch per kernel and step)
     persistent = ldm.Equation(props)
     ldm.tuning_set("persistent", 0)
     stepwise = ldm.Equation(props)
@@ -795,7 +796,9 @@ def test_history_straight_into_pinned_host_buffers(ldm, G):
     buffers take, in every record mode, for a one-chunk grid and a chunked one"""
     import torch
     props = ldm.Properties.Generate(1, 0.12, 0.09, 0.4, 0.2, 0.001, G)
+    ldm.tuning_set("persistent", 1)       # chunked grid: the work-list kernel (on one rank it runs only where it is asked for)
     eq = ldm.Equation(props)
+    ldm.tuning_set("reset")
     g = props.MomentsGrid
     init = eq.GenerateEquilibriumValuesForNAndC(200)
     init[1:] *= (1 + 0.5 * np.exp(-(g[:, None] ** 2 + g[None, :] ** 2) / (2 * 0.1 ** 2))).ravel()
