@@ -21,6 +21,8 @@ RECORD_LAST, RECORD_OBSERVABLES, RECORD_VALUES, RECORD_ALL = 0, 1, 2, 3
 # enum ExtrapolationType (Solver.cpp:28); every experiment passes SquaredN for C; the other three are built to the letter
 # of the reference (ldm.h)
 Zero, SquaredN, Alpha, Exponential = 0, 1, 2, 3
+# closure of the third moment (ldm.h ldm_set_closure): the reference's power-1, and the two whose integral does not factorise
+CLOSURE_POWER1, CLOSURE_POWER2_SYMMETRIC, CLOSURE_POWER3 = 1, 2, 3
 
 
 class LdmError(RuntimeError):
@@ -53,6 +55,9 @@ _SIGNATURES = {
     "ldm_set_algorithm": (C.c_int, [C.c_void_p, C.c_int]),
     "ldm_get_algorithm": (C.c_int, [C.c_void_p]),
     "ldm_set_extrapolation": (C.c_int, [C.c_void_p, C.c_int]),
+    "ldm_set_closure": (C.c_int, [C.c_void_p, C.c_int]),
+    "ldm_get_closure": (C.c_int, [C.c_void_p]),
+    "ldm_closure_integrals": (C.c_int, [C.c_void_p, _dp, C.c_void_p, C.c_void_p]),
     "ldm_count_points_rk4": (C.c_int, [C.c_double, C.c_double]),
     "ldm_solve_rk4": (C.c_int, [C.c_void_p, _dp, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int)]),
     "ldm_rhs": (C.c_int, [C.c_void_p, _dp, _dp]),
@@ -224,6 +229,22 @@ class Equation:
     def set_extrapolation(self, chosen_type):
         """the ExtrapolationType the equation is evaluated with from here on (Solver.cpp:431: chosen_type)"""
         _check(library().ldm_set_extrapolation(self._h, int(chosen_type)))
+
+    def set_closure(self, closure):
+        """extension (ldm.h): CLOSURE_POWER1 is the reference; the other two evaluate (w*C)(xi) and K(xi) at every node"""
+        _check(library().ldm_set_closure(self._h, int(closure)))
+
+    @property
+    def closure(self):
+        return library().ldm_get_closure(self._h)
+
+    def closure_integrals(self, vals):
+        """(w*C)(xi) and K(xi) = integral of w(xi') C(xi') C(xi + xi') at every node, G x G each"""
+        vals = np.ascontiguousarray(vals, dtype=np.float64)
+        G = self.props.G
+        w_conv, k = np.empty((G, G)), np.empty((G, G))
+        _check(library().ldm_closure_integrals(self._h, vals, w_conv.ctypes.data, k.ctypes.data))
+        return w_conv, k
 
     def __call__(self, times, vals, chosen_type=SquaredN):
         self.set_extrapolation(chosen_type)

@@ -158,6 +158,20 @@ void launch_integral(ldm_context* c, const ldm::StepArgs& args, cudaStream_t s)
 void rhs_and_update(ldm_context* c, const DevProblem& P, const double* C, const double* N_cur, double* N_next, double dt,
                     double* sum_out, double* deriv_out, double* C_next, cudaStream_t s)
 {
+    if (c->closure != LDM_CLOSURE_POWER1) {
+        // a closure that does not factorise (ldm_closure.cu): the m*C sums, WC and the first-moment equation as always --
+        // this function once more, as the reference's closure would run it, closing nothing -- then the integrals over the
+        // w quadrature and the closing with the exchanged term
+        const int closure = c->closure;
+        c->closure = LDM_CLOSURE_POWER1;
+        try { rhs_and_update(c, P, C, N_cur, N_next, dt, c->d_sum, nullptr, nullptr, s); }
+        catch (...) { c->closure = closure; throw; }
+        c->closure = closure;
+        if (sum_out && sum_out != c->d_sum)
+            LDM_CUDA(cudaMemcpyAsync(sum_out, c->d_sum, c->P() * sizeof(double), cudaMemcpyDeviceToDevice, s));
+        closure_close(c, P, C, N_cur, dt, deriv_out, C_next, s);
+        return;
+    }
     const double* out_exp = nullptr;
     if (P.extrapolation == LDM_EXTRAPOLATION_EXPONENTIAL) {
         // the one type whose outside value depends on each sample's own distance, through a decay rate that changes every
@@ -171,8 +185,10 @@ void rhs_and_update(ldm_context* c, const DevProblem& P, const double* C, const 
     if (c->algo == LDM_ALGO_DIRECT) {
         ldm::launch_sample_sum(P, ldm::SAMPLES_INSIDE, C, c->d_sum, s);
         ldm::launch_wc(P, C, N_cur, N_next, c->d_scalars, dt, s);
+        c->launches += 2;
+        if (!deriv_out && !C_next) return;             // integrals only (ldm_integrals, a closure that closes elsewhere)
         ldm::launch_pointwise(P, C, c->d_sum, N_cur, c->d_scalars, dt, deriv_out, C_next, s, out_exp);
-        c->launches += 3;
+        c->launches += 1;
         return;
     }
     ensure_ring_operator(c);
@@ -365,6 +381,7 @@ bool persistent_possible(ldm_context* c)
 {
     if (!c->persistent_enabled || c->algo == LDM_ALGO_DIRECT || c->dev.world != 1) return false;
     if (c->dev.extrapolation == LDM_EXTRAPOLATION_EXPONENTIAL) return false;        // needs its own launches every step
+    if (c->closure != LDM_CLOSURE_POWER1) return false;                             // likewise (ldm_closure.cu)
     const ldm::FactoredPlan& p = c->plan;
     if (p.slabs() != 1) return false;
     if (c->persistent_grid == 0) {
@@ -678,6 +695,22 @@ int ldm_create(const ldm_problem* p, int device, ldm_handle* out)
         LDM_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
 
         ldm::build_tables(*p, c->tables);
+        {   // what a closure over the w quadrature would be built from (ldm_set_closure): the caller's problem may be gone by then
+            ldm::OwnedProblem& seed = c->w_seed;
+            seed.moments_grid.assign(p->moments_grid, p->moments_grid + p->G);
+            seed.kernels_grid.assign(p->kernels_grid, p->kernels_grid + p->K);
+            seed.W.assign(p->W, p->W + (size_t)p->K * p->K);
+            seed.view = *p;
+            seed.view.species = 1;
+            seed.view.moments_grid = seed.moments_grid.data();
+            seed.view.kernels_grid = seed.kernels_grid.data();
+            seed.view.W = seed.W.data();
+            seed.view.M = seed.W.data();               // the w table in the m table's place: build_tables lays out ITS quadrature
+            seed.view.mM = p->mW;
+            seed.view.sigma_m = p->sigma_w;
+            seed.view.mM_of = nullptr; seed.view.mW_of = nullptr; seed.view.sigma_m_of = nullptr; seed.view.sigma_w_of = nullptr;
+            seed.view.b_of = nullptr; seed.view.d_of = nullptr; seed.view.d_prime_of = nullptr;
+        }
         const ldm::Tables& t = c->tables;
         DevProblem& d = c->dev;
         d.G = t.G; d.n_off = t.offM.n_off; d.A = t.offM.A;
@@ -861,6 +894,8 @@ int ldm_set_extrapolation(ldm_handle h, int type)
     if (type == LDM_EXTRAPOLATION_EXPONENTIAL && (h->species != 1 || h->dev.G < 5))
         return fail(LDM_ERR_UNSUPPORTED, "Exponential extrapolation is built for one species on grids of at least 5 nodes (it reads the last 5 of row 0, Solver.cpp:394-401)");
     if (type < LDM_EXTRAPOLATION_ZERO || type > LDM_EXTRAPOLATION_EXPONENTIAL) return fail(LDM_ERR_ARGUMENT, "unknown extrapolation type");
+    if (type != LDM_EXTRAPOLATION_SQUARED_N && h->closure != LDM_CLOSURE_POWER1)
+        return fail(LDM_ERR_UNSUPPORTED, "the closures over the w quadrature are built for SquaredN extrapolation (ldm_set_closure)");
     h->dev.extrapolation = type;
     return LDM_OK;
 }
@@ -1534,10 +1569,12 @@ int ldm_solve_batch(int n, const ldm_handle* handles, const double* const* inits
         for (int i = 0; i < n; i++) {
             if (handles[i]->dev.world != 1) throw std::invalid_argument("a batch entry is configured as one rank of several (ldm_shard_configure)");
             ldm_context* h = handles[i];
-            batched = batched && h->algo != LDM_ALGO_DIRECT && h->dev.world == 1 && h->dev.extrapolation != LDM_EXTRAPOLATION_EXPONENTIAL;
+            batched = batched && h->algo != LDM_ALGO_DIRECT && h->dev.world == 1 && h->dev.extrapolation != LDM_EXTRAPOLATION_EXPONENTIAL &&
+                      h->closure == LDM_CLOSURE_POWER1;
         }
         if (!batched) {
-            // sample-by-sample algorithm or Exponential extrapolation: every parameter set advances on its own stream
+            // sample-by-sample algorithm, Exponential extrapolation or a closure over the w quadrature: every parameter set
+            // advances on its own stream
             for (int i = 0; i < n; i++) {
                 LDM_CUDA(cudaSetDevice(handles[i]->device));
                 upload_state(handles[i], inits_of[i]);

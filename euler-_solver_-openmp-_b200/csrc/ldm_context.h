@@ -127,6 +127,17 @@ struct ldm_context {
     double multi_graph_dt = 0;
     int multi_graph_extrapolation = -1;
     long long multi_graph_launches = 0;
+    // closures whose triple integral does not factorise (ldm_closure.cu; ldm.h ldm_set_closure).  w_seed: what the tables
+    // of the w quadrature are built from when such a closure is first asked for (grids and the W table of ldm_create's
+    // problem); closure_w: those tables on the device, laid out like the m side's so that the same enumeration serves
+    int closure = LDM_CLOSURE_POWER1;
+    ldm::OwnedProblem w_seed;
+    bool closure_ready = false;
+    ldm::DevProblem closure_w{};
+    double closure_w_sum = 0;              // sum of w over all quadrature samples (times hh: the midpoint integral of w)
+    double* d_own_density = nullptr;       // [n_off_w][n_off_w] C~ at the samples of the WC integral, this step
+    double* d_w_conv = nullptr;            // [P] (w*C)(xi)
+    double* d_k_int = nullptr;             // [P] K(xi)
     int cur = 0;
     int algo = LDM_ALGO_FACTORED;
     long long launches = 0;
@@ -206,6 +217,12 @@ void rhs_and_update(ldm_context* c, const DevProblem& P, const double* C, const 
                     double* sum_out, double* deriv_out, double* C_next, cudaStream_t s);
 // throws CudaError when a bounded wait of a persistent kernel ran out (the stream must have drained); clears the word
 void check_device_status(ldm_context* c);
+
+// defined in ldm_closure.cu: what follows the m*C integral and the first-moment equation when the handle's closure is not
+// the reference's -- the integrals over the w quadrature and the closing with the exchanged term.  inside_sum: the m*C
+// sums of this right-hand side (c->d_sum); scalars[0] = WC.
+void closure_close(ldm_context* c, const DevProblem& P, const double* C, const double* N_cur, double dt, double* deriv_out,
+                   double* C_next, cudaStream_t s);
 
 // defined in ldm_shard_api.cu: the persistent work-list kernel on this handle's current sharding.  replicas: the
 // handle's own d_C (one rank, natural layout) or the peer group's.  History pointers (device) may be NULL.

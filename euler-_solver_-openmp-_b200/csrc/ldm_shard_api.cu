@@ -150,6 +150,7 @@ bool chunked_possible(ldm_context* c)
 {
     if (!c->persistent_enabled || c->species != 1 || c->algo != LDM_ALGO_PREFIX || !c->plan.scan) return false;
     if (c->dev.extrapolation == LDM_EXTRAPOLATION_EXPONENTIAL) return false;        // needs its own launches every step
+    if (c->closure != LDM_CLOSURE_POWER1) return false;
     if (c->chunk_grid == 0) {
         ChunkedArgs probe{};
         probe.step = make_step_args(c, c->d_C[0], c->d_N, c->d_N + 1, 0.0, nullptr, nullptr, nullptr);
@@ -244,6 +245,8 @@ int ldm_shard_configure(ldm_handle h, int rank, int world)
     if (!h || world < 1 || rank < 0 || rank >= world) return fail(LDM_ERR_ARGUMENT, "bad rank/world");
     if (h->species != 1) return fail(LDM_ERR_UNSUPPORTED, "not built for several species (ldm.h: ldm_problem_generate_multi)");
     if (world > h->dev.G) return fail(LDM_ERR_ARGUMENT, "more ranks than moment-grid rows");
+    if (world > 1 && h->closure != LDM_CLOSURE_POWER1)
+        return fail(LDM_ERR_UNSUPPORTED, "the closures over the w quadrature run on one rank (ldm_set_closure)");
     h->dev.world = world;
     h->dev.rank = rank;
     h->dev.rows_per_rank = (h->dev.G + world - 1) / world;

@@ -109,6 +109,29 @@ LDM_API int  ldm_get_algorithm(ldm_handle h);                                /* 
 #define LDM_EXTRAPOLATION_EXPONENTIAL 3
 LDM_API int  ldm_set_extrapolation(ldm_handle h, int type);
 
+/* ---- EXTENSION (no counterpart in the reference): the closures whose triple integral does NOT factorise.
+ * The reference closes the third moment with the power-1 closure T(xi, xi') = C(xi) C(xi') / N (Law & Dieckmann 2000,
+ * eq. 14.10), so its integral of w(xi') T(xi, xi') is C(xi) * WC / N with one scalar WC (S:265-274, S:483-488).  The
+ * other closures of the same paper need, at EVERY node xi, the two integrals BASELINE.json's north_star names:
+ *     (w*C)(xi) = integral of w(xi') C(xi + xi') dxi'          K(xi) = integral of w(xi') C(xi') C(xi + xi') dxi'
+ *   LDM_CLOSURE_POWER1            C(xi) WC / N                                                   (the reference; default)
+ *   LDM_CLOSURE_POWER2_SYMMETRIC  1/2 [ C(xi) WC / N + C(xi) (w*C)(xi) / N + K(xi) / N - N^3 integral of w ]
+ *   LDM_CLOSURE_POWER3            C(xi) K(xi) / N^3                                              (Kirkwood superposition)
+ * replace the term of S:486-487; everything else of Equation::operator() stays.  Same quadrature as the reference's WC
+ * (MakeIntegralWithPairDensity, S:297-316, extent MaxNumForW, bilinear C, N^2 beyond the cutoff).  K(xi) is a
+ * convolution with the time-varying table w(xi') C(xi'), which is not separable: it is evaluated sample by sample
+ * (G*G*(mW-1)^2 gathers per right-hand side), whatever ldm_set_algorithm says about the m*C integral.  One species,
+ * SquaredN extrapolation, one rank; such a handle steps with one launch per kernel and step (no persistent kernel) in
+ * ldm_rhs, ldm_solve, ldm_solve_rk4, ldm_advance and ldm_solve_batch.  At C == N^2 all three closures give the
+ * reference's right-hand side; away from it there is no reference to compare with (oracle: ldm_oracle_closure.c). */
+#define LDM_CLOSURE_POWER1            1
+#define LDM_CLOSURE_POWER2_SYMMETRIC  2
+#define LDM_CLOSURE_POWER3            3
+LDM_API int  ldm_set_closure(ldm_handle h, int closure);
+LDM_API int  ldm_get_closure(ldm_handle h);
+/* the two integrals on their own at `state` (1+G*G doubles): G*G each, either may be NULL; works under any closure */
+LDM_API int  ldm_closure_integrals(ldm_handle h, const double* state, double* w_conv_C, double* K);
+
 /* ---- Equation::operator()(t, vals, type) (S:431-513): host state in, host derivative out ---- */
 LDM_API int  ldm_rhs(ldm_handle h, const double* state, double* deriv);
 /* the two integrals on their own (S:265-295): WC scalar, MC G*G (MC may be NULL) */

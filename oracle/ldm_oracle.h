@@ -94,6 +94,15 @@ void ldmo_rhs_multi(const ldmo_multi* p, const double* state, double* deriv);
 /* EulerSolver::Solve (S:557-592) on such a state: full history, values n_points * width; returns the number of points */
 int ldmo_solve_multi(const ldmo_multi* p, double t_max, double dt, const double* init, double* times, double* values);
 
+/* ---- EXTENSION, parity unpinned beyond the uniform state (ldm_oracle_closure.c): the integrals that do not factorise --
+ * (w*C)(xi) and K(xi) = integral of w(xi') C(xi') C(xi + xi') at every node (G*G each, either may be NULL) -- and the
+ * right-hand side / Euler solve with the closure term of S:486-487 exchanged: closure 1 power-1 (the reference; ldmo_rhs
+ * bit for bit), 2 power-2 symmetric, 3 power-3.  SquaredN beyond the cutoff. ---- */
+double ldmo_w_mass(const ldmo_problem* p);
+void ldmo_closure_integrals(const ldmo_problem* p, const double* state, double* w_conv_C, double* K_out);
+void ldmo_rhs_closure(const ldmo_problem* p, const double* state, int closure, double* deriv);
+int ldmo_solve_closure(const ldmo_problem* p, int closure, double t_max, double dt, const double* init, double* times, double* values);
+
 /* threads the integrals' outer loop may use (results are identical for any count) */
 void ldmo_set_threads(int n);
 

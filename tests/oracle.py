@@ -38,6 +38,12 @@ def _load():
     lib.ldmo_count_points_rk4.argtypes = [C.c_double, C.c_double]
     lib.ldmo_solve_rk4.restype = C.c_int
     lib.ldmo_solve_rk4.argtypes = [C.POINTER(_Problem), C.c_double, C.c_double, _dp, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.ldmo_w_mass.restype = C.c_double
+    lib.ldmo_w_mass.argtypes = [C.POINTER(_Problem)]
+    lib.ldmo_closure_integrals.argtypes = [C.POINTER(_Problem), _dp, C.c_void_p, C.c_void_p]
+    lib.ldmo_rhs_closure.argtypes = [C.POINTER(_Problem), _dp, C.c_int, _dp]
+    lib.ldmo_solve_closure.restype = C.c_int
+    lib.ldmo_solve_closure.argtypes = [C.POINTER(_Problem), C.c_int, C.c_double, C.c_double, _dp, C.c_void_p, C.c_void_p]
     return lib
 
 
@@ -163,6 +169,31 @@ class OracleProblem:
         got = self.lib.ldmo_solve_rk4(self.p, t_max, dt, init, times.ctypes.data, values.ctypes.data, derivs.ctypes.data)
         assert got == n
         return times, values, derivs
+
+    # ---- extension, parity unpinned beyond the uniform state (oracle/ldm_oracle_closure.c) ----
+    def w_mass(self):
+        return self.lib.ldmo_w_mass(self.p)
+
+    def closure_integrals(self, state):
+        """(w*C)(xi) and K(xi) = integral of w(xi') C(xi') C(xi + xi') at every node"""
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        wc, k = np.zeros((self.G, self.G)), np.zeros((self.G, self.G))
+        self.lib.ldmo_closure_integrals(self.p, state, wc.ctypes.data, k.ctypes.data)
+        return wc, k
+
+    def rhs_closure(self, state, closure):
+        state = np.ascontiguousarray(state, dtype=np.float64)
+        out = np.zeros_like(state)
+        self.lib.ldmo_rhs_closure(self.p, state, int(closure), out)
+        return out
+
+    def solve_closure(self, closure, t_max, dt=0.1, init=None):
+        init = self.equilibrium() if init is None else np.ascontiguousarray(init, dtype=np.float64)
+        n = self.count_points(t_max, dt)
+        times, values = np.zeros(n), np.zeros((n, 1 + self.P))
+        got = self.lib.ldmo_solve_closure(self.p, int(closure), t_max, dt, init, times.ctypes.data, values.ctypes.data)
+        assert got == n
+        return times, values
 
     def close(self):
         if self.p:
