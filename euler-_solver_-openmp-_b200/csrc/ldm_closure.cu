@@ -8,8 +8,9 @@
 // per-axis tables of the w quadrature (abscissa, interval, weight, exact cutoff threshold) laid out exactly like the m
 // side's (ldm_model.cpp build_tables on a view of the problem with W in M's place).  Three kernels per right-hand side
 // behind the m*C integral and the first-moment equation:
-//   own_density_kernel   C~ at the (mW-1)^2 samples of the WC integral (shift (0,0)) -> the factor C~(xi') of K
-//   w_sums_kernel<OWN>   the sums above at every node (w*C only where the power-2 closure asks for it)
+//   own_density_kernel   w(xi') C~(xi') at the (mW-1)^2 samples of the WC integral (shift (0,0)): the table K convolves with
+//   w_sums_kernel<BOTH>  K at every node, and w*C from the same samples where the power-2 closure asks for it; the rows of C
+//                        interpolated along x are staged in shared memory once per CTA (16 nodes of one grid row)
 //   closing_kernel       dC/dt in the reference's operation order with the term of S:486-487 exchanged, Euler update, clamp
 // FP64 CUDA-core work: data-dependent 4-tap gathers; C (<= 2 MB) stays in L1/L2.  S:n = Solver.cpp line n.
 #include "ldm_context.h"
@@ -19,21 +20,17 @@ namespace ldm {
 
 namespace {
 
-constexpr int kNodesPerBlock = 8;          // one warp per node y, 8 consecutive y of one row x per CTA
+constexpr int kWarpsPerBlock = 16;         // one warp per node y: 16 consecutive y of one row x per CTA
+constexpr int kTileRows = 8;               // sample rows (offsets along x) whose x-interpolated C rows are staged at a time
+constexpr size_t kTileBytes = 48u << 10;   // shared memory a CTA may take without opting in
 
-__device__ __forceinline__ double bilinear_inside(const double* __restrict__ c_lo, const double* __restrict__ c_hi, int uy,
-                                                  double wx, double wy)
-{
-    // a(1-w) + b w along x, then along y: the form of sample_sum_kernel (ldm_kernels.cu)
-    const double ux_w = 1.0 - wx;
-    const double lo = c_lo[uy - 1] * ux_w + c_hi[uy - 1] * wx;
-    const double hi = c_lo[uy] * ux_w + c_hi[uy] * wx;
-    return lo * (1.0 - wy) + hi * wy;
-}
+// a(1-w) + b w, the form of sample_sum_kernel (ldm_kernels.cu): exact at w = 0 and w = 1, like S:348-351
+__device__ __forceinline__ double lerp2(double a, double b, double w) { return a * (1.0 - w) + b * w; }
 
-// C~ at the samples of the WC integral: (s[0][oi], s[0][oj]) -- node 0 is xi = 0, so these are (|xi'_x|, |xi'_y|)
+// t[oi][oj] = w(xi') C~(xi') at the samples of the WC integral: xi' = (s[0][oi], s[0][oj]) -- node 0 is xi = 0, so these
+// are (|xi'_x|, |xi'_y|).  The time-varying table K(xi) is a convolution with.
 __global__ void __launch_bounds__(256)
-own_density_kernel(DevProblem W, const double* __restrict__ C, const double* __restrict__ N_cur, double* __restrict__ own)
+own_density_kernel(DevProblem W, const double* __restrict__ C, const double* __restrict__ N_cur, double* __restrict__ t)
 {
     const int n_off = W.n_off, G = W.G;
     const int at = blockIdx.x * blockDim.x + threadIdx.x;
@@ -43,51 +40,78 @@ own_density_kernel(DevProblem W, const double* __restrict__ C, const double* __r
     double v = N * N;                                            // beyond the cutoff (S:329-331, SquaredN)
     if (W.s[oj] <= W.limit[oi]) {                                // row 0 of the tables: node 0
         const int ux = W.upper[oi], uy = W.upper[oj];
-        v = bilinear_inside(C + (size_t)(ux - 1) * G, C + (size_t)ux * G, uy, W.weight[oi], W.weight[oj]);
+        const double wx = W.weight[oi];
+        const double* c_lo = C + (size_t)(ux - 1) * G;
+        const double* c_hi = C + (size_t)ux * G;
+        v = lerp2(lerp2(c_lo[uy - 1], c_hi[uy - 1], wx), lerp2(c_lo[uy], c_hi[uy], wx), W.weight[oj]);
     }
-    own[at] = v;
+    t[at] = W.quadrant[(size_t)W.alpha[oi] * W.A + W.alpha[oj]] * v;
 }
 
-// out[x][y] = hh * (sum over inside samples of t * bilinear(C) + N^2 * sum over outside samples of t),
-// t = w (OWN false: the convolution w*C) or w * own[oi][oj] (OWN true: K)
-template <bool OWN>
-__global__ void __launch_bounds__(32 * kNodesPerBlock)
-w_sums_kernel(DevProblem W, const double* __restrict__ C, const double* __restrict__ own, const double* __restrict__ N_cur,
-              double* __restrict__ out)
+// K(xi) -- and with BOTH also (w*C)(xi) from the same samples -- at the nodes (x, y) of one row x:
+//     hh * (sum over inside samples of t * bilinear(C) + N^2 * sum over outside samples of t),   t = w C~(xi')  or  w.
+// The interpolation along x is the same for every y of the row: for `rows` sample rows at a time the CTA stages
+// E[oi][:] = (1 - wx) C[ux-1][:] + wx C[ux][:] in shared memory (coalesced reads of two rows of C), then every warp
+// walks its y's samples of those rows: two shared-memory taps and one interpolation along y per sample instead of four
+// gathers from global memory and three interpolations.  Lanes stride the offsets along y; fixed reduction order.
+template <bool BOTH>
+__global__ void __launch_bounds__(32 * kWarpsPerBlock)
+w_sums_kernel(DevProblem W, const double* __restrict__ C, const double* __restrict__ t, const double* __restrict__ N_cur,
+              int rows, double* __restrict__ k_out, double* __restrict__ w_out)
 {
+    extern __shared__ double tile[];                             // [rows][G]
     const int G = W.G, n_off = W.n_off, A = W.A;
     const int x = blockIdx.y;
-    const int y = blockIdx.x * kNodesPerBlock + threadIdx.y;
-    if (y >= G) return;
-    const int lane = threadIdx.x;
+    const int y = blockIdx.x * kWarpsPerBlock + threadIdx.y;
+    const bool live = y < G;                                     // the warps beyond the row's end still build and wait
+    const int lane = threadIdx.x, thread = threadIdx.y * 32 + lane;
     const double* lim_row = W.limit + (size_t)x * n_off;
     const double* wx_row = W.weight + (size_t)x * n_off;
     const int* ux_row = W.upper + (size_t)x * n_off;
-    const double* sy_row = W.s + (size_t)y * n_off;
-    const double* wy_row = W.weight + (size_t)y * n_off;
-    const int* uy_row = W.upper + (size_t)y * n_off;
+    const double* sy_row = W.s + (size_t)(live ? y : 0) * n_off;
+    const double* wy_row = W.weight + (size_t)(live ? y : 0) * n_off;
+    const int* uy_row = W.upper + (size_t)(live ? y : 0) * n_off;
 
-    double inside = 0.0, outside = 0.0;
-    for (int oi = 0; oi < n_off; oi++) {
-        const double lim = lim_row[oi];
-        const int ux = ux_row[oi];
-        const double wx = wx_row[oi];
-        const double* q_row = W.quadrant + (size_t)W.alpha[oi] * A;
-        const double* own_row = OWN ? own + (size_t)oi * n_off : nullptr;
-        const double* c_lo = C + (size_t)(ux > 0 ? ux - 1 : 0) * G;
-        const double* c_hi = C + (size_t)ux * G;
-        for (int oj = lane; oj < n_off; oj += 32) {
-            double t = q_row[W.alpha[oj]];
-            if (OWN) t *= own_row[oj];
-            if (sy_row[oj] <= lim) inside += t * bilinear_inside(c_lo, c_hi, uy_row[oj], wx, wy_row[oj]);
-            else outside += t;
+    double k_inside = 0.0, k_outside = 0.0, w_inside = 0.0, w_outside = 0.0;
+    for (int first = 0; first < n_off; first += rows) {
+        const int n_rows = min(rows, n_off - first);
+        for (int e = thread; e < n_rows * G; e += 32 * kWarpsPerBlock) {
+            const int r = e / G, col = e - r * G;
+            const int ux = ux_row[first + r];
+            tile[e] = lerp2(C[(size_t)(ux > 0 ? ux - 1 : 0) * G + col], C[(size_t)ux * G + col], wx_row[first + r]);
         }
+        __syncthreads();
+        if (live) {
+            for (int r = 0; r < n_rows; r++) {
+                const int oi = first + r;
+                const double lim = lim_row[oi];
+                const double* t_row = t + (size_t)oi * n_off;
+                const double* q_row = W.quadrant + (size_t)W.alpha[oi] * A;
+                const double* E = tile + (size_t)r * G;
+                for (int oj = lane; oj < n_off; oj += 32) {
+                    const double tk = t_row[oj];
+                    const double tw = BOTH ? q_row[W.alpha[oj]] : 0.0;
+                    if (sy_row[oj] <= lim) {
+                        const int uy = uy_row[oj];
+                        const double v = lerp2(E[uy - 1], E[uy], wy_row[oj]);
+                        k_inside += tk * v;
+                        if (BOTH) w_inside += tw * v;
+                    } else {
+                        k_outside += tk;
+                        if (BOTH) w_outside += tw;
+                    }
+                }
+            }
+        }
+        __syncthreads();
     }
-    inside = warp_sum_fixed(inside);
-    outside = warp_sum_fixed(outside);
-    if (lane == 0) {
-        const double N = N_cur[0];
-        out[(size_t)x * G + y] = __dmul_rn(__dadd_rn(inside, __dmul_rn(__dmul_rn(N, N), outside)), W.hh);
+    k_inside = warp_sum_fixed(k_inside);
+    k_outside = warp_sum_fixed(k_outside);
+    if (BOTH) { w_inside = warp_sum_fixed(w_inside); w_outside = warp_sum_fixed(w_outside); }
+    if (live && lane == 0) {
+        const double N = N_cur[0], asymptote = __dmul_rn(N, N);
+        k_out[(size_t)x * G + y] = __dmul_rn(__dadd_rn(k_inside, __dmul_rn(asymptote, k_outside)), W.hh);
+        if (BOTH) w_out[(size_t)x * G + y] = __dmul_rn(__dadd_rn(w_inside, __dmul_rn(asymptote, w_outside)), W.hh);
     }
 }
 
@@ -166,10 +190,13 @@ void closure_integrals_on_device(ldm_context* c, const double* C, const double* 
     const DevProblem& w = c->closure_w;
     const int samples = w.n_off * w.n_off;
     own_density_kernel<<<(samples + 255) / 256, 256, 0, s>>>(w, C, N_cur, c->d_own_density);
-    const dim3 block(32, kNodesPerBlock), grid((w.G + kNodesPerBlock - 1) / kNodesPerBlock, w.G);
-    if (want_w_conv) w_sums_kernel<false><<<grid, block, 0, s>>>(w, C, nullptr, N_cur, c->d_w_conv);
-    w_sums_kernel<true><<<grid, block, 0, s>>>(w, C, c->d_own_density, N_cur, c->d_k_int);
-    c->launches += want_w_conv ? 3 : 2;
+    const int rows = (int)std::min<size_t>(kTileRows, kTileBytes / ((size_t)w.G * sizeof(double)));
+    if (rows < 1) throw std::invalid_argument("a row of C does not fit the shared-memory tile of the closure integrals");
+    const dim3 block(32, kWarpsPerBlock), grid((w.G + kWarpsPerBlock - 1) / kWarpsPerBlock, w.G);
+    const size_t smem = (size_t)rows * w.G * sizeof(double);
+    if (want_w_conv) w_sums_kernel<true><<<grid, block, smem, s>>>(w, C, c->d_own_density, N_cur, rows, c->d_k_int, c->d_w_conv);
+    else w_sums_kernel<false><<<grid, block, smem, s>>>(w, C, c->d_own_density, N_cur, rows, c->d_k_int, nullptr);
+    c->launches += 2;
     LDM_CUDA(cudaGetLastError());
 }
 

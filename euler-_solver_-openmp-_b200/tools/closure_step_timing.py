@@ -1,7 +1,7 @@
 """Step time of the Euler loop under the three closures (ldm.h ldm_set_closure): power-1 is the reference's (persistent
 kernel where the grid allows), power-2 / power-3 add the integrals over the w quadrature -- G*G*(mW-1)^2 gathers per step for
 K(xi), twice that for power-2 -- with one launch per kernel and step.  Device time of ldm_advance (CUDA events on the stream);
-usage: closure_step_timing.py [steps]"""
+usage: closure_step_timing.py [steps] [forced_G: only that synthetic grid]"""
 import os
 import sys
 
@@ -12,8 +12,11 @@ from __graft_entry__ import load_package
 
 ldm = load_package()
 steps = int(sys.argv[1]) if len(sys.argv) > 1 else 50
+only = int(sys.argv[2]) if len(sys.argv) > 2 else -1
 for label, sigma, forced_G in (("14.4a", 0.15, 0), ("14.4b", 0.05, 0), ("14.4a parameters, 4 096 points", 0.15, 64),
                                ("14.4a parameters, 16 384 points", 0.15, 128)):
+    if only >= 0 and forced_G != only:
+        continue
     props = ldm.Properties.Generate(1, sigma, sigma, 0.4, 0.2, 0.001, forced_G)
     eq = ldm.Equation(props)
     g = np.array(props.MomentsGrid)
