@@ -618,7 +618,8 @@ int ldm_tuning_set(const char* name, int value)
     if (!name) return fail(LDM_ERR_ARGUMENT, "NULL argument");
     ldm::Tuning& t = tuning();
     const std::string key(name);
-    if (key == "reset") t = ldm::Tuning();
+    if (key == "reset") { t = ldm::Tuning(); ldm::closure_force_tiles(-1); }
+    else if (key == "closure_tiles") ldm::closure_force_tiles(value);
     else if (key == "scan_bn") t.scan_bn = value;
     else if (key == "scan_nt") t.scan_nt = value;
     else if (key == "factored_bm") t.factored_bm = value;

@@ -54,7 +54,14 @@ own_density_kernel(DevProblem W, const double* __restrict__ C, const double* __r
 // E[oi][:] = (1 - wx) C[ux-1][:] + wx C[ux][:] in shared memory (coalesced reads of two rows of C), then every warp
 // walks its y's samples of those rows: two shared-memory taps and one interpolation along y per sample instead of four
 // gathers from global memory and three interpolations.  Lanes stride the offsets along y; fixed reduction order.
-template <bool BOTH>
+// The kernel is bound by the load/store data pipe (ncu at 16 384 points: 72-78 % of its peak, profiles/r02o_ncu_w_sums_g128.csv).
+// What a lane needs of ITS offsets along y -- abscissa, interval, weight, table column: the same for every sample row -- is
+// held in registers where the quadrature is at most 64 offsets wide (TILES = 2: every experiment of the reference's 14.4;
+// 14.4a: 64.8 -> 57.6 us per step); wider quadratures read them per sample (TILES = 0): holding 5 or 8 tiles was measured
+// and is slower (16 384 points: 955 against 811 us per step -- 62-100 registers per thread cost a third of the resident
+// warps, and this kernel lives on them: `long_scoreboard` is its first stall reason).  Both variants add the same numbers
+// in the same order.
+template <bool BOTH, int TILES>
 __global__ void __launch_bounds__(32 * kWarpsPerBlock)
 w_sums_kernel(DevProblem W, const double* __restrict__ C, const double* __restrict__ t, const double* __restrict__ N_cur,
               int rows, double* __restrict__ k_out, double* __restrict__ w_out)
@@ -72,6 +79,21 @@ w_sums_kernel(DevProblem W, const double* __restrict__ C, const double* __restri
     const double* wy_row = W.weight + (size_t)(live ? y : 0) * n_off;
     const int* uy_row = W.upper + (size_t)(live ? y : 0) * n_off;
 
+    constexpr int kHeld = TILES > 0 ? TILES : 1;
+    double sy_held[kHeld], wy_held[kHeld];
+    int uy_held[kHeld], column_held[kHeld];
+    if (TILES > 0) {
+        #pragma unroll
+        for (int k = 0; k < kHeld; k++) {
+            const int oj = lane + 32 * k;
+            const bool mine = oj < n_off;
+            sy_held[k] = mine ? sy_row[oj] : 0.0;
+            wy_held[k] = mine ? wy_row[oj] : 0.0;
+            uy_held[k] = mine ? uy_row[oj] : 1;
+            column_held[k] = (BOTH && mine) ? W.alpha[oj] : 0;
+        }
+    }
+
     double k_inside = 0.0, k_outside = 0.0, w_inside = 0.0, w_outside = 0.0;
     for (int first = 0; first < n_off; first += rows) {
         const int n_rows = min(rows, n_off - first);
@@ -88,17 +110,36 @@ w_sums_kernel(DevProblem W, const double* __restrict__ C, const double* __restri
                 const double* t_row = t + (size_t)oi * n_off;
                 const double* q_row = W.quadrant + (size_t)W.alpha[oi] * A;
                 const double* E = tile + (size_t)r * G;
-                for (int oj = lane; oj < n_off; oj += 32) {
-                    const double tk = t_row[oj];
-                    const double tw = BOTH ? q_row[W.alpha[oj]] : 0.0;
-                    if (sy_row[oj] <= lim) {
-                        const int uy = uy_row[oj];
-                        const double v = lerp2(E[uy - 1], E[uy], wy_row[oj]);
-                        k_inside += tk * v;
-                        if (BOTH) w_inside += tw * v;
-                    } else {
-                        k_outside += tk;
-                        if (BOTH) w_outside += tw;
+                if (TILES > 0) {
+                    #pragma unroll
+                    for (int k = 0; k < kHeld; k++) {
+                        const int oj = lane + 32 * k;
+                        if (oj < n_off) {
+                            const double tk = t_row[oj];
+                            const double tw = BOTH ? q_row[column_held[k]] : 0.0;
+                            if (sy_held[k] <= lim) {
+                                const double v = lerp2(E[uy_held[k] - 1], E[uy_held[k]], wy_held[k]);
+                                k_inside += tk * v;
+                                if (BOTH) w_inside += tw * v;
+                            } else {
+                                k_outside += tk;
+                                if (BOTH) w_outside += tw;
+                            }
+                        }
+                    }
+                } else {
+                    for (int oj = lane; oj < n_off; oj += 32) {
+                        const double tk = t_row[oj];
+                        const double tw = BOTH ? q_row[W.alpha[oj]] : 0.0;
+                        if (sy_row[oj] <= lim) {
+                            const int uy = uy_row[oj];
+                            const double v = lerp2(E[uy - 1], E[uy], wy_row[oj]);
+                            k_inside += tk * v;
+                            if (BOTH) w_inside += tw * v;
+                        } else {
+                            k_outside += tk;
+                            if (BOTH) w_outside += tw;
+                        }
                     }
                 }
             }
@@ -113,6 +154,21 @@ w_sums_kernel(DevProblem W, const double* __restrict__ C, const double* __restri
         k_out[(size_t)x * G + y] = __dmul_rn(__dadd_rn(k_inside, __dmul_rn(asymptote, k_outside)), W.hh);
         if (BOTH) w_out[(size_t)x * G + y] = __dmul_rn(__dadd_rn(w_inside, __dmul_rn(asymptote, w_outside)), W.hh);
     }
+}
+
+int g_forced_tiles = -1;                   // ldm_tuning_set("closure_tiles"): tests reach every variant on small grids
+
+template <bool BOTH>
+void launch_w_sums(const DevProblem& w, const double* C, const double* t, const double* N_cur, double* k_out, double* w_out, cudaStream_t s)
+{
+    const int rows = (int)std::min<size_t>(kTileRows, kTileBytes / ((size_t)w.G * sizeof(double)));
+    if (rows < 1) throw std::invalid_argument("a row of C does not fit the shared-memory tile of the closure integrals");
+    const dim3 block(32, kWarpsPerBlock), grid((w.G + kWarpsPerBlock - 1) / kWarpsPerBlock, w.G);
+    const size_t smem = (size_t)rows * w.G * sizeof(double);
+    int tiles = w.n_off <= 64 ? 2 : 0;
+    if (g_forced_tiles >= 0) tiles = g_forced_tiles * 32 >= w.n_off ? g_forced_tiles : 0;
+    if (tiles == 2) w_sums_kernel<BOTH, 2><<<grid, block, smem, s>>>(w, C, t, N_cur, rows, k_out, w_out);
+    else w_sums_kernel<BOTH, 0><<<grid, block, smem, s>>>(w, C, t, N_cur, rows, k_out, w_out);
 }
 
 // Solver.cpp:459-508 with the term of S:486-487 exchanged, then value + derivative * step and the clamp (S:577-580).
@@ -190,17 +246,15 @@ void closure_integrals_on_device(ldm_context* c, const double* C, const double* 
     const DevProblem& w = c->closure_w;
     const int samples = w.n_off * w.n_off;
     own_density_kernel<<<(samples + 255) / 256, 256, 0, s>>>(w, C, N_cur, c->d_own_density);
-    const int rows = (int)std::min<size_t>(kTileRows, kTileBytes / ((size_t)w.G * sizeof(double)));
-    if (rows < 1) throw std::invalid_argument("a row of C does not fit the shared-memory tile of the closure integrals");
-    const dim3 block(32, kWarpsPerBlock), grid((w.G + kWarpsPerBlock - 1) / kWarpsPerBlock, w.G);
-    const size_t smem = (size_t)rows * w.G * sizeof(double);
-    if (want_w_conv) w_sums_kernel<true><<<grid, block, smem, s>>>(w, C, c->d_own_density, N_cur, rows, c->d_k_int, c->d_w_conv);
-    else w_sums_kernel<false><<<grid, block, smem, s>>>(w, C, c->d_own_density, N_cur, rows, c->d_k_int, nullptr);
+    if (want_w_conv) launch_w_sums<true>(w, C, c->d_own_density, N_cur, c->d_k_int, c->d_w_conv, s);
+    else launch_w_sums<false>(w, C, c->d_own_density, N_cur, c->d_k_int, nullptr, s);
     c->launches += 2;
     LDM_CUDA(cudaGetLastError());
 }
 
 }  // namespace
+
+void closure_force_tiles(int tiles) { g_forced_tiles = (tiles == 0 || tiles == 2) ? tiles : -1; }
 
 void closure_close(ldm_context* c, const DevProblem& P, const double* C, const double* N_cur, double dt, double* deriv_out,
                    double* C_next, cudaStream_t s)

@@ -223,6 +223,9 @@ void check_device_status(ldm_context* c);
 // sums of this right-hand side (c->d_sum); scalars[0] = WC.
 void closure_close(ldm_context* c, const DevProblem& P, const double* C, const double* N_cur, double dt, double* deriv_out,
                    double* C_next, cudaStream_t s);
+// test hook (ldm_tuning_set "closure_tiles"): which variant of the sums kernel runs -- a lane's offsets held in registers
+// (2 tiles of 32) or read per sample (0); anything else: chosen by the width of the quadrature
+void closure_force_tiles(int tiles);
 
 // defined in ldm_shard_api.cu: the persistent work-list kernel on this handle's current sharding.  replicas: the
 // handle's own d_C (one rank, natural layout) or the peer group's.  History pointers (device) may be NULL.

@@ -222,6 +222,7 @@ LDM_API int  ldm_shard_peer_download(ldm_handle h, double* C_gathered, double* N
  * "factored_bm", "factored_bn", "factored_tn" (dense contraction tiles), "persistent" (0: one launch per kernel and
  * step), "scan" (0: never the prefix-sum path), "chunk_grid" (CTAs of the persistent work-list kernel), "batch_capacity" (CTA budget of
  * the persistent batch kernel), "item_order" (work-list kernel, measurements: 0 rows ascending, 1 chunk by chunk, 2 rows descending),
+ * "closure_tiles" (closure integrals: 2 = a lane's offsets held in registers, two tiles of 32; 0 = read per sample),
  * "reset". ---- */
 LDM_API int  ldm_tuning_set(const char* name, int value);
 

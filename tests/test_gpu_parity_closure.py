@@ -152,3 +152,27 @@ def test_what_the_closures_are_not_built_for_is_refused(ldm):
     two = ldm.Properties.Generate(2, [[0.05, 0.06], [0.06, 0.05]], [0.05] * 2, [0.4, 0.401], [0.2] * 2, np.full((2, 2), 0.001))
     with pytest.raises(ldm.LdmError, match="one species"):
         ldm.Equation(two).set_closure(ldm.CLOSURE_POWER3)
+
+
+@pytest.mark.parametrize("name", ["exp_14_4_b", "exp_14_4_a", "synth_g32"])
+def test_every_variant_of_the_sums_kernel_adds_the_same_numbers(ldm, name):
+    """the sums kernel holds a lane's offsets in registers where the quadrature is at most 64 offsets wide and reads them
+    per sample otherwise: the same additions in the same order, so the same bits; the width picks the variant,
+    ldm_tuning_set("closure_tiles") forces one (the held variant falls back to per-sample reads on a wider quadrature)"""
+    g = golden(name)
+    props, o = problems_from(g, name, ldm)
+    eq = ldm.Equation(props)
+    state = a_state(g, name, o)
+    try:
+        results = []
+        for tiles in (-1, 0, 2):
+            ldm.tuning_set("closure_tiles", tiles)
+            results.append(eq.closure_integrals(state))
+            eq.set_closure(ldm.CLOSURE_POWER2_SYMMETRIC)
+            results[-1] += (eq(0.0, state, ldm.SquaredN),)
+            eq.set_closure(ldm.CLOSURE_POWER1)
+    finally:
+        ldm.tuning_set("reset")
+    for other in results[1:]:
+        for a, b in zip(results[0], other):
+            assert np.array_equal(a, b)
