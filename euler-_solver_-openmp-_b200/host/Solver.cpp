@@ -128,11 +128,16 @@ class Equation
     std::shared_ptr<ldm_context> handle;     // copies of an Equation share one device context
 
 public:
+    // --closure on the command line (an extension, include/ldm.h ldm_set_closure): the closure every Equation of this run
+    // is evaluated with; the reference's own (power-1) unless asked otherwise
+    static int& closure_of_this_run() { static int closure = LDM_CLOSURE_POWER1; return closure; }
+
     Equation(Properties p, int device = 0) : props(p)
     {
         ldm_handle h = nullptr;
         ldm_require(ldm_create(props.flat.get(), device, &h), "ldm_create");
         handle = std::shared_ptr<ldm_context>(h, ldm_destroy);
+        if (closure_of_this_run() != LDM_CLOSURE_POWER1) ldm_require(ldm_set_closure(h, closure_of_this_run()), "ldm_set_closure");
     }
 
     int state_size() const { const int n = props.flat->species; return n + n * n * props.flat->G * props.flat->G; }   // S:260
@@ -642,6 +647,12 @@ int main(int argc, char** argv)
         const std::string a = argv[i];
         if (a == "--data-dir" && i + 1 < argc) data_dir = argv[++i];
         else if (a == "--describe" && i + 1 < argc) { Experiments(data_dir).Describe(parse_choice(argv[++i])); return 0; }
+        else if (a == "--closure" && i + 1 < argc) {
+            const std::string name = argv[++i];
+            const int closure = name == "power1" ? LDM_CLOSURE_POWER1 : name == "power2" ? LDM_CLOSURE_POWER2_SYMMETRIC : name == "power3" ? LDM_CLOSURE_POWER3 : 0;
+            if (closure == 0) { std::cerr << "unknown closure '" << name << "' (power1, power2, power3)\n"; return 2; }
+            Equation::closure_of_this_run() = closure;
+        }
         else args.push_back(a);
     }
     Experiments run(data_dir);

@@ -86,6 +86,27 @@ def test_experiment_14_4_writes_visdata(tmp_path, choice, golden, title):
 
 
 @pytest.mark.gpu
+def test_experiment_14_4_under_another_closure(tmp_path):
+    """--closure power3 (an extension, ldm.h ldm_set_closure): Experiment 14.4 (b) with the third moment closed by the
+    Kirkwood superposition -- the columns the front-end writes against the extension's CPU oracle at all 1001 points,
+    and a run that visibly differs from the reference's closure (N ends near 177 instead of 89.47)"""
+    from oracle import OracleProblem
+    solver = build_solver()
+    os.makedirs(tmp_path / "Data")
+    subprocess.check_call(["cp", "-r", os.path.join(HOST, "Data", "14"), str(tmp_path / "Data")])
+    subprocess.check_call([solver, "--closure", "power3", "14.4.b"], cwd=tmp_path, stdout=subprocess.DEVNULL)
+    number, title, labels, data = read_visdata(tmp_path / "Data" / "VisData.csv")
+    assert number == 14.4 and title == "(b)" and data.shape == (1001, 3)
+    o = OracleProblem(0.05, 0.05)
+    times, values = o.solve_closure(3, 100, 0.1)
+    want = np.stack([times, values[:, 0], np.sqrt(values[:, o.G])], 1)
+    assert np.allclose(data, want, rtol=1e-5, atol=0)
+    g = np.load(os.path.join(ROOT, "tests", "golden", "exp_14_4_b.npz"))
+    assert abs(data[-1, 1] - g["obs"][-1, 0]) > 1.0                # power-1 ends at N = 89.4668
+    assert subprocess.call([solver, "--closure", "power9", "14.4.b"], cwd=tmp_path, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL) == 2
+
+
+@pytest.mark.gpu
 def test_custom_experiment_with_two_species(tmp_path):
     """Custom_Experiment (Solver.cpp:1073-1103) on the reference's own two-species example input, copied to where the
     experiment reads it: same positional parser, Properties::Generate with num = 2, 1001 points, and the two columns the
