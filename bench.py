@@ -515,6 +515,41 @@ def run_sweep(ldm, torch, local_rank):
             "reference": "estimated >= 15 h on 8 cores (SURVEY 6): entries i = 12 and 80 alone take 141 s and 20 s of one core"}
 
 
+def run_closures(ldm, props, init, local_rank, lsu_peak, steps=10):
+    """The extension of DESIGN.md 11 on the headline grid: Euler steps with the third moment closed by the power-3 and the
+    power-2 (symmetric) closure -- K(xi) = integral of w(xi') C(xi') C(xi + xi') (and (w*C)(xi)) at every node, sample by
+    sample, behind the same m*C integral.  Device time of ldm_advance.  Never lets the bench line down: an error is reported
+    in the leg."""
+    try:
+        eq = ldm.Equation(props, device=local_rank)
+        n_off = max(props.MaxNumForW - 1, 1)
+        samples = props.G ** 2 * n_off ** 2
+        # load/store data-pipe wavefronts the sums kernel needs at least: per warp iteration (32 offsets along y of one sample row)
+        # table entry, abscissa and weight two each, interval one, two 8-byte shared-memory taps two each (DESIGN.md 11)
+        wavefronts_min = 11.0 * props.G ** 2 * n_off * ((n_off + 31) // 32)
+        out = {"workload": f"{props.G * props.G} xi-points, w quadrature {n_off} x {n_off}: {samples} samples per integral and step",
+               "steps": steps, "parity": "extension: pinned to the reference at the uniform state and for power-1 only (DESIGN.md 11)"}
+        for closure, name in ((ldm.CLOSURE_POWER3, "power3"), (ldm.CLOSURE_POWER2_SYMMETRIC, "power2")):
+            eq.set_closure(closure)
+            eq.upload(init); eq.advance(3, DT); eq.synchronize()
+            eq.upload(init); eq.synchronize()
+            before = eq.launches
+            eq.advance(steps, DT); eq.synchronize()
+            ms = eq.last_elapsed_ms() / steps
+            state = eq.download()
+            assert np.all(np.isfinite(state))
+            out[name] = {"ms_per_step": ms, "value": props.G ** 2 / (ms * 1e-3), "unit": UNIT,
+                         "gpu_launches_per_step": (eq.launches - before) / steps,
+                         "samples_per_s": samples * (2 if closure == ldm.CLOSURE_POWER2_SYMMETRIC else 1) / (ms * 1e-3),
+                         "N_after": float(state[0])}
+        out["lsu_frac_power3"] = wavefronts_min / (out["power3"]["ms_per_step"] * 1e-3) / lsu_peak
+        out["lsu_frac_note"] = ("minimal data-pipe wavefronts of the K integral over the whole power-3 step (m*C integral and closing "
+                                "included in the time) against the pipe's peak measured live")
+        return out
+    except Exception as e:                       # noqa: BLE001 -- the headline legs must not depend on the extension
+        return {"error": f"{type(e).__name__}: {e}"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -674,6 +709,7 @@ def main():
         batch = run_batch(ldm, torch, dist, rank, world, local_rank, args.batch_sets, args.batch_steps)
 
     sweep = run_sweep(ldm, torch, local_rank) if (world == 1 and not args.no_sweep) else None
+    closures = run_closures(ldm, props, state0, local_rank, lsu_peak) if (world == 1 and not args.no_sweep) else None
 
     if rank == 0:
         ms_per_step = total_ms / args.steps
@@ -738,6 +774,8 @@ def main():
             line["batch"] = batch
         if sweep is not None:
             line["sweep"] = sweep
+        if closures is not None:
+            line["closures"] = closures
         if not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline(args.workload)
         emit(line)
