@@ -41,8 +41,8 @@ own_density_kernel(DevProblem W, const double* __restrict__ C, const double* __r
     if (W.s[oj] <= W.limit[oi]) {                                // row 0 of the tables: node 0
         const int ux = W.upper[oi], uy = W.upper[oj];
         const double wx = W.weight[oi];
-        const double* c_lo = C + (size_t)(ux - 1) * G;
-        const double* c_hi = C + (size_t)ux * G;
+        const double* c_lo = C + (size_t)row_slot(W, ux - 1) * G;
+        const double* c_hi = C + (size_t)row_slot(W, ux) * G;
         v = lerp2(lerp2(c_lo[uy - 1], c_hi[uy - 1], wx), lerp2(c_lo[uy], c_hi[uy], wx), W.weight[oj]);
     }
     t[at] = W.quadrant[(size_t)W.alpha[oi] * W.A + W.alpha[oj]] * v;
@@ -68,7 +68,7 @@ w_sums_kernel(DevProblem W, const double* __restrict__ C, const double* __restri
 {
     extern __shared__ double tile[];                             // [rows][G]
     const int G = W.G, n_off = W.n_off, A = W.A;
-    const int x = blockIdx.y;
+    const int x = W.rank + W.world * blockIdx.y;                 // this rank's rows (all rows when world == 1)
     const int y = blockIdx.x * kWarpsPerBlock + threadIdx.y;
     const bool live = y < G;                                     // the warps beyond the row's end still build and wait
     const int lane = threadIdx.x, thread = threadIdx.y * 32 + lane;
@@ -100,7 +100,7 @@ w_sums_kernel(DevProblem W, const double* __restrict__ C, const double* __restri
         for (int e = thread; e < n_rows * G; e += 32 * kWarpsPerBlock) {
             const int r = e / G, col = e - r * G;
             const int ux = ux_row[first + r];
-            tile[e] = lerp2(C[(size_t)(ux > 0 ? ux - 1 : 0) * G + col], C[(size_t)ux * G + col], wx_row[first + r]);
+            tile[e] = lerp2(C[(size_t)row_slot(W, ux > 0 ? ux - 1 : 0) * G + col], C[(size_t)row_slot(W, ux) * G + col], wx_row[first + r]);
         }
         __syncthreads();
         if (live) {
@@ -151,8 +151,8 @@ w_sums_kernel(DevProblem W, const double* __restrict__ C, const double* __restri
     if (BOTH) { w_inside = warp_sum_fixed(w_inside); w_outside = warp_sum_fixed(w_outside); }
     if (live && lane == 0) {
         const double N = N_cur[0], asymptote = __dmul_rn(N, N);
-        k_out[(size_t)x * G + y] = __dmul_rn(__dadd_rn(k_inside, __dmul_rn(asymptote, k_outside)), W.hh);
-        if (BOTH) w_out[(size_t)x * G + y] = __dmul_rn(__dadd_rn(w_inside, __dmul_rn(asymptote, w_outside)), W.hh);
+        k_out[(size_t)blockIdx.y * G + y] = __dmul_rn(__dadd_rn(k_inside, __dmul_rn(asymptote, k_outside)), W.hh);      // shard-local
+        if (BOTH) w_out[(size_t)blockIdx.y * G + y] = __dmul_rn(__dadd_rn(w_inside, __dmul_rn(asymptote, w_outside)), W.hh);
     }
 }
 
@@ -163,7 +163,7 @@ void launch_w_sums(const DevProblem& w, const double* C, const double* t, const 
 {
     const int rows = (int)std::min<size_t>(kTileRows, kTileBytes / ((size_t)w.G * sizeof(double)));
     if (rows < 1) throw std::invalid_argument("a row of C does not fit the shared-memory tile of the closure integrals");
-    const dim3 block(32, kWarpsPerBlock), grid((w.G + kWarpsPerBlock - 1) / kWarpsPerBlock, w.G);
+    const dim3 block(32, kWarpsPerBlock), grid((w.G + kWarpsPerBlock - 1) / kWarpsPerBlock, local_rows(w));
     const size_t smem = (size_t)rows * w.G * sizeof(double);
     int tiles = w.n_off <= 64 ? 2 : 0;
     if (g_forced_tiles >= 0) tiles = g_forced_tiles * 32 >= w.n_off ? g_forced_tiles : 0;
@@ -178,10 +178,13 @@ closing_kernel(DevProblem P, const double* __restrict__ C, const double* __restr
                const double* __restrict__ scalars, double dt, int closure, double w_mass, const double* __restrict__ w_conv,
                const double* __restrict__ k_int, double* __restrict__ deriv_out, double* __restrict__ C_next)
 {
-    const int q = blockIdx.x * blockDim.x + threadIdx.x;
-    if (q >= P.G * P.G) return;
-    const double N = N_cur[0], WC = scalars[0], c = C[q];
-    const double mc = __dmul_rn(add_outside(P, inside_sum[q], N, C, scalars, P.out_weight[q], 0.0), P.hh);      // S:311, S:314
+    const int ql = blockIdx.x * blockDim.x + threadIdx.x;        // shard-local index: inside_sum, w_conv, k_int, deriv_out, C_next
+    if (ql >= local_rows(P) * P.G) return;
+    const int lx = ql / P.G, y = ql - lx * P.G;
+    const int q = (P.rank + P.world * lx) * P.G + y;             // natural index of this node: the time-invariant tables
+    const double N = N_cur[0], WC = scalars[0];
+    const double c = C[(size_t)(P.rank * P.rows_per_rank + lx) * P.G + y];                  // gathered layout
+    const double mc = __dmul_rn(add_outside(P, inside_sum[ql], N, C, scalars, P.out_weight[q], 0.0), P.hh);     // S:311, S:314
     double r = __dadd_rn(__dmul_rn(P.b, mc), __dmul_rn(P.b, mc));                           // S:464
     r = __dadd_rn(r, __dmul_rn(__dmul_rn(__dmul_rn(2.0, P.b), N), P.m_nodes[q]));           // S:469
     const double death = __dmul_rn(P.d, c);
@@ -190,10 +193,10 @@ closing_kernel(DevProblem P, const double* __restrict__ C, const double* __restr
     const double cube = __dmul_rn(__dmul_rn(N, N), N);
     double triplets;                                                                        // integral of w(xi') T(xi, xi')
     if (closure == LDM_CLOSURE_POWER3) {
-        triplets = __ddiv_rn(__dmul_rn(c, k_int[q]), cube);
+        triplets = __ddiv_rn(__dmul_rn(c, k_int[ql]), cube);
     } else {
-        double sum = __dadd_rn(__ddiv_rn(__dmul_rn(WC, c), N), __ddiv_rn(__dmul_rn(c, w_conv[q]), N));
-        sum = __dadd_rn(sum, __ddiv_rn(k_int[q], N));
+        double sum = __dadd_rn(__ddiv_rn(__dmul_rn(WC, c), N), __ddiv_rn(__dmul_rn(c, w_conv[ql]), N));
+        sum = __dadd_rn(sum, __ddiv_rn(k_int[ql], N));
         sum = __dsub_rn(sum, __dmul_rn(cube, w_mass));
         triplets = __dmul_rn(0.5, sum);
     }
@@ -203,10 +206,10 @@ closing_kernel(DevProblem P, const double* __restrict__ C, const double* __restr
     const double local = __dmul_rn(__dmul_rn(P.dd, c), P.w_nodes[q]);                       // S:490
     r = __dsub_rn(r, local);
     r = __dsub_rn(r, local);                                                                // S:498
-    if (deriv_out) deriv_out[q] = r;
+    if (deriv_out) deriv_out[ql] = r;
     if (C_next) {
         const double v = __dadd_rn(c, __dmul_rn(r, dt));                                    // S:577
-        C_next[q] = v < 0.0 ? 0.0 : v;                                                      // S:578-580
+        C_next[ql] = v < 0.0 ? 0.0 : v;                                                     // S:578-580
     }
 }
 
@@ -240,10 +243,11 @@ void ensure_closure_tables(ldm_context* c)
 }
 
 // (w*C)(xi) (when wanted) and K(xi) at the state (N_cur, C), natural layout
-void closure_integrals_on_device(ldm_context* c, const double* C, const double* N_cur, bool want_w_conv, cudaStream_t s)
+void closure_integrals_on_device(ldm_context* c, const DevProblem& P, const double* C, const double* N_cur, bool want_w_conv, cudaStream_t s)
 {
     ensure_closure_tables(c);
-    const DevProblem& w = c->closure_w;
+    DevProblem& w = c->closure_w;
+    w.world = P.world; w.rank = P.rank; w.rows_per_rank = P.rows_per_rank;      // xi-sharding: C in gathered layout, this rank's rows
     const int samples = w.n_off * w.n_off;
     own_density_kernel<<<(samples + 255) / 256, 256, 0, s>>>(w, C, N_cur, c->d_own_density);
     if (want_w_conv) launch_w_sums<true>(w, C, c->d_own_density, N_cur, c->d_k_int, c->d_w_conv, s);
@@ -261,8 +265,8 @@ void closure_close(ldm_context* c, const DevProblem& P, const double* C, const d
 {
     if (!deriv_out && !C_next) return;                // integrals only
     const bool power2 = c->closure == LDM_CLOSURE_POWER2_SYMMETRIC;
-    closure_integrals_on_device(c, C, N_cur, power2, s);
-    const int n = P.G * P.G;
+    closure_integrals_on_device(c, P, C, N_cur, power2, s);
+    const int n = local_rows(P) * P.G;
     closing_kernel<<<(n + 255) / 256, 256, 0, s>>>(P, C, c->d_sum, N_cur, c->d_scalars, dt, c->closure, c->closure_w_sum * P.hh,
                                                    c->d_w_conv, c->d_k_int, deriv_out, C_next);
     c->launches += 1;
@@ -282,9 +286,9 @@ int ldm_set_closure(ldm_handle h, int closure)
         return fail(LDM_ERR_ARGUMENT, "unknown closure");
     if (closure == LDM_CLOSURE_POWER1) { h->closure = closure; return LDM_OK; }
     if (h->species != 1) return fail(LDM_ERR_UNSUPPORTED, "the closures over the w quadrature are built for one species");
-    if (h->dev.world != 1) return fail(LDM_ERR_UNSUPPORTED, "the closures over the w quadrature run on one rank (ldm_shard_configure(h, 0, 1) to go back)");
     if (h->dev.extrapolation != LDM_EXTRAPOLATION_SQUARED_N)
         return fail(LDM_ERR_UNSUPPORTED, "the closures over the w quadrature are built for SquaredN extrapolation");
+    if (h->peer_connected) return fail(LDM_ERR_UNSUPPORTED, "the fused exchange (ldm_shard_peer_*) carries the reference's closure only: use ldm_shard_step");
     const int rc = guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
         ensure_closure_tables(h);
@@ -310,7 +314,7 @@ int ldm_closure_integrals(ldm_handle h, const double* state, double* w_conv_C, d
         h->cur = 0;
         LDM_CUDA(cudaMemcpyAsync(h->d_N, state, sizeof(double), cudaMemcpyHostToDevice, s));
         LDM_CUDA(cudaMemcpyAsync(h->d_C[0], state + 1, P * sizeof(double), cudaMemcpyHostToDevice, s));
-        closure_integrals_on_device(h, h->d_C[0], h->d_N, w_conv_C != nullptr, s);
+        closure_integrals_on_device(h, h->dev, h->d_C[0], h->d_N, w_conv_C != nullptr, s);
         if (w_conv_C) LDM_CUDA(cudaMemcpyAsync(w_conv_C, h->d_w_conv, P * sizeof(double), cudaMemcpyDeviceToHost, s));
         if (K) LDM_CUDA(cudaMemcpyAsync(K, h->d_k_int, P * sizeof(double), cudaMemcpyDeviceToHost, s));
         LDM_CUDA(cudaStreamSynchronize(s));

@@ -245,8 +245,6 @@ int ldm_shard_configure(ldm_handle h, int rank, int world)
     if (!h || world < 1 || rank < 0 || rank >= world) return fail(LDM_ERR_ARGUMENT, "bad rank/world");
     if (h->species != 1) return fail(LDM_ERR_UNSUPPORTED, "not built for several species (ldm.h: ldm_problem_generate_multi)");
     if (world > h->dev.G) return fail(LDM_ERR_ARGUMENT, "more ranks than moment-grid rows");
-    if (world > 1 && h->closure != LDM_CLOSURE_POWER1)
-        return fail(LDM_ERR_UNSUPPORTED, "the closures over the w quadrature run on one rank (ldm_set_closure)");
     h->dev.world = world;
     h->dev.rank = rank;
     h->dev.rows_per_rank = (h->dev.G + world - 1) / world;
@@ -297,6 +295,7 @@ int ldm_shard_peer_alloc(ldm_handle h, unsigned char* handles)
     if (!h || !handles) return fail(LDM_ERR_ARGUMENT, "NULL argument");
     if (h->species != 1) return fail(LDM_ERR_UNSUPPORTED, "not built for several species (ldm.h: ldm_problem_generate_multi)");
     if (h->dev.world > ldm::kMaxPeers) return fail(LDM_ERR_ARGUMENT, "at most 8 ranks");
+    if (h->closure != LDM_CLOSURE_POWER1) return fail(LDM_ERR_UNSUPPORTED, "the fused exchange carries the reference's closure only: use ldm_shard_step (ldm_set_closure)");
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
         peer_buffers_alloc(h);
@@ -343,6 +342,7 @@ int ldm_shard_peer_connect_local(int world, const ldm_handle* handles)
     for (int r = 0; r < world; r++) {
         if (!handles[r]) return fail(LDM_ERR_ARGUMENT, "NULL handle");
         if (handles[r]->species != 1) return fail(LDM_ERR_UNSUPPORTED, "not built for several species (ldm.h: ldm_problem_generate_multi)");
+        if (handles[r]->closure != LDM_CLOSURE_POWER1) return fail(LDM_ERR_UNSUPPORTED, "the fused exchange carries the reference's closure only: use ldm_shard_step (ldm_set_closure)");
         if (handles[r]->dev.world != world || handles[r]->dev.rank != r || handles[r]->dev.G != handles[0]->dev.G)
             return fail(LDM_ERR_ARGUMENT, "handles[r] must be configured as rank r of `world` on the same grid (ldm_shard_configure)");
     }
@@ -432,6 +432,7 @@ int ldm_shard_peer_advance(ldm_handle h, int n_steps, double dt, void* cuda_stre
     if (!h->peer_connected) return fail(LDM_ERR_ARGUMENT, "peers are not connected");
     if (h->algo == LDM_ALGO_DIRECT) return fail(LDM_ERR_UNSUPPORTED, "the fused exchange rides on the factored path");
     if (h->dev.extrapolation == LDM_EXTRAPOLATION_EXPONENTIAL) return fail(LDM_ERR_UNSUPPORTED, "Exponential extrapolation: use ldm_shard_step");
+    if (h->closure != LDM_CLOSURE_POWER1) return fail(LDM_ERR_UNSUPPORTED, "a closure over the w quadrature: use ldm_shard_step");
     return guarded([&] {
         LDM_CUDA(cudaSetDevice(h->device));
         cudaStream_t s = static_cast<cudaStream_t>(cuda_stream);

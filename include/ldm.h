@@ -121,8 +121,10 @@ LDM_API int  ldm_set_extrapolation(ldm_handle h, int type);
  * (MakeIntegralWithPairDensity, S:297-316, extent MaxNumForW, bilinear C, N^2 beyond the cutoff).  K(xi) is a
  * convolution with the time-varying table w(xi') C(xi'), which is not separable: it is evaluated sample by sample
  * (G*G*(mW-1)^2 gathers per right-hand side), whatever ldm_set_algorithm says about the m*C integral.  One species,
- * SquaredN extrapolation, one rank; such a handle steps with one launch per kernel and step (no persistent kernel) in
- * ldm_rhs, ldm_solve, ldm_solve_rk4, ldm_advance and ldm_solve_batch.  At C == N^2 all three closures give the
+ * SquaredN extrapolation; such a handle steps with one launch per kernel and step (no persistent kernel) in ldm_rhs,
+ * ldm_solve, ldm_solve_rk4, ldm_advance, ldm_solve_batch and -- xi-sharded: the rows of both integrals are independent
+ * given C, as for m*C -- ldm_shard_step (the caller all-gathers); the fused exchange (ldm_shard_peer_*) carries the
+ * reference's closure only.  At C == N^2 all three closures give the
  * reference's right-hand side; away from it there is no reference to compare with (oracle: ldm_oracle_closure.c). */
 #define LDM_CLOSURE_POWER1            1
 #define LDM_CLOSURE_POWER2_SYMMETRIC  2

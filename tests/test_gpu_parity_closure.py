@@ -2,6 +2,7 @@
 against the CPU oracle of the extension (oracle/ldm_oracle_closure.c) -- and, where the reference has an answer (the uniform
 state, power-1), against the reference's own fixtures.  Tolerances as in test_gpu_parity.py: 1e-13 on an integral, 1e-12 of
 the sum of the term magnitudes on a right-hand side, 1e-10 on every component of a trajectory."""
+import ctypes as C
 import os
 
 import numpy as np
@@ -144,7 +145,9 @@ def test_what_the_closures_are_not_built_for_is_refused(ldm):
     eq.set_closure(ldm.CLOSURE_POWER3)
     with pytest.raises(ldm.LdmError, match="SquaredN"):
         eq.set_extrapolation(ldm.Zero)
-    assert ldm.library().ldm_shard_configure(eq._h, 0, 2) == -3          # LDM_ERR_UNSUPPORTED: one rank only
+    assert ldm.library().ldm_shard_configure(eq._h, 0, 2) == 0           # xi-sharding: ldm_shard_step carries the closures ...
+    assert ldm.library().ldm_shard_peer_connect_local(1, (C.c_void_p * 1)(eq._h)) == -3      # ... the fused exchange does not
+    assert ldm.library().ldm_shard_configure(eq._h, 0, 1) == 0
     eq.set_closure(ldm.CLOSURE_POWER1)
     eq.set_extrapolation(ldm.Zero)
     with pytest.raises(ldm.LdmError, match="SquaredN"):
@@ -176,3 +179,39 @@ def test_every_variant_of_the_sums_kernel_adds_the_same_numbers(ldm, name):
     for other in results[1:]:
         for a, b in zip(results[0], other):
             assert np.array_equal(a, b)
+
+
+@pytest.mark.parametrize("closure", [2, 3])
+@pytest.mark.parametrize("world", [2, 3, 5])
+def test_sharded_step_under_the_closures_emulated_on_one_device(ldm, world, closure):
+    """xi-sharding of the closure integrals, all ranks emulated on one GPU as in test_gpu_parity.py: each rank
+    computes (w*C), K and the update for ITS rows from the gathered replica; the 'all-gather' is a concatenation.  The rows
+    are independent given C, so the result must equal the unsharded run bit for bit."""
+    import torch
+    g = golden("exp_14_4_b")
+    props, o = problems_from(g, "exp_14_4_b", ldm)
+    G = props.G
+    ranks = [ldm.ShardedEquation(props, r, world) for r in range(world)]
+    for r in ranks:
+        r.eq.set_closure(closure)
+    rpr = ranks[0].rows_per_rank
+    state = bumped_state(o)
+    bufs = [torch.from_numpy(ranks[0].to_gathered(state[1:])).cuda(), torch.zeros(world * rpr, G, dtype=torch.float64, device="cuda")]
+    for r in ranks:
+        r.set_N(state[0])
+    stream = torch.cuda.current_stream().cuda_stream
+    steps = 5
+    for k in range(steps):
+        src, dst = bufs[k % 2], bufs[(k + 1) % 2]
+        for r in ranks:
+            r.step(src.data_ptr(), dst[r.rank * rpr:(r.rank + 1) * rpr].data_ptr(), 0.1, stream)
+    torch.cuda.synchronize()
+    single = ldm.Equation(props)
+    single.set_closure(closure)
+    single.upload(state)
+    single.advance(steps, 0.1)
+    want = single.download()
+    got_C = ranks[0].from_gathered(bufs[steps % 2].cpu().numpy())
+    assert np.array_equal(got_C.ravel(), want[1:])
+    for r in ranks:
+        assert r.get_N() == want[0]
