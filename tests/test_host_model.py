@@ -180,3 +180,24 @@ def test_tuning_keys(ldm):
     ldm.tuning_set("reset")
     with pytest.raises(ldm.LdmError):
         ldm.tuning_set("no such key", 1)
+
+
+def test_bench_accepts_the_committed_counters():
+    """bench.py's roofline block reads profiles/r02_counters.json only while the sources of the profiled kernels are the
+    captured ones (sha256 over ldm_persist.cu and the headers it includes): an edit to any of them without a new capture
+    must show up here, not as a silent `counters_refused` in the round's bench line"""
+    import sys
+    sys.path.insert(0, ROOT)
+    import bench
+    for workload, kernel in (("g128", "persistent_scan_kernel"), ("g512", "persistent_chunks_kernel")):
+        entry, refused = bench.measured_counters(workload, kernel)
+        assert refused is None and entry["source_sha"] == bench.source_sha(), refused
+        assert entry["lsu_wavefronts_per_step"] > 0 and entry["dram_bytes_per_step"] > 0
+    csrc = os.path.join(ROOT, "euler-_solver_-openmp-_b200", "csrc")
+    text = open(os.path.join(csrc, "ldm_persist.cu")).read()
+    for name in bench.PROFILED_SOURCES:                          # the list IS that translation unit: nothing it includes is missing
+        assert os.path.exists(os.path.join(csrc, name))
+    includes = {line.split('"')[1] for name in bench.PROFILED_SOURCES for line in open(os.path.join(csrc, name))
+                if line.startswith('#include "') and not line.split('"')[1].startswith("..")}
+    assert includes <= set(bench.PROFILED_SOURCES), includes
+    assert "persistent_scan_kernel" in text and "persistent_chunks_kernel" in text
